@@ -1,0 +1,133 @@
+/* laps_b200 — C ABI of the B200-native LAPS hot path (pseudo-spectral RHS + RK3 step).
+ *
+ * The reference (chenshihelio/LAPS) has no FFI layer: its Fortran driver calls FFTW through
+ * `include 'fftw3.f03'` (src_compressible/fftw.f90:8) and MPI through `include 'mpif.h'`
+ * (parallel.f90:3).  This header is the boundary a LAPS-style driver binds through ISO_C_BINDING
+ * in place of those calls; every entry point names the reference call site it replaces
+ * (file:line relative to src_compressible/).  INTEGRATION.md shows the Fortran interface module.
+ *
+ * Conventions: all functions return 0 on success, non-zero on failure (message via
+ * laps_last_error); no exceptions cross the boundary; one host thread per handle; every device
+ * allocation belongs to the library, every host buffer to the caller.  Host arrays use the
+ * reference layout uu(ix,iy,iz,ivar): x fastest, then local y, local z, variable slowest.
+ */
+#ifndef LAPS_B200_H
+#define LAPS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LAPS_ABI_VERSION 1
+#define LAPS_MAX_RANKS 8
+
+typedef struct laps_solver* laps_handle;
+
+/* Flat mirror of the namelists read in mhd.f90:30-53 that the hot path depends on. */
+typedef struct laps_params {
+  int32_t abi_version;           /* must be LAPS_ABI_VERSION */
+  int32_t nx, ny, nz;            /* &grid */
+  double Lx, Ly, Lz;
+  double adiabatic_index;        /* &phys */
+  int32_t if_resis, if_resis_exp;
+  double resistivity;
+  int32_t if_visc, if_visc_exp;
+  double viscosity;
+  int32_t if_conserve_background; /* &numerical */
+  double cfl;
+  int32_t dealias_option;        /* 1: spherical 1/3 truncation, 2: compact filter, 0: none */
+  double afx, afy, afz;
+  int32_t if_AEB, if_corotating; /* &AEB */
+  double radius0, Ur0, corotating_angle;
+  int32_t if_hall;               /* &Hall */
+  double ion_inertial_length;
+  int32_t rank, nranks;          /* slab decomposition = ndim_parallel=1 (parallel.f90:56-58) */
+  int32_t device;                /* CUDA device ordinal for this rank */
+} laps_params;
+
+/* Local extents as decompose_1d (parallel.f90:326-349) assigns them in slab mode. */
+typedef struct laps_extents {
+  int32_t nx, ny, nz, nxh;       /* nxh = nx/2+1 */
+  int32_t z_offset, z_size;      /* real space: z in Zj(rank)   (zj_offset/zj_size) */
+  int32_t y_offset, y_size;      /* Fourier space: ky in Yj(rank) (yj_offset/yj_size) */
+} laps_extents;
+
+/* parallel_start + fftw_initialize + grid_initialize + arrays_initialize + AEB_initialize +
+ * dealias_initialize (mhd.f90:58-99). */
+int laps_create(const laps_params* params, laps_handle* out);
+/* parallel_end + fftw_finalize (mhd.f90:291-293). */
+int laps_destroy(laps_handle h);
+const char* laps_last_error(laps_handle h); /* h may be NULL: error of the last failed laps_create */
+int laps_get_extents(laps_handle h, laps_extents* out);
+
+/* Multi-rank wiring (replaces the communicators of parallel.f90:77-95).  Each rank exports an
+ * opaque blob describing its exchange buffers (CUDA IPC handles), the driver all-gathers the
+ * blobs (MPI_Allgather in a Fortran driver) and hands the concatenation back.  laps_barrier_fn
+ * is called by the library wherever all ranks must have finished a pass (an MPI_Barrier thunk).
+ * Not needed when nranks == 1. */
+#define LAPS_PEER_BLOB_BYTES 256
+int laps_export_peer_blob(laps_handle h, void* blob /* LAPS_PEER_BLOB_BYTES */);
+int laps_import_peer_blobs(laps_handle h, const void* blobs /* nranks * LAPS_PEER_BLOB_BYTES */);
+typedef void (*laps_barrier_fn)(void* user);
+int laps_set_barrier(laps_handle h, laps_barrier_fn fn, void* user);
+/* Single-process multi-GPU: wire the handles of all ranks created in this process to each other. */
+int laps_connect_local(laps_handle* handles, int32_t nranks);
+
+/* initial_calc_conserve_variable + transform_uu_real_to_fourier (mhd.f90:121-122):
+ * uu_local = primitive rho,ux,uy,uz,bx,by,bz,p as background/perturbation_initialize or
+ * read_restart leave them (mhdinit.f90:183-1036, restart.f90:17-63). */
+int laps_set_primitive(laps_handle h, const double* uu_local);
+/* evolve_radius(time) (mhd.f90:102,248; AEBmod.f90:56-73): radius, tau_exp, k_square. */
+int laps_set_time(laps_handle h, double time);
+/* vardt (mhd.f90:136,285,328-429): CFL limit, global min, 2 % hysteresis on *dt_inout, rkt_init. */
+int laps_vardt(laps_handle h, double* dt_inout);
+/* rkt_init(dt) alone (rktmod.f90:15-32) — fixed-dt runs and tests. */
+int laps_rkt_init(laps_handle h, double dt);
+/* evolve (mhd.f90:245,298-326): three RK stages with the coefficients armed by vardt/rkt_init.
+ * Asynchronous: returns after enqueueing (multi-rank: after the last inter-rank barrier). */
+int laps_evolve(laps_handle h);
+/* One iteration of the Principal loop body, mhd.f90:245-248,285:
+ * evolve; time += dt; evolve_radius(time); vardt.  Updates *time_inout and *dt_inout. */
+int laps_step(laps_handle h, double* time_inout, double* dt_inout);
+int laps_sync(laps_handle h);
+
+/* calc_max_divB (mhd.f90:157,522-570). */
+int laps_max_divb(laps_handle h, double* out);
+/* calc_rms (mhdrms.f90:53-126): out = uu_ave(8), uu_rms(8), rho_u2(3); the driver keeps the
+ * rms.dat formatting of mhdrms.f90:25,48. */
+int laps_rms(laps_handle h, double out[19]);
+/* Not in the reference (it has no energy / cross-helicity diagnostic): mean of uu(8), mean of
+ * u.B, max |k.B^|. */
+int laps_invariants(laps_handle h, double out[3]);
+
+/* Host copy of the state for output_uu / restart (mhdoutput.f90:95-123): conserved uu (8 fields)
+ * and uu_prim (ux,uy,uz,p); either pointer may be NULL. */
+int laps_get_state(laps_handle h, double* uu_local, double* uu_prim_local);
+/* Spectral state uu_fourier as complex128 pairs in the library's internal layout
+ * [ivar][kx][ky_local][kz] (kz fastest) — for parity tests. */
+int laps_get_spectral(laps_handle h, double* uu_fourier_local);
+
+/* Unit-level transforms mirroring fftw.f90:42-71 / 73-103 (+136-222) for parity tests:
+ * real [nfields][z_local][y][x]  <->  spectral [nfields][kx][ky_local][kz] (complex128 pairs). */
+int laps_fft_forward(laps_handle h, const double* real_fields, int32_t nfields, double* spec_out);
+int laps_fft_inverse(laps_handle h, const double* spec_in, int32_t nfields, double* real_out);
+/* Index map of transpose_yz (parallel.f90:185-210,273-297) as this library realises it: for every
+ * element of this rank's post-y-pass block (order: kx, ky, z_local with z_local fastest) the
+ * destination rank and the destination linear offset in that rank's [kx][ky_local][z] block.
+ * out = int64 pairs (rank, offset), nxh*ny*z_size of them. */
+int laps_transpose_yz_indexmap(laps_handle h, int64_t* out);
+
+/* Device-time of the last laps_evolve/laps_step in milliseconds (CUDA events on the compute
+ * stream), and the number of kernel launches it issued. */
+int laps_last_step_ms(laps_handle h, float* ms, int32_t* launches);
+/* Per-kernel device time of the last instrumented evolve: names and milliseconds of up to `cap`
+ * launches (laps_set_profiling(h,1) inserts events around every launch). */
+int laps_set_profiling(laps_handle h, int32_t on);
+int laps_get_profile(laps_handle h, char* names /* cap*32 */, float* ms, int32_t cap, int32_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAPS_B200_H */

@@ -1,0 +1,38 @@
+// Build-mode glue.  The product is built by nvcc for sm_100a.  The only other mode (LAPS_EMU) is
+// the test-only CPU emulation under tests/emu/, which compiles these same sources with g++ to
+// check index math in a container without a GPU; it is never shipped or loaded by the package.
+#pragma once
+
+#ifdef LAPS_EMU_BUILD
+#include "cuda_emu.h"
+#define LAPS_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::g_dyn_smem)
+#define LAPS_UNROLL
+#else
+#include <cuda_runtime.h>
+#define LAPS_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char name##_raw_[]; \
+  type* name = reinterpret_cast<type*>(name##_raw_)
+#define LAPS_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define LAPS_UNROLL _Pragma("unroll")
+#endif
+
+#include <cstdint>
+
+#define LAPS_HD __host__ __device__ __forceinline__
+#define LAPS_D __device__ __forceinline__
+
+namespace laps {
+
+typedef double2 cplx;
+
+LAPS_HD cplx mk(double a, double b) { return make_double2(a, b); }
+LAPS_HD cplx cadd(cplx a, cplx b) { return mk(a.x + b.x, a.y + b.y); }
+LAPS_HD cplx csub(cplx a, cplx b) { return mk(a.x - b.x, a.y - b.y); }
+LAPS_HD cplx cmul(cplx a, cplx b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+LAPS_HD cplx csqr(cplx a) { return mk(a.x * a.x - a.y * a.y, 2.0 * a.x * a.y); }
+LAPS_HD cplx cconj(cplx a) { return mk(a.x, -a.y); }
+LAPS_HD cplx cscale(cplx a, double s) { return mk(a.x * s, a.y * s); }
+// multiply by i*s (s real): (x + i y) * (i s) = -s y + i s x
+LAPS_HD cplx cmul_i(cplx a, double s) { return mk(-s * a.y, s * a.x); }
+
+}  // namespace laps

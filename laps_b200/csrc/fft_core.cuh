@@ -1,0 +1,189 @@
+// In-shared-memory FP64 complex FFT building blocks for one "line" of N = 2^L points (16 <= N <= 4096).
+//
+// Replaces the per-line FFTW executions of the reference (fftw.f90:61,97,159,176,198,215 and
+// mhdrhs.f90:146,162,357): N/8 threads cooperate on a line, every thread holds 8 points in
+// registers per stage, stages are radix-8 (the last one radix 2/4/8), data is exchanged between
+// stages IN PLACE through a padded shared-memory line (one __syncthreads per exchange).
+//
+//   positions:  pos = sum_s d_s * w_s      (d_s = input digit n_s before stage s, output digit k_s after)
+//   input index n = pos at the start;  output index k = sum_s k_s * v_s
+//   after stage s (not last) output k_s is multiplied by W_N^(v_s * j' * k_s), j' = pos mod w_s.
+//
+// The index math is mirrored and validated in tools/fft_model.py (tests/test_fft_model.py).
+#pragma once
+#include "compat.h"
+
+namespace laps {
+
+constexpr int ilog2c(int n) { return n <= 1 ? 0 : 1 + ilog2c(n >> 1); }
+
+template <int N>
+struct Geom {
+  static_assert(N >= 16 && N <= 4096 && (N & (N - 1)) == 0, "line length must be a power of two in [16,4096]");
+  static constexpr int LOG2 = ilog2c(N);
+  static constexpr int NSTAGE = (LOG2 + 2) / 3;
+  static constexpr int RLAST = 1 << (LOG2 - 3 * (NSTAGE - 1));
+  static constexpr int NT = N / 8;  // threads per line
+  LAPS_HD static constexpr int w(int s) { return s < NSTAGE - 1 ? (N >> (3 * (s + 1))) : 1; }
+  LAPS_HD static constexpr int v(int s) { return 1 << (3 * s); }
+  LAPS_HD static constexpr int pad(int i) { return i + (i >> 3) + (i >> 6) + (i >> 9); }
+  // line pitch (in elements) congruent to `m` modulo 8: m=1 makes accesses that walk 8 lines at a
+  // fixed position conflict free, m=2 serves 4 lines x 2 adjacent positions.
+  LAPS_HD static constexpr int pitch(int m) {
+    int p = pad(N - 1) + 1;
+    while ((p & 7) != m) ++p;
+    return p;
+  }
+};
+
+// ------------------------------------------------------------------ butterflies (natural order out)
+template <int DIR>
+LAPS_D cplx mul_w4(cplx a) {  // a * W4,  W4 = -i (forward, DIR<0) or +i (inverse)
+  return DIR < 0 ? mk(a.y, -a.x) : mk(-a.y, a.x);
+}
+
+template <int DIR>
+LAPS_D void bfly8(cplx (&r)[8]) {
+  const double h = 0.70710678118654752440;
+  cplx a0 = cadd(r[0], r[4]), a4 = csub(r[0], r[4]);
+  cplx a1 = cadd(r[1], r[5]), a5 = csub(r[1], r[5]);
+  cplx a2 = cadd(r[2], r[6]), a6 = csub(r[2], r[6]);
+  cplx a3 = cadd(r[3], r[7]), a7 = csub(r[3], r[7]);
+  // odd branch twiddles W8^1, W8^2, W8^3
+  if (DIR < 0) {
+    a5 = mk((a5.x + a5.y) * h, (a5.y - a5.x) * h);
+    a7 = mk((a7.y - a7.x) * h, -(a7.x + a7.y) * h);
+  } else {
+    a5 = mk((a5.x - a5.y) * h, (a5.x + a5.y) * h);
+    a7 = mk(-(a7.x + a7.y) * h, (a7.x - a7.y) * h);
+  }
+  a6 = mul_w4<DIR>(a6);
+  cplx b0 = cadd(a0, a2), b2 = csub(a0, a2);
+  cplx b1 = cadd(a1, a3), b3 = mul_w4<DIR>(csub(a1, a3));
+  cplx c0 = cadd(a4, a6), c2 = csub(a4, a6);
+  cplx c1 = cadd(a5, a7), c3 = mul_w4<DIR>(csub(a5, a7));
+  r[0] = cadd(b0, b1); r[4] = csub(b0, b1);
+  r[2] = cadd(b2, b3); r[6] = csub(b2, b3);
+  r[1] = cadd(c0, c1); r[5] = csub(c0, c1);
+  r[3] = cadd(c2, c3); r[7] = csub(c2, c3);
+}
+
+template <int DIR>
+LAPS_D void bfly4(cplx& r0, cplx& r1, cplx& r2, cplx& r3) {
+  cplx b0 = cadd(r0, r2), b2 = csub(r0, r2);
+  cplx b1 = cadd(r1, r3), b3 = mul_w4<DIR>(csub(r1, r3));
+  r0 = cadd(b0, b1); r2 = csub(b0, b1);
+  r1 = cadd(b2, b3); r3 = csub(b2, b3);
+}
+
+LAPS_D void bfly2(cplx& r0, cplx& r1) {
+  cplx a = cadd(r0, r1), b = csub(r0, r1);
+  r0 = a; r1 = b;
+}
+
+// r[e] *= w^e, e = 1..7.  Powers are built from the base twiddle by multiplication
+// (3 squarings + 3 products), which keeps shared-memory/L1 traffic for twiddles negligible.
+LAPS_D void twiddle8(cplx (&r)[8], cplx w) {
+  cplx w2 = csqr(w);
+  cplx w3 = cmul(w2, w);
+  cplx w4 = csqr(w2);
+  r[1] = cmul(r[1], w);
+  r[2] = cmul(r[2], w2);
+  r[3] = cmul(r[3], w3);
+  r[4] = cmul(r[4], w4);
+  r[5] = cmul(r[5], cmul(w4, w));
+  r[6] = cmul(r[6], csqr(w3));
+  r[7] = cmul(r[7], cmul(w4, w3));
+}
+
+// ------------------------------------------------------------------ staged FFT of one line
+// `tw` points to the forward table tw[m] = exp(-2 pi i m / N), m < N (global memory, L1 resident).
+template <int N, int DIR>
+struct Fft {
+  typedef Geom<N> G;
+
+  LAPS_D static cplx twid(const cplx* __restrict__ tw, int m) {
+    cplx w = __ldg(tw + m);
+    if (DIR > 0) w.y = -w.y;
+    return w;
+  }
+
+  // Stage 0.  r[e] = x[u + e*N/8] on entry.  Leaves the twiddled outputs in the smem line.
+  LAPS_D static void first(cplx (&r)[8], int u, cplx* __restrict__ line, const cplx* __restrict__ tw) {
+    bfly8<DIR>(r);
+    twiddle8(r, twid(tw, u));  // v_0 = 1, j' = u
+    LAPS_UNROLL
+    for (int e = 0; e < 8; ++e) line[G::pad(u + e * G::w(0))] = r[e];
+  }
+
+  // Middle stage S (1 <= S < NSTAGE-1), in place.
+  template <int S>
+  LAPS_D static void middle(int u, cplx* __restrict__ line, const cplx* __restrict__ tw) {
+    constexpr int ws = G::w(S);
+    const int jp = u & (ws - 1);
+    const int base = (u / ws) * (8 * ws) + jp;
+    cplx r[8];
+    LAPS_UNROLL
+    for (int e = 0; e < 8; ++e) r[e] = line[G::pad(base + e * ws)];
+    bfly8<DIR>(r);
+    twiddle8(r, twid(tw, G::v(S) * jp));
+    LAPS_UNROLL
+    for (int e = 0; e < 8; ++e) line[G::pad(base + e * ws)] = r[e];
+  }
+
+  // Base position (8 consecutive slots base..base+7) read by thread u in the last stage.
+  LAPS_D static int last_base(int u) {
+    constexpr int s = G::NSTAGE - 1;
+    if (G::RLAST == 8) {
+      int base = 0;
+      LAPS_UNROLL
+      for (int t = 0; t < s; ++t) base += ((u >> (3 * t)) & 7) * G::w(t);
+      return base;
+    } else {
+      constexpr int vsm1 = G::v(s - 1);
+      const int qlo = u & (vsm1 - 1);
+      int o = u / vsm1;
+      LAPS_UNROLL
+      for (int t = 0; t < s - 1; ++t) o += ((qlo >> (3 * t)) & 7) * (G::w(t) / 8);
+      return 8 * o;
+    }
+  }
+
+  // Output index k held in register slot e of thread u after the last stage.
+  LAPS_D static int kout(int u, int e) {
+    if (G::RLAST == 8) return u + e * (N / 8);
+    constexpr int s = G::NSTAGE - 1;
+    constexpr int R = G::RLAST;
+    constexpr int vsm1 = G::v(s - 1);
+    const int qlo = u & (vsm1 - 1);
+    const int h = u / vsm1;
+    const int i = e / R, ee = e % R;
+    return qlo + ((8 / R) * h + i) * vsm1 + ee * (N / R);
+  }
+
+  // Last stage: reads the line, leaves X[kout(u,e)] in r[e].
+  LAPS_D static void last(cplx (&r)[8], int u, const cplx* __restrict__ line) {
+    const int base = last_base(u);
+    LAPS_UNROLL
+    for (int e = 0; e < 8; ++e) r[e] = line[G::pad(base + e)];
+    if (G::RLAST == 8) {
+      bfly8<DIR>(r);
+    } else if (G::RLAST == 4) {
+      bfly4<DIR>(r[0], r[1], r[2], r[3]);
+      bfly4<DIR>(r[4], r[5], r[6], r[7]);
+    } else {
+      bfly2(r[0], r[1]); bfly2(r[2], r[3]); bfly2(r[4], r[5]); bfly2(r[6], r[7]);
+    }
+  }
+
+  // All stages after `first` up to and including `last`; every thread of the CTA must call it
+  // (it contains the block barriers).  `line` is this thread's line.
+  LAPS_D static void finish(cplx (&r)[8], int u, cplx* __restrict__ line, const cplx* __restrict__ tw) {
+    __syncthreads();
+    if constexpr (G::NSTAGE >= 3) { middle<1>(u, line, tw); __syncthreads(); }
+    if constexpr (G::NSTAGE >= 4) { middle<2>(u, line, tw); __syncthreads(); }
+    last(r, u, line);
+  }
+};
+
+}  // namespace laps

@@ -1,0 +1,219 @@
+// Batched x- and y-passes of the slab-decomposed 3D FFT (forward: fftw.f90:42-71,136-164;
+// inverse: fftw.f90:73-103,203-222 of the reference), one launch per pass over ALL fields.
+//
+// Work-array layouts (complex128 unless noted; the right-most index is contiguous).  They rotate
+// so that every pass reads or writes whole contiguous lines on one side and TL*16-byte chunks on
+// the other, and so that the z-pass (spectral_z.cuh) sees contiguous z-lines:
+//   real   R [f][zl][y][x]      zl = local z of this rank's slab (z in Zj(rank), parallel.f90:102)
+//   W1     [f][kx][zl][y]       after the x-pass      (kx = 0..nx/2)
+//   W2     [f][kx][kyl][z]      after the y-pass, ON THE RANK THAT OWNS ky (kyl local, z global):
+//                               the y-pass stores straight into the owner's buffer, which is the
+//                               reference's transpose_yz (parallel.f90:273-297) fused into the pass
+//   V1     [g][kx][ky][zl]      inverse z-pass output, on the rank that owns z (transpose_zy fused)
+//   V2     [g][kx][zl][y]       after the inverse y-pass
+// The reference's transpose_xy/yx are identity in slab mode (iproc=1, parallel.f90:56-58).
+#pragma once
+#include "fft_core.cuh"
+
+namespace laps {
+
+constexpr int kMaxPeers = 8;
+
+// Where the slab-exchange side of a pass lives: one base pointer per peer plus the
+// decompose_1d tables (parallel.f90:326-349) of the exchanged axis.
+struct PeerTable {
+  cplx* base[kMaxPeers];
+  int off[kMaxPeers];   // first global index owned by peer p
+  int len[kMaxPeers];   // number owned
+  int nparts;
+  int quot;             // n / nparts (owner = min(i / quot, nparts-1))
+  LAPS_HD int owner(int i) const { int p = i / quot; return p < nparts - 1 ? p : nparts - 1; }
+};
+
+// Shared-memory tile of TL lines.  A quarter warp (8 lanes of a 128-bit access) covers
+// min(TL,8) lines x 8/min(TL,8) adjacent positions when lines are walked side by side, so the
+// line pitch is chosen congruent to 8/min(TL,8) modulo 8 to keep those accesses conflict free.
+template <int N, int TL>
+struct Tile {
+  typedef Geom<N> G;
+  static constexpr int PITCH = G::pitch(TL >= 8 ? 1 : (TL == 4 ? 2 : (TL == 2 ? 4 : 0)));
+  static constexpr int NTHREADS = TL * G::NT;
+  static constexpr size_t SMEM = (size_t)TL * PITCH * sizeof(cplx);
+};
+
+// ---------------------------------------------------------------------------------------------
+// forward x: real lines -> half spectra, two real lines per complex transform
+// (replaces the r2c loops fftw.f90:58-64 / mhdrhs.f90:143-149, including the "/nx").
+// grid.x = nzl * (ny / (2*TL)), grid.y = number of fields
+template <int N, int TL>
+__global__ void __launch_bounds__(Tile<N, TL>::NTHREADS)
+k_fwd_x(const double* __restrict__ in, size_t in_fstride, cplx* __restrict__ W1,
+        int nzl, int ny, const cplx* __restrict__ tw, double scale) {
+  typedef Geom<N> G;
+  typedef Fft<N, -1> F;
+  typedef Tile<N, TL> T;
+  LAPS_DYN_SMEM(cplx, sm);
+  const int tid = threadIdx.x;
+  const int l = tid / G::NT, u = tid % G::NT;
+  const int ytiles = ny / (2 * TL);
+  const int zl = blockIdx.x / ytiles;
+  const int y0 = (blockIdx.x % ytiles) * 2 * TL;
+  const int f = blockIdx.y;
+  const int nxh = N / 2 + 1;
+
+  const double* ra = in + (size_t)f * in_fstride + ((size_t)zl * ny + y0 + 2 * l) * N;
+  const double* rb = ra + N;
+  cplx r[8];
+  LAPS_UNROLL
+  for (int e = 0; e < 8; ++e) r[e] = mk(ra[u + e * G::NT], rb[u + e * G::NT]);
+  cplx* line = sm + l * T::PITCH;
+  F::first(r, u, line, tw);
+  F::finish(r, u, line, tw);
+  __syncthreads();  // everyone has consumed its last-stage slots
+  LAPS_UNROLL
+  for (int e = 0; e < 8; ++e) line[G::pad(F::kout(u, e))] = r[e];
+  __syncthreads();
+  // split Z = A + iB into the two half spectra; TL line-pairs side by side give 2*TL*16-byte chunks
+  const double hs = 0.5 * scale;
+  for (int it = tid; it < nxh * TL; it += T::NTHREADS) {
+    const int lp = it % TL, k = it / TL;
+    const cplx zk = sm[lp * T::PITCH + G::pad(k)];
+    const cplx zn = sm[lp * T::PITCH + G::pad((N - k) & (N - 1))];
+    cplx a = mk((zk.x + zn.x) * hs, (zk.y - zn.y) * hs);
+    cplx b = mk((zk.y + zn.y) * hs, (zn.x - zk.x) * hs);
+    cplx* dst = W1 + (((size_t)f * nxh + k) * nzl + zl) * ny + y0 + 2 * lp;
+    dst[0] = a;
+    dst[1] = b;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward y: contiguous y-lines of W1 -> W2 on the owner of ky, z fastest
+// (fftw.f90:156-162 incl. "/ny", fused with transpose_yz parallel.f90:273-297).
+// grid.x = ceil(nzl/TL) * nxh, grid.y = fields
+template <int N, int TL>
+__global__ void __launch_bounds__(Tile<N, TL>::NTHREADS)
+k_fwd_y(const cplx* __restrict__ W1, PeerTable W2, int nzl, int nz, int zoff,
+        const cplx* __restrict__ tw, double scale) {
+  typedef Geom<N> G;
+  typedef Fft<N, -1> F;
+  typedef Tile<N, TL> T;
+  LAPS_DYN_SMEM(cplx, sm);
+  const int tid = threadIdx.x;
+  const int ztiles = (nzl + TL - 1) / TL;
+  const int kx = blockIdx.x / ztiles;
+  const int z0 = (blockIdx.x % ztiles) * TL;
+  const int f = blockIdx.y;
+  const int nxh = gridDim.x / ztiles;
+  {
+    const int l = tid / G::NT, u = tid % G::NT;  // mapping A: coalesced along the line
+    cplx r[8];
+    if (z0 + l < nzl) {
+      const cplx* src = W1 + (((size_t)f * nxh + kx) * nzl + z0 + l) * N;
+      LAPS_UNROLL
+      for (int e = 0; e < 8; ++e) r[e] = src[u + e * G::NT];
+    } else {
+      LAPS_UNROLL
+      for (int e = 0; e < 8; ++e) r[e] = mk(0.0, 0.0);
+    }
+    F::first(r, u, sm + l * T::PITCH, tw);
+  }
+  const int l = tid % TL, u = tid / TL;  // mapping B: TL lines side by side
+  cplx r[8];
+  F::finish(r, u, sm + l * T::PITCH, tw);
+  if (z0 + l < nzl) {
+    LAPS_UNROLL
+    for (int e = 0; e < 8; ++e) {
+      const int ky = F::kout(u, e);
+      const int p = W2.owner(ky);
+      cplx* dst = W2.base[p] + (((size_t)f * nxh + kx) * W2.len[p] + (ky - W2.off[p])) * nz + zoff + z0 + l;
+      *dst = cscale(r[e], scale);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// inverse y: V1 [g][kx][ky][zl] (z fastest) -> contiguous y-lines V2 [g][kx][zl][y]
+// (fftw.f90:212-218, unnormalised).  grid.x = ceil(nzl/TL) * nxh, grid.y = fields
+template <int N, int TL>
+__global__ void __launch_bounds__(Tile<N, TL>::NTHREADS)
+k_inv_y(const cplx* __restrict__ V1, cplx* __restrict__ V2, int nzl, const cplx* __restrict__ tw) {
+  typedef Geom<N> G;
+  typedef Fft<N, +1> F;
+  typedef Tile<N, TL> T;
+  LAPS_DYN_SMEM(cplx, sm);
+  const int tid = threadIdx.x;
+  const int ztiles = (nzl + TL - 1) / TL;
+  const int kx = blockIdx.x / ztiles;
+  const int z0 = (blockIdx.x % ztiles) * TL;
+  const int g = blockIdx.y;
+  const int nxh = gridDim.x / ztiles;
+  {
+    const int l = tid % TL, u = tid / TL;  // mapping B
+    cplx r[8];
+    if (z0 + l < nzl) {
+      const cplx* src = V1 + (((size_t)g * nxh + kx) * N) * nzl + z0 + l;
+      LAPS_UNROLL
+      for (int e = 0; e < 8; ++e) r[e] = src[(size_t)(u + e * G::NT) * nzl];
+    } else {
+      LAPS_UNROLL
+      for (int e = 0; e < 8; ++e) r[e] = mk(0.0, 0.0);
+    }
+    F::first(r, u, sm + l * T::PITCH, tw);
+  }
+  const int l = tid / G::NT, u = tid % G::NT;  // mapping A
+  cplx r[8];
+  F::finish(r, u, sm + l * T::PITCH, tw);
+  if (z0 + l < nzl) {
+    cplx* dst = V2 + (((size_t)g * nxh + kx) * nzl + z0 + l) * N;
+    LAPS_UNROLL
+    for (int e = 0; e < 8; ++e) dst[F::kout(u, e)] = r[e];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// inverse x: V2 [g][kx][zl][y] -> real lines, two per complex transform
+// (c2r loops fftw.f90:94-100 / mhdrhs.f90:354-360; like FFTW's c2r the imaginary parts of the
+// DC and Nyquist bins are ignored).  Destination pointer per field (uu(:,:,:,v) or J component).
+struct RealDst { double* ptr[16]; };
+
+template <int N, int TL>
+__global__ void __launch_bounds__(Tile<N, TL>::NTHREADS)
+k_inv_x(const cplx* __restrict__ V2, RealDst dst, int nzl, int ny, const cplx* __restrict__ tw) {
+  typedef Geom<N> G;
+  typedef Fft<N, +1> F;
+  typedef Tile<N, TL> T;
+  LAPS_DYN_SMEM(cplx, sm);
+  const int tid = threadIdx.x;
+  const int ytiles = ny / (2 * TL);
+  const int zl = blockIdx.x / ytiles;
+  const int y0 = (blockIdx.x % ytiles) * 2 * TL;
+  const int g = blockIdx.y;
+  const int nxh = N / 2 + 1;
+  for (int it = tid; it < nxh * TL; it += T::NTHREADS) {
+    const int lp = it % TL, k = it / TL;
+    const cplx* src = V2 + (((size_t)g * nxh + k) * nzl + zl) * ny + y0 + 2 * lp;
+    cplx a = src[0], b = src[1];
+    if (k == 0 || k == N / 2) { a.y = 0.0; b.y = 0.0; }
+    sm[lp * T::PITCH + G::pad(k)] = mk(a.x - b.y, a.y + b.x);
+    if (k != 0 && k != N / 2) sm[lp * T::PITCH + G::pad(N - k)] = mk(a.x + b.y, b.x - a.y);
+  }
+  __syncthreads();
+  const int l = tid / G::NT, u = tid % G::NT;
+  cplx* line = sm + l * T::PITCH;
+  cplx r[8];
+  LAPS_UNROLL
+  for (int e = 0; e < 8; ++e) r[e] = line[G::pad(u + e * G::NT)];
+  F::first(r, u, line, tw);
+  F::finish(r, u, line, tw);
+  double* oa = dst.ptr[g] + ((size_t)zl * ny + y0 + 2 * l) * N;
+  double* ob = oa + N;
+  LAPS_UNROLL
+  for (int e = 0; e < 8; ++e) {
+    const int n = F::kout(u, e);
+    oa[n] = r[e].x;
+    ob[n] = r[e].y;
+  }
+}
+
+}  // namespace laps

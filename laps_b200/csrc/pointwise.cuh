@@ -1,0 +1,255 @@
+// Real-space pointwise kernels and reductions (memory-bound, FP64):
+//   k_flux           calc_flux incl. Hall E and EBM energy source      (mhdrhs.f90:48-122)
+//   k_prim_to_cons   initial_calc_conserve_variable                    (mhdinit.f90:1038-1056)
+//   k_cons_to_prim   update_uu_prim_from_uu                            (mhdrhs.f90:282-294)
+//   k_cfl            per-point CFL limit + min reduction (vardt)       (mhd.f90:352-416)
+//   k_moments1/2     calc_rms sums                                     (mhdrms.f90:73-125)
+//   k_divb           calc_max_divB                                     (mhd.f90:541-568)
+// Primitive velocity/pressure are recomputed in registers from uu wherever they are needed, in
+// the reference's expression order, so the uu_prim array of the reference never exists on the GPU.
+#pragma once
+#include "compat.h"
+
+namespace laps {
+
+struct Prim { double ux, uy, uz, p; };
+
+// mhdrhs.f90:285-293
+LAPS_D Prim prim_of(double rho, double mx, double my, double mz, double bx, double by, double bz,
+                    double e, double gm1) {
+  Prim q;
+  q.ux = mx / rho;
+  q.uy = my / rho;
+  q.uz = mz / rho;
+  q.p = (e - 0.5 * (mx * q.ux + my * q.uy + mz * q.uz + bx * bx + by * by + bz * bz)) * gm1;
+  return q;
+}
+
+struct FluxParams {
+  const double* uu;     // [8][npts]
+  const double* J;      // [3][npts] (Hall) or null
+  double* F;            // [nf][npts]: 0-2 mass, 3-11 momentum tensor, 12-14 E, 15-17 energy, 18 EBM source
+  size_t npts;
+  int hall, aeb;
+  double gamma, di, tau;
+};
+
+__global__ void __launch_bounds__(256) k_flux(const FluxParams P) {
+  const size_t n = P.npts;
+  const double gm1 = P.gamma - 1.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double rho = P.uu[i], mx = P.uu[n + i], my = P.uu[2 * n + i], mz = P.uu[3 * n + i];
+    const double Bx = P.uu[4 * n + i], By = P.uu[5 * n + i], Bz = P.uu[6 * n + i], en = P.uu[7 * n + i];
+    const Prim q = prim_of(rho, mx, my, mz, Bx, By, Bz, en, gm1);
+    const double ux = q.ux, uy = q.uy, uz = q.uz, p = q.p;
+    const double ptot = p + 0.5 * (Bx * Bx + By * By + Bz * Bz);
+    const double udotb = ux * Bx + uy * By + uz * Bz;
+    double* F = P.F + i;
+    F[0] = mx; F[n] = my; F[2 * n] = mz;
+    F[3 * n] = mx * ux - Bx * Bx + ptot;
+    F[4 * n] = my * ux - By * Bx;
+    F[5 * n] = mz * ux - Bz * Bx;
+    F[6 * n] = mx * uy - Bx * By;
+    F[7 * n] = my * uy - By * By + ptot;
+    F[8 * n] = mz * uy - Bz * By;
+    F[9 * n] = mx * uz - Bx * Bz;
+    F[10 * n] = my * uz - By * Bz;
+    F[11 * n] = mz * uz - Bz * Bz + ptot;
+    double Ex = uz * By - uy * Bz;
+    double Ey = ux * Bz - uz * Bx;
+    double Ez = uy * Bx - ux * By;
+    if (P.hall) {
+      const double Jx = P.J[i], Jy = P.J[n + i], Jz = P.J[2 * n + i];
+      const double dr = P.di / rho;
+      Ex = Ex + dr * (Jy * Bz - Jz * By);
+      Ey = Ey + dr * (Jz * Bx - Jx * Bz);
+      Ez = Ez + dr * (Jx * By - Jy * Bx);
+    }
+    F[12 * n] = Ex; F[13 * n] = Ey; F[14 * n] = Ez;
+    const double h = en + ptot;
+    F[15 * n] = h * ux - udotb * Bx;
+    F[16 * n] = h * uy - udotb * By;
+    F[17 * n] = h * uz - udotb * Bz;
+    if (P.aeb) {
+      F[18 * n] = -2 * P.gamma / gm1 * p / P.tau - (2.0 * Bx * Bx + By * By + Bz * Bz) / P.tau -
+                  (mx * ux + 2 * my * uy + 2 * mz * uz) / P.tau;
+    }
+  }
+}
+
+// in place: [rho,ux,uy,uz,bx,by,bz,p] -> [rho,rho u,B,e]
+__global__ void __launch_bounds__(256) k_prim_to_cons(double* uu, size_t n, double gamma) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double rho = uu[i], ux = uu[n + i], uy = uu[2 * n + i], uz = uu[3 * n + i];
+    const double bx = uu[4 * n + i], by = uu[5 * n + i], bz = uu[6 * n + i], p = uu[7 * n + i];
+    uu[n + i] = rho * ux;
+    uu[2 * n + i] = rho * uy;
+    uu[3 * n + i] = rho * uz;
+    uu[7 * n + i] = p / (gamma - 1) + 0.5 * (rho * (ux * ux + uy * uy + uz * uz) + bx * bx + by * by + bz * bz);
+  }
+}
+
+// prim[4][n] = (ux,uy,uz,p) from conserved uu
+__global__ void __launch_bounds__(256) k_cons_to_prim(const double* uu, double* prim, size_t n, double gamma) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const Prim q = prim_of(uu[i], uu[n + i], uu[2 * n + i], uu[3 * n + i], uu[4 * n + i], uu[5 * n + i],
+                           uu[6 * n + i], uu[7 * n + i], gamma - 1.0);
+    prim[i] = q.ux; prim[n + i] = q.uy; prim[2 * n + i] = q.uz; prim[3 * n + i] = q.p;
+  }
+}
+
+// ------------------------------------------------------------------ block reductions
+template <class Op>
+LAPS_D double block_reduce(double v, Op op, double* scratch /* >= 32 doubles */) {
+  LAPS_UNROLL
+  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  double r = scratch[0];
+  for (int i = 1; i < nw; ++i) r = op(r, scratch[i]);
+  return r;
+}
+struct OpSum { LAPS_D double operator()(double a, double b) const { return a + b; } };
+struct OpMin { LAPS_D double operator()(double a, double b) const { return a < b ? a : b; } };
+struct OpMax { LAPS_D double operator()(double a, double b) const { return a > b ? a : b; } };
+
+struct CflParams {
+  const double* uu; size_t npts;
+  double gamma, di, dx, dy, dz, rr;  // rr = radius / radius0
+  int hall;
+  double* partial;  // [gridDim.x]
+};
+
+// mhd.f90:352-416.  partial[b] = min over the block's points of min(dtx,dty,dtz)
+__global__ void __launch_bounds__(256) k_cfl(const CflParams P) {
+  __shared__ double scratch[32];
+  const size_t n = P.npts;
+  const double s2 = sqrt(2.0);
+  const double dmin = fmin(fmin(P.dx, P.dy), P.dz);
+  double best = 1.0e300;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double rho = P.uu[i], mx = P.uu[n + i], my = P.uu[2 * n + i], mz = P.uu[3 * n + i];
+    const double Bx = P.uu[4 * n + i], By = P.uu[5 * n + i], Bz = P.uu[6 * n + i], en = P.uu[7 * n + i];
+    const Prim q = prim_of(rho, mx, my, mz, Bx, By, Bz, en, P.gamma - 1.0);
+    const double cs2 = P.gamma * q.p / rho;
+    const double sr = sqrt(rho);
+    const double ca[3] = {Bx / sr, By / sr, Bz / sr};
+    const double uvel[3] = {q.ux, q.uy, q.uz};
+    const double ca2 = ca[0] * ca[0] + ca[1] * ca[1] + ca[2] * ca[2];
+    const double cms2 = cs2 + ca2;
+    double chall = 0.0;
+    if (P.hall) chall = P.di / rho * fmax(fmax(Bx, By), Bz) / dmin;
+    double cmax[3];
+    LAPS_UNROLL
+    for (int d = 0; d < 3; ++d) {
+      const double cns = sqrt(fmax(cms2 * cms2 - 4 * cs2 * ca[d] * ca[d], 0.0));
+      const double cf = sqrt(cms2 + cns) / s2;
+      const double csl = sqrt(fmax(cms2 - cns, 0.0)) / s2;
+      const double uu_ = uvel[d];
+      double c = fabs(uu_ + cf);
+      c = fmax(c, fabs(uu_ + csl));
+      c = fmax(c, fabs(uu_ + ca[d]));
+      c = fmax(c, fabs(uu_ - cf));
+      c = fmax(c, fabs(uu_ - csl));
+      c = fmax(c, fabs(uu_ - ca[d]));
+      c = fmax(c, fabs(uu_));
+      if (P.hall) c = fmax(c, chall);
+      cmax[d] = c;
+    }
+    const double dtx = P.dx / cmax[0];
+    const double dty = P.dy / cmax[1] * P.rr;
+    const double dtz = P.dz / cmax[2] * P.rr;
+    best = fmin(best, fmin(fmin(dtx, dty), dtz));
+  }
+  const double r = block_reduce(best, OpMin(), scratch);
+  if (threadIdx.x == 0) P.partial[blockIdx.x] = r;
+}
+
+// final reduction of per-block partials: out[j] = op over b of partial[j*nb + b]; one block per j
+template <class Op>
+__global__ void __launch_bounds__(256) k_reduce_final(const double* partial, int nb, double* out, double init) {
+  __shared__ double scratch[32];
+  double v = init;
+  Op op;
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) v = op(v, partial[(size_t)blockIdx.x * nb + b]);
+  const double r = block_reduce(v, op, scratch);
+  if (threadIdx.x == 0) out[blockIdx.x] = r;
+}
+
+// mhdrms.f90:73-93: sums and sums of squares of (rho,u,B,p), plus sum(e) and sum(u.B) (invariants).
+// partial layout [18][gridDim.x]
+__global__ void __launch_bounds__(256) k_moments1(const double* uu, size_t n, double gamma, double* partial) {
+  __shared__ double scratch[32];
+  double s[18];
+  LAPS_UNROLL
+  for (int j = 0; j < 18; ++j) s[j] = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double rho = uu[i], mx = uu[n + i], my = uu[2 * n + i], mz = uu[3 * n + i];
+    const double Bx = uu[4 * n + i], By = uu[5 * n + i], Bz = uu[6 * n + i], en = uu[7 * n + i];
+    const Prim q = prim_of(rho, mx, my, mz, Bx, By, Bz, en, gamma - 1.0);
+    const double f[8] = {rho, q.ux, q.uy, q.uz, Bx, By, Bz, q.p};
+    LAPS_UNROLL
+    for (int j = 0; j < 8; ++j) { s[j] += f[j]; s[8 + j] += f[j] * f[j]; }
+    s[16] += en;
+    s[17] += q.ux * Bx + q.uy * By + q.uz * Bz;
+  }
+  LAPS_UNROLL
+  for (int j = 0; j < 18; ++j) {
+    const double r = block_reduce(s[j], OpSum(), scratch);
+    if (threadIdx.x == 0) partial[(size_t)j * gridDim.x + blockIdx.x] = r;
+  }
+}
+
+// mhdrms.f90:109-120: sum rho (u_i - ubar_i)^2 ; partial layout [3][gridDim.x]
+__global__ void __launch_bounds__(256) k_moments2(const double* uu, size_t n, double ubx, double uby, double ubz,
+                                                  double* partial) {
+  __shared__ double scratch[32];
+  double s0 = 0, s1 = 0, s2 = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double rho = uu[i];
+    const double ux = uu[n + i] / rho, uy = uu[2 * n + i] / rho, uz = uu[3 * n + i] / rho;
+    s0 += rho * (ux - ubx) * (ux - ubx);
+    s1 += rho * (uy - uby) * (uy - uby);
+    s2 += rho * (uz - ubz) * (uz - ubz);
+  }
+  double r = block_reduce(s0, OpSum(), scratch);
+  if (threadIdx.x == 0) partial[blockIdx.x] = r;
+  r = block_reduce(s1, OpSum(), scratch);
+  if (threadIdx.x == 0) partial[gridDim.x + blockIdx.x] = r;
+  r = block_reduce(s2, OpSum(), scratch);
+  if (threadIdx.x == 0) partial[2 * (size_t)gridDim.x + blockIdx.x] = r;
+}
+
+// mhd.f90:541-568: max | kx Bx^ + ky By^ + kz Bz^ | over the local modes; u = [8][ncol][nz]
+struct DivbParams {
+  const cplx* u; size_t fstride; int ncol, nz, nyl, yoff;
+  const double* kxr; const double* kyr; const double* kze;
+  double radius0, radius, cosa, sina; int corot_k;
+  double* partial;
+};
+__global__ void __launch_bounds__(256) k_divb(const DivbParams P) {
+  __shared__ double scratch[32];
+  double best = 0.0;
+  const size_t total = (size_t)P.ncol * P.nz;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int col = (int)(i / P.nz), kz = (int)(i % P.nz);
+    const int kx = col / P.nyl, ky = P.yoff + col % P.nyl;
+    const double kxr = P.kxr[kx], kyr = P.kyr[ky];
+    double kxe = kxr, kye = __ddiv_rn(__dmul_rn(kyr, P.radius0), P.radius);
+    if (P.corot_k) {
+      kxe = __dadd_rn(__dmul_rn(kxr, P.cosa), __dmul_rn(kyr, P.sina));
+      kye = __ddiv_rn(__dmul_rn(__dadd_rn(__dmul_rn(-kxr, P.sina), __dmul_rn(kyr, P.cosa)), P.radius0), P.radius);
+    }
+    const double kzz = P.kze[kz];
+    const cplx bx = P.u[4 * P.fstride + i], by = P.u[5 * P.fstride + i], bz = P.u[6 * P.fstride + i];
+    const cplx d = cadd(cadd(cmul_i(bx, kxe), cmul_i(by, kye)), cmul_i(bz, kzz));
+    best = fmax(best, sqrt(d.x * d.x + d.y * d.y));
+  }
+  const double r = block_reduce(best, OpMax(), scratch);
+  if (threadIdx.x == 0) P.partial[blockIdx.x] = r;
+}
+
+}  // namespace laps

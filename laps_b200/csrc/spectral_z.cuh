@@ -1,0 +1,273 @@
+// Fused z-pass: forward z-FFT of the flux fields + spectral right-hand side + Runge-Kutta stage
+// update + implicit diffusion + dealiasing + inverse z-FFT of the updated state, one launch per
+// RK stage.  It replaces, for one (kx,ky) column at a time and without ever materialising
+// flux_fourier/fnl/k_square:
+//   fftw.f90:173-179 (forward z lines, "/nz")      mhdrhs.f90:174-279 (calc_rhs)
+//   rktmod.f90:34-62 (rkt)                         dealiasing.f90:70-112 (dealias)
+//   fftw.f90:195-201 (inverse z lines)             AEBmod.f90:87-124 (k_square, on the fly)
+// A second small launch (kind kZCurrent) forms J^ = i k x B^ (mhdrhs.f90:313-339) from the
+// updated field and inverse-transforms it.
+//
+// Linearity is used to save transforms: kx and ky are constant along a z-line, so
+//   -(kx F^a + ky F^b + kz F^c) = -( FFTz[kx fa + ky fb] + kz FFTz[fc] )
+// needs two z-transforms instead of three (results differ from the reference's order of
+// operations by round-off only).
+#pragma once
+#include "fft_passes.cuh"
+
+namespace laps {
+
+enum ZKind { kZRhs = 0, kZForwardOnly = 1, kZInverseOnly = 2, kZCurrent = 3 };
+
+// One row of work (blockIdx.y).  For kZRhs:
+//   G = ca*(i kx)*W2[fa] + cb*(i ky)*W2[fb] + cx*W2[fx]      (missing terms have index < 0)
+//   fnl = sg*FFTz[G] + sc*(i kz)*FFTz[W2[fc]]
+struct ZTask {
+  int kind;
+  int v;       // state component updated (0..7) / read (kZInverseOnly)
+  int gout;    // slot of the inverse-z output in V1, < 0: none
+  int fa, fb, fx, fc;
+  double ca, cb, cx, sg, sc;
+  double aeb_c;   // 2,2,3,3,2,1,1,0 (mhdrhs.f90:235-247)
+  int diff;       // 0 none, 1 viscosity (v=1..3), 2 resistivity (v=4..6)
+  int jcomp;      // kZCurrent: 0,1,2
+};
+
+struct ZParams {
+  int nxh, ny, nyl, yoff, nz, ncol;
+  const cplx* W2;        // [f][col][z]
+  size_t fstride;        // ncol * nz
+  const cplx* u_in;      // [v][col][kz]
+  cplx* u_out;
+  cplx* fnl_rk;
+  PeerTable V1;          // [g][kx][ky][zl] on the owner of z
+  const cplx* tw;
+  // 1-D tables (host-built in the reference's operation order, tables.cpp)
+  const double* kxr;     // wave_number_x(1:nx/2+1)
+  const double* kyr;     // wave_number_y
+  const double* kze;     // wave_number_z * radius0 / radius
+  const double* ksq_x;   // terms of k_square (see tables.cpp)
+  const double* ksq_y;
+  const double* ksq_z;
+  const double* dax;     // dealias: option 1 -> squared radius terms, option 2 -> filters
+  const double* day;
+  const double* daz;
+  double radius0, radius, cosa, sina, tau;
+  double ksq_c1, ksq_c2, ksq_c3;   // corotating k_square coefficients (AEBmod.f90:103-110)
+  int corot_k;           // if_AEB .and. if_corotating (derivative vectors)
+  int corot_ksq;         // corotating k_square formula active
+  int aeb;
+  double cc, dd, dt_irk;
+  int visc_imp, visc_exp, resis_imp, resis_exp, conserve_bg;
+  double nu, eta;
+  int dealias_option;
+  int read_rk, write_rk;
+  double scale;          // 1/nz
+  ZTask task[12];
+};
+
+template <int N, int CG>
+struct ZTile {
+  typedef Geom<N> G;
+  static constexpr int PITCH = G::pitch(1);
+  static constexpr int NTHREADS = CG * G::NT;
+  static constexpr size_t SMEM = (size_t)2 * CG * PITCH * sizeof(cplx);
+};
+
+// k_square(ix,iy,iz) exactly as update_ksquare / grid_initialize evaluate it.
+LAPS_D double ksq_eval(const ZParams& P, double kxr, double kyr, int kx, int ky, int kz) {
+  if (P.corot_ksq) {
+    const double t1 = __dmul_rn(__ldg(P.ksq_x + kx), P.ksq_c1);
+    const double t2 = __dmul_rn(__ldg(P.ksq_y + ky), P.ksq_c2);
+    double t3 = __dmul_rn(kxr, kyr);
+    t3 = __dmul_rn(t3, 2.0);
+    t3 = __dmul_rn(t3, P.cosa);
+    t3 = __dmul_rn(t3, P.sina);
+    t3 = __dmul_rn(t3, P.ksq_c3);
+    return __dadd_rn(__dadd_rn(__dadd_rn(t1, t2), t3), __ldg(P.ksq_z + kz));
+  }
+  return __dadd_rn(__dadd_rn(__ldg(P.ksq_x + kx), __ldg(P.ksq_y + ky)), __ldg(P.ksq_z + kz));
+}
+
+template <int N, int CG>
+__global__ void __launch_bounds__(ZTile<N, CG>::NTHREADS)
+k_spec_z(const ZParams P) {
+  typedef Geom<N> G;
+  typedef Fft<N, -1> FF;
+  typedef Fft<N, +1> FI;
+  typedef ZTile<N, CG> T;
+  LAPS_DYN_SMEM(cplx, sm);
+  const ZTask& K = P.task[blockIdx.y];
+  const int tid = threadIdx.x;
+  const int l = tid / G::NT, u = tid % G::NT;
+  const int col = blockIdx.x * CG + l;
+  const bool live = col < P.ncol;
+  const int kx = live ? col / P.nyl : 0;
+  const int ky = live ? P.yoff + col % P.nyl : 0;
+  cplx* lineG = sm + (2 * l) * T::PITCH;
+  cplx* lineC = lineG + T::PITCH;
+  const size_t coff = (size_t)col * N;
+
+  // derivative vectors (imaginary parts), mhdrhs.f90:191-204
+  const double kxr = __ldg(P.kxr + kx), kyr = __ldg(P.kyr + ky);
+  double kxe = kxr, kye = __ddiv_rn(__dmul_rn(kyr, P.radius0), P.radius);
+  if (P.corot_k) {
+    kxe = __dadd_rn(__dmul_rn(kxr, P.cosa), __dmul_rn(kyr, P.sina));
+    kye = __ddiv_rn(__dmul_rn(__dadd_rn(__dmul_rn(-kxr, P.sina), __dmul_rn(kyr, P.cosa)), P.radius0), P.radius);
+  }
+
+  cplx r[8];
+  if (K.kind == kZRhs || K.kind == kZForwardOnly) {
+    // ---------------- forward z of G (and of C) ----------------
+    LAPS_UNROLL
+    for (int e = 0; e < 8; ++e) r[e] = mk(0.0, 0.0);
+    if (live) {
+      if (K.fa >= 0) {
+        const cplx* s = P.W2 + (size_t)K.fa * P.fstride + coff;
+        const double c = (K.kind == kZRhs) ? K.ca * kxe : 0.0;
+        LAPS_UNROLL
+        for (int e = 0; e < 8; ++e) {
+          const cplx a = s[u + e * G::NT];
+          r[e] = (K.kind == kZRhs) ? cmul_i(a, c) : a;
+        }
+      }
+      if (K.fb >= 0) {
+        const cplx* s = P.W2 + (size_t)K.fb * P.fstride + coff;
+        const double c = K.cb * kye;
+        LAPS_UNROLL
+        for (int e = 0; e < 8; ++e) r[e] = cadd(r[e], cmul_i(s[u + e * G::NT], c));
+      }
+      if (K.fx >= 0) {
+        const cplx* s = P.W2 + (size_t)K.fx * P.fstride + coff;
+        LAPS_UNROLL
+        for (int e = 0; e < 8; ++e) r[e] = cadd(r[e], cscale(s[u + e * G::NT], K.cx));
+      }
+    }
+    FF::first(r, u, lineG, P.tw);
+    const bool hasC = K.fc >= 0;
+    cplx rc[8];
+    if (hasC) {
+      LAPS_UNROLL
+      for (int e = 0; e < 8; ++e) rc[e] = mk(0.0, 0.0);
+      if (live) {
+        const cplx* s = P.W2 + (size_t)K.fc * P.fstride + coff;
+        LAPS_UNROLL
+        for (int e = 0; e < 8; ++e) rc[e] = s[u + e * G::NT];
+      }
+      FF::first(rc, u, lineC, P.tw);
+    }
+    __syncthreads();
+    if constexpr (G::NSTAGE >= 3) {
+      FF::template middle<1>(u, lineG, P.tw);
+      if (hasC) FF::template middle<1>(u, lineC, P.tw);
+      __syncthreads();
+    }
+    if constexpr (G::NSTAGE >= 4) {
+      FF::template middle<2>(u, lineG, P.tw);
+      if (hasC) FF::template middle<2>(u, lineC, P.tw);
+      __syncthreads();
+    }
+    FF::last(r, u, lineG);
+    if (hasC) FF::last(rc, u, lineC);
+
+    // ---------------- spectral update on the 8 modes this thread holds ----------------
+    const size_t voff = (size_t)K.v * P.fstride + coff;
+    LAPS_UNROLL
+    for (int e = 0; e < 8; ++e) {
+      const int kz = FF::kout(u, e);
+      if (K.kind == kZForwardOnly) {
+        r[e] = cscale(r[e], P.scale);
+        if (live) P.u_out[voff + kz] = r[e];
+        continue;
+      }
+      cplx fnl = cscale(r[e], K.sg * P.scale);
+      if (hasC) fnl = cadd(fnl, cmul_i(rc[e], K.sc * P.scale * __ldg(P.kze + kz)));
+      const cplx uo = live ? P.u_in[voff + kz] : mk(0.0, 0.0);
+      if (P.aeb && K.aeb_c != 0.0) {
+        fnl.x -= __ddiv_rn(__dmul_rn(K.aeb_c, uo.x), P.tau);
+        fnl.y -= __ddiv_rn(__dmul_rn(K.aeb_c, uo.y), P.tau);
+      }
+      double ksq = 0.0;
+      if (K.diff) ksq = ksq_eval(P, kxr, kyr, kx, ky, kz);
+      if (K.diff == 1 && P.visc_exp) {
+        fnl.x -= (P.nu * uo.x) * ksq;
+        fnl.y -= (P.nu * uo.y) * ksq;
+      }
+      if (K.diff == 2 && P.resis_exp && !(P.conserve_bg && kx == 0 && kz == 0)) {
+        fnl.x -= (P.eta * uo.x) * ksq;
+        fnl.y -= (P.eta * uo.y) * ksq;
+      }
+      // rkt (rktmod.f90:40-42): u = cc*fnl + dd*fnl_rk + u ; fnl_rk = fnl
+      cplx un;
+      if (P.read_rk) {
+        const cplx fr = live ? P.fnl_rk[voff + kz] : mk(0.0, 0.0);
+        un = mk((P.cc * fnl.x + P.dd * fr.x) + uo.x, (P.cc * fnl.y + P.dd * fr.y) + uo.y);
+      } else {
+        un = mk(P.cc * fnl.x + uo.x, P.cc * fnl.y + uo.y);
+      }
+      if (P.write_rk && live) P.fnl_rk[voff + kz] = fnl;
+      // implicit diffusion (rktmod.f90:47-60)
+      if ((K.diff == 1 && P.visc_imp) || (K.diff == 2 && P.resis_imp)) {
+        const double coef = (K.diff == 1) ? P.nu : P.eta;
+        const double den = __dadd_rn(__dmul_rn(__dmul_rn(P.dt_irk, ksq), coef), 1.0);
+        un.x = __ddiv_rn(un.x, den);
+        un.y = __ddiv_rn(un.y, den);
+      }
+      // dealias (dealiasing.f90:87-110)
+      if (P.dealias_option == 1) {
+        const double rad = __dsqrt_rn(__dadd_rn(__dadd_rn(__ldg(P.dax + kx), __ldg(P.day + ky)), __ldg(P.daz + kz)));
+        if (rad > (1.0 / 3.0)) un = mk(0.0, 0.0);
+      } else if (P.dealias_option == 2) {
+        const double fx = __ldg(P.dax + kx), fy = __ldg(P.day + ky), fz = __ldg(P.daz + kz);
+        un = mk(__dmul_rn(__dmul_rn(__dmul_rn(un.x, fx), fy), fz), __dmul_rn(__dmul_rn(__dmul_rn(un.y, fx), fy), fz));
+      }
+      if (live) P.u_out[voff + kz] = un;
+      r[e] = un;
+    }
+    if (K.kind == kZForwardOnly || K.gout < 0) return;
+    // re-shape the register contents into the stage-0 input pattern of the inverse transform
+    __syncthreads();  // all last-stage reads of lineG are done
+    if constexpr (G::RLAST != 8) {
+      LAPS_UNROLL
+      for (int e = 0; e < 8; ++e) lineG[G::pad(FF::kout(u, e))] = r[e];
+      __syncthreads();
+      LAPS_UNROLL
+      for (int e = 0; e < 8; ++e) r[e] = lineG[G::pad(u + e * G::NT)];
+      __syncthreads();
+    }
+  } else if (K.kind == kZInverseOnly) {
+    const size_t voff = (size_t)K.v * P.fstride + coff;
+    LAPS_UNROLL
+    for (int e = 0; e < 8; ++e) r[e] = live ? P.u_in[voff + u + e * G::NT] : mk(0.0, 0.0);
+  } else {  // kZCurrent: J^ = i k x B^ (mhdrhs.f90:329-336) from the updated state
+    const int j = K.jcomp;
+    const cplx* B1 = P.u_in + (size_t)(4 + (j + 1) % 3) * P.fstride + coff;  // B_{j+1}
+    const cplx* B2 = P.u_in + (size_t)(4 + (j + 2) % 3) * P.fstride + coff;  // B_{j+2}
+    LAPS_UNROLL
+    for (int e = 0; e < 8; ++e) {
+      const int kz = u + e * G::NT;
+      const double kzz = __ldg(P.kze + kz);
+      // k_{j+1} B_{j+2} - k_{j+2} B_{j+1}   with (k0,k1,k2) = (kx,ky,kz)
+      const double k1 = (j == 0) ? kye : (j == 1 ? kzz : kxe);
+      const double k2 = (j == 0) ? kzz : (j == 1 ? kxe : kye);
+      const cplx b1 = live ? B1[kz] : mk(0.0, 0.0);
+      const cplx b2 = live ? B2[kz] : mk(0.0, 0.0);
+      r[e] = csub(cmul_i(b2, k1), cmul_i(b1, k2));
+    }
+  }
+
+  // ---------------- inverse z, stored on the owner of each z (transpose_zy fused) ----------------
+  FI::first(r, u, lineG, P.tw);
+  FI::finish(r, u, lineG, P.tw);
+  if (live) {
+    LAPS_UNROLL
+    for (int e = 0; e < 8; ++e) {
+      const int z = FI::kout(u, e);
+      const int p = P.V1.owner(z);
+      cplx* dst = P.V1.base[p] + (((size_t)K.gout * P.nxh + kx) * P.ny + ky) * P.V1.len[p] + (z - P.V1.off[p]);
+      *dst = r[e];
+    }
+  }
+}
+
+}  // namespace laps

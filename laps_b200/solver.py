@@ -1,0 +1,173 @@
+"""Host-side mirror of the reference's module interface for the hot path.
+
+Method names follow the Fortran subroutines they stand in for (``evolve``, ``vardt``,
+``evolve_radius``, ``calc_rms``, ``calc_max_divB`` ...; file:line in each docstring, relative to
+``src_compressible/``) so that parity tests read like a LAPS driver.  All work is done by the CUDA
+library through the C ABI (``capi.py``); arrays here are only the host copies a driver owns.
+
+Array convention (same memory layout as the Fortran arrays): real fields ``a[v, iz_local, iy, ix]``
+(= ``uu(ix,iy,iz,v)``), spectral fields ``a[v, kz, ky_local, kx]`` (= ``uu_fourier(ix,iy,iz,v)``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import capi
+
+
+class Solver:
+    def __init__(self, lib_path: Optional[str] = None, **params):
+        self._lib = capi.load(lib_path)
+        self.params = capi.make_params(**params)
+        self._h = C.c_void_p()
+        rc = self._lib.laps_create(C.byref(self.params), C.byref(self._h))
+        if rc:
+            raise capi.LapsError("laps_create: " + self._lib.laps_last_error(None).decode())
+        ext = capi.LapsExtents()
+        self._ck(self._lib.laps_get_extents(self._h, C.byref(ext)))
+        self.ext = ext
+        self.nx, self.ny, self.nz, self.nxh = ext.nx, ext.ny, ext.nz, ext.nxh
+        self.nzl, self.nyl = ext.z_size, ext.y_size
+        self.time = 0.0
+        self.dt = 0.0
+
+    # ------------------------------------------------------------------ plumbing
+    def _ck(self, rc):
+        if rc:
+            raise capi.LapsError(self._lib.laps_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            self._lib.laps_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def real_shape(self):
+        return (self.nzl, self.ny, self.nx)
+
+    # ------------------------------------------------------------------ driver-facing calls
+    def set_primitive(self, prim: np.ndarray):
+        """initial_calc_conserve_variable + transform_uu_real_to_fourier (mhd.f90:121-122)."""
+        a = np.ascontiguousarray(prim, dtype=np.float64)
+        assert a.shape == (8,) + self.real_shape, (a.shape, self.real_shape)
+        self._ck(self._lib.laps_set_primitive(self._h, capi._dptr(a)))
+
+    def evolve_radius(self, time: float):
+        """AEBmod.f90:56-73."""
+        self._ck(self._lib.laps_set_time(self._h, float(time)))
+
+    def vardt(self) -> float:
+        """mhd.f90:328-429."""
+        dt = C.c_double(self.dt)
+        self._ck(self._lib.laps_vardt(self._h, C.byref(dt)))
+        self.dt = dt.value
+        return self.dt
+
+    def rkt_init(self, dt: float):
+        """rktmod.f90:15-32."""
+        self._ck(self._lib.laps_rkt_init(self._h, float(dt)))
+        self.dt = float(dt)
+
+    def evolve(self):
+        """mhd.f90:298-326 (asynchronous)."""
+        self._ck(self._lib.laps_evolve(self._h))
+
+    def step(self) -> float:
+        """One pass of the Principal loop body (mhd.f90:245-248,285)."""
+        t = C.c_double(self.time)
+        dt = C.c_double(self.dt)
+        self._ck(self._lib.laps_step(self._h, C.byref(t), C.byref(dt)))
+        self.time, self.dt = t.value, dt.value
+        return self.dt
+
+    def sync(self):
+        self._ck(self._lib.laps_sync(self._h))
+
+    def calc_max_divB(self) -> float:
+        """mhd.f90:522-570."""
+        out = C.c_double()
+        self._ck(self._lib.laps_max_divb(self._h, C.byref(out)))
+        return out.value
+
+    def calc_rms(self):
+        """mhdrms.f90:53-126 -> (uu_ave[8], uu_rms[8], rho_u2[3])."""
+        out = np.zeros(19)
+        self._ck(self._lib.laps_rms(self._h, capi._dptr(out)))
+        return out[:8].copy(), out[8:16].copy(), out[16:].copy()
+
+    def invariants(self) -> np.ndarray:
+        out = np.zeros(3)
+        self._ck(self._lib.laps_invariants(self._h, capi._dptr(out)))
+        return out
+
+    def get_state(self, want_prim=True):
+        """Host copies of uu and uu_prim for output_uu / restart (mhdoutput.f90:95-123)."""
+        uu = np.empty((8,) + self.real_shape)
+        prim = np.empty((4,) + self.real_shape) if want_prim else None
+        self._ck(self._lib.laps_get_state(self._h, capi._dptr(uu), capi._dptr(prim) if want_prim else None))
+        return uu, prim
+
+    def uu_fourier(self) -> np.ndarray:
+        """Spectral state in the reference index order [v, kz, ky_local, kx]."""
+        raw = np.empty((8, self.nxh, self.nyl, self.nz), dtype=np.complex128)
+        self._ck(self._lib.laps_get_spectral(self._h, raw.ctypes.data_as(C.POINTER(C.c_double))))
+        return np.ascontiguousarray(raw.transpose(0, 3, 2, 1))
+
+    def fft_forward(self, fields: np.ndarray) -> np.ndarray:
+        """fftw.f90:42-71 + 136-180 for up to 8 fields; result [f, kz, ky_local, kx]."""
+        a = np.ascontiguousarray(fields, dtype=np.float64)
+        nf = a.shape[0]
+        assert a.shape == (nf,) + self.real_shape
+        raw = np.empty((nf, self.nxh, self.nyl, self.nz), dtype=np.complex128)
+        self._ck(self._lib.laps_fft_forward(self._h, capi._dptr(a), nf, raw.ctypes.data_as(C.POINTER(C.c_double))))
+        return np.ascontiguousarray(raw.transpose(0, 3, 2, 1))
+
+    def fft_inverse(self, spec: np.ndarray) -> np.ndarray:
+        """fftw.f90:73-103 + 182-222 for up to 8 fields given as [f, kz, ky_local, kx]."""
+        nf = spec.shape[0]
+        assert spec.shape == (nf, self.nz, self.nyl, self.nxh)
+        raw = np.ascontiguousarray(np.asarray(spec, dtype=np.complex128).transpose(0, 3, 2, 1))
+        out = np.empty((nf,) + self.real_shape)
+        self._ck(self._lib.laps_fft_inverse(self._h, raw.ctypes.data_as(C.POINTER(C.c_double)), nf, capi._dptr(out)))
+        return out
+
+    def transpose_yz_indexmap(self) -> np.ndarray:
+        out = np.empty((self.nxh * self.ny * self.nzl, 2), dtype=np.int64)
+        self._ck(self._lib.laps_transpose_yz_indexmap(self._h, out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return out
+
+    # ------------------------------------------------------------------ measurement helpers
+    def last_step_ms(self):
+        ms = C.c_float()
+        n = C.c_int32()
+        self._ck(self._lib.laps_last_step_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def set_profiling(self, on: bool):
+        self._ck(self._lib.laps_set_profiling(self._h, 1 if on else 0))
+
+    def get_profile(self, cap=512):
+        names = C.create_string_buffer(cap * 32)
+        ms = (C.c_float * cap)()
+        cnt = C.c_int32()
+        self._ck(self._lib.laps_get_profile(self._h, names, ms, cap, C.byref(cnt)))
+        out = []
+        for i in range(cnt.value):
+            nm = names.raw[i * 32:(i + 1) * 32].split(b"\0", 1)[0].decode()
+            out.append((nm, ms[i]))
+        return out

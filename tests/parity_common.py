@@ -1,0 +1,109 @@
+"""Shared parity checks: the CUDA path (through the C ABI) against the CPU oracle.
+
+Used by tests/test_gpu_parity.py on a B200 (`-m gpu`) and — with the test-only kernel emulator —
+by tests/test_emulated_kernels.py in the CPU-only container."""
+import numpy as np
+
+from laps_b200 import Solver
+from oracle import laps_oracle as lo
+
+
+def rel_l2(a, b):
+    d = np.linalg.norm((np.asarray(a) - np.asarray(b)).ravel())
+    n = np.linalg.norm(np.asarray(b).ravel())
+    return d / n if n > 0 else d
+
+
+def make_case(nx, ny, nz, hall=True, aeb=True, corot=False, dealias=1, visc=True, resis=True,
+              explicit=False, conserve_bg=False, seed=101, nmode=2):
+    """Oracle parameters + primitive initial data (ifield=3 + ipert=7-style turbulence)."""
+    p = lo.Params(nx=nx, ny=ny, nz=nz, Lx=24.0, Ly=24.0, Lz=24.0, adiabatic_index=1.666667,
+                  if_resis=resis, resistivity=1e-4 if not explicit else 1e-3, if_resis_exp=explicit,
+                  if_visc=visc, viscosity=1e-4 if not explicit else 1e-3, if_visc_exp=explicit,
+                  if_conserve_background=conserve_bg, cfl=0.5, dealias_option=dealias,
+                  if_AEB=aeb, radius0=30.0, Ur0=1.167 if aeb else 0.0, if_corotating=corot,
+                  corotating_angle=0.3 if corot else 0.0,
+                  if_hall=hall, ion_inertial_length=0.2 if hall else 0.0)
+    prim = lo.ic_uniform_background(p, bx0=1.0, press0=1.0)
+    prim = lo.ic_turbulence(p, prim, 1.0, 0.0, 0.0, db0=0.1, dv0=0.1, drho0=0.01,
+                            nmodex=nmode, nmodey=nmode, nmodez=nmode, seeds=(seed, seed + 15, seed + 31))
+    return p, prim
+
+
+def solver_kwargs(p: lo.Params):
+    return dict(nx=p.nx, ny=p.ny, nz=p.nz, Lx=p.Lx, Ly=p.Ly, Lz=p.Lz, adiabatic_index=p.adiabatic_index,
+                if_resis=p.if_resis, if_resis_exp=p.if_resis_exp, resistivity=p.resistivity,
+                if_visc=p.if_visc, if_visc_exp=p.if_visc_exp, viscosity=p.viscosity,
+                if_conserve_background=p.if_conserve_background, cfl=p.cfl, dealias_option=p.dealias_option,
+                afx=p.afx, afy=p.afy, afz=p.afz, if_AEB=p.if_AEB, if_corotating=p.if_corotating,
+                radius0=p.radius0, Ur0=p.Ur0, corotating_angle=p.corotating_angle,
+                if_hall=p.if_hall, ion_inertial_length=p.ion_inertial_length)
+
+
+def run_both(p, prim, nsteps, lib_path=None, t0=0.0):
+    """Drive oracle and library exactly as mhd.f90 does: [set time]; vardt; nsteps x step."""
+    o = lo.State(p)
+    o.set_primitive(prim)
+    g = Solver(lib_path, **solver_kwargs(p))
+    g.set_primitive(prim)
+    if t0:
+        o.time = t0
+        o.evolve_radius(t0)
+        g.time = t0
+        g.evolve_radius(t0)
+    o.vardt()
+    g.vardt()
+    for _ in range(nsteps):
+        o.step()
+        g.step()
+    return o, g
+
+
+def check_fft(nx, ny, nz, lib_path=None, tol=1e-13, seed=0):
+    rng = np.random.default_rng(seed)
+    a = rng.standard_normal((3, nz, ny, nx))
+    with Solver(lib_path, nx=nx, ny=ny, nz=nz, Lx=1.0, Ly=1.0, Lz=1.0, dealias_option=0) as s:
+        w = s.fft_forward(a)
+        ref = lo.fft_forward(a)
+        assert rel_l2(w, ref) < tol, ("forward", rel_l2(w, ref))
+        # inverse of an arbitrary (not Hermitian-consistent) spectrum: c2r must drop Im(DC/Nyquist)
+        spec = ref + 0.0
+        spec[..., 0] += 0.25j
+        spec[..., -1] -= 0.5j
+        b = s.fft_inverse(spec)
+        assert rel_l2(b, a) < tol, ("inverse", rel_l2(b, a))
+        # single-mode known answer: cos(2 pi (2x/Lx + 3y/Ly + 1 z/Lz)) -> 1/2 at (kx,ky,kz)=(2,3,1)
+        z, y, x = np.meshgrid(np.arange(nz) / nz, np.arange(ny) / ny, np.arange(nx) / nx, indexing="ij")
+        m = np.cos(2 * np.pi * (2 * x + 3 * y + 1 * z))[None]
+        wm = s.fft_forward(m)[0]
+        assert abs(wm[1, 3, 2] - 0.5) < 1e-14
+        wm[1, 3, 2] = 0
+        assert np.abs(wm).max() < 1e-14
+
+
+def check_state(o, g, tol_field, tol_spec=None):
+    uu, prim = g.get_state()
+    for v in range(8):
+        assert rel_l2(uu[v], o.uu[v]) < tol_field, (v, rel_l2(uu[v], o.uu[v]))
+    for v in range(4):
+        assert rel_l2(prim[v], o.uu_prim[v]) < 10 * tol_field, (v, rel_l2(prim[v], o.uu_prim[v]))
+    uf = g.uu_fourier()
+    for v in range(8):
+        assert rel_l2(uf[v], o.uu_fourier[v]) < (tol_spec or tol_field), (v, rel_l2(uf[v], o.uu_fourier[v]))
+    assert abs(g.dt - o.dt) <= 1e-12 * abs(o.dt), (g.dt, o.dt)
+    assert abs(g.time - o.time) <= 1e-12 * max(abs(o.time), 1e-300)
+
+
+def check_diagnostics(o, g, tol):
+    ave, rms, ru2 = g.calc_rms()
+    oave, orms, oru2 = o.calc_rms()
+    assert np.allclose(ave, oave, rtol=tol, atol=tol * 1e-3), (ave, oave)
+    assert np.allclose(rms, orms, rtol=tol, atol=1e-15), (rms, orms)
+    assert np.allclose(ru2, oru2, rtol=tol, atol=1e-18), (ru2, oru2)
+    inv = g.invariants()
+    oinv = o.invariants()
+    assert abs(inv[0] - oinv[0]) <= tol * abs(oinv[0])
+    assert abs(inv[1] - oinv[1]) <= tol * max(abs(oinv[1]), 1e-6)
+    # div B sits at round-off in both; compare magnitudes, not digits
+    assert inv[2] < 1e-13 and oinv[2] < 1e-13, (inv[2], oinv[2])
+    assert abs(g.calc_max_divB() - inv[2]) == 0.0
