@@ -92,6 +92,9 @@ int laps_evolve(laps_handle h);
  * evolve; time += dt; evolve_radius(time); vardt.  Updates *time_inout and *dt_inout. */
 int laps_step(laps_handle h, double* time_inout, double* dt_inout);
 int laps_sync(laps_handle h);
+/* The CUDA stream (cudaStream_t) every kernel of this handle is launched on, so that a harness can
+ * bracket calls with its own CUDA events. */
+int laps_get_stream(laps_handle h, void** stream_out);
 
 /* calc_max_divB (mhd.f90:157,522-570). */
 int laps_max_divb(laps_handle h, double* out);

@@ -58,7 +58,7 @@ SYMBOLS = [
     "laps_create", "laps_destroy", "laps_last_error", "laps_get_extents",
     "laps_export_peer_blob", "laps_import_peer_blobs", "laps_set_barrier", "laps_connect_local",
     "laps_set_primitive", "laps_set_time", "laps_vardt", "laps_rkt_init", "laps_evolve", "laps_step",
-    "laps_sync", "laps_max_divb", "laps_rms", "laps_invariants", "laps_get_state", "laps_get_spectral",
+    "laps_sync", "laps_get_stream", "laps_max_divb", "laps_rms", "laps_invariants", "laps_get_state", "laps_get_spectral",
     "laps_fft_forward", "laps_fft_inverse", "laps_transpose_yz_indexmap",
     "laps_last_step_ms", "laps_set_profiling", "laps_get_profile",
 ]
@@ -99,6 +99,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.laps_evolve.argtypes = [H]
     lib.laps_step.argtypes = [H, dp, dp]
     lib.laps_sync.argtypes = [H]
+    lib.laps_get_stream.argtypes = [H, C.POINTER(C.c_void_p)]
     lib.laps_max_divb.argtypes = [H, dp]
     lib.laps_rms.argtypes = [H, dp]
     lib.laps_invariants.argtypes = [H, dp]

@@ -577,6 +577,12 @@ int laps_sync(laps_handle s) {
   return 0;
 }
 
+int laps_get_stream(laps_handle s, void** stream_out) {
+  if (!s || !stream_out) return 1;
+  *stream_out = (void*)s->stream;
+  return 0;
+}
+
 int laps_set_primitive(laps_handle s, const double* uu_local) {
   if (!s || !uu_local) return 1;
   LAPS_CK(s, cudaMemcpyAsync(s->uu, uu_local, 8 * s->npts * sizeof(double), cudaMemcpyHostToDevice, s->stream));

@@ -60,6 +60,17 @@ class Solver:
     def real_shape(self):
         return (self.nzl, self.ny, self.nx)
 
+    # ------------------------------------------------------------------ multi-rank wiring
+    def export_peer_blob(self) -> bytes:
+        """This rank's exchange-buffer descriptor (CUDA IPC handles); all-gather and import."""
+        buf = C.create_string_buffer(capi.PEER_BLOB_BYTES)
+        self._ck(self._lib.laps_export_peer_blob(self._h, buf))
+        return buf.raw
+
+    def import_peer_blobs(self, blobs: bytes):
+        assert len(blobs) == capi.PEER_BLOB_BYTES * self.params.nranks
+        self._ck(self._lib.laps_import_peer_blobs(self._h, C.create_string_buffer(blobs, len(blobs))))
+
     # ------------------------------------------------------------------ driver-facing calls
     def set_primitive(self, prim: np.ndarray):
         """initial_calc_conserve_variable + transform_uu_real_to_fourier (mhd.f90:121-122)."""
@@ -98,6 +109,12 @@ class Solver:
     def sync(self):
         self._ck(self._lib.laps_sync(self._h))
 
+    def cuda_stream(self) -> int:
+        """cudaStream_t of this handle as an integer (for torch.cuda.ExternalStream)."""
+        out = C.c_void_p()
+        self._ck(self._lib.laps_get_stream(self._h, C.byref(out)))
+        return out.value or 0
+
     def calc_max_divB(self) -> float:
         """mhd.f90:522-570."""
         out = C.c_double()
@@ -115,10 +132,11 @@ class Solver:
         self._ck(self._lib.laps_invariants(self._h, capi._dptr(out)))
         return out
 
-    def get_state(self, want_prim=True):
+    def get_state(self, want_prim=True, out_uu=None, out_prim=None):
         """Host copies of uu and uu_prim for output_uu / restart (mhdoutput.f90:95-123)."""
-        uu = np.empty((8,) + self.real_shape)
-        prim = np.empty((4,) + self.real_shape) if want_prim else None
+        uu = np.empty((8,) + self.real_shape) if out_uu is None else out_uu
+        prim = (np.empty((4,) + self.real_shape) if out_prim is None else out_prim) if want_prim else None
+        assert uu.shape == (8,) + self.real_shape and uu.dtype == np.float64 and uu.flags.c_contiguous
         self._ck(self._lib.laps_get_state(self._h, capi._dptr(uu), capi._dptr(prim) if want_prim else None))
         return uu, prim
 

@@ -104,6 +104,10 @@ def check_diagnostics(o, g, tol):
     oinv = o.invariants()
     assert abs(inv[0] - oinv[0]) <= tol * abs(oinv[0])
     assert abs(inv[1] - oinv[1]) <= tol * max(abs(oinv[1]), 1e-6)
-    # div B sits at round-off in both; compare magnitudes, not digits
-    assert inv[2] < 1e-13 and oinv[2] < 1e-13, (inv[2], oinv[2])
+    # without the expanding box div B sits at round-off in both (compare magnitudes, not digits);
+    # with it the stretched wave vectors leave an O(dt^2) residual that both must agree on
+    if oinv[2] < 1e-12:
+        assert inv[2] < 1e-12, (inv[2], oinv[2])
+    else:
+        assert abs(inv[2] - oinv[2]) <= max(1e3 * tol, 1e-7) * oinv[2], (inv[2], oinv[2])
     assert abs(g.calc_max_divB() - inv[2]) == 0.0
