@@ -110,17 +110,20 @@ class ClockSampler:
 # algorithmic bytes per launch of each kernel; R, C in bytes per field
 # ------------------------------------------------------------------------------------------
 def kernel_bytes(name, R, C, nf, ni, hall):
+    """Algorithmic HBM bytes of one launch.  Pass launches carry their field
+    count in the name (fwd_x19, inv_y11, inv_y3 ...)."""
+    import re
+    m = re.fullmatch(r"(fwd_x|fwd_y|inv_y|inv_x)(\d+)", name)
+    if m:
+        k, n = m.group(1), int(m.group(2))
+        return {"fwd_x": n * R + n * C, "fwd_y": 2 * n * C, "inv_y": 2 * n * C, "inv_x": n * C + n * R}[k]
     table = {
         "flux": (8 + (3 if hall else 0)) * R + nf * R,
-        "fwd_x": nf * R + nf * C,
-        "fwd_y": 2 * nf * C,
         # reads nf flux spectra + u (8C) + fnl_rk (8C, stages 2,3), writes u (8C) + fnl_rk (8C, stages 1,2)
         # + inverse-z output (8C): averaged over the three stages
         "spec_z": (nf + 8 + 8 * 2 / 3 + 8 + 8 * 2 / 3 + 8) * C,
         "curl_b_inv_z": 3 * C + 3 * C,
-        "inv_y": 2 * ni * C,
-        "inv_x": ni * C + ni * R,
-        "inv_y3": 6 * C, "inv_x3": 3 * C + 3 * R,
+        "fwd_z": 2 * 8 * C,
         "cfl": 8 * R,
     }
     return table.get(name)
@@ -307,6 +310,7 @@ def run_gpu(args):
                                         for k, v in prof.items() if kernel_bytes(k, R, C, nf, ni, hall)},
                     "time_share": shares}
 
+    barrier()          # no rank may free its exchange buffers while a peer can still store into them
     g.close()
     if rank != 0:
         if world > 1:

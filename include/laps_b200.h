@@ -62,17 +62,22 @@ int laps_destroy(laps_handle h);
 const char* laps_last_error(laps_handle h); /* h may be NULL: error of the last failed laps_create */
 int laps_get_extents(laps_handle h, laps_extents* out);
 
-/* Multi-rank wiring (replaces the communicators of parallel.f90:77-95).  Each rank exports an
- * opaque blob describing its exchange buffers (CUDA IPC handles), the driver all-gathers the
- * blobs (MPI_Allgather in a Fortran driver) and hands the concatenation back.  laps_barrier_fn
- * is called by the library wherever all ranks must have finished a pass (an MPI_Barrier thunk).
+/* Multi-rank wiring (replaces the communicators and subarray datatypes of parallel.f90:77-211).
+ * The FFT passes on either side of transpose_yz / transpose_zy (parallel.f90:273-324) store
+ * straight into the owning rank's buffer over NVLink and order themselves with device-side
+ * flags, so the only host-side step is an exchange of addresses at start-up: each rank exports
+ * an opaque blob (CUDA IPC handles of its exchange buffers), the driver all-gathers the blobs
+ * (MPI_Allgather in a Fortran driver) and hands the concatenation, ordered by rank, back.
+ * After that, laps_set_primitive, laps_evolve, laps_step, laps_vardt, laps_max_divb, laps_rms,
+ * laps_invariants, laps_fft_forward and laps_fft_inverse are COLLECTIVE: every rank must call
+ * them in the same order (exactly as every MPI rank of the reference does).  The driver must
+ * synchronise the ranks (MPI_Barrier) before any of them calls laps_destroy.
  * Not needed when nranks == 1. */
 #define LAPS_PEER_BLOB_BYTES 256
 int laps_export_peer_blob(laps_handle h, void* blob /* LAPS_PEER_BLOB_BYTES */);
 int laps_import_peer_blobs(laps_handle h, const void* blobs /* nranks * LAPS_PEER_BLOB_BYTES */);
-typedef void (*laps_barrier_fn)(void* user);
-int laps_set_barrier(laps_handle h, laps_barrier_fn fn, void* user);
-/* Single-process multi-GPU: wire the handles of all ranks created in this process to each other. */
+/* Single-process multi-GPU: wire the handles of all ranks created in this process to each other
+ * (peer access instead of IPC).  Each handle must then be driven by its own host thread. */
 int laps_connect_local(laps_handle* handles, int32_t nranks);
 
 /* initial_calc_conserve_variable + transform_uu_real_to_fourier (mhd.f90:121-122):

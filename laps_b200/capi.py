@@ -51,12 +51,10 @@ class LapsExtents(C.Structure):
                 ("y_offset", C.c_int32), ("y_size", C.c_int32)]
 
 
-BARRIER_FN = C.CFUNCTYPE(None, C.c_void_p)
-
 # every symbol include/laps_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "laps_create", "laps_destroy", "laps_last_error", "laps_get_extents",
-    "laps_export_peer_blob", "laps_import_peer_blobs", "laps_set_barrier", "laps_connect_local",
+    "laps_export_peer_blob", "laps_import_peer_blobs", "laps_connect_local",
     "laps_set_primitive", "laps_set_time", "laps_vardt", "laps_rkt_init", "laps_evolve", "laps_step",
     "laps_sync", "laps_get_stream", "laps_max_divb", "laps_rms", "laps_invariants", "laps_get_state", "laps_get_spectral",
     "laps_fft_forward", "laps_fft_inverse", "laps_transpose_yz_indexmap",
@@ -90,7 +88,6 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.laps_get_extents.argtypes = [H, C.POINTER(LapsExtents)]
     lib.laps_export_peer_blob.argtypes = [H, C.c_void_p]
     lib.laps_import_peer_blobs.argtypes = [H, C.c_void_p]
-    lib.laps_set_barrier.argtypes = [H, BARRIER_FN, C.c_void_p]
     lib.laps_connect_local.argtypes = [C.POINTER(H), C.c_int32]
     lib.laps_set_primitive.argtypes = [H, dp]
     lib.laps_set_time.argtypes = [H, C.c_double]

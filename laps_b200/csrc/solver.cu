@@ -10,6 +10,9 @@
 #include <string>
 #include <vector>
 
+#include <unistd.h>
+
+#include "exchange.cuh"
 #include "fft_passes.cuh"
 #include "pointwise.cuh"
 #include "spectral_z.cuh"
@@ -94,8 +97,12 @@ struct laps_solver {
   bool have_state = false;
 
   PeerTable tabW2, tabV1;
-  laps_barrier_fn barrier = nullptr;
-  void* barrier_user = nullptr;
+  // slab exchange (exchange.cuh): this rank's flag/mailbox block, the peers' mappings, the epoch
+  XchgBlock* xblk = nullptr;
+  XchgPeers xp;
+  unsigned long long epoch = 0;
+  bool wired = false;
+  void* ipc_opened[LAPS_MAX_RANKS][3];   // mappings obtained with cudaIpcOpenMemHandle
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int launches = 0;
@@ -216,11 +223,12 @@ int check_launch(S* s, const char* what) {
 // ---- pass launchers ---------------------------------------------------------------------------
 template <int N>
 int do_fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1) {
+  char name[32]; std::snprintf(name, sizeof(name), "fwd_x%d", nfields);
   constexpr int TL = tlx(N);
   typedef Tile<N, TL> T;
   if (s->ny % (2 * TL) != 0) { s->err = "ny must be a multiple of " + std::to_string(2 * TL); return 1; }
   LAPS_CK(s, cudaFuncSetAttribute(k_fwd_x<N, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
-  LaunchScope ls(s, "fwd_x");
+  LaunchScope ls(s, name);
   dim3 grid((unsigned)(s->nzl * (s->ny / (2 * TL))), (unsigned)nfields);
   LAPS_LAUNCH((k_fwd_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, in, fstride, W1, s->nzl, s->ny, s->tw_x,
               1.0 / N);
@@ -229,10 +237,11 @@ int do_fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1) {
 
 template <int N>
 int do_fwd_y(S* s, const cplx* W1, int nfields) {
+  char name[32]; std::snprintf(name, sizeof(name), "fwd_y%d", nfields);
   constexpr int TL = tly(N);
   typedef Tile<N, TL> T;
   LAPS_CK(s, cudaFuncSetAttribute(k_fwd_y<N, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
-  LaunchScope ls(s, "fwd_y");
+  LaunchScope ls(s, name);
   const int ztiles = (s->nzl + TL - 1) / TL;
   dim3 grid((unsigned)(ztiles * s->nxh), (unsigned)nfields);
   LAPS_LAUNCH((k_fwd_y<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, W1, s->tabW2, s->nzl, s->nz, s->zo,
@@ -242,10 +251,11 @@ int do_fwd_y(S* s, const cplx* W1, int nfields) {
 
 template <int N>
 int do_inv_y(S* s, const cplx* V1, cplx* V2, int nfields) {
+  char name[32]; std::snprintf(name, sizeof(name), "inv_y%d", nfields);
   constexpr int TL = tly(N);
   typedef Tile<N, TL> T;
   LAPS_CK(s, cudaFuncSetAttribute(k_inv_y<N, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
-  LaunchScope ls(s, "inv_y");
+  LaunchScope ls(s, name);
   const int ztiles = (s->nzl + TL - 1) / TL;
   dim3 grid((unsigned)(ztiles * s->nxh), (unsigned)nfields);
   LAPS_LAUNCH((k_inv_y<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, V1, V2, s->nzl, s->tw_y);
@@ -254,10 +264,11 @@ int do_inv_y(S* s, const cplx* V1, cplx* V2, int nfields) {
 
 template <int N>
 int do_inv_x(S* s, const cplx* V2, const RealDst& dst, int nfields) {
+  char name[32]; std::snprintf(name, sizeof(name), "inv_x%d", nfields);
   constexpr int TL = tlx(N);
   typedef Tile<N, TL> T;
   LAPS_CK(s, cudaFuncSetAttribute(k_inv_x<N, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
-  LaunchScope ls(s, "inv_x");
+  LaunchScope ls(s, name);
   dim3 grid((unsigned)(s->nzl * (s->ny / (2 * TL))), (unsigned)nfields);
   LAPS_LAUNCH((k_inv_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, V2, dst, s->nzl, s->ny, s->tw_x);
   return check_launch(s, "k_inv_x");
@@ -347,11 +358,15 @@ int launch_current_tasks(S* s, const cplx* u) {  // J^ = i k x B^, inverse z  (m
   return spec_z(s, z, 3, "curl_b_inv_z");
 }
 
+// Every rank has finished the passes enqueued so far (stands where the reference's blocking
+// mpi_sendrecv loops of transpose_yz/zy return, parallel.f90:273-324).  Device side, asynchronous.
 int host_barrier(S* s) {
   if (s->P > 1) {
-    LAPS_CK(s, cudaStreamSynchronize(s->stream));
-    if (!s->barrier) { s->err = "nranks > 1 but no barrier callback set (laps_set_barrier)"; return 1; }
-    s->barrier(s->barrier_user);
+    if (!s->wired) { s->err = "nranks > 1 but the ranks are not connected (laps_import_peer_blobs / laps_connect_local)"; return 1; }
+    ++s->epoch;
+    LaunchScope ls(s, "xchg_barrier");
+    LAPS_LAUNCH(k_xchg_barrier, dim3(1), dim3(32), 0, s->stream, s->xp, s->epoch);
+    return check_launch(s, "k_xchg_barrier");
   }
   return 0;
 }
@@ -417,11 +432,15 @@ int stage(S* s, int irk) {
     z.task[7] = rhs_task(7, 7, 15, 1.0, 16, 1.0, X, -1.0, -1.0, 17, -1.0);
     LAPS_TRY(spec_z(s, z, 8, "spec_z"));
   }
-  if (p.if_hall) LAPS_TRY(launch_current_tasks(s, s->uB));
+  // J for the next stage's calc_flux.  After the last stage of a step in the expanding box the
+  // driver moves the radius (evolve_radius, mhd.f90:248) and with it the wave vectors J is built
+  // from (mhdrhs.f90:313-326), so that J would be discarded: leave it to refresh_current.
+  const bool want_j = p.if_hall && !(irk == 2 && s->Ur != 0.0);
+  if (want_j) LAPS_TRY(launch_current_tasks(s, s->uB));
   LAPS_TRY(host_barrier(s));
-  LAPS_TRY(inverse_yx(s, 0, p.if_hall ? 11 : 8));
+  LAPS_TRY(inverse_yx(s, 0, want_j ? 11 : 8));
   std::swap(s->uA, s->uB);
-  s->j_stale = false;
+  s->j_stale = p.if_hall && !want_j;
   return 0;
 }
 
@@ -431,6 +450,12 @@ int reduce_final(S* s, int nrows, int op /*0 sum,1 min,2 max*/, double init) {
   if (op == 1) LAPS_LAUNCH((k_reduce_final<OpMin>), dim3((unsigned)nrows), dim3(256), 0, s->stream, s->d_partial, s->nblk, s->d_scal, init);
   if (op == 2) LAPS_LAUNCH((k_reduce_final<OpMax>), dim3((unsigned)nrows), dim3(256), 0, s->stream, s->d_partial, s->nblk, s->d_scal, init);
   LAPS_TRY(check_launch(s, "k_reduce_final"));
+  if (s->P > 1) {  // mpi_allreduce (mhd.f90:419,567; mhdrms.f90:96,98,122), combined in rank order
+    if (!s->wired) { s->err = "nranks > 1 but the ranks are not connected"; return 1; }
+    ++s->epoch;
+    LAPS_LAUNCH(k_xchg_allreduce, dim3(1), dim3(32), 0, s->stream, s->xp, s->epoch, s->d_scal, nrows, op);
+    LAPS_TRY(check_launch(s, "k_xchg_allreduce"));
+  }
   LAPS_CK(s, cudaMemcpyAsync(s->h_scal, s->d_scal, nrows * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   LAPS_CK(s, cudaStreamSynchronize(s->stream));
   return 0;
@@ -481,7 +506,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
   s->w1sz = (size_t)s->nxh * s->nzl * s->ny;
   s->nf = 18 + (p.if_AEB ? 1 : 0);
   s->ni = 8 + (p.if_hall ? 3 : 0);
-  s->nblk = 148 * 8;
+  s->nblk = (int)std::min<size_t>(148 * 8, (s->npts + 255) / 256);   // grid-stride loops: 8 CTAs per SM at most
 
   // expanding box: mhd.f90:88-91, AEBmod.f90:16-31
   s->Ur = p.if_AEB ? p.Ur0 : 0.0;
@@ -511,6 +536,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
   alloc((void**)&s->d_tab, (size_t)3 * (s->nxh + s->ny + s->nz) * sizeof(double));
   alloc((void**)&s->d_partial, (size_t)32 * s->nblk * sizeof(double));
   alloc((void**)&s->d_scal, 64 * sizeof(double));
+  alloc((void**)&s->xblk, sizeof(XchgBlock));
   if (!ok) return fail("device allocation failed (state + work buffers need about " +
                        std::to_string((s->bytesX + s->bytesY + s->bytesZ + 24 * s->csz * 16 + 11 * s->npts * 8) >> 20) + " MiB)");
   if (cudaMallocHost((void**)&s->h_scal, 64 * sizeof(double)) != cudaSuccess) return fail("cudaMallocHost failed");
@@ -539,6 +565,12 @@ int laps_create(const laps_params* params, laps_handle* out) {
   }
   s->tabW2.base[s->rank] = buf_W2(s);
   s->tabV1.base[s->rank] = buf_V1(s);
+  std::memset(&s->xp, 0, sizeof(s->xp));
+  std::memset(s->ipc_opened, 0, sizeof(s->ipc_opened));
+  s->xp.rank = s->rank; s->xp.nranks = s->P;
+  s->xp.blk[s->rank] = s->xblk;
+  if (cudaMemset(s->xblk, 0, sizeof(XchgBlock)) != cudaSuccess) return fail("cudaMemset failed");
+  if (cudaStreamSynchronize(s->stream) != cudaSuccess) return fail("stream sync failed");
   *out = s;
   return 0;
 }
@@ -546,6 +578,10 @@ int laps_create(const laps_params* params, laps_handle* out) {
 int laps_destroy(laps_handle s) {
   if (!s) return 0;
   if (s->stream) cudaStreamSynchronize(s->stream);
+  for (int q = 0; q < LAPS_MAX_RANKS; ++q)
+    for (int j = 0; j < 3; ++j)
+      if (s->ipc_opened[q][j]) cudaIpcCloseMemHandle(s->ipc_opened[q][j]);
+  cudaFree(s->xblk);
   cudaFree(s->uu); cudaFree(s->J); cudaFree(s->prim); cudaFree(s->bufX); cudaFree(s->bufY); cudaFree(s->bufZ);
   cudaFree(s->uA); cudaFree(s->uB); cudaFree(s->rk); cudaFree(s->tw_x); cudaFree(s->tw_y); cudaFree(s->tw_z);
   cudaFree(s->d_tab); cudaFree(s->d_partial); cudaFree(s->d_scal);
@@ -562,12 +598,6 @@ int laps_get_extents(laps_handle s, laps_extents* e) {
   if (!s || !e) return 1;
   e->nx = s->nx; e->ny = s->ny; e->nz = s->nz; e->nxh = s->nxh;
   e->z_offset = s->zo; e->z_size = s->nzl; e->y_offset = s->yo; e->y_size = s->nyl;
-  return 0;
-}
-
-int laps_set_barrier(laps_handle s, laps_barrier_fn fn, void* user) {
-  if (!s) return 1;
-  s->barrier = fn; s->barrier_user = user;
   return 0;
 }
 
@@ -648,7 +678,6 @@ int laps_vardt(laps_handle s, double* dt_inout) {  // mhd.f90:328-429
   }
   LAPS_TRY(reduce_final(s, 1, 1, 1.0e300));
   double dtmin = s->h_scal[0];
-  // TODO(multi-rank): mpi_allreduce(min) of mhd.f90:419 goes through the collective callback
   dtmin = dtmin * p.cfl;
   double dt = *dt_inout;
   if (dt < 0.98 * dtmin || dt > 1.02 * dtmin) dt = dtmin;
@@ -857,19 +886,79 @@ int laps_transpose_yz_indexmap(laps_handle s, int64_t* out) {
   return 0;
 }
 
+namespace {
+// What a rank tells its peers about its exchange buffers (fits LAPS_PEER_BLOB_BYTES).
+struct PeerBlob {
+  uint32_t magic;
+  int32_t rank, nranks, device;
+  int64_t pid;
+  uint64_t ptr[3];                 // bufY (V1), bufZ (W2), xblk as seen by the owning process
+  cudaIpcMemHandle_t ipc[3];
+};
+static_assert(sizeof(PeerBlob) <= LAPS_PEER_BLOB_BYTES, "peer blob too large");
+constexpr uint32_t kBlobMagic = 0x4c415053u;  // "LAPS"
+}  // namespace
+
 int laps_export_peer_blob(laps_handle s, void* blob) {
   if (!s || !blob) return 1;
-  s->err = "multi-rank exchange is not wired yet in this build";
-  return 1;
+  PeerBlob b; std::memset(&b, 0, sizeof(b));
+  b.magic = kBlobMagic; b.rank = s->rank; b.nranks = s->P; b.device = s->p.device; b.pid = (int64_t)getpid();
+  void* ptrs[3] = {s->bufY, s->bufZ, (void*)s->xblk};
+  LAPS_CK(s, cudaSetDevice(s->p.device));
+  for (int j = 0; j < 3; ++j) {
+    b.ptr[j] = (uint64_t)(uintptr_t)ptrs[j];
+    LAPS_CK(s, cudaIpcGetMemHandle(&b.ipc[j], ptrs[j]));
+  }
+  std::memset(blob, 0, LAPS_PEER_BLOB_BYTES);
+  std::memcpy(blob, &b, sizeof(b));
+  return 0;
 }
+
 int laps_import_peer_blobs(laps_handle s, const void* blobs) {
   if (!s || !blobs) return 1;
-  s->err = "multi-rank exchange is not wired yet in this build";
-  return 1;
+  LAPS_CK(s, cudaSetDevice(s->p.device));
+  for (int q = 0; q < s->P; ++q) {
+    if (q == s->rank) continue;
+    PeerBlob b;
+    std::memcpy(&b, (const char*)blobs + (size_t)q * LAPS_PEER_BLOB_BYTES, sizeof(b));
+    if (b.magic != kBlobMagic || b.rank != q || b.nranks != s->P) { s->err = "laps_import_peer_blobs: blob " + std::to_string(q) + " is not rank " + std::to_string(q) + "'s export"; return 1; }
+    void* ptrs[3];
+    if (b.pid == (int64_t)getpid()) {
+      // same process (one host thread per GPU): plain peer access to the owner's allocations
+      if (b.device != s->p.device) {
+        int can = 0;
+        LAPS_CK(s, cudaDeviceCanAccessPeer(&can, s->p.device, b.device));
+        if (!can) { s->err = "no peer access between devices " + std::to_string(s->p.device) + " and " + std::to_string(b.device); return 1; }
+        cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { s->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); return 1; }
+        (void)cudaGetLastError();
+      }
+      for (int j = 0; j < 3; ++j) ptrs[j] = (void*)(uintptr_t)b.ptr[j];
+    } else {
+      for (int j = 0; j < 3; ++j) {
+        if (s->ipc_opened[q][j]) { ptrs[j] = s->ipc_opened[q][j]; continue; }
+        LAPS_CK(s, cudaIpcOpenMemHandle(&ptrs[j], b.ipc[j], cudaIpcMemLazyEnablePeerAccess));
+        s->ipc_opened[q][j] = ptrs[j];
+      }
+    }
+    s->tabV1.base[q] = (cplx*)ptrs[0];
+    s->tabW2.base[q] = (cplx*)ptrs[1];
+    s->xp.blk[q] = (XchgBlock*)ptrs[2];
+  }
+  s->wired = true;
+  return 0;
 }
+
+// Single process, one handle per GPU (each driven by its own host thread afterwards).
 int laps_connect_local(laps_handle* handles, int32_t nranks) {
-  (void)handles; (void)nranks;
-  return 1;
+  if (!handles || nranks < 1 || nranks > LAPS_MAX_RANKS) return 1;
+  std::vector<char> blobs((size_t)nranks * LAPS_PEER_BLOB_BYTES);
+  for (int q = 0; q < nranks; ++q) {
+    if (!handles[q] || handles[q]->P != nranks || handles[q]->rank != q) return 1;
+    LAPS_TRY(laps_export_peer_blob(handles[q], blobs.data() + (size_t)q * LAPS_PEER_BLOB_BYTES));
+  }
+  for (int q = 0; q < nranks; ++q) LAPS_TRY(laps_import_peer_blobs(handles[q], blobs.data()));
+  return 0;
 }
 
 }  // extern "C"

@@ -1,6 +1,15 @@
 // Fiber-based CTA executor for cuda_emu.h — TEST INFRASTRUCTURE ONLY (see header).
 #include "cuda_emu.h"
 
+#include <fcntl.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <map>
+#include <string>
+
 namespace emu {
 uint3e g_threadIdx, g_blockIdx;
 dim3 g_blockDim, g_gridDim;
@@ -27,6 +36,64 @@ void trampoline() {
   swapcontext(&g_fibers[g_cur].ctx, &g_sched);
 }
 }  // namespace
+
+// ---- shared-memory backed "device" allocations --------------------------------------------
+namespace {
+struct Region { std::string name; size_t size; bool owner; };
+std::map<void*, Region> g_regions;
+unsigned g_counter = 0;
+struct Cleanup {
+  ~Cleanup() { for (auto& kv : g_regions) if (kv.second.owner) shm_unlink(kv.second.name.c_str()); }
+} g_cleanup;
+}  // namespace
+
+void* shm_alloc(size_t n) {
+  char name[64];
+  std::snprintf(name, sizeof(name), "/laps_emu_%d_%u", (int)getpid(), g_counter++);
+  int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+  if (fd < 0) return nullptr;
+  if (ftruncate(fd, (off_t)n) != 0) { close(fd); shm_unlink(name); return nullptr; }
+  void* p = mmap(nullptr, n, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) { shm_unlink(name); return nullptr; }
+  g_regions[p] = Region{name, n, true};
+  return p;   // fresh shared memory is zero-filled, like the calloc it replaces
+}
+
+void shm_free(void* p) {
+  if (!p) return;
+  auto it = g_regions.find(p);
+  if (it == g_regions.end()) return;
+  munmap(p, it->second.size);
+  if (it->second.owner) shm_unlink(it->second.name.c_str());
+  g_regions.erase(it);
+}
+
+int shm_export(void* p, char name_out[64]) {
+  auto it = g_regions.find(p);
+  if (it == g_regions.end()) return 1;
+  std::memset(name_out, 0, 64);
+  std::snprintf(name_out, 48, "%s", it->second.name.c_str());
+  unsigned long long sz = it->second.size;
+  std::memcpy(name_out + 48, &sz, 8);
+  return 0;
+}
+
+void* shm_import(const char name[64]) {
+  unsigned long long sz = 0;
+  std::memcpy(&sz, name + 48, 8);
+  int fd = shm_open(name, O_RDWR, 0600);
+  if (fd < 0) return nullptr;
+  void* p = mmap(nullptr, (size_t)sz, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) return nullptr;
+  g_regions[p] = Region{std::string(name), (size_t)sz, false};
+  return p;
+}
+
+void shm_unmap(void* p) { shm_free(p); }
+
+void spin_pause() { sched_yield(); }
 
 void yield_barrier() {
   int me = g_cur;

@@ -45,6 +45,14 @@ void yield_barrier();
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
 extern double g_shfl_scratch[2048];
 extern unsigned long long g_shfl_scratch_u[2048];
+// "device" memory is POSIX shared memory so that another emulator PROCESS (a second rank of a
+// gloo test) can map it through the cudaIpc* stand-ins below.
+void* shm_alloc(size_t n);
+void shm_free(void* p);
+int shm_export(void* p, char name_out[64]);
+void* shm_import(const char name[64]);
+void shm_unmap(void* p);
+void spin_pause();
 }  // namespace emu
 
 #define threadIdx (emu::g_threadIdx)
@@ -105,14 +113,21 @@ static inline double fmin_(double a, double b) { return a < b ? a : b; }
 typedef int cudaError_t;
 typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
-enum { cudaSuccess = 0 };
+enum { cudaSuccess = 0, cudaErrorPeerAccessAlreadyEnabled = 704 };
+struct cudaIpcMemHandle_t { char reserved[64]; };
+#define cudaIpcMemLazyEnablePeerAccess 1
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
 static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 static inline cudaError_t cudaGetLastError() { return 0; }
-static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = std::calloc(n ? n : 1, 1); return *p ? 0 : 2; }
+static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = emu::shm_alloc(n ? n : 1); return *p ? 0 : 2; }
 template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
-static inline cudaError_t cudaFree(void* p) { std::free(p); return 0; }
+static inline cudaError_t cudaFree(void* p) { emu::shm_free(p); return 0; }
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { return emu::shm_export(p, h->reserved); }
+static inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { *p = emu::shm_import(h.reserved); return *p ? 0 : 2; }
+static inline cudaError_t cudaIpcCloseMemHandle(void* p) { emu::shm_unmap(p); return 0; }
+static inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 1; return 0; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return 0; }
 static inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = std::calloc(n ? n : 1, 1); return *p ? 0 : 2; }
 template <class T> static inline cudaError_t cudaMallocHost(T** p, size_t n) { return cudaMallocHost((void**)p, n); }
 static inline cudaError_t cudaFreeHost(void* p) { std::free(p); return 0; }
