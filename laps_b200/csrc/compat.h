@@ -35,4 +35,20 @@ LAPS_HD cplx cscale(cplx a, double s) { return mk(a.x * s, a.y * s); }
 // multiply by i*s (s real): (x + i y) * (i s) = -s y + i s x
 LAPS_HD cplx cmul_i(cplx a, double s) { return mk(-s * a.y, s * a.x); }
 
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256): two adjacent complex128 values, 32-byte aligned.
+LAPS_D void ld256(const cplx* p, cplx& a, cplx& b) {
+#ifdef LAPS_EMU_BUILD
+  a = p[0]; b = p[1];
+#else
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+#endif
+}
+LAPS_D void st256(cplx* p, cplx a, cplx b) {
+#ifdef LAPS_EMU_BUILD
+  p[0] = a; p[1] = b;
+#else
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+#endif
+}
+
 }  // namespace laps

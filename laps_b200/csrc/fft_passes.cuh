@@ -39,6 +39,10 @@ struct Tile {
   static constexpr int PITCH = G::pitch(TL >= 8 ? 1 : (TL == 4 ? 2 : (TL == 2 ? 4 : 0)));
   static constexpr int NTHREADS = TL * G::NT;
   static constexpr size_t SMEM = (size_t)TL * PITCH * sizeof(cplx);
+  // resident CTAs per SM to compile for: what shared memory allows, but never below 64 registers
+  static constexpr int BY_SMEM = (int)((227 * 1024) / (SMEM + 1024));
+  static constexpr int BY_REGS = 65536 / (NTHREADS * 64);
+  static constexpr int MINB = BY_SMEM < BY_REGS ? (BY_SMEM < 1 ? 1 : BY_SMEM) : (BY_REGS < 1 ? 1 : BY_REGS);
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -46,7 +50,7 @@ struct Tile {
 // (replaces the r2c loops fftw.f90:58-64 / mhdrhs.f90:143-149, including the "/nx").
 // grid.x = nzl * (ny / (2*TL)), grid.y = number of fields
 template <int N, int TL>
-__global__ void __launch_bounds__(Tile<N, TL>::NTHREADS)
+__global__ void __launch_bounds__(Tile<N, TL>::NTHREADS, Tile<N, TL>::MINB)
 k_fwd_x(const double* __restrict__ in, size_t in_fstride, cplx* __restrict__ W1,
         int nzl, int ny, const cplx* __restrict__ tw, double scale) {
   typedef Geom<N> G;
@@ -73,17 +77,22 @@ k_fwd_x(const double* __restrict__ in, size_t in_fstride, cplx* __restrict__ W1,
   LAPS_UNROLL
   for (int e = 0; e < 8; ++e) line[G::pad(F::kout(u, e))] = r[e];
   __syncthreads();
-  // split Z = A + iB into the two half spectra; TL line-pairs side by side give 2*TL*16-byte chunks
+  // split Z = A + iB into the two half spectra; TL line-pairs side by side give 2*TL*16-byte chunks,
+  // each thread storing its (a, b) pair as one 256-bit access
   const double hs = 0.5 * scale;
-  for (int it = tid; it < nxh * TL; it += T::NTHREADS) {
-    const int lp = it % TL, k = it / TL;
-    const cplx zk = sm[lp * T::PITCH + G::pad(k)];
-    const cplx zn = sm[lp * T::PITCH + G::pad((N - k) & (N - 1))];
-    cplx a = mk((zk.x + zn.x) * hs, (zk.y - zn.y) * hs);
-    cplx b = mk((zk.y + zn.y) * hs, (zn.x - zk.x) * hs);
-    cplx* dst = W1 + (((size_t)f * nxh + k) * nzl + zl) * ny + y0 + 2 * lp;
-    dst[0] = a;
-    dst[1] = b;
+  constexpr int TOT = (N / 2 + 1) * TL;
+  constexpr int ITERS = (TOT + T::NTHREADS - 1) / T::NTHREADS;
+  LAPS_UNROLL
+  for (int i = 0; i < ITERS; ++i) {
+    const int it = tid + i * T::NTHREADS;
+    if (it < TOT) {
+      const int lp = it % TL, k = it / TL;
+      const cplx zk = sm[lp * T::PITCH + G::pad(k)];
+      const cplx zn = sm[lp * T::PITCH + G::pad((N - k) & (N - 1))];
+      const cplx a = mk((zk.x + zn.x) * hs, (zk.y - zn.y) * hs);
+      const cplx b = mk((zk.y + zn.y) * hs, (zn.x - zk.x) * hs);
+      st256(W1 + (((size_t)f * nxh + k) * nzl + zl) * ny + y0 + 2 * lp, a, b);
+    }
   }
 }
 
@@ -92,7 +101,7 @@ k_fwd_x(const double* __restrict__ in, size_t in_fstride, cplx* __restrict__ W1,
 // (fftw.f90:156-162 incl. "/ny", fused with transpose_yz parallel.f90:273-297).
 // grid.x = ceil(nzl/TL) * nxh, grid.y = fields
 template <int N, int TL>
-__global__ void __launch_bounds__(Tile<N, TL>::NTHREADS)
+__global__ void __launch_bounds__(Tile<N, TL>::NTHREADS, Tile<N, TL>::MINB)
 k_fwd_y(const cplx* __restrict__ W1, PeerTable W2, int nzl, int nz, int zoff,
         const cplx* __restrict__ tw, double scale) {
   typedef Geom<N> G;
@@ -136,7 +145,7 @@ k_fwd_y(const cplx* __restrict__ W1, PeerTable W2, int nzl, int nz, int zoff,
 // inverse y: V1 [g][kx][ky][zl] (z fastest) -> contiguous y-lines V2 [g][kx][zl][y]
 // (fftw.f90:212-218, unnormalised).  grid.x = ceil(nzl/TL) * nxh, grid.y = fields
 template <int N, int TL>
-__global__ void __launch_bounds__(Tile<N, TL>::NTHREADS)
+__global__ void __launch_bounds__(Tile<N, TL>::NTHREADS, Tile<N, TL>::MINB)
 k_inv_y(const cplx* __restrict__ V1, cplx* __restrict__ V2, int nzl, const cplx* __restrict__ tw) {
   typedef Geom<N> G;
   typedef Fft<N, +1> F;
@@ -178,7 +187,7 @@ k_inv_y(const cplx* __restrict__ V1, cplx* __restrict__ V2, int nzl, const cplx*
 struct RealDst { double* ptr[16]; };
 
 template <int N, int TL>
-__global__ void __launch_bounds__(Tile<N, TL>::NTHREADS)
+__global__ void __launch_bounds__(Tile<N, TL>::NTHREADS, Tile<N, TL>::MINB)
 k_inv_x(const cplx* __restrict__ V2, RealDst dst, int nzl, int ny, const cplx* __restrict__ tw) {
   typedef Geom<N> G;
   typedef Fft<N, +1> F;
@@ -190,13 +199,29 @@ k_inv_x(const cplx* __restrict__ V2, RealDst dst, int nzl, int ny, const cplx* _
   const int y0 = (blockIdx.x % ytiles) * 2 * TL;
   const int g = blockIdx.y;
   const int nxh = N / 2 + 1;
-  for (int it = tid; it < nxh * TL; it += T::NTHREADS) {
-    const int lp = it % TL, k = it / TL;
-    const cplx* src = V2 + (((size_t)g * nxh + k) * nzl + zl) * ny + y0 + 2 * lp;
-    cplx a = src[0], b = src[1];
-    if (k == 0 || k == N / 2) { a.y = 0.0; b.y = 0.0; }
-    sm[lp * T::PITCH + G::pad(k)] = mk(a.x - b.y, a.y + b.x);
-    if (k != 0 && k != N / 2) sm[lp * T::PITCH + G::pad(N - k)] = mk(a.x + b.y, b.x - a.y);
+  {  // all loads of the tile in flight before the first use (256-bit: the pair of lines of one kx)
+    constexpr int TOT = (N / 2 + 1) * TL;
+    constexpr int ITERS = (TOT + T::NTHREADS - 1) / T::NTHREADS;
+    cplx a[ITERS], b[ITERS];
+    LAPS_UNROLL
+    for (int i = 0; i < ITERS; ++i) {
+      const int it = tid + i * T::NTHREADS;
+      if (it < TOT) {
+        const int lp = it % TL, k = it / TL;
+        ld256(V2 + (((size_t)g * nxh + k) * nzl + zl) * ny + y0 + 2 * lp, a[i], b[i]);
+      }
+    }
+    LAPS_UNROLL
+    for (int i = 0; i < ITERS; ++i) {
+      const int it = tid + i * T::NTHREADS;
+      if (it < TOT) {
+        const int lp = it % TL, k = it / TL;
+        cplx av = a[i], bv = b[i];
+        if (k == 0 || k == N / 2) { av.y = 0.0; bv.y = 0.0; }
+        sm[lp * T::PITCH + G::pad(k)] = mk(av.x - bv.y, av.y + bv.x);
+        if (k != 0 && k != N / 2) sm[lp * T::PITCH + G::pad(N - k)] = mk(av.x + bv.y, bv.x - av.y);
+      }
+    }
   }
   __syncthreads();
   const int l = tid / G::NT, u = tid % G::NT;

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -41,7 +42,7 @@ constexpr int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi 
 constexpr int cap_threads(int t, int nt) { return t * nt > 1024 ? 1024 / nt : t; }
 constexpr int tlx(int N) { return cap_threads(clampi(256 / (N / 8), 4, 8), N / 8); }   // complex lines per x-pass CTA
 constexpr int tly(int N) { return cap_threads(clampi(512 / (N / 8), 4, 8), N / 8); }   // lines per y-pass CTA
-constexpr int cgz(int N) { return clampi(256 / (N / 8), 1, 32); }                      // columns per z-pass CTA
+constexpr int cgz(int N) { return clampi(128 / (N / 8), 1, 32); }                      // columns per z-pass CTA
 
 #define LAPS_FOR_SIZES(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048)
 
@@ -102,6 +103,8 @@ struct laps_solver {
   XchgPeers xp;
   unsigned long long epoch = 0;
   bool wired = false;
+  int tune_cgz = 0, tune_z = 3;
+  double da_thresh = 0;
   void* ipc_opened[LAPS_MAX_RANKS][3];   // mappings obtained with cudaIpcOpenMemHandle
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -221,13 +224,25 @@ int check_launch(S* s, const char* what) {
 }
 
 // ---- pass launchers ---------------------------------------------------------------------------
+// Opt in to the large dynamic shared memory size and ask for exactly the shared-memory carve-out
+// that `ctas` resident CTAs need: the rest of the 256 KB stays L1, which the strided sides of the
+// passes rely on (measured: the maximum carve-out costs the y passes 25 % of their bandwidth, the
+// default heuristic leaves the x and z passes one CTA short).
+template <class K>
+cudaError_t prepare_kernel(K kernel, size_t smem, int ctas) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int pct = (int)((ctas * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+  if (pct > 100) pct = 100;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
 template <int N>
 int do_fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1) {
   char name[32]; std::snprintf(name, sizeof(name), "fwd_x%d", nfields);
   constexpr int TL = tlx(N);
   typedef Tile<N, TL> T;
   if (s->ny % (2 * TL) != 0) { s->err = "ny must be a multiple of " + std::to_string(2 * TL); return 1; }
-  LAPS_CK(s, cudaFuncSetAttribute(k_fwd_x<N, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
+  LAPS_CK(s, prepare_kernel(k_fwd_x<N, TL>, T::SMEM, T::MINB));
   LaunchScope ls(s, name);
   dim3 grid((unsigned)(s->nzl * (s->ny / (2 * TL))), (unsigned)nfields);
   LAPS_LAUNCH((k_fwd_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, in, fstride, W1, s->nzl, s->ny, s->tw_x,
@@ -240,7 +255,7 @@ int do_fwd_y(S* s, const cplx* W1, int nfields) {
   char name[32]; std::snprintf(name, sizeof(name), "fwd_y%d", nfields);
   constexpr int TL = tly(N);
   typedef Tile<N, TL> T;
-  LAPS_CK(s, cudaFuncSetAttribute(k_fwd_y<N, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
+  LAPS_CK(s, prepare_kernel(k_fwd_y<N, TL>, T::SMEM, T::MINB));
   LaunchScope ls(s, name);
   const int ztiles = (s->nzl + TL - 1) / TL;
   dim3 grid((unsigned)(ztiles * s->nxh), (unsigned)nfields);
@@ -254,7 +269,7 @@ int do_inv_y(S* s, const cplx* V1, cplx* V2, int nfields) {
   char name[32]; std::snprintf(name, sizeof(name), "inv_y%d", nfields);
   constexpr int TL = tly(N);
   typedef Tile<N, TL> T;
-  LAPS_CK(s, cudaFuncSetAttribute(k_inv_y<N, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
+  LAPS_CK(s, prepare_kernel(k_inv_y<N, TL>, T::SMEM, T::MINB));
   LaunchScope ls(s, name);
   const int ztiles = (s->nzl + TL - 1) / TL;
   dim3 grid((unsigned)(ztiles * s->nxh), (unsigned)nfields);
@@ -267,22 +282,30 @@ int do_inv_x(S* s, const cplx* V2, const RealDst& dst, int nfields) {
   char name[32]; std::snprintf(name, sizeof(name), "inv_x%d", nfields);
   constexpr int TL = tlx(N);
   typedef Tile<N, TL> T;
-  LAPS_CK(s, cudaFuncSetAttribute(k_inv_x<N, TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
+  LAPS_CK(s, prepare_kernel(k_inv_x<N, TL>, T::SMEM, T::MINB));
   LaunchScope ls(s, name);
   dim3 grid((unsigned)(s->nzl * (s->ny / (2 * TL))), (unsigned)nfields);
   LAPS_LAUNCH((k_inv_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, V2, dst, s->nzl, s->ny, s->tw_x);
   return check_launch(s, "k_inv_x");
 }
 
-template <int N>
-int do_spec_z(S* s, const ZParams& zp, int ntasks, const char* name) {
-  constexpr int CG = cgz(N);
+template <int N, int CG>
+int do_spec_z_cg(S* s, const ZParams& zp, int ntasks, const char* name) {
   typedef ZTile<N, CG> T;
-  LAPS_CK(s, cudaFuncSetAttribute(k_spec_z<N, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM));
+  LAPS_CK(s, prepare_kernel(k_spec_z<N, CG>, T::SMEM, T::MINB));
   LaunchScope ls(s, name);
   dim3 grid((unsigned)((s->ncol + CG - 1) / CG), (unsigned)ntasks);
   LAPS_LAUNCH((k_spec_z<N, CG>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, zp);
   return check_launch(s, "k_spec_z");
+}
+
+template <int N>
+int do_spec_z(S* s, const ZParams& zp, int ntasks, const char* name) {
+  if constexpr (N == 512) {  // tuning knob for the benchmark grid (columns per CTA)
+    if (s->tune_cgz == 1) return do_spec_z_cg<N, 1>(s, zp, ntasks, name);
+    if (s->tune_cgz == 4) return do_spec_z_cg<N, 4>(s, zp, ntasks, name);
+  }
+  return do_spec_z_cg<N, cgz(N)>(s, zp, ntasks, name);
 }
 
 #define LAPS_DISPATCH(n, fn, ...)                                   \
@@ -335,6 +358,8 @@ void fill_zparams(S* s, ZParams& z) {
   z.nu = p.viscosity; z.eta = p.resistivity;
   z.dealias_option = p.dealias_option;
   z.scale = 1.0 / s->nz;
+  z.da_thresh = s->da_thresh;
+  z.tune = s->tune_z;
 }
 
 ZTask rhs_task(int v, int gout, int fa, double ca, int fb, double cb, int fx, double cx, double sg, int fc, double sc) {
@@ -506,6 +531,16 @@ int laps_create(const laps_params* params, laps_handle* out) {
   s->w1sz = (size_t)s->nxh * s->nzl * s->ny;
   s->nf = 18 + (p.if_AEB ? 1 : 0);
   s->ni = 8 + (p.if_hall ? 3 : 0);
+  {  // the mask test "sqrt(s) > 1./3." (dealiasing.f90:94) as a threshold on s: sqrt is correctly rounded
+     // and monotonic, so { s : sqrt(s) > c } = { s >= T } with T the smallest double that passes
+    const double c = 1.0 / 3.0;
+    double t = c * c;
+    while (std::sqrt(t) > c) t = std::nextafter(t, 0.0);
+    while (!(std::sqrt(t) > c)) t = std::nextafter(t, 1.0);
+    s->da_thresh = t;
+  }
+  if (const char* e = std::getenv("LAPS_TUNE_CGZ")) s->tune_cgz = std::atoi(e);
+  if (const char* e = std::getenv("LAPS_TUNE_Z")) s->tune_z = std::atoi(e);
   s->nblk = (int)std::min<size_t>(148 * 8, (s->npts + 255) / 256);   // grid-stride loops: 8 CTAs per SM at most
 
   // expanding box: mhd.f90:88-91, AEBmod.f90:16-31

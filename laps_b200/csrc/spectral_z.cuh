@@ -63,16 +63,34 @@ struct ZParams {
   int dealias_option;
   int read_rk, write_rk;
   double scale;          // 1/nz
+  double da_thresh;      // dealias option 1: smallest s with sqrt(s) > 1./3. (dealiasing.f90:94)
+  int tune;              // bit 0: L2-prefetch state/history lines, bit 1: L2-prefetch the G inputs
   ZTask task[12];
 };
 
+// Shared memory per column: one padded work line (the FFT exchanges) and one unpadded stash line
+// holding the (i kz)-term between the two forward transforms, so that a thread never keeps more
+// than one set of 8 points in registers (occupancy: the kernel is latency-bound otherwise).
 template <int N, int CG>
 struct ZTile {
   typedef Geom<N> G;
   static constexpr int PITCH = G::pitch(1);
   static constexpr int NTHREADS = CG * G::NT;
-  static constexpr size_t SMEM = (size_t)2 * CG * PITCH * sizeof(cplx);
+  static constexpr int COLSTRIDE = PITCH + N;
+  static constexpr size_t SMEM = (size_t)CG * COLSTRIDE * sizeof(cplx);
+  // resident CTAs per SM to compile for: what shared memory allows, but never below 80 registers
+  static constexpr int BY_SMEM = (int)((227 * 1024) / (SMEM + 1024));
+  static constexpr int BY_REGS = 65536 / (NTHREADS * 80);
+  static constexpr int MINB = BY_SMEM < BY_REGS ? (BY_SMEM < 1 ? 1 : BY_SMEM) : (BY_REGS < 1 ? 1 : BY_REGS);
 };
+
+LAPS_D void prefetch_l2(const void* p) {
+#ifndef LAPS_EMU_BUILD
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
 
 // k_square(ix,iy,iz) exactly as update_ksquare / grid_initialize evaluate it.
 LAPS_D double ksq_eval(const ZParams& P, double kxr, double kyr, int kx, int ky, int kz) {
@@ -90,7 +108,7 @@ LAPS_D double ksq_eval(const ZParams& P, double kxr, double kyr, int kx, int ky,
 }
 
 template <int N, int CG>
-__global__ void __launch_bounds__(ZTile<N, CG>::NTHREADS)
+__global__ void __launch_bounds__(ZTile<N, CG>::NTHREADS, ZTile<N, CG>::MINB)
 k_spec_z(const ZParams P) {
   typedef Geom<N> G;
   typedef Fft<N, -1> FF;
@@ -104,8 +122,8 @@ k_spec_z(const ZParams P) {
   const bool live = col < P.ncol;
   const int kx = live ? col / P.nyl : 0;
   const int ky = live ? P.yoff + col % P.nyl : 0;
-  cplx* lineG = sm + (2 * l) * T::PITCH;
-  cplx* lineC = lineG + T::PITCH;
+  cplx* lineG = sm + l * T::COLSTRIDE;
+  cplx* stash = lineG + T::PITCH;          // thread-private slots e*NT + u
   const size_t coff = (size_t)col * N;
 
   // derivative vectors (imaginary parts), mhdrhs.f90:191-204
@@ -118,7 +136,39 @@ k_spec_z(const ZParams P) {
 
   cplx r[8];
   if (K.kind == kZRhs || K.kind == kZForwardOnly) {
-    // ---------------- forward z of G (and of C) ----------------
+    const bool hasC = K.fc >= 0;
+    const size_t voff = (size_t)K.v * P.fstride + coff;
+    if (K.kind == kZRhs && live) {
+      // Lines needed by the later phases of this CTA are pulled into L2 now (no registers held), so
+      // that their DRAM latency overlaps the first transform instead of being exposed phase by phase.
+      const size_t po = coff + (size_t)u * (N / G::NT);
+      if (P.tune & 1) {
+        prefetch_l2(P.u_in + (size_t)K.v * P.fstride + po);
+        if (P.read_rk) prefetch_l2(P.fnl_rk + (size_t)K.v * P.fstride + po);
+      }
+      if ((P.tune & 2) && hasC) {
+        if (K.fa >= 0) prefetch_l2(P.W2 + (size_t)K.fa * P.fstride + po);
+        if (K.fb >= 0) prefetch_l2(P.W2 + (size_t)K.fb * P.fstride + po);
+        if (K.fx >= 0) prefetch_l2(P.W2 + (size_t)K.fx * P.fstride + po);
+      }
+    }
+    // ---------------- forward z of the (i kz) term, kept in the stash ----------------
+    if (hasC) {
+      LAPS_UNROLL
+      for (int e = 0; e < 8; ++e) r[e] = mk(0.0, 0.0);
+      if (live) {
+        const cplx* s = P.W2 + (size_t)K.fc * P.fstride + coff;
+        LAPS_UNROLL
+        for (int e = 0; e < 8; ++e) r[e] = s[u + e * G::NT];
+      }
+      FF::first(r, u, lineG, P.tw);
+      FF::finish(r, u, lineG, P.tw);
+      const double cs = K.sc * P.scale;
+      LAPS_UNROLL
+      for (int e = 0; e < 8; ++e) stash[e * G::NT + u] = cmul_i(r[e], cs * __ldg(P.kze + FF::kout(u, e)));
+      __syncthreads();  // every last-stage read of the work line is done before it is refilled
+    }
+    // ---------------- forward z of G ----------------
     LAPS_UNROLL
     for (int e = 0; e < 8; ++e) r[e] = mk(0.0, 0.0);
     if (live) {
@@ -144,58 +194,44 @@ k_spec_z(const ZParams P) {
       }
     }
     FF::first(r, u, lineG, P.tw);
-    const bool hasC = K.fc >= 0;
-    cplx rc[8];
-    if (hasC) {
-      LAPS_UNROLL
-      for (int e = 0; e < 8; ++e) rc[e] = mk(0.0, 0.0);
-      if (live) {
-        const cplx* s = P.W2 + (size_t)K.fc * P.fstride + coff;
-        LAPS_UNROLL
-        for (int e = 0; e < 8; ++e) rc[e] = s[u + e * G::NT];
-      }
-      FF::first(rc, u, lineC, P.tw);
-    }
-    __syncthreads();
-    if constexpr (G::NSTAGE >= 3) {
-      FF::template middle<1>(u, lineG, P.tw);
-      if (hasC) FF::template middle<1>(u, lineC, P.tw);
-      __syncthreads();
-    }
-    if constexpr (G::NSTAGE >= 4) {
-      FF::template middle<2>(u, lineG, P.tw);
-      if (hasC) FF::template middle<2>(u, lineC, P.tw);
-      __syncthreads();
-    }
-    FF::last(r, u, lineG);
-    if (hasC) FF::last(rc, u, lineC);
+    FF::finish(r, u, lineG, P.tw);
 
     // ---------------- spectral update on the 8 modes this thread holds ----------------
-    const size_t voff = (size_t)K.v * P.fstride + coff;
+    if (K.kind == kZForwardOnly) {
+      if (live) {
+        LAPS_UNROLL
+        for (int e = 0; e < 8; ++e) P.u_out[voff + FF::kout(u, e)] = cscale(r[e], P.scale);
+      }
+      return;
+    }
+    // Task-uniform coefficients first, so that the per-mode code below is straight-line arithmetic
+    // the compiler can interleave across the 8 modes (a zero coefficient switches a term off).
+    // Divisions by a common divisor become multiplications by its reciprocal, and the mask test
+    // sqrt(s) > 1/3 becomes s >= P.da_thresh with the host-computed smallest s that passes it
+    // (bit-identical decisions, see upload_tables).
+    const double sgs = K.sg * P.scale;
+    const double ca = (P.aeb && K.aeb_c != 0.0) ? K.aeb_c / P.tau : 0.0;                       // mhdrhs.f90:235-247
+    const double ce = (K.diff == 1 && P.visc_exp) ? P.nu : ((K.diff == 2 && P.resis_exp) ? P.eta : 0.0);   // :253-275
+    const double ci = (K.diff == 1 && P.visc_imp) ? P.nu : ((K.diff == 2 && P.resis_imp) ? P.eta : 0.0);   // rktmod.f90:47-60
+    const bool need_ksq = (ce != 0.0) || (ci != 0.0);
+    const bool keep_bg = K.diff == 2 && P.conserve_bg && kx == 0;   // "ix==1 .and. iz==1" skip of mhdrhs.f90:262-270
+    const double dxy = (P.dealias_option == 1) ? __dadd_rn(__ldg(P.dax + kx), __ldg(P.day + ky))
+                                               : ((P.dealias_option == 2) ? __ldg(P.dax + kx) : 0.0);
+    const double dfy = (P.dealias_option == 2) ? __ldg(P.day + ky) : 0.0;
     LAPS_UNROLL
     for (int e = 0; e < 8; ++e) {
       const int kz = FF::kout(u, e);
-      if (K.kind == kZForwardOnly) {
-        r[e] = cscale(r[e], P.scale);
-        if (live) P.u_out[voff + kz] = r[e];
-        continue;
-      }
-      cplx fnl = cscale(r[e], K.sg * P.scale);
-      if (hasC) fnl = cadd(fnl, cmul_i(rc[e], K.sc * P.scale * __ldg(P.kze + kz)));
+      cplx fnl = cscale(r[e], sgs);
+      if (hasC) fnl = cadd(fnl, stash[e * G::NT + u]);
       const cplx uo = live ? P.u_in[voff + kz] : mk(0.0, 0.0);
-      if (P.aeb && K.aeb_c != 0.0) {
-        fnl.x -= __ddiv_rn(__dmul_rn(K.aeb_c, uo.x), P.tau);
-        fnl.y -= __ddiv_rn(__dmul_rn(K.aeb_c, uo.y), P.tau);
-      }
+      fnl.x -= ca * uo.x;
+      fnl.y -= ca * uo.y;
       double ksq = 0.0;
-      if (K.diff) ksq = ksq_eval(P, kxr, kyr, kx, ky, kz);
-      if (K.diff == 1 && P.visc_exp) {
-        fnl.x -= (P.nu * uo.x) * ksq;
-        fnl.y -= (P.nu * uo.y) * ksq;
-      }
-      if (K.diff == 2 && P.resis_exp && !(P.conserve_bg && kx == 0 && kz == 0)) {
-        fnl.x -= (P.eta * uo.x) * ksq;
-        fnl.y -= (P.eta * uo.y) * ksq;
+      if (need_ksq) {
+        ksq = ksq_eval(P, kxr, kyr, kx, ky, kz);
+        const double cee = (keep_bg && kz == 0) ? 0.0 : ce;
+        fnl.x -= (cee * uo.x) * ksq;
+        fnl.y -= (cee * uo.y) * ksq;
       }
       // rkt (rktmod.f90:40-42): u = cc*fnl + dd*fnl_rk + u ; fnl_rk = fnl
       cplx un;
@@ -206,20 +242,17 @@ k_spec_z(const ZParams P) {
         un = mk(P.cc * fnl.x + uo.x, P.cc * fnl.y + uo.y);
       }
       if (P.write_rk && live) P.fnl_rk[voff + kz] = fnl;
-      // implicit diffusion (rktmod.f90:47-60)
-      if ((K.diff == 1 && P.visc_imp) || (K.diff == 2 && P.resis_imp)) {
-        const double coef = (K.diff == 1) ? P.nu : P.eta;
-        const double den = __dadd_rn(__dmul_rn(__dmul_rn(P.dt_irk, ksq), coef), 1.0);
-        un.x = __ddiv_rn(un.x, den);
-        un.y = __ddiv_rn(un.y, den);
+      if (need_ksq) {  // implicit diffusion (rktmod.f90:47-60); ci == 0 gives exactly 1
+        const double inv = __drcp_rn(__dadd_rn(__dmul_rn(__dmul_rn(P.dt_irk, ksq), ci), 1.0));
+        un.x *= inv;
+        un.y *= inv;
       }
       // dealias (dealiasing.f90:87-110)
       if (P.dealias_option == 1) {
-        const double rad = __dsqrt_rn(__dadd_rn(__dadd_rn(__ldg(P.dax + kx), __ldg(P.day + ky)), __ldg(P.daz + kz)));
-        if (rad > (1.0 / 3.0)) un = mk(0.0, 0.0);
+        if (__dadd_rn(dxy, __ldg(P.daz + kz)) >= P.da_thresh) un = mk(0.0, 0.0);
       } else if (P.dealias_option == 2) {
-        const double fx = __ldg(P.dax + kx), fy = __ldg(P.day + ky), fz = __ldg(P.daz + kz);
-        un = mk(__dmul_rn(__dmul_rn(__dmul_rn(un.x, fx), fy), fz), __dmul_rn(__dmul_rn(__dmul_rn(un.y, fx), fy), fz));
+        const double fz = __ldg(P.daz + kz);
+        un = mk(__dmul_rn(__dmul_rn(__dmul_rn(un.x, dxy), dfy), fz), __dmul_rn(__dmul_rn(__dmul_rn(un.y, dxy), dfy), fz));
       }
       if (live) P.u_out[voff + kz] = un;
       r[e] = un;

@@ -70,6 +70,7 @@ static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dsqrt_rn(double a) { return std::sqrt(a); }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline double __drcp_rn(double a) { return 1.0 / a; }
 static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
 static inline long long __double_as_longlong(double d) { long long v; std::memcpy(&v, &d, 8); return v; }
 
@@ -117,7 +118,7 @@ enum { cudaSuccess = 0, cudaErrorPeerAccessAlreadyEnabled = 704 };
 struct cudaIpcMemHandle_t { char reserved[64]; };
 #define cudaIpcMemLazyEnablePeerAccess 1
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
-enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize, cudaFuncAttributePreferredSharedMemoryCarveout };
 static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 static inline cudaError_t cudaGetLastError() { return 0; }
 static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = emu::shm_alloc(n ? n : 1); return *p ? 0 : 2; }
