@@ -51,4 +51,27 @@ LAPS_D void st256(cplx* p, cplx a, cplx b) {
 #endif
 }
 
+// Asynchronous 16-byte global -> shared copies (LDGSTS, L2-only caching).  Used with THREAD-PRIVATE
+// landing slots: the thread that issues a copy is the only one that reads the slot, so
+// cp_async_wait<>() is the only synchronisation needed.
+LAPS_D void cp_async16(void* smem_dst, const void* gsrc) {
+#ifdef LAPS_EMU_BUILD
+  *reinterpret_cast<cplx*>(smem_dst) = *reinterpret_cast<const cplx*>(gsrc);
+#else
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+#endif
+}
+LAPS_D void cp_async_commit() {
+#ifndef LAPS_EMU_BUILD
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int PENDING>
+LAPS_D void cp_async_wait() {   // at most PENDING of this thread's most recent groups still in flight
+#ifndef LAPS_EMU_BUILD
+  asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+#endif
+}
+
 }  // namespace laps

@@ -108,17 +108,29 @@ struct Fft {
     return w;
   }
 
+  // The base twiddle a thread needs in stage S depends only on its position u in the line, so a
+  // persistent kernel can fetch it once (tw_stage) and pass it to the *_w variants below.
+  template <int S>
+  LAPS_D static cplx tw_stage(const cplx* __restrict__ tw, int u) {
+    if (S == 0) return twid(tw, u);                       // v_0 = 1, j' = u
+    constexpr int ws = G::w(S);
+    return twid(tw, G::v(S) * (u & (ws - 1)));
+  }
+
   // Stage 0.  r[e] = x[u + e*N/8] on entry.  Leaves the twiddled outputs in the smem line.
-  LAPS_D static void first(cplx (&r)[8], int u, cplx* __restrict__ line, const cplx* __restrict__ tw) {
+  LAPS_D static void first_w(cplx (&r)[8], int u, cplx* __restrict__ line, cplx w) {
     bfly8<DIR>(r);
-    twiddle8(r, twid(tw, u));  // v_0 = 1, j' = u
+    twiddle8(r, w);
     LAPS_UNROLL
     for (int e = 0; e < 8; ++e) line[G::pad(u + e * G::w(0))] = r[e];
+  }
+  LAPS_D static void first(cplx (&r)[8], int u, cplx* __restrict__ line, const cplx* __restrict__ tw) {
+    first_w(r, u, line, tw_stage<0>(tw, u));
   }
 
   // Middle stage S (1 <= S < NSTAGE-1), in place.
   template <int S>
-  LAPS_D static void middle(int u, cplx* __restrict__ line, const cplx* __restrict__ tw) {
+  LAPS_D static void middle_w(int u, cplx* __restrict__ line, cplx w) {
     constexpr int ws = G::w(S);
     const int jp = u & (ws - 1);
     const int base = (u / ws) * (8 * ws) + jp;
@@ -126,9 +138,13 @@ struct Fft {
     LAPS_UNROLL
     for (int e = 0; e < 8; ++e) r[e] = line[G::pad(base + e * ws)];
     bfly8<DIR>(r);
-    twiddle8(r, twid(tw, G::v(S) * jp));
+    twiddle8(r, w);
     LAPS_UNROLL
     for (int e = 0; e < 8; ++e) line[G::pad(base + e * ws)] = r[e];
+  }
+  template <int S>
+  LAPS_D static void middle(int u, cplx* __restrict__ line, const cplx* __restrict__ tw) {
+    middle_w<S>(u, line, tw_stage<S>(tw, u));
   }
 
   // Base position (8 consecutive slots base..base+7) read by thread u in the last stage.
@@ -182,6 +198,12 @@ struct Fft {
     __syncthreads();
     if constexpr (G::NSTAGE >= 3) { middle<1>(u, line, tw); __syncthreads(); }
     if constexpr (G::NSTAGE >= 4) { middle<2>(u, line, tw); __syncthreads(); }
+    last(r, u, line);
+  }
+  LAPS_D static void finish_w(cplx (&r)[8], int u, cplx* __restrict__ line, cplx w1, cplx w2) {
+    __syncthreads();
+    if constexpr (G::NSTAGE >= 3) { middle_w<1>(u, line, w1); __syncthreads(); }
+    if constexpr (G::NSTAGE >= 4) { middle_w<2>(u, line, w2); __syncthreads(); }
     last(r, u, line);
   }
 };

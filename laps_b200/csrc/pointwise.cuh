@@ -118,18 +118,23 @@ struct OpMax { LAPS_D double operator()(double a, double b) const { return a > b
 
 struct CflParams {
   const double* uu; size_t npts;
-  double gamma, di, dx, dy, dz, rr;  // rr = radius / radius0
+  double gamma, di, dx, dy, dz;
   int hall;
   double* partial;  // [gridDim.x]
 };
 
-// mhd.f90:352-416.  partial[b] = min over the block's points of min(dtx,dty,dtz)
+// mhd.f90:352-416.  partial[d][b] = max over the block's points of the signal speed along d.
+// The reference takes min over points of dx/cmax_x, dy/cmax_y*(R/R0), dz/cmax_z*(R/R0); a correctly
+// rounded division (and the product with R/R0) is monotonic, so min_i fl(dx/c_i) == fl(dx/max_i c_i)
+// bit for bit: reduce the three maxima and divide once on the host (laps_vardt).  The slow-mode
+// candidates |u +- csl| are dropped, also exactly: csl <= cf holds in floating point (sqrt and the
+// division by sqrt(2) are monotonic), so they can never exceed max(|u + cf|, |u - cf|).
 __global__ void __launch_bounds__(256) k_cfl(const CflParams P) {
   __shared__ double scratch[32];
   const size_t n = P.npts;
   const double s2 = sqrt(2.0);
   const double dmin = fmin(fmin(P.dx, P.dy), P.dz);
-  double best = 1.0e300;
+  double best[3] = {0.0, 0.0, 0.0};
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const double rho = P.uu[i], mx = P.uu[n + i], my = P.uu[2 * n + i], mz = P.uu[3 * n + i];
     const double Bx = P.uu[4 * n + i], By = P.uu[5 * n + i], Bz = P.uu[6 * n + i], en = P.uu[7 * n + i];
@@ -141,31 +146,26 @@ __global__ void __launch_bounds__(256) k_cfl(const CflParams P) {
     const double ca2 = ca[0] * ca[0] + ca[1] * ca[1] + ca[2] * ca[2];
     const double cms2 = cs2 + ca2;
     double chall = 0.0;
-    if (P.hall) chall = P.di / rho * fmax(fmax(Bx, By), Bz) / dmin;
-    double cmax[3];
+    if (P.hall) chall = P.di / rho * fmax(fmax(Bx, By), Bz) / dmin;   // signed max, as mhd.f90:396-398
     LAPS_UNROLL
     for (int d = 0; d < 3; ++d) {
       const double cns = sqrt(fmax(cms2 * cms2 - 4 * cs2 * ca[d] * ca[d], 0.0));
       const double cf = sqrt(cms2 + cns) / s2;
-      const double csl = sqrt(fmax(cms2 - cns, 0.0)) / s2;
       const double uu_ = uvel[d];
       double c = fabs(uu_ + cf);
-      c = fmax(c, fabs(uu_ + csl));
       c = fmax(c, fabs(uu_ + ca[d]));
       c = fmax(c, fabs(uu_ - cf));
-      c = fmax(c, fabs(uu_ - csl));
       c = fmax(c, fabs(uu_ - ca[d]));
       c = fmax(c, fabs(uu_));
       if (P.hall) c = fmax(c, chall);
-      cmax[d] = c;
+      best[d] = fmax(best[d], c);
     }
-    const double dtx = P.dx / cmax[0];
-    const double dty = P.dy / cmax[1] * P.rr;
-    const double dtz = P.dz / cmax[2] * P.rr;
-    best = fmin(best, fmin(fmin(dtx, dty), dtz));
   }
-  const double r = block_reduce(best, OpMin(), scratch);
-  if (threadIdx.x == 0) P.partial[blockIdx.x] = r;
+  LAPS_UNROLL
+  for (int d = 0; d < 3; ++d) {
+    const double r = block_reduce(best[d], OpMax(), scratch);
+    if (threadIdx.x == 0) P.partial[(size_t)d * gridDim.x + blockIdx.x] = r;
+  }
 }
 
 // final reduction of per-block partials: out[j] = op over b of partial[j*nb + b]; one block per j

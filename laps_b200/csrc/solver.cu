@@ -16,6 +16,7 @@
 #include "exchange.cuh"
 #include "fft_passes.cuh"
 #include "pointwise.cuh"
+#include "spectral_rhs.cuh"
 #include "spectral_z.cuh"
 
 using namespace laps;
@@ -42,6 +43,7 @@ constexpr int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi 
 constexpr int cap_threads(int t, int nt) { return t * nt > 1024 ? 1024 / nt : t; }
 constexpr int tlx(int N) { return cap_threads(clampi(256 / (N / 8), 4, 8), N / 8); }   // complex lines per x-pass CTA
 constexpr int tly(int N) { return cap_threads(clampi(512 / (N / 8), 4, 8), N / 8); }   // lines per y-pass CTA
+constexpr int rcg(int N) { return clampi(64 / (N / 8), 1, 32); }                       // columns per CTA of the pipelined RHS z pass
 constexpr int cgz(int N) { return clampi(128 / (N / 8), 1, 32); }                      // columns per z-pass CTA
 
 #define LAPS_FOR_SIZES(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048)
@@ -103,7 +105,8 @@ struct laps_solver {
   XchgPeers xp;
   unsigned long long epoch = 0;
   bool wired = false;
-  int tune_cgz = 0, tune_z = 3;
+  int tune_cgz = 0, tune_z = 3, tune_rhs = 1, tune_rcg = 0;
+  int num_sms = 148;
   double da_thresh = 0;
   void* ipc_opened[LAPS_MAX_RANKS][3];   // mappings obtained with cudaIpcOpenMemHandle
   cudaStream_t stream = nullptr;
@@ -308,6 +311,27 @@ int do_spec_z(S* s, const ZParams& zp, int ntasks, const char* name) {
   return do_spec_z_cg<N, cgz(N)>(s, zp, ntasks, name);
 }
 
+template <int N, int CG>
+int do_rhs_z_cg(S* s, const ZParams& zp, int ntasks) {
+  typedef RTile<N, CG> T;
+  LAPS_CK(s, prepare_kernel(k_rhs_z<N, CG>, T::SMEM, T::MINB));
+  LaunchScope ls(s, "spec_z");
+  const int ngroups = (int)((s->ncol + CG - 1) / CG);
+  const long long nitems = (long long)ngroups * ntasks;
+  const long long wave = (long long)s->num_sms * T::MINB;
+  dim3 grid((unsigned)std::min(nitems, wave));
+  LAPS_LAUNCH((k_rhs_z<N, CG>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, zp, ntasks, ngroups);
+  return check_launch(s, "k_rhs_z");
+}
+
+template <int N>
+int do_rhs_z(S* s, const ZParams& zp, int ntasks) {
+  if constexpr (N == 512) {  // tuning knob for the benchmark grid (columns per CTA)
+    if (s->tune_rcg == 2) return do_rhs_z_cg<N, 2>(s, zp, ntasks);
+  }
+  return do_rhs_z_cg<N, rcg(N)>(s, zp, ntasks);
+}
+
 #define LAPS_DISPATCH(n, fn, ...)                                   \
   switch (n) {                                                      \
     case 16: return fn<16>(__VA_ARGS__);                            \
@@ -326,6 +350,7 @@ int fwd_y(S* s, const cplx* W1, int nfields) { LAPS_DISPATCH(s->ny, do_fwd_y, s,
 int inv_y(S* s, const cplx* V1, cplx* V2, int nfields) { LAPS_DISPATCH(s->ny, do_inv_y, s, V1, V2, nfields) }
 int inv_x(S* s, const cplx* V2, const RealDst& dst, int nfields) { LAPS_DISPATCH(s->nx, do_inv_x, s, V2, dst, nfields) }
 int spec_z(S* s, const ZParams& zp, int ntasks, const char* name) { LAPS_DISPATCH(s->nz, do_spec_z, s, zp, ntasks, name) }
+int rhs_z(S* s, const ZParams& zp, int ntasks) { LAPS_DISPATCH(s->nz, do_rhs_z, s, zp, ntasks) }
 
 // buffers (see the memory plan in DESIGN.md)
 double* buf_F(S* s) { return (double*)s->bufX; }
@@ -455,7 +480,8 @@ int stage(S* s, int irk) {
     z.task[6] = rhs_task(6, 6, 13, -1.0, 12, 1.0, -1, 0.0, +1.0, -1, 0.0);
     // energy: -(kx F16 + ky F17 + kz F18) + X  (mhdrhs.f90:231-233,250)
     z.task[7] = rhs_task(7, 7, 15, 1.0, 16, 1.0, X, -1.0, -1.0, 17, -1.0);
-    LAPS_TRY(spec_z(s, z, 8, "spec_z"));
+    if (s->tune_rhs) LAPS_TRY(rhs_z(s, z, 8));
+    else LAPS_TRY(spec_z(s, z, 8, "spec_z"));
   }
   // J for the next stage's calc_flux.  After the last stage of a step in the expanding box the
   // driver moves the radius (evolve_radius, mhd.f90:248) and with it the wave vectors J is built
@@ -519,6 +545,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("no CUDA device available (this library has no CPU path)");
   if (p.device < 0 || p.device >= ndev) return fail("bad device ordinal");
   if (cudaSetDevice(p.device) != cudaSuccess) return fail("cudaSetDevice failed");
+  if (cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, p.device) != cudaSuccess) return fail("cudaDeviceGetAttribute failed");
 #endif
   s->nx = p.nx; s->ny = p.ny; s->nz = p.nz; s->nxh = p.nx / 2 + 1; s->P = p.nranks; s->rank = p.rank;
   decompose_1d(s->nz, s->P, s->zoffs, s->zlens);   // zj_offset/zj_size (parallel.f90:102)
@@ -540,6 +567,8 @@ int laps_create(const laps_params* params, laps_handle* out) {
     s->da_thresh = t;
   }
   if (const char* e = std::getenv("LAPS_TUNE_CGZ")) s->tune_cgz = std::atoi(e);
+  if (const char* e = std::getenv("LAPS_TUNE_RHS")) s->tune_rhs = std::atoi(e);
+  if (const char* e = std::getenv("LAPS_TUNE_RCG")) s->tune_rcg = std::atoi(e);
   if (const char* e = std::getenv("LAPS_TUNE_Z")) s->tune_z = std::atoi(e);
   s->nblk = (int)std::min<size_t>(148 * 8, (s->npts + 255) / 256);   // grid-stride loops: 8 CTAs per SM at most
 
@@ -704,15 +733,19 @@ int laps_vardt(laps_handle s, double* dt_inout) {  // mhd.f90:328-429
   const laps_params& p = s->p;
   CflParams c;
   c.uu = s->uu; c.npts = s->npts; c.gamma = p.adiabatic_index; c.di = p.ion_inertial_length;
-  c.dx = p.Lx / s->nx; c.dy = p.Ly / s->ny; c.dz = p.Lz / s->nz; c.rr = s->radius / p.radius0;
+  c.dx = p.Lx / s->nx; c.dy = p.Ly / s->ny; c.dz = p.Lz / s->nz;
   c.hall = p.if_hall; c.partial = s->d_partial;
   {
     LaunchScope ls(s, "cfl");
     LAPS_LAUNCH(k_cfl, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, c);
     LAPS_TRY(check_launch(s, "k_cfl"));
   }
-  LAPS_TRY(reduce_final(s, 1, 1, 1.0e300));
-  double dtmin = s->h_scal[0];
+  LAPS_TRY(reduce_final(s, 3, 2, 0.0));   // global maxima of the three signal speeds (mhd.f90:419 as max)
+  const double rr = s->radius / p.radius0;
+  const double dtx = c.dx / s->h_scal[0];
+  const double dty = c.dy / s->h_scal[1] * rr;
+  const double dtz = c.dz / s->h_scal[2] * rr;
+  double dtmin = std::min(std::min(dtx, dty), dtz);
   dtmin = dtmin * p.cfl;
   double dt = *dt_inout;
   if (dt < 0.98 * dtmin || dt > 1.02 * dtmin) dt = dtmin;

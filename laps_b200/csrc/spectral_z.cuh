@@ -92,19 +92,23 @@ LAPS_D void prefetch_l2(const void* p) {
 #endif
 }
 
-// k_square(ix,iy,iz) exactly as update_ksquare / grid_initialize evaluate it.
-LAPS_D double ksq_eval(const ZParams& P, double kxr, double kyr, int kx, int ky, int kz) {
+// k_square(ix,iy,iz) exactly as update_ksquare / grid_initialize evaluate it: the terms that do not
+// depend on iz are summed first there too, so  k_square = ksq_xy(ix,iy) + ksq_z(iz)  bit for bit.
+LAPS_D double ksq_xy_of(const ZParams& P, double kxr, double kyr, double ksqx, double ksqy) {
   if (P.corot_ksq) {
-    const double t1 = __dmul_rn(__ldg(P.ksq_x + kx), P.ksq_c1);
-    const double t2 = __dmul_rn(__ldg(P.ksq_y + ky), P.ksq_c2);
+    const double t1 = __dmul_rn(ksqx, P.ksq_c1);
+    const double t2 = __dmul_rn(ksqy, P.ksq_c2);
     double t3 = __dmul_rn(kxr, kyr);
     t3 = __dmul_rn(t3, 2.0);
     t3 = __dmul_rn(t3, P.cosa);
     t3 = __dmul_rn(t3, P.sina);
     t3 = __dmul_rn(t3, P.ksq_c3);
-    return __dadd_rn(__dadd_rn(__dadd_rn(t1, t2), t3), __ldg(P.ksq_z + kz));
+    return __dadd_rn(__dadd_rn(t1, t2), t3);
   }
-  return __dadd_rn(__dadd_rn(__ldg(P.ksq_x + kx), __ldg(P.ksq_y + ky)), __ldg(P.ksq_z + kz));
+  return __dadd_rn(ksqx, ksqy);
+}
+LAPS_D double ksq_xy_eval(const ZParams& P, double kxr, double kyr, int kx, int ky) {
+  return ksq_xy_of(P, kxr, kyr, __ldg(P.ksq_x + kx), __ldg(P.ksq_y + ky));
 }
 
 template <int N, int CG>
@@ -214,6 +218,7 @@ k_spec_z(const ZParams P) {
     const double ce = (K.diff == 1 && P.visc_exp) ? P.nu : ((K.diff == 2 && P.resis_exp) ? P.eta : 0.0);   // :253-275
     const double ci = (K.diff == 1 && P.visc_imp) ? P.nu : ((K.diff == 2 && P.resis_imp) ? P.eta : 0.0);   // rktmod.f90:47-60
     const bool need_ksq = (ce != 0.0) || (ci != 0.0);
+    const double ksq_xy = need_ksq ? ksq_xy_eval(P, kxr, kyr, kx, ky) : 0.0;
     const bool keep_bg = K.diff == 2 && P.conserve_bg && kx == 0;   // "ix==1 .and. iz==1" skip of mhdrhs.f90:262-270
     const double dxy = (P.dealias_option == 1) ? __dadd_rn(__ldg(P.dax + kx), __ldg(P.day + ky))
                                                : ((P.dealias_option == 2) ? __ldg(P.dax + kx) : 0.0);
@@ -228,7 +233,7 @@ k_spec_z(const ZParams P) {
       fnl.y -= ca * uo.y;
       double ksq = 0.0;
       if (need_ksq) {
-        ksq = ksq_eval(P, kxr, kyr, kx, ky, kz);
+        ksq = __dadd_rn(ksq_xy, __ldg(P.ksq_z + kz));
         const double cee = (keep_bg && kz == 0) ? 0.0 : ce;
         fnl.x -= (cee * uo.x) * ksq;
         fnl.y -= (cee * uo.y) * ksq;
