@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define LAPS_ABI_VERSION 1
+#define LAPS_ABI_VERSION 2
 #define LAPS_MAX_RANKS 8
 
 typedef struct laps_solver* laps_handle;
@@ -45,6 +45,13 @@ typedef struct laps_params {
   double ion_inertial_length;
   int32_t rank, nranks;          /* slab decomposition = ndim_parallel=1 (parallel.f90:56-58) */
   int32_t device;                /* CUDA device ordinal for this rank */
+  /* 2D tree (src_compressible/2D/): ndim = 2 with nz = 1 runs the (nx, ny) algorithm of 2D/mhdrhs.f90,
+   * 2D/mhd.f90:296-406 (vardt), 2D/dealiasing.f90 (dealias_option 3 = square truncation) on one GPU;
+   * ndim = 0 or 3 is the 3D tree.  if_z_radial: 2D/mhd.f90:44 (&AEB); if_limit_dt_increase:
+   * 2D/mhd.f90:23,396-404 (&numerical).  Not supported in 2D: if_corotating, if_external_force. */
+  int32_t ndim;
+  int32_t if_z_radial;
+  int32_t if_limit_dt_increase;
 } laps_params;
 
 /* Local extents as decompose_1d (parallel.f90:326-349) assigns them in slab mode. */

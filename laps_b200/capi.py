@@ -14,7 +14,7 @@ from typing import Optional
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_RANKS = 8
 PEER_BLOB_BYTES = 256
 
@@ -42,6 +42,7 @@ class LapsParams(C.Structure):
         ("ion_inertial_length", C.c_double),
         ("rank", C.c_int32), ("nranks", C.c_int32),
         ("device", C.c_int32),
+        ("ndim", C.c_int32), ("if_z_radial", C.c_int32), ("if_limit_dt_increase", C.c_int32),
     ]
 
 
@@ -132,6 +133,7 @@ def make_params(**kw) -> LapsParams:
     p.afx = p.afy = p.afz = 0.495
     p.radius0 = 30.0
     p.rank, p.nranks, p.device = 0, 1, 0
+    p.ndim = 3
     names = {f[0] for f in LapsParams._fields_}
     for k, v in kw.items():
         if k not in names:

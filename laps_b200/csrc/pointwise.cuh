@@ -32,6 +32,8 @@ struct FluxParams {
   size_t npts;
   int hall, aeb;
   double gamma, di, tau;
+  int z_radial;         // 2D tree, radial direction along z (2D/mhdrhs.f90:96-100)
+  int slot[19];         // field slot of each flux in F, < 0: not needed (the z fluxes of the 2D tree)
 };
 
 __global__ void __launch_bounds__(256) k_flux(const FluxParams P) {
@@ -45,16 +47,17 @@ __global__ void __launch_bounds__(256) k_flux(const FluxParams P) {
     const double ptot = p + 0.5 * (Bx * Bx + By * By + Bz * Bz);
     const double udotb = ux * Bx + uy * By + uz * Bz;
     double* F = P.F + i;
-    F[0] = mx; F[n] = my; F[2 * n] = mz;
-    F[3 * n] = mx * ux - Bx * Bx + ptot;
-    F[4 * n] = my * ux - By * Bx;
-    F[5 * n] = mz * ux - Bz * Bx;
-    F[6 * n] = mx * uy - Bx * By;
-    F[7 * n] = my * uy - By * By + ptot;
-    F[8 * n] = mz * uy - Bz * By;
-    F[9 * n] = mx * uz - Bx * Bz;
-    F[10 * n] = my * uz - By * Bz;
-    F[11 * n] = mz * uz - Bz * Bz + ptot;
+    double f[19];
+    f[0] = mx; f[1] = my; f[2] = mz;
+    f[3] = mx * ux - Bx * Bx + ptot;
+    f[4] = my * ux - By * Bx;
+    f[5] = mz * ux - Bz * Bx;
+    f[6] = mx * uy - Bx * By;
+    f[7] = my * uy - By * By + ptot;
+    f[8] = mz * uy - Bz * By;
+    f[9] = mx * uz - Bx * Bz;
+    f[10] = my * uz - By * Bz;
+    f[11] = mz * uz - Bz * Bz + ptot;
     double Ex = uz * By - uy * Bz;
     double Ey = ux * Bz - uz * Bx;
     double Ez = uy * Bx - ux * By;
@@ -65,15 +68,23 @@ __global__ void __launch_bounds__(256) k_flux(const FluxParams P) {
       Ey = Ey + dr * (Jz * Bx - Jx * Bz);
       Ez = Ez + dr * (Jx * By - Jy * Bx);
     }
-    F[12 * n] = Ex; F[13 * n] = Ey; F[14 * n] = Ez;
+    f[12] = Ex; f[13] = Ey; f[14] = Ez;
     const double h = en + ptot;
-    F[15 * n] = h * ux - udotb * Bx;
-    F[16 * n] = h * uy - udotb * By;
-    F[17 * n] = h * uz - udotb * Bz;
+    f[15] = h * ux - udotb * Bx;
+    f[16] = h * uy - udotb * By;
+    f[17] = h * uz - udotb * Bz;
+    f[18] = 0.0;
     if (P.aeb) {
-      F[18 * n] = -2 * P.gamma / gm1 * p / P.tau - (2.0 * Bx * Bx + By * By + Bz * Bz) / P.tau -
-                  (mx * ux + 2 * my * uy + 2 * mz * uz) / P.tau;
+      if (P.z_radial)
+        f[18] = -2 * P.gamma / gm1 * p / P.tau - (Bx * Bx + By * By + 2.0 * Bz * Bz) / P.tau -
+                (2 * mx * ux + 2 * my * uy + mz * uz) / P.tau;
+      else
+        f[18] = -2 * P.gamma / gm1 * p / P.tau - (2.0 * Bx * Bx + By * By + Bz * Bz) / P.tau -
+                (mx * ux + 2 * my * uy + 2 * mz * uz) / P.tau;
     }
+    LAPS_UNROLL
+    for (int j = 0; j < 19; ++j)
+      if (P.slot[j] >= 0) F[(size_t)P.slot[j] * n] = f[j];
   }
 }
 
@@ -118,7 +129,9 @@ struct OpMax { LAPS_D double operator()(double a, double b) const { return a > b
 
 struct CflParams {
   const double* uu; size_t npts;
-  double gamma, di, dx, dy, dz;
+  double gamma, di;
+  double dmin;            // min(dx,dy,dz) (mhd.f90:398); min(dx,dy) in the 2D tree (2D/mhd.f90:369)
+  double floor_x, floor_y; // resistivity/dx, resistivity/dy of the 2D tree's explicit-resistivity limit (2D/mhd.f90:361-364), else 0
   int hall;
   double* partial;  // [gridDim.x]
 };
@@ -133,7 +146,7 @@ __global__ void __launch_bounds__(256) k_cfl(const CflParams P) {
   __shared__ double scratch[32];
   const size_t n = P.npts;
   const double s2 = sqrt(2.0);
-  const double dmin = fmin(fmin(P.dx, P.dy), P.dz);
+  const double dmin = P.dmin;
   double best[3] = {0.0, 0.0, 0.0};
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const double rho = P.uu[i], mx = P.uu[n + i], my = P.uu[2 * n + i], mz = P.uu[3 * n + i];
@@ -157,6 +170,8 @@ __global__ void __launch_bounds__(256) k_cfl(const CflParams P) {
       c = fmax(c, fabs(uu_ - cf));
       c = fmax(c, fabs(uu_ - ca[d]));
       c = fmax(c, fabs(uu_));
+      if (d == 0) c = fmax(c, P.floor_x);
+      if (d == 1) c = fmax(c, P.floor_y);
       if (P.hall) c = fmax(c, chall);
       best[d] = fmax(best[d], c);
     }
@@ -228,6 +243,7 @@ struct DivbParams {
   const cplx* u; size_t fstride; int ncol, nz, nyl, yoff;
   const double* kxr; const double* kyr; const double* kze;
   double radius0, radius, cosa, sina; int corot_k;
+  int mode2d, z_radial;   // 2D tree: the line axis carries ky, kz = 0 (2D/mhd.f90:527-550)
   double* partial;
 };
 __global__ void __launch_bounds__(256) k_divb(const DivbParams P) {
@@ -243,9 +259,11 @@ __global__ void __launch_bounds__(256) k_divb(const DivbParams P) {
       kxe = __dadd_rn(__dmul_rn(kxr, P.cosa), __dmul_rn(kyr, P.sina));
       kye = __ddiv_rn(__dmul_rn(__dadd_rn(__dmul_rn(-kxr, P.sina), __dmul_rn(kyr, P.cosa)), P.radius0), P.radius);
     }
+    if (P.z_radial) kxe = __ddiv_rn(__dmul_rn(kxr, P.radius0), P.radius);
     const double kzz = P.kze[kz];
     const cplx bx = P.u[4 * P.fstride + i], by = P.u[5 * P.fstride + i], bz = P.u[6 * P.fstride + i];
-    const cplx d = cadd(cadd(cmul_i(bx, kxe), cmul_i(by, kye)), cmul_i(bz, kzz));
+    const cplx d = P.mode2d ? cadd(cadd(cmul_i(bx, kxe), cmul_i(by, kzz)), cmul_i(bz, 0.0))
+                            : cadd(cadd(cmul_i(bx, kxe), cmul_i(by, kye)), cmul_i(bz, kzz));
     best = fmax(best, sqrt(d.x * d.x + d.y * d.y));
   }
   const double r = block_reduce(best, OpMax(), scratch);

@@ -63,7 +63,10 @@ struct ProfEntry { char name[32]; cudaEvent_t e0, e1; };
 }  // namespace
 
 struct laps_solver {
-  laps_params p;
+  laps_params p;       // INTERNAL parameters: in the 2D tree the grid is held as (nx, 1, ny), see laps_create
+  laps_params user;    // as given by the driver
+  bool two_d = false;
+  int xz = 0, xy = 0;  // line counts (planes, lines per plane) the x passes run over
   int nx, ny, nz, nxh, P, rank;
   int zoffs[LAPS_MAX_RANKS], zlens[LAPS_MAX_RANKS], yoffs[LAPS_MAX_RANKS], ylens[LAPS_MAX_RANKS];
   int nzl, nyl, zo, yo;
@@ -105,6 +108,7 @@ struct laps_solver {
   XchgPeers xp;
   unsigned long long epoch = 0;
   bool wired = false;
+  int slot[19];        // field slot of each flux (F1..F18, expand_term), < 0: not transformed
   int tune_cgz = 0, tune_z = 3, tune_rhs = 1, tune_rcg = 0;
   int num_sms = 148;
   double da_thresh = 0;
@@ -174,6 +178,8 @@ int upload_tables(S* s) {
   for (int i = 0; i < ny; ++i) kyr[i] = s->wny[i];
   for (int i = 0; i < nz; ++i) kze[i] = s->wnz[i] * r0 / r;          // mhdrhs.f90:192
   for (int i = 0; i < nxh; ++i) ksq_x[i] = s->wnx[i] * s->wnx[i];
+  if (!s->ksq_initial && s->two_d && p.if_z_radial)                   // 2D/AEBmod.f90:109-111
+    for (int i = 0; i < nxh; ++i) { const double a = s->wnx[i] * r0 / r; ksq_x[i] = a * a; }
   if (s->ksq_initial) {                                               // mhdinit.f90:114-122
     for (int i = 0; i < ny; ++i) ksq_y[i] = s->wny[i] * s->wny[i];
     for (int i = 0; i < nz; ++i) ksq_z[i] = s->wnz[i] * s->wnz[i];
@@ -192,6 +198,11 @@ int upload_tables(S* s) {
     for (int i = 0; i < nxh; ++i) dax[i] = filter_1d(s->wnx[i], p.Lx, s->nx, p.afx);
     for (int i = 0; i < ny; ++i) day[i] = filter_1d(s->wny[i], p.Ly, ny, p.afy);
     for (int i = 0; i < nz; ++i) daz[i] = filter_1d(s->wnz[i], p.Lz, nz, p.afz);
+    if (s->two_d) day[0] = 1.0;                                       // 2D/dealiasing.f90:96: filtx * filty only
+  } else if (p.dealias_option == 3) {                                 // 2D/dealiasing.f90:102-117 (square): per-axis flags
+    for (int i = 0; i < nxh; ++i) dax[i] = std::fabs(s->wnx[i] * p.Lx / (2 * kPi * s->nx)) > (1.0 / 3.0) ? 1.0 : 0.0;
+    for (int i = 0; i < ny; ++i) day[i] = 0.0;
+    for (int i = 0; i < nz; ++i) daz[i] = std::fabs(s->wnz[i] * p.Lz / (2 * kPi * nz)) > (1.0 / 3.0) ? 1.0 : 0.0;
   }
   LAPS_CK(s, cudaMemcpyAsync(s->d_tab, t, s->h_tab.size() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   // the host vector is reused on the next call: make the copy complete before returning
@@ -244,11 +255,11 @@ int do_fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1) {
   char name[32]; std::snprintf(name, sizeof(name), "fwd_x%d", nfields);
   constexpr int TL = tlx(N);
   typedef Tile<N, TL> T;
-  if (s->ny % (2 * TL) != 0) { s->err = "ny must be a multiple of " + std::to_string(2 * TL); return 1; }
+  if (s->xy % (2 * TL) != 0) { s->err = "ny must be a multiple of " + std::to_string(2 * TL); return 1; }
   LAPS_CK(s, prepare_kernel(k_fwd_x<N, TL>, T::SMEM, T::MINB));
   LaunchScope ls(s, name);
-  dim3 grid((unsigned)(s->nzl * (s->ny / (2 * TL))), (unsigned)nfields);
-  LAPS_LAUNCH((k_fwd_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, in, fstride, W1, s->nzl, s->ny, s->tw_x,
+  dim3 grid((unsigned)(s->xz * (s->xy / (2 * TL))), (unsigned)nfields);
+  LAPS_LAUNCH((k_fwd_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, in, fstride, W1, s->xz, s->xy, s->tw_x,
               1.0 / N);
   return check_launch(s, "k_fwd_x");
 }
@@ -287,8 +298,8 @@ int do_inv_x(S* s, const cplx* V2, const RealDst& dst, int nfields) {
   typedef Tile<N, TL> T;
   LAPS_CK(s, prepare_kernel(k_inv_x<N, TL>, T::SMEM, T::MINB));
   LaunchScope ls(s, name);
-  dim3 grid((unsigned)(s->nzl * (s->ny / (2 * TL))), (unsigned)nfields);
-  LAPS_LAUNCH((k_inv_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, V2, dst, s->nzl, s->ny, s->tw_x);
+  dim3 grid((unsigned)(s->xz * (s->xy / (2 * TL))), (unsigned)nfields);
+  LAPS_LAUNCH((k_inv_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, V2, dst, s->xz, s->xy, s->tw_x);
   return check_launch(s, "k_inv_x");
 }
 
@@ -348,6 +359,15 @@ int do_rhs_z(S* s, const ZParams& zp, int ntasks) {
 int fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1) { LAPS_DISPATCH(s->nx, do_fwd_x, s, in, fstride, nfields, W1) }
 int fwd_y(S* s, const cplx* W1, int nfields) { LAPS_DISPATCH(s->ny, do_fwd_y, s, W1, nfields) }
 int inv_y(S* s, const cplx* V1, cplx* V2, int nfields) { LAPS_DISPATCH(s->ny, do_inv_y, s, V1, V2, nfields) }
+
+// Forward x (+y) passes of `nfields` real fields into the z-pass input buffer W2.  In the 2D tree
+// (grid held as (nx, 1, ny)) the post-x-pass layout [f][kx][1][y] IS the z-pass layout
+// [f][kx][ky_local=1][line], so the x pass writes W2 directly and there is no y pass.
+int forward_xy(S* s, const double* in, size_t fstride, int nfields) {
+  if (s->two_d) return fwd_x(s, in, fstride, nfields, (cplx*)s->bufZ);
+  LAPS_TRY(fwd_x(s, in, fstride, nfields, (cplx*)s->bufY));
+  return fwd_y(s, (const cplx*)s->bufY, nfields);
+}
 int inv_x(S* s, const cplx* V2, const RealDst& dst, int nfields) { LAPS_DISPATCH(s->nx, do_inv_x, s, V2, dst, nfields) }
 int spec_z(S* s, const ZParams& zp, int ntasks, const char* name) { LAPS_DISPATCH(s->nz, do_spec_z, s, zp, ntasks, name) }
 int rhs_z(S* s, const ZParams& zp, int ntasks) { LAPS_DISPATCH(s->nz, do_rhs_z, s, zp, ntasks) }
@@ -384,6 +404,7 @@ void fill_zparams(S* s, ZParams& z) {
   z.dealias_option = p.dealias_option;
   z.scale = 1.0 / s->nz;
   z.da_thresh = s->da_thresh;
+  z.mode2d = s->two_d; z.z_radial = s->two_d && p.if_AEB && p.if_z_radial; z.bg_all_kz = s->two_d;
   z.tune = s->tune_z;
 }
 
@@ -431,10 +452,11 @@ RealDst dst_state_and_current(S* s) {
 // inverse y and x passes for V1 slots [g0, g0+n)
 int inverse_yx(S* s, int g0, int n) {
   const size_t vs = (size_t)s->nxh * s->ny * s->nzl;
-  LAPS_TRY(inv_y(s, buf_V1(s) + (size_t)g0 * vs, buf_V2(s) + (size_t)g0 * vs, n));
   RealDst d = dst_state_and_current(s), d2;
   std::memset(&d2, 0, sizeof(d2));
   for (int i = 0; i < n; ++i) d2.ptr[i] = d.ptr[g0 + i];
+  if (s->two_d) return inv_x(s, buf_V1(s) + (size_t)g0 * vs, d2, n);   // [g][kx][1][line] is already the x-pass layout
+  LAPS_TRY(inv_y(s, buf_V1(s) + (size_t)g0 * vs, buf_V2(s) + (size_t)g0 * vs, n));
   return inv_x(s, buf_V2(s) + (size_t)g0 * vs, d2, n);
 }
 
@@ -452,34 +474,54 @@ int refresh_current(S* s) {
 int stage(S* s, int irk) {
   const laps_params& p = s->p;
   LAPS_TRY(refresh_current(s));
-  {  // calc_flux (mhdrhs.f90:21-124)
+  {  // calc_flux (mhdrhs.f90:21-124; 2D/mhdrhs.f90:23-128)
     FluxParams f;
     f.uu = s->uu; f.J = s->J; f.F = buf_F(s); f.npts = s->npts;
     f.hall = p.if_hall; f.aeb = p.if_AEB; f.gamma = p.adiabatic_index; f.di = p.ion_inertial_length; f.tau = s->tau;
+    f.z_radial = s->two_d && p.if_z_radial;
+    for (int j = 0; j < 19; ++j) f.slot[j] = s->slot[j];
     LaunchScope ls(s, "flux");
     LAPS_LAUNCH(k_flux, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, f);
     LAPS_TRY(check_launch(s, "k_flux"));
   }
   // transform_flux_real_to_fourier (mhdrhs.f90:128-172)
-  LAPS_TRY(fwd_x(s, buf_F(s), s->npts, s->nf, buf_W1(s)));
-  LAPS_TRY(fwd_y(s, buf_W1(s), s->nf));
+  LAPS_TRY(forward_xy(s, buf_F(s), s->npts, s->nf));
   LAPS_TRY(host_barrier(s));
   {  // z-pass + calc_rhs + rkt + dealias + inverse z
     ZParams z; fill_zparams(s, z);
     z.cc = s->cc1[irk]; z.dd = s->dd1[irk]; z.dt_irk = s->tstep[irk];
     z.read_rk = (irk > 0); z.write_rk = (irk < 2);
-    const int X = p.if_AEB ? 18 : -1;
-    //                 v  g  fa  ca   fb  cb   fx cx   sg   fc  sc
-    z.task[0] = rhs_task(0, 0, 0, 1.0, 1, 1.0, -1, 0.0, -1.0, 2, -1.0);
-    z.task[1] = rhs_task(1, 1, 3, 1.0, 4, 1.0, -1, 0.0, -1.0, 5, -1.0);
-    z.task[2] = rhs_task(2, 2, 6, 1.0, 7, 1.0, -1, 0.0, -1.0, 8, -1.0);
-    z.task[3] = rhs_task(3, 3, 9, 1.0, 10, 1.0, -1, 0.0, -1.0, 11, -1.0);
-    // dB/dt = curl E (mhdrhs.f90:223-228): fnl5 = kz F14 - ky F15 ; fnl6 = kx F15 - kz F13 ; fnl7 = ky F13 - kx F14
-    z.task[4] = rhs_task(4, 4, -1, 0.0, 14, 1.0, -1, 0.0, -1.0, 13, +1.0);
-    z.task[5] = rhs_task(5, 5, 14, 1.0, -1, 0.0, -1, 0.0, +1.0, 12, -1.0);
-    z.task[6] = rhs_task(6, 6, 13, -1.0, 12, 1.0, -1, 0.0, +1.0, -1, 0.0);
-    // energy: -(kx F16 + ky F17 + kz F18) + X  (mhdrhs.f90:231-233,250)
-    z.task[7] = rhs_task(7, 7, 15, 1.0, 16, 1.0, X, -1.0, -1.0, 17, -1.0);
+    const int* L = s->slot;   // flux index (0-based: F1..F18, expand_term) -> field slot
+    const int X = p.if_AEB ? L[18] : -1;
+    if (!s->two_d) {
+      //                 v  g  fa     ca   fb     cb   fx cx   sg   fc     sc
+      z.task[0] = rhs_task(0, 0, L[0], 1.0, L[1], 1.0, -1, 0.0, -1.0, L[2], -1.0);
+      z.task[1] = rhs_task(1, 1, L[3], 1.0, L[4], 1.0, -1, 0.0, -1.0, L[5], -1.0);
+      z.task[2] = rhs_task(2, 2, L[6], 1.0, L[7], 1.0, -1, 0.0, -1.0, L[8], -1.0);
+      z.task[3] = rhs_task(3, 3, L[9], 1.0, L[10], 1.0, -1, 0.0, -1.0, L[11], -1.0);
+      // dB/dt = curl E (mhdrhs.f90:223-228): fnl5 = kz F14 - ky F15 ; fnl6 = kx F15 - kz F13 ; fnl7 = ky F13 - kx F14
+      z.task[4] = rhs_task(4, 4, -1, 0.0, L[14], 1.0, -1, 0.0, -1.0, L[13], +1.0);
+      z.task[5] = rhs_task(5, 5, L[14], 1.0, -1, 0.0, -1, 0.0, +1.0, L[12], -1.0);
+      z.task[6] = rhs_task(6, 6, L[13], -1.0, L[12], 1.0, -1, 0.0, +1.0, -1, 0.0);
+      // energy: -(kx F16 + ky F17 + kz F18) + X  (mhdrhs.f90:231-233,250)
+      z.task[7] = rhs_task(7, 7, L[15], 1.0, L[16], 1.0, X, -1.0, -1.0, L[17], -1.0);
+    } else {
+      // 2D tree (2D/mhdrhs.f90:290-317), kz = 0: the x derivative is applied before the line transform
+      // (kx is constant along a line), the y derivative after it (the line axis carries ky).
+      z.task[0] = rhs_task(0, 0, L[0], 1.0, -1, 0.0, -1, 0.0, -1.0, L[1], -1.0);
+      z.task[1] = rhs_task(1, 1, L[3], 1.0, -1, 0.0, -1, 0.0, -1.0, L[4], -1.0);
+      z.task[2] = rhs_task(2, 2, L[6], 1.0, -1, 0.0, -1, 0.0, -1.0, L[7], -1.0);
+      z.task[3] = rhs_task(3, 3, L[9], 1.0, -1, 0.0, -1, 0.0, -1.0, L[10], -1.0);
+      // fnl5 = -ky F15 ; fnl6 = kx F15 ; fnl7 = ky F13 - kx F14
+      z.task[4] = rhs_task(4, 4, -1, 0.0, -1, 0.0, -1, 0.0, -1.0, L[14], -1.0);
+      z.task[5] = rhs_task(5, 5, L[14], 1.0, -1, 0.0, -1, 0.0, +1.0, -1, 0.0);
+      z.task[6] = rhs_task(6, 6, L[13], -1.0, -1, 0.0, -1, 0.0, +1.0, L[12], +1.0);
+      z.task[7] = rhs_task(7, 7, L[15], 1.0, -1, 0.0, X, -1.0, -1.0, L[16], -1.0);
+      if (p.if_AEB && p.if_z_radial) {   // 2D/mhdrhs.f90:324-343
+        static const double c2[8] = {2.0, 3.0, 3.0, 2.0, 1.0, 1.0, 2.0, 0.0};
+        for (int v = 0; v < 8; ++v) z.task[v].aeb_c = c2[v];
+      }
+    }
     if (s->tune_rhs) LAPS_TRY(rhs_z(s, z, 8));
     else LAPS_TRY(spec_z(s, z, 8, "spec_z"));
   }
@@ -527,18 +569,36 @@ const char* laps_last_error(laps_handle h) { return h ? h->err.c_str() : g_creat
 int laps_create(const laps_params* params, laps_handle* out) {
   if (!params || !out) { g_create_error = "null argument"; return 1; }
   *out = nullptr;
-  const laps_params& p = *params;
-  if (p.abi_version != LAPS_ABI_VERSION) { g_create_error = "laps_params.abi_version mismatch"; return 1; }
-  if (!size_supported(p.nx) || !size_supported(p.ny) || !size_supported(p.nz)) {
-    g_create_error = "nx, ny, nz must be powers of two in [16, 2048]"; return 1;
+  const laps_params& u = *params;
+  if (u.abi_version != LAPS_ABI_VERSION) { g_create_error = "laps_params.abi_version mismatch"; return 1; }
+  const bool two_d = u.ndim == 2;
+  if (u.ndim != 0 && u.ndim != 2 && u.ndim != 3) { g_create_error = "ndim must be 2 or 3"; return 1; }
+  laps_params p = u;   // internal view
+  if (two_d) {
+    // 2D tree (src_compressible/2D/): the (nx, ny, 1) grid is held as (nx, 1, ny) so that the
+    // reference's y lines are the contiguous lines of the fused spectral pass; the reference's
+    // ky tables become the internal z tables (Ly -> Lz, afy -> afz).
+    if (u.nz != 1) { g_create_error = "ndim = 2 needs nz = 1"; return 1; }
+    if (u.nranks != 1) { g_create_error = "the 2D tree runs on one GPU (nranks = 1)"; return 1; }
+    if (u.if_AEB && u.if_corotating) { g_create_error = "if_corotating is not supported in the 2D tree"; return 1; }
+    if (!size_supported(u.nx) || !size_supported(u.ny)) { g_create_error = "nx, ny must be powers of two in [16, 2048]"; return 1; }
+    p.ny = 1; p.nz = u.ny; p.Ly = 1.0; p.Lz = u.Ly; p.afz = u.afy; p.if_corotating = 0;
+    if (u.dealias_option < 0 || u.dealias_option > 3) { g_create_error = "dealias_option must be 0..3 in the 2D tree"; return 1; }
+  } else {
+    if (!size_supported(p.nx) || !size_supported(p.ny) || !size_supported(p.nz)) {
+      g_create_error = "nx, ny, nz must be powers of two in [16, 2048]"; return 1;
+    }
+    if (p.dealias_option < 0 || p.dealias_option > 2) { g_create_error = "dealias_option must be 0, 1 or 2"; return 1; }
+    p.if_z_radial = 0; p.if_limit_dt_increase = 0;
   }
   if (p.nranks < 1 || p.nranks > LAPS_MAX_RANKS || p.rank < 0 || p.rank >= p.nranks) {
     g_create_error = "bad rank/nranks (1..8 ranks, slab decomposition)"; return 1;
   }
-  if (p.nz / p.nranks < 1 || p.ny / p.nranks < 1) { g_create_error = "more ranks than planes"; return 1; }
-  if (p.dealias_option < 0 || p.dealias_option > 2) { g_create_error = "dealias_option must be 0, 1 or 2"; return 1; }
+  if (p.nz / p.nranks < 1 || (!two_d && p.ny / p.nranks < 1)) { g_create_error = "more ranks than planes"; return 1; }
   S* s = new S();
   s->p = p;
+  s->user = u;
+  s->two_d = two_d;
   auto fail = [&](const std::string& m) { g_create_error = m; laps_destroy(s); return 1; };
 #ifndef LAPS_EMU_BUILD
   int ndev = 0;
@@ -556,7 +616,16 @@ int laps_create(const laps_params* params, laps_handle* out) {
   s->ncol = (size_t)s->nxh * s->nyl;
   s->csz = s->ncol * s->nz;
   s->w1sz = (size_t)s->nxh * s->nzl * s->ny;
-  s->nf = 18 + (p.if_AEB ? 1 : 0);
+  s->xz = two_d ? 1 : s->nzl; s->xy = two_d ? s->nzl : s->ny;
+  {  // field slots of the fluxes; the 2D tree never uses the z fluxes F3,F6,F9,F12,F18 (kz = 0)
+    int n = 0;
+    for (int j = 0; j < 19; ++j) {
+      const bool zflux = (j == 2 || j == 5 || j == 8 || j == 11 || j == 17);
+      const bool on = j == 18 ? (p.if_AEB != 0) : !(two_d && zflux);
+      s->slot[j] = on ? n++ : -1;
+    }
+    s->nf = n;
+  }
   s->ni = 8 + (p.if_hall ? 3 : 0);
   {  // the mask test "sqrt(s) > 1./3." (dealiasing.f90:94) as a threshold on s: sqrt is correctly rounded
      // and monotonic, so { s : sqrt(s) > c } = { s >= T } with T the smallest double that passes
@@ -662,6 +731,9 @@ int laps_get_extents(laps_handle s, laps_extents* e) {
   if (!s || !e) return 1;
   e->nx = s->nx; e->ny = s->ny; e->nz = s->nz; e->nxh = s->nxh;
   e->z_offset = s->zo; e->z_size = s->nzl; e->y_offset = s->yo; e->y_size = s->nyl;
+  if (s->two_d) {  // the driver's view: uu(1:nx, 1:ny, 1, 1:8); spectral block (kx, all ky)
+    e->ny = s->nz; e->nz = 1; e->z_offset = 0; e->z_size = 1; e->y_offset = 0; e->y_size = s->nz;
+  }
   return 0;
 }
 
@@ -686,8 +758,7 @@ int laps_set_primitive(laps_handle s, const double* uu_local) {
     LAPS_TRY(check_launch(s, "k_prim_to_cons"));
   }
   // transform_uu_real_to_fourier (fftw.f90:42-71)
-  LAPS_TRY(fwd_x(s, s->uu, s->npts, 8, buf_W1(s)));
-  LAPS_TRY(fwd_y(s, buf_W1(s), 8));
+  LAPS_TRY(forward_xy(s, s->uu, s->npts, 8));
   LAPS_TRY(host_barrier(s));
   ZParams z; fill_zparams(s, z);
   z.u_out = s->uA;
@@ -733,7 +804,11 @@ int laps_vardt(laps_handle s, double* dt_inout) {  // mhd.f90:328-429
   const laps_params& p = s->p;
   CflParams c;
   c.uu = s->uu; c.npts = s->npts; c.gamma = p.adiabatic_index; c.di = p.ion_inertial_length;
-  c.dx = p.Lx / s->nx; c.dy = p.Ly / s->ny; c.dz = p.Lz / s->nz;
+  const double dx = p.Lx / s->nx, dy = s->two_d ? p.Lz / s->nz : p.Ly / s->ny, dz = p.Lz / s->nz;
+  c.dmin = s->two_d ? std::min(dx, dy) : std::min(std::min(dx, dy), dz);
+  const bool rfloor = s->two_d && p.if_resis && p.if_resis_exp;      // 2D/mhd.f90:361-364
+  c.floor_x = rfloor ? p.resistivity / dx : 0.0;
+  c.floor_y = rfloor ? p.resistivity / dy : 0.0;
   c.hall = p.if_hall; c.partial = s->d_partial;
   {
     LaunchScope ls(s, "cfl");
@@ -742,13 +817,23 @@ int laps_vardt(laps_handle s, double* dt_inout) {  // mhd.f90:328-429
   }
   LAPS_TRY(reduce_final(s, 3, 2, 0.0));   // global maxima of the three signal speeds (mhd.f90:419 as max)
   const double rr = s->radius / p.radius0;
-  const double dtx = c.dx / s->h_scal[0];
-  const double dty = c.dy / s->h_scal[1] * rr;
-  const double dtz = c.dz / s->h_scal[2] * rr;
-  double dtmin = std::min(std::min(dtx, dty), dtz);
+  double dtmin;
+  if (s->two_d) {                          // 2D/mhd.f90:375-381
+    double dtx = dx / s->h_scal[0];
+    if (p.if_AEB && p.if_z_radial) dtx = dtx * rr;
+    const double dty = dy / s->h_scal[1] * rr;
+    dtmin = std::min(dtx, dty);
+  } else {
+    const double dtx = dx / s->h_scal[0];
+    const double dty = dy / s->h_scal[1] * rr;
+    const double dtz = dz / s->h_scal[2] * rr;
+    dtmin = std::min(std::min(dtx, dty), dtz);
+  }
   dtmin = dtmin * p.cfl;
   double dt = *dt_inout;
-  if (dt < 0.98 * dtmin || dt > 1.02 * dtmin) dt = dtmin;
+  if (s->two_d && p.if_limit_dt_increase) {   // 2D/mhd.f90:396-400
+    if (dt == 0.0 || dt > 1.02 * dtmin) dt = dtmin;
+  } else if (dt < 0.98 * dtmin || dt > 1.02 * dtmin) dt = dtmin;
   *dt_inout = dt;
   return laps_rkt_init(s, dt);
 }
@@ -806,6 +891,7 @@ int laps_max_divb(laps_handle s, double* out) {  // mhd.f90:522-570
   d.kxr = s->kxr; d.kyr = s->kyr; d.kze = s->kze;
   d.radius0 = s->p.radius0; d.radius = s->radius; d.cosa = s->cosa; d.sina = s->sina;
   d.corot_k = (s->p.if_AEB && s->p.if_corotating) ? 1 : 0;
+  d.mode2d = s->two_d; d.z_radial = s->two_d && s->p.if_AEB && s->p.if_z_radial;
   d.partial = s->d_partial;
   {
     LaunchScope ls(s, "divb");
@@ -890,8 +976,7 @@ int laps_fft_forward(laps_handle s, const double* real_fields, int32_t nfields, 
   if (nfields < 1 || nfields > 8) { s->err = "laps_fft_forward: 1..8 fields per call"; return 1; }
   // uses the flux work buffers and u_B as scratch; the state (u_A, uu) is untouched
   LAPS_CK(s, cudaMemcpyAsync(buf_F(s), real_fields, (size_t)nfields * s->npts * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-  LAPS_TRY(fwd_x(s, buf_F(s), s->npts, nfields, buf_W1(s)));
-  LAPS_TRY(fwd_y(s, buf_W1(s), nfields));
+  LAPS_TRY(forward_xy(s, buf_F(s), s->npts, nfields));
   LAPS_TRY(host_barrier(s));
   ZParams z; fill_zparams(s, z);
   z.u_out = s->uB;
@@ -922,14 +1007,14 @@ int laps_fft_inverse(laps_handle s, const double* spec_in, int32_t nfields, doub
   LAPS_TRY(host_barrier(s));
   const size_t vs = (size_t)s->nxh * s->ny * s->nzl;
   (void)vs;
-  LAPS_TRY(inv_y(s, buf_V1(s), buf_V2(s), nfields));
+  if (!s->two_d) LAPS_TRY(inv_y(s, buf_V1(s), buf_V2(s), nfields));
   // real output goes to the flux scratch area?  bufX holds V2; use the prim scratch / J-free area:
   // write into a temporary device buffer
   double* tmp = nullptr;
   LAPS_CK(s, cudaMalloc((void**)&tmp, (size_t)nfields * s->npts * sizeof(double)));
   RealDst d; std::memset(&d, 0, sizeof(d));
   for (int v = 0; v < nfields; ++v) d.ptr[v] = tmp + (size_t)v * s->npts;
-  int rc = inv_x(s, buf_V2(s), d, nfields);
+  int rc = inv_x(s, s->two_d ? buf_V1(s) : buf_V2(s), d, nfields);
   if (!rc) {
     cudaError_t e = cudaMemcpyAsync(real_out, tmp, (size_t)nfields * s->npts * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);

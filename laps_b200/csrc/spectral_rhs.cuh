@@ -117,6 +117,7 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
     const double dax = P.dealias_option ? __ldg(P.dax + kx) : 0.0, day = P.dealias_option ? __ldg(P.day + ky) : 0.0;
     // derivative vectors (imaginary parts), mhdrhs.f90:191-204
     double kxe = kxr, kye = __ddiv_rn(__dmul_rn(kyr, P.radius0), P.radius);
+    if (P.z_radial) kxe = __ddiv_rn(__dmul_rn(kxr, P.radius0), P.radius);
     if (P.corot_k) {
       kxe = __dadd_rn(__dmul_rn(kxr, P.cosa), __dmul_rn(kyr, P.sina));
       kye = __ddiv_rn(__dmul_rn(__dadd_rn(__dmul_rn(-kxr, P.sina), __dmul_rn(kyr, P.cosa)), P.radius0), P.radius);
@@ -176,7 +177,7 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
     const bool need_ksq = (ce != 0.0) || (ci != 0.0);
     const double ksq_xy = ksq_xy_of(P, kxr, kyr, ksqx, ksqy);
     const bool keep_bg = K.diff == 2 && P.conserve_bg && kx == 0;   // "ix==1 .and. iz==1" skip of mhdrhs.f90:262-270
-    const double dxy = (P.dealias_option == 1) ? __dadd_rn(dax, day) : dax;
+    const double dxy = (P.dealias_option == 1 || P.dealias_option == 3) ? __dadd_rn(dax, day) : dax;
     const double dfy = day;
     cp_async_wait<0>();   // u, rk
     LAPS_UNROLL
@@ -190,7 +191,7 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
       double ksq = 0.0;
       if (need_ksq) {
         ksq = __dadd_rn(ksq_xy, t_ksqz[e]);
-        const double cee = (keep_bg && kz == 0) ? 0.0 : ce;
+        const double cee = (keep_bg && (P.bg_all_kz || kz == 0)) ? 0.0 : ce;
         fnl.x -= (cee * uo.x) * ksq;
         fnl.y -= (cee * uo.y) * ksq;
       }
@@ -214,6 +215,8 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
       } else if (P.dealias_option == 2) {
         const double fz = t_daz[e];
         un = mk(__dmul_rn(__dmul_rn(__dmul_rn(un.x, dxy), dfy), fz), __dmul_rn(__dmul_rn(__dmul_rn(un.y, dxy), dfy), fz));
+      } else if (P.dealias_option == 3) {   // square truncation (2D/dealiasing.f90:102-117): per-axis flags
+        if (dxy != 0.0 || t_daz[e] != 0.0) un = mk(0.0, 0.0);
       }
       if (live) P.u_out[voff + kz] = un;
       r[e] = un;

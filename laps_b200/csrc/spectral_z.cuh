@@ -63,6 +63,9 @@ struct ZParams {
   int dealias_option;
   int read_rk, write_rk;
   double scale;          // 1/nz
+  int mode2d;            // 2D tree: the line axis is the reference's y, d/dz = 0 (src_compressible/2D/mhdrhs.f90:272)
+  int z_radial;          // 2D/mhdrhs.f90:278-280: kx is stretched too
+  int bg_all_kz;         // 2D/mhdrhs.f90:372-374: if_conserve_background skips every mode with ix == 1
   double da_thresh;      // dealias option 1: smallest s with sqrt(s) > 1./3. (dealiasing.f90:94)
   int tune;              // bit 0: L2-prefetch state/history lines, bit 1: L2-prefetch the G inputs
   ZTask task[12];
@@ -133,6 +136,7 @@ k_spec_z(const ZParams P) {
   // derivative vectors (imaginary parts), mhdrhs.f90:191-204
   const double kxr = __ldg(P.kxr + kx), kyr = __ldg(P.kyr + ky);
   double kxe = kxr, kye = __ddiv_rn(__dmul_rn(kyr, P.radius0), P.radius);
+  if (P.z_radial) kxe = __ddiv_rn(__dmul_rn(kxr, P.radius0), P.radius);
   if (P.corot_k) {
     kxe = __dadd_rn(__dmul_rn(kxr, P.cosa), __dmul_rn(kyr, P.sina));
     kye = __ddiv_rn(__dmul_rn(__dadd_rn(__dmul_rn(-kxr, P.sina), __dmul_rn(kyr, P.cosa)), P.radius0), P.radius);
@@ -220,7 +224,7 @@ k_spec_z(const ZParams P) {
     const bool need_ksq = (ce != 0.0) || (ci != 0.0);
     const double ksq_xy = need_ksq ? ksq_xy_eval(P, kxr, kyr, kx, ky) : 0.0;
     const bool keep_bg = K.diff == 2 && P.conserve_bg && kx == 0;   // "ix==1 .and. iz==1" skip of mhdrhs.f90:262-270
-    const double dxy = (P.dealias_option == 1) ? __dadd_rn(__ldg(P.dax + kx), __ldg(P.day + ky))
+    const double dxy = (P.dealias_option == 1 || P.dealias_option == 3) ? __dadd_rn(__ldg(P.dax + kx), __ldg(P.day + ky))
                                                : ((P.dealias_option == 2) ? __ldg(P.dax + kx) : 0.0);
     const double dfy = (P.dealias_option == 2) ? __ldg(P.day + ky) : 0.0;
     LAPS_UNROLL
@@ -234,7 +238,7 @@ k_spec_z(const ZParams P) {
       double ksq = 0.0;
       if (need_ksq) {
         ksq = __dadd_rn(ksq_xy, __ldg(P.ksq_z + kz));
-        const double cee = (keep_bg && kz == 0) ? 0.0 : ce;
+        const double cee = (keep_bg && (P.bg_all_kz || kz == 0)) ? 0.0 : ce;
         fnl.x -= (cee * uo.x) * ksq;
         fnl.y -= (cee * uo.y) * ksq;
       }
@@ -258,6 +262,8 @@ k_spec_z(const ZParams P) {
       } else if (P.dealias_option == 2) {
         const double fz = __ldg(P.daz + kz);
         un = mk(__dmul_rn(__dmul_rn(__dmul_rn(un.x, dxy), dfy), fz), __dmul_rn(__dmul_rn(__dmul_rn(un.y, dxy), dfy), fz));
+      } else if (P.dealias_option == 3) {   // square truncation (2D/dealiasing.f90:102-117): per-axis flags
+        if (dxy != 0.0 || __ldg(P.daz + kz) != 0.0) un = mk(0.0, 0.0);
       }
       if (live) P.u_out[voff + kz] = un;
       r[e] = un;
@@ -285,9 +291,11 @@ k_spec_z(const ZParams P) {
     for (int e = 0; e < 8; ++e) {
       const int kz = u + e * G::NT;
       const double kzz = __ldg(P.kze + kz);
-      // k_{j+1} B_{j+2} - k_{j+2} B_{j+1}   with (k0,k1,k2) = (kx,ky,kz)
-      const double k1 = (j == 0) ? kye : (j == 1 ? kzz : kxe);
-      const double k2 = (j == 0) ? kzz : (j == 1 ? kxe : kye);
+      // k_{j+1} B_{j+2} - k_{j+2} B_{j+1}   with (k0,k1,k2) = (kx,ky,kz) of the REFERENCE axes; in the
+      // 2D tree the line axis carries the reference's ky and kz = 0 (2D/mhdrhs.f90:412-440)
+      const double ry = P.mode2d ? kzz : kye, rz = P.mode2d ? 0.0 : kzz;
+      const double k1 = (j == 0) ? ry : (j == 1 ? rz : kxe);
+      const double k2 = (j == 0) ? rz : (j == 1 ? kxe : ry);
       const cplx b1 = live ? B1[kz] : mk(0.0, 0.0);
       const cplx b2 = live ? B2[kz] : mk(0.0, 0.0);
       r[e] = csub(cmul_i(b2, k1), cmul_i(b1, k2));

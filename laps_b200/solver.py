@@ -98,8 +98,14 @@ class Solver:
         """mhd.f90:298-326 (asynchronous)."""
         self._ck(self._lib.laps_evolve(self._h))
 
-    def step(self) -> float:
-        """One pass of the Principal loop body (mhd.f90:245-248,285)."""
+    def step(self, calc_dt: bool = True) -> float:
+        """One pass of the Principal loop body (mhd.f90:245-248,285).  ``calc_dt=False`` leaves out
+        vardt, as the 2D tree's driver does on 19 steps out of 20 (2D/mhd.f90:237-240)."""
+        if not calc_dt:
+            self.evolve()
+            self.time = self.time + self.dt
+            self.evolve_radius(self.time)
+            return self.dt
         t = C.c_double(self.time)
         dt = C.c_double(self.dt)
         self._ck(self._lib.laps_step(self._h, C.byref(t), C.byref(dt)))

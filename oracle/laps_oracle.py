@@ -64,6 +64,9 @@ class Params:
     afx: float = 0.495
     afy: float = 0.495
     afz: float = 0.495
+    # 2D tree only (src_compressible/2D/mhd.f90:23,35,44; 2D/mhdinit.f90:23)
+    if_z_radial: bool = False
+    if_limit_dt_increase: bool = False
 
 
 # --------------------------------------------------------------------------------------
@@ -462,6 +465,165 @@ class State:
         return np.array([uu[7].sum() / n,
                          (pr[0] * uu[4] + pr[1] * uu[5] + pr[2] * uu[6]).sum() / n,
                          self.calc_max_divB()])
+
+
+# --------------------------------------------------------------------------------------
+# 2D tree (src_compressible/2D/): the same algorithm on an (nx, ny, 1) grid with kz = 0
+# --------------------------------------------------------------------------------------
+class State2D(State):
+    """Restatement of the 2D compressible tree; citations are relative to src_compressible/2D/.
+    Arrays keep the 3D shapes with nz = 1 ([v, 0, iy, ix]), exactly like the Fortran arrays
+    uu(ix,iy,1,v); the z transform of length 1 is the identity (2D/fftw.f90 has only x and y passes).
+    Not restated: the user-supplied external force (2D/mhdrhs.f90:480-531, if_external_force)."""
+
+    def __init__(self, p: Params):
+        assert p.nz == 1, "the 2D tree has nz = 1"
+        assert not (p.if_z_radial and p.if_corotating)          # 2D/mhd.f90:62-67
+        super().__init__(p)
+        self.k_square = self.g.KX ** 2 + self.g.KY ** 2 + 0.0 * self.g.KZ   # 2D/mhdinit.f90 grid_initialize
+
+    # 2D/AEBmod.f90:66-118
+    def update_ksquare(self):
+        p, g = self.p, self.g
+        kx, ky = g.KX, g.KY
+        r0, r = p.radius0, self.radius
+        if p.if_corotating:
+            c, s = self.cos_cor_ang, self.sin_cor_ang
+            self.k_square = (kx ** 2 * (c ** 2 + (s * r0 / r) ** 2)
+                             + ky ** 2 * (s ** 2 + (c * r0 / r) ** 2)
+                             + kx * ky * 2 * c * s * (1 - (r0 / r) ** 2)) + 0.0 * g.KZ
+        elif p.if_z_radial:
+            self.k_square = (kx * r0 / r) ** 2 + (ky * r0 / r) ** 2 + 0.0 * g.KZ
+        else:
+            self.k_square = kx ** 2 + (ky * r0 / r) ** 2 + 0.0 * g.KZ
+
+    # 2D/mhdrhs.f90:272-288 (also :412-428, 2D/mhd.f90:527-543)
+    def kvec(self):
+        p, g = self.p, self.g
+        r0, r = p.radius0, self.radius
+        kz = 0.0 * g.KZ
+        ky = g.KY * r0 / r
+        kx = g.KX + 0.0 * g.KY
+        if p.if_AEB and p.if_z_radial:
+            kx = kx * r0 / r
+        if p.if_AEB and p.if_corotating:
+            c, s = self.cos_cor_ang, self.sin_cor_ang
+            kx = g.KX * c + g.KY * s
+            ky = (-g.KX * s + g.KY * c) * r0 / r
+        return kx, ky, kz
+
+    def calc_flux(self):
+        """2D/mhdrhs.f90:23-128: as the 3D fluxes; the EBM source differs when the radial direction is z."""
+        flux, expand = super().calc_flux()
+        p = self.p
+        if p.if_AEB and p.if_z_radial:                           # 2D/mhdrhs.f90:96-100
+            uu, pr = self.uu, self.uu_prim
+            gam, tau = p.adiabatic_index, self.tau_exp
+            Bx, By, Bz = uu[4], uu[5], uu[6]
+            expand = (-2 * gam / (gam - 1) * pr[3] / tau
+                      - (Bx ** 2 + By ** 2 + 2.0 * Bz ** 2) / tau
+                      - (2 * uu[1] * pr[0] + 2 * uu[2] * pr[1] + uu[3] * pr[2]) / tau)
+        return flux, expand
+
+    def calc_rhs(self, flux_fourier, expand_fourier):
+        """2D/mhdrhs.f90:255-392."""
+        p = self.p
+        kxi, kyi, kzi = self.kvec()
+        kx, ky, kz = 1j * kxi, 1j * kyi, 1j * kzi
+        ff, uf = flux_fourier, self.uu_fourier
+        fnl = np.empty_like(uf)
+        fnl[0] = -(kx * ff[0] + ky * ff[1] + kz * ff[2])
+        fnl[1] = -(kx * ff[3] + ky * ff[4] + kz * ff[5])
+        fnl[2] = -(kx * ff[6] + ky * ff[7] + kz * ff[8])
+        fnl[3] = -(kx * ff[9] + ky * ff[10] + kz * ff[11])
+        fnl[4] = kz * ff[13] - ky * ff[14]
+        fnl[5] = kx * ff[14] - kz * ff[12]
+        fnl[6] = ky * ff[12] - kx * ff[13]
+        fnl[7] = -(kx * ff[15] + ky * ff[16] + kz * ff[17])
+        if p.if_AEB:
+            tau = self.tau_exp
+            coef = (2.0, 3.0, 3.0, 2.0, 1.0, 1.0, 2.0) if p.if_z_radial else (2.0, 2.0, 3.0, 3.0, 2.0, 1.0, 1.0)
+            for v, c in enumerate(coef):
+                fnl[v] = fnl[v] - c * uf[v] / tau
+            fnl[7] = fnl[7] + expand_fourier
+        if p.if_visc and p.if_visc_exp:
+            for v in (1, 2, 3):
+                fnl[v] = fnl[v] - p.viscosity * uf[v] * self.k_square
+        if p.if_resis and p.if_resis_exp:
+            ksq = np.broadcast_to(self.k_square, uf[0].shape).copy()
+            if p.if_conserve_background:
+                ksq[:, :, 0] = 0.0  # `cycle` where ix==1 (2D/mhdrhs.f90:372-374)
+            for v in (4, 5, 6):
+                fnl[v] = fnl[v] - p.resistivity * uf[v] * ksq
+        self.fnl = fnl
+        return fnl
+
+    def dealias(self):
+        """2D/dealiasing.f90:62-119 (option 3 = square truncation)."""
+        p, g = self.p, self.g
+        if p.dealias_option == 1:
+            tx = (g.wnx[: g.nxh] * p.Lx / (2 * PI * p.nx)) ** 2
+            ty = (g.wny * p.Ly / (2 * PI * p.ny)) ** 2
+            mask = np.sqrt(tx[None, None, :] + ty[None, :, None]) > (1.0 / 3.0)
+            self.uu_fourier[:, mask] = 0.0
+        elif p.dealias_option == 2:
+            fx, fy, _ = self._filters
+            self.uu_fourier = self.uu_fourier * fx[None, None, None, :] * fy[None, None, :, None]
+        elif p.dealias_option == 3:
+            rx = np.abs(g.wnx[: g.nxh] * p.Lx / (2 * PI * p.nx))
+            ry = np.abs(g.wny * p.Ly / (2 * PI * p.ny))
+            mask = (rx[None, None, :] > (1.0 / 3.0)) | (ry[None, :, None] > (1.0 / 3.0))
+            self.uu_fourier[:, mask] = 0.0
+
+    def vardt(self):
+        """2D/mhd.f90:296-406."""
+        p, g = self.p, self.g
+        uu, pr = self.uu, self.uu_prim
+        rho = uu[0]
+        csound2 = p.adiabatic_index * pr[3] / rho
+        sq = np.sqrt(rho)
+        ca = [uu[4] / sq, uu[5] / sq, uu[6] / sq]
+        cms2 = csound2 + (ca[0] ** 2 + ca[1] ** 2 + ca[2] ** 2)
+        s2 = math.sqrt(2.0)
+        cmax = []
+        for d in (0, 1):
+            cns2 = np.sqrt(np.maximum(cms2 ** 2 - 4 * csound2 * ca[d] ** 2, 0.0))
+            cfast = np.sqrt(cms2 + cns2) / s2
+            cslow = np.sqrt(np.maximum(cms2 - cns2, 0.0)) / s2
+            u = pr[d]
+            c = np.abs(u + cfast)
+            for t in (np.abs(u + cslow), np.abs(u + ca[d]), np.abs(u - cfast), np.abs(u - cslow),
+                      np.abs(u - ca[d]), np.abs(u)):
+                c = np.maximum(c, t)
+            cmax.append(c)
+        if p.if_resis and p.if_resis_exp:                        # 2D/mhd.f90:361-364
+            cmax[0] = np.maximum(cmax[0], p.resistivity / g.dx)
+            cmax[1] = np.maximum(cmax[1], p.resistivity / g.dy)
+        if p.if_hall:                                            # 2D/mhd.f90:366-374
+            ch = p.ion_inertial_length / rho * np.maximum(np.maximum(uu[4], uu[5]), uu[6]) / min(g.dx, g.dy)
+            cmax[0] = np.maximum(cmax[0], ch)
+            cmax[1] = np.maximum(cmax[1], ch)
+        dtx = g.dx / cmax[0]
+        if p.if_AEB and p.if_z_radial:
+            dtx = dtx * (self.radius / p.radius0)
+        dty = g.dy / cmax[1] * (self.radius / p.radius0)
+        dtmin = float(np.minimum(dtx, dty).min()) * p.cfl
+        if p.if_limit_dt_increase:                               # 2D/mhd.f90:396-404
+            if self.dt == 0.0 or self.dt > 1.02 * dtmin:
+                self.dt = dtmin
+        elif self.dt < 0.98 * dtmin or self.dt > 1.02 * dtmin:
+            self.dt = dtmin
+        self.rkt_init(self.dt)
+        return self.dt
+
+    def step(self, calc_dt: bool = True):
+        """2D/mhd.f90:209-240: evolve; time+=dt; evolve_radius; vardt (the driver calls vardt only every
+        dstep_calcdt = 20 steps: pass calc_dt=False for the steps in between)."""
+        self.evolve()
+        self.time = self.time + self.dt
+        self.evolve_radius(self.time)
+        if calc_dt:
+            self.vardt()
 
 
 # --------------------------------------------------------------------------------------

@@ -30,7 +30,46 @@ def make_case(nx, ny, nz, hall=True, aeb=True, corot=False, dealias=1, visc=True
     return p, prim
 
 
+def make_case_2d(nx, ny, hall=True, aeb=True, z_radial=False, dealias=1, visc=True, resis=True, explicit=False,
+                 conserve_bg=False, limit_dt=False, seed=3):
+    """2D tree (src_compressible/2D): oracle parameters + smooth random primitive data on (nx, ny, 1)."""
+    p = lo.Params(nx=nx, ny=ny, nz=1, Lx=24.0, Ly=12.0, Lz=1.0, adiabatic_index=1.666667,
+                  if_resis=resis, resistivity=1e-4 if not explicit else 1e-3, if_resis_exp=explicit,
+                  if_visc=visc, viscosity=1e-4 if not explicit else 1e-3, if_visc_exp=explicit,
+                  if_conserve_background=conserve_bg, cfl=0.5, dealias_option=dealias,
+                  if_AEB=aeb, radius0=30.0, Ur0=1.167 if aeb else 0.0, if_z_radial=z_radial,
+                  if_hall=hall, ion_inertial_length=0.2 if hall else 0.0, if_limit_dt_increase=limit_dt)
+    rng = np.random.default_rng(seed)
+    x = 2 * np.pi * np.arange(nx) / nx
+    y = 2 * np.pi * np.arange(ny) / ny
+    Y, X = np.meshgrid(y, x, indexing="ij")
+
+    def smooth(amp):
+        f = np.zeros((ny, nx))
+        for kx in range(0, 3):
+            for ky in range(-2, 3):
+                if kx == 0 and ky <= 0:
+                    continue
+                f += rng.standard_normal() * np.cos(kx * X + ky * Y + rng.uniform(0, 2 * np.pi)) / (kx * kx + ky * ky)
+        return amp * f
+
+    prim = np.zeros((8, 1, ny, nx))
+    prim[0, 0] = 1.0 + smooth(0.01)
+    for v in (1, 2, 3):
+        prim[v, 0] = smooth(0.1)
+    prim[4, 0] = 1.0 + smooth(0.1)
+    prim[5, 0] = smooth(0.1)
+    prim[6, 0] = 0.3 + smooth(0.1)
+    prim[7, 0] = 1.0 + smooth(0.02)
+    return p, prim
+
+
 def solver_kwargs(p: lo.Params):
+    extra = dict(ndim=2, if_z_radial=p.if_z_radial, if_limit_dt_increase=p.if_limit_dt_increase) if p.nz == 1 else {}
+    return dict(**extra, **_solver_kwargs(p))
+
+
+def _solver_kwargs(p: lo.Params):
     return dict(nx=p.nx, ny=p.ny, nz=p.nz, Lx=p.Lx, Ly=p.Ly, Lz=p.Lz, adiabatic_index=p.adiabatic_index,
                 if_resis=p.if_resis, if_resis_exp=p.if_resis_exp, resistivity=p.resistivity,
                 if_visc=p.if_visc, if_visc_exp=p.if_visc_exp, viscosity=p.viscosity,
@@ -42,7 +81,7 @@ def solver_kwargs(p: lo.Params):
 
 def run_both(p, prim, nsteps, lib_path=None, t0=0.0):
     """Drive oracle and library exactly as mhd.f90 does: [set time]; vardt; nsteps x step."""
-    o = lo.State(p)
+    o = lo.State2D(p) if p.nz == 1 else lo.State(p)
     o.set_primitive(prim)
     g = Solver(lib_path, **solver_kwargs(p))
     g.set_primitive(prim)

@@ -35,6 +35,16 @@ def test_one_step(emu, kw):
     g.close()
 
 
+@pytest.mark.parametrize("kw", [dict(hall=True, aeb=True, dealias=1), dict(hall=True, aeb=True, z_radial=True, dealias=3),
+                                dict(hall=False, aeb=False, dealias=2, explicit=True, conserve_bg=True, limit_dt=True)])
+def test_one_step_2d_tree(emu, kw):
+    p, prim = pc.make_case_2d(32, 16, **kw)
+    o, g = pc.run_both(p, prim, 2, lib_path=emu)
+    pc.check_state(o, g, 1e-11)
+    pc.check_diagnostics(o, g, 1e-9)
+    g.close()
+
+
 def test_synthetic_slab_matches_the_mode_sum():
     p = lo.Params(nx=16, ny=32, nz=24, Lx=24.0, Ly=20.0, Lz=12.0)
     prim = lo.ic_uniform_background(p, bx0=1.0, by0=0.3, press0=1.0)

@@ -13,7 +13,7 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_multi_gpu_one_step_parity(world):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
