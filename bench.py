@@ -109,20 +109,23 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # algorithmic bytes per launch of each kernel; R, C in bytes per field
 # ------------------------------------------------------------------------------------------
-def kernel_bytes(name, R, C, nf, ni, hall):
-    """Algorithmic HBM bytes of one launch (DESIGN.md section 5).  Pass launches carry their field
-    count in the name (fwd_x19, inv_y11, inv_y3 ...)."""
+def kernel_bytes(name, R, C, nf, ni, hall, fx=1.0, fy=1.0, fyl=1.0):
+    """Algorithmic HBM bytes of one launch (DESIGN.md section 4).  Pass launches carry their field
+    count in the name (fwd_x19, inv_y11, inv_y3 ...).  fx, fy = fractions of the kx columns / ky rows
+    that survive the dealiasing mask (the passes skip the rest exactly, laps_get_pruning); fyl = the
+    same for the ky rows this rank owns."""
     import re
     m = re.fullmatch(r"(fwd_x|fwd_y|inv_y|inv_x)(\d+)", name)
     if m:
         k, n = m.group(1), int(m.group(2))
-        return {"fwd_x": n * R + n * C, "fwd_y": 2 * n * C, "inv_y": 2 * n * C, "inv_x": n * C + n * R}[k]
+        return {"fwd_x": n * R + n * C * fx, "fwd_y": n * C * fx + n * C * fx * fy,
+                "inv_y": n * C * fx * fy + n * C * fx, "inv_x": n * C * fx + n * R}[k]
     table = {
         "flux": (8 + (3 if hall else 0)) * R + nf * R,
         # reads nf flux spectra + u (8C) + fnl_rk (8C, stages 2,3), writes u (8C) + fnl_rk (8C, stages 1,2)
         # + inverse-z output (8C): averaged over the three stages
-        "spec_z": (nf + 8 + 8 * 2 / 3 + 8 + 8 * 2 / 3 + 8) * C,
-        "curl_b_inv_z": 3 * C + 3 * C,
+        "spec_z": (nf + 8 + 8 * 2 / 3 + 8 + 8 * 2 / 3 + 8) * C * fx * fyl,
+        "curl_b_inv_z": (3 * C + 3 * C) * fx * fyl,
         "fwd_z": 2 * 8 * C,
         "cfl": 8 * R,
     }
@@ -292,6 +295,9 @@ def run_gpu(args):
     R = 8.0 * n * n * g.nzl
     C = 16.0 * g.nxh * g.nyl * n
     nf, ni, hall = 18 + kw["if_AEB"], 8 + 3 * kw["if_hall"], bool(kw["if_hall"])
+    nkx, kymax, nkyl = g.pruning()
+    fx, fy, fyl = nkx / g.nxh, min(1.0, (2 * kymax + 1) / n), nkyl / g.nyl
+    kb = lambda k: kernel_bytes(k, R, C, nf, ni, hall, fx, fy, fyl)  # noqa: E731
     peak, peak_src = peaks()
     top = max(prof.items(), key=lambda kv: kv[1][0]) if prof else None
     roofline = None
@@ -300,14 +306,15 @@ def run_gpu(args):
         tot = sum(v[0] for v in prof.values())
         shares = {k: round(v[0] / tot, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
         name, (tms, cnt) = top
-        b = kernel_bytes(name, R, C, nf, ni, hall)
+        b = kb(name)
         avg_ms = tms / cnt
         ach = b / (avg_ms * 1e-3) / 1e9 if b else None
         roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
                     "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": b,
-                    "per_kernel_GBps": {k: (kernel_bytes(k, R, C, nf, ni, hall) or 0) / (v[0] / v[1] * 1e-3) / 1e9
-                                        for k, v in prof.items() if kernel_bytes(k, R, C, nf, ni, hall)},
+                    "per_kernel_GBps": {k: (kb(k) or 0) / (v[0] / v[1] * 1e-3) / 1e9 for k, v in prof.items() if kb(k)},
+                    "pruning": {"nkx": nkx, "nxh": g.nxh, "kymax": kymax, "ny": n, "nky_local": nkyl,
+                                "what": "columns removed by the dealiasing mask are skipped exactly (bit-identical state)"},
                     "time_share": shares}
 
     barrier()          # no rank may free its exchange buffers while a peer can still store into them

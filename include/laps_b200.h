@@ -134,6 +134,13 @@ int laps_fft_inverse(laps_handle h, const double* spec_in, int32_t nfields, doub
  * out = int64 pairs (rank, offset), nxh*ny*z_size of them. */
 int laps_transpose_yz_indexmap(laps_handle h, int64_t* out);
 
+/* Work the passes skip exactly.  With dealias_option 1 (or 3 in 2D) every mode with kx >= *nkx, or with
+ * *kymax < ky < ny - *kymax, is zeroed by the mask at the end of every stage (dealiasing.f90:87-99), so
+ * the passes of a stage neither compute nor move those columns; the state is bit-identical to the
+ * unpruned computation (tests/…::test_mask_pruning_is_bit_exact).  *nky_local = this rank's surviving
+ * ky rows.  No pruning: *nkx = nx/2+1, *kymax = ny/2, *nky_local = y_size. */
+int laps_get_pruning(laps_handle h, int32_t* nkx, int32_t* kymax, int32_t* nky_local);
+
 /* Device-time of the last laps_evolve/laps_step in milliseconds (CUDA events on the compute
  * stream), and the number of kernel launches it issued. */
 int laps_last_step_ms(laps_handle h, float* ms, int32_t* launches);

@@ -52,7 +52,7 @@ struct Tile {
 template <int N, int TL>
 __global__ void __launch_bounds__(Tile<N, TL>::NTHREADS, Tile<N, TL>::MINB)
 k_fwd_x(const double* __restrict__ in, size_t in_fstride, cplx* __restrict__ W1,
-        int nzl, int ny, const cplx* __restrict__ tw, double scale) {
+        int nzl, int ny, const cplx* __restrict__ tw, double scale, int nkx) {
   typedef Geom<N> G;
   typedef Fft<N, -1> F;
   typedef Tile<N, TL> T;
@@ -85,7 +85,7 @@ k_fwd_x(const double* __restrict__ in, size_t in_fstride, cplx* __restrict__ W1,
   LAPS_UNROLL
   for (int i = 0; i < ITERS; ++i) {
     const int it = tid + i * T::NTHREADS;
-    if (it < TOT) {
+    if (it < nkx * TL) {   // nkx <= N/2+1: columns beyond it are removed by the dealiasing mask anyway
       const int lp = it % TL, k = it / TL;
       const cplx zk = sm[lp * T::PITCH + G::pad(k)];
       const cplx zn = sm[lp * T::PITCH + G::pad((N - k) & (N - 1))];
@@ -103,7 +103,7 @@ k_fwd_x(const double* __restrict__ in, size_t in_fstride, cplx* __restrict__ W1,
 template <int N, int TL>
 __global__ void __launch_bounds__(Tile<N, TL>::NTHREADS, Tile<N, TL>::MINB)
 k_fwd_y(const cplx* __restrict__ W1, PeerTable W2, int nzl, int nz, int zoff,
-        const cplx* __restrict__ tw, double scale) {
+        const cplx* __restrict__ tw, double scale, int nxh, int kymax) {
   typedef Geom<N> G;
   typedef Fft<N, -1> F;
   typedef Tile<N, TL> T;
@@ -113,7 +113,6 @@ k_fwd_y(const cplx* __restrict__ W1, PeerTable W2, int nzl, int nz, int zoff,
   const int kx = blockIdx.x / ztiles;
   const int z0 = (blockIdx.x % ztiles) * TL;
   const int f = blockIdx.y;
-  const int nxh = gridDim.x / ztiles;
   {
     const int l = tid / G::NT, u = tid % G::NT;  // mapping A: coalesced along the line
     cplx r[8];
@@ -134,6 +133,7 @@ k_fwd_y(const cplx* __restrict__ W1, PeerTable W2, int nzl, int nz, int zoff,
     LAPS_UNROLL
     for (int e = 0; e < 8; ++e) {
       const int ky = F::kout(u, e);
+      if (ky > kymax && ky < N - kymax) continue;   // rows the dealiasing mask removes entirely
       const int p = W2.owner(ky);
       cplx* dst = W2.base[p] + (((size_t)f * nxh + kx) * W2.len[p] + (ky - W2.off[p])) * nz + zoff + z0 + l;
       *dst = cscale(r[e], scale);
@@ -146,7 +146,7 @@ k_fwd_y(const cplx* __restrict__ W1, PeerTable W2, int nzl, int nz, int zoff,
 // (fftw.f90:212-218, unnormalised).  grid.x = ceil(nzl/TL) * nxh, grid.y = fields
 template <int N, int TL>
 __global__ void __launch_bounds__(Tile<N, TL>::NTHREADS, Tile<N, TL>::MINB)
-k_inv_y(const cplx* __restrict__ V1, cplx* __restrict__ V2, int nzl, const cplx* __restrict__ tw) {
+k_inv_y(const cplx* __restrict__ V1, cplx* __restrict__ V2, int nzl, const cplx* __restrict__ tw, int nxh, int kymax) {
   typedef Geom<N> G;
   typedef Fft<N, +1> F;
   typedef Tile<N, TL> T;
@@ -156,14 +156,16 @@ k_inv_y(const cplx* __restrict__ V1, cplx* __restrict__ V2, int nzl, const cplx*
   const int kx = blockIdx.x / ztiles;
   const int z0 = (blockIdx.x % ztiles) * TL;
   const int g = blockIdx.y;
-  const int nxh = gridDim.x / ztiles;
   {
     const int l = tid % TL, u = tid / TL;  // mapping B
     cplx r[8];
     if (z0 + l < nzl) {
       const cplx* src = V1 + (((size_t)g * nxh + kx) * N) * nzl + z0 + l;
       LAPS_UNROLL
-      for (int e = 0; e < 8; ++e) r[e] = src[(size_t)(u + e * G::NT) * nzl];
+      for (int e = 0; e < 8; ++e) {
+        const int ky = u + e * G::NT;
+        r[e] = (ky > kymax && ky < N - kymax) ? mk(0.0, 0.0) : src[(size_t)ky * nzl];   // masked rows are zero
+      }
     } else {
       LAPS_UNROLL
       for (int e = 0; e < 8; ++e) r[e] = mk(0.0, 0.0);
@@ -188,7 +190,7 @@ struct RealDst { double* ptr[16]; };
 
 template <int N, int TL>
 __global__ void __launch_bounds__(Tile<N, TL>::NTHREADS, Tile<N, TL>::MINB)
-k_inv_x(const cplx* __restrict__ V2, RealDst dst, int nzl, int ny, const cplx* __restrict__ tw) {
+k_inv_x(const cplx* __restrict__ V2, RealDst dst, int nzl, int ny, const cplx* __restrict__ tw, int nkx) {
   typedef Geom<N> G;
   typedef Fft<N, +1> F;
   typedef Tile<N, TL> T;
@@ -206,7 +208,8 @@ k_inv_x(const cplx* __restrict__ V2, RealDst dst, int nzl, int ny, const cplx* _
     LAPS_UNROLL
     for (int i = 0; i < ITERS; ++i) {
       const int it = tid + i * T::NTHREADS;
-      if (it < TOT) {
+      a[i] = mk(0.0, 0.0); b[i] = mk(0.0, 0.0);
+      if (it < nkx * TL) {   // columns beyond nkx are zero (dealiasing mask)
         const int lp = it % TL, k = it / TL;
         ld256(V2 + (((size_t)g * nxh + k) * nzl + zl) * ny + y0 + 2 * lp, a[i], b[i]);
       }

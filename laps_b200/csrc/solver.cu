@@ -108,6 +108,12 @@ struct laps_solver {
   XchgPeers xp;
   unsigned long long epoch = 0;
   bool wired = false;
+  // Work skipped exactly (dealias option 1 / 3): every mode with kx >= nkx, or with kymax < ky < ny-kymax,
+  // is zeroed by the mask at the end of each stage, so the passes of a stage neither compute nor
+  // move those columns.  nkx = nxh and kymax = ny/2 mean "no pruning".
+  int nkx = 0, kymax = 0, tune_prune = 1;
+  int pr_nkyl = 0, pr_nA = 0, pr_a0 = 0, pr_b0 = 0;   // this rank's surviving ky rows (see ZParams)
+  bool spectrum_full = true;   // the state still holds masked columns (fresh from laps_set_primitive)
   int slot[19];        // field slot of each flux (F1..F18, expand_term), < 0: not transformed
   int tune_cgz = 0, tune_z = 3, tune_rhs = 1, tune_rcg = 0;
   int num_sms = 148;
@@ -251,7 +257,7 @@ cudaError_t prepare_kernel(K kernel, size_t smem, int ctas) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 template <int N>
-int do_fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1) {
+int do_fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1, bool prune) {
   char name[32]; std::snprintf(name, sizeof(name), "fwd_x%d", nfields);
   constexpr int TL = tlx(N);
   typedef Tile<N, TL> T;
@@ -260,46 +266,48 @@ int do_fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1) {
   LaunchScope ls(s, name);
   dim3 grid((unsigned)(s->xz * (s->xy / (2 * TL))), (unsigned)nfields);
   LAPS_LAUNCH((k_fwd_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, in, fstride, W1, s->xz, s->xy, s->tw_x,
-              1.0 / N);
+              1.0 / N, prune ? s->nkx : s->nxh);
   return check_launch(s, "k_fwd_x");
 }
 
 template <int N>
-int do_fwd_y(S* s, const cplx* W1, int nfields) {
+int do_fwd_y(S* s, const cplx* W1, int nfields, bool prune) {
   char name[32]; std::snprintf(name, sizeof(name), "fwd_y%d", nfields);
   constexpr int TL = tly(N);
   typedef Tile<N, TL> T;
   LAPS_CK(s, prepare_kernel(k_fwd_y<N, TL>, T::SMEM, T::MINB));
   LaunchScope ls(s, name);
   const int ztiles = (s->nzl + TL - 1) / TL;
-  dim3 grid((unsigned)(ztiles * s->nxh), (unsigned)nfields);
+  dim3 grid((unsigned)(ztiles * (prune ? s->nkx : s->nxh)), (unsigned)nfields);
   LAPS_LAUNCH((k_fwd_y<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, W1, s->tabW2, s->nzl, s->nz, s->zo,
-              s->tw_y, 1.0 / N);
+              s->tw_y, 1.0 / N, s->nxh, prune ? s->kymax : N);
   return check_launch(s, "k_fwd_y");
 }
 
 template <int N>
-int do_inv_y(S* s, const cplx* V1, cplx* V2, int nfields) {
+int do_inv_y(S* s, const cplx* V1, cplx* V2, int nfields, bool prune) {
   char name[32]; std::snprintf(name, sizeof(name), "inv_y%d", nfields);
   constexpr int TL = tly(N);
   typedef Tile<N, TL> T;
   LAPS_CK(s, prepare_kernel(k_inv_y<N, TL>, T::SMEM, T::MINB));
   LaunchScope ls(s, name);
   const int ztiles = (s->nzl + TL - 1) / TL;
-  dim3 grid((unsigned)(ztiles * s->nxh), (unsigned)nfields);
-  LAPS_LAUNCH((k_inv_y<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, V1, V2, s->nzl, s->tw_y);
+  dim3 grid((unsigned)(ztiles * (prune ? s->nkx : s->nxh)), (unsigned)nfields);
+  LAPS_LAUNCH((k_inv_y<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, V1, V2, s->nzl, s->tw_y, s->nxh,
+              prune ? s->kymax : N);
   return check_launch(s, "k_inv_y");
 }
 
 template <int N>
-int do_inv_x(S* s, const cplx* V2, const RealDst& dst, int nfields) {
+int do_inv_x(S* s, const cplx* V2, const RealDst& dst, int nfields, bool prune) {
   char name[32]; std::snprintf(name, sizeof(name), "inv_x%d", nfields);
   constexpr int TL = tlx(N);
   typedef Tile<N, TL> T;
   LAPS_CK(s, prepare_kernel(k_inv_x<N, TL>, T::SMEM, T::MINB));
   LaunchScope ls(s, name);
   dim3 grid((unsigned)(s->xz * (s->xy / (2 * TL))), (unsigned)nfields);
-  LAPS_LAUNCH((k_inv_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, V2, dst, s->xz, s->xy, s->tw_x);
+  LAPS_LAUNCH((k_inv_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, V2, dst, s->xz, s->xy, s->tw_x,
+              prune ? s->nkx : s->nxh);
   return check_launch(s, "k_inv_x");
 }
 
@@ -308,7 +316,8 @@ int do_spec_z_cg(S* s, const ZParams& zp, int ntasks, const char* name) {
   typedef ZTile<N, CG> T;
   LAPS_CK(s, prepare_kernel(k_spec_z<N, CG>, T::SMEM, T::MINB));
   LaunchScope ls(s, name);
-  dim3 grid((unsigned)((s->ncol + CG - 1) / CG), (unsigned)ntasks);
+  if (zp.ncolc == 0) return 0;   // this rank owns no surviving column
+  dim3 grid((unsigned)((zp.ncolc + CG - 1) / CG), (unsigned)ntasks);
   LAPS_LAUNCH((k_spec_z<N, CG>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, zp);
   return check_launch(s, "k_spec_z");
 }
@@ -327,7 +336,8 @@ int do_rhs_z_cg(S* s, const ZParams& zp, int ntasks) {
   typedef RTile<N, CG> T;
   LAPS_CK(s, prepare_kernel(k_rhs_z<N, CG>, T::SMEM, T::MINB));
   LaunchScope ls(s, "spec_z");
-  const int ngroups = (int)((s->ncol + CG - 1) / CG);
+  if (zp.ncolc == 0) return 0;   // this rank owns no surviving column
+  const int ngroups = (zp.ncolc + CG - 1) / CG;
   const long long nitems = (long long)ngroups * ntasks;
   const long long wave = (long long)s->num_sms * T::MINB;
   dim3 grid((unsigned)std::min(nitems, wave));
@@ -356,19 +366,19 @@ int do_rhs_z(S* s, const ZParams& zp, int ntasks) {
     default: s->err = "unsupported line length"; return 1;          \
   }
 
-int fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1) { LAPS_DISPATCH(s->nx, do_fwd_x, s, in, fstride, nfields, W1) }
-int fwd_y(S* s, const cplx* W1, int nfields) { LAPS_DISPATCH(s->ny, do_fwd_y, s, W1, nfields) }
-int inv_y(S* s, const cplx* V1, cplx* V2, int nfields) { LAPS_DISPATCH(s->ny, do_inv_y, s, V1, V2, nfields) }
+int fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1, bool prune) { LAPS_DISPATCH(s->nx, do_fwd_x, s, in, fstride, nfields, W1, prune) }
+int fwd_y(S* s, const cplx* W1, int nfields, bool prune) { LAPS_DISPATCH(s->ny, do_fwd_y, s, W1, nfields, prune) }
+int inv_y(S* s, const cplx* V1, cplx* V2, int nfields, bool prune) { LAPS_DISPATCH(s->ny, do_inv_y, s, V1, V2, nfields, prune) }
 
 // Forward x (+y) passes of `nfields` real fields into the z-pass input buffer W2.  In the 2D tree
 // (grid held as (nx, 1, ny)) the post-x-pass layout [f][kx][1][y] IS the z-pass layout
 // [f][kx][ky_local=1][line], so the x pass writes W2 directly and there is no y pass.
-int forward_xy(S* s, const double* in, size_t fstride, int nfields) {
-  if (s->two_d) return fwd_x(s, in, fstride, nfields, (cplx*)s->bufZ);
-  LAPS_TRY(fwd_x(s, in, fstride, nfields, (cplx*)s->bufY));
-  return fwd_y(s, (const cplx*)s->bufY, nfields);
+int forward_xy(S* s, const double* in, size_t fstride, int nfields, bool prune) {
+  if (s->two_d) return fwd_x(s, in, fstride, nfields, (cplx*)s->bufZ, prune);
+  LAPS_TRY(fwd_x(s, in, fstride, nfields, (cplx*)s->bufY, prune));
+  return fwd_y(s, (const cplx*)s->bufY, nfields, prune);
 }
-int inv_x(S* s, const cplx* V2, const RealDst& dst, int nfields) { LAPS_DISPATCH(s->nx, do_inv_x, s, V2, dst, nfields) }
+int inv_x(S* s, const cplx* V2, const RealDst& dst, int nfields, bool prune) { LAPS_DISPATCH(s->nx, do_inv_x, s, V2, dst, nfields, prune) }
 int spec_z(S* s, const ZParams& zp, int ntasks, const char* name) { LAPS_DISPATCH(s->nz, do_spec_z, s, zp, ntasks, name) }
 int rhs_z(S* s, const ZParams& zp, int ntasks) { LAPS_DISPATCH(s->nz, do_rhs_z, s, zp, ntasks) }
 
@@ -379,8 +389,10 @@ cplx* buf_W1(S* s) { return (cplx*)s->bufY; }
 cplx* buf_V1(S* s) { return (cplx*)s->bufY; }
 cplx* buf_W2(S* s) { return (cplx*)s->bufZ; }
 
-void fill_zparams(S* s, ZParams& z) {
+void fill_zparams(S* s, ZParams& z, bool prune = false) {
   std::memset(&z, 0, sizeof(z));
+  if (prune) { z.nkyl = s->pr_nkyl; z.nA = s->pr_nA; z.a0 = s->pr_a0; z.b0 = s->pr_b0; z.ncolc = s->nkx * s->pr_nkyl; }
+  else { z.nkyl = s->nyl; z.nA = s->nyl; z.a0 = 0; z.b0 = 0; z.ncolc = (int)s->ncol; }
   const laps_params& p = s->p;
   z.nxh = s->nxh; z.ny = s->ny; z.nyl = s->nyl; z.yoff = s->yo; z.nz = s->nz; z.ncol = (int)s->ncol;
   z.W2 = buf_W2(s); z.fstride = s->csz;
@@ -418,8 +430,8 @@ ZTask rhs_task(int v, int gout, int fa, double ca, int fb, double cb, int fx, do
   return t;
 }
 
-int launch_current_tasks(S* s, const cplx* u) {  // J^ = i k x B^, inverse z  (mhdrhs.f90:296-339)
-  ZParams z; fill_zparams(s, z);
+int launch_current_tasks(S* s, const cplx* u, bool prune) {  // J^ = i k x B^, inverse z  (mhdrhs.f90:296-339)
+  ZParams z; fill_zparams(s, z, prune);
   z.u_in = u;
   for (int j = 0; j < 3; ++j) {
     ZTask t; std::memset(&t, 0, sizeof(t));
@@ -450,23 +462,25 @@ RealDst dst_state_and_current(S* s) {
 }
 
 // inverse y and x passes for V1 slots [g0, g0+n)
-int inverse_yx(S* s, int g0, int n) {
+int inverse_yx(S* s, int g0, int n, bool prune) {
   const size_t vs = (size_t)s->nxh * s->ny * s->nzl;
   RealDst d = dst_state_and_current(s), d2;
   std::memset(&d2, 0, sizeof(d2));
   for (int i = 0; i < n; ++i) d2.ptr[i] = d.ptr[g0 + i];
-  if (s->two_d) return inv_x(s, buf_V1(s) + (size_t)g0 * vs, d2, n);   // [g][kx][1][line] is already the x-pass layout
-  LAPS_TRY(inv_y(s, buf_V1(s) + (size_t)g0 * vs, buf_V2(s) + (size_t)g0 * vs, n));
-  return inv_x(s, buf_V2(s) + (size_t)g0 * vs, d2, n);
+  if (s->two_d) return inv_x(s, buf_V1(s) + (size_t)g0 * vs, d2, n, prune);   // [g][kx][1][line] is already the x-pass layout
+  LAPS_TRY(inv_y(s, buf_V1(s) + (size_t)g0 * vs, buf_V2(s) + (size_t)g0 * vs, n, prune));
+  return inv_x(s, buf_V2(s) + (size_t)g0 * vs, d2, n, prune);
 }
 
 // J from the current spectral state when the cached one is stale (first stage after
 // set_primitive or after the radius changed).
 int refresh_current(S* s) {
   if (!s->p.if_hall || !s->j_stale) return 0;
-  LAPS_TRY(launch_current_tasks(s, s->uA));
+  // the state may still hold masked columns here (first stage after laps_set_primitive): no pruning then
+  const bool prune = !s->spectrum_full;
+  LAPS_TRY(launch_current_tasks(s, s->uA, prune));
   LAPS_TRY(host_barrier(s));
-  LAPS_TRY(inverse_yx(s, 8, 3));
+  LAPS_TRY(inverse_yx(s, 8, 3, prune));
   s->j_stale = false;
   return 0;
 }
@@ -485,10 +499,10 @@ int stage(S* s, int irk) {
     LAPS_TRY(check_launch(s, "k_flux"));
   }
   // transform_flux_real_to_fourier (mhdrhs.f90:128-172)
-  LAPS_TRY(forward_xy(s, buf_F(s), s->npts, s->nf));
+  LAPS_TRY(forward_xy(s, buf_F(s), s->npts, s->nf, true));
   LAPS_TRY(host_barrier(s));
   {  // z-pass + calc_rhs + rkt + dealias + inverse z
-    ZParams z; fill_zparams(s, z);
+    ZParams z; fill_zparams(s, z, true);
     z.cc = s->cc1[irk]; z.dd = s->dd1[irk]; z.dt_irk = s->tstep[irk];
     z.read_rk = (irk > 0); z.write_rk = (irk < 2);
     const int* L = s->slot;   // flux index (0-based: F1..F18, expand_term) -> field slot
@@ -529,9 +543,16 @@ int stage(S* s, int irk) {
   // driver moves the radius (evolve_radius, mhd.f90:248) and with it the wave vectors J is built
   // from (mhdrhs.f90:313-326), so that J would be discarded: leave it to refresh_current.
   const bool want_j = p.if_hall && !(irk == 2 && s->Ur != 0.0);
-  if (want_j) LAPS_TRY(launch_current_tasks(s, s->uB));
+  if (want_j) LAPS_TRY(launch_current_tasks(s, s->uB, true));
   LAPS_TRY(host_barrier(s));
-  LAPS_TRY(inverse_yx(s, 0, want_j ? 11 : 8));
+  LAPS_TRY(inverse_yx(s, 0, want_j ? 11 : 8, true));
+  if (s->spectrum_full) {
+    // First stage after laps_set_primitive: the buffer just read still holds the unmasked initial
+    // spectrum; it becomes the output buffer of the next stage, which writes surviving columns only.
+    if (s->nkx < s->nxh || s->kymax < s->ny / 2)
+      LAPS_CK(s, cudaMemsetAsync(s->uA, 0, 8 * s->csz * sizeof(cplx), s->stream));
+    s->spectrum_full = false;
+  }
   std::swap(s->uA, s->uB);
   s->j_stale = p.if_hall && !want_j;
   return 0;
@@ -686,6 +707,38 @@ int laps_create(const laps_params* params, laps_handle* out) {
     if (cudaMemcpy(d, t.data(), n * sizeof(cplx), cudaMemcpyHostToDevice) != cudaSuccess) return fail("twiddle upload failed");
   }
   if (upload_tables(s)) return fail(s->err);
+  {  // columns the dealiasing mask removes entirely (see laps_solver::nkx)
+    if (const char* e = std::getenv("LAPS_TUNE_PRUNE")) s->tune_prune = std::atoi(e);
+    const double* dax = s->h_tab.data() + 2 * (s->nxh + s->ny + s->nz);
+    const double* day = dax + s->nxh;
+    s->nkx = s->nxh; s->kymax = s->ny / 2;
+    if (s->tune_prune && (p.dealias_option == 1 || p.dealias_option == 3)) {
+      // option 1: the test is fl(fl(tx+ty)+tz) >= T with non-negative terms, and floating-point addition
+      // is monotonic, so tx >= T (or ty >= T) alone already removes the mode.  option 3: per-axis flags.
+      auto gone = [&](double t) { return p.dealias_option == 1 ? t >= s->da_thresh : t != 0.0; };
+      int nk = 0;
+      while (nk < s->nxh && !gone(dax[nk])) ++nk;
+      bool tail_gone = true;
+      for (int i = nk; i < s->nxh; ++i) tail_gone = tail_gone && gone(dax[i]);
+      if (tail_gone && nk >= 1) s->nkx = nk;
+      if (!s->two_d) {
+        int km = 0;
+        while (km + 1 <= s->ny / 2 && !gone(day[km + 1])) ++km;
+        bool mid_gone = true;
+        for (int j = km + 1; j < s->ny - km; ++j) mid_gone = mid_gone && gone(day[j]);
+        if (mid_gone) s->kymax = km;
+      }
+    }
+    // this rank's surviving ky rows: run A = owned rows with ky <= kymax, run B = owned rows with ky >= ny - kymax
+    const int y0 = s->yo, y1 = s->yo + s->nyl;
+    const int aEnd = std::min(y1, s->kymax + 1);
+    s->pr_a0 = 0; s->pr_nA = std::max(0, aEnd - y0);
+    const int bBeg = std::max(std::max(y0, s->ny - s->kymax), y0 + s->pr_nA);
+    s->pr_b0 = bBeg - y0;
+    const int nB = std::max(0, y1 - bBeg);
+    s->pr_nkyl = s->pr_nA + nB;
+    if (s->kymax >= s->ny / 2) { s->pr_nkyl = s->nyl; s->pr_nA = s->nyl; s->pr_a0 = 0; s->pr_b0 = 0; }
+  }
   cudaMemsetAsync(s->rk, 0, 8 * s->csz * sizeof(cplx), s->stream);
 
   // single rank: the exchange tables point at this rank's own buffers
@@ -758,7 +811,9 @@ int laps_set_primitive(laps_handle s, const double* uu_local) {
     LAPS_TRY(check_launch(s, "k_prim_to_cons"));
   }
   // transform_uu_real_to_fourier (fftw.f90:42-71)
-  LAPS_TRY(forward_xy(s, s->uu, s->npts, 8));
+  LAPS_TRY(forward_xy(s, s->uu, s->npts, 8, false));
+  LAPS_CK(s, cudaMemsetAsync(s->uB, 0, 8 * s->csz * sizeof(cplx), s->stream));   // masked columns of the first output
+  s->spectrum_full = true;
   LAPS_TRY(host_barrier(s));
   ZParams z; fill_zparams(s, z);
   z.u_out = s->uA;
@@ -864,6 +919,14 @@ int laps_last_step_ms(laps_handle s, float* ms, int32_t* launches) {
   LAPS_CK(s, cudaEventSynchronize(s->ev1));
   if (ms) LAPS_CK(s, cudaEventElapsedTime(ms, s->ev0, s->ev1));
   if (launches) *launches = s->launches;
+  return 0;
+}
+
+int laps_get_pruning(laps_handle s, int32_t* nkx, int32_t* kymax, int32_t* nky_local) {
+  if (!s) return 1;
+  if (nkx) *nkx = s->nkx;
+  if (kymax) *kymax = s->kymax;
+  if (nky_local) *nky_local = s->pr_nkyl;
   return 0;
 }
 
@@ -976,7 +1039,7 @@ int laps_fft_forward(laps_handle s, const double* real_fields, int32_t nfields, 
   if (nfields < 1 || nfields > 8) { s->err = "laps_fft_forward: 1..8 fields per call"; return 1; }
   // uses the flux work buffers and u_B as scratch; the state (u_A, uu) is untouched
   LAPS_CK(s, cudaMemcpyAsync(buf_F(s), real_fields, (size_t)nfields * s->npts * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-  LAPS_TRY(forward_xy(s, buf_F(s), s->npts, nfields));
+  LAPS_TRY(forward_xy(s, buf_F(s), s->npts, nfields, false));
   LAPS_TRY(host_barrier(s));
   ZParams z; fill_zparams(s, z);
   z.u_out = s->uB;
@@ -987,6 +1050,7 @@ int laps_fft_forward(laps_handle s, const double* real_fields, int32_t nfields, 
   }
   LAPS_TRY(spec_z(s, z, nfields, "fwd_z"));
   LAPS_CK(s, cudaMemcpyAsync(spec_out, s->uB, (size_t)nfields * s->csz * sizeof(cplx), cudaMemcpyDeviceToHost, s->stream));
+  LAPS_CK(s, cudaMemsetAsync(s->uB, 0, 8 * s->csz * sizeof(cplx), s->stream));   // u_B must keep its masked columns zero
   LAPS_CK(s, cudaStreamSynchronize(s->stream));
   LAPS_TRY(host_barrier(s));
   return 0;
@@ -1004,17 +1068,18 @@ int laps_fft_inverse(laps_handle s, const double* spec_in, int32_t nfields, doub
     z.task[v] = t;
   }
   LAPS_TRY(spec_z(s, z, nfields, "inv_z"));
+  LAPS_CK(s, cudaMemsetAsync(s->uB, 0, 8 * s->csz * sizeof(cplx), s->stream));   // u_B must keep its masked columns zero
   LAPS_TRY(host_barrier(s));
   const size_t vs = (size_t)s->nxh * s->ny * s->nzl;
   (void)vs;
-  if (!s->two_d) LAPS_TRY(inv_y(s, buf_V1(s), buf_V2(s), nfields));
+  if (!s->two_d) LAPS_TRY(inv_y(s, buf_V1(s), buf_V2(s), nfields, false));
   // real output goes to the flux scratch area?  bufX holds V2; use the prim scratch / J-free area:
   // write into a temporary device buffer
   double* tmp = nullptr;
   LAPS_CK(s, cudaMalloc((void**)&tmp, (size_t)nfields * s->npts * sizeof(double)));
   RealDst d; std::memset(&d, 0, sizeof(d));
   for (int v = 0; v < nfields; ++v) d.ptr[v] = tmp + (size_t)v * s->npts;
-  int rc = inv_x(s, s->two_d ? buf_V1(s) : buf_V2(s), d, nfields);
+  int rc = inv_x(s, s->two_d ? buf_V1(s) : buf_V2(s), d, nfields, false);
   if (!rc) {
     cudaError_t e = cudaMemcpyAsync(real_out, tmp, (size_t)nfields * s->npts * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);

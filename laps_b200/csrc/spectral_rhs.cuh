@@ -76,18 +76,25 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
     cp_async_commit();
   };
 
+  // compact column index -> memory column (see ZParams); -1 past the end
+  auto column_of = [&](int cc) -> int {
+    if (cc >= P.ncolc) return -1;
+    const int kr = cc % P.nkyl;
+    return (cc / P.nkyl) * P.nyl + (kr < P.nA ? P.a0 + kr : P.b0 + kr - P.nA);
+  };
   int item = blockIdx.x;
   if (item < nitems) {  // prologue: the first item's fc
     const ZTask& K = P.task[item % ntasks];
-    const int col = (item / ntasks) * CG + l;
-    land_in(S, P.W2 + (size_t)(K.fc >= 0 ? K.fc : 0) * P.fstride + (size_t)col * N, K.fc >= 0 && col < P.ncol);
+    const int col = column_of((item / ntasks) * CG + l);
+    land_in(S, P.W2 + (size_t)(K.fc >= 0 ? K.fc : 0) * P.fstride + (size_t)(col < 0 ? 0 : col) * N, K.fc >= 0 && col >= 0);
   }
   for (; item < nitems; item += gridDim.x) {
     const ZTask& K = P.task[item % ntasks];
-    const int col = (item / ntasks) * CG + l;
-    const bool live = col < P.ncol;
-    const int kx = live ? col / P.nyl : 0;
-    const int ky = live ? P.yoff + col % P.nyl : 0;
+    const int colm = column_of((item / ntasks) * CG + l);
+    const bool live = colm >= 0;
+    const int col = live ? colm : 0;
+    const int kx = col / P.nyl;
+    const int ky = P.yoff + col % P.nyl;
     const size_t coff = (size_t)col * N;
     const size_t voff = (size_t)K.v * P.fstride + coff;
     const bool hasC = K.fc >= 0;
@@ -100,8 +107,8 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
       const int nxt = item + gridDim.x;
       if (nxt < nitems) {
         const ZTask& Kn = P.task[nxt % ntasks];
-        const int coln = (nxt / ntasks) * CG + l;
-        if (coln < P.ncol) {
+        const int coln = column_of((nxt / ntasks) * CG + l);
+        if (coln >= 0) {
           const size_t po = (size_t)coln * N + (size_t)u * (N / G::NT);
           if (Kn.fa >= 0) prefetch_l2(P.W2 + (size_t)Kn.fa * P.fstride + po);
           if (Kn.fb >= 0) prefetch_l2(P.W2 + (size_t)Kn.fb * P.fstride + po);
@@ -225,8 +232,8 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
       const int nxt = item + gridDim.x;
       if (nxt < nitems) {
         const ZTask& Kn = P.task[nxt % ntasks];
-        const int coln = (nxt / ntasks) * CG + l;
-        land_in(S, P.W2 + (size_t)(Kn.fc >= 0 ? Kn.fc : 0) * P.fstride + (size_t)coln * N, Kn.fc >= 0 && coln < P.ncol);
+        const int coln = column_of((nxt / ntasks) * CG + l);
+        land_in(S, P.W2 + (size_t)(Kn.fc >= 0 ? Kn.fc : 0) * P.fstride + (size_t)(coln < 0 ? 0 : coln) * N, Kn.fc >= 0 && coln >= 0);
       } else {
         cp_async_commit();
       }

@@ -63,6 +63,11 @@ struct ZParams {
   int dealias_option;
   int read_rk, write_rk;
   double scale;          // 1/nz
+  // Columns the kernels visit: compact index c in [0, ncolc) -> kx = c / nkyl, and the local ky index
+  // kyl = (r < nA ? a0 + r : b0 + r - nA), r = c % nkyl: the locally owned ky rows that survive the
+  // dealiasing mask form at most two runs (ky <= kymax and ky >= ny - kymax).  Without pruning
+  // ncolc = ncol, nkyl = nA = nyl, a0 = 0.
+  int ncolc, nkyl, nA, a0, b0;
   int mode2d;            // 2D tree: the line axis is the reference's y, d/dz = 0 (src_compressible/2D/mhdrhs.f90:272)
   int z_radial;          // 2D/mhdrhs.f90:278-280: kx is stretched too
   int bg_all_kz;         // 2D/mhdrhs.f90:372-374: if_conserve_background skips every mode with ix == 1
@@ -125,10 +130,13 @@ k_spec_z(const ZParams P) {
   const ZTask& K = P.task[blockIdx.y];
   const int tid = threadIdx.x;
   const int l = tid / G::NT, u = tid % G::NT;
-  const int col = blockIdx.x * CG + l;
-  const bool live = col < P.ncol;
-  const int kx = live ? col / P.nyl : 0;
-  const int ky = live ? P.yoff + col % P.nyl : 0;
+  const int cc = blockIdx.x * CG + l;
+  const bool live = cc < P.ncolc;
+  const int kx = live ? cc / P.nkyl : 0;
+  const int kr = live ? cc % P.nkyl : 0;
+  const int kyl = kr < P.nA ? P.a0 + kr : P.b0 + kr - P.nA;
+  const int ky = P.yoff + kyl;
+  const int col = kx * P.nyl + kyl;
   cplx* lineG = sm + l * T::COLSTRIDE;
   cplx* stash = lineG + T::PITCH;          // thread-private slots e*NT + u
   const size_t coff = (size_t)col * N;

@@ -182,6 +182,12 @@ class Solver:
         self._ck(self._lib.laps_last_step_ms(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def pruning(self):
+        """(nkx, kymax, nky_local): the columns that survive the dealiasing mask (laps_get_pruning)."""
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        self._ck(self._lib.laps_get_pruning(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     def set_profiling(self, on: bool):
         self._ck(self._lib.laps_set_profiling(self._h, 1 if on else 0))
 

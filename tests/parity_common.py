@@ -150,3 +150,27 @@ def check_diagnostics(o, g, tol):
     else:
         assert abs(inv[2] - oinv[2]) <= max(1e3 * tol, 1e-7) * oinv[2], (inv[2], oinv[2])
     assert abs(g.calc_max_divB() - inv[2]) == 0.0
+
+
+def check_pruning_is_exact(shape, nsteps, lib_path=None, **case):
+    """The passes skip the columns the dealiasing mask removes (LAPS_TUNE_PRUNE, default on).  The
+    state must be BIT-IDENTICAL to a run that computes and moves everything."""
+    import os
+    p, prim = (make_case_2d(*shape, **case) if len(shape) == 2 else make_case(*shape, **case))
+    out = []
+    for flag in ("0", "1"):
+        os.environ["LAPS_TUNE_PRUNE"] = flag
+        try:
+            g = Solver(lib_path, **solver_kwargs(p))
+        finally:
+            del os.environ["LAPS_TUNE_PRUNE"]
+        g.set_primitive(prim)
+        g.vardt()
+        for _ in range(nsteps):
+            g.step()
+        uu, _ = g.get_state()
+        out.append((uu, g.uu_fourier(), g.dt, g.calc_max_divB()))
+        g.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1])
+    assert out[0][2] == out[1][2] and out[0][3] == out[1][3]

@@ -45,6 +45,11 @@ def test_one_step_2d_tree(emu, kw):
     g.close()
 
 
+def test_mask_pruning_is_bit_exact(emu):
+    pc.check_pruning_is_exact((32, 16, 32), 2, lib_path=emu, hall=True, aeb=True, dealias=1)
+    pc.check_pruning_is_exact((32, 32), 2, lib_path=emu, hall=True, aeb=True, dealias=3)
+
+
 def test_synthetic_slab_matches_the_mode_sum():
     p = lo.Params(nx=16, ny=32, nz=24, Lx=24.0, Ly=20.0, Lz=12.0)
     prim = lo.ic_uniform_background(p, bx0=1.0, by0=0.3, press0=1.0)

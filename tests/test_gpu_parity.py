@@ -45,6 +45,40 @@ def test_one_step_parity_anisotropic_grid_and_late_start():
     g.close()
 
 
+def test_mask_pruning_is_bit_exact():
+    pc.check_pruning_is_exact((64, 64, 64), 3, hall=True, aeb=True, dealias=1)
+    pc.check_pruning_is_exact((128, 64), 3, hall=True, aeb=True, dealias=3)
+
+
+@pytest.mark.parametrize("name,kw", [("hall_aeb", dict(hall=True, aeb=True, dealias=1)),
+                                     ("z_radial_square", dict(hall=True, aeb=True, z_radial=True, dealias=3)),
+                                     ("filter_explicit", dict(hall=False, aeb=False, dealias=2, explicit=True, conserve_bg=True, limit_dt=True))])
+def test_2d_tree_parity(name, kw):
+    """BASELINE config 2 family (src_compressible/2D) at 256 x 128, two steps."""
+    p, prim = pc.make_case_2d(256, 128, **kw)
+    o, g = pc.run_both(p, prim, 2)
+    pc.check_state(o, g, 1e-11)
+    pc.check_diagnostics(o, g, 1e-9)
+    g.close()
+
+
+def test_2d_tree_2048_properties():
+    """BASELINE config 2 at full size (2048^2, Hall, no expansion): k=0 mode conserved bit-exactly,
+    div B at round-off, forward transform of the real state reproduces the spectrum."""
+    p, prim = pc.make_case_2d(2048, 2048, hall=True, aeb=False, dealias=1)
+    with Solver(**pc.solver_kwargs(p)) as g:
+        g.set_primitive(prim)
+        s0 = g.uu_fourier()[:, 0, 0, 0].copy()
+        g.vardt()
+        for i in range(3):
+            g.step(calc_dt=(i == 2))
+        assert np.array_equal(g.uu_fourier()[:, 0, 0, 0], s0)
+        assert g.calc_max_divB() < 1e-12
+        uu, _ = g.get_state()
+        assert np.isfinite(uu).all()
+        assert pc.rel_l2(g.fft_forward(uu[:2]), g.uu_fourier()[:2]) < 1e-13
+
+
 def test_dealias_mask_bit_exact():
     p, prim = pc.make_case(32, 64, 32, hall=False, aeb=False, dealias=1)
     o, g = pc.run_both(p, prim, 1)

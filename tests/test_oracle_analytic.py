@@ -196,3 +196,80 @@ def test_out_file_format_roundtrip(tmp_path):
     s2 = lo.State(p)
     s2.set_primitive(data)
     assert np.allclose(s2.uu, s.uu, rtol=1e-15, atol=1e-15)
+
+
+# --------------------------------------------------------------------------------------
+# 2D tree (src_compressible/2D): pinned against the 3D restatement and the same known answers
+# --------------------------------------------------------------------------------------
+def _state_2d_and_3d(nz3=16, **kw):
+    """A 2D problem and the same problem as a z-invariant 3D one (Lz arbitrary)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import parity_common as pc
+    p2, prim2 = pc.make_case_2d(32, 16, **kw)
+    p3 = lo.Params(**{**p2.__dict__, "nz": nz3, "Lz": 7.0, "if_z_radial": False})
+    prim3 = np.repeat(prim2, nz3, axis=1)
+    s2, s3 = lo.State2D(p2), lo.State(p3)
+    s2.set_primitive(prim2)
+    s3.set_primitive(prim3)
+    return s2, s3
+
+
+@pytest.mark.parametrize("kw", [dict(hall=True, aeb=True, dealias=1), dict(hall=False, aeb=False, dealias=2, explicit=True)])
+def test_2d_tree_equals_z_invariant_3d(kw):
+    """With d/dz = 0 the 3D equations reduce to the 2D tree's (kz = 0 in 2D/mhdrhs.f90:272): the two
+    restatements must agree to round-off when driven with the same fixed dt."""
+    s2, s3 = _state_2d_and_3d(**kw)
+    for s in (s2, s3):
+        run_fixed_dt(s, 0.01, 3)
+    for v in range(8):
+        ref = s2.uu[v][0]
+        assert np.abs(s3.uu[v] - ref[None]).max() < 1e-13 * max(1.0, np.abs(ref).max()), v
+    assert np.abs(s3.uu_fourier[:, 1:]).max() < 1e-15          # no z dependence is ever generated
+    assert np.abs(s3.uu_fourier[:, 0] - s2.uu_fourier[:, 0]).max() < 1e-14
+
+
+def test_2d_ebm_k0_decay_with_z_radial_coefficients():
+    """k=0 mode in the 2D expanding box with the radial direction along z (2D/mhdrhs.f90:324-343):
+    the flux divergence vanishes at k=0, so every stage multiplies u^(k=0) by the RK3 polynomial of
+    z = -c_v dt Ur/R with c = (2; 3,3,2; 1,1,2)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import parity_common as pc
+    p, prim = pc.make_case_2d(32, 16, hall=True, aeb=True, z_radial=True, visc=False, resis=False, dealias=3)
+    s = lo.State2D(p)
+    s.set_primitive(prim)
+    k0 = s.uu_fourier[:7, 0, 0, 0].copy()
+    dt = 0.01
+    expect = k0.copy()
+    s.dt = dt
+    s.rkt_init(dt)
+    for _ in range(10):
+        z = -np.array([2.0, 3.0, 3.0, 2.0, 1.0, 1.0, 2.0]) * dt * s.Ur / s.radius
+        expect = expect * (1 + z + z ** 2 / 2 + z ** 3 / 6)
+        s.evolve()
+        s.time += dt
+        s.evolve_radius(s.time)
+        s.rkt_init(dt)
+    got = s.uu_fourier[:7, 0, 0, 0]
+    assert np.abs(got - expect).max() <= 1e-13 * np.abs(expect).max()
+
+
+def test_2d_square_dealias_and_vardt_limits():
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import parity_common as pc
+    p, prim = pc.make_case_2d(32, 16, hall=True, aeb=False, dealias=3, limit_dt=True)
+    s = lo.State2D(p)
+    s.set_primitive(prim)
+    s.uu_fourier[:] = 1.0
+    s.dealias()
+    kept = np.abs(s.uu_fourier[0, 0]) > 0
+    assert kept[:, :11].any() and not kept[:, 11:].any()        # kx/nx <= 1/3  ->  kx <= 10 of 32
+    assert kept[:6].all(axis=0)[:11].all() and not kept[6:11].any()   # |ky|/ny <= 1/3 -> |ky| <= 5 of 16
+    s.set_primitive(prim)
+    dt0 = s.vardt()
+    s.dt = 0.5 * dt0                                             # if_limit_dt_increase: dt may only be raised from 0
+    assert s.vardt() == 0.5 * dt0
+    s.dt = 2.0 * dt0
+    assert s.vardt() == dt0
