@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define LAPS_ABI_VERSION 2
+#define LAPS_ABI_VERSION 3
 #define LAPS_MAX_RANKS 8
 
 typedef struct laps_solver* laps_handle;
@@ -52,6 +52,13 @@ typedef struct laps_params {
   int32_t ndim;
   int32_t if_z_radial;
   int32_t if_limit_dt_increase;
+  /* Incompressible tree (src_incompressible/, 3D): incompressible = 1 runs evolve of
+   * src_incompressible/mhd.f90:298-354 — J and grad u (12 inverse transforms), the pressure projection
+   * (mhdrhs.f90:392-523), E = -u x B (+ Hall), calc_rhs (:118-236), update_rho_p — and vardt of :356-457.
+   * uu(8) is the PRESSURE in this tree (mhdinit.f90:210) and uu_prim has the velocity only.
+   * rho0: the namelist background density (mhdinit.f90:15) that calc_gradient_velocity_real divides by. */
+  int32_t incompressible;
+  double rho0;
 } laps_params;
 
 /* Local extents as decompose_1d (parallel.f90:326-349) assigns them in slab mode. */
@@ -110,6 +117,14 @@ int laps_get_stream(laps_handle h, void** stream_out);
 
 /* calc_max_divB (mhd.f90:157,522-570). */
 int laps_max_divb(laps_handle h, double* out);
+/* Incompressible tree: calc_max_divV (src_incompressible/mhd.f90:616-664), max |k.(rho u)^| / rho0. */
+int laps_max_divv(laps_handle h, double* out);
+/* calc_divB_real + calc_max_divB_real and calc_divV_real + calc_max_divV_real
+ * (src_incompressible/mhdrhs.f90:536-647, mhd.f90:668-731), the pair the incompressible driver prints at
+ * dtrms cadence: out[0] = max |div B|, out[1] = max |div (rho u)| / rho0, both in REAL space. */
+int laps_max_div_real(laps_handle h, double out[2]);
+/* Current rho0 (update_rho_p compounds it after every evolve in the expanding box, AEBmod.f90:123-134). */
+int laps_get_rho0(laps_handle h, double* rho0);
 /* calc_rms (mhdrms.f90:53-126): out = uu_ave(8), uu_rms(8), rho_u2(3); the driver keeps the
  * rms.dat formatting of mhdrms.f90:25,48. */
 int laps_rms(laps_handle h, double out[19]);

@@ -14,7 +14,7 @@ from typing import Optional
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_RANKS = 8
 PEER_BLOB_BYTES = 256
 
@@ -43,6 +43,7 @@ class LapsParams(C.Structure):
         ("rank", C.c_int32), ("nranks", C.c_int32),
         ("device", C.c_int32),
         ("ndim", C.c_int32), ("if_z_radial", C.c_int32), ("if_limit_dt_increase", C.c_int32),
+        ("incompressible", C.c_int32), ("rho0", C.c_double),
     ]
 
 
@@ -60,6 +61,7 @@ SYMBOLS = [
     "laps_sync", "laps_get_stream", "laps_max_divb", "laps_rms", "laps_invariants", "laps_get_state", "laps_get_spectral",
     "laps_fft_forward", "laps_fft_inverse", "laps_transpose_yz_indexmap",
     "laps_last_step_ms", "laps_set_profiling", "laps_get_profile", "laps_get_pruning",
+    "laps_max_divv", "laps_max_div_real", "laps_get_rho0",
 ]
 
 
@@ -99,6 +101,9 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.laps_sync.argtypes = [H]
     lib.laps_get_stream.argtypes = [H, C.POINTER(C.c_void_p)]
     lib.laps_max_divb.argtypes = [H, dp]
+    lib.laps_max_divv.argtypes = [H, dp]
+    lib.laps_max_div_real.argtypes = [H, dp]
+    lib.laps_get_rho0.argtypes = [H, dp]
     lib.laps_rms.argtypes = [H, dp]
     lib.laps_invariants.argtypes = [H, dp]
     lib.laps_get_state.argtypes = [H, dp, dp]
@@ -135,6 +140,7 @@ def make_params(**kw) -> LapsParams:
     p.radius0 = 30.0
     p.rank, p.nranks, p.device = 0, 1, 0
     p.ndim = 3
+    p.incompressible, p.rho0 = 0, 1.0
     names = {f[0] for f in LapsParams._fields_}
     for k, v in kw.items():
         if k not in names:

@@ -36,7 +36,8 @@ struct FluxParams {
   int slot[19];         // field slot of each flux in F, < 0: not needed (the z fluxes of the 2D tree)
 };
 
-__global__ void __launch_bounds__(256) k_flux(const FluxParams P) {
+// 3 CTAs per SM (<= 85 registers): 11 loads + 19 stores per point want the occupancy (measured: 2 CTAs/SM cost 17 %)
+__global__ void __launch_bounds__(256, 3) k_flux(const FluxParams P) {
   const size_t n = P.npts;
   const double gm1 = P.gamma - 1.0;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -47,17 +48,18 @@ __global__ void __launch_bounds__(256) k_flux(const FluxParams P) {
     const double ptot = p + 0.5 * (Bx * Bx + By * By + Bz * Bz);
     const double udotb = ux * Bx + uy * By + uz * Bz;
     double* F = P.F + i;
-    double f[19];
-    f[0] = mx; f[1] = my; f[2] = mz;
-    f[3] = mx * ux - Bx * Bx + ptot;
-    f[4] = my * ux - By * Bx;
-    f[5] = mz * ux - Bz * Bx;
-    f[6] = mx * uy - Bx * By;
-    f[7] = my * uy - By * By + ptot;
-    f[8] = mz * uy - Bz * By;
-    f[9] = mx * uz - Bx * Bz;
-    f[10] = my * uz - By * Bz;
-    f[11] = mz * uz - Bz * Bz + ptot;
+    // every flux is stored as soon as it is formed (few live values: the kernel wants 3 CTAs per SM)
+#define LAPS_PUT(j, val) do { if (P.slot[j] >= 0) F[(size_t)P.slot[j] * n] = (val); } while (0)
+    LAPS_PUT(0, mx); LAPS_PUT(1, my); LAPS_PUT(2, mz);
+    LAPS_PUT(3, mx * ux - Bx * Bx + ptot);
+    LAPS_PUT(4, my * ux - By * Bx);
+    LAPS_PUT(5, mz * ux - Bz * Bx);
+    LAPS_PUT(6, mx * uy - Bx * By);
+    LAPS_PUT(7, my * uy - By * By + ptot);
+    LAPS_PUT(8, mz * uy - Bz * By);
+    LAPS_PUT(9, mx * uz - Bx * Bz);
+    LAPS_PUT(10, my * uz - By * Bz);
+    LAPS_PUT(11, mz * uz - Bz * Bz + ptot);
     double Ex = uz * By - uy * Bz;
     double Ey = ux * Bz - uz * Bx;
     double Ez = uy * Bx - ux * By;
@@ -68,44 +70,46 @@ __global__ void __launch_bounds__(256) k_flux(const FluxParams P) {
       Ey = Ey + dr * (Jz * Bx - Jx * Bz);
       Ez = Ez + dr * (Jx * By - Jy * Bx);
     }
-    f[12] = Ex; f[13] = Ey; f[14] = Ez;
+    LAPS_PUT(12, Ex); LAPS_PUT(13, Ey); LAPS_PUT(14, Ez);
     const double h = en + ptot;
-    f[15] = h * ux - udotb * Bx;
-    f[16] = h * uy - udotb * By;
-    f[17] = h * uz - udotb * Bz;
-    f[18] = 0.0;
+    LAPS_PUT(15, h * ux - udotb * Bx);
+    LAPS_PUT(16, h * uy - udotb * By);
+    LAPS_PUT(17, h * uz - udotb * Bz);
     if (P.aeb) {
+      double src;
       if (P.z_radial)
-        f[18] = -2 * P.gamma / gm1 * p / P.tau - (Bx * Bx + By * By + 2.0 * Bz * Bz) / P.tau -
-                (2 * mx * ux + 2 * my * uy + mz * uz) / P.tau;
+        src = -2 * P.gamma / gm1 * p / P.tau - (Bx * Bx + By * By + 2.0 * Bz * Bz) / P.tau -
+              (2 * mx * ux + 2 * my * uy + mz * uz) / P.tau;
       else
-        f[18] = -2 * P.gamma / gm1 * p / P.tau - (2.0 * Bx * Bx + By * By + Bz * Bz) / P.tau -
-                (mx * ux + 2 * my * uy + 2 * mz * uz) / P.tau;
+        src = -2 * P.gamma / gm1 * p / P.tau - (2.0 * Bx * Bx + By * By + Bz * Bz) / P.tau -
+              (mx * ux + 2 * my * uy + 2 * mz * uz) / P.tau;
+      LAPS_PUT(18, src);
     }
-    LAPS_UNROLL
-    for (int j = 0; j < 19; ++j)
-      if (P.slot[j] >= 0) F[(size_t)P.slot[j] * n] = f[j];
+#undef LAPS_PUT
   }
 }
 
 // in place: [rho,ux,uy,uz,bx,by,bz,p] -> [rho,rho u,B,e]
-__global__ void __launch_bounds__(256) k_prim_to_cons(double* uu, size_t n, double gamma) {
+// (incompressible tree, src_incompressible/mhdinit.f90:1031-1042: uu(8) stays the pressure)
+__global__ void __launch_bounds__(256) k_prim_to_cons(double* uu, size_t n, double gamma, int incomp) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const double rho = uu[i], ux = uu[n + i], uy = uu[2 * n + i], uz = uu[3 * n + i];
     const double bx = uu[4 * n + i], by = uu[5 * n + i], bz = uu[6 * n + i], p = uu[7 * n + i];
     uu[n + i] = rho * ux;
     uu[2 * n + i] = rho * uy;
     uu[3 * n + i] = rho * uz;
-    uu[7 * n + i] = p / (gamma - 1) + 0.5 * (rho * (ux * ux + uy * uy + uz * uz) + bx * bx + by * by + bz * bz);
+    if (!incomp) uu[7 * n + i] = p / (gamma - 1) + 0.5 * (rho * (ux * ux + uy * uy + uz * uz) + bx * bx + by * by + bz * bz);
   }
 }
 
 // prim[4][n] = (ux,uy,uz,p) from conserved uu
-__global__ void __launch_bounds__(256) k_cons_to_prim(const double* uu, double* prim, size_t n, double gamma) {
+// (incompressible tree: uu_prim has the velocity only, src_incompressible/mhdrhs.f90:239-246; the 4th
+// row returns the pressure uu(8))
+__global__ void __launch_bounds__(256) k_cons_to_prim(const double* uu, double* prim, size_t n, double gamma, int incomp) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const Prim q = prim_of(uu[i], uu[n + i], uu[2 * n + i], uu[3 * n + i], uu[4 * n + i], uu[5 * n + i],
                            uu[6 * n + i], uu[7 * n + i], gamma - 1.0);
-    prim[i] = q.ux; prim[n + i] = q.uy; prim[2 * n + i] = q.uz; prim[3 * n + i] = q.p;
+    prim[i] = q.ux; prim[n + i] = q.uy; prim[2 * n + i] = q.uz; prim[3 * n + i] = incomp ? uu[7 * n + i] : q.p;
   }
 }
 
@@ -196,7 +200,9 @@ __global__ void __launch_bounds__(256) k_reduce_final(const double* partial, int
 
 // mhdrms.f90:73-93: sums and sums of squares of (rho,u,B,p), plus sum(e) and sum(u.B) (invariants).
 // partial layout [18][gridDim.x]
-__global__ void __launch_bounds__(256) k_moments1(const double* uu, size_t n, double gamma, double* partial) {
+// Incompressible tree: entry 8 is the pressure uu(8) (the reference reads the non-existent uu_prim(:,:,:,4),
+// src_incompressible/mhdrms.f90:72) and the energy invariant is (rho u^2 + B^2)/2.
+__global__ void __launch_bounds__(256) k_moments1(const double* uu, size_t n, double gamma, double* partial, int incomp) {
   __shared__ double scratch[32];
   double s[18];
   LAPS_UNROLL
@@ -205,10 +211,10 @@ __global__ void __launch_bounds__(256) k_moments1(const double* uu, size_t n, do
     const double rho = uu[i], mx = uu[n + i], my = uu[2 * n + i], mz = uu[3 * n + i];
     const double Bx = uu[4 * n + i], By = uu[5 * n + i], Bz = uu[6 * n + i], en = uu[7 * n + i];
     const Prim q = prim_of(rho, mx, my, mz, Bx, By, Bz, en, gamma - 1.0);
-    const double f[8] = {rho, q.ux, q.uy, q.uz, Bx, By, Bz, q.p};
+    const double f[8] = {rho, q.ux, q.uy, q.uz, Bx, By, Bz, incomp ? en : q.p};
     LAPS_UNROLL
     for (int j = 0; j < 8; ++j) { s[j] += f[j]; s[8 + j] += f[j] * f[j]; }
-    s[16] += en;
+    s[16] += incomp ? 0.5 * (mx * q.ux + my * q.uy + mz * q.uz + Bx * Bx + By * By + Bz * Bz) : en;
     s[17] += q.ux * Bx + q.uy * By + q.uz * Bz;
   }
   LAPS_UNROLL
@@ -244,6 +250,7 @@ struct DivbParams {
   const double* kxr; const double* kyr; const double* kze;
   double radius0, radius, cosa, sina; int corot_k;
   int mode2d, z_radial;   // 2D tree: the line axis carries ky, kz = 0 (2D/mhd.f90:527-550)
+  int v0;                 // first component of the vector: 4 = B (calc_max_divB), 1 = rho u (calc_max_divV, src_incompressible/mhd.f90:616-664)
   double* partial;
 };
 __global__ void __launch_bounds__(256) k_divb(const DivbParams P) {
@@ -261,13 +268,93 @@ __global__ void __launch_bounds__(256) k_divb(const DivbParams P) {
     }
     if (P.z_radial) kxe = __ddiv_rn(__dmul_rn(kxr, P.radius0), P.radius);
     const double kzz = P.kze[kz];
-    const cplx bx = P.u[4 * P.fstride + i], by = P.u[5 * P.fstride + i], bz = P.u[6 * P.fstride + i];
+    const cplx bx = P.u[(size_t)P.v0 * P.fstride + i], by = P.u[(size_t)(P.v0 + 1) * P.fstride + i], bz = P.u[(size_t)(P.v0 + 2) * P.fstride + i];
     const cplx d = P.mode2d ? cadd(cadd(cmul_i(bx, kxe), cmul_i(by, kzz)), cmul_i(bz, 0.0))
                             : cadd(cadd(cmul_i(bx, kxe), cmul_i(by, kye)), cmul_i(bz, kzz));
     best = fmax(best, sqrt(d.x * d.x + d.y * d.y));
   }
   const double r = block_reduce(best, OpMax(), scratch);
   if (threadIdx.x == 0) P.partial[blockIdx.x] = r;
+}
+
+// ------------------------------------------------------------------ incompressible tree (src_incompressible/)
+// calc_flux_for_pressure (mhdrhs.f90:392-441) and calc_flux (mhdrhs.f90:26-85) in one sweep: both are
+// functions of the same real fields.  F slots 0-2: Fp = -(rho u . grad) u + J x B ; 3-5: E = -u x B (+ Hall).
+struct FluxIncParams {
+  const double* uu;     // [8][npts]  rho, rho u, B, p
+  const double* J;      // [3][npts]
+  const double* G;      // [9][npts]  d u_b / d x_a at slot 3*b + a
+  double* F;            // [6][npts]
+  size_t npts;
+  int hall;
+  double di;
+};
+
+__global__ void __launch_bounds__(256) k_flux_incomp(const FluxIncParams P) {
+  const size_t n = P.npts;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double rho = P.uu[i], mx = P.uu[n + i], my = P.uu[2 * n + i], mz = P.uu[3 * n + i];
+    const double Bx = P.uu[4 * n + i], By = P.uu[5 * n + i], Bz = P.uu[6 * n + i];
+    const double Jx = P.J[i], Jy = P.J[n + i], Jz = P.J[2 * n + i];
+    double g[9];
+    LAPS_UNROLL
+    for (int j = 0; j < 9; ++j) g[j] = P.G[(size_t)j * n + i];
+    double* F = P.F + i;
+    F[0] = -mx * g[0] - my * g[1] - mz * g[2] + Jy * Bz - Jz * By;
+    F[n] = -mx * g[3] - my * g[4] - mz * g[5] + Jz * Bx - Jx * Bz;
+    F[2 * n] = -mx * g[6] - my * g[7] - mz * g[8] + Jx * By - Jy * Bx;
+    const double ux = mx / rho, uy = my / rho, uz = mz / rho;   // uu_prim (mhdrhs.f90:239-246)
+    double Ex = uz * By - uy * Bz;
+    double Ey = ux * Bz - uz * Bx;
+    double Ez = uy * Bx - ux * By;
+    if (P.hall) {
+      const double dr = P.di / rho;
+      Ex = Ex + dr * (Jy * Bz - Jz * By);
+      Ey = Ey + dr * (Jz * Bx - Jx * Bz);
+      Ez = Ez + dr * (Jx * By - Jy * Bx);
+    }
+    F[3 * n] = Ex; F[4 * n] = Ey; F[5 * n] = Ez;
+  }
+}
+
+// vardt of the incompressible tree (src_incompressible/mhd.f90:356-457): Alfven and flow speeds only.
+// Same reduction as k_cfl: the three maxima of the signal speeds (division is monotonic).
+__global__ void __launch_bounds__(256) k_cfl_incomp(const CflParams P) {
+  __shared__ double scratch[32];
+  const size_t n = P.npts;
+  double best[3] = {0.0, 0.0, 0.0};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double rho = P.uu[i];
+    const double sr = sqrt(rho);
+    double chall = 0.0;
+    if (P.hall) chall = P.di / rho * fmax(fmax(P.uu[4 * n + i], P.uu[5 * n + i]), P.uu[6 * n + i]) / P.dmin;
+    LAPS_UNROLL
+    for (int d = 0; d < 3; ++d) {
+      const double ca = P.uu[(size_t)(4 + d) * n + i] / sr;
+      const double u = P.uu[(size_t)(1 + d) * n + i] / rho;
+      double c = fmax(fmax(fabs(u + ca), fabs(u - ca)), fabs(u));
+      if (P.hall) c = fmax(c, chall);
+      best[d] = fmax(best[d], c);
+    }
+  }
+  LAPS_UNROLL
+  for (int d = 0; d < 3; ++d) {
+    const double r = block_reduce(best[d], OpMax(), scratch);
+    if (threadIdx.x == 0) P.partial[(size_t)d * gridDim.x + blockIdx.x] = r;
+  }
+}
+
+// max |f| over nfields real fields (calc_max_divB_real / calc_max_divV_real, src_incompressible/mhd.f90:668-731);
+// partial layout [nfields][gridDim.x]
+__global__ void __launch_bounds__(256) k_absmax(const double* f, size_t n, int nfields, double* partial) {
+  __shared__ double scratch[32];
+  for (int j = 0; j < nfields; ++j) {
+    double best = 0.0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+      best = fmax(best, fabs(f[(size_t)j * n + i]));
+    const double r = block_reduce(best, OpMax(), scratch);
+    if (threadIdx.x == 0) partial[(size_t)j * gridDim.x + blockIdx.x] = r;
+  }
 }
 
 }  // namespace laps

@@ -16,6 +16,7 @@
 #include "exchange.cuh"
 #include "fft_passes.cuh"
 #include "pointwise.cuh"
+#include "spectral_incomp.cuh"
 #include "spectral_rhs.cuh"
 #include "spectral_z.cuh"
 
@@ -66,6 +67,12 @@ struct laps_solver {
   laps_params p;       // INTERNAL parameters: in the 2D tree the grid is held as (nx, 1, ny), see laps_create
   laps_params user;    // as given by the driver
   bool two_d = false;
+  // incompressible tree (src_incompressible/): pressure projection, uu(8) = p, no energy equation
+  bool incomp = false;
+  double rho0 = 1.0;     // namelist background density (mhdinit.f90:15), compounded by update_rho_p (AEBmod.f90:123-134)
+  double p0 = 1.0;
+  double* G = nullptr;   // [9][npts] grad u (incompressible)
+  bool retransform = false;   // re-derive the spectrum from the real fields at the start of every stage (mhd.f90:305)
   int xz = 0, xy = 0;  // line counts (planes, lines per plane) the x passes run over
   int nx, ny, nz, nxh, P, rank;
   int zoffs[LAPS_MAX_RANKS], zlens[LAPS_MAX_RANKS], yoffs[LAPS_MAX_RANKS], ylens[LAPS_MAX_RANKS];
@@ -353,6 +360,18 @@ int do_rhs_z(S* s, const ZParams& zp, int ntasks) {
   return do_rhs_z_cg<N, rcg(N)>(s, zp, ntasks);
 }
 
+template <int N>
+int do_incomp_z(S* s, const ZParams& zp) {
+  constexpr int CG = rcg(N);
+  typedef ITile<N, CG> T;
+  LAPS_CK(s, prepare_kernel(k_incomp_z<N, CG>, T::SMEM, T::MINB));
+  LaunchScope ls(s, "incomp_z");
+  if (zp.ncolc == 0) return 0;
+  dim3 grid((unsigned)((zp.ncolc + CG - 1) / CG));
+  LAPS_LAUNCH((k_incomp_z<N, CG>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, zp);
+  return check_launch(s, "k_incomp_z");
+}
+
 #define LAPS_DISPATCH(n, fn, ...)                                   \
   switch (n) {                                                      \
     case 16: return fn<16>(__VA_ARGS__);                            \
@@ -381,6 +400,7 @@ int forward_xy(S* s, const double* in, size_t fstride, int nfields, bool prune) 
 int inv_x(S* s, const cplx* V2, const RealDst& dst, int nfields, bool prune) { LAPS_DISPATCH(s->nx, do_inv_x, s, V2, dst, nfields, prune) }
 int spec_z(S* s, const ZParams& zp, int ntasks, const char* name) { LAPS_DISPATCH(s->nz, do_spec_z, s, zp, ntasks, name) }
 int rhs_z(S* s, const ZParams& zp, int ntasks) { LAPS_DISPATCH(s->nz, do_rhs_z, s, zp, ntasks) }
+int incomp_z(S* s, const ZParams& zp) { LAPS_DISPATCH(s->nz, do_incomp_z, s, zp) }
 
 // buffers (see the memory plan in DESIGN.md)
 double* buf_F(S* s) { return (double*)s->bufX; }
@@ -418,6 +438,7 @@ void fill_zparams(S* s, ZParams& z, bool prune = false) {
   z.da_thresh = s->da_thresh;
   z.mode2d = s->two_d; z.z_radial = s->two_d && p.if_AEB && p.if_z_radial; z.bg_all_kz = s->two_d;
   z.tune = s->tune_z;
+  z.aeb_p = 2.0 * p.adiabatic_index;   // src_incompressible/mhdrhs.f90:196-197
 }
 
 ZTask rhs_task(int v, int gout, int fa, double ca, int fb, double cb, int fx, double cx, double sg, int fc, double sc) {
@@ -454,19 +475,23 @@ int host_barrier(S* s) {
   return 0;
 }
 
-RealDst dst_state_and_current(S* s) {
-  RealDst d; std::memset(&d, 0, sizeof(d));
+struct RealSlots { double* ptr[20]; };
+RealSlots dst_state_and_current(S* s) {   // V1 slot -> real field: 0-7 uu, 8-10 J, 11-19 grad u (incompressible)
+  RealSlots d; std::memset(&d, 0, sizeof(d));
   for (int v = 0; v < 8; ++v) d.ptr[v] = s->uu + (size_t)v * s->npts;
   for (int j = 0; j < 3; ++j) d.ptr[8 + j] = s->J ? s->J + (size_t)j * s->npts : nullptr;
+  for (int j = 0; j < 9; ++j) d.ptr[11 + j] = s->G ? s->G + (size_t)j * s->npts : nullptr;
   return d;
 }
 
-// inverse y and x passes for V1 slots [g0, g0+n)
-int inverse_yx(S* s, int g0, int n, bool prune) {
+// inverse y and x passes for V1 slots [g0, g0+n) into the real fields [r0, r0+n) of dst_state_and_current (r0 < 0: r0 = g0)
+int inverse_yx(S* s, int g0, int n, bool prune, int r0 = -1) {
+  if (r0 < 0) r0 = g0;
   const size_t vs = (size_t)s->nxh * s->ny * s->nzl;
-  RealDst d = dst_state_and_current(s), d2;
+  RealSlots d = dst_state_and_current(s);
+  RealDst d2;
   std::memset(&d2, 0, sizeof(d2));
-  for (int i = 0; i < n; ++i) d2.ptr[i] = d.ptr[g0 + i];
+  for (int i = 0; i < n; ++i) d2.ptr[i] = d.ptr[r0 + i];
   if (s->two_d) return inv_x(s, buf_V1(s) + (size_t)g0 * vs, d2, n, prune);   // [g][kx][1][line] is already the x-pass layout
   LAPS_TRY(inv_y(s, buf_V1(s) + (size_t)g0 * vs, buf_V2(s) + (size_t)g0 * vs, n, prune));
   return inv_x(s, buf_V2(s) + (size_t)g0 * vs, d2, n, prune);
@@ -485,8 +510,80 @@ int refresh_current(S* s) {
   return 0;
 }
 
+// transform_uu_real_to_fourier (fftw.f90:42-71): u_A = FFT(uu)
+int spectrum_from_real(S* s, bool prune) {
+  LAPS_TRY(forward_xy(s, s->uu, s->npts, 8, prune));
+  LAPS_TRY(host_barrier(s));
+  ZParams z; fill_zparams(s, z, prune);
+  z.u_out = s->uA;
+  for (int v = 0; v < 8; ++v) {
+    ZTask t; std::memset(&t, 0, sizeof(t));
+    t.kind = kZForwardOnly; t.v = v; t.gout = -1; t.fa = v; t.fb = t.fx = t.fc = -1;
+    z.task[v] = t;
+  }
+  LAPS_TRY(spec_z(s, z, 8, "fwd_z"));
+  return host_barrier(s);
+}
+
+// One RK stage of the incompressible tree (src_incompressible/mhd.f90:303-350).
+int stage_incomp(S* s, int irk) {
+  const laps_params& p = s->p;
+  const bool prune = !s->spectrum_full;
+  if (s->retransform) LAPS_TRY(spectrum_from_real(s, prune));            // mhd.f90:305
+  {  // calc_current_density_real + calc_gradient_velocity_real (mhdrhs.f90:248-390): 12 inverse transforms
+    ZParams z; fill_zparams(s, z, prune);
+    z.u_in = s->uA;
+    for (int j = 0; j < 3; ++j) {
+      ZTask t; std::memset(&t, 0, sizeof(t));
+      t.kind = kZCurrent; t.jcomp = j; t.gout = j; t.fa = t.fb = t.fx = t.fc = -1;
+      z.task[j] = t;
+    }
+    for (int b = 0; b < 3; ++b)
+      for (int a = 0; a < 3; ++a) {
+        ZTask t; std::memset(&t, 0, sizeof(t));
+        t.kind = kZGrad; t.v = 1 + b; t.jcomp = a; t.cx = s->rho0; t.gout = 3 + 3 * b + a; t.fa = t.fb = t.fx = t.fc = -1;
+        z.task[3 + 3 * b + a] = t;
+      }
+    LAPS_TRY(spec_z(s, z, 12, "deriv_inv_z"));
+    LAPS_TRY(host_barrier(s));
+    LAPS_TRY(inverse_yx(s, 0, 12, prune, 8));   // V1 slots 0-11 -> J (3), grad u (9)
+  }
+  {  // calc_flux_for_pressure + calc_flux (mhdrhs.f90:392-441, 26-85)
+    FluxIncParams f;
+    f.uu = s->uu; f.J = s->J; f.G = s->G; f.F = buf_F(s); f.npts = s->npts;
+    f.hall = p.if_hall; f.di = p.ion_inertial_length;
+    LaunchScope ls(s, "flux");
+    LAPS_LAUNCH(k_flux_incomp, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, f);
+    LAPS_TRY(check_launch(s, "k_flux_incomp"));
+  }
+  LAPS_TRY(forward_xy(s, buf_F(s), s->npts, 6, true));
+  LAPS_TRY(host_barrier(s));
+  {
+    ZParams z; fill_zparams(s, z, true);
+    z.cc = s->cc1[irk]; z.dd = s->dd1[irk]; z.dt_irk = s->tstep[irk];
+    z.read_rk = (irk > 0); z.write_rk = (irk < 2);
+    // projection rows: rho u, p, rho (slots 0-2 = Fp)
+    LAPS_TRY(incomp_z(s, z));
+    // dB/dt = curl E (mhdrhs.f90:168-174), slots 3-5 = E
+    z.task[0] = rhs_task(4, 4, -1, 0.0, 5, 1.0, -1, 0.0, -1.0, 4, +1.0);
+    z.task[1] = rhs_task(5, 5, 5, 1.0, -1, 0.0, -1, 0.0, +1.0, 3, -1.0);
+    z.task[2] = rhs_task(6, 6, 4, -1.0, 3, 1.0, -1, 0.0, +1.0, -1, 0.0);
+    LAPS_TRY(spec_z(s, z, 3, "spec_z"));
+  }
+  LAPS_TRY(host_barrier(s));
+  LAPS_TRY(inverse_yx(s, 0, 8, true));
+  if (s->spectrum_full) {
+    if (s->nkx < s->nxh || s->kymax < s->ny / 2)
+      LAPS_CK(s, cudaMemsetAsync(s->uA, 0, 8 * s->csz * sizeof(cplx), s->stream));
+    s->spectrum_full = false;
+  }
+  std::swap(s->uA, s->uB);
+  return 0;
+}
+
 int stage(S* s, int irk) {
   const laps_params& p = s->p;
+  if (s->incomp) return stage_incomp(s, irk);
   LAPS_TRY(refresh_current(s));
   {  // calc_flux (mhdrhs.f90:21-124; 2D/mhdrhs.f90:23-128)
     FluxParams f;
@@ -612,6 +709,10 @@ int laps_create(const laps_params* params, laps_handle* out) {
     if (p.dealias_option < 0 || p.dealias_option > 2) { g_create_error = "dealias_option must be 0, 1 or 2"; return 1; }
     p.if_z_radial = 0; p.if_limit_dt_increase = 0;
   }
+  if (u.incompressible) {
+    if (two_d) { g_create_error = "the incompressible tree is 3D only here (src_incompressible/2D is not built)"; return 1; }
+    if (!(u.rho0 > 0.0)) { g_create_error = "incompressible: rho0 must be positive (mhdinit.f90:15)"; return 1; }
+  }
   if (p.nranks < 1 || p.nranks > LAPS_MAX_RANKS || p.rank < 0 || p.rank >= p.nranks) {
     g_create_error = "bad rank/nranks (1..8 ranks, slab decomposition)"; return 1;
   }
@@ -620,6 +721,8 @@ int laps_create(const laps_params* params, laps_handle* out) {
   s->p = p;
   s->user = u;
   s->two_d = two_d;
+  s->incomp = u.incompressible != 0;
+  s->rho0 = u.rho0; s->p0 = 1.0;
   auto fail = [&](const std::string& m) { g_create_error = m; laps_destroy(s); return 1; };
 #ifndef LAPS_EMU_BUILD
   int ndev = 0;
@@ -648,6 +751,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
     s->nf = n;
   }
   s->ni = 8 + (p.if_hall ? 3 : 0);
+  if (s->incomp) { s->nf = 6; s->ni = 12; }   // Fp (3) + E (3) forward; J (3) + grad u (9) / the state (8) inverse
   {  // the mask test "sqrt(s) > 1./3." (dealiasing.f90:94) as a threshold on s: sqrt is correctly rounded
      // and monotonic, so { s : sqrt(s) > c } = { s >= T } with T the smallest double that passes
     const double c = 1.0 / 3.0;
@@ -660,6 +764,12 @@ int laps_create(const laps_params* params, laps_handle* out) {
   if (const char* e = std::getenv("LAPS_TUNE_RHS")) s->tune_rhs = std::atoi(e);
   if (const char* e = std::getenv("LAPS_TUNE_RCG")) s->tune_rcg = std::atoi(e);
   if (const char* e = std::getenv("LAPS_TUNE_Z")) s->tune_z = std::atoi(e);
+  // The reference re-derives uu_fourier from the real fields at the start of every stage
+  // (src_incompressible/mhd.f90:305).  For a spectrum the dealiasing has band-limited (options 1, 2: the
+  // Nyquist planes are removed) that round trip is the identity up to round-off and is skipped; with
+  // dealias_option 0 it projects out the non-Hermitian Nyquist content the derivatives create, so it is done.
+  s->retransform = s->incomp && p.dealias_option == 0;
+  if (const char* e = std::getenv("LAPS_TUNE_RETRANSFORM")) s->retransform = s->incomp && std::atoi(e) != 0;
   s->nblk = (int)std::min<size_t>(148 * 8, (s->npts + 255) / 256);   // grid-stride loops: 8 CTAs per SM at most
 
   // expanding box: mhd.f90:88-91, AEBmod.f90:16-31
@@ -677,11 +787,12 @@ int laps_create(const laps_params* params, laps_handle* out) {
   // largest per-rank slab sizes of the exchanged layouts (the last rank holds the remainder)
   s->bytesX = std::max((size_t)s->nf * s->npts * sizeof(double), (size_t)s->ni * s->w1sz * sizeof(cplx));
   s->bytesY = (size_t)nmax * s->w1sz * sizeof(cplx);
-  s->bytesZ = (size_t)s->nf * s->csz * sizeof(cplx);
+  s->bytesZ = (size_t)std::max(s->nf, 8) * s->csz * sizeof(cplx);   // the 8 state fields pass through W2 in laps_set_primitive
   bool ok = true;
   auto alloc = [&](void** ptr, size_t bytes) { if (ok && cudaMalloc(ptr, bytes) != cudaSuccess) ok = false; };
   alloc((void**)&s->uu, 8 * s->npts * sizeof(double));
-  if (p.if_hall) alloc((void**)&s->J, 3 * s->npts * sizeof(double));
+  if (p.if_hall || s->incomp) alloc((void**)&s->J, 3 * s->npts * sizeof(double));
+  if (s->incomp) alloc((void**)&s->G, 9 * s->npts * sizeof(double));
   alloc(&s->bufX, s->bytesX); alloc(&s->bufY, s->bytesY); alloc(&s->bufZ, s->bytesZ);
   alloc((void**)&s->uA, 8 * s->csz * sizeof(cplx));
   alloc((void**)&s->uB, 8 * s->csz * sizeof(cplx));
@@ -768,7 +879,7 @@ int laps_destroy(laps_handle s) {
     for (int j = 0; j < 3; ++j)
       if (s->ipc_opened[q][j]) cudaIpcCloseMemHandle(s->ipc_opened[q][j]);
   cudaFree(s->xblk);
-  cudaFree(s->uu); cudaFree(s->J); cudaFree(s->prim); cudaFree(s->bufX); cudaFree(s->bufY); cudaFree(s->bufZ);
+  cudaFree(s->uu); cudaFree(s->J); cudaFree(s->G); cudaFree(s->prim); cudaFree(s->bufX); cudaFree(s->bufY); cudaFree(s->bufZ);
   cudaFree(s->uA); cudaFree(s->uB); cudaFree(s->rk); cudaFree(s->tw_x); cudaFree(s->tw_y); cudaFree(s->tw_z);
   cudaFree(s->d_tab); cudaFree(s->d_partial); cudaFree(s->d_scal);
   if (s->h_scal) cudaFreeHost(s->h_scal);
@@ -807,23 +918,12 @@ int laps_set_primitive(laps_handle s, const double* uu_local) {
   LAPS_CK(s, cudaMemcpyAsync(s->uu, uu_local, 8 * s->npts * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   {
     LaunchScope ls(s, "prim_to_cons");
-    LAPS_LAUNCH(k_prim_to_cons, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, s->uu, s->npts, s->p.adiabatic_index);
+    LAPS_LAUNCH(k_prim_to_cons, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, s->uu, s->npts, s->p.adiabatic_index, s->incomp ? 1 : 0);
     LAPS_TRY(check_launch(s, "k_prim_to_cons"));
   }
-  // transform_uu_real_to_fourier (fftw.f90:42-71)
-  LAPS_TRY(forward_xy(s, s->uu, s->npts, 8, false));
   LAPS_CK(s, cudaMemsetAsync(s->uB, 0, 8 * s->csz * sizeof(cplx), s->stream));   // masked columns of the first output
   s->spectrum_full = true;
-  LAPS_TRY(host_barrier(s));
-  ZParams z; fill_zparams(s, z);
-  z.u_out = s->uA;
-  for (int v = 0; v < 8; ++v) {
-    ZTask t; std::memset(&t, 0, sizeof(t));
-    t.kind = kZForwardOnly; t.v = v; t.gout = -1; t.fa = v; t.fb = t.fx = t.fc = -1;
-    z.task[v] = t;
-  }
-  LAPS_TRY(spec_z(s, z, 8, "fwd_z"));
-  LAPS_TRY(host_barrier(s));
+  LAPS_TRY(spectrum_from_real(s, false));
   s->have_state = true;
   s->j_stale = true;
   LAPS_CK(s, cudaStreamSynchronize(s->stream));  // the caller may reuse uu_local
@@ -867,7 +967,8 @@ int laps_vardt(laps_handle s, double* dt_inout) {  // mhd.f90:328-429
   c.hall = p.if_hall; c.partial = s->d_partial;
   {
     LaunchScope ls(s, "cfl");
-    LAPS_LAUNCH(k_cfl, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, c);
+    if (s->incomp) LAPS_LAUNCH(k_cfl_incomp, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, c);   // src_incompressible/mhd.f90:356-457
+    else LAPS_LAUNCH(k_cfl, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, c);
     LAPS_TRY(check_launch(s, "k_cfl"));
   }
   LAPS_TRY(reduce_final(s, 3, 2, 0.0));   // global maxima of the three signal speeds (mhd.f90:419 as max)
@@ -902,6 +1003,11 @@ int laps_evolve(laps_handle s) {  // mhd.f90:298-326
   LAPS_CK(s, cudaEventRecord(s->ev0, s->stream));
   for (int irk = 0; irk < 3; ++irk) LAPS_TRY(stage(s, irk));
   LAPS_CK(s, cudaEventRecord(s->ev1, s->stream));
+  if (s->incomp) {  // update_rho_p (src_incompressible/mhd.f90:353, AEBmod.f90:123-134): compounds with the CURRENT radius
+    const double q = s->p.radius0 / s->radius;
+    s->rho0 = s->rho0 * std::pow(q, 2);
+    s->p0 = s->p0 * std::pow(q, 2 * s->p.adiabatic_index);
+  }
   return 0;
 }
 
@@ -946,10 +1052,9 @@ int laps_get_profile(laps_handle s, char* names, float* ms, int32_t cap, int32_t
   return 0;
 }
 
-int laps_max_divb(laps_handle s, double* out) {  // mhd.f90:522-570
-  if (!s || !out) return 1;
-  LAPS_TRY(require_state(s));
+static int max_div_fourier(laps_handle s, int v0, double* out) {
   DivbParams d;
+  d.v0 = v0;
   d.u = s->uA; d.fstride = s->csz; d.ncol = (int)s->ncol; d.nz = s->nz; d.nyl = s->nyl; d.yoff = s->yo;
   d.kxr = s->kxr; d.kyr = s->kyr; d.kze = s->kze;
   d.radius0 = s->p.radius0; d.radius = s->radius; d.cosa = s->cosa; d.sina = s->sina;
@@ -966,10 +1071,63 @@ int laps_max_divb(laps_handle s, double* out) {  // mhd.f90:522-570
   return 0;
 }
 
+int laps_max_divb(laps_handle s, double* out) {  // mhd.f90:522-570
+  if (!s || !out) return 1;
+  LAPS_TRY(require_state(s));
+  return max_div_fourier(s, 4, out);
+}
+
+int laps_max_divv(laps_handle s, double* out) {  // src_incompressible/mhd.f90:616-664: max |k . (rho u)^| / rho0
+  if (!s || !out) return 1;
+  LAPS_TRY(require_state(s));
+  LAPS_TRY(max_div_fourier(s, 1, out));
+  *out = *out / (s->incomp ? s->rho0 : 1.0);
+  return 0;
+}
+
+// calc_divB_real + calc_max_divB_real, calc_divV_real + calc_max_divV_real
+// (src_incompressible/mhdrhs.f90:536-647, mhd.f90:668-731): maxima of |div B| and |div (rho u)/rho0| in REAL space.
+int laps_max_div_real(laps_handle s, double out[2]) {
+  if (!s || !out) return 1;
+  LAPS_TRY(require_state(s));
+  if (s->two_d) { s->err = "laps_max_div_real: 3D trees only"; return 1; }
+  const bool prune = !s->spectrum_full;
+  ZParams z; fill_zparams(s, z, prune);
+  z.u_in = s->uA;
+  for (int j = 0; j < 2; ++j) {
+    ZTask t; std::memset(&t, 0, sizeof(t));
+    t.kind = kZDiv; t.v = j == 0 ? 4 : 1; t.cx = j == 0 ? 1.0 : (s->incomp ? s->rho0 : 1.0); t.gout = j; t.fa = t.fb = t.fx = t.fc = -1;
+    z.task[j] = t;
+  }
+  LAPS_TRY(spec_z(s, z, 2, "div_inv_z"));
+  LAPS_TRY(host_barrier(s));
+  const size_t vs = (size_t)s->nxh * s->ny * s->nzl;
+  // the two real fields land in the flux work area (free between stages)
+  RealDst d; std::memset(&d, 0, sizeof(d));
+  d.ptr[0] = buf_F(s) + (size_t)(s->nf - 2) * s->npts; d.ptr[1] = buf_F(s) + (size_t)(s->nf - 1) * s->npts;
+  LAPS_TRY(inv_y(s, buf_V1(s), buf_V2(s), 2, prune));
+  LAPS_TRY(inv_x(s, buf_V2(s), d, 2, prune));
+  (void)vs;
+  {
+    LaunchScope ls(s, "absmax");
+    LAPS_LAUNCH(k_absmax, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, (const double*)d.ptr[0], s->npts, 2, s->d_partial);
+    LAPS_TRY(check_launch(s, "k_absmax"));
+  }
+  LAPS_TRY(reduce_final(s, 2, 2, 0.0));
+  out[0] = s->h_scal[0]; out[1] = s->h_scal[1];
+  return 0;
+}
+
+int laps_get_rho0(laps_handle s, double* rho0) {
+  if (!s || !rho0) return 1;
+  *rho0 = s->rho0;
+  return 0;
+}
+
 static int moments(laps_handle s, double sums[18]) {
   {
     LaunchScope ls(s, "moments1");
-    LAPS_LAUNCH(k_moments1, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, s->uu, s->npts, s->p.adiabatic_index, s->d_partial);
+    LAPS_LAUNCH(k_moments1, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, s->uu, s->npts, s->p.adiabatic_index, s->d_partial, s->incomp ? 1 : 0);
     LAPS_TRY(check_launch(s, "k_moments1"));
   }
   LAPS_TRY(reduce_final(s, 18, 0, 0.0));
@@ -1017,7 +1175,7 @@ int laps_get_state(laps_handle s, double* uu_local, double* uu_prim_local) {
     if (!s->prim) LAPS_CK(s, cudaMalloc((void**)&s->prim, 4 * s->npts * sizeof(double)));
     {
       LaunchScope ls(s, "cons_to_prim");
-      LAPS_LAUNCH(k_cons_to_prim, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, (const double*)s->uu, s->prim, s->npts, s->p.adiabatic_index);
+      LAPS_LAUNCH(k_cons_to_prim, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, (const double*)s->uu, s->prim, s->npts, s->p.adiabatic_index, s->incomp ? 1 : 0);
       LAPS_TRY(check_launch(s, "k_cons_to_prim"));
     }
     LAPS_CK(s, cudaMemcpyAsync(uu_prim_local, s->prim, 4 * s->npts * sizeof(double), cudaMemcpyDeviceToHost, s->stream));

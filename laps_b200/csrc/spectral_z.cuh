@@ -17,7 +17,10 @@
 
 namespace laps {
 
-enum ZKind { kZRhs = 0, kZForwardOnly = 1, kZInverseOnly = 2, kZCurrent = 3 };
+enum ZKind { kZRhs = 0, kZForwardOnly = 1, kZInverseOnly = 2, kZCurrent = 3,
+             // incompressible tree (src_incompressible/mhdrhs.f90):
+             kZGrad = 4,   // i k_a u^[v] / cx, a = jcomp   (calc_gradient_velocity_real, :308-390)
+             kZDiv = 5 };  // i (kx u^[v] + ky u^[v+1] + kz u^[v+2]) / cx   (calc_divB_real / calc_divV_real, :536-647)
 
 // One row of work (blockIdx.y).  For kZRhs:
 //   G = ca*(i kx)*W2[fa] + cb*(i ky)*W2[fb] + cx*W2[fx]      (missing terms have index < 0)
@@ -72,6 +75,7 @@ struct ZParams {
   int z_radial;          // 2D/mhdrhs.f90:278-280: kx is stretched too
   int bg_all_kz;         // 2D/mhdrhs.f90:372-374: if_conserve_background skips every mode with ix == 1
   double da_thresh;      // dealias option 1: smallest s with sqrt(s) > 1./3. (dealiasing.f90:94)
+  double aeb_p;          // incompressible tree: 2*adiabatic_index, the expanding-box coefficient of the pressure row
   int tune;              // bit 0: L2-prefetch state/history lines, bit 1: L2-prefetch the G inputs
   ZTask task[12];
 };
@@ -291,6 +295,26 @@ k_spec_z(const ZParams P) {
     const size_t voff = (size_t)K.v * P.fstride + coff;
     LAPS_UNROLL
     for (int e = 0; e < 8; ++e) r[e] = live ? P.u_in[voff + u + e * G::NT] : mk(0.0, 0.0);
+  } else if (K.kind == kZGrad) {
+    const cplx* U = P.u_in + (size_t)K.v * P.fstride + coff;
+    LAPS_UNROLL
+    for (int e = 0; e < 8; ++e) {
+      const int kz = u + e * G::NT;
+      const double ka = K.jcomp == 0 ? kxe : (K.jcomp == 1 ? kye : __ldg(P.kze + kz));
+      const cplx t = cmul_i(live ? U[kz] : mk(0.0, 0.0), ka);
+      r[e] = mk(__ddiv_rn(t.x, K.cx), __ddiv_rn(t.y, K.cx));
+    }
+  } else if (K.kind == kZDiv) {
+    const cplx* U = P.u_in + (size_t)K.v * P.fstride + coff;
+    LAPS_UNROLL
+    for (int e = 0; e < 8; ++e) {
+      const int kz = u + e * G::NT;
+      const cplx a = live ? U[kz] : mk(0.0, 0.0);
+      const cplx b = live ? U[P.fstride + kz] : mk(0.0, 0.0);
+      const cplx c = live ? U[2 * P.fstride + kz] : mk(0.0, 0.0);
+      const cplx t = cadd(cadd(cmul_i(a, kxe), cmul_i(b, kye)), cmul_i(c, __ldg(P.kze + kz)));
+      r[e] = mk(__ddiv_rn(t.x, K.cx), __ddiv_rn(t.y, K.cx));
+    }
   } else {  // kZCurrent: J^ = i k x B^ (mhdrhs.f90:329-336) from the updated state
     const int j = K.jcomp;
     const cplx* B1 = P.u_in + (size_t)(4 + (j + 1) % 3) * P.fstride + coff;  // B_{j+1}

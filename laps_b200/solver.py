@@ -127,6 +127,26 @@ class Solver:
         self._ck(self._lib.laps_max_divb(self._h, C.byref(out)))
         return out.value
 
+    def calc_max_divV(self) -> float:
+        """src_incompressible/mhd.f90:616-664."""
+        out = C.c_double()
+        self._ck(self._lib.laps_max_divv(self._h, C.byref(out)))
+        return out.value
+
+    def calc_max_div_real(self):
+        """calc_divB_real/calc_divV_real + calc_max_div*_real (src_incompressible/mhdrhs.f90:536-647,
+        mhd.f90:668-731) -> (max |div B|, max |div u|) in real space."""
+        out = np.zeros(2)
+        self._ck(self._lib.laps_max_div_real(self._h, capi._dptr(out)))
+        return float(out[0]), float(out[1])
+
+    @property
+    def rho0(self) -> float:
+        """Background density of the incompressible tree after update_rho_p (AEBmod.f90:123-134)."""
+        out = C.c_double()
+        self._ck(self._lib.laps_get_rho0(self._h, C.byref(out)))
+        return out.value
+
     def calc_rms(self):
         """mhdrms.f90:53-126 -> (uu_ave[8], uu_rms[8], rho_u2[3])."""
         out = np.zeros(19)

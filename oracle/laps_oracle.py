@@ -67,6 +67,9 @@ class Params:
     # 2D tree only (src_compressible/2D/mhd.f90:23,35,44; 2D/mhdinit.f90:23)
     if_z_radial: bool = False
     if_limit_dt_increase: bool = False
+    # incompressible tree only (src_incompressible/mhdinit.f90:15): which State class applies, and rho0
+    incompressible: bool = False
+    rho0: float = 1.0
 
 
 # --------------------------------------------------------------------------------------
@@ -624,6 +627,208 @@ class State2D(State):
         self.evolve_radius(self.time)
         if calc_dt:
             self.vardt()
+
+
+# --------------------------------------------------------------------------------------
+# incompressible tree (src_incompressible/): pressure projection instead of an energy equation
+# --------------------------------------------------------------------------------------
+class StateIncompressible(State):
+    """Restatement of the 3D incompressible tree; citations are relative to src_incompressible/.
+    uu = [rho, rho*u (3), B (3), p] (uu(8) is the PRESSURE here, mhdinit.f90:210), uu_prim = u (3
+    components, mhdinit.f90:5,142; the 4th row of the base-class array is unused).  ``rho0`` is the
+    namelist background density (mhdinit.f90:15) that calc_gradient_velocity_real divides by
+    (mhdrhs.f90:366); update_rho_p compounds it every step in the expanding box (AEBmod.f90:123-134).
+    Every stage re-derives the spectrum from the real fields (mhd.f90:305)."""
+
+    def __init__(self, p: Params, p0: float = 1.0):
+        super().__init__(p)
+        self.rho0 = float(p.rho0)
+        self.p0 = float(p0)
+        self.current_density = np.zeros((3, p.nz, p.ny, p.nx))
+        self.grad_velocity = np.zeros((9, p.nz, p.ny, p.nx))
+
+    def set_primitive(self, prim: np.ndarray):
+        """initial_calc_conserve_variable (mhdinit.f90:1031-1042) + transform_uu_real_to_fourier."""
+        uu = np.array(prim, dtype=np.float64, copy=True)
+        self.uu_prim[0:3] = uu[1:4]
+        uu[1] = uu[0] * self.uu_prim[0]
+        uu[2] = uu[0] * self.uu_prim[1]
+        uu[3] = uu[0] * self.uu_prim[2]
+        self.uu = uu
+        self.uu_fourier = fft_forward(self.uu)
+
+    def calc_gradient_velocity_real(self):
+        """mhdrhs.f90:308-390 — d u_b / d x_a = IFFT( k_a (rho u_b)^ / rho0 ), slot 3*b + a."""
+        kx, ky, kz = self.kvec()
+        uf = self.uu_fourier
+        gf = np.empty((9,) + uf.shape[1:], dtype=np.complex128)
+        for b in range(3):
+            gf[3 * b + 0] = 1j * kx * uf[1 + b]
+            gf[3 * b + 1] = 1j * ky * uf[1 + b]
+            gf[3 * b + 2] = 1j * kz * uf[1 + b]
+        gf = gf / self.rho0                                     # mhdrhs.f90:366
+        self.grad_velocity = fft_inverse(gf, self.p.nx)
+
+    def calc_flux_for_pressure(self):
+        """mhdrhs.f90:392-441 — -(rho u . grad) u + J x B."""
+        uu, G, J = self.uu, self.grad_velocity, self.current_density
+        fp = np.empty((3,) + uu.shape[1:])
+        fp[0] = (-uu[1] * G[0] - uu[2] * G[1] - uu[3] * G[2] + J[1] * uu[6] - J[2] * uu[5])
+        fp[1] = (-uu[1] * G[3] - uu[2] * G[4] - uu[3] * G[5] + J[2] * uu[4] - J[0] * uu[6])
+        fp[2] = (-uu[1] * G[6] - uu[2] * G[7] - uu[3] * G[8] + J[0] * uu[5] - J[1] * uu[4])
+        return fp
+
+    def calc_pressure_fourier(self, fpf):
+        """mhdrhs.f90:471-523 — p^ = -(k . Fp^)/k^2, zero where k^2 < 1e-10."""
+        kxi, kyi, kzi = self.kvec()
+        kx, ky, kz = 1j * kxi, 1j * kyi, 1j * kzi
+        k2 = np.broadcast_to(self.k_square, fpf[0].shape)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ph = -(kx * fpf[0] + ky * fpf[1] + kz * fpf[2]) / k2
+        self.uu_fourier[7] = np.where(k2 < 1e-10, 0.0, ph)
+
+    def calc_flux(self):
+        """mhdrhs.f90:26-85 — the electric field -u x B (+ Hall term)."""
+        p = self.p
+        uu, pr = self.uu, self.uu_prim
+        ux, uy, uz = pr[0], pr[1], pr[2]
+        Bx, By, Bz = uu[4], uu[5], uu[6]
+        flux = np.empty((3,) + uu.shape[1:])
+        flux[0] = uz * By - uy * Bz
+        flux[1] = ux * Bz - uz * Bx
+        flux[2] = uy * Bx - ux * By
+        if p.if_hall:
+            J, di, rho = self.current_density, p.ion_inertial_length, uu[0]
+            flux[0] = flux[0] + di / rho * (J[1] * uu[6] - J[2] * uu[5])
+            flux[1] = flux[1] + di / rho * (J[2] * uu[4] - J[0] * uu[6])
+            flux[2] = flux[2] + di / rho * (J[0] * uu[5] - J[1] * uu[4])
+        return flux
+
+    def calc_rhs(self, flux_fourier, fpf):
+        """mhdrhs.f90:118-236."""
+        p = self.p
+        kxi, kyi, kzi = self.kvec()
+        kx, ky, kz = 1j * kxi, 1j * kyi, 1j * kzi
+        ff, uf = flux_fourier, self.uu_fourier
+        k2 = np.broadcast_to(self.k_square, uf[0].shape)
+        bg = k2 < 1e-10
+        fnl = np.zeros_like(uf)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            kdotfp = (kx * fpf[0] + ky * fpf[1] + kz * fpf[2]) / k2
+        kdotfp = np.where(bg, 0.0, kdotfp)
+        fnl[1] = np.where(bg, 0.0, fpf[0] + kdotfp * kx)
+        fnl[2] = np.where(bg, 0.0, fpf[1] + kdotfp * ky)
+        fnl[3] = np.where(bg, 0.0, fpf[2] + kdotfp * kz)
+        fnl[4] = kz * ff[1] - ky * ff[2]
+        fnl[5] = kx * ff[2] - kz * ff[0]
+        fnl[6] = ky * ff[0] - kx * ff[1]
+        if p.if_AEB:
+            tau = self.tau_exp
+            for v, c in enumerate((2.0, 2.0, 3.0, 3.0, 2.0, 1.0, 1.0)):
+                fnl[v] = fnl[v] - c * uf[v] / tau
+            fnl[7] = fnl[7] - 2.0 * p.adiabatic_index * uf[7] / tau
+        if p.if_visc and p.if_visc_exp:
+            for v in (1, 2, 3):
+                fnl[v] = fnl[v] - p.viscosity * uf[v] * self.k_square
+        if p.if_resis and p.if_resis_exp:
+            ksq = k2.copy()
+            if p.if_conserve_background:
+                ksq[0, :, 0] = 0.0                              # `cycle` where ix==1 .and. iz==1 (mhdrhs.f90:223-225)
+            for v in (4, 5, 6):
+                fnl[v] = fnl[v] - p.resistivity * uf[v] * ksq
+        self.fnl = fnl
+        return fnl
+
+    def update_uu_prim_from_uu(self):
+        """mhdrhs.f90:239-246."""
+        uu, pr = self.uu, self.uu_prim
+        pr[0] = uu[1] / uu[0]
+        pr[1] = uu[2] / uu[0]
+        pr[2] = uu[3] / uu[0]
+
+    def stage(self, irk, retransform: bool = True):
+        """One pass of the loop body of evolve (mhd.f90:303-350)."""
+        if retransform:
+            self.uu_fourier = fft_forward(self.uu)               # mhd.f90:305
+        self.calc_current_density_real()                         # :308 (always, J x B needs it)
+        self.calc_gradient_velocity_real()                       # :309
+        fpf = fft_forward(self.calc_flux_for_pressure())         # :312-315
+        self.calc_pressure_fourier(fpf)                          # :318
+        ff = fft_forward(self.calc_flux())                       # :321-324
+        self.calc_rhs(ff, fpf)
+        self.rkt(irk)
+        self.dealias()
+        self.uu = fft_inverse(self.uu_fourier, self.p.nx)
+        self.update_uu_prim_from_uu()
+
+    def update_rho_p(self):
+        """AEBmod.f90:123-134 — compounds rho0 and p0 with the CURRENT radius on every call."""
+        q = self.p.radius0 / self.radius
+        self.rho0 = self.rho0 * q ** 2
+        self.p0 = self.p0 * q ** (2 * self.p.adiabatic_index)
+
+    def evolve(self, retransform: bool = True):
+        for irk in range(3):
+            self.stage(irk, retransform)
+        self.update_rho_p()                                      # mhd.f90:353
+
+    def vardt(self):
+        """mhd.f90:356-457 — Alfven and flow speeds only."""
+        p, g = self.p, self.g
+        uu, pr = self.uu, self.uu_prim
+        sq = np.sqrt(uu[0])
+        dmin = min(g.dx, g.dy, g.dz)
+        cm = []
+        for d in range(3):
+            ca = uu[4 + d] / sq
+            u = pr[d]
+            cm.append(np.maximum(np.maximum(np.abs(u + ca), np.abs(u - ca)), np.abs(u)))
+        if p.if_hall:
+            ch = p.ion_inertial_length / uu[0] * np.maximum(np.maximum(uu[4], uu[5]), uu[6]) / dmin
+            cm = [np.maximum(c, ch) for c in cm]
+        rr = self.radius / p.radius0
+        with np.errstate(divide="ignore"):
+            dtx = g.dx / cm[0]
+            dty = g.dy / cm[1] * rr
+            dtz = g.dz / cm[2] * rr
+        dtmin = float(np.minimum(np.minimum(dtx, dty), dtz).min()) * p.cfl
+        if self.dt < 0.98 * dtmin or self.dt > 1.02 * dtmin:
+            self.dt = dtmin
+        self.rkt_init(self.dt)
+        return self.dt
+
+    # ---------------------------------------------------------------- diagnostics
+    def calc_max_divV(self):
+        """mhd.f90:616-664 (Fourier-space maximum of |k . (rho u)^| / rho0)."""
+        kx, ky, kz = self.kvec()
+        uf = self.uu_fourier
+        return float(np.max(np.abs(1j * kx * uf[1] + 1j * ky * uf[2] + 1j * kz * uf[3]))) / self.rho0
+
+    def calc_max_div_real(self):
+        """calc_divB_real/calc_divV_real + calc_max_div*_real (mhdrhs.f90:536-647, mhd.f90:668-731):
+        maxima of |div B| and |div u| in real space, as the driver prints them."""
+        kx, ky, kz = self.kvec()
+        uf = self.uu_fourier
+        db = fft_inverse(1j * kx * uf[4] + 1j * ky * uf[5] + 1j * kz * uf[6], self.p.nx)
+        dv = fft_inverse((1j * kx * uf[1] + 1j * ky * uf[2] + 1j * kz * uf[3]) / self.rho0, self.p.nx)
+        return float(np.abs(db).max()), float(np.abs(dv).max())
+
+    def calc_rms(self):
+        """mhdrms.f90:47-120.  The reference reads uu_prim(:,:,:,4), which does not exist in this tree
+        (uu_prim has 3 components): entry 8 is taken from the pressure uu(8) here."""
+        uu, pr = self.uu, self.uu_prim
+        fields = [uu[0], pr[0], pr[1], pr[2], uu[4], uu[5], uu[6], uu[7]]
+        n = float(self.p.nx * self.p.ny * self.p.nz)
+        ave = np.array([f.sum() for f in fields]) / n
+        sq = np.array([(f ** 2).sum() for f in fields]) / n
+        rho_u2 = np.array([(uu[0] * (pr[i] - ave[1 + i]) ** 2).sum() for i in range(3)]) / n
+        return ave, sq - ave ** 2, rho_u2
+
+    def invariants(self):
+        uu, pr = self.uu, self.uu_prim
+        n = float(self.p.nx * self.p.ny * self.p.nz)
+        e = 0.5 * (uu[1] * pr[0] + uu[2] * pr[1] + uu[3] * pr[2] + uu[4] ** 2 + uu[5] ** 2 + uu[6] ** 2)
+        return np.array([e.sum() / n, (pr[0] * uu[4] + pr[1] * uu[5] + pr[2] * uu[6]).sum() / n, self.calc_max_divB()])
 
 
 # --------------------------------------------------------------------------------------

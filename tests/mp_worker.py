@@ -43,7 +43,8 @@ def main():
         dist.init_process_group("gloo")
     lib = cfg.get("lib")
     nx, ny, nz = cfg["shape"]
-    p, prim = pc.make_case(nx, ny, nz, **cfg.get("case", {}))
+    make = pc.make_case_incompressible if cfg.get("incompressible") else pc.make_case
+    p, prim = make(nx, ny, nz, **cfg.get("case", {}))
     g = Solver(lib, rank=rank, nranks=world, device=rank if backend == "nccl" else 0, **pc.solver_kwargs(p))
     connect(g, world, device)
     zo, zn, yo, yn = g.ext.z_offset, g.ext.z_size, g.ext.y_offset, g.ext.y_size
@@ -74,7 +75,7 @@ def main():
     assert pc.rel_l2(b, a[:, zo:zo + zn]) < 1e-13
 
     # the RK step, driven like mhd.f90: vardt; nsteps x (evolve; evolve_radius; vardt)
-    o = lo.State(p)
+    o = pc.oracle_state(p)
     o.set_primitive(prim)
     g.set_primitive(prim[:, zo:zo + zn])
     o.vardt()
@@ -99,7 +100,14 @@ def main():
     inv = g.invariants()
     oinv = o.invariants()
     assert abs(inv[0] - oinv[0]) <= 1e-9 * abs(oinv[0])
-    t = torch.tensor(list(ave) + list(rms) + list(ru2) + list(inv) + [g.dt], dtype=torch.float64)
+    extra = []
+    if p.incompressible:   # the divergence diagnostics of the incompressible driver (mhd.f90:616-731)
+        dv, odv = g.calc_max_divV(), o.calc_max_divV()
+        assert abs(dv - odv) <= 1e-9 * odv, (dv, odv)
+        dr, odr = g.calc_max_div_real(), o.calc_max_div_real()
+        assert abs(dr[1] - odr[1]) <= 1e-9 * odr[1], (dr, odr)
+        extra = [dv, dr[0], dr[1], g.rho0]
+    t = torch.tensor(list(ave) + list(rms) + list(ru2) + list(inv) + [g.dt] + extra, dtype=torch.float64)
     if device is not None:
         t = t.to(device)
     ts = [torch.empty_like(t) for _ in range(world)]

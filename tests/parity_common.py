@@ -66,6 +66,8 @@ def make_case_2d(nx, ny, hall=True, aeb=True, z_radial=False, dealias=1, visc=Tr
 
 def solver_kwargs(p: lo.Params):
     extra = dict(ndim=2, if_z_radial=p.if_z_radial, if_limit_dt_increase=p.if_limit_dt_increase) if p.nz == 1 else {}
+    if p.incompressible:
+        extra = dict(incompressible=1, rho0=p.rho0)
     return dict(**extra, **_solver_kwargs(p))
 
 
@@ -79,9 +81,24 @@ def _solver_kwargs(p: lo.Params):
                 if_hall=p.if_hall, ion_inertial_length=p.ion_inertial_length)
 
 
+def oracle_state(p):
+    if p.incompressible:
+        return lo.StateIncompressible(p)
+    return lo.State2D(p) if p.nz == 1 else lo.State(p)
+
+
+def make_case_incompressible(nx, ny, nz, rho0=1.0, **kw):
+    """BASELINE config 3 family (src_incompressible): the turbulence case of make_case run through the
+    incompressible tree (uu(8) = pressure); drho0 = 0.01 keeps rho non-uniform, which the tree allows."""
+    p, prim = make_case(nx, ny, nz, **kw)
+    p.incompressible = True
+    p.rho0 = rho0
+    return p, prim
+
+
 def run_both(p, prim, nsteps, lib_path=None, t0=0.0):
     """Drive oracle and library exactly as mhd.f90 does: [set time]; vardt; nsteps x step."""
-    o = lo.State2D(p) if p.nz == 1 else lo.State(p)
+    o = oracle_state(p)
     o.set_primitive(prim)
     g = Solver(lib_path, **solver_kwargs(p))
     g.set_primitive(prim)
@@ -124,7 +141,7 @@ def check_state(o, g, tol_field, tol_spec=None):
     uu, prim = g.get_state()
     for v in range(8):
         assert rel_l2(uu[v], o.uu[v]) < tol_field, (v, rel_l2(uu[v], o.uu[v]))
-    for v in range(4):
+    for v in range(3 if o.p.incompressible else 4):
         assert rel_l2(prim[v], o.uu_prim[v]) < 10 * tol_field, (v, rel_l2(prim[v], o.uu_prim[v]))
     uf = g.uu_fourier()
     for v in range(8):

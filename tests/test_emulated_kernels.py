@@ -45,6 +45,22 @@ def test_one_step_2d_tree(emu, kw):
     g.close()
 
 
+@pytest.mark.parametrize("kw", [dict(hall=True, aeb=True, dealias=1), dict(hall=True, aeb=True, corot=True, dealias=2),
+                                dict(hall=False, aeb=False, dealias=0, explicit=True, conserve_bg=True)])
+def test_one_step_incompressible_tree(emu, kw):
+    """src_incompressible: projection kernel, gradient/current tasks, retransform mode (dealias_option 0)."""
+    p, prim = pc.make_case_incompressible(16, 16, 16, **kw)
+    o, g = pc.run_both(p, prim, 2, lib_path=emu)
+    pc.check_state(o, g, 1e-11)
+    pc.check_diagnostics(o, g, 1e-9)
+    assert abs(g.calc_max_divV() - o.calc_max_divV()) <= 1e-9 * o.calc_max_divV()
+    db, dv = g.calc_max_div_real()
+    odb, odv = o.calc_max_div_real()
+    assert abs(dv - odv) <= 1e-9 * odv and abs(db - odb) <= 1e-9 * max(odb, 1e-6)
+    assert g.rho0 == o.rho0
+    g.close()
+
+
 def test_mask_pruning_is_bit_exact(emu):
     pc.check_pruning_is_exact((32, 16, 32), 2, lib_path=emu, hall=True, aeb=True, dealias=1)
     pc.check_pruning_is_exact((32, 32), 2, lib_path=emu, hall=True, aeb=True, dealias=3)

@@ -24,3 +24,9 @@ def test_three_gpus_remainder_on_last_rank():
     if _ngpu() < 3:
         pytest.skip("needs 3 GPUs")
     run_ranks(3, dict(backend="nccl", shape=(32, 64, 32), case=dict(hall=True, aeb=True, corot=True, dealias=2), steps=1))
+
+
+def test_two_gpus_incompressible_tree():
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_ranks(2, dict(backend="nccl", shape=(64, 64, 64), incompressible=True, case=dict(hall=True, aeb=True, dealias=1), steps=2))

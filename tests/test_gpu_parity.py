@@ -64,19 +64,61 @@ def test_2d_tree_parity(name, kw):
 
 def test_2d_tree_2048_properties():
     """BASELINE config 2 at full size (2048^2, Hall, no expansion): k=0 mode conserved bit-exactly,
-    div B at round-off, forward transform of the real state reproduces the spectrum."""
+    div B conserved to round-off, forward transform of the real state reproduces the spectrum."""
     p, prim = pc.make_case_2d(2048, 2048, hall=True, aeb=False, dealias=1)
     with Solver(**pc.solver_kwargs(p)) as g:
         g.set_primitive(prim)
         s0 = g.uu_fourier()[:, 0, 0, 0].copy()
+        d0 = g.calc_max_divB()     # the smooth test field is not solenoidal: div B is a conserved, non-zero quantity
         g.vardt()
         for i in range(3):
             g.step(calc_dt=(i == 2))
         assert np.array_equal(g.uu_fourier()[:, 0, 0, 0], s0)
-        assert g.calc_max_divB() < 1e-12
+        # dB/dt = curl E (2D/mhdrhs.f90:308-313) keeps k.B^ fixed; only the implicit resistivity damps it (~4e-7 here)
+        assert abs(g.calc_max_divB() - d0) < 1e-5 * d0
         uu, _ = g.get_state()
         assert np.isfinite(uu).all()
         assert pc.rel_l2(g.fft_forward(uu[:2]), g.uu_fourier()[:2]) < 1e-13
+
+
+@pytest.mark.parametrize("name,kw", [("mhd", dict(hall=False, aeb=False, dealias=1)),
+                                     ("hall_aeb_mask", dict(hall=True, aeb=True, dealias=1)),
+                                     ("hall_aeb_corot_filter", dict(hall=True, aeb=True, corot=True, dealias=2)),
+                                     ("explicit_retransform", dict(hall=True, aeb=False, dealias=0, explicit=True, conserve_bg=True))])
+def test_incompressible_tree_parity_64(name, kw):
+    """BASELINE config 3 family (src_incompressible) at 64^3, two steps, against the oracle."""
+    p, prim = pc.make_case_incompressible(64, 64, 64, **kw)
+    o, g = pc.run_both(p, prim, 2)
+    pc.check_state(o, g, 1e-11)
+    pc.check_diagnostics(o, g, 1e-9)
+    assert abs(g.calc_max_divV() - o.calc_max_divV()) <= 1e-9 * o.calc_max_divV()
+    db, dv = g.calc_max_div_real()
+    odb, odv = o.calc_max_div_real()
+    assert abs(dv - odv) <= 1e-9 * odv and abs(db - odb) <= 1e-9 * max(odb, 1e-6)
+    assert g.rho0 == o.rho0
+    g.close()
+
+
+def test_incompressible_tree_256_properties():
+    """BASELINE config 3 at full size (256^3 decaying turbulence, no expansion, no Hall): the projection keeps
+    div(rho u) fixed, the k=0 mode of rho u and B is conserved bit-exactly, div B stays at round-off."""
+    n = 256
+    kw = dict(nx=n, ny=n, nz=n, Lx=24.0, Ly=24.0, Lz=24.0, adiabatic_index=1.666667, if_resis=1, resistivity=1e-4,
+              if_visc=1, viscosity=1e-4, cfl=0.5, dealias_option=1, incompressible=1, rho0=1.0)
+    prim = synthetic.turbulence_slab(n, n, n, 24.0, 24.0, 24.0, kmax=8, drho0=0.0)
+    with Solver(**kw) as g:
+        g.set_primitive(prim)
+        s0 = g.uu_fourier()[:7, 0, 0, 0].copy()
+        dv0 = g.calc_max_divV()
+        g.vardt()
+        for _ in range(2):
+            g.step()
+        uu, _ = g.get_state()
+        assert np.isfinite(uu).all()
+        assert np.array_equal(g.uu_fourier()[:7, 0, 0, 0], s0)
+        assert g.calc_max_divB() < 1e-13
+        assert g.calc_max_divV() < max(2 * dv0, 1e-12)       # solenoidal initial velocity, uniform density
+        assert abs(uu[7].mean()) < 1e-14                      # the pressure carries no k=0 mode (mhdrhs.f90:508-511)
 
 
 def test_dealias_mask_bit_exact():

@@ -58,3 +58,8 @@ def test_two_ranks_hall_aeb(emu):
 def test_three_ranks_remainder_on_last_rank(emu):
     # ny = nz = 16 over 3 ranks: slabs of 5, 5, 6 (parallel.f90:326-349)
     run_ranks(3, dict(lib=emu, shape=(16, 16, 16), case=dict(hall=True, aeb=True, corot=True, dealias=2), steps=1))
+
+
+def test_two_ranks_incompressible_tree(emu):
+    # src_incompressible: pressure projection, 12 inverse + 6 forward transforms per stage through the same exchange
+    run_ranks(2, dict(lib=emu, shape=(16, 16, 16), incompressible=True, case=dict(hall=True, aeb=True, dealias=1), steps=1))

@@ -273,3 +273,104 @@ def test_2d_square_dealias_and_vardt_limits():
     assert s.vardt() == 0.5 * dt0
     s.dt = 2.0 * dt0
     assert s.vardt() == dt0
+
+
+# --------------------------------------------------------------------------------------
+# incompressible tree (src_incompressible): pins for StateIncompressible
+# --------------------------------------------------------------------------------------
+def _incompressible_alfven_error(dt, T=0.4):
+    p = lo.Params(nx=32, ny=8, nz=8, Lx=2 * lo.PI, Ly=2 * lo.PI, Lz=2 * lo.PI, dealias_option=1, incompressible=True)
+    prim = lo.ic_uniform_background(p, bx0=1.0, press0=1.0)
+    prim = lo.ic_alfven_wave(p, prim, db0=0.1)
+    s = lo.StateIncompressible(p)
+    s.set_primitive(prim)
+    s.dt = dt
+    s.rkt_init(dt)
+    for _ in range(int(round(T / dt))):
+        s.evolve()
+        s.time += dt
+        s.evolve_radius(s.time)
+        s.rkt_init(dt)
+    x = lo.Grid(p).xgrid
+    err = max(np.abs(s.uu[6][0, 0, :] + 0.1 * np.sin(x - s.time)).max(),
+              np.abs(s.uu[5][0, 0, :] + 0.1 * np.cos(x - s.time)).max())
+    return err, s
+
+
+def test_incompressible_alfven_wave_is_an_exact_solution_third_order():
+    """A finite-amplitude Alfven wave u = -b/sqrt(rho) is an exact solution of incompressible MHD:
+    it translates at v_A with the RK3 error only, and the projected pressure fluctuation vanishes."""
+    e1, _ = _incompressible_alfven_error(0.02)
+    e2, s2 = _incompressible_alfven_error(0.01)
+    assert e1 < 5e-8 and e2 < 5e-9 and 6.5 < e1 / e2 < 9.5
+    assert np.abs(s2.uu[7]).max() < 1e-15          # |B| uniform: -(u.grad)u + JxB is solenoidal, p^ = 0
+    assert s2.calc_max_divV() < 1e-15 and s2.calc_max_divB() < 1e-15
+
+
+def _incompressible_turbulence(n=16, **kw):
+    p = lo.Params(nx=n, ny=n, nz=n, Lx=24.0, Ly=24.0, Lz=24.0, dealias_option=kw.pop("dealias", 1), incompressible=True,
+                  if_resis=True, resistivity=1e-4, if_visc=True, viscosity=1e-4, **kw)
+    prim = lo.ic_uniform_background(p, bx0=1.0, press0=1.0)
+    prim = lo.ic_turbulence(p, prim, 1.0, 0.0, 0.0, nmodex=2, nmodey=2, nmodez=2, seeds=(3, 4, 5))
+    s = lo.StateIncompressible(p)
+    s.set_primitive(prim)
+    return p, s
+
+
+def test_incompressible_pressure_solves_the_poisson_equation():
+    """calc_pressure_fourier (mhdrhs.f90:471-523) against an independent full-complex-FFT evaluation of
+    laplace(p) = div Fp, and the projected momentum tendency is solenoidal."""
+    p, s = _incompressible_turbulence()
+    s.calc_current_density_real()
+    s.calc_gradient_velocity_real()
+    fp = s.calc_flux_for_pressure()
+    fpf = lo.fft_forward(fp)
+    s.calc_pressure_fourier(fpf)
+    pressure = lo.fft_inverse(s.uu_fourier[7], p.nx)
+    k = 2 * np.pi * np.fft.fftfreq(p.nx, d=p.Lx / p.nx)
+    KZ, KY, KX = np.meshgrid(k, k, k, indexing="ij")
+    F = [np.fft.fftn(f) for f in fp]
+    div = 1j * (KX * F[0] + KY * F[1] + KZ * F[2])
+    lap = -(KX ** 2 + KY ** 2 + KZ ** 2) * np.fft.fftn(pressure)
+    nyq = (np.abs(KX) == np.abs(k).max()) | (np.abs(KY) == np.abs(k).max()) | (np.abs(KZ) == np.abs(k).max())
+    assert np.abs((lap - div)[~nyq]).max() < 1e-10 * np.abs(div).max()
+    assert abs(pressure.mean()) < 1e-16
+    ff = lo.fft_forward(s.calc_flux())
+    fnl = s.calc_rhs(ff, fpf)
+    kx, ky, kz = s.kvec()
+    assert np.abs(kx * fnl[1] + ky * fnl[2] + kz * fnl[3]).max() < 1e-16
+    assert np.all(fnl[0] == 0) and np.all(fnl[7] == 0)
+
+
+@pytest.mark.parametrize("dealias,tol", [(1, 1e-12), (2, 1e-12)])
+def test_incompressible_retransform_is_identity_on_band_limited_spectra(dealias, tol):
+    """mhd.f90:305 re-derives uu_fourier from uu at the start of every stage; after dealiasing (Nyquist
+    planes removed) that is the identity to round-off — the property the library's default relies on."""
+    p, a = _incompressible_turbulence(dealias=dealias, if_hall=True, ion_inertial_length=0.2, if_AEB=True, Ur0=1.167)
+    _, b = _incompressible_turbulence(dealias=dealias, if_hall=True, ion_inertial_length=0.2, if_AEB=True, Ur0=1.167)
+    a.vardt()
+    b.vardt()
+    for _ in range(4):
+        a.step()
+        b.evolve(retransform=False)
+        b.time += b.dt
+        b.evolve_radius(b.time)
+        b.vardt()
+    for v in range(8):
+        d = np.linalg.norm(a.uu[v] - b.uu[v]) / np.linalg.norm(a.uu[v])
+        assert d < tol, (v, d)
+    assert a.rho0 == b.rho0 and a.rho0 < 1.0       # update_rho_p compounds (AEBmod.f90:123-134)
+
+
+def test_incompressible_k0_and_divergence_invariants():
+    p, s = _incompressible_turbulence(if_hall=True, ion_inertial_length=0.2)
+    k0 = s.uu_fourier[:7, 0, 0, 0].copy()
+    dv0 = s.calc_max_divV()
+    s.vardt()
+    for _ in range(5):
+        s.step()
+    # fnl(k=0) = 0 exactly; the per-stage FFT round trip of mhd.f90:305 moves the mode by round-off only
+    assert np.abs(s.uu_fourier[:7, 0, 0, 0] - k0).max() < 1e-15
+    assert s.calc_max_divB() < 1e-15
+    # div(rho u) of the initial data (non-uniform rho) only decays viscously
+    assert 0.99 * dv0 < s.calc_max_divV() <= dv0 * (1 + 1e-12)
