@@ -122,6 +122,8 @@ def kernel_bytes(name, R, C, nf, ni, hall, fx=1.0, fy=1.0, fyl=1.0):
                 "inv_y": n * C * fx * fy + n * C * fx, "inv_x": n * C * fx + n * R}[k]
     table = {
         "flux": (8 + (3 if hall else 0)) * R + nf * R,
+        # calc_flux fused into the forward x pass: reads uu (8R) + J (3R), writes nf half spectra
+        "flux_fwd_x": (8 + (3 if hall else 0)) * R + nf * C * fx,
         # reads nf flux spectra + u (8C) + fnl_rk (8C, stages 2,3), writes u (8C) + fnl_rk (8C, stages 1,2)
         # + inverse-z output (8C): averaged over the three stages
         "spec_z": (nf + 8 + 8 * 2 / 3 + 8 + 8 * 2 / 3 + 8) * C * fx * fyl,

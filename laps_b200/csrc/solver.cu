@@ -15,6 +15,7 @@
 
 #include "exchange.cuh"
 #include "fft_passes.cuh"
+#include "flux_fwd_x.cuh"
 #include "pointwise.cuh"
 #include "spectral_incomp.cuh"
 #include "spectral_rhs.cuh"
@@ -123,6 +124,7 @@ struct laps_solver {
   bool spectrum_full = true;   // the state still holds masked columns (fresh from laps_set_primitive)
   int slot[19];        // field slot of each flux (F1..F18, expand_term), < 0: not transformed
   int tune_cgz = 0, tune_z = 3, tune_rhs = 1, tune_rcg = 0;
+  int tune_fusex = -1;   // calc_flux fused into the forward x pass: -1 = where it pays (128 <= nx <= 512), 0 = never, 1 = whenever possible
   int num_sms = 148;
   double da_thresh = 0;
   void* ipc_opened[LAPS_MAX_RANKS][3];   // mappings obtained with cudaIpcOpenMemHandle
@@ -277,6 +279,22 @@ int do_fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1, bool
   return check_launch(s, "k_fwd_x");
 }
 
+constexpr int kFuseGroups = 10;   // thread groups (fluxes in flight) per CTA of k_flux_fwd_x: 19 fluxes in two rounds
+template <int N>
+int do_flux_fwd_x(S* s, const FusedFluxParams& fp) {
+  if constexpr (N <= 512) {
+    typedef FTile<N, kFuseGroups> T;
+    constexpr int ctas = (227 * 1024) / (int)(T::SMEM + 1024) < 1 ? 1 : ((227 * 1024) / (int)(T::SMEM + 1024) > 2 ? 2 : (227 * 1024) / (int)(T::SMEM + 1024));
+    LAPS_CK(s, prepare_kernel(k_flux_fwd_x<N, kFuseGroups>, T::SMEM, ctas));
+    LaunchScope ls(s, "flux_fwd_x");
+    dim3 grid((unsigned)(s->nzl * (s->ny / 2)));
+    LAPS_LAUNCH((k_flux_fwd_x<N, kFuseGroups>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, fp);
+    return check_launch(s, "k_flux_fwd_x");
+  } else {
+    s->err = "k_flux_fwd_x: line too long for the shared-memory staging"; return 1;
+  }
+}
+
 template <int N>
 int do_fwd_y(S* s, const cplx* W1, int nfields, bool prune) {
   char name[32]; std::snprintf(name, sizeof(name), "fwd_y%d", nfields);
@@ -387,6 +405,12 @@ int do_incomp_z(S* s, const ZParams& zp) {
 
 int fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1, bool prune) { LAPS_DISPATCH(s->nx, do_fwd_x, s, in, fstride, nfields, W1, prune) }
 int fwd_y(S* s, const cplx* W1, int nfields, bool prune) { LAPS_DISPATCH(s->ny, do_fwd_y, s, W1, nfields, prune) }
+int flux_fwd_x(S* s, const FusedFluxParams& fp) { LAPS_DISPATCH(s->nx, do_flux_fwd_x, s, fp) }
+bool use_fused_flux(const S* s) {
+  if (s->two_d || s->incomp || s->nx > 512 || (s->ny & 1)) return false;
+  if (s->tune_fusex >= 0) return s->tune_fusex != 0;
+  return s->nx >= 128;
+}
 int inv_y(S* s, const cplx* V1, cplx* V2, int nfields, bool prune) { LAPS_DISPATCH(s->ny, do_inv_y, s, V1, V2, nfields, prune) }
 
 // Forward x (+y) passes of `nfields` real fields into the z-pass input buffer W2.  In the 2D tree
@@ -585,6 +609,17 @@ int stage(S* s, int irk) {
   const laps_params& p = s->p;
   if (s->incomp) return stage_incomp(s, irk);
   LAPS_TRY(refresh_current(s));
+  if (use_fused_flux(s)) {  // calc_flux + the forward x pass in one kernel (flux_fwd_x.cuh), then the y pass
+    FusedFluxParams fp;
+    std::memset(&fp, 0, sizeof(fp));
+    fp.uu = s->uu; fp.J = s->J; fp.W1 = buf_W1(s); fp.npts = s->npts;
+    fp.nzl = s->nzl; fp.ny = s->ny; fp.nkx = s->nkx; fp.tw = s->tw_x; fp.scale = 1.0 / s->nx;
+    fp.hall = p.if_hall; fp.aeb = p.if_AEB; fp.gamma = p.adiabatic_index; fp.di = p.ion_inertial_length; fp.tau = s->tau;
+    fp.nflux = s->nf;
+    for (int j = 0; j < 19; ++j) if (s->slot[j] >= 0) fp.id[s->slot[j]] = j;
+    LAPS_TRY(flux_fwd_x(s, fp));
+    LAPS_TRY(fwd_y(s, buf_W1(s), s->nf, true));
+  } else {
   {  // calc_flux (mhdrhs.f90:21-124; 2D/mhdrhs.f90:23-128)
     FluxParams f;
     f.uu = s->uu; f.J = s->J; f.F = buf_F(s); f.npts = s->npts;
@@ -597,6 +632,7 @@ int stage(S* s, int irk) {
   }
   // transform_flux_real_to_fourier (mhdrhs.f90:128-172)
   LAPS_TRY(forward_xy(s, buf_F(s), s->npts, s->nf, true));
+  }
   LAPS_TRY(host_barrier(s));
   {  // z-pass + calc_rhs + rkt + dealias + inverse z
     ZParams z; fill_zparams(s, z, true);
@@ -764,6 +800,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
   if (const char* e = std::getenv("LAPS_TUNE_RHS")) s->tune_rhs = std::atoi(e);
   if (const char* e = std::getenv("LAPS_TUNE_RCG")) s->tune_rcg = std::atoi(e);
   if (const char* e = std::getenv("LAPS_TUNE_Z")) s->tune_z = std::atoi(e);
+  if (const char* e = std::getenv("LAPS_TUNE_FUSEX")) s->tune_fusex = std::atoi(e);
   // The reference re-derives uu_fourier from the real fields at the start of every stage
   // (src_incompressible/mhd.f90:305).  For a spectrum the dealiasing has band-limited (options 1, 2: the
   // Nyquist planes are removed) that round trip is the identity up to round-off and is skipped; with

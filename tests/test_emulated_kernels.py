@@ -61,6 +61,20 @@ def test_one_step_incompressible_tree(emu, kw):
     g.close()
 
 
+def test_fused_flux_forward_x_pass_matches_the_separate_kernels(emu, monkeypatch):
+    """k_flux_fwd_x (calc_flux inside the forward x pass) against k_flux + k_fwd_x: same expressions, same
+    transform -> bit-identical state on the emulator; and against the oracle."""
+    p, prim = pc.make_case(32, 16, 16, hall=True, aeb=True, dealias=1)
+    out = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("LAPS_TUNE_FUSEX", flag)
+        o, g = pc.run_both(p, prim, 2, lib_path=emu)
+        pc.check_state(o, g, 1e-11)
+        out.append((g.get_state()[0], g.uu_fourier()))
+        g.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
 def test_mask_pruning_is_bit_exact(emu):
     pc.check_pruning_is_exact((32, 16, 32), 2, lib_path=emu, hall=True, aeb=True, dealias=1)
     pc.check_pruning_is_exact((32, 32), 2, lib_path=emu, hall=True, aeb=True, dealias=3)

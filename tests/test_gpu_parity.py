@@ -45,6 +45,18 @@ def test_one_step_parity_anisotropic_grid_and_late_start():
     g.close()
 
 
+@pytest.mark.parametrize("flag", ["0", "1"])
+def test_fused_and_separate_flux_x_pass_parity_128(flag, monkeypatch):
+    """calc_flux inside the forward x pass (k_flux_fwd_x, default for 128 <= nx <= 512) and the separate
+    k_flux + k_fwd_x path, both against the oracle at 128 x 64 x 64."""
+    monkeypatch.setenv("LAPS_TUNE_FUSEX", flag)
+    p, prim = pc.make_case(128, 64, 64, hall=True, aeb=True, dealias=1)
+    o, g = pc.run_both(p, prim, 2)
+    pc.check_state(o, g, 1e-11)
+    pc.check_diagnostics(o, g, 1e-9)
+    g.close()
+
+
 def test_mask_pruning_is_bit_exact():
     pc.check_pruning_is_exact((64, 64, 64), 3, hall=True, aeb=True, dealias=1)
     pc.check_pruning_is_exact((128, 64), 3, hall=True, aeb=True, dealias=3)
