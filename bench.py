@@ -109,11 +109,13 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # algorithmic bytes per launch of each kernel; R, C in bytes per field
 # ------------------------------------------------------------------------------------------
-def kernel_bytes(name, R, C, nf, ni, hall, fx=1.0, fy=1.0, fyl=1.0):
+def kernel_bytes(name, R, C, nf, ni, hall, fx=1.0, fy=1.0, fyl=1.0, mass=False):
     """Algorithmic HBM bytes of one launch.  Pass launches carry their field
     count in the name (fwd_x19, inv_y11, inv_y3 ...).  fx, fy = fractions of the kx columns / ky rows
     that survive the dealiasing mask (the passes skip the rest exactly, laps_get_pruning); fyl = the
-    same for the ky rows this rank owns."""
+    same for the ky rows this rank owns.  mass: the continuity row takes its fluxes from the state
+    (laps_get_field_counts) and runs inside the curl_b_inv_z launch instead of the spec_z one."""
+    rows = 7 if mass else 8
     import re
     m = re.fullmatch(r"(fwd_x|fwd_y|inv_y|inv_x)(\d+)", name)
     if m:
@@ -124,10 +126,11 @@ def kernel_bytes(name, R, C, nf, ni, hall, fx=1.0, fy=1.0, fyl=1.0):
         "flux": (8 + (3 if hall else 0)) * R + nf * R,
         # calc_flux fused into the forward x pass: reads uu (8R) + J (3R), writes nf half spectra
         "flux_fwd_x": (8 + (3 if hall else 0)) * R + nf * C * fx,
-        # reads nf flux spectra + u (8C) + fnl_rk (8C, stages 2,3), writes u (8C) + fnl_rk (8C, stages 1,2)
-        # + inverse-z output (8C): averaged over the three stages
-        "spec_z": (nf + 8 + 8 * 2 / 3 + 8 + 8 * 2 / 3 + 8) * C * fx * fyl,
-        "curl_b_inv_z": (3 * C + 3 * C) * fx * fyl,
+        # reads nf flux spectra + u (rows C) + fnl_rk (rows C, stages 2,3), writes u (rows C) + fnl_rk (rows C, stages 1,2)
+        # + inverse-z output (rows C): averaged over the three stages
+        "spec_z": (nf + rows + rows * 2 / 3 + rows + rows * 2 / 3 + rows) * C * fx * fyl,
+        # J^ = ik x B^ (3C in, 3C out) + the continuity row (reads rho u, rho, fnl_rk: 4C + 2/3 C; writes rho, fnl_rk, inverse-z: 2C + 2/3 C)
+        "curl_b_inv_z": (3 * C + 3 * C + ((4 + 2 / 3 + 2 + 2 / 3) * C if mass else 0.0)) * fx * fyl,
         "fwd_z": 2 * 8 * C,
         "cfl": 8 * R,
     }
@@ -296,10 +299,11 @@ def run_gpu(args):
     # ---------------- roofline of the dominant kernel ----------------
     R = 8.0 * n * n * g.nzl
     C = 16.0 * g.nxh * g.nyl * n
-    nf, ni, hall = 18 + kw["if_AEB"], 8 + 3 * kw["if_hall"], bool(kw["if_hall"])
+    (nf, ni), hall = g.field_counts(), bool(kw["if_hall"])
     nkx, kymax, nkyl = g.pruning()
     fx, fy, fyl = nkx / g.nxh, min(1.0, (2 * kymax + 1) / n), nkyl / g.nyl
-    kb = lambda k: kernel_bytes(k, R, C, nf, ni, hall, fx, fy, fyl)  # noqa: E731
+    mass = nf < 18
+    kb = lambda k: kernel_bytes(k, R, C, nf, ni, hall, fx, fy, fyl, mass)  # noqa: E731
     peak, peak_src = peaks()
     top = max(prof.items(), key=lambda kv: kv[1][0]) if prof else None
     roofline = None

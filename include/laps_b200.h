@@ -156,6 +156,12 @@ int laps_transpose_yz_indexmap(laps_handle h, int64_t* out);
  * ky rows.  No pruning: *nkx = nx/2+1, *kymax = ny/2, *nky_local = y_size. */
 int laps_get_pruning(laps_handle h, int32_t* nkx, int32_t* kymax, int32_t* nky_local);
 
+/* Fields transformed per RK stage: *nf forward (real fluxes -> spectra), *ni inverse (state + current density).
+ * The reference transforms 18 (+1 with the expanding box) and 8 (+3 with the Hall term); here the three
+ * mass fluxes are not transformed when dealiasing is on — calc_flux sets them to uu(2:4) (mhdrhs.f90:58-60),
+ * whose spectrum is the state itself — and the 2D tree drops the z fluxes (kz = 0). */
+int laps_get_field_counts(laps_handle h, int32_t* nf, int32_t* ni);
+
 /* Device-time of the last laps_evolve/laps_step in milliseconds (CUDA events on the compute
  * stream), and the number of kernel launches it issued. */
 int laps_last_step_ms(laps_handle h, float* ms, int32_t* launches);

@@ -7,6 +7,7 @@
 #include "cuda_emu.h"
 #define LAPS_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::g_dyn_smem)
 #define LAPS_UNROLL
+#define LAPS_GRID_CONSTANT
 #else
 #include <cuda_runtime.h>
 #define LAPS_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char name##_raw_[]; \
@@ -14,6 +15,8 @@
 #define LAPS_LAUNCH(kernel, grid, block, smem, stream, ...) \
   kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define LAPS_UNROLL _Pragma("unroll")
+// kernel parameter structs that are indexed dynamically stay in the constant bank (no local-memory copy)
+#define LAPS_GRID_CONSTANT __grid_constant__
 #endif
 
 #include <cstdint>

@@ -96,6 +96,31 @@ LAPS_D void twiddle8(cplx (&r)[8], cplx w) {
   r[7] = cmul(r[7], cmul(w4, w3));
 }
 
+// Barrier over the NT threads of one line (whole warps: NT % 32 == 0), else over the CTA.  `bar` is
+// in 1..NBAR (one named barrier per line of the CTA); the ids are immediates so that ptxas reserves
+// NBAR + 1 hardware barriers for the CTA, not all sixteen.
+template <int NT, int NBAR>
+LAPS_D void group_barrier(int bar) {
+#ifdef LAPS_EMU_BUILD
+  (void)bar;
+  __syncthreads();
+#else
+  static_assert(NBAR <= 15, "a CTA has 16 named barriers");
+  if constexpr (NT % 32 == 0) {
+#define LAPS_BAR_CASE(I) case I: if constexpr (I <= NBAR) asm volatile("bar.sync " #I ", %0;" ::"n"(NT) : "memory"); break;
+    switch (bar) {
+      LAPS_BAR_CASE(1) LAPS_BAR_CASE(2) LAPS_BAR_CASE(3) LAPS_BAR_CASE(4) LAPS_BAR_CASE(5)
+      LAPS_BAR_CASE(6) LAPS_BAR_CASE(7) LAPS_BAR_CASE(8) LAPS_BAR_CASE(9) LAPS_BAR_CASE(10)
+      LAPS_BAR_CASE(11) LAPS_BAR_CASE(12) LAPS_BAR_CASE(13) LAPS_BAR_CASE(14) LAPS_BAR_CASE(15)
+      default: break;
+    }
+#undef LAPS_BAR_CASE
+  } else {
+    __syncthreads();
+  }
+#endif
+}
+
 // ------------------------------------------------------------------ staged FFT of one line
 // `tw` points to the forward table tw[m] = exp(-2 pi i m / N), m < N (global memory, L1 resident).
 template <int N, int DIR>
@@ -198,6 +223,15 @@ struct Fft {
     __syncthreads();
     if constexpr (G::NSTAGE >= 3) { middle<1>(u, line, tw); __syncthreads(); }
     if constexpr (G::NSTAGE >= 4) { middle<2>(u, line, tw); __syncthreads(); }
+    last(r, u, line);
+  }
+  // The same with barriers over ONE line's threads only (named barrier `bar`, 1..15): for kernels in
+  // which every line is transformed by whole warps of its own, so that lines need not wait for each other.
+  template <int NBAR>
+  LAPS_D static void finish_g(cplx (&r)[8], int u, cplx* __restrict__ line, const cplx* __restrict__ tw, int bar) {
+    group_barrier<G::NT, NBAR>(bar);
+    if constexpr (G::NSTAGE >= 3) { middle<1>(u, line, tw); group_barrier<G::NT, NBAR>(bar); }
+    if constexpr (G::NSTAGE >= 4) { middle<2>(u, line, tw); group_barrier<G::NT, NBAR>(bar); }
     last(r, u, line);
   }
   LAPS_D static void finish_w(cplx (&r)[8], int u, cplx* __restrict__ line, cplx w1, cplx w2) {

@@ -72,8 +72,8 @@ k_fwd_x(const double* __restrict__ in, size_t in_fstride, cplx* __restrict__ W1,
   for (int e = 0; e < 8; ++e) r[e] = mk(ra[u + e * G::NT], rb[u + e * G::NT]);
   cplx* line = sm + l * T::PITCH;
   F::first(r, u, line, tw);
-  F::finish(r, u, line, tw);
-  __syncthreads();  // everyone has consumed its last-stage slots
+  F::template finish_g<TL>(r, u, line, tw, 1 + l);   // a line's transform synchronises its own N/8 threads only
+  group_barrier<G::NT, TL>(1 + l);          // everyone has consumed its last-stage slots
   LAPS_UNROLL
   for (int e = 0; e < 8; ++e) line[G::pad(F::kout(u, e))] = r[e];
   __syncthreads();
@@ -190,7 +190,7 @@ struct RealDst { double* ptr[16]; };
 
 template <int N, int TL>
 __global__ void __launch_bounds__(Tile<N, TL>::NTHREADS, Tile<N, TL>::MINB)
-k_inv_x(const cplx* __restrict__ V2, RealDst dst, int nzl, int ny, const cplx* __restrict__ tw, int nkx) {
+k_inv_x(const cplx* __restrict__ V2, const LAPS_GRID_CONSTANT RealDst dst, int nzl, int ny, const cplx* __restrict__ tw, int nkx) {
   typedef Geom<N> G;
   typedef Fft<N, +1> F;
   typedef Tile<N, TL> T;
@@ -233,7 +233,7 @@ k_inv_x(const cplx* __restrict__ V2, RealDst dst, int nzl, int ny, const cplx* _
   LAPS_UNROLL
   for (int e = 0; e < 8; ++e) r[e] = line[G::pad(u + e * G::NT)];
   F::first(r, u, line, tw);
-  F::finish(r, u, line, tw);
+  F::template finish_g<TL>(r, u, line, tw, 1 + l);   // a line's transform synchronises its own N/8 threads only
   double* oa = dst.ptr[g] + ((size_t)zl * ny + y0 + 2 * l) * N;
   double* ob = oa + N;
   LAPS_UNROLL

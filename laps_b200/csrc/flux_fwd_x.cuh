@@ -10,6 +10,8 @@
 //   phase 1  GR thread groups of N/8 threads each take one flux per round: form it at the 16 points
 //            the group's transform needs (8 per line), transform, split the two half spectra and
 //            store the (y, y+1) pair of every kx as one 32-byte access into W1 [f][kx][zl][y].
+//            A group synchronises only with itself (named barriers), so groups overlap each other's
+//            transform, split and store phases.
 // Adjacent CTAs (y fastest) complete each 128-byte line of W1 within microseconds, so the L2 merges
 // the sectors before they are written back.
 #pragma once
@@ -37,7 +39,7 @@ struct FTile {
   typedef Geom<N> G;
   static constexpr int PITCH = G::pitch(1);
   static constexpr int NTHREADS = GR * G::NT;
-  static constexpr int NIN = 12;   // rho | di/rho, mx, my, mz, Bx, By, Bz, e, ux, uy, uz, p
+  static constexpr int NIN = 15;   // rho | di/rho, mx, my, mz, Bx, By, Bz, e, ux, uy, uz, p, Jx, Jy, Jz
   static constexpr size_t SMEM_IN = (size_t)NIN * 2 * N * sizeof(double);
   static constexpr size_t SMEM = SMEM_IN + (size_t)GR * PITCH * sizeof(cplx);
 };
@@ -64,6 +66,12 @@ k_flux_fwd_x(const FusedFluxParams P) {
     const double2 a = *reinterpret_cast<const double2*>(P.uu + (size_t)v * P.npts + row + o);
     *reinterpret_cast<double2*>(in + v * L2N + o) = a;
   }
+  if (P.hall)
+    for (int i = tid * 2; i < 3 * L2N; i += T::NTHREADS * 2) {
+      const int v = i / L2N, o = i % L2N;
+      const double2 a = *reinterpret_cast<const double2*>(P.J + (size_t)v * P.npts + row + o);
+      *reinterpret_cast<double2*>(in + (12 + v) * L2N + o) = a;
+    }
   __syncthreads();
   const double gm1 = P.gamma - 1.0;
   for (int i = tid; i < L2N; i += T::NTHREADS) {
@@ -124,7 +132,7 @@ k_flux_fwd_x(const FusedFluxParams P) {
           const int x = h * N + u + e * G::NT;
           double v = u2[x] * b1[x] - u1[x] * b2[x];
           if (P.hall) {
-            const double j1 = P.J[(size_t)c1 * P.npts + row + x], j2 = P.J[(size_t)c2 * P.npts + row + x];
+            const double j1 = in[(12 + c1) * L2N + x], j2 = in[(12 + c2) * L2N + x];
             v = v + in[x] * (j1 * b2[x] - j2 * b1[x]);
           }
           o[h] = v;
@@ -162,12 +170,13 @@ k_flux_fwd_x(const FusedFluxParams P) {
         r[e] = mk(o[0], o[1]);
       }
     }
+    // from here on only the group's own threads touch its work line: group barriers, the groups drift freely
     F::first(r, u, line, P.tw);
-    F::finish(r, u, line, P.tw);
-    __syncthreads();  // everyone has consumed its last-stage slots
+    F::template finish_g<GR>(r, u, line, P.tw, 1 + g);
+    group_barrier<G::NT, GR>(1 + g);  // everyone has consumed its last-stage slots
     LAPS_UNROLL
     for (int e = 0; e < 8; ++e) line[G::pad(F::kout(u, e))] = r[e];
-    __syncthreads();
+    group_barrier<G::NT, GR>(1 + g);
     if (live) {       // split Z = A + iB into the half spectra of the two lines; (a, b) = W1[..][y0], W1[..][y0+1]
       const double hs = 0.5 * P.scale;
       for (int k = u; k < P.nkx; k += G::NT) {
@@ -178,7 +187,7 @@ k_flux_fwd_x(const FusedFluxParams P) {
         st256(P.W1 + (((size_t)f * nxh + k) * P.nzl + zl) * P.ny + y0, a, b);
       }
     }
-    __syncthreads();  // the work lines are refilled by the next round
+    group_barrier<G::NT, GR>(1 + g);  // the work line is refilled by the next round
   }
 }
 

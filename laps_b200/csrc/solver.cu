@@ -124,7 +124,11 @@ struct laps_solver {
   bool spectrum_full = true;   // the state still holds masked columns (fresh from laps_set_primitive)
   int slot[19];        // field slot of each flux (F1..F18, expand_term), < 0: not transformed
   int tune_cgz = 0, tune_z = 3, tune_rhs = 1, tune_rcg = 0;
-  int tune_fusex = -1;   // calc_flux fused into the forward x pass: -1 = where it pays (128 <= nx <= 512), 0 = never, 1 = whenever possible
+  // The three mass fluxes are the momentum itself: their spectra are taken from the state (kZMass) instead of
+  // being re-transformed.  Off with dealias_option 0, where the state keeps non-Hermitian Nyquist content that
+  // the reference's real-space round trip would drop.
+  bool mass_from_state = false;
+  int tune_fusex = -1;   // calc_flux fused into the forward x pass (LAPS_TUNE_FUSEX): -1 = library default, 0 = never, 1 = whenever possible (nx <= 512)
   int num_sms = 148;
   double da_thresh = 0;
   void* ipc_opened[LAPS_MAX_RANKS][3];   // mappings obtained with cudaIpcOpenMemHandle
@@ -409,7 +413,7 @@ int flux_fwd_x(S* s, const FusedFluxParams& fp) { LAPS_DISPATCH(s->nx, do_flux_f
 bool use_fused_flux(const S* s) {
   if (s->two_d || s->incomp || s->nx > 512 || (s->ny & 1)) return false;
   if (s->tune_fusex >= 0) return s->tune_fusex != 0;
-  return s->nx >= 128;
+  return false;   // measured on B200 (profiles/r01c): 19 ms per stage against 12 ms for k_flux + k_fwd_x; opt-in until it wins
 }
 int inv_y(S* s, const cplx* V1, cplx* V2, int nfields, bool prune) { LAPS_DISPATCH(s->ny, do_inv_y, s, V1, V2, nfields, prune) }
 
@@ -475,15 +479,28 @@ ZTask rhs_task(int v, int gout, int fa, double ca, int fb, double cb, int fx, do
   return t;
 }
 
-int launch_current_tasks(S* s, const cplx* u, bool prune) {  // J^ = i k x B^, inverse z  (mhdrhs.f90:296-339)
+// J^ = i k x B^ from the state `u`, inverse z (mhdrhs.f90:296-339); with irk >= 0 also the continuity row of
+// stage irk (kZMass: reads the stage's input state u_A, writes u_B(1), fnl_rk(1) and the inverse-z output).
+int launch_current_tasks(S* s, const cplx* u, bool prune, bool want_j = true, int irk = -1) {
   ZParams z; fill_zparams(s, z, prune);
   z.u_in = u;
-  for (int j = 0; j < 3; ++j) {
+  int n = 0;
+  if (want_j)
+    for (int j = 0; j < 3; ++j) {
+      ZTask t; std::memset(&t, 0, sizeof(t));
+      t.kind = kZCurrent; t.jcomp = j; t.gout = 8 + j; t.fa = t.fb = t.fx = t.fc = -1;
+      z.task[n++] = t;
+    }
+  if (irk >= 0) {
+    z.u_old = s->uA; z.u_out = s->uB;
+    z.cc = s->cc1[irk]; z.dd = s->dd1[irk]; z.dt_irk = s->tstep[irk];
+    z.read_rk = (irk > 0); z.write_rk = (irk < 2);
     ZTask t; std::memset(&t, 0, sizeof(t));
-    t.kind = kZCurrent; t.jcomp = j; t.gout = 8 + j; t.fa = t.fb = t.fx = t.fc = -1;
-    z.task[j] = t;
+    t.kind = kZMass; t.v = 0; t.gout = 0; t.aeb_c = 2.0; t.fa = t.fb = t.fx = t.fc = -1;
+    z.task[n++] = t;
   }
-  return spec_z(s, z, 3, "curl_b_inv_z");
+  if (n == 0) return 0;
+  return spec_z(s, z, n, "curl_b_inv_z");
 }
 
 // Every rank has finished the passes enqueued so far (stands where the reference's blocking
@@ -669,14 +686,16 @@ int stage(S* s, int irk) {
         for (int v = 0; v < 8; ++v) z.task[v].aeb_c = c2[v];
       }
     }
-    if (s->tune_rhs) LAPS_TRY(rhs_z(s, z, 8));
-    else LAPS_TRY(spec_z(s, z, 8, "spec_z"));
+    const int t0 = s->mass_from_state ? 1 : 0;   // the continuity row is a kZMass task of the launch below
+    if (t0) for (int v = 1; v < 8; ++v) z.task[v - 1] = z.task[v];
+    if (s->tune_rhs) LAPS_TRY(rhs_z(s, z, 8 - t0));
+    else LAPS_TRY(spec_z(s, z, 8 - t0, "spec_z"));
   }
   // J for the next stage's calc_flux.  After the last stage of a step in the expanding box the
   // driver moves the radius (evolve_radius, mhd.f90:248) and with it the wave vectors J is built
   // from (mhdrhs.f90:313-326), so that J would be discarded: leave it to refresh_current.
   const bool want_j = p.if_hall && !(irk == 2 && s->Ur != 0.0);
-  if (want_j) LAPS_TRY(launch_current_tasks(s, s->uB, true));
+  LAPS_TRY(launch_current_tasks(s, s->uB, true, want_j, s->mass_from_state ? irk : -1));
   LAPS_TRY(host_barrier(s));
   LAPS_TRY(inverse_yx(s, 0, want_j ? 11 : 8, true));
   if (s->spectrum_full) {
@@ -777,11 +796,13 @@ int laps_create(const laps_params* params, laps_handle* out) {
   s->csz = s->ncol * s->nz;
   s->w1sz = (size_t)s->nxh * s->nzl * s->ny;
   s->xz = two_d ? 1 : s->nzl; s->xy = two_d ? s->nzl : s->ny;
+  s->mass_from_state = !s->incomp && p.dealias_option != 0;
+  if (const char* e = std::getenv("LAPS_TUNE_MASS")) s->mass_from_state = !s->incomp && std::atoi(e) != 0;
   {  // field slots of the fluxes; the 2D tree never uses the z fluxes F3,F6,F9,F12,F18 (kz = 0)
     int n = 0;
     for (int j = 0; j < 19; ++j) {
       const bool zflux = (j == 2 || j == 5 || j == 8 || j == 11 || j == 17);
-      const bool on = j == 18 ? (p.if_AEB != 0) : !(two_d && zflux);
+      const bool on = j == 18 ? (p.if_AEB != 0) : !(two_d && zflux) && !(s->mass_from_state && j < 3);
       s->slot[j] = on ? n++ : -1;
     }
     s->nf = n;
@@ -1070,6 +1091,13 @@ int laps_get_pruning(laps_handle s, int32_t* nkx, int32_t* kymax, int32_t* nky_l
   if (nkx) *nkx = s->nkx;
   if (kymax) *kymax = s->kymax;
   if (nky_local) *nky_local = s->pr_nkyl;
+  return 0;
+}
+
+int laps_get_field_counts(laps_handle s, int32_t* nf, int32_t* ni) {
+  if (!s) return 1;
+  if (nf) *nf = s->nf;
+  if (ni) *ni = s->ni;
   return 0;
 }
 

@@ -20,7 +20,10 @@ namespace laps {
 enum ZKind { kZRhs = 0, kZForwardOnly = 1, kZInverseOnly = 2, kZCurrent = 3,
              // incompressible tree (src_incompressible/mhdrhs.f90):
              kZGrad = 4,   // i k_a u^[v] / cx, a = jcomp   (calc_gradient_velocity_real, :308-390)
-             kZDiv = 5 };  // i (kx u^[v] + ky u^[v+1] + kz u^[v+2]) / cx   (calc_divB_real / calc_divV_real, :536-647)
+             kZDiv = 5,
+             // fnl(1) = -i k . (rho u)^ taken from the spectral state itself: calc_flux sets flux(1:3) = uu(2:4)
+             // (mhdrhs.f90:58-60), whose transform (mhdrhs.f90:128-172) is uu_fourier(2:4) again — no transform needed
+             kZMass = 6 };  // i (kx u^[v] + ky u^[v+1] + kz u^[v+2]) / cx   (calc_divB_real / calc_divV_real, :536-647)
 
 // One row of work (blockIdx.y).  For kZRhs:
 //   G = ca*(i kx)*W2[fa] + cb*(i ky)*W2[fb] + cx*W2[fx]      (missing terms have index < 0)
@@ -41,6 +44,7 @@ struct ZParams {
   const cplx* W2;        // [f][col][z]
   size_t fstride;        // ncol * nz
   const cplx* u_in;      // [v][col][kz]
+  const cplx* u_old;     // kZMass: the state at the start of the stage (u_in then points at the updated one)
   cplx* u_out;
   cplx* fnl_rk;
   PeerTable V1;          // [g][kx][ky][zl] on the owner of z
@@ -295,6 +299,46 @@ k_spec_z(const ZParams P) {
     const size_t voff = (size_t)K.v * P.fstride + coff;
     LAPS_UNROLL
     for (int e = 0; e < 8; ++e) r[e] = live ? P.u_in[voff + u + e * G::NT] : mk(0.0, 0.0);
+  } else if (K.kind == kZMass) {
+    // continuity row (mhdrhs.f90:207-209,235-237), rkt, dealias — in the INPUT order of the inverse transform
+    const cplx* M = P.u_old + P.fstride + coff;
+    const size_t voff = coff;   // v = 0
+    const double ca = P.aeb ? K.aeb_c / P.tau : 0.0;
+    const double dxy = (P.dealias_option == 1 || P.dealias_option == 3) ? __dadd_rn(__ldg(P.dax + kx), __ldg(P.day + ky))
+                                               : ((P.dealias_option == 2) ? __ldg(P.dax + kx) : 0.0);
+    const double dfy = (P.dealias_option == 2) ? __ldg(P.day + ky) : 0.0;
+    LAPS_UNROLL
+    for (int e = 0; e < 8; ++e) {
+      const int kz = u + e * G::NT;
+      const double kzz = __ldg(P.kze + kz);
+      const double ry = P.mode2d ? kzz : kye, rz = P.mode2d ? 0.0 : kzz;
+      const cplx m1 = live ? M[kz] : mk(0.0, 0.0);
+      const cplx m2 = live ? M[P.fstride + kz] : mk(0.0, 0.0);
+      const cplx m3 = live ? M[2 * P.fstride + kz] : mk(0.0, 0.0);
+      const cplx sum = cadd(cadd(cmul_i(m1, kxe), cmul_i(m2, ry)), cmul_i(m3, rz));
+      cplx fnl = mk(-sum.x, -sum.y);
+      const cplx uo = live ? P.u_old[voff + kz] : mk(0.0, 0.0);
+      fnl.x -= ca * uo.x;
+      fnl.y -= ca * uo.y;
+      cplx un;
+      if (P.read_rk) {
+        const cplx fr = live ? P.fnl_rk[voff + kz] : mk(0.0, 0.0);
+        un = mk((P.cc * fnl.x + P.dd * fr.x) + uo.x, (P.cc * fnl.y + P.dd * fr.y) + uo.y);
+      } else {
+        un = mk(P.cc * fnl.x + uo.x, P.cc * fnl.y + uo.y);
+      }
+      if (P.write_rk && live) P.fnl_rk[voff + kz] = fnl;
+      if (P.dealias_option == 1) {
+        if (__dadd_rn(dxy, __ldg(P.daz + kz)) >= P.da_thresh) un = mk(0.0, 0.0);
+      } else if (P.dealias_option == 2) {
+        const double fz = __ldg(P.daz + kz);
+        un = mk(__dmul_rn(__dmul_rn(__dmul_rn(un.x, dxy), dfy), fz), __dmul_rn(__dmul_rn(__dmul_rn(un.y, dxy), dfy), fz));
+      } else if (P.dealias_option == 3) {
+        if (dxy != 0.0 || __ldg(P.daz + kz) != 0.0) un = mk(0.0, 0.0);
+      }
+      if (live) P.u_out[voff + kz] = un;
+      r[e] = un;
+    }
   } else if (K.kind == kZGrad) {
     const cplx* U = P.u_in + (size_t)K.v * P.fstride + coff;
     LAPS_UNROLL

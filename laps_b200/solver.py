@@ -208,6 +208,12 @@ class Solver:
         self._ck(self._lib.laps_get_pruning(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def field_counts(self):
+        """(nf, ni): fields transformed forward / inverse per RK stage (laps_get_field_counts)."""
+        a, b = C.c_int32(), C.c_int32()
+        self._ck(self._lib.laps_get_field_counts(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def set_profiling(self, on: bool):
         self._ck(self._lib.laps_set_profiling(self._h, 1 if on else 0))
 
