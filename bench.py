@@ -299,10 +299,11 @@ def run_gpu(args):
     # ---------------- roofline of the dominant kernel ----------------
     R = 8.0 * n * n * g.nzl
     C = 16.0 * g.nxh * g.nyl * n
-    (nf, ni), hall = g.field_counts(), bool(kw["if_hall"])
+    nf, ni, rows = g.field_counts()
+    hall = bool(kw["if_hall"])
     nkx, kymax, nkyl = g.pruning()
     fx, fy, fyl = nkx / g.nxh, min(1.0, (2 * kymax + 1) / n), nkyl / g.nyl
-    mass = nf < 18
+    mass = rows < 8
     kb = lambda k: kernel_bytes(k, R, C, nf, ni, hall, fx, fy, fyl, mass)  # noqa: E731
     peak, peak_src = peaks()
     top = max(prof.items(), key=lambda kv: kv[1][0]) if prof else None

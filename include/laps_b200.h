@@ -53,8 +53,8 @@ typedef struct laps_params {
   int32_t if_z_radial;
   int32_t if_limit_dt_increase;
   /* Incompressible tree (src_incompressible/, 3D): incompressible = 1 runs evolve of
-   * src_incompressible/mhd.f90:298-354 — J and grad u (12 inverse transforms), the pressure projection
-   * (mhdrhs.f90:392-523), E = -u x B (+ Hall), calc_rhs (:118-236), update_rho_p — and vardt of :356-457.
+   * src_incompressible/mhd.f90:318-367 — J and grad u (12 inverse transforms), the pressure projection
+   * (mhdrhs.f90:393-518), E = -u x B (+ Hall), calc_rhs (:117-232), update_rho_p — and vardt of :356-457.
    * uu(8) is the PRESSURE in this tree (mhdinit.f90:210) and uu_prim has the velocity only.
    * rho0: the namelist background density (mhdinit.f90:15) that calc_gradient_velocity_real divides by. */
   int32_t incompressible;
@@ -117,10 +117,10 @@ int laps_get_stream(laps_handle h, void** stream_out);
 
 /* calc_max_divB (mhd.f90:157,522-570). */
 int laps_max_divb(laps_handle h, double* out);
-/* Incompressible tree: calc_max_divV (src_incompressible/mhd.f90:616-664), max |k.(rho u)^| / rho0. */
+/* Incompressible tree: calc_max_divV (src_incompressible/mhd.f90:620-668), max |k.(rho u)^| / rho0. */
 int laps_max_divv(laps_handle h, double* out);
 /* calc_divB_real + calc_max_divB_real and calc_divV_real + calc_max_divV_real
- * (src_incompressible/mhdrhs.f90:536-647, mhd.f90:668-731), the pair the incompressible driver prints at
+ * (src_incompressible/mhdrhs.f90:532-648, mhd.f90:672-732), the pair the incompressible driver prints at
  * dtrms cadence: out[0] = max |div B|, out[1] = max |div (rho u)| / rho0, both in REAL space. */
 int laps_max_div_real(laps_handle h, double out[2]);
 /* Current rho0 (update_rho_p compounds it after every evolve in the expanding box, AEBmod.f90:123-134). */
@@ -157,10 +157,15 @@ int laps_transpose_yz_indexmap(laps_handle h, int64_t* out);
 int laps_get_pruning(laps_handle h, int32_t* nkx, int32_t* kymax, int32_t* nky_local);
 
 /* Fields transformed per RK stage: *nf forward (real fluxes -> spectra), *ni inverse (state + current density).
- * The reference transforms 18 (+1 with the expanding box) and 8 (+3 with the Hall term); here the three
- * mass fluxes are not transformed when dealiasing is on — calc_flux sets them to uu(2:4) (mhdrhs.f90:58-60),
- * whose spectrum is the state itself — and the 2D tree drops the z fluxes (kz = 0). */
-int laps_get_field_counts(laps_handle h, int32_t* nf, int32_t* ni);
+ * The reference transforms 18 (+1 with the expanding box) and 8 (+3 with the Hall term).  Here
+ *  - the three mass fluxes are not transformed when dealiasing is on: calc_flux sets them to uu(2:4)
+ *    (mhdrhs.f90:58-60), whose spectrum is the state itself;
+ *  - the momentum flux tensor is symmetric, so F7, F10, F11 (mhdrhs.f90:69,74,75) read the spectra of their
+ *    transposes F5, F6, F9 (:64,65,70);
+ *  - the 2D tree drops the z fluxes (kz = 0).
+ * 13 and 11 for 3D Hall-MHD in the expanding box.  *spec_rows = state rows updated by the main z-pass launch
+ * (the continuity row runs with the current-density tasks when its fluxes come from the state). */
+int laps_get_field_counts(laps_handle h, int32_t* nf, int32_t* ni, int32_t* spec_rows);
 
 /* Device-time of the last laps_evolve/laps_step in milliseconds (CUDA events on the compute
  * stream), and the number of kernel launches it issued. */

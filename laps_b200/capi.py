@@ -113,7 +113,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.laps_transpose_yz_indexmap.argtypes = [H, C.POINTER(C.c_int64)]
     lib.laps_last_step_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     lib.laps_get_pruning.argtypes = [H, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
-    lib.laps_get_field_counts.argtypes = [H, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.laps_get_field_counts.argtypes = [H, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.laps_set_profiling.argtypes = [H, C.c_int32]
     lib.laps_get_profile.argtypes = [H, C.c_char_p, C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_int32)]
     for name in SYMBOLS:

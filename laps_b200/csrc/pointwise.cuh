@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(256) k_prim_to_cons(double* uu, size_t n, doub
 }
 
 // prim[4][n] = (ux,uy,uz,p) from conserved uu
-// (incompressible tree: uu_prim has the velocity only, src_incompressible/mhdrhs.f90:239-246; the 4th
+// (incompressible tree: uu_prim has the velocity only, src_incompressible/mhdrhs.f90:235-242; the 4th
 // row returns the pressure uu(8))
 __global__ void __launch_bounds__(256) k_cons_to_prim(const double* uu, double* prim, size_t n, double gamma, int incomp) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) k_reduce_final(const double* partial, int
 // mhdrms.f90:73-93: sums and sums of squares of (rho,u,B,p), plus sum(e) and sum(u.B) (invariants).
 // partial layout [18][gridDim.x]
 // Incompressible tree: entry 8 is the pressure uu(8) (the reference reads the non-existent uu_prim(:,:,:,4),
-// src_incompressible/mhdrms.f90:72) and the energy invariant is (rho u^2 + B^2)/2.
+// src_incompressible/mhdrms.f90:73,83) and the energy invariant is (rho u^2 + B^2)/2.
 __global__ void __launch_bounds__(256) k_moments1(const double* uu, size_t n, double gamma, double* partial, int incomp) {
   __shared__ double scratch[32];
   double s[18];
@@ -250,7 +250,7 @@ struct DivbParams {
   const double* kxr; const double* kyr; const double* kze;
   double radius0, radius, cosa, sina; int corot_k;
   int mode2d, z_radial;   // 2D tree: the line axis carries ky, kz = 0 (2D/mhd.f90:527-550)
-  int v0;                 // first component of the vector: 4 = B (calc_max_divB), 1 = rho u (calc_max_divV, src_incompressible/mhd.f90:616-664)
+  int v0;                 // first component of the vector: 4 = B (calc_max_divB), 1 = rho u (calc_max_divV, src_incompressible/mhd.f90:620-668)
   double* partial;
 };
 __global__ void __launch_bounds__(256) k_divb(const DivbParams P) {
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256) k_divb(const DivbParams P) {
 }
 
 // ------------------------------------------------------------------ incompressible tree (src_incompressible/)
-// calc_flux_for_pressure (mhdrhs.f90:392-441) and calc_flux (mhdrhs.f90:26-85) in one sweep: both are
+// calc_flux_for_pressure (mhdrhs.f90:393-437) and calc_flux (mhdrhs.f90:25-84) in one sweep: both are
 // functions of the same real fields.  F slots 0-2: Fp = -(rho u . grad) u + J x B ; 3-5: E = -u x B (+ Hall).
 struct FluxIncParams {
   const double* uu;     // [8][npts]  rho, rho u, B, p
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(256) k_flux_incomp(const FluxIncParams P) {
     F[0] = -mx * g[0] - my * g[1] - mz * g[2] + Jy * Bz - Jz * By;
     F[n] = -mx * g[3] - my * g[4] - mz * g[5] + Jz * Bx - Jx * Bz;
     F[2 * n] = -mx * g[6] - my * g[7] - mz * g[8] + Jx * By - Jy * Bx;
-    const double ux = mx / rho, uy = my / rho, uz = mz / rho;   // uu_prim (mhdrhs.f90:239-246)
+    const double ux = mx / rho, uy = my / rho, uz = mz / rho;   // uu_prim (mhdrhs.f90:235-242)
     double Ex = uz * By - uy * Bz;
     double Ey = ux * Bz - uz * Bx;
     double Ez = uy * Bx - ux * By;
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(256) k_flux_incomp(const FluxIncParams P) {
   }
 }
 
-// vardt of the incompressible tree (src_incompressible/mhd.f90:356-457): Alfven and flow speeds only.
+// vardt of the incompressible tree (src_incompressible/mhd.f90:369-476): Alfven and flow speeds only.
 // Same reduction as k_cfl: the three maxima of the signal speeds (division is monotonic).
 __global__ void __launch_bounds__(256) k_cfl_incomp(const CflParams P) {
   __shared__ double scratch[32];
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(256) k_cfl_incomp(const CflParams P) {
   }
 }
 
-// max |f| over nfields real fields (calc_max_divB_real / calc_max_divV_real, src_incompressible/mhd.f90:668-731);
+// max |f| over nfields real fields (calc_max_divB_real / calc_max_divV_real, src_incompressible/mhd.f90:672-732);
 // partial layout [nfields][gridDim.x]
 __global__ void __launch_bounds__(256) k_absmax(const double* f, size_t n, int nfields, double* partial) {
   __shared__ double scratch[32];

@@ -73,7 +73,7 @@ struct laps_solver {
   double rho0 = 1.0;     // namelist background density (mhdinit.f90:15), compounded by update_rho_p (AEBmod.f90:123-134)
   double p0 = 1.0;
   double* G = nullptr;   // [9][npts] grad u (incompressible)
-  bool retransform = false;   // re-derive the spectrum from the real fields at the start of every stage (mhd.f90:305)
+  bool retransform = false;   // re-derive the spectrum from the real fields at the start of every stage (mhd.f90:325)
   int xz = 0, xy = 0;  // line counts (planes, lines per plane) the x passes run over
   int nx, ny, nz, nxh, P, rank;
   int zoffs[LAPS_MAX_RANKS], zlens[LAPS_MAX_RANKS], yoffs[LAPS_MAX_RANKS], ylens[LAPS_MAX_RANKS];
@@ -122,7 +122,14 @@ struct laps_solver {
   int nkx = 0, kymax = 0, tune_prune = 1;
   int pr_nkyl = 0, pr_nA = 0, pr_a0 = 0, pr_b0 = 0;   // this rank's surviving ky rows (see ZParams)
   bool spectrum_full = true;   // the state still holds masked columns (fresh from laps_set_primitive)
-  int slot[19];        // field slot of each flux (F1..F18, expand_term), < 0: not transformed
+  int slot[19];        // field slot the z pass reads each flux from (F1..F18, expand_term), < 0: not transformed
+  int fslot[19];       // field slot calc_flux stores each flux to, < 0: not stored (differs from slot[] for the
+                       // off-diagonal momentum fluxes that share the slot of their transpose, see sym_tensor)
+  // The momentum flux tensor rho u_i u_j - B_i B_j + ptot delta_ij is symmetric: calc_flux forms both
+  // rho u_y * u_x (mhdrhs.f90:64) and rho u_x * u_y (:69) and the reference transforms both.  Here the
+  // transposed entries F7, F10, F11 read the spectrum of F5, F6, F9: 3 forward transforms fewer per stage,
+  // equal to the reference up to the rounding of (m_y/rho) m_x against (m_x/rho) m_y.
+  bool sym_tensor = true;
   int tune_cgz = 0, tune_z = 3, tune_rhs = 1, tune_rcg = 0;
   // The three mass fluxes are the momentum itself: their spectra are taken from the state (kZMass) instead of
   // being re-transformed.  Off with dealias_option 0, where the state keeps non-Hermitian Nyquist content that
@@ -466,7 +473,7 @@ void fill_zparams(S* s, ZParams& z, bool prune = false) {
   z.da_thresh = s->da_thresh;
   z.mode2d = s->two_d; z.z_radial = s->two_d && p.if_AEB && p.if_z_radial; z.bg_all_kz = s->two_d;
   z.tune = s->tune_z;
-  z.aeb_p = 2.0 * p.adiabatic_index;   // src_incompressible/mhdrhs.f90:196-197
+  z.aeb_p = 2.0 * p.adiabatic_index;   // src_incompressible/mhdrhs.f90:202-203
 }
 
 ZTask rhs_task(int v, int gout, int fa, double ca, int fb, double cb, int fx, double cx, double sg, int fc, double sc) {
@@ -566,12 +573,12 @@ int spectrum_from_real(S* s, bool prune) {
   return host_barrier(s);
 }
 
-// One RK stage of the incompressible tree (src_incompressible/mhd.f90:303-350).
+// One RK stage of the incompressible tree (src_incompressible/mhd.f90:323-364).
 int stage_incomp(S* s, int irk) {
   const laps_params& p = s->p;
   const bool prune = !s->spectrum_full;
-  if (s->retransform) LAPS_TRY(spectrum_from_real(s, prune));            // mhd.f90:305
-  {  // calc_current_density_real + calc_gradient_velocity_real (mhdrhs.f90:248-390): 12 inverse transforms
+  if (s->retransform) LAPS_TRY(spectrum_from_real(s, prune));            // mhd.f90:325
+  {  // calc_current_density_real + calc_gradient_velocity_real (mhdrhs.f90:244-391): 12 inverse transforms
     ZParams z; fill_zparams(s, z, prune);
     z.u_in = s->uA;
     for (int j = 0; j < 3; ++j) {
@@ -589,7 +596,7 @@ int stage_incomp(S* s, int irk) {
     LAPS_TRY(host_barrier(s));
     LAPS_TRY(inverse_yx(s, 0, 12, prune, 8));   // V1 slots 0-11 -> J (3), grad u (9)
   }
-  {  // calc_flux_for_pressure + calc_flux (mhdrhs.f90:392-441, 26-85)
+  {  // calc_flux_for_pressure + calc_flux (mhdrhs.f90:393-437, 25-84)
     FluxIncParams f;
     f.uu = s->uu; f.J = s->J; f.G = s->G; f.F = buf_F(s); f.npts = s->npts;
     f.hall = p.if_hall; f.di = p.ion_inertial_length;
@@ -605,7 +612,7 @@ int stage_incomp(S* s, int irk) {
     z.read_rk = (irk > 0); z.write_rk = (irk < 2);
     // projection rows: rho u, p, rho (slots 0-2 = Fp)
     LAPS_TRY(incomp_z(s, z));
-    // dB/dt = curl E (mhdrhs.f90:168-174), slots 3-5 = E
+    // dB/dt = curl E (mhdrhs.f90:175-181), slots 3-5 = E
     z.task[0] = rhs_task(4, 4, -1, 0.0, 5, 1.0, -1, 0.0, -1.0, 4, +1.0);
     z.task[1] = rhs_task(5, 5, 5, 1.0, -1, 0.0, -1, 0.0, +1.0, 3, -1.0);
     z.task[2] = rhs_task(6, 6, 4, -1.0, 3, 1.0, -1, 0.0, +1.0, -1, 0.0);
@@ -633,7 +640,7 @@ int stage(S* s, int irk) {
     fp.nzl = s->nzl; fp.ny = s->ny; fp.nkx = s->nkx; fp.tw = s->tw_x; fp.scale = 1.0 / s->nx;
     fp.hall = p.if_hall; fp.aeb = p.if_AEB; fp.gamma = p.adiabatic_index; fp.di = p.ion_inertial_length; fp.tau = s->tau;
     fp.nflux = s->nf;
-    for (int j = 0; j < 19; ++j) if (s->slot[j] >= 0) fp.id[s->slot[j]] = j;
+    for (int j = 0; j < 19; ++j) if (s->fslot[j] >= 0) fp.id[s->fslot[j]] = j;
     LAPS_TRY(flux_fwd_x(s, fp));
     LAPS_TRY(fwd_y(s, buf_W1(s), s->nf, true));
   } else {
@@ -642,7 +649,7 @@ int stage(S* s, int irk) {
     f.uu = s->uu; f.J = s->J; f.F = buf_F(s); f.npts = s->npts;
     f.hall = p.if_hall; f.aeb = p.if_AEB; f.gamma = p.adiabatic_index; f.di = p.ion_inertial_length; f.tau = s->tau;
     f.z_radial = s->two_d && p.if_z_radial;
-    for (int j = 0; j < 19; ++j) f.slot[j] = s->slot[j];
+    for (int j = 0; j < 19; ++j) f.slot[j] = s->fslot[j];
     LaunchScope ls(s, "flux");
     LAPS_LAUNCH(k_flux, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, f);
     LAPS_TRY(check_launch(s, "k_flux"));
@@ -798,12 +805,16 @@ int laps_create(const laps_params* params, laps_handle* out) {
   s->xz = two_d ? 1 : s->nzl; s->xy = two_d ? s->nzl : s->ny;
   s->mass_from_state = !s->incomp && p.dealias_option != 0;
   if (const char* e = std::getenv("LAPS_TUNE_MASS")) s->mass_from_state = !s->incomp && std::atoi(e) != 0;
+  if (const char* e = std::getenv("LAPS_TUNE_SYM")) s->sym_tensor = std::atoi(e) != 0;
   {  // field slots of the fluxes; the 2D tree never uses the z fluxes F3,F6,F9,F12,F18 (kz = 0)
     int n = 0;
     for (int j = 0; j < 19; ++j) {
       const bool zflux = (j == 2 || j == 5 || j == 8 || j == 11 || j == 17);
       const bool on = j == 18 ? (p.if_AEB != 0) : !(two_d && zflux) && !(s->mass_from_state && j < 3);
       s->slot[j] = on ? n++ : -1;
+      s->fslot[j] = s->slot[j];
+      const int twin = j == 6 ? 4 : (j == 9 ? 5 : (j == 10 ? 8 : -1));   // (row, dir) -> (dir, row)
+      if (on && s->sym_tensor && twin >= 0 && s->slot[twin] >= 0) { s->slot[j] = s->slot[twin]; s->fslot[j] = -1; --n; }
     }
     s->nf = n;
   }
@@ -823,7 +834,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
   if (const char* e = std::getenv("LAPS_TUNE_Z")) s->tune_z = std::atoi(e);
   if (const char* e = std::getenv("LAPS_TUNE_FUSEX")) s->tune_fusex = std::atoi(e);
   // The reference re-derives uu_fourier from the real fields at the start of every stage
-  // (src_incompressible/mhd.f90:305).  For a spectrum the dealiasing has band-limited (options 1, 2: the
+  // (src_incompressible/mhd.f90:325).  For a spectrum the dealiasing has band-limited (options 1, 2: the
   // Nyquist planes are removed) that round trip is the identity up to round-off and is skipped; with
   // dealias_option 0 it projects out the non-Hermitian Nyquist content the derivatives create, so it is done.
   s->retransform = s->incomp && p.dealias_option == 0;
@@ -1025,7 +1036,7 @@ int laps_vardt(laps_handle s, double* dt_inout) {  // mhd.f90:328-429
   c.hall = p.if_hall; c.partial = s->d_partial;
   {
     LaunchScope ls(s, "cfl");
-    if (s->incomp) LAPS_LAUNCH(k_cfl_incomp, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, c);   // src_incompressible/mhd.f90:356-457
+    if (s->incomp) LAPS_LAUNCH(k_cfl_incomp, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, c);   // src_incompressible/mhd.f90:369-476
     else LAPS_LAUNCH(k_cfl, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, c);
     LAPS_TRY(check_launch(s, "k_cfl"));
   }
@@ -1061,7 +1072,7 @@ int laps_evolve(laps_handle s) {  // mhd.f90:298-326
   LAPS_CK(s, cudaEventRecord(s->ev0, s->stream));
   for (int irk = 0; irk < 3; ++irk) LAPS_TRY(stage(s, irk));
   LAPS_CK(s, cudaEventRecord(s->ev1, s->stream));
-  if (s->incomp) {  // update_rho_p (src_incompressible/mhd.f90:353, AEBmod.f90:123-134): compounds with the CURRENT radius
+  if (s->incomp) {  // update_rho_p (src_incompressible/mhd.f90:366, AEBmod.f90:123-134): compounds with the CURRENT radius
     const double q = s->p.radius0 / s->radius;
     s->rho0 = s->rho0 * std::pow(q, 2);
     s->p0 = s->p0 * std::pow(q, 2 * s->p.adiabatic_index);
@@ -1094,10 +1105,11 @@ int laps_get_pruning(laps_handle s, int32_t* nkx, int32_t* kymax, int32_t* nky_l
   return 0;
 }
 
-int laps_get_field_counts(laps_handle s, int32_t* nf, int32_t* ni) {
+int laps_get_field_counts(laps_handle s, int32_t* nf, int32_t* ni, int32_t* spec_rows) {
   if (!s) return 1;
   if (nf) *nf = s->nf;
   if (ni) *ni = s->ni;
+  if (spec_rows) *spec_rows = s->incomp ? 3 : (s->mass_from_state ? 7 : 8);
   return 0;
 }
 
@@ -1142,7 +1154,7 @@ int laps_max_divb(laps_handle s, double* out) {  // mhd.f90:522-570
   return max_div_fourier(s, 4, out);
 }
 
-int laps_max_divv(laps_handle s, double* out) {  // src_incompressible/mhd.f90:616-664: max |k . (rho u)^| / rho0
+int laps_max_divv(laps_handle s, double* out) {  // src_incompressible/mhd.f90:620-668: max |k . (rho u)^| / rho0
   if (!s || !out) return 1;
   LAPS_TRY(require_state(s));
   LAPS_TRY(max_div_fourier(s, 1, out));
@@ -1151,7 +1163,7 @@ int laps_max_divv(laps_handle s, double* out) {  // src_incompressible/mhd.f90:6
 }
 
 // calc_divB_real + calc_max_divB_real, calc_divV_real + calc_max_divV_real
-// (src_incompressible/mhdrhs.f90:536-647, mhd.f90:668-731): maxima of |div B| and |div (rho u)/rho0| in REAL space.
+// (src_incompressible/mhdrhs.f90:532-648, mhd.f90:672-732): maxima of |div B| and |div (rho u)/rho0| in REAL space.
 int laps_max_div_real(laps_handle s, double out[2]) {
   if (!s || !out) return 1;
   LAPS_TRY(require_state(s));

@@ -2,8 +2,8 @@
 // the pressure projection — rho u (3 components), the pressure, and rho — for one (kx,ky) column
 // at a time.  It replaces, without ever materialising flux_pressure_fourier, fnl or k_square:
 //   fftw.f90:173-179 (forward z lines of the three Fp fields, "/nz")
-//   mhdrhs.f90:471-523 calc_pressure_fourier     p^ = -(k . Fp^)/k^2        (0 where k^2 < 1e-10)
-//   mhdrhs.f90:118-236 calc_rhs                  fnl(2:4) = Fp^ + ((k . Fp^)/k^2) k, fnl(1) = fnl(8) = 0,
+//   mhdrhs.f90:468-518 calc_pressure_fourier     p^ = -(k . Fp^)/k^2        (0 where k^2 < 1e-10)
+//   mhdrhs.f90:117-232 calc_rhs                  fnl(2:4) = Fp^ + ((k . Fp^)/k^2) k, fnl(1) = fnl(8) = 0,
 //                                                expanding-box terms (fnl(8) uses the NEW p^), explicit viscosity
 //   rktmod.f90:34-62 rkt, dealiasing.f90:70-112 dealias, fftw.f90:195-201 (inverse z lines),
 //   parallel.f90:300-324 transpose_zy (stores go to the owner of each z)
@@ -54,7 +54,7 @@ k_incomp_z(const ZParams P) {
   cplx* S1 = S0 + N;
   cplx* S2 = S1 + N;
 
-  // derivative vectors (imaginary parts), mhdrhs.f90:135-148
+  // derivative vectors (imaginary parts), mhdrhs.f90:134-150
   const double kxr = __ldg(P.kxr + kx), kyr = __ldg(P.kyr + ky);
   double kxe = kxr, kye = __ddiv_rn(__dmul_rn(kyr, P.radius0), P.radius);
   if (P.corot_k) {
@@ -90,7 +90,7 @@ k_incomp_z(const ZParams P) {
     const double k2 = __dadd_rn(ksq_xy, __ldg(P.ksq_z + kz));
     const cplx f1 = S0[e * G::NT + u], f2 = S1[e * G::NT + u], f3 = cscale(r[e], P.scale);
     const cplx sum = cadd(cadd(cmul_i(f1, kxe), cmul_i(f2, kye)), cmul_i(f3, kzz));
-    if (k2 < 1e-10) {   // "background field, not important in Fourier space" (mhdrhs.f90:152-156,508-511)
+    if (k2 < 1e-10) {   // "background field, not important in Fourier space" (mhdrhs.f90:155-159,505-508)
       S0[e * G::NT + u] = mk(0.0, 0.0); S1[e * G::NT + u] = mk(0.0, 0.0); S2[e * G::NT + u] = mk(0.0, 0.0);
       r[e] = mk(0.0, 0.0);
     } else {
@@ -108,18 +108,18 @@ k_incomp_z(const ZParams P) {
     const int v = round == 0 ? 7 : (round == 4 ? 0 : round);
     const size_t voff = (size_t)v * P.fstride + coff;
     const cplx* S = round == 1 ? S0 : (round == 2 ? S1 : S2);
-    // expanding box (mhdrhs.f90:180-198): 2, 2, 3, 3 for rho, rho u; 2*gamma for p
+    // expanding box (mhdrhs.f90:187-204): 2, 2, 3, 3 for rho, rho u; 2*gamma for p
     const double cab = v == 7 ? P.aeb_p : ((v == 2 || v == 3) ? 3.0 : 2.0);
     const double ca = P.aeb ? cab / P.tau : 0.0;
     const bool mom = v >= 1 && v <= 3;
-    const double ce = (mom && P.visc_exp) ? P.nu : 0.0;    // mhdrhs.f90:200-210
+    const double ce = (mom && P.visc_exp) ? P.nu : 0.0;    // mhdrhs.f90:206-216
     const double ci = (mom && P.visc_imp) ? P.nu : 0.0;    // rktmod.f90:47-52
     const bool need_ksq = (ce != 0.0) || (ci != 0.0);
     LAPS_UNROLL
     for (int e = 0; e < 8; ++e) {
       const int kz = FF::kout(u, e);
       cplx fnl = mom ? S[e * G::NT + u] : mk(0.0, 0.0);
-      // the pressure row reads the value calc_pressure_fourier has just written (mhd.f90:318 precedes calc_rhs)
+      // the pressure row reads the value calc_pressure_fourier has just written (mhd.f90:338 precedes calc_rhs, :350)
       const cplx uo = round == 0 ? r[e] : (live ? P.u_in[voff + kz] : mk(0.0, 0.0));
       fnl.x -= ca * uo.x;
       fnl.y -= ca * uo.y;

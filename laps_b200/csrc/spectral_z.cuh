@@ -19,11 +19,11 @@ namespace laps {
 
 enum ZKind { kZRhs = 0, kZForwardOnly = 1, kZInverseOnly = 2, kZCurrent = 3,
              // incompressible tree (src_incompressible/mhdrhs.f90):
-             kZGrad = 4,   // i k_a u^[v] / cx, a = jcomp   (calc_gradient_velocity_real, :308-390)
+             kZGrad = 4,   // i k_a u^[v] / cx, a = jcomp   (calc_gradient_velocity_real, :312-391)
              kZDiv = 5,
              // fnl(1) = -i k . (rho u)^ taken from the spectral state itself: calc_flux sets flux(1:3) = uu(2:4)
              // (mhdrhs.f90:58-60), whose transform (mhdrhs.f90:128-172) is uu_fourier(2:4) again — no transform needed
-             kZMass = 6 };  // i (kx u^[v] + ky u^[v+1] + kz u^[v+2]) / cx   (calc_divB_real / calc_divV_real, :536-647)
+             kZMass = 6 };  // i (kx u^[v] + ky u^[v+1] + kz u^[v+2]) / cx   (calc_divB_real / calc_divV_real, :532-648)
 
 // One row of work (blockIdx.y).  For kZRhs:
 //   G = ca*(i kx)*W2[fa] + cb*(i ky)*W2[fb] + cx*W2[fx]      (missing terms have index < 0)

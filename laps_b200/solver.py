@@ -128,14 +128,14 @@ class Solver:
         return out.value
 
     def calc_max_divV(self) -> float:
-        """src_incompressible/mhd.f90:616-664."""
+        """src_incompressible/mhd.f90:620-668."""
         out = C.c_double()
         self._ck(self._lib.laps_max_divv(self._h, C.byref(out)))
         return out.value
 
     def calc_max_div_real(self):
-        """calc_divB_real/calc_divV_real + calc_max_div*_real (src_incompressible/mhdrhs.f90:536-647,
-        mhd.f90:668-731) -> (max |div B|, max |div u|) in real space."""
+        """calc_divB_real/calc_divV_real + calc_max_div*_real (src_incompressible/mhdrhs.f90:532-648,
+        mhd.f90:672-732) -> (max |div B|, max |div u|) in real space."""
         out = np.zeros(2)
         self._ck(self._lib.laps_max_div_real(self._h, capi._dptr(out)))
         return float(out[0]), float(out[1])
@@ -209,10 +209,11 @@ class Solver:
         return a.value, b.value, c.value
 
     def field_counts(self):
-        """(nf, ni): fields transformed forward / inverse per RK stage (laps_get_field_counts)."""
-        a, b = C.c_int32(), C.c_int32()
-        self._ck(self._lib.laps_get_field_counts(self._h, C.byref(a), C.byref(b)))
-        return a.value, b.value
+        """(nf, ni, spec_rows): fields transformed forward / inverse per RK stage and the state rows of the
+        main z-pass launch (laps_get_field_counts)."""
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        self._ck(self._lib.laps_get_field_counts(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def set_profiling(self, on: bool):
         self._ck(self._lib.laps_set_profiling(self._h, 1 if on else 0))

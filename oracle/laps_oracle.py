@@ -637,8 +637,8 @@ class StateIncompressible(State):
     uu = [rho, rho*u (3), B (3), p] (uu(8) is the PRESSURE here, mhdinit.f90:210), uu_prim = u (3
     components, mhdinit.f90:5,142; the 4th row of the base-class array is unused).  ``rho0`` is the
     namelist background density (mhdinit.f90:15) that calc_gradient_velocity_real divides by
-    (mhdrhs.f90:366); update_rho_p compounds it every step in the expanding box (AEBmod.f90:123-134).
-    Every stage re-derives the spectrum from the real fields (mhd.f90:305)."""
+    (mhdrhs.f90:369); update_rho_p compounds it every step in the expanding box (AEBmod.f90:123-134).
+    Every stage re-derives the spectrum from the real fields (mhd.f90:325)."""
 
     def __init__(self, p: Params, p0: float = 1.0):
         super().__init__(p)
@@ -658,7 +658,7 @@ class StateIncompressible(State):
         self.uu_fourier = fft_forward(self.uu)
 
     def calc_gradient_velocity_real(self):
-        """mhdrhs.f90:308-390 — d u_b / d x_a = IFFT( k_a (rho u_b)^ / rho0 ), slot 3*b + a."""
+        """mhdrhs.f90:312-391 — d u_b / d x_a = IFFT( k_a (rho u_b)^ / rho0 ), slot 3*b + a."""
         kx, ky, kz = self.kvec()
         uf = self.uu_fourier
         gf = np.empty((9,) + uf.shape[1:], dtype=np.complex128)
@@ -666,11 +666,11 @@ class StateIncompressible(State):
             gf[3 * b + 0] = 1j * kx * uf[1 + b]
             gf[3 * b + 1] = 1j * ky * uf[1 + b]
             gf[3 * b + 2] = 1j * kz * uf[1 + b]
-        gf = gf / self.rho0                                     # mhdrhs.f90:366
+        gf = gf / self.rho0                                     # mhdrhs.f90:369
         self.grad_velocity = fft_inverse(gf, self.p.nx)
 
     def calc_flux_for_pressure(self):
-        """mhdrhs.f90:392-441 — -(rho u . grad) u + J x B."""
+        """mhdrhs.f90:393-437 — -(rho u . grad) u + J x B."""
         uu, G, J = self.uu, self.grad_velocity, self.current_density
         fp = np.empty((3,) + uu.shape[1:])
         fp[0] = (-uu[1] * G[0] - uu[2] * G[1] - uu[3] * G[2] + J[1] * uu[6] - J[2] * uu[5])
@@ -679,7 +679,7 @@ class StateIncompressible(State):
         return fp
 
     def calc_pressure_fourier(self, fpf):
-        """mhdrhs.f90:471-523 — p^ = -(k . Fp^)/k^2, zero where k^2 < 1e-10."""
+        """mhdrhs.f90:468-518 — p^ = -(k . Fp^)/k^2, zero where k^2 < 1e-10."""
         kxi, kyi, kzi = self.kvec()
         kx, ky, kz = 1j * kxi, 1j * kyi, 1j * kzi
         k2 = np.broadcast_to(self.k_square, fpf[0].shape)
@@ -688,7 +688,7 @@ class StateIncompressible(State):
         self.uu_fourier[7] = np.where(k2 < 1e-10, 0.0, ph)
 
     def calc_flux(self):
-        """mhdrhs.f90:26-85 — the electric field -u x B (+ Hall term)."""
+        """mhdrhs.f90:25-84 — the electric field -u x B (+ Hall term)."""
         p = self.p
         uu, pr = self.uu, self.uu_prim
         ux, uy, uz = pr[0], pr[1], pr[2]
@@ -705,7 +705,7 @@ class StateIncompressible(State):
         return flux
 
     def calc_rhs(self, flux_fourier, fpf):
-        """mhdrhs.f90:118-236."""
+        """mhdrhs.f90:117-232."""
         p = self.p
         kxi, kyi, kzi = self.kvec()
         kx, ky, kz = 1j * kxi, 1j * kyi, 1j * kzi
@@ -733,28 +733,28 @@ class StateIncompressible(State):
         if p.if_resis and p.if_resis_exp:
             ksq = k2.copy()
             if p.if_conserve_background:
-                ksq[0, :, 0] = 0.0                              # `cycle` where ix==1 .and. iz==1 (mhdrhs.f90:223-225)
+                ksq[0, :, 0] = 0.0                              # `cycle` where ix==1 .and. iz==1 (mhdrhs.f90:219-221)
             for v in (4, 5, 6):
                 fnl[v] = fnl[v] - p.resistivity * uf[v] * ksq
         self.fnl = fnl
         return fnl
 
     def update_uu_prim_from_uu(self):
-        """mhdrhs.f90:239-246."""
+        """mhdrhs.f90:235-242."""
         uu, pr = self.uu, self.uu_prim
         pr[0] = uu[1] / uu[0]
         pr[1] = uu[2] / uu[0]
         pr[2] = uu[3] / uu[0]
 
     def stage(self, irk, retransform: bool = True):
-        """One pass of the loop body of evolve (mhd.f90:303-350)."""
+        """One pass of the loop body of evolve (mhd.f90:323-364)."""
         if retransform:
-            self.uu_fourier = fft_forward(self.uu)               # mhd.f90:305
-        self.calc_current_density_real()                         # :308 (always, J x B needs it)
-        self.calc_gradient_velocity_real()                       # :309
-        fpf = fft_forward(self.calc_flux_for_pressure())         # :312-315
-        self.calc_pressure_fourier(fpf)                          # :318
-        ff = fft_forward(self.calc_flux())                       # :321-324
+            self.uu_fourier = fft_forward(self.uu)               # mhd.f90:325
+        self.calc_current_density_real()                         # :328 (always, J x B needs it)
+        self.calc_gradient_velocity_real()                       # :329
+        fpf = fft_forward(self.calc_flux_for_pressure())         # :332-335
+        self.calc_pressure_fourier(fpf)                          # :338
+        ff = fft_forward(self.calc_flux())                       # :341-344
         self.calc_rhs(ff, fpf)
         self.rkt(irk)
         self.dealias()
@@ -770,10 +770,10 @@ class StateIncompressible(State):
     def evolve(self, retransform: bool = True):
         for irk in range(3):
             self.stage(irk, retransform)
-        self.update_rho_p()                                      # mhd.f90:353
+        self.update_rho_p()                                      # mhd.f90:366
 
     def vardt(self):
-        """mhd.f90:356-457 — Alfven and flow speeds only."""
+        """mhd.f90:369-476 — Alfven and flow speeds only."""
         p, g = self.p, self.g
         uu, pr = self.uu, self.uu_prim
         sq = np.sqrt(uu[0])
@@ -799,13 +799,13 @@ class StateIncompressible(State):
 
     # ---------------------------------------------------------------- diagnostics
     def calc_max_divV(self):
-        """mhd.f90:616-664 (Fourier-space maximum of |k . (rho u)^| / rho0)."""
+        """mhd.f90:620-668 (Fourier-space maximum of |k . (rho u)^| / rho0)."""
         kx, ky, kz = self.kvec()
         uf = self.uu_fourier
         return float(np.max(np.abs(1j * kx * uf[1] + 1j * ky * uf[2] + 1j * kz * uf[3]))) / self.rho0
 
     def calc_max_div_real(self):
-        """calc_divB_real/calc_divV_real + calc_max_div*_real (mhdrhs.f90:536-647, mhd.f90:668-731):
+        """calc_divB_real/calc_divV_real + calc_max_div*_real (mhdrhs.f90:532-648, mhd.f90:672-732):
         maxima of |div B| and |div u| in real space, as the driver prints them."""
         kx, ky, kz = self.kvec()
         uf = self.uu_fourier

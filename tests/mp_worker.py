@@ -101,7 +101,7 @@ def main():
     oinv = o.invariants()
     assert abs(inv[0] - oinv[0]) <= 1e-9 * abs(oinv[0])
     extra = []
-    if p.incompressible:   # the divergence diagnostics of the incompressible driver (mhd.f90:616-731)
+    if p.incompressible:   # the divergence diagnostics of the incompressible driver (mhd.f90:620-732)
         dv, odv = g.calc_max_divV(), o.calc_max_divV()
         assert abs(dv - odv) <= 1e-9 * odv, (dv, odv)
         dr, odr = g.calc_max_div_real(), o.calc_max_div_real()

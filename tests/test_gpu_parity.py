@@ -130,7 +130,7 @@ def test_incompressible_tree_256_properties():
         assert np.array_equal(g.uu_fourier()[:7, 0, 0, 0], s0)
         assert g.calc_max_divB() < 1e-13
         assert g.calc_max_divV() < max(2 * dv0, 1e-12)       # solenoidal initial velocity, uniform density
-        assert abs(uu[7].mean()) < 1e-14                      # the pressure carries no k=0 mode (mhdrhs.f90:508-511)
+        assert abs(uu[7].mean()) < 1e-14                      # the pressure carries no k=0 mode (mhdrhs.f90:505-508)
 
 
 def test_dealias_mask_bit_exact():

@@ -318,7 +318,7 @@ def _incompressible_turbulence(n=16, **kw):
 
 
 def test_incompressible_pressure_solves_the_poisson_equation():
-    """calc_pressure_fourier (mhdrhs.f90:471-523) against an independent full-complex-FFT evaluation of
+    """calc_pressure_fourier (mhdrhs.f90:468-518) against an independent full-complex-FFT evaluation of
     laplace(p) = div Fp, and the projected momentum tendency is solenoidal."""
     p, s = _incompressible_turbulence()
     s.calc_current_density_real()
@@ -344,7 +344,7 @@ def test_incompressible_pressure_solves_the_poisson_equation():
 
 @pytest.mark.parametrize("dealias,tol", [(1, 1e-12), (2, 1e-12)])
 def test_incompressible_retransform_is_identity_on_band_limited_spectra(dealias, tol):
-    """mhd.f90:305 re-derives uu_fourier from uu at the start of every stage; after dealiasing (Nyquist
+    """mhd.f90:325 re-derives uu_fourier from uu at the start of every stage; after dealiasing (Nyquist
     planes removed) that is the identity to round-off — the property the library's default relies on."""
     p, a = _incompressible_turbulence(dealias=dealias, if_hall=True, ion_inertial_length=0.2, if_AEB=True, Ur0=1.167)
     _, b = _incompressible_turbulence(dealias=dealias, if_hall=True, ion_inertial_length=0.2, if_AEB=True, Ur0=1.167)
@@ -369,7 +369,7 @@ def test_incompressible_k0_and_divergence_invariants():
     s.vardt()
     for _ in range(5):
         s.step()
-    # fnl(k=0) = 0 exactly; the per-stage FFT round trip of mhd.f90:305 moves the mode by round-off only
+    # fnl(k=0) = 0 exactly; the per-stage FFT round trip of mhd.f90:325 moves the mode by round-off only
     assert np.abs(s.uu_fourier[:7, 0, 0, 0] - k0).max() < 1e-15
     assert s.calc_max_divB() < 1e-15
     # div(rho u) of the initial data (non-uniform rho) only decays viscously
