@@ -48,11 +48,12 @@ struct Tile {
 // ---------------------------------------------------------------------------------------------
 // forward x: real lines -> half spectra, two real lines per complex transform
 // (replaces the r2c loops fftw.f90:58-64 / mhdrhs.f90:143-149, including the "/nx").
-// grid.x = nzl * (ny / (2*TL)), grid.y = number of fields
+// grid.x = planes * (ny / (2*TL)), grid.y = number of fields.  `in` holds `planes` z planes per field (the
+// whole slab, or one z chunk of it whose first plane is zl0 of the slab); W1 is always the whole slab.
 template <int N, int TL>
 __global__ void __launch_bounds__(Tile<N, TL>::NTHREADS, Tile<N, TL>::MINB)
 k_fwd_x(const double* __restrict__ in, size_t in_fstride, cplx* __restrict__ W1,
-        int nzl, int ny, const cplx* __restrict__ tw, double scale, int nkx) {
+        int nzl, int ny, const cplx* __restrict__ tw, double scale, int nkx, int zl0) {
   typedef Geom<N> G;
   typedef Fft<N, -1> F;
   typedef Tile<N, TL> T;
@@ -91,7 +92,7 @@ k_fwd_x(const double* __restrict__ in, size_t in_fstride, cplx* __restrict__ W1,
       const cplx zn = sm[lp * T::PITCH + G::pad((N - k) & (N - 1))];
       const cplx a = mk((zk.x + zn.x) * hs, (zk.y - zn.y) * hs);
       const cplx b = mk((zk.y + zn.y) * hs, (zn.x - zk.x) * hs);
-      st256(W1 + (((size_t)f * nxh + k) * nzl + zl) * ny + y0 + 2 * lp, a, b);
+      st256(W1 + (((size_t)f * nxh + k) * nzl + zl0 + zl) * ny + y0 + 2 * lp, a, b);
     }
   }
 }

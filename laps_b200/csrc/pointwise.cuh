@@ -28,8 +28,10 @@ LAPS_D Prim prim_of(double rho, double mx, double my, double mz, double bx, doub
 struct FluxParams {
   const double* uu;     // [8][npts]
   const double* J;      // [3][npts] (Hall) or null
-  double* F;            // [nf][npts]: 0-2 mass, 3-11 momentum tensor, 12-14 E, 15-17 energy, 18 EBM source
-  size_t npts;
+  double* F;            // [nf][fstride]: 0-2 mass, 3-11 momentum tensor, 12-14 E, 15-17 energy, 18 EBM source
+  size_t npts;          // field stride of uu and J
+  size_t in_off, count; // points [in_off, in_off + count) of the slab are processed (z-chunked launches) ...
+  size_t fstride;       // ... into F[slot * fstride + (point - in_off)]
   int hall, aeb;
   double gamma, di, tau;
   int z_radial;         // 2D tree, radial direction along z (2D/mhdrhs.f90:96-100)
@@ -40,16 +42,17 @@ struct FluxParams {
 __global__ void __launch_bounds__(256, 3) k_flux(const FluxParams P) {
   const size_t n = P.npts;
   const double gm1 = P.gamma - 1.0;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+  for (size_t ii = blockIdx.x * (size_t)blockDim.x + threadIdx.x; ii < P.count; ii += (size_t)gridDim.x * blockDim.x) {
+    const size_t i = P.in_off + ii;
     const double rho = P.uu[i], mx = P.uu[n + i], my = P.uu[2 * n + i], mz = P.uu[3 * n + i];
     const double Bx = P.uu[4 * n + i], By = P.uu[5 * n + i], Bz = P.uu[6 * n + i], en = P.uu[7 * n + i];
     const Prim q = prim_of(rho, mx, my, mz, Bx, By, Bz, en, gm1);
     const double ux = q.ux, uy = q.uy, uz = q.uz, p = q.p;
     const double ptot = p + 0.5 * (Bx * Bx + By * By + Bz * Bz);
     const double udotb = ux * Bx + uy * By + uz * Bz;
-    double* F = P.F + i;
+    double* F = P.F + ii;
     // every flux is stored as soon as it is formed (few live values: the kernel wants 3 CTAs per SM)
-#define LAPS_PUT(j, val) do { if (P.slot[j] >= 0) F[(size_t)P.slot[j] * n] = (val); } while (0)
+#define LAPS_PUT(j, val) do { if (P.slot[j] >= 0) F[(size_t)P.slot[j] * P.fstride] = (val); } while (0)
     LAPS_PUT(0, mx); LAPS_PUT(1, my); LAPS_PUT(2, mz);
     LAPS_PUT(3, mx * ux - Bx * Bx + ptot);
     LAPS_PUT(4, my * ux - By * Bx);

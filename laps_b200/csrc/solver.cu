@@ -135,6 +135,7 @@ struct laps_solver {
   // being re-transformed.  Off with dealias_option 0, where the state keeps non-Hermitian Nyquist content that
   // the reference's real-space round trip would drop.
   bool mass_from_state = false;
+  int tune_zchunk = 0;   // LAPS_TUNE_ZCHUNK: z planes per interleaved calc_flux / forward-x launch pair (0 = whole slab)
   int tune_fusex = -1;   // calc_flux fused into the forward x pass (LAPS_TUNE_FUSEX): -1 = library default, 0 = never, 1 = whenever possible (nx <= 512)
   int num_sms = 148;
   double da_thresh = 0;
@@ -276,17 +277,25 @@ cudaError_t prepare_kernel(K kernel, size_t smem, int ctas) {
   if (pct > 100) pct = 100;
   return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
+// planes < 0: the whole slab; otherwise `in` holds the `planes` z planes starting at plane zl0 of the slab
 template <int N>
-int do_fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1, bool prune) {
+int do_fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1, bool prune, int zl0, int planes, bool scoped) {
   char name[32]; std::snprintf(name, sizeof(name), "fwd_x%d", nfields);
   constexpr int TL = tlx(N);
   typedef Tile<N, TL> T;
   if (s->xy % (2 * TL) != 0) { s->err = "ny must be a multiple of " + std::to_string(2 * TL); return 1; }
   LAPS_CK(s, prepare_kernel(k_fwd_x<N, TL>, T::SMEM, T::MINB));
-  LaunchScope ls(s, name);
-  dim3 grid((unsigned)(s->xz * (s->xy / (2 * TL))), (unsigned)nfields);
-  LAPS_LAUNCH((k_fwd_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, in, fstride, W1, s->xz, s->xy, s->tw_x,
-              1.0 / N, prune ? s->nkx : s->nxh);
+  const int np = planes < 0 ? s->xz : planes;
+  dim3 grid((unsigned)(np * (s->xy / (2 * TL))), (unsigned)nfields);
+  if (scoped) {
+    LaunchScope ls(s, name);
+    LAPS_LAUNCH((k_fwd_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, in, fstride, W1, s->xz, s->xy, s->tw_x,
+                1.0 / N, prune ? s->nkx : s->nxh, zl0);
+  } else {
+    ++s->launches;
+    LAPS_LAUNCH((k_fwd_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, in, fstride, W1, s->xz, s->xy, s->tw_x,
+                1.0 / N, prune ? s->nkx : s->nxh, zl0);
+  }
   return check_launch(s, "k_fwd_x");
 }
 
@@ -414,7 +423,9 @@ int do_incomp_z(S* s, const ZParams& zp) {
     default: s->err = "unsupported line length"; return 1;          \
   }
 
-int fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1, bool prune) { LAPS_DISPATCH(s->nx, do_fwd_x, s, in, fstride, nfields, W1, prune) }
+int fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1, bool prune, int zl0 = 0, int planes = -1, bool scoped = true) {
+  LAPS_DISPATCH(s->nx, do_fwd_x, s, in, fstride, nfields, W1, prune, zl0, planes, scoped)
+}
 int fwd_y(S* s, const cplx* W1, int nfields, bool prune) { LAPS_DISPATCH(s->ny, do_fwd_y, s, W1, nfields, prune) }
 int flux_fwd_x(S* s, const FusedFluxParams& fp) { LAPS_DISPATCH(s->nx, do_flux_fwd_x, s, fp) }
 bool use_fused_flux(const S* s) {
@@ -643,10 +654,33 @@ int stage(S* s, int irk) {
     for (int j = 0; j < 19; ++j) if (s->fslot[j] >= 0) fp.id[s->fslot[j]] = j;
     LAPS_TRY(flux_fwd_x(s, fp));
     LAPS_TRY(fwd_y(s, buf_W1(s), s->nf, true));
+  } else if (s->tune_zchunk > 0 && !s->two_d) {
+    // calc_flux and the forward x pass interleaved over z chunks small enough for the chunk's fluxes to stay in
+    // the L2 between the two kernels (nf x chunk planes x 8 nx ny bytes): the fluxes need not reach HBM at all
+    FluxParams f;
+    f.uu = s->uu; f.J = s->J; f.F = buf_F(s); f.npts = s->npts;
+    f.hall = p.if_hall; f.aeb = p.if_AEB; f.gamma = p.adiabatic_index; f.di = p.ion_inertial_length; f.tau = s->tau;
+    f.z_radial = 0;
+    for (int j = 0; j < 19; ++j) f.slot[j] = s->fslot[j];
+    const size_t plane = (size_t)s->nx * s->ny;
+    const int cz = std::min(s->tune_zchunk, s->nzl);
+    f.fstride = (size_t)cz * plane;
+    LaunchScope ls(s, "flux+fwd_x");
+    for (int z0 = 0; z0 < s->nzl; z0 += cz) {
+      const int nzc = std::min(cz, s->nzl - z0);
+      f.in_off = (size_t)z0 * plane; f.count = (size_t)nzc * plane;
+      const unsigned gb = (unsigned)std::min<size_t>((size_t)s->nblk, (f.count + 255) / 256);
+      ++s->launches;
+      LAPS_LAUNCH(k_flux, dim3(gb), dim3(256), 0, s->stream, f);
+      LAPS_TRY(check_launch(s, "k_flux"));
+      LAPS_TRY(fwd_x(s, buf_F(s), f.fstride, s->nf, buf_W1(s), true, z0, nzc, false));
+    }
+    LAPS_TRY(fwd_y(s, buf_W1(s), s->nf, true));
   } else {
   {  // calc_flux (mhdrhs.f90:21-124; 2D/mhdrhs.f90:23-128)
     FluxParams f;
     f.uu = s->uu; f.J = s->J; f.F = buf_F(s); f.npts = s->npts;
+    f.in_off = 0; f.count = s->npts; f.fstride = s->npts;
     f.hall = p.if_hall; f.aeb = p.if_AEB; f.gamma = p.adiabatic_index; f.di = p.ion_inertial_length; f.tau = s->tau;
     f.z_radial = s->two_d && p.if_z_radial;
     for (int j = 0; j < 19; ++j) f.slot[j] = s->fslot[j];
@@ -833,6 +867,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
   if (const char* e = std::getenv("LAPS_TUNE_RCG")) s->tune_rcg = std::atoi(e);
   if (const char* e = std::getenv("LAPS_TUNE_Z")) s->tune_z = std::atoi(e);
   if (const char* e = std::getenv("LAPS_TUNE_FUSEX")) s->tune_fusex = std::atoi(e);
+  if (const char* e = std::getenv("LAPS_TUNE_ZCHUNK")) s->tune_zchunk = std::atoi(e);
   // The reference re-derives uu_fourier from the real fields at the start of every stage
   // (src_incompressible/mhd.f90:325).  For a spectrum the dealiasing has band-limited (options 1, 2: the
   // Nyquist planes are removed) that round trip is the identity up to round-off and is skipped; with
@@ -920,6 +955,30 @@ int laps_create(const laps_params* params, laps_handle* out) {
     if (s->kymax >= s->ny / 2) { s->pr_nkyl = s->nyl; s->pr_nA = s->nyl; s->pr_a0 = 0; s->pr_b0 = 0; }
   }
   cudaMemsetAsync(s->rk, 0, 8 * s->csz * sizeof(cplx), s->stream);
+#ifndef LAPS_EMU_BUILD
+  if (s->tune_zchunk > 0 && !two_d && !s->incomp) {
+    // keep the flux chunk resident: persisting L2 lines for the chunk buffer, streaming for everything else
+    int persist = 1;
+    if (const char* e = std::getenv("LAPS_TUNE_L2PERSIST")) persist = std::atoi(e);
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, p.device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, p.device);
+    const size_t want = (size_t)s->nf * std::min(s->tune_zchunk, s->nzl) * s->nx * s->ny * sizeof(double);
+    if (persist && max_persist > 0 && max_window > 0) {
+      const size_t carve = std::min(want, (size_t)max_persist);
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+      cudaStreamAttrValue a;
+      std::memset(&a, 0, sizeof(a));
+      a.accessPolicyWindow.base_ptr = s->bufX;
+      a.accessPolicyWindow.num_bytes = std::min(want, (size_t)max_window);
+      a.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)a.accessPolicyWindow.num_bytes);
+      a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &a);
+      (void)cudaGetLastError();
+    }
+  }
+#endif
 
   // single rank: the exchange tables point at this rank's own buffers
   std::memset(&s->tabW2, 0, sizeof(PeerTable)); std::memset(&s->tabV1, 0, sizeof(PeerTable));
