@@ -10,8 +10,8 @@ evolve (3 RK stages) + evolve_radius + vardt, through the C ABI (include/laps_b2
 value  : K steps with the state resident in HBM, CUDA events on the library's stream, max over ranks.
 e2e    : a driver session through the same C ABI with HOST buffers inside the timed region:
          laps_set_primitive from pinned host memory (H2D + conversion + 8 forward FFTs), K steps
-         (each reads dt back to the host), laps_get_state into pinned host memory (D2H of uu and
-         uu_prim) -- the traffic a LAPS driver generates between two outNNN.dat dumps.
+         (each reads dt back to the host), laps_get_output into pinned host memory (D2H of the 8-field
+         array output_uu writes) -- the traffic a LAPS driver generates between two outNNN.dat dumps.
 roofline: dominant kernel by device time (CUDA events around every launch, laps_set_profiling),
          algorithmic bytes per launch as stated in DESIGN.md, against MEASURED_PEAKS.json.
 cpu_baseline / --impl reference: the CPU oracle (NumPy/SciPy restatement of the reference, kind
@@ -237,7 +237,6 @@ def run_gpu(args):
     synthetic.turbulence_slab(n, n, n, kw["Lx"], kw["Ly"], kw["Lz"], z_offset=g.ext.z_offset, z_size=g.ext.z_size,
                               kmax=min(8, n // 2 - 1), out=prim)
     host_uu = torch.empty(shape, dtype=torch.float64).pin_memory()
-    host_prim = torch.empty((4,) + g.real_shape, dtype=torch.float64).pin_memory()
 
     def ev():
         return torch.cuda.Event(enable_timing=True)
@@ -288,12 +287,12 @@ def run_gpu(args):
     g.vardt()
     for _ in range(args.steps):
         g.step()                               # reads dt back every step
-    g.get_state(out_uu=host_uu.numpy(), out_prim=host_prim.numpy())   # D2H into pinned memory
+    g.get_output(True, out=host_uu.numpy())   # D2H of the array output_uu writes (rho, u, B, p) into pinned memory
     f1.record(stream)
     barrier()
     e2e_ms = max_over_ranks(f0.elapsed_time(f1)) / args.steps
     h2d = world * prim.nbytes / args.steps
-    d2h = world * (host_uu.numel() + host_prim.numel()) * 8 / args.steps + 8
+    d2h = world * host_uu.numel() * 8 / args.steps + 8
     finite = bool(np.isfinite(host_uu.numpy()).all())
 
     # ---------------- roofline of the dominant kernel ----------------
@@ -347,7 +346,7 @@ def run_gpu(args):
                    "ic": "ifield=3 uniform B0=(1,0,0) + ipert=7-style random-phase modes |k|<=8, k^-3/2"},
         "clocks": clocks,
         "e2e": {"value": float(n) ** 3 / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms, "what": "laps_set_primitive(host) + K x laps_step + laps_get_state(host), per step"},
+                "ms_per_step": e2e_ms, "what": "laps_set_primitive(host) + K x laps_step + laps_get_output(host), per step"},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,

@@ -135,6 +135,9 @@ int laps_invariants(laps_handle h, double out[3]);
 /* Host copy of the state for output_uu / restart (mhdoutput.f90:95-123): conserved uu (8 fields)
  * and uu_prim (ux,uy,uz,p); either pointer may be NULL. */
 int laps_get_state(laps_handle h, double* uu_local, double* uu_prim_local);
+/* The 8-field array output_uu writes (mhdoutput.f90:95-123): primitive != 0 -> rho, u, B, p
+ * (output_primitive = .true.), else the conserved uu.  Same layout as uu_local. */
+int laps_get_output(laps_handle h, double* out_local, int32_t primitive);
 /* Spectral state uu_fourier as complex128 pairs in the library's internal layout
  * [ivar][kx][ky_local][kz] (kz fastest) — for parity tests. */
 int laps_get_spectral(laps_handle h, double* uu_fourier_local);

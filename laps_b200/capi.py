@@ -61,7 +61,7 @@ SYMBOLS = [
     "laps_sync", "laps_get_stream", "laps_max_divb", "laps_rms", "laps_invariants", "laps_get_state", "laps_get_spectral",
     "laps_fft_forward", "laps_fft_inverse", "laps_transpose_yz_indexmap",
     "laps_last_step_ms", "laps_set_profiling", "laps_get_profile", "laps_get_pruning",
-    "laps_max_divv", "laps_max_div_real", "laps_get_rho0", "laps_get_field_counts",
+    "laps_max_divv", "laps_max_div_real", "laps_get_rho0", "laps_get_field_counts", "laps_get_output",
 ]
 
 
@@ -108,6 +108,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.laps_invariants.argtypes = [H, dp]
     lib.laps_get_state.argtypes = [H, dp, dp]
     lib.laps_get_spectral.argtypes = [H, dp]
+    lib.laps_get_output.argtypes = [H, dp, C.c_int32]
     lib.laps_fft_forward.argtypes = [H, dp, C.c_int32, dp]
     lib.laps_fft_inverse.argtypes = [H, dp, C.c_int32, dp]
     lib.laps_transpose_yz_indexmap.argtypes = [H, C.POINTER(C.c_int64)]

@@ -1320,6 +1320,30 @@ int laps_get_state(laps_handle s, double* uu_local, double* uu_prim_local) {
   return 0;
 }
 
+// The array output_uu writes (mhdoutput.f90:95-123): uu with rho u -> u and e -> p when output_primitive,
+// else the conserved uu.  One 8-field device->host copy instead of the 12 fields of laps_get_state.
+int laps_get_output(laps_handle s, double* out_local, int32_t primitive) {
+  if (!s || !out_local) return 1;
+  LAPS_TRY(require_state(s));
+  const size_t fb = s->npts * sizeof(double);
+  if (!primitive) {
+    LAPS_CK(s, cudaMemcpyAsync(out_local, s->uu, 8 * fb, cudaMemcpyDeviceToHost, s->stream));
+  } else {
+    if (!s->prim) LAPS_CK(s, cudaMalloc((void**)&s->prim, 4 * fb));
+    {
+      LaunchScope ls(s, "cons_to_prim");
+      LAPS_LAUNCH(k_cons_to_prim, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, (const double*)s->uu, s->prim, s->npts, s->p.adiabatic_index, s->incomp ? 1 : 0);
+      LAPS_TRY(check_launch(s, "k_cons_to_prim"));
+    }
+    LAPS_CK(s, cudaMemcpyAsync(out_local, s->uu, fb, cudaMemcpyDeviceToHost, s->stream));                                 // rho
+    LAPS_CK(s, cudaMemcpyAsync(out_local + s->npts, s->prim, 3 * fb, cudaMemcpyDeviceToHost, s->stream));                  // u
+    LAPS_CK(s, cudaMemcpyAsync(out_local + 4 * s->npts, s->uu + 4 * s->npts, 3 * fb, cudaMemcpyDeviceToHost, s->stream)); // B
+    LAPS_CK(s, cudaMemcpyAsync(out_local + 7 * s->npts, s->prim + 3 * s->npts, fb, cudaMemcpyDeviceToHost, s->stream));   // p
+  }
+  LAPS_CK(s, cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
 int laps_get_spectral(laps_handle s, double* out) {
   if (!s || !out) return 1;
   LAPS_TRY(require_state(s));

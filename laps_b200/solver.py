@@ -166,6 +166,13 @@ class Solver:
         self._ck(self._lib.laps_get_state(self._h, capi._dptr(uu), capi._dptr(prim) if want_prim else None))
         return uu, prim
 
+    def get_output(self, primitive=True, out=None):
+        """The array output_uu writes (mhdoutput.f90:95-123): [rho, u, B, p] or the conserved uu."""
+        a = np.empty((8,) + self.real_shape) if out is None else out
+        assert a.shape == (8,) + self.real_shape and a.dtype == np.float64 and a.flags.c_contiguous
+        self._ck(self._lib.laps_get_output(self._h, capi._dptr(a), 1 if primitive else 0))
+        return a
+
     def uu_fourier(self) -> np.ndarray:
         """Spectral state in the reference index order [v, kz, ky_local, kx]."""
         raw = np.empty((8, self.nxh, self.nyl, self.nz), dtype=np.complex128)

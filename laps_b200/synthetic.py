@@ -87,3 +87,31 @@ def turbulence_slab(nx, ny, nz, Lx, Ly, Lz, z_offset=0, z_size=None, bx0=1.0, by
         prim[v] += back[v]
     prim[7] = press0
     return prim
+
+
+def uniform_background(nx, ny, z_size, bx0=0.0, by0=0.0, bz0=0.0, press0=1.0, rho0=1.0, out=None):
+    """``ifield = 3`` (mhdinit.f90:193-194,251-256): uniform rho, B and p; primitive [8, z_size, ny, nx]."""
+    prim = out if out is not None else np.empty((8, z_size, ny, nx))
+    prim[...] = 0.0
+    prim[0] = rho0
+    prim[4], prim[5], prim[6] = bx0, by0, bz0
+    prim[7] = press0
+    return prim
+
+
+def add_alfven_wave(prim, nx, Lx, db0=0.1, wave_number_jet=1, cor_angle=0.0):
+    """``ipert = 1`` (mhdinit.f90:328-342): circularly polarised Alfven wave along x, added in place
+    to the primitive slab ``prim`` = [8, z_size, ny, nx]."""
+    x = np.arange(nx) * (Lx / nx)
+    kx = 2 * PI / Lx * wave_number_jet
+    s = np.sin(kx * x)[None, None, :]
+    c = np.cos(kx * x)[None, None, :]
+    ca, sa = math.cos(cor_angle), math.sin(cor_angle)
+    rs = np.sqrt(prim[0])
+    prim[6] = prim[6] - db0 * s
+    prim[3] = prim[3] + db0 / rs * s
+    prim[1] = prim[1] + db0 / rs * c * sa
+    prim[4] = prim[4] - db0 * c * sa
+    prim[2] = prim[2] + db0 / rs * c * ca
+    prim[5] = prim[5] - db0 * c * ca
+    return prim

@@ -1,0 +1,177 @@
+"""File formats either side of the hot path (laps_b200/lapsio.py) and the stand-in driver
+(laps_b200/driver.py, the ``program mhd`` loop of mhd.f90:16-293).
+
+The golden files under tests/golden/io were read back by the reference's own post-processing reader
+when they were generated (tests/golden/make_io_fixtures.py, run in the build container where
+/root/reference exists); expected.npz holds what that reader returned."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+sys.path.insert(0, os.path.join(HERE, "emu"))
+
+import make_io_fixtures as fx  # noqa: E402
+import parity_common as pc  # noqa: E402
+from laps_b200 import lapsio  # noqa: E402
+from laps_b200.driver import Driver, params_from_namelists  # noqa: E402
+from oracle import laps_oracle as lo  # noqa: E402
+
+GOLD = os.path.join(HERE, "golden", "io")
+
+
+def test_writers_reproduce_the_golden_files_byte_for_byte(tmp_path):
+    fx.write_all(str(tmp_path))
+    for name in ("grid.dat", "parallel_info.dat", "out003.dat", "rms.dat", "EBM_info.dat"):
+        with open(os.path.join(GOLD, "output", name), "rb") as a, open(tmp_path / name, "rb") as b:
+            assert a.read() == b.read(), name
+
+
+def test_readers_agree_with_what_the_reference_reader_returned():
+    e = np.load(os.path.join(GOLD, "expected.npz"))
+    out = os.path.join(GOLD, "output")
+    assert lapsio.read_parallel_info(os.path.join(out, "parallel_info.dat")) == (int(e["npe"]), int(e["iproc"]), int(e["jproc"]), int(e["nvar"]))
+    xg, yg, zg = lapsio.read_grid(os.path.join(out, "grid.dat"))
+    assert np.array_equal(xg, e["xgrid"]) and np.array_equal(yg, e["ygrid"]) and np.array_equal(zg, e["zgrid"])
+    nx, ny, nz = len(xg), len(yg), len(zg)
+    f = os.path.join(out, "out003.dat")
+    assert lapsio.read_out_header(f) == float(e["t"])
+    full = lapsio.read_out_slab(f, nx, ny, nz)
+    assert np.array_equal(full.transpose(3, 2, 1, 0), e["uu"])          # reference layout uu[ix,iy,iz,ivar]
+    slab = lapsio.read_out_slab(f, nx, ny, nz, z_offset=2, z_size=3)     # a rank's block, as read_restart reads it
+    assert np.array_equal(slab, full[:, 2:5])
+    assert np.array_equal(full[:, 3, 1, 2], e["loc"])
+    rms = np.loadtxt(os.path.join(out, "rms.dat"))
+    assert np.array_equal(rms, e["rms"])
+
+
+def test_fortran_edit_descriptors():
+    assert lapsio.fmt_1pe16_8(1.0) == "  1.00000000E+00"
+    assert lapsio.fmt_1pe16_8(-3.75e5) == " -3.75000000E+05"
+    assert lapsio.fmt_1pe16_8(0.0) == "  0.00000000E+00"
+    assert lapsio.fmt_1pe16_8(1e-110) == "  1.00000000-110"               # three-digit exponents drop the E
+    assert lapsio.rms_line(0.05, [1.0] * 8, [0.0] * 8, [2.0] * 3).startswith("    0.050000    1.00000000E+00")
+    assert len(lapsio.rms_line(0.0, [0] * 8, [0] * 8, [0] * 3)) == 12 + 2 + 19 * 16
+    assert [lapsio.out_name(i) for i in (0, 7, 42, 999)] == ["out000.dat", "out007.dat", "out042.dat", "out999.dat"]
+
+
+INPUT = """&genr
+   tmax = 100.0
+   dtout = 0.5
+   dtrms = 0.2   ! comment
+/
+&numerical
+   cfl = 0.5
+   dealias_option = 1
+/
+&prl
+   ndim_parallel = 1
+/
+&grid
+   nx = 16
+   ny = 16
+   nz = 16
+   Lx = 24.0
+   Ly = 24.0
+   Lz = 24.0
+/
+&field
+   ifield = 3
+   Bx0 = 1.
+   By0 = 0.
+   Bz0 = 0.
+   press0 = 1.0
+/
+&pert
+   ipert = 7
+   db0 = 0.1, dv0 = 0.1
+   drho0 = 1d-2
+   nmodex = 2
+/
+&phys
+   adiabatic_index = 1.666667
+   if_resis = T
+   resistivity = 1e-4
+   if_visc = .true.
+   viscosity = 1e-4
+/
+&AEB
+   if_AEB = T
+   radius0 = 30.0
+   Ur0 = 1.167
+/
+&Hall
+   if_Hall = T 
+   ion_inertial_length = 0.2
+/
+"""
+
+
+def test_namelist_parser_reads_the_shipped_input_syntax(tmp_path):
+    p = tmp_path / "mhd.input"
+    p.write_text(INPUT)
+    nl = lapsio.read_namelists(str(p))
+    assert nl["genr"] == {"tmax": 100.0, "dtout": 0.5, "dtrms": 0.2}
+    assert nl["pert"] == {"ipert": 7, "db0": 0.1, "dv0": 0.1, "drho0": 0.01, "nmodex": 2}
+    assert nl["phys"]["if_resis"] is True and nl["phys"]["if_visc"] is True and nl["hall"]["if_hall"] is True
+    kw = params_from_namelists(nl)
+    assert kw["nx"] == 16 and kw["if_AEB"] is True and kw["Ur0"] == 1.167 and kw["dealias_option"] == 1
+    assert kw["afx"] == 0.495 and kw["if_resis_exp"] is False          # module defaults (dealiasing.f90:10)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import build_emu
+    return build_emu.build()
+
+
+def test_driver_loop_files_and_restart_on_the_emulator(emu, tmp_path):
+    """The Principal loop against the oracle driven the same way, the files it leaves, and a restart from
+    one of its own outNNN.dat files (restart.f90:17-63)."""
+    (tmp_path / "mhd.input").write_text(INPUT)
+    d = Driver(str(tmp_path / "mhd.input"), str(tmp_path), lib_path=emu)
+    prim0 = d.initial_primitive()
+    nsteps = d.run(max_steps=3, echo=False)
+    assert nsteps == 3
+    # oracle, same sequencing (mhd.f90:244-248,285)
+    p = lo.Params(**{k: v for k, v in d.kw.items() if k not in ("rank", "nranks", "device")})
+    o = lo.State(p)
+    o.set_primitive(prim0)
+    o.vardt()
+    for i in range(3):
+        o.evolve()
+        o.time += o.dt
+        o.evolve_radius(o.time)
+        if i < 2:
+            o.vardt()
+    assert abs(d.time - o.time) < 1e-12
+    # dtout = 0.5 < 3 steps of ~0.8: out000 (t=0), out001 (after step 1), out002, and the final one
+    names = sorted(f for f in os.listdir(tmp_path) if f.startswith("out"))
+    assert names[0] == "out000.dat" and len(names) >= 2
+    last = str(tmp_path / names[-1])
+    assert abs(lapsio.read_out_header(last) - np.float32(o.time)) < 1e-6
+    data = lapsio.read_out_slab(last, 16, 16, 16)
+    ref = lo.primitive_of(o)
+    for v in range(8):
+        assert pc.rel_l2(data[v], ref[v]) < 1e-10, v
+    first = lapsio.read_out_slab(str(tmp_path / "out000.dat"), 16, 16, 16)
+    assert pc.rel_l2(first, prim0) < 1e-13                                 # primitives round-trip through uu_prim
+    rms = np.loadtxt(tmp_path / "rms.dat")
+    ebm = np.loadtxt(tmp_path / "EBM_info.dat")
+    assert rms.shape[1] == 20 and ebm.shape[1] == 3 and rms.shape[0] == ebm.shape[0] >= 2
+    assert abs(ebm[-1, 1] - (30.0 + 1.167 * d.time)) < 1e-6 and ebm[0, 2] == 1.167
+    assert os.path.exists(tmp_path / "grid.dat") and os.path.exists(tmp_path / "log")
+    assert "Iterations     :       3" in (tmp_path / "log").read_text()
+    d.solver.close()
+    # restart from the last file
+    n = int(names[-1][3:6])
+    (tmp_path / "mhd.input").write_text(INPUT.replace("dtrms = 0.2", "dtrms = 0.2\n   if_restart = T\n   n_start = %d" % n))
+    r = Driver(str(tmp_path / "mhd.input"), str(tmp_path), lib_path=emu)
+    assert r.if_restart and r.n_start == n
+    r.run(max_steps=1, echo=False)
+    assert r.time > o.time and r.istep == 1
+    assert os.path.exists(tmp_path / lapsio.out_name(n + 1))
+    r.solver.close()
