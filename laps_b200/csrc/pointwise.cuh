@@ -25,6 +25,62 @@ LAPS_D Prim prim_of(double rho, double mx, double my, double mz, double bx, doub
   return q;
 }
 
+// ------------------------------------------------------------------ block reductions
+template <class Op>
+LAPS_D double block_reduce(double v, Op op, double* scratch /* >= 32 doubles */) {
+  LAPS_UNROLL
+  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  double r = scratch[0];
+  for (int i = 1; i < nw; ++i) r = op(r, scratch[i]);
+  return r;
+}
+struct OpSum { LAPS_D double operator()(double a, double b) const { return a + b; } };
+struct OpMin { LAPS_D double operator()(double a, double b) const { return a < b ? a : b; } };
+struct OpMax { LAPS_D double operator()(double a, double b) const { return a > b ? a : b; } };
+
+struct CflParams {
+  const double* uu; size_t npts;
+  double gamma, di;
+  double dmin;            // min(dx,dy,dz) (mhd.f90:398); min(dx,dy) in the 2D tree (2D/mhd.f90:369)
+  double floor_x, floor_y; // resistivity/dx, resistivity/dy of the 2D tree's explicit-resistivity limit (2D/mhd.f90:361-364), else 0
+  int hall;
+  double* partial;  // [gridDim.x]
+};
+
+// Signal speeds of one point along x, y, z, folded into best[] (mhd.f90:352-416; see k_cfl for why the
+// slow-mode candidates are absent and why maxima are reduced instead of minima of dx/c).
+LAPS_D void cfl_point(const CflParams& P, double rho, double Bx, double By, double Bz, const Prim& q, double (&best)[3]) {
+  const double s2 = sqrt(2.0);
+  const double cs2 = P.gamma * q.p / rho;
+  const double sr = sqrt(rho);
+  const double ca[3] = {Bx / sr, By / sr, Bz / sr};
+  const double uvel[3] = {q.ux, q.uy, q.uz};
+  const double ca2 = ca[0] * ca[0] + ca[1] * ca[1] + ca[2] * ca[2];
+  const double cms2 = cs2 + ca2;
+  double chall = 0.0;
+  if (P.hall) chall = P.di / rho * fmax(fmax(Bx, By), Bz) / P.dmin;   // signed max, as mhd.f90:396-398
+  LAPS_UNROLL
+  for (int d = 0; d < 3; ++d) {
+    const double cns = sqrt(fmax(cms2 * cms2 - 4 * cs2 * ca[d] * ca[d], 0.0));
+    const double cf = sqrt(cms2 + cns) / s2;
+    const double uu_ = uvel[d];
+    double c = fabs(uu_ + cf);
+    c = fmax(c, fabs(uu_ + ca[d]));
+    c = fmax(c, fabs(uu_ - cf));
+    c = fmax(c, fabs(uu_ - ca[d]));
+    c = fmax(c, fabs(uu_));
+    if (d == 0) c = fmax(c, P.floor_x);
+    if (d == 1) c = fmax(c, P.floor_y);
+    if (P.hall) c = fmax(c, chall);
+    best[d] = fmax(best[d], c);
+  }
+}
+
 struct FluxParams {
   const double* uu;     // [8][npts]
   const double* J;      // [3][npts] (Hall) or null
@@ -36,17 +92,21 @@ struct FluxParams {
   double gamma, di, tau;
   int z_radial;         // 2D tree, radial direction along z (2D/mhdrhs.f90:96-100)
   int slot[19];         // field slot of each flux in F, < 0: not needed (the z fluxes of the 2D tree)
+  CflParams cfl;        // k_flux<true>: the CFL maxima of vardt are taken in the same sweep (same points, same primitives)
 };
 
 // 3 CTAs per SM (<= 85 registers): 11 loads + 19 stores per point want the occupancy (measured: 2 CTAs/SM cost 17 %)
-__global__ void __launch_bounds__(256, 3) k_flux(const FluxParams P) {
+template <bool CFL>
+__global__ void __launch_bounds__(256, CFL ? 2 : 3) k_flux(const FluxParams P) {
   const size_t n = P.npts;
   const double gm1 = P.gamma - 1.0;
+  double best[3] = {0.0, 0.0, 0.0};
   for (size_t ii = blockIdx.x * (size_t)blockDim.x + threadIdx.x; ii < P.count; ii += (size_t)gridDim.x * blockDim.x) {
     const size_t i = P.in_off + ii;
     const double rho = P.uu[i], mx = P.uu[n + i], my = P.uu[2 * n + i], mz = P.uu[3 * n + i];
     const double Bx = P.uu[4 * n + i], By = P.uu[5 * n + i], Bz = P.uu[6 * n + i], en = P.uu[7 * n + i];
     const Prim q = prim_of(rho, mx, my, mz, Bx, By, Bz, en, gm1);
+    if (CFL) cfl_point(P.cfl, rho, Bx, By, Bz, q, best);
     const double ux = q.ux, uy = q.uy, uz = q.uz, p = q.p;
     const double ptot = p + 0.5 * (Bx * Bx + By * By + Bz * Bz);
     const double udotb = ux * Bx + uy * By + uz * Bz;
@@ -90,6 +150,14 @@ __global__ void __launch_bounds__(256, 3) k_flux(const FluxParams P) {
     }
 #undef LAPS_PUT
   }
+  if (CFL) {
+    __shared__ double scratch[32];
+    LAPS_UNROLL
+    for (int d = 0; d < 3; ++d) {
+      const double r = block_reduce(best[d], OpMax(), scratch);
+      if (threadIdx.x == 0) P.cfl.partial[(size_t)d * gridDim.x + blockIdx.x] = r;
+    }
+  }
 }
 
 // in place: [rho,ux,uy,uz,bx,by,bz,p] -> [rho,rho u,B,e]
@@ -116,33 +184,6 @@ __global__ void __launch_bounds__(256) k_cons_to_prim(const double* uu, double* 
   }
 }
 
-// ------------------------------------------------------------------ block reductions
-template <class Op>
-LAPS_D double block_reduce(double v, Op op, double* scratch /* >= 32 doubles */) {
-  LAPS_UNROLL
-  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  __syncthreads();
-  if (lane == 0) scratch[w] = v;
-  __syncthreads();
-  const int nw = (blockDim.x + 31) >> 5;
-  double r = scratch[0];
-  for (int i = 1; i < nw; ++i) r = op(r, scratch[i]);
-  return r;
-}
-struct OpSum { LAPS_D double operator()(double a, double b) const { return a + b; } };
-struct OpMin { LAPS_D double operator()(double a, double b) const { return a < b ? a : b; } };
-struct OpMax { LAPS_D double operator()(double a, double b) const { return a > b ? a : b; } };
-
-struct CflParams {
-  const double* uu; size_t npts;
-  double gamma, di;
-  double dmin;            // min(dx,dy,dz) (mhd.f90:398); min(dx,dy) in the 2D tree (2D/mhd.f90:369)
-  double floor_x, floor_y; // resistivity/dx, resistivity/dy of the 2D tree's explicit-resistivity limit (2D/mhd.f90:361-364), else 0
-  int hall;
-  double* partial;  // [gridDim.x]
-};
-
 // mhd.f90:352-416.  partial[d][b] = max over the block's points of the signal speed along d.
 // The reference takes min over points of dx/cmax_x, dy/cmax_y*(R/R0), dz/cmax_z*(R/R0); a correctly
 // rounded division (and the product with R/R0) is monotonic, so min_i fl(dx/c_i) == fl(dx/max_i c_i)
@@ -152,36 +193,12 @@ struct CflParams {
 __global__ void __launch_bounds__(256) k_cfl(const CflParams P) {
   __shared__ double scratch[32];
   const size_t n = P.npts;
-  const double s2 = sqrt(2.0);
-  const double dmin = P.dmin;
   double best[3] = {0.0, 0.0, 0.0};
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const double rho = P.uu[i], mx = P.uu[n + i], my = P.uu[2 * n + i], mz = P.uu[3 * n + i];
     const double Bx = P.uu[4 * n + i], By = P.uu[5 * n + i], Bz = P.uu[6 * n + i], en = P.uu[7 * n + i];
     const Prim q = prim_of(rho, mx, my, mz, Bx, By, Bz, en, P.gamma - 1.0);
-    const double cs2 = P.gamma * q.p / rho;
-    const double sr = sqrt(rho);
-    const double ca[3] = {Bx / sr, By / sr, Bz / sr};
-    const double uvel[3] = {q.ux, q.uy, q.uz};
-    const double ca2 = ca[0] * ca[0] + ca[1] * ca[1] + ca[2] * ca[2];
-    const double cms2 = cs2 + ca2;
-    double chall = 0.0;
-    if (P.hall) chall = P.di / rho * fmax(fmax(Bx, By), Bz) / dmin;   // signed max, as mhd.f90:396-398
-    LAPS_UNROLL
-    for (int d = 0; d < 3; ++d) {
-      const double cns = sqrt(fmax(cms2 * cms2 - 4 * cs2 * ca[d] * ca[d], 0.0));
-      const double cf = sqrt(cms2 + cns) / s2;
-      const double uu_ = uvel[d];
-      double c = fabs(uu_ + cf);
-      c = fmax(c, fabs(uu_ + ca[d]));
-      c = fmax(c, fabs(uu_ - cf));
-      c = fmax(c, fabs(uu_ - ca[d]));
-      c = fmax(c, fabs(uu_));
-      if (d == 0) c = fmax(c, P.floor_x);
-      if (d == 1) c = fmax(c, P.floor_y);
-      if (P.hall) c = fmax(c, chall);
-      best[d] = fmax(best[d], c);
-    }
+    cfl_point(P, rho, Bx, By, Bz, q, best);
   }
   LAPS_UNROLL
   for (int d = 0; d < 3; ++d) {

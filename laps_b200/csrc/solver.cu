@@ -135,13 +135,18 @@ struct laps_solver {
   // being re-transformed.  Off with dealias_option 0, where the state keeps non-Hermitian Nyquist content that
   // the reference's real-space round trip would drop.
   bool mass_from_state = false;
+  // laps_step runs the dt-independent front half of the NEXT step's first stage (with the CFL sweep fused into
+  // calc_flux) before it returns: front_ready tells the next laps_evolve to skip it.  Anything that changes the
+  // state, the radius or the work buffers in between clears it.
+  bool front_ready = false;
+  int tune_spec = 1;     // LAPS_TUNE_SPEC=0: laps_step = evolve; set_time; vardt with the separate k_cfl sweep
   int tune_zchunk = 0;   // LAPS_TUNE_ZCHUNK: z planes per interleaved calc_flux / forward-x launch pair (0 = whole slab)
   int tune_fusex = -1;   // calc_flux fused into the forward x pass (LAPS_TUNE_FUSEX): -1 = library default, 0 = never, 1 = whenever possible (nx <= 512)
   int num_sms = 148;
   double da_thresh = 0;
   void* ipc_opened[LAPS_MAX_RANKS][3];   // mappings obtained with cudaIpcOpenMemHandle
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_scal = nullptr;
   int launches = 0;
   bool profiling = false;
   std::vector<ProfEntry> prof;
@@ -640,9 +645,24 @@ int stage_incomp(S* s, int irk) {
   return 0;
 }
 
-int stage(S* s, int irk) {
+int reduce_launch(S* s, int nrows, int op, double init);
+
+void fill_cfl_params(S* s, CflParams& c) {
   const laps_params& p = s->p;
-  if (s->incomp) return stage_incomp(s, irk);
+  c.uu = s->uu; c.npts = s->npts; c.gamma = p.adiabatic_index; c.di = p.ion_inertial_length;
+  const double dx = p.Lx / s->nx, dy = s->two_d ? p.Lz / s->nz : p.Ly / s->ny, dz = p.Lz / s->nz;
+  c.dmin = s->two_d ? std::min(dx, dy) : std::min(std::min(dx, dy), dz);
+  const bool rfloor = s->two_d && p.if_resis && p.if_resis_exp;      // 2D/mhd.f90:361-364
+  c.floor_x = rfloor ? p.resistivity / dx : 0.0;
+  c.floor_y = rfloor ? p.resistivity / dy : 0.0;
+  c.hall = p.if_hall; c.partial = s->d_partial;
+}
+
+// The part of a stage that does not depend on the time step: J refresh, calc_flux, forward x and y passes.
+// with_cfl: the CFL maxima of vardt (mhd.f90:352-416) are taken inside the calc_flux sweep (k_flux<true>) and
+// left in d_partial — used by laps_step, which runs this for the NEXT step before it knows the next dt.
+int stage_front(S* s, bool with_cfl) {
+  const laps_params& p = s->p;
   LAPS_TRY(refresh_current(s));
   if (use_fused_flux(s)) {  // calc_flux + the forward x pass in one kernel (flux_fwd_x.cuh), then the y pass
     FusedFluxParams fp;
@@ -671,7 +691,7 @@ int stage(S* s, int irk) {
       f.in_off = (size_t)z0 * plane; f.count = (size_t)nzc * plane;
       const unsigned gb = (unsigned)std::min<size_t>((size_t)s->nblk, (f.count + 255) / 256);
       ++s->launches;
-      LAPS_LAUNCH(k_flux, dim3(gb), dim3(256), 0, s->stream, f);
+      LAPS_LAUNCH(k_flux<false>, dim3(gb), dim3(256), 0, s->stream, f);
       LAPS_TRY(check_launch(s, "k_flux"));
       LAPS_TRY(fwd_x(s, buf_F(s), f.fstride, s->nf, buf_W1(s), true, z0, nzc, false));
     }
@@ -684,13 +704,32 @@ int stage(S* s, int irk) {
     f.hall = p.if_hall; f.aeb = p.if_AEB; f.gamma = p.adiabatic_index; f.di = p.ion_inertial_length; f.tau = s->tau;
     f.z_radial = s->two_d && p.if_z_radial;
     for (int j = 0; j < 19; ++j) f.slot[j] = s->fslot[j];
-    LaunchScope ls(s, "flux");
-    LAPS_LAUNCH(k_flux, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, f);
+    LaunchScope ls(s, with_cfl ? "flux+cfl" : "flux");
+    if (with_cfl) {
+      fill_cfl_params(s, f.cfl);
+      LAPS_LAUNCH(k_flux<true>, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, f);
+    } else {
+      LAPS_LAUNCH(k_flux<false>, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, f);
+    }
     LAPS_TRY(check_launch(s, "k_flux"));
   }
+  if (with_cfl) LAPS_TRY(reduce_launch(s, 3, 2, 0.0));   // the maxima travel to the host while the passes below run
   // transform_flux_real_to_fourier (mhdrhs.f90:128-172)
   LAPS_TRY(forward_xy(s, buf_F(s), s->npts, s->nf, true));
   }
+  return 0;
+}
+
+// The CFL sweep can ride on calc_flux only on the plain path (one k_flux launch over the whole slab).
+bool can_speculate(const S* s) {
+  return s->tune_spec && !s->incomp && !use_fused_flux(s) && !(s->tune_zchunk > 0 && !s->two_d);
+}
+
+int stage(S* s, int irk) {
+  const laps_params& p = s->p;
+  if (s->incomp) return stage_incomp(s, irk);
+  if (irk == 0 && s->front_ready) s->front_ready = false;   // laps_step has already run this stage's front half
+  else LAPS_TRY(stage_front(s, false));
   LAPS_TRY(host_barrier(s));
   {  // z-pass + calc_rhs + rkt + dealias + inverse z
     ZParams z; fill_zparams(s, z, true);
@@ -751,7 +790,9 @@ int stage(S* s, int irk) {
   return 0;
 }
 
-int reduce_final(S* s, int nrows, int op /*0 sum,1 min,2 max*/, double init) {
+// reduce_launch enqueues the final reduction (+ the inter-rank allreduce) and the copy of the scalars to the host,
+// reduce_wait blocks until that copy has landed (later launches in the stream keep the GPU busy meanwhile).
+int reduce_launch(S* s, int nrows, int op /*0 sum,1 min,2 max*/, double init) {
   LaunchScope ls(s, "reduce");
   if (op == 0) LAPS_LAUNCH((k_reduce_final<OpSum>), dim3((unsigned)nrows), dim3(256), 0, s->stream, s->d_partial, s->nblk, s->d_scal, init);
   if (op == 1) LAPS_LAUNCH((k_reduce_final<OpMin>), dim3((unsigned)nrows), dim3(256), 0, s->stream, s->d_partial, s->nblk, s->d_scal, init);
@@ -764,8 +805,16 @@ int reduce_final(S* s, int nrows, int op /*0 sum,1 min,2 max*/, double init) {
     LAPS_TRY(check_launch(s, "k_xchg_allreduce"));
   }
   LAPS_CK(s, cudaMemcpyAsync(s->h_scal, s->d_scal, nrows * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-  LAPS_CK(s, cudaStreamSynchronize(s->stream));
+  LAPS_CK(s, cudaEventRecord(s->ev_scal, s->stream));
   return 0;
+}
+int reduce_wait(S* s) {
+  LAPS_CK(s, cudaEventSynchronize(s->ev_scal));
+  return 0;
+}
+int reduce_final(S* s, int nrows, int op, double init) {
+  LAPS_TRY(reduce_launch(s, nrows, op, init));
+  return reduce_wait(s);
 }
 
 int require_state(S* s) {
@@ -868,6 +917,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
   if (const char* e = std::getenv("LAPS_TUNE_Z")) s->tune_z = std::atoi(e);
   if (const char* e = std::getenv("LAPS_TUNE_FUSEX")) s->tune_fusex = std::atoi(e);
   if (const char* e = std::getenv("LAPS_TUNE_ZCHUNK")) s->tune_zchunk = std::atoi(e);
+  if (const char* e = std::getenv("LAPS_TUNE_SPEC")) s->tune_spec = std::atoi(e);
   // The reference re-derives uu_fourier from the real fields at the start of every stage
   // (src_incompressible/mhd.f90:325).  For a spectrum the dealiasing has band-limited (options 1, 2: the
   // Nyquist planes are removed) that round trip is the identity up to round-off and is skipped; with
@@ -885,7 +935,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
   s->wnx = wave_numbers(s->nx, p.Lx); s->wny = wave_numbers(s->ny, p.Ly); s->wnz = wave_numbers(s->nz, p.Lz);
 
   if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
-  cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1);
+  cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1); cudaEventCreate(&s->ev_scal);
 
   const int nmax = s->nf > s->ni ? s->nf : s->ni;
   // largest per-rank slab sizes of the exchanged layouts (the last rank holds the remainder)
@@ -1014,6 +1064,7 @@ int laps_destroy(laps_handle s) {
   for (auto& pe : s->prof) { cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1); }
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->ev_scal) cudaEventDestroy(s->ev_scal);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
   return 0;
@@ -1043,6 +1094,7 @@ int laps_get_stream(laps_handle s, void** stream_out) {
 
 int laps_set_primitive(laps_handle s, const double* uu_local) {
   if (!s || !uu_local) return 1;
+  s->front_ready = false;
   LAPS_CK(s, cudaMemcpyAsync(s->uu, uu_local, 8 * s->npts * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   {
     LaunchScope ls(s, "prim_to_cons");
@@ -1060,6 +1112,7 @@ int laps_set_primitive(laps_handle s, const double* uu_local) {
 
 int laps_set_time(laps_handle s, double time) {  // AEBmod.f90:56-73
   if (!s) return 1;
+  s->front_ready = false;
   const double old = s->radius;
   s->radius = s->p.radius0 + s->Ur * time;
   aeb_calc(s);
@@ -1081,25 +1134,10 @@ int laps_rkt_init(laps_handle s, double dt) {  // rktmod.f90:15-32 (fnl_rk is ne
   return 0;
 }
 
-int laps_vardt(laps_handle s, double* dt_inout) {  // mhd.f90:328-429
-  if (!s || !dt_inout) return 1;
-  LAPS_TRY(require_state(s));
+// dt from the three global maxima in h_scal (mhd.f90:404-428), hysteresis, rkt_init
+static int vardt_finish(laps_handle s, double* dt_inout) {
   const laps_params& p = s->p;
-  CflParams c;
-  c.uu = s->uu; c.npts = s->npts; c.gamma = p.adiabatic_index; c.di = p.ion_inertial_length;
   const double dx = p.Lx / s->nx, dy = s->two_d ? p.Lz / s->nz : p.Ly / s->ny, dz = p.Lz / s->nz;
-  c.dmin = s->two_d ? std::min(dx, dy) : std::min(std::min(dx, dy), dz);
-  const bool rfloor = s->two_d && p.if_resis && p.if_resis_exp;      // 2D/mhd.f90:361-364
-  c.floor_x = rfloor ? p.resistivity / dx : 0.0;
-  c.floor_y = rfloor ? p.resistivity / dy : 0.0;
-  c.hall = p.if_hall; c.partial = s->d_partial;
-  {
-    LaunchScope ls(s, "cfl");
-    if (s->incomp) LAPS_LAUNCH(k_cfl_incomp, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, c);   // src_incompressible/mhd.f90:369-476
-    else LAPS_LAUNCH(k_cfl, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, c);
-    LAPS_TRY(check_launch(s, "k_cfl"));
-  }
-  LAPS_TRY(reduce_final(s, 3, 2, 0.0));   // global maxima of the three signal speeds (mhd.f90:419 as max)
   const double rr = s->radius / p.radius0;
   double dtmin;
   if (s->two_d) {                          // 2D/mhd.f90:375-381
@@ -1120,6 +1158,21 @@ int laps_vardt(laps_handle s, double* dt_inout) {  // mhd.f90:328-429
   } else if (dt < 0.98 * dtmin || dt > 1.02 * dtmin) dt = dtmin;
   *dt_inout = dt;
   return laps_rkt_init(s, dt);
+}
+
+int laps_vardt(laps_handle s, double* dt_inout) {  // mhd.f90:328-429
+  if (!s || !dt_inout) return 1;
+  LAPS_TRY(require_state(s));
+  CflParams c;
+  fill_cfl_params(s, c);
+  {
+    LaunchScope ls(s, "cfl");
+    if (s->incomp) LAPS_LAUNCH(k_cfl_incomp, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, c);   // src_incompressible/mhd.f90:369-476
+    else LAPS_LAUNCH(k_cfl, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, c);
+    LAPS_TRY(check_launch(s, "k_cfl"));
+  }
+  LAPS_TRY(reduce_final(s, 3, 2, 0.0));   // global maxima of the three signal speeds (mhd.f90:419 as max)
+  return vardt_finish(s, dt_inout);
 }
 
 int laps_evolve(laps_handle s) {  // mhd.f90:298-326
@@ -1145,7 +1198,14 @@ int laps_step(laps_handle s, double* time_inout, double* dt_inout) {  // mhd.f90
   *time_inout = *time_inout + s->dt;
   LAPS_TRY(laps_set_time(s, *time_inout));
   *dt_inout = s->dt;
-  return laps_vardt(s, dt_inout);
+  if (!can_speculate(s)) return laps_vardt(s, dt_inout);
+  // vardt reads the same state as the next step's calc_flux: one sweep serves both.  The launches below are the
+  // dt-independent front half of the next step's first stage; the host waits only for the three maxima.
+  LAPS_TRY(stage_front(s, true));
+  LAPS_CK(s, cudaEventRecord(s->ev1, s->stream));   // laps_last_step_ms: this step's evolve + the next step's front half
+  LAPS_TRY(reduce_wait(s));
+  s->front_ready = true;
+  return vardt_finish(s, dt_inout);
 }
 
 int laps_last_step_ms(laps_handle s, float* ms, int32_t* launches) {
@@ -1227,6 +1287,7 @@ int laps_max_div_real(laps_handle s, double out[2]) {
   if (!s || !out) return 1;
   LAPS_TRY(require_state(s));
   if (s->two_d) { s->err = "laps_max_div_real: 3D trees only"; return 1; }
+  s->front_ready = false;   // the work buffers are used as scratch
   const bool prune = !s->spectrum_full;
   ZParams z; fill_zparams(s, z, prune);
   z.u_in = s->uA;
@@ -1355,6 +1416,7 @@ int laps_get_spectral(laps_handle s, double* out) {
 int laps_fft_forward(laps_handle s, const double* real_fields, int32_t nfields, double* spec_out) {
   if (!s || !real_fields || !spec_out) return 1;
   if (nfields < 1 || nfields > 8) { s->err = "laps_fft_forward: 1..8 fields per call"; return 1; }
+  s->front_ready = false;   // the work buffers are used as scratch
   // uses the flux work buffers and u_B as scratch; the state (u_A, uu) is untouched
   LAPS_CK(s, cudaMemcpyAsync(buf_F(s), real_fields, (size_t)nfields * s->npts * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   LAPS_TRY(forward_xy(s, buf_F(s), s->npts, nfields, false));
@@ -1377,6 +1439,7 @@ int laps_fft_forward(laps_handle s, const double* real_fields, int32_t nfields, 
 int laps_fft_inverse(laps_handle s, const double* spec_in, int32_t nfields, double* real_out) {
   if (!s || !spec_in || !real_out) return 1;
   if (nfields < 1 || nfields > 8) { s->err = "laps_fft_inverse: 1..8 fields per call"; return 1; }
+  s->front_ready = false;   // the work buffers are used as scratch
   LAPS_CK(s, cudaMemcpyAsync(s->uB, spec_in, (size_t)nfields * s->csz * sizeof(cplx), cudaMemcpyHostToDevice, s->stream));
   ZParams z; fill_zparams(s, z);
   z.u_in = s->uB;

@@ -75,6 +75,40 @@ def test_fused_flux_forward_x_pass_matches_the_separate_kernels(emu, monkeypatch
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
 
 
+@pytest.mark.parametrize("shape,kw", [((32, 16, 16), dict(hall=True, aeb=True, dealias=1)),
+                                      ((32, 16), dict(hall=True, aeb=True, z_radial=True, dealias=3))])
+def test_speculative_front_half_is_bit_identical(emu, monkeypatch, shape, kw):
+    """laps_step runs the next step's dt-independent front half with the CFL sweep fused into calc_flux
+    (k_flux<true>); the state and dt must equal evolve; set_time; vardt bit for bit, also when calls that use the
+    work buffers or move the radius come in between."""
+    p, prim = (pc.make_case_2d(*shape, **kw) if len(shape) == 2 else pc.make_case(*shape, **kw))
+    out = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("LAPS_TUNE_SPEC", flag)
+        o, g = pc.run_both(p, prim, 2, lib_path=emu)
+        g.fft_forward(np.ones((1,) + g.real_shape))     # clobbers the work buffers: the front half must be redone
+        g.step(); o.step()
+        g.evolve_radius(g.time)                          # same radius again: still consistent
+        g.step(); o.step()
+        g.get_output(); g.calc_rms(); g.calc_max_divB()  # read-only calls keep the speculative front valid
+        g.step(); o.step()
+        pc.check_state(o, g, 1e-11)
+        out.append((g.get_state()[0], g.uu_fourier(), g.dt))
+        g.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and out[0][2] == out[1][2]
+
+
+def test_get_output_is_the_array_output_uu_writes(emu):
+    p, prim = pc.make_case(16, 16, 16, hall=True, aeb=True)
+    o, g = pc.run_both(p, prim, 1, lib_path=emu)
+    uu, pr = g.get_state()
+    out = g.get_output(True)
+    assert np.array_equal(out[0], uu[0]) and np.array_equal(out[1:4], pr[0:3]) and np.array_equal(out[4:7], uu[4:7])
+    assert np.array_equal(out[7], pr[3]) and np.array_equal(g.get_output(False), uu)
+    assert pc.rel_l2(out, lo.primitive_of(o)) < 1e-11
+    g.close()
+
+
 def test_mask_pruning_is_bit_exact(emu):
     pc.check_pruning_is_exact((32, 16, 32), 2, lib_path=emu, hall=True, aeb=True, dealias=1)
     pc.check_pruning_is_exact((32, 32), 2, lib_path=emu, hall=True, aeb=True, dealias=3)

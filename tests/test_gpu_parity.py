@@ -57,6 +57,22 @@ def test_fused_and_separate_flux_x_pass_parity_128(flag, monkeypatch):
     g.close()
 
 
+@pytest.mark.parametrize("env", [dict(LAPS_TUNE_SPEC="0"), dict(LAPS_TUNE_MASS="0"), dict(LAPS_TUNE_SYM="0"),
+                                 dict(LAPS_TUNE_MASS="0", LAPS_TUNE_SYM="0", LAPS_TUNE_SPEC="0", LAPS_TUNE_PRUNE="0"),
+                                 dict(LAPS_TUNE_ZCHUNK="3")])
+def test_work_skipping_switched_off_parity_64(env, monkeypatch):
+    """Every exact work-skipping device (continuity row from the state, symmetric flux tensor, speculative front
+    half with the fused CFL sweep, mask pruning) switched off in turn: the reference's own operation count
+    (19 forward transforms, separate vardt sweep) must give the same parity against the oracle."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    p, prim = pc.make_case(64, 64, 64, hall=True, aeb=True, dealias=1)
+    o, g = pc.run_both(p, prim, 2)
+    pc.check_state(o, g, 1e-11)
+    pc.check_diagnostics(o, g, 1e-9)
+    g.close()
+
+
 def test_mask_pruning_is_bit_exact():
     pc.check_pruning_is_exact((64, 64, 64), 3, hall=True, aeb=True, dealias=1)
     pc.check_pruning_is_exact((128, 64), 3, hall=True, aeb=True, dealias=3)
