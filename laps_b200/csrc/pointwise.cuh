@@ -353,6 +353,8 @@ __global__ void __launch_bounds__(256) k_cfl_incomp(const CflParams P) {
       const double ca = P.uu[(size_t)(4 + d) * n + i] / sr;
       const double u = P.uu[(size_t)(1 + d) * n + i] / rho;
       double c = fmax(fmax(fabs(u + ca), fabs(u - ca)), fabs(u));
+      if (d == 0) c = fmax(c, P.floor_x);   // explicit-resistivity limit of the 2D tree (src_incompressible/2D/mhd.f90:436-439)
+      if (d == 1) c = fmax(c, P.floor_y);
       if (P.hall) c = fmax(c, chall);
       best[d] = fmax(best[d], c);
     }

@@ -629,9 +629,15 @@ int stage_incomp(S* s, int irk) {
     // projection rows: rho u, p, rho (slots 0-2 = Fp)
     LAPS_TRY(incomp_z(s, z));
     // dB/dt = curl E (mhdrhs.f90:175-181), slots 3-5 = E
-    z.task[0] = rhs_task(4, 4, -1, 0.0, 5, 1.0, -1, 0.0, -1.0, 4, +1.0);
-    z.task[1] = rhs_task(5, 5, 5, 1.0, -1, 0.0, -1, 0.0, +1.0, 3, -1.0);
-    z.task[2] = rhs_task(6, 6, 4, -1.0, 3, 1.0, -1, 0.0, +1.0, -1, 0.0);
+    if (!s->two_d) {
+      z.task[0] = rhs_task(4, 4, -1, 0.0, 5, 1.0, -1, 0.0, -1.0, 4, +1.0);
+      z.task[1] = rhs_task(5, 5, 5, 1.0, -1, 0.0, -1, 0.0, +1.0, 3, -1.0);
+      z.task[2] = rhs_task(6, 6, 4, -1.0, 3, 1.0, -1, 0.0, +1.0, -1, 0.0);
+    } else {   // kz = 0 (2D/mhdrhs.f90:228-233): fnl5 = -ky Ez ; fnl6 = kx Ez ; fnl7 = ky Ex - kx Ey; ky rides the line axis
+      z.task[0] = rhs_task(4, 4, -1, 0.0, -1, 0.0, -1, 0.0, -1.0, 5, -1.0);
+      z.task[1] = rhs_task(5, 5, 5, 1.0, -1, 0.0, -1, 0.0, +1.0, -1, 0.0);
+      z.task[2] = rhs_task(6, 6, 4, -1.0, -1, 0.0, -1, 0.0, +1.0, 3, +1.0);
+    }
     LAPS_TRY(spec_z(s, z, 3, "spec_z"));
   }
   LAPS_TRY(host_barrier(s));
@@ -855,7 +861,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
     p.if_z_radial = 0; p.if_limit_dt_increase = 0;
   }
   if (u.incompressible) {
-    if (two_d) { g_create_error = "the incompressible tree is 3D only here (src_incompressible/2D is not built)"; return 1; }
+    if (two_d && u.if_z_radial) { g_create_error = "if_z_radial does not exist in src_incompressible/2D"; return 1; }
     if (!(u.rho0 > 0.0)) { g_create_error = "incompressible: rho0 must be positive (mhdinit.f90:15)"; return 1; }
   }
   if (p.nranks < 1 || p.nranks > LAPS_MAX_RANKS || p.rank < 0 || p.rank >= p.nranks) {
@@ -1286,7 +1292,6 @@ int laps_max_divv(laps_handle s, double* out) {  // src_incompressible/mhd.f90:6
 int laps_max_div_real(laps_handle s, double out[2]) {
   if (!s || !out) return 1;
   LAPS_TRY(require_state(s));
-  if (s->two_d) { s->err = "laps_max_div_real: 3D trees only"; return 1; }
   s->front_ready = false;   // the work buffers are used as scratch
   const bool prune = !s->spectrum_full;
   ZParams z; fill_zparams(s, z, prune);
@@ -1302,8 +1307,8 @@ int laps_max_div_real(laps_handle s, double out[2]) {
   // the two real fields land in the flux work area (free between stages)
   RealDst d; std::memset(&d, 0, sizeof(d));
   d.ptr[0] = buf_F(s) + (size_t)(s->nf - 2) * s->npts; d.ptr[1] = buf_F(s) + (size_t)(s->nf - 1) * s->npts;
-  LAPS_TRY(inv_y(s, buf_V1(s), buf_V2(s), 2, prune));
-  LAPS_TRY(inv_x(s, buf_V2(s), d, 2, prune));
+  if (!s->two_d) LAPS_TRY(inv_y(s, buf_V1(s), buf_V2(s), 2, prune));
+  LAPS_TRY(inv_x(s, s->two_d ? buf_V1(s) : buf_V2(s), d, 2, prune));
   (void)vs;
   {
     LaunchScope ls(s, "absmax");

@@ -62,7 +62,7 @@ k_incomp_z(const ZParams P) {
     kye = __ddiv_rn(__dmul_rn(__dadd_rn(__dmul_rn(-kxr, P.sina), __dmul_rn(kyr, P.cosa)), P.radius0), P.radius);
   }
   const double ksq_xy = ksq_xy_eval(P, kxr, kyr, kx, ky);
-  const double dxy = (P.dealias_option == 1) ? __dadd_rn(__ldg(P.dax + kx), __ldg(P.day + ky))
+  const double dxy = (P.dealias_option == 1 || P.dealias_option == 3) ? __dadd_rn(__ldg(P.dax + kx), __ldg(P.day + ky))
                                              : ((P.dealias_option == 2) ? __ldg(P.dax + kx) : 0.0);
   const double dfy = (P.dealias_option == 2) ? __ldg(P.day + ky) : 0.0;
 
@@ -86,17 +86,19 @@ k_incomp_z(const ZParams P) {
   LAPS_UNROLL
   for (int e = 0; e < 8; ++e) {
     const int kz = FF::kout(u, e);
-    const double kzz = __ldg(P.kze + kz);
+    // 2D tree (src_incompressible/2D/mhdrhs.f90:189): the line axis carries the reference's ky, kz = 0
+    const double kl = __ldg(P.kze + kz);
+    const double kyy = P.mode2d ? kl : kye, kzz = P.mode2d ? 0.0 : kl;
     const double k2 = __dadd_rn(ksq_xy, __ldg(P.ksq_z + kz));
     const cplx f1 = S0[e * G::NT + u], f2 = S1[e * G::NT + u], f3 = cscale(r[e], P.scale);
-    const cplx sum = cadd(cadd(cmul_i(f1, kxe), cmul_i(f2, kye)), cmul_i(f3, kzz));
+    const cplx sum = cadd(cadd(cmul_i(f1, kxe), cmul_i(f2, kyy)), cmul_i(f3, kzz));
     if (k2 < 1e-10) {   // "background field, not important in Fourier space" (mhdrhs.f90:155-159,505-508)
       S0[e * G::NT + u] = mk(0.0, 0.0); S1[e * G::NT + u] = mk(0.0, 0.0); S2[e * G::NT + u] = mk(0.0, 0.0);
       r[e] = mk(0.0, 0.0);
     } else {
       const cplx kd = mk(__ddiv_rn(sum.x, k2), __ddiv_rn(sum.y, k2));
       S0[e * G::NT + u] = cadd(f1, cmul_i(kd, kxe));
-      S1[e * G::NT + u] = cadd(f2, cmul_i(kd, kye));
+      S1[e * G::NT + u] = cadd(f2, cmul_i(kd, kyy));
       S2[e * G::NT + u] = cadd(f3, cmul_i(kd, kzz));
       r[e] = mk(-kd.x, -kd.y);   // p^
     }
@@ -147,6 +149,8 @@ k_incomp_z(const ZParams P) {
       } else if (P.dealias_option == 2) {
         const double fz = __ldg(P.daz + kz);
         un = mk(__dmul_rn(__dmul_rn(__dmul_rn(un.x, dxy), dfy), fz), __dmul_rn(__dmul_rn(__dmul_rn(un.y, dxy), dfy), fz));
+      } else if (P.dealias_option == 3) {   // square truncation (2D/dealiasing.f90:99-114): per-axis flags
+        if (dxy != 0.0 || __ldg(P.daz + kz) != 0.0) un = mk(0.0, 0.0);
       }
       if (live) P.u_out[voff + kz] = un;
       r[e] = un;

@@ -344,7 +344,9 @@ k_spec_z(const ZParams P) {
     LAPS_UNROLL
     for (int e = 0; e < 8; ++e) {
       const int kz = u + e * G::NT;
-      const double ka = K.jcomp == 0 ? kxe : (K.jcomp == 1 ? kye : __ldg(P.kze + kz));
+      // 2D trees: the line axis carries the reference's ky and kz = 0 (src_incompressible/2D/mhdrhs.f90:396)
+      const double kzz = __ldg(P.kze + kz);
+      const double ka = K.jcomp == 0 ? kxe : (K.jcomp == 1 ? (P.mode2d ? kzz : kye) : (P.mode2d ? 0.0 : kzz));
       const cplx t = cmul_i(live ? U[kz] : mk(0.0, 0.0), ka);
       r[e] = mk(__ddiv_rn(t.x, K.cx), __ddiv_rn(t.y, K.cx));
     }
@@ -356,7 +358,8 @@ k_spec_z(const ZParams P) {
       const cplx a = live ? U[kz] : mk(0.0, 0.0);
       const cplx b = live ? U[P.fstride + kz] : mk(0.0, 0.0);
       const cplx c = live ? U[2 * P.fstride + kz] : mk(0.0, 0.0);
-      const cplx t = cadd(cadd(cmul_i(a, kxe), cmul_i(b, kye)), cmul_i(c, __ldg(P.kze + kz)));
+      const double kzz = __ldg(P.kze + kz);
+      const cplx t = cadd(cadd(cmul_i(a, kxe), cmul_i(b, P.mode2d ? kzz : kye)), cmul_i(c, P.mode2d ? 0.0 : kzz));
       r[e] = mk(__ddiv_rn(t.x, K.cx), __ddiv_rn(t.y, K.cx));
     }
   } else {  // kZCurrent: J^ = i k x B^ (mhdrhs.f90:329-336) from the updated state

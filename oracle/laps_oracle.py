@@ -831,6 +831,75 @@ class StateIncompressible(State):
         return np.array([e.sum() / n, (pr[0] * uu[4] + pr[1] * uu[5] + pr[2] * uu[6]).sum() / n, self.calc_max_divB()])
 
 
+class StateIncompressible2D(StateIncompressible):
+    """src_incompressible/2D/: the incompressible tree on an (nx, ny, 1) grid with kz = 0 (2D/mhdrhs.f90:189,
+    312,396,583).  All nine velocity gradients and three currents are still formed (the z derivatives are
+    transforms of zeros).  Wave vectors, k_square and dealiasing (incl. option 3) as in the compressible 2D
+    tree — the files differ only in names; vardt has its own two-direction form (2D/mhd.f90:380-478)."""
+
+    def __init__(self, p: Params, p0: float = 1.0):
+        assert p.nz == 1 and not p.if_z_radial
+        super().__init__(p, p0)
+        self.k_square = self.g.KX ** 2 + self.g.KY ** 2 + 0.0 * self.g.KZ
+
+    kvec = State2D.kvec
+    update_ksquare = State2D.update_ksquare
+    dealias = State2D.dealias
+
+    def calc_rhs(self, flux_fourier, fpf):
+        """2D/mhdrhs.f90:170-290: as the 3D routine; if_conserve_background skips every mode with ix == 1 (:268)."""
+        p = self.p
+        if not (p.if_resis and p.if_resis_exp and p.if_conserve_background):
+            return super().calc_rhs(flux_fourier, fpf)
+        q = dataclasses.replace(p, if_conserve_background=False)
+        self.p = q
+        try:
+            fnl = super().calc_rhs(flux_fourier, fpf)
+        finally:
+            self.p = p
+        ksq = np.broadcast_to(self.k_square, fnl[0].shape)
+        for v in (4, 5, 6):   # undo the resistive term where ix == 1
+            fnl[v][:, :, 0] = fnl[v][:, :, 0] + p.resistivity * self.uu_fourier[v][:, :, 0] * ksq[:, :, 0]
+        self.fnl = fnl
+        return fnl
+
+    def vardt(self):
+        """2D/mhd.f90:380-478."""
+        p, g = self.p, self.g
+        uu, pr = self.uu, self.uu_prim
+        sq = np.sqrt(uu[0])
+        cm = []
+        for d in range(2):
+            ca = uu[4 + d] / sq
+            u = pr[d]
+            cm.append(np.maximum(np.maximum(np.abs(u + ca), np.abs(u - ca)), np.abs(u)))
+        if p.if_resis and p.if_resis_exp:
+            cm[0] = np.maximum(cm[0], p.resistivity / g.dx)
+            cm[1] = np.maximum(cm[1], p.resistivity / g.dy)
+        if p.if_hall:
+            ch = p.ion_inertial_length / uu[0] * np.maximum(np.maximum(uu[4], uu[5]), uu[6]) / min(g.dx, g.dy)
+            cm = [np.maximum(c, ch) for c in cm]
+        with np.errstate(divide="ignore"):
+            dtx = g.dx / cm[0]
+            dty = g.dy / cm[1] * (self.radius / p.radius0)
+        dtmin = float(np.minimum(dtx, dty).min()) * p.cfl
+        if p.if_limit_dt_increase:
+            if self.dt == 0.0 or self.dt > 1.02 * dtmin:
+                self.dt = dtmin
+        elif self.dt < 0.98 * dtmin or self.dt > 1.02 * dtmin:
+            self.dt = dtmin
+        self.rkt_init(self.dt)
+        return self.dt
+
+    def step(self, calc_dt: bool = True):
+        """2D/mhd.f90:259-290: evolve; time+=dt; evolve_radius; vardt only every dstep_calcdt = 20 steps."""
+        self.evolve()
+        self.time = self.time + self.dt
+        self.evolve_radius(self.time)
+        if calc_dt:
+            self.vardt()
+
+
 # --------------------------------------------------------------------------------------
 # dealiasing tables (dealiasing.f90)
 # --------------------------------------------------------------------------------------

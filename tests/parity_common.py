@@ -67,7 +67,8 @@ def make_case_2d(nx, ny, hall=True, aeb=True, z_radial=False, dealias=1, visc=Tr
 def solver_kwargs(p: lo.Params):
     extra = dict(ndim=2, if_z_radial=p.if_z_radial, if_limit_dt_increase=p.if_limit_dt_increase) if p.nz == 1 else {}
     if p.incompressible:
-        extra = dict(incompressible=1, rho0=p.rho0)
+        extra = dict(extra, incompressible=1, rho0=p.rho0)
+        extra.pop("if_z_radial", None)
     return dict(**extra, **_solver_kwargs(p))
 
 
@@ -83,7 +84,7 @@ def _solver_kwargs(p: lo.Params):
 
 def oracle_state(p):
     if p.incompressible:
-        return lo.StateIncompressible(p)
+        return lo.StateIncompressible2D(p) if p.nz == 1 else lo.StateIncompressible(p)
     return lo.State2D(p) if p.nz == 1 else lo.State(p)
 
 
@@ -91,6 +92,14 @@ def make_case_incompressible(nx, ny, nz, rho0=1.0, **kw):
     """BASELINE config 3 family (src_incompressible): the turbulence case of make_case run through the
     incompressible tree (uu(8) = pressure); drho0 = 0.01 keeps rho non-uniform, which the tree allows."""
     p, prim = make_case(nx, ny, nz, **kw)
+    p.incompressible = True
+    p.rho0 = rho0
+    return p, prim
+
+
+def make_case_incompressible_2d(nx, ny, rho0=1.0, **kw):
+    """src_incompressible/2D: the smooth 2D data of make_case_2d run through the incompressible tree."""
+    p, prim = make_case_2d(nx, ny, **kw)
     p.incompressible = True
     p.rho0 = rho0
     return p, prim

@@ -109,6 +109,21 @@ def test_get_output_is_the_array_output_uu_writes(emu):
     g.close()
 
 
+@pytest.mark.parametrize("kw", [dict(hall=True, aeb=True, dealias=3), dict(hall=False, aeb=False, dealias=2, explicit=True, conserve_bg=True, limit_dt=True),
+                                dict(hall=True, aeb=False, dealias=0)])
+def test_one_step_incompressible_2d_tree(emu, kw):
+    """src_incompressible/2D: kz = 0, the line axis carries ky in the projection, gradient and divergence tasks."""
+    p, prim = pc.make_case_incompressible_2d(32, 16, **kw)
+    o, g = pc.run_both(p, prim, 2, lib_path=emu)
+    pc.check_state(o, g, 1e-11)
+    pc.check_diagnostics(o, g, 1e-9)
+    assert abs(g.calc_max_divV() - o.calc_max_divV()) <= 1e-9 * o.calc_max_divV()
+    db, dv = g.calc_max_div_real()
+    odb, odv = o.calc_max_div_real()
+    assert abs(dv - odv) <= 1e-9 * odv and abs(db - odb) <= 1e-9 * odb
+    g.close()
+
+
 def test_mask_pruning_is_bit_exact(emu):
     pc.check_pruning_is_exact((32, 16, 32), 2, lib_path=emu, hall=True, aeb=True, dealias=1)
     pc.check_pruning_is_exact((32, 32), 2, lib_path=emu, hall=True, aeb=True, dealias=3)

@@ -127,6 +127,21 @@ def test_incompressible_tree_parity_64(name, kw):
     g.close()
 
 
+@pytest.mark.parametrize("name,kw", [("hall_aeb_square", dict(hall=True, aeb=True, dealias=3)),
+                                     ("filter_explicit", dict(hall=False, aeb=False, dealias=2, explicit=True, conserve_bg=True, limit_dt=True)),
+                                     ("retransform", dict(hall=True, aeb=False, dealias=0))])
+def test_incompressible_2d_tree_parity(name, kw):
+    """src_incompressible/2D at 256 x 128, two steps, against the oracle."""
+    p, prim = pc.make_case_incompressible_2d(256, 128, **kw)
+    o, g = pc.run_both(p, prim, 2)
+    pc.check_state(o, g, 1e-11)
+    pc.check_diagnostics(o, g, 1e-9)
+    db, dv = g.calc_max_div_real()
+    odb, odv = o.calc_max_div_real()
+    assert abs(dv - odv) <= 1e-9 * odv and abs(db - odb) <= 1e-9 * odb
+    g.close()
+
+
 def test_incompressible_tree_256_properties():
     """BASELINE config 3 at full size (256^3 decaying turbulence, no expansion, no Hall): the projection keeps
     div(rho u) fixed, the k=0 mode of rho u and B is conserved bit-exactly, div B stays at round-off."""

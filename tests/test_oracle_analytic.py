@@ -374,3 +374,28 @@ def test_incompressible_k0_and_divergence_invariants():
     assert s.calc_max_divB() < 1e-15
     # div(rho u) of the initial data (non-uniform rho) only decays viscously
     assert 0.99 * dv0 < s.calc_max_divV() <= dv0 * (1 + 1e-12)
+
+
+def test_incompressible_2d_state_equals_a_z_uniform_3d_state():
+    """src_incompressible/2D is the 3D tree with kz = 0: one RK step of StateIncompressible2D must equal, bit for
+    bit, StateIncompressible on the same data repeated along z."""
+    p = lo.Params(nx=32, ny=16, nz=1, Lx=24.0, Ly=12.0, Lz=1.0, dealias_option=1, incompressible=True, if_hall=True,
+                  ion_inertial_length=0.2, if_AEB=True, Ur0=1.167, if_resis=True, resistivity=1e-4, if_visc=True, viscosity=1e-4)
+    rng = np.random.default_rng(5)
+    x = 2 * np.pi * np.arange(32) / 32
+    y = 2 * np.pi * np.arange(16) / 16
+    Y, X = np.meshgrid(y, x, indexing="ij")
+    prim = np.zeros((8, 1, 16, 32))
+    for v, (mean, amp) in enumerate([(1.0, 0.01), (0, 0.1), (0, 0.1), (0, 0.1), (1.0, 0.1), (0, 0.1), (0.3, 0.1), (1.0, 0.02)]):
+        prim[v, 0] = mean + amp * (np.cos(X + 2 * Y + rng.uniform(0, 6)) + 0.5 * np.sin(2 * X - Y + rng.uniform(0, 6)))
+    a = lo.StateIncompressible2D(p)
+    a.set_primitive(prim)
+    p3 = lo.Params(**{**p.__dict__, "nz": 4})
+    b = lo.StateIncompressible(p3)
+    b.set_primitive(np.repeat(prim, 4, axis=1))
+    for s_ in (a, b):
+        s_.dt = 1e-2
+        s_.rkt_init(1e-2)
+        s_.evolve()
+    assert all(np.array_equal(a.uu[v][0], b.uu[v][2]) for v in range(8))
+    assert a.rho0 == b.rho0
