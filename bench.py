@@ -109,28 +109,31 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # algorithmic bytes per launch of each kernel; R, C in bytes per field
 # ------------------------------------------------------------------------------------------
-def kernel_bytes(name, R, C, nf, ni, hall, fx=1.0, fy=1.0, fyl=1.0, mass=False):
+def kernel_bytes(name, R, C, nf, ni, hall, fx=1.0, fcol=1.0, fmode=1.0, mass=False):
     """Algorithmic HBM bytes of one launch.  Pass launches carry their field
-    count in the name (fwd_x19, inv_y11, inv_y3 ...).  fx, fy = fractions of the kx columns / ky rows
-    that survive the dealiasing mask (the passes skip the rest exactly, laps_get_pruning); fyl = the
-    same for the ky rows this rank owns.  mass: the continuity row takes its fluxes from the state
-    (laps_get_field_counts) and runs inside the curl_b_inv_z launch instead of the spec_z one."""
-    rows = 7 if mass else 8
+    count in the name (fwd_x13, inv_y11, inv_y3 ...).  fx = fraction of the kx columns that survive
+    the dealiasing mask, fcol = fraction of this rank's (kx, ky) columns, fmode = fraction of its
+    (kx, ky, kz) modes (laps_get_pruning, laps_get_pruning_counts): the passes skip the rest exactly.
+    mass: the continuity row takes its fluxes from the state (laps_get_field_counts) and runs inside
+    the curl_b_inv_z launch instead of the spec_z one."""
     import re
+    rows = 7 if mass else 8
     m = re.fullmatch(r"(fwd_x|fwd_y|inv_y|inv_x)(\d+)", name)
     if m:
         k, n = m.group(1), int(m.group(2))
-        return {"fwd_x": n * R + n * C * fx, "fwd_y": n * C * fx + n * C * fx * fy,
-                "inv_y": n * C * fx * fy + n * C * fx, "inv_x": n * C * fx + n * R}[k]
+        return {"fwd_x": n * R + n * C * fx, "fwd_y": n * C * fx + n * C * fcol,
+                "inv_y": n * C * fcol + n * C * fx, "inv_x": n * C * fx + n * R}[k]
+    flux = (8 + (3 if hall else 0)) * R + nf * R
     table = {
-        "flux": (8 + (3 if hall else 0)) * R + nf * R,
+        "flux": flux,
+        "flux+cfl": flux,
         # calc_flux fused into the forward x pass: reads uu (8R) + J (3R), writes nf half spectra
         "flux_fwd_x": (8 + (3 if hall else 0)) * R + nf * C * fx,
-        # reads nf flux spectra + u (rows C) + fnl_rk (rows C, stages 2,3), writes u (rows C) + fnl_rk (rows C, stages 1,2)
-        # + inverse-z output (rows C): averaged over the three stages
-        "spec_z": (nf + rows + rows * 2 / 3 + rows + rows * 2 / 3 + rows) * C * fx * fyl,
-        # J^ = ik x B^ (3C in, 3C out) + the continuity row (reads rho u, rho, fnl_rk: 4C + 2/3 C; writes rho, fnl_rk, inverse-z: 2C + 2/3 C)
-        "curl_b_inv_z": (3 * C + 3 * C + ((4 + 2 / 3 + 2 + 2 / 3) * C if mass else 0.0)) * fx * fyl,
+        # reads nf flux lines and writes `rows` inverse-z lines of every surviving column; reads u + fnl_rk (stages
+        # 2,3) and writes u + fnl_rk (stages 1,2) of the surviving modes only: averaged over the three stages
+        "spec_z": (nf + rows) * C * fcol + (rows + rows * 2 / 3 + rows + rows * 2 / 3) * C * fmode,
+        # J^ = ik x B^ (3 state reads, 3 lines out) + the continuity row (reads rho u, rho, fnl_rk; writes rho, fnl_rk, 1 line out)
+        "curl_b_inv_z": 3 * C * fmode + 3 * C * fcol + (((4 + 2 / 3 + 1 + 2 / 3) * C * fmode + C * fcol) if mass else 0.0),
         "fwd_z": 2 * 8 * C,
         "cfl": 8 * R,
     }
@@ -301,9 +304,12 @@ def run_gpu(args):
     nf, ni, rows = g.field_counts()
     hall = bool(kw["if_hall"])
     nkx, kymax, nkyl = g.pruning()
-    fx, fy, fyl = nkx / g.nxh, min(1.0, (2 * kymax + 1) / n), nkyl / g.nyl
+    live_cols, live_modes = g.pruning_counts()
+    fx = nkx / g.nxh
+    fcol = live_cols / float(g.nxh * g.nyl)
+    fmode = live_modes / float(g.nxh * g.nyl * n)
     mass = rows < 8
-    kb = lambda k: kernel_bytes(k, R, C, nf, ni, hall, fx, fy, fyl, mass)  # noqa: E731
+    kb = lambda k: kernel_bytes(k, R, C, nf, ni, hall, fx, fcol, fmode, mass)  # noqa: E731
     peak, peak_src = peaks()
     top = max(prof.items(), key=lambda kv: kv[1][0]) if prof else None
     roofline = None
@@ -319,7 +325,7 @@ def run_gpu(args):
                     "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
                     "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": b,
                     "per_kernel_GBps": {k: (kb(k) or 0) / (v[0] / v[1] * 1e-3) / 1e9 for k, v in prof.items() if kb(k)},
-                    "pruning": {"nkx": nkx, "nxh": g.nxh, "kymax": kymax, "ny": n, "nky_local": nkyl,
+                    "pruning": {"nkx": nkx, "nxh": g.nxh, "kymax": kymax, "ny": n, "nky_local": nkyl, "live_column_fraction": fcol, "live_mode_fraction": fmode,
                                 "what": "columns removed by the dealiasing mask are skipped exactly (bit-identical state)"},
                     "time_share": shares}
 

@@ -158,6 +158,11 @@ int laps_transpose_yz_indexmap(laps_handle h, int64_t* out);
  * unpruned computation (tests/…::test_mask_pruning_is_bit_exact).  *nky_local = this rank's surviving
  * ky rows.  No pruning: *nkx = nx/2+1, *kymax = ny/2, *nky_local = y_size. */
 int laps_get_pruning(laps_handle h, int32_t* nkx, int32_t* kymax, int32_t* nky_local);
+/* The same, finer: with the spherical mask of option 1 the surviving (kx, ky) columns of this rank lie inside a
+ * circle (*live_columns of nxh * y_size; the y and z passes visit only those), and inside a surviving column the
+ * z pass neither loads nor stores the state / RK-history entries of masked kz (*live_modes of nxh * y_size * nz
+ * are touched).  Bit-identical to the unpruned computation as well. */
+int laps_get_pruning_counts(laps_handle h, int64_t* live_columns, int64_t* live_modes);
 
 /* Fields transformed per RK stage: *nf forward (real fluxes -> spectra), *ni inverse (state + current density).
  * The reference transforms 18 (+1 with the expanding box) and 8 (+3 with the Hall term).  Here

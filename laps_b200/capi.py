@@ -61,7 +61,7 @@ SYMBOLS = [
     "laps_sync", "laps_get_stream", "laps_max_divb", "laps_rms", "laps_invariants", "laps_get_state", "laps_get_spectral",
     "laps_fft_forward", "laps_fft_inverse", "laps_transpose_yz_indexmap",
     "laps_last_step_ms", "laps_set_profiling", "laps_get_profile", "laps_get_pruning",
-    "laps_max_divv", "laps_max_div_real", "laps_get_rho0", "laps_get_field_counts", "laps_get_output",
+    "laps_max_divv", "laps_max_div_real", "laps_get_rho0", "laps_get_field_counts", "laps_get_output", "laps_get_pruning_counts",
 ]
 
 
@@ -115,6 +115,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.laps_last_step_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     lib.laps_get_pruning.argtypes = [H, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.laps_get_field_counts.argtypes = [H, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.laps_get_pruning_counts.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.laps_set_profiling.argtypes = [H, C.c_int32]
     lib.laps_get_profile.argtypes = [H, C.c_char_p, C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_int32)]
     for name in SYMBOLS:

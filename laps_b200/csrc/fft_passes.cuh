@@ -104,7 +104,7 @@ k_fwd_x(const double* __restrict__ in, size_t in_fstride, cplx* __restrict__ W1,
 template <int N, int TL>
 __global__ void __launch_bounds__(Tile<N, TL>::NTHREADS, Tile<N, TL>::MINB)
 k_fwd_y(const cplx* __restrict__ W1, PeerTable W2, int nzl, int nz, int zoff,
-        const cplx* __restrict__ tw, double scale, int nxh, int kymax) {
+        const cplx* __restrict__ tw, double scale, int nxh, int kymax_all, const int* __restrict__ kymax_x) {
   typedef Geom<N> G;
   typedef Fft<N, -1> F;
   typedef Tile<N, TL> T;
@@ -114,6 +114,9 @@ k_fwd_y(const cplx* __restrict__ W1, PeerTable W2, int nzl, int nz, int zoff,
   const int kx = blockIdx.x / ztiles;
   const int z0 = (blockIdx.x % ztiles) * TL;
   const int f = blockIdx.y;
+  // rows kymax < ky < N - kymax of this kx column are removed by the dealiasing mask for every kz (per-kx
+  // table: the mask is a sphere, dealiasing.f90:91-94)
+  const int kymax = kymax_x ? __ldg(kymax_x + kx) : kymax_all;
   {
     const int l = tid / G::NT, u = tid % G::NT;  // mapping A: coalesced along the line
     cplx r[8];
@@ -147,7 +150,8 @@ k_fwd_y(const cplx* __restrict__ W1, PeerTable W2, int nzl, int nz, int zoff,
 // (fftw.f90:212-218, unnormalised).  grid.x = ceil(nzl/TL) * nxh, grid.y = fields
 template <int N, int TL>
 __global__ void __launch_bounds__(Tile<N, TL>::NTHREADS, Tile<N, TL>::MINB)
-k_inv_y(const cplx* __restrict__ V1, cplx* __restrict__ V2, int nzl, const cplx* __restrict__ tw, int nxh, int kymax) {
+k_inv_y(const cplx* __restrict__ V1, cplx* __restrict__ V2, int nzl, const cplx* __restrict__ tw, int nxh, int kymax_all,
+        const int* __restrict__ kymax_x) {
   typedef Geom<N> G;
   typedef Fft<N, +1> F;
   typedef Tile<N, TL> T;
@@ -157,6 +161,7 @@ k_inv_y(const cplx* __restrict__ V1, cplx* __restrict__ V2, int nzl, const cplx*
   const int kx = blockIdx.x / ztiles;
   const int z0 = (blockIdx.x % ztiles) * TL;
   const int g = blockIdx.y;
+  const int kymax = kymax_x ? __ldg(kymax_x + kx) : kymax_all;
   {
     const int l = tid % TL, u = tid / TL;  // mapping B
     cplx r[8];

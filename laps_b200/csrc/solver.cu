@@ -121,6 +121,12 @@ struct laps_solver {
   // move those columns.  nkx = nxh and kymax = ny/2 mean "no pruning".
   int nkx = 0, kymax = 0, tune_prune = 1;
   int pr_nkyl = 0, pr_nA = 0, pr_a0 = 0, pr_b0 = 0;   // this rank's surviving ky rows (see ZParams)
+  // spherical mask (option 1): per-kx largest surviving |ky| and the list of this rank's surviving columns
+  int* d_kymax_x = nullptr;   // [nxh]
+  int* d_colmap = nullptr;    // [pr_ncol]
+  int pr_ncol = 0;            // this rank's surviving columns
+  long long pr_modes = 0;     // this rank's surviving modes (kx, ky, kz), for the traffic model of bench.py
+  bool kzprune = false;       // masked modes are neither loaded nor stored by the z pass (see ZParams::kzprune)
   bool spectrum_full = true;   // the state still holds masked columns (fresh from laps_set_primitive)
   int slot[19];        // field slot the z pass reads each flux from (F1..F18, expand_term), < 0: not transformed
   int fslot[19];       // field slot calc_flux stores each flux to, < 0: not stored (differs from slot[] for the
@@ -330,7 +336,7 @@ int do_fwd_y(S* s, const cplx* W1, int nfields, bool prune) {
   const int ztiles = (s->nzl + TL - 1) / TL;
   dim3 grid((unsigned)(ztiles * (prune ? s->nkx : s->nxh)), (unsigned)nfields);
   LAPS_LAUNCH((k_fwd_y<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, W1, s->tabW2, s->nzl, s->nz, s->zo,
-              s->tw_y, 1.0 / N, s->nxh, prune ? s->kymax : N);
+              s->tw_y, 1.0 / N, s->nxh, prune ? s->kymax : N, prune ? (const int*)s->d_kymax_x : (const int*)nullptr);
   return check_launch(s, "k_fwd_y");
 }
 
@@ -344,7 +350,7 @@ int do_inv_y(S* s, const cplx* V1, cplx* V2, int nfields, bool prune) {
   const int ztiles = (s->nzl + TL - 1) / TL;
   dim3 grid((unsigned)(ztiles * (prune ? s->nkx : s->nxh)), (unsigned)nfields);
   LAPS_LAUNCH((k_inv_y<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, V1, V2, s->nzl, s->tw_y, s->nxh,
-              prune ? s->kymax : N);
+              prune ? s->kymax : N, prune ? (const int*)s->d_kymax_x : (const int*)nullptr);
   return check_launch(s, "k_inv_y");
 }
 
@@ -462,8 +468,11 @@ cplx* buf_W2(S* s) { return (cplx*)s->bufZ; }
 
 void fill_zparams(S* s, ZParams& z, bool prune = false) {
   std::memset(&z, 0, sizeof(z));
-  if (prune) { z.nkyl = s->pr_nkyl; z.nA = s->pr_nA; z.a0 = s->pr_a0; z.b0 = s->pr_b0; z.ncolc = s->nkx * s->pr_nkyl; }
-  else { z.nkyl = s->nyl; z.nA = s->nyl; z.a0 = 0; z.b0 = 0; z.ncolc = (int)s->ncol; }
+  if (prune) {
+    z.nkyl = s->pr_nkyl; z.nA = s->pr_nA; z.a0 = s->pr_a0; z.b0 = s->pr_b0; z.ncolc = s->nkx * s->pr_nkyl;
+    if (s->d_colmap) { z.colmap = s->d_colmap; z.ncolc = s->pr_ncol; }
+    z.kzprune = s->kzprune ? 1 : 0;
+  } else { z.nkyl = s->nyl; z.nA = s->nyl; z.a0 = 0; z.b0 = 0; z.ncolc = (int)s->ncol; }
   const laps_params& p = s->p;
   z.nxh = s->nxh; z.ny = s->ny; z.nyl = s->nyl; z.yoff = s->yo; z.nz = s->nz; z.ncol = (int)s->ncol;
   z.W2 = buf_W2(s); z.fstride = s->csz;
@@ -643,7 +652,7 @@ int stage_incomp(S* s, int irk) {
   LAPS_TRY(host_barrier(s));
   LAPS_TRY(inverse_yx(s, 0, 8, true));
   if (s->spectrum_full) {
-    if (s->nkx < s->nxh || s->kymax < s->ny / 2)
+    if (s->nkx < s->nxh || s->kymax < s->ny / 2 || s->kzprune || s->d_colmap)
       LAPS_CK(s, cudaMemsetAsync(s->uA, 0, 8 * s->csz * sizeof(cplx), s->stream));
     s->spectrum_full = false;
   }
@@ -787,7 +796,7 @@ int stage(S* s, int irk) {
   if (s->spectrum_full) {
     // First stage after laps_set_primitive: the buffer just read still holds the unmasked initial
     // spectrum; it becomes the output buffer of the next stage, which writes surviving columns only.
-    if (s->nkx < s->nxh || s->kymax < s->ny / 2)
+    if (s->nkx < s->nxh || s->kymax < s->ny / 2 || s->kzprune || s->d_colmap)
       LAPS_CK(s, cudaMemsetAsync(s->uA, 0, 8 * s->csz * sizeof(cplx), s->stream));
     s->spectrum_full = false;
   }
@@ -1009,6 +1018,50 @@ int laps_create(const laps_params* params, laps_handle* out) {
     const int nB = std::max(0, y1 - bBeg);
     s->pr_nkyl = s->pr_nA + nB;
     if (s->kymax >= s->ny / 2) { s->pr_nkyl = s->nyl; s->pr_nA = s->nyl; s->pr_a0 = 0; s->pr_b0 = 0; }
+    s->pr_ncol = s->nkx * s->pr_nkyl;
+    const double* daz = day + s->ny;
+    const bool masked = s->tune_prune && (p.dealias_option == 1 || p.dealias_option == 3);
+    int tune_circle = 1, tune_kz = 1;
+    if (const char* e = std::getenv("LAPS_TUNE_CIRCLE")) tune_circle = std::atoi(e);
+    if (const char* e = std::getenv("LAPS_TUNE_KZPRUNE")) tune_kz = std::atoi(e);
+    s->kzprune = masked && tune_kz != 0;
+    if (masked && p.dealias_option == 1 && tune_circle) {
+      // A column (kx, ky) is dead for every kz iff it is dead at kz = 0: the test fl(fl(tx + ty) + tz) >= T is
+      // monotonic in tz >= 0.  ty grows with |ky| (each operation of dealiasing.f90:92 is monotonic), so the
+      // surviving rows of a kx column are |ky| <= kymax_x[kx].
+      std::vector<int> kym(s->nxh, -1), cmap;
+      for (int kx = 0; kx < s->nkx; ++kx) {
+        int km = -1;
+        while (km + 1 <= s->kymax && !(dax[kx] + day[km + 1] >= s->da_thresh)) ++km;
+        kym[kx] = km;
+        for (int r = 0; r < s->pr_nkyl; ++r) {
+          const int kyl = r < s->pr_nA ? s->pr_a0 + r : s->pr_b0 + r - s->pr_nA;
+          const int ky = s->yo + kyl;
+          if (!(dax[kx] + day[ky] >= s->da_thresh)) cmap.push_back(kx * s->nyl + kyl);
+        }
+      }
+      s->pr_ncol = (int)cmap.size();
+      alloc((void**)&s->d_kymax_x, s->nxh * sizeof(int));
+      alloc((void**)&s->d_colmap, std::max<size_t>(1, cmap.size()) * sizeof(int));
+      if (!ok) return fail("device allocation failed (pruning tables)");
+      if (cudaMemcpy(s->d_kymax_x, kym.data(), s->nxh * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+          (!cmap.empty() && cudaMemcpy(s->d_colmap, cmap.data(), cmap.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess))
+        return fail("pruning table upload failed");
+    }
+    {  // surviving modes of this rank (traffic model)
+      long long m = 0;
+      for (int kx = 0; kx < s->nxh; ++kx)
+        for (int kyl = 0; kyl < s->nyl; ++kyl) {
+          const double dxy = (p.dealias_option == 1 || p.dealias_option == 3) ? dax[kx] + day[s->yo + kyl] : 0.0;
+          for (int kz = 0; kz < s->nz; ++kz) {
+            bool dead = false;
+            if (masked && p.dealias_option == 1) dead = dxy + daz[kz] >= s->da_thresh;
+            if (masked && p.dealias_option == 3) dead = dxy != 0.0 || daz[kz] != 0.0;
+            m += dead ? 0 : 1;
+          }
+        }
+      s->pr_modes = m;
+    }
   }
   cudaMemsetAsync(s->rk, 0, 8 * s->csz * sizeof(cplx), s->stream);
 #ifndef LAPS_EMU_BUILD
@@ -1065,7 +1118,7 @@ int laps_destroy(laps_handle s) {
   cudaFree(s->xblk);
   cudaFree(s->uu); cudaFree(s->J); cudaFree(s->G); cudaFree(s->prim); cudaFree(s->bufX); cudaFree(s->bufY); cudaFree(s->bufZ);
   cudaFree(s->uA); cudaFree(s->uB); cudaFree(s->rk); cudaFree(s->tw_x); cudaFree(s->tw_y); cudaFree(s->tw_z);
-  cudaFree(s->d_tab); cudaFree(s->d_partial); cudaFree(s->d_scal);
+  cudaFree(s->d_tab); cudaFree(s->d_partial); cudaFree(s->d_scal); cudaFree(s->d_kymax_x); cudaFree(s->d_colmap);
   if (s->h_scal) cudaFreeHost(s->h_scal);
   for (auto& pe : s->prof) { cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1); }
   if (s->ev0) cudaEventDestroy(s->ev0);
@@ -1227,6 +1280,13 @@ int laps_get_pruning(laps_handle s, int32_t* nkx, int32_t* kymax, int32_t* nky_l
   if (nkx) *nkx = s->nkx;
   if (kymax) *kymax = s->kymax;
   if (nky_local) *nky_local = s->pr_nkyl;
+  return 0;
+}
+
+int laps_get_pruning_counts(laps_handle s, int64_t* live_columns, int64_t* live_modes) {
+  if (!s) return 1;
+  if (live_columns) *live_columns = s->pr_ncol;
+  if (live_modes) *live_modes = s->pr_modes;
   return 0;
 }
 

@@ -41,13 +41,11 @@ k_incomp_z(const ZParams P) {
   LAPS_DYN_SMEM(cplx, sm);
   const int tid = threadIdx.x;
   const int l = tid / G::NT, u = tid % G::NT;
-  const int cc = blockIdx.x * CG + l;
-  const bool live = cc < P.ncolc;
-  const int kx = live ? cc / P.nkyl : 0;
-  const int kr = live ? cc % P.nkyl : 0;
-  const int kyl = kr < P.nA ? P.a0 + kr : P.b0 + kr - P.nA;
-  const int ky = P.yoff + kyl;
-  const int col = kx * P.nyl + kyl;
+  const int colm = z_column(P, blockIdx.x * CG + l);
+  const bool live = colm >= 0;
+  const int col = live ? colm : 0;
+  const int kx = col / P.nyl;
+  const int ky = P.yoff + col % P.nyl;
   const size_t coff = (size_t)col * N;
   cplx* W = sm + l * T::COLSTRIDE;   // padded work line of the transforms
   cplx* S0 = W + T::PITCH;           // thread-private slots e*NT + u (forward OUTPUT order)
@@ -122,7 +120,8 @@ k_incomp_z(const ZParams P) {
       const int kz = FF::kout(u, e);
       cplx fnl = mom ? S[e * G::NT + u] : mk(0.0, 0.0);
       // the pressure row reads the value calc_pressure_fourier has just written (mhd.f90:338 precedes calc_rhs, :350)
-      const cplx uo = round == 0 ? r[e] : (live ? P.u_in[voff + kz] : mk(0.0, 0.0));
+      const bool keep = live && !z_mode_dead(P, dxy, kz);   // masked modes: zero in memory, not touched
+      const cplx uo = round == 0 ? r[e] : (keep ? P.u_in[voff + kz] : mk(0.0, 0.0));
       fnl.x -= ca * uo.x;
       fnl.y -= ca * uo.y;
       double ksq = 0.0;
@@ -133,12 +132,12 @@ k_incomp_z(const ZParams P) {
       }
       cplx un;   // rkt (rktmod.f90:40-42)
       if (P.read_rk) {
-        const cplx fr = live ? P.fnl_rk[voff + kz] : mk(0.0, 0.0);
+        const cplx fr = keep ? P.fnl_rk[voff + kz] : mk(0.0, 0.0);
         un = mk((P.cc * fnl.x + P.dd * fr.x) + uo.x, (P.cc * fnl.y + P.dd * fr.y) + uo.y);
       } else {
         un = mk(P.cc * fnl.x + uo.x, P.cc * fnl.y + uo.y);
       }
-      if (P.write_rk && live) P.fnl_rk[voff + kz] = fnl;
+      if (P.write_rk && keep) P.fnl_rk[voff + kz] = fnl;
       if (need_ksq) {
         const double inv = __drcp_rn(__dadd_rn(__dmul_rn(__dmul_rn(P.dt_irk, ksq), ci), 1.0));
         un.x *= inv;
@@ -152,7 +151,7 @@ k_incomp_z(const ZParams P) {
       } else if (P.dealias_option == 3) {   // square truncation (2D/dealiasing.f90:99-114): per-axis flags
         if (dxy != 0.0 || __ldg(P.daz + kz) != 0.0) un = mk(0.0, 0.0);
       }
-      if (live) P.u_out[voff + kz] = un;
+      if (keep) P.u_out[voff + kz] = un;
       r[e] = un;
     }
     // re-shape the register contents into the stage-0 input pattern of the inverse transform

@@ -68,20 +68,18 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
     }
     cp_async_commit();
   };
-  auto land_out = [&](cplx* buf, const cplx* line, bool on) {   // indexed by the OUTPUT order of the forward FFT
+  // indexed by the OUTPUT order of the forward FFT; modes in `dead` (bit e) are masked: zero in memory, not fetched
+  auto land_out = [&](cplx* buf, const cplx* line, bool on, unsigned dead) {
     if (on) {
       LAPS_UNROLL
-      for (int e = 0; e < 8; ++e) cp_async16(buf + e * G::NT + u, line + FF::kout(u, e));
+      for (int e = 0; e < 8; ++e)
+        if (!((dead >> e) & 1u)) cp_async16(buf + e * G::NT + u, line + FF::kout(u, e));
     }
     cp_async_commit();
   };
 
   // compact column index -> memory column (see ZParams); -1 past the end
-  auto column_of = [&](int cc) -> int {
-    if (cc >= P.ncolc) return -1;
-    const int kr = cc % P.nkyl;
-    return (cc / P.nkyl) * P.nyl + (kr < P.nA ? P.a0 + kr : P.b0 + kr - P.nA);
-  };
+  auto column_of = [&](int cc) -> int { return z_column(P, cc); };
   int item = blockIdx.x;
   if (item < nitems) {  // prologue: the first item's fc
     const ZTask& K = P.task[item % ntasks];
@@ -113,8 +111,18 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
           if (Kn.fa >= 0) prefetch_l2(P.W2 + (size_t)Kn.fa * P.fstride + po);
           if (Kn.fb >= 0) prefetch_l2(P.W2 + (size_t)Kn.fb * P.fstride + po);
           if (Kn.fx >= 0) prefetch_l2(P.W2 + (size_t)Kn.fx * P.fstride + po);
-          prefetch_l2(P.u_in + (size_t)Kn.v * P.fstride + po);
-          if (P.read_rk) prefetch_l2(P.fnl_rk + (size_t)Kn.v * P.fstride + po);
+          // (state lines: not the 128-byte groups that lie entirely inside the masked kz interval)
+          bool want = true;
+          if (P.kzprune) {
+            const int kxn = coln / P.nyl, kyn = P.yoff + coln % P.nyl;
+            const double dn = __dadd_rn(__ldg(P.dax + kxn), __ldg(P.day + kyn));
+            const int k0 = u * (N / G::NT);
+            want = !(z_mode_dead(P, dn, k0) && z_mode_dead(P, dn, k0 + N / G::NT - 1));
+          }
+          if (want) {
+            prefetch_l2(P.u_in + (size_t)Kn.v * P.fstride + po);
+            if (P.read_rk) prefetch_l2(P.fnl_rk + (size_t)Kn.v * P.fstride + po);
+          }
         }
       }
     }
@@ -128,6 +136,13 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
     if (P.corot_k) {
       kxe = __dadd_rn(__dmul_rn(kxr, P.cosa), __dmul_rn(kyr, P.sina));
       kye = __ddiv_rn(__dmul_rn(__dadd_rn(__dmul_rn(-kxr, P.sina), __dmul_rn(kyr, P.cosa)), P.radius0), P.radius);
+    }
+
+    const double dxy = (P.dealias_option == 1 || P.dealias_option == 3) ? __dadd_rn(dax, day) : dax;
+    unsigned dead = 0;   // bit e: the mask removes mode kout(u, e) of this column
+    if (P.kzprune) {
+      LAPS_UNROLL
+      for (int e = 0; e < 8; ++e) dead |= z_mode_dead(P, dxy, FF::kout(u, e)) ? (1u << e) : 0u;
     }
 
     cplx r[8];
@@ -158,13 +173,13 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
       LAPS_UNROLL
       for (int e = 0; e < 8; ++e) r[e] = cadd(r[e], cmul_i(Q1[e * G::NT + u], c));
     }
-    land_out(Q1, P.u_in + voff, live);
+    land_out(Q1, P.u_in + voff, live, dead);
     cp_async_wait<1>();   // fx
     if (live && K.fx >= 0) {
       LAPS_UNROLL
       for (int e = 0; e < 8; ++e) r[e] = cadd(r[e], cscale(Q0[e * G::NT + u], K.cx));
     }
-    land_out(Q0, P.fnl_rk + voff, live && P.read_rk);
+    land_out(Q0, P.fnl_rk + voff, live && P.read_rk, dead);
     FF::first_w(r, u, W, tw0);
     FF::finish_w(r, u, W, tw1, tw2);
 
@@ -184,7 +199,6 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
     const bool need_ksq = (ce != 0.0) || (ci != 0.0);
     const double ksq_xy = ksq_xy_of(P, kxr, kyr, ksqx, ksqy);
     const bool keep_bg = K.diff == 2 && P.conserve_bg && kx == 0;   // "ix==1 .and. iz==1" skip of mhdrhs.f90:262-270
-    const double dxy = (P.dealias_option == 1 || P.dealias_option == 3) ? __dadd_rn(dax, day) : dax;
     const double dfy = day;
     cp_async_wait<0>();   // u, rk
     LAPS_UNROLL
@@ -192,7 +206,8 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
       const int kz = FF::kout(u, e);
       cplx fnl = cscale(r[e], sgs);
       if (hasC) fnl = cadd(fnl, S[e * G::NT + u]);
-      const cplx uo = live ? Q1[e * G::NT + u] : mk(0.0, 0.0);
+      const bool keep = live && !((dead >> e) & 1u);
+      const cplx uo = keep ? Q1[e * G::NT + u] : mk(0.0, 0.0);
       fnl.x -= ca * uo.x;
       fnl.y -= ca * uo.y;
       double ksq = 0.0;
@@ -205,12 +220,12 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
       // rkt (rktmod.f90:40-42): u = cc*fnl + dd*fnl_rk + u ; fnl_rk = fnl
       cplx un;
       if (P.read_rk) {
-        const cplx fr = live ? Q0[e * G::NT + u] : mk(0.0, 0.0);
+        const cplx fr = keep ? Q0[e * G::NT + u] : mk(0.0, 0.0);
         un = mk((P.cc * fnl.x + P.dd * fr.x) + uo.x, (P.cc * fnl.y + P.dd * fr.y) + uo.y);
       } else {
         un = mk(P.cc * fnl.x + uo.x, P.cc * fnl.y + uo.y);
       }
-      if (P.write_rk && live) P.fnl_rk[voff + kz] = fnl;
+      if (P.write_rk && keep) P.fnl_rk[voff + kz] = fnl;
       if (need_ksq) {  // implicit diffusion (rktmod.f90:47-60); ci == 0 gives exactly 1
         const double inv = __drcp_rn(__dadd_rn(__dmul_rn(__dmul_rn(P.dt_irk, ksq), ci), 1.0));
         un.x *= inv;
@@ -225,7 +240,7 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
       } else if (P.dealias_option == 3) {   // square truncation (2D/dealiasing.f90:102-117): per-axis flags
         if (dxy != 0.0 || t_daz[e] != 0.0) un = mk(0.0, 0.0);
       }
-      if (live) P.u_out[voff + kz] = un;
+      if (keep) P.u_out[voff + kz] = un;
       r[e] = un;
     }
     {  // next item's fc -> S (this thread has finished with its S slots)

@@ -75,6 +75,13 @@ struct ZParams {
   // dealiasing mask form at most two runs (ky <= kymax and ky >= ny - kymax).  Without pruning
   // ncolc = ncol, nkyl = nA = nyl, a0 = 0.
   int ncolc, nkyl, nA, a0, b0;
+  // With the spherical mask (option 1) the surviving columns are those inside a circle in (kx, ky): colmap[c] is
+  // then the memory column (kx * nyl + kyl) of compact index c and the formula above is not used.
+  const int* colmap;
+  // kzprune: modes the mask removes are neither loaded nor stored (they are zero in the state arrays, and
+  // whatever fnl_rk holds there is never used): mask(kz) = dax + day + daz[kz] >= da_thresh (option 1) or a
+  // non-zero per-axis flag (option 3).
+  int kzprune;
   int mode2d;            // 2D tree: the line axis is the reference's y, d/dz = 0 (src_compressible/2D/mhdrhs.f90:272)
   int z_radial;          // 2D/mhdrhs.f90:278-280: kx is stretched too
   int bg_all_kz;         // 2D/mhdrhs.f90:372-374: if_conserve_background skips every mode with ix == 1
@@ -99,6 +106,21 @@ struct ZTile {
   static constexpr int BY_REGS = 65536 / (NTHREADS * 80);
   static constexpr int MINB = BY_SMEM < BY_REGS ? (BY_SMEM < 1 ? 1 : BY_SMEM) : (BY_REGS < 1 ? 1 : BY_REGS);
 };
+
+// memory column (kx * nyl + kyl) of compact column index cc; -1 past the end
+LAPS_D int z_column(const ZParams& P, int cc) {
+  if (cc >= P.ncolc) return -1;
+  if (P.colmap) return __ldg(P.colmap + cc);
+  const int kr = cc % P.nkyl;
+  return (cc / P.nkyl) * P.nyl + (kr < P.nA ? P.a0 + kr : P.b0 + kr - P.nA);
+}
+
+// true where the dealiasing mask removes mode (kx, ky, kz): dxy = dax + day of the column (options 1, 3)
+LAPS_D bool z_mode_dead(const ZParams& P, double dxy, int kz) {
+  if (!P.kzprune) return false;
+  const double dz = __ldg(P.daz + kz);
+  return P.dealias_option == 1 ? (__dadd_rn(dxy, dz) >= P.da_thresh) : (dxy != 0.0 || dz != 0.0);
+}
 
 LAPS_D void prefetch_l2(const void* p) {
 #ifndef LAPS_EMU_BUILD
@@ -138,13 +160,11 @@ k_spec_z(const ZParams P) {
   const ZTask& K = P.task[blockIdx.y];
   const int tid = threadIdx.x;
   const int l = tid / G::NT, u = tid % G::NT;
-  const int cc = blockIdx.x * CG + l;
-  const bool live = cc < P.ncolc;
-  const int kx = live ? cc / P.nkyl : 0;
-  const int kr = live ? cc % P.nkyl : 0;
-  const int kyl = kr < P.nA ? P.a0 + kr : P.b0 + kr - P.nA;
-  const int ky = P.yoff + kyl;
-  const int col = kx * P.nyl + kyl;
+  const int colm = z_column(P, blockIdx.x * CG + l);
+  const bool live = colm >= 0;
+  const int col = live ? colm : 0;
+  const int kx = col / P.nyl;
+  const int ky = P.yoff + col % P.nyl;
   cplx* lineG = sm + l * T::COLSTRIDE;
   cplx* stash = lineG + T::PITCH;          // thread-private slots e*NT + u
   const size_t coff = (size_t)col * N;
@@ -248,7 +268,8 @@ k_spec_z(const ZParams P) {
       const int kz = FF::kout(u, e);
       cplx fnl = cscale(r[e], sgs);
       if (hasC) fnl = cadd(fnl, stash[e * G::NT + u]);
-      const cplx uo = live ? P.u_in[voff + kz] : mk(0.0, 0.0);
+      const bool keep = live && !z_mode_dead(P, dxy, kz);   // masked modes: zero in memory, not touched
+      const cplx uo = keep ? P.u_in[voff + kz] : mk(0.0, 0.0);
       fnl.x -= ca * uo.x;
       fnl.y -= ca * uo.y;
       double ksq = 0.0;
@@ -261,12 +282,12 @@ k_spec_z(const ZParams P) {
       // rkt (rktmod.f90:40-42): u = cc*fnl + dd*fnl_rk + u ; fnl_rk = fnl
       cplx un;
       if (P.read_rk) {
-        const cplx fr = live ? P.fnl_rk[voff + kz] : mk(0.0, 0.0);
+        const cplx fr = keep ? P.fnl_rk[voff + kz] : mk(0.0, 0.0);
         un = mk((P.cc * fnl.x + P.dd * fr.x) + uo.x, (P.cc * fnl.y + P.dd * fr.y) + uo.y);
       } else {
         un = mk(P.cc * fnl.x + uo.x, P.cc * fnl.y + uo.y);
       }
-      if (P.write_rk && live) P.fnl_rk[voff + kz] = fnl;
+      if (P.write_rk && keep) P.fnl_rk[voff + kz] = fnl;
       if (need_ksq) {  // implicit diffusion (rktmod.f90:47-60); ci == 0 gives exactly 1
         const double inv = __drcp_rn(__dadd_rn(__dmul_rn(__dmul_rn(P.dt_irk, ksq), ci), 1.0));
         un.x *= inv;
@@ -281,7 +302,7 @@ k_spec_z(const ZParams P) {
       } else if (P.dealias_option == 3) {   // square truncation (2D/dealiasing.f90:102-117): per-axis flags
         if (dxy != 0.0 || __ldg(P.daz + kz) != 0.0) un = mk(0.0, 0.0);
       }
-      if (live) P.u_out[voff + kz] = un;
+      if (keep) P.u_out[voff + kz] = un;
       r[e] = un;
     }
     if (K.kind == kZForwardOnly || K.gout < 0) return;
@@ -312,22 +333,23 @@ k_spec_z(const ZParams P) {
       const int kz = u + e * G::NT;
       const double kzz = __ldg(P.kze + kz);
       const double ry = P.mode2d ? kzz : kye, rz = P.mode2d ? 0.0 : kzz;
-      const cplx m1 = live ? M[kz] : mk(0.0, 0.0);
-      const cplx m2 = live ? M[P.fstride + kz] : mk(0.0, 0.0);
-      const cplx m3 = live ? M[2 * P.fstride + kz] : mk(0.0, 0.0);
+      const bool keep = live && !z_mode_dead(P, dxy, kz);   // masked modes: zero in memory, not touched
+      const cplx m1 = keep ? M[kz] : mk(0.0, 0.0);
+      const cplx m2 = keep ? M[P.fstride + kz] : mk(0.0, 0.0);
+      const cplx m3 = keep ? M[2 * P.fstride + kz] : mk(0.0, 0.0);
       const cplx sum = cadd(cadd(cmul_i(m1, kxe), cmul_i(m2, ry)), cmul_i(m3, rz));
       cplx fnl = mk(-sum.x, -sum.y);
-      const cplx uo = live ? P.u_old[voff + kz] : mk(0.0, 0.0);
+      const cplx uo = keep ? P.u_old[voff + kz] : mk(0.0, 0.0);
       fnl.x -= ca * uo.x;
       fnl.y -= ca * uo.y;
       cplx un;
       if (P.read_rk) {
-        const cplx fr = live ? P.fnl_rk[voff + kz] : mk(0.0, 0.0);
+        const cplx fr = keep ? P.fnl_rk[voff + kz] : mk(0.0, 0.0);
         un = mk((P.cc * fnl.x + P.dd * fr.x) + uo.x, (P.cc * fnl.y + P.dd * fr.y) + uo.y);
       } else {
         un = mk(P.cc * fnl.x + uo.x, P.cc * fnl.y + uo.y);
       }
-      if (P.write_rk && live) P.fnl_rk[voff + kz] = fnl;
+      if (P.write_rk && keep) P.fnl_rk[voff + kz] = fnl;
       if (P.dealias_option == 1) {
         if (__dadd_rn(dxy, __ldg(P.daz + kz)) >= P.da_thresh) un = mk(0.0, 0.0);
       } else if (P.dealias_option == 2) {
@@ -336,7 +358,7 @@ k_spec_z(const ZParams P) {
       } else if (P.dealias_option == 3) {
         if (dxy != 0.0 || __ldg(P.daz + kz) != 0.0) un = mk(0.0, 0.0);
       }
-      if (live) P.u_out[voff + kz] = un;
+      if (keep) P.u_out[voff + kz] = un;
       r[e] = un;
     }
   } else if (K.kind == kZGrad) {
@@ -364,6 +386,7 @@ k_spec_z(const ZParams P) {
     }
   } else {  // kZCurrent: J^ = i k x B^ (mhdrhs.f90:329-336) from the updated state
     const int j = K.jcomp;
+    const double dxy_col = P.kzprune ? __dadd_rn(__ldg(P.dax + kx), __ldg(P.day + ky)) : 0.0;
     const cplx* B1 = P.u_in + (size_t)(4 + (j + 1) % 3) * P.fstride + coff;  // B_{j+1}
     const cplx* B2 = P.u_in + (size_t)(4 + (j + 2) % 3) * P.fstride + coff;  // B_{j+2}
     LAPS_UNROLL
@@ -375,8 +398,9 @@ k_spec_z(const ZParams P) {
       const double ry = P.mode2d ? kzz : kye, rz = P.mode2d ? 0.0 : kzz;
       const double k1 = (j == 0) ? ry : (j == 1 ? rz : kxe);
       const double k2 = (j == 0) ? rz : (j == 1 ? kxe : ry);
-      const cplx b1 = live ? B1[kz] : mk(0.0, 0.0);
-      const cplx b2 = live ? B2[kz] : mk(0.0, 0.0);
+      const bool keep = live && !z_mode_dead(P, dxy_col, kz);   // masked modes of the state are zero
+      const cplx b1 = keep ? B1[kz] : mk(0.0, 0.0);
+      const cplx b2 = keep ? B2[kz] : mk(0.0, 0.0);
       r[e] = csub(cmul_i(b2, k1), cmul_i(b1, k2));
     }
   }

@@ -215,6 +215,12 @@ class Solver:
         self._ck(self._lib.laps_get_pruning(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def pruning_counts(self):
+        """(live_columns, live_modes) of this rank (laps_get_pruning_counts)."""
+        a, b = C.c_int64(), C.c_int64()
+        self._ck(self._lib.laps_get_pruning_counts(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def field_counts(self):
         """(nf, ni, spec_rows): fields transformed forward / inverse per RK stage and the state rows of the
         main z-pass launch (laps_get_field_counts)."""

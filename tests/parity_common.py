@@ -178,25 +178,39 @@ def check_diagnostics(o, g, tol):
     assert abs(g.calc_max_divB() - inv[2]) == 0.0
 
 
-def check_pruning_is_exact(shape, nsteps, lib_path=None, **case):
-    """The passes skip the columns the dealiasing mask removes (LAPS_TUNE_PRUNE, default on).  The
-    state must be BIT-IDENTICAL to a run that computes and moves everything."""
+def check_pruning_is_exact(shape, nsteps, lib_path=None, incompressible=False, **case):
+    """The passes skip what the dealiasing mask removes (LAPS_TUNE_PRUNE, default on): whole kx columns and ky
+    rows (rectangle), with the spherical mask also the (kx, ky) columns outside the circle (LAPS_TUNE_CIRCLE)
+    and, inside a surviving column, the state / RK-history entries of masked kz (LAPS_TUNE_KZPRUNE).  The state
+    must be BIT-IDENTICAL to a run that computes and moves everything, for every combination."""
     import os
-    p, prim = (make_case_2d(*shape, **case) if len(shape) == 2 else make_case(*shape, **case))
+    if incompressible:
+        p, prim = (make_case_incompressible_2d(*shape, **case) if len(shape) == 2 else make_case_incompressible(*shape, **case))
+    else:
+        p, prim = (make_case_2d(*shape, **case) if len(shape) == 2 else make_case(*shape, **case))
+    keys = ("LAPS_TUNE_PRUNE", "LAPS_TUNE_CIRCLE", "LAPS_TUNE_KZPRUNE")
     out = []
-    for flag in ("0", "1"):
-        os.environ["LAPS_TUNE_PRUNE"] = flag
+    for env in (dict(LAPS_TUNE_PRUNE="0"), {}, dict(LAPS_TUNE_CIRCLE="0"), dict(LAPS_TUNE_KZPRUNE="0"),
+                dict(LAPS_TUNE_CIRCLE="0", LAPS_TUNE_KZPRUNE="0")):
+        saved = {k: os.environ.pop(k, None) for k in keys}
+        os.environ.update(env)
         try:
             g = Solver(lib_path, **solver_kwargs(p))
         finally:
-            del os.environ["LAPS_TUNE_PRUNE"]
+            for k in keys:
+                os.environ.pop(k, None)
+                if saved[k] is not None:
+                    os.environ[k] = saved[k]
         g.set_primitive(prim)
         g.vardt()
         for _ in range(nsteps):
             g.step()
         uu, _ = g.get_state()
-        out.append((uu, g.uu_fourier(), g.dt, g.calc_max_divB()))
+        out.append((uu, g.uu_fourier(), g.dt, g.calc_max_divB(), g.pruning_counts()))
         g.close()
-    assert np.array_equal(out[0][0], out[1][0])
-    assert np.array_equal(out[0][1], out[1][1])
-    assert out[0][2] == out[1][2] and out[0][3] == out[1][3]
+    for o in out[1:]:
+        assert np.array_equal(out[0][0], o[0])
+        assert np.array_equal(out[0][1], o[1])
+        assert out[0][2] == o[2] and out[0][3] == o[3]
+    assert out[1][4][1] < out[0][4][1]          # the default does skip modes
+    return [o[4] for o in out]

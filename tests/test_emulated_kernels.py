@@ -125,8 +125,12 @@ def test_one_step_incompressible_2d_tree(emu, kw):
 
 
 def test_mask_pruning_is_bit_exact(emu):
-    pc.check_pruning_is_exact((32, 16, 32), 2, lib_path=emu, hall=True, aeb=True, dealias=1)
+    counts = pc.check_pruning_is_exact((32, 32, 32), 2, lib_path=emu, hall=True, aeb=True, dealias=1)
+    # 32^3, spherical mask: 189 of the 231 columns of the surviving rectangle lie inside the circle,
+    # 2699 of 17 * 32 * 32 modes inside the sphere
+    assert counts[0] == (17 * 32, 17 * 32 * 32) and counts[1] == (189, 2699) and counts[2] == (231, 2699)
     pc.check_pruning_is_exact((32, 32), 2, lib_path=emu, hall=True, aeb=True, dealias=3)
+    pc.check_pruning_is_exact((32, 16, 32), 2, lib_path=emu, incompressible=True, hall=True, aeb=True, dealias=1)
 
 
 def test_synthetic_slab_matches_the_mode_sum():

@@ -76,6 +76,8 @@ def test_work_skipping_switched_off_parity_64(env, monkeypatch):
 def test_mask_pruning_is_bit_exact():
     pc.check_pruning_is_exact((64, 64, 64), 3, hall=True, aeb=True, dealias=1)
     pc.check_pruning_is_exact((128, 64), 3, hall=True, aeb=True, dealias=3)
+    pc.check_pruning_is_exact((128, 64), 2, hall=True, aeb=True, dealias=1)
+    pc.check_pruning_is_exact((64, 64, 64), 2, incompressible=True, hall=True, aeb=True, dealias=1)
 
 
 @pytest.mark.parametrize("name,kw", [("hall_aeb", dict(hall=True, aeb=True, dealias=1)),
