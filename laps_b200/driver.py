@@ -5,6 +5,7 @@ in the reference's formats (``lapsio.py``).  This is the caller on either side o
 (SURVEY.md 8(f) rank 1); a Fortran driver patched as in INTEGRATION.md makes the same calls.
 
     python -m laps_b200.driver [--input mhd.input] [--outdir .] [--max-steps N]
+                               [--tree compressible|compressible2d|incompressible|incompressible2d]
     torchrun --nproc-per-node P -m laps_b200.driver ...          (one rank per GPU, slab decomposition)
 
 Initial conditions built in: ``ifield = 3`` (uniform background) with ``ipert`` 0 (none), 1 (Alfven wave,
@@ -30,14 +31,29 @@ def _get(groups, group, key, default):
     return groups.get(group, {}).get(key.lower(), default)
 
 
-def params_from_namelists(nl, rank=0, nranks=1, device=0):
+TREES = ("compressible", "compressible2d", "incompressible", "incompressible2d")
+
+
+def params_from_namelists(nl, rank=0, nranks=1, device=0, tree="compressible"):
     """laps_params fields from the namelists of mhd.f90:30-53 (module defaults where a key is absent:
-    mhdinit.f90:5-54, dealiasing.f90:9-10, AEBmod.f90:10-12, mhd.f90:21)."""
+    mhdinit.f90:5-54, dealiasing.f90:9-10, AEBmod.f90:10-12, mhd.f90:21).  ``tree`` selects which of the
+    reference's four source trees the input file belongs to (they share the namelist syntax; the 2D trees add
+    if_limit_dt_increase and, compressible only, if_z_radial; the incompressible trees use rho0 = 1,
+    src_incompressible/mhdinit.f90:15)."""
+    if tree not in TREES:
+        raise ValueError(f"tree must be one of {TREES}")
     g = lambda grp, key, d: _get(nl, grp, key, d)  # noqa: E731
+    extra = {}
+    if tree.endswith("2d"):
+        extra.update(ndim=2, if_limit_dt_increase=bool(g("numerical", "if_limit_dt_increase", False)))
+        if tree == "compressible2d":
+            extra.update(if_z_radial=bool(g("aeb", "if_z_radial", False)))
+    if tree.startswith("incompressible"):
+        extra.update(incompressible=1, rho0=1.0)
     if int(g("prl", "ndim_parallel", 1)) != 1 and nranks > 1:
         raise ValueError("only the slab decomposition (ndim_parallel = 1) is supported on more than one rank")
     return dict(
-        nx=int(g("grid", "nx", 128)), ny=int(g("grid", "ny", 128)), nz=int(g("grid", "nz", 64)),
+        nx=int(g("grid", "nx", 128)), ny=int(g("grid", "ny", 128)), nz=1 if tree.endswith("2d") else int(g("grid", "nz", 64)),
         Lx=float(g("grid", "Lx", 1.0)), Ly=float(g("grid", "Ly", 1.0)), Lz=float(g("grid", "Lz", 1.0)),
         adiabatic_index=float(g("phys", "adiabatic_index", 5.0 / 3.0)),
         if_resis=bool(g("phys", "if_resis", False)), resistivity=float(g("phys", "resistivity", 0.0)),
@@ -50,17 +66,20 @@ def params_from_namelists(nl, rank=0, nranks=1, device=0):
         radius0=float(g("aeb", "radius0", 30.0)), Ur0=float(g("aeb", "Ur0", 0.0)),
         corotating_angle=float(g("aeb", "corotating_angle", 0.0)),
         if_hall=bool(g("hall", "if_Hall", False)), ion_inertial_length=float(g("hall", "ion_inertial_length", 0.0)),
-        rank=rank, nranks=nranks, device=device)
+        rank=rank, nranks=nranks, device=device, **extra)
 
 
 class Driver:
     def __init__(self, input_path="mhd.input", outdir=".", rank=0, nranks=1, device=0, lib_path=None, barrier=None,
-                 connect=None):
+                 connect=None, tree="compressible"):
         self.nl = lapsio.read_namelists(input_path)
+        self.tree = tree
+        self.two_d = tree.endswith("2d")
+        self.dstep_calcdt = 20 if self.two_d else 1          # 2D/mhd.f90:22,237-240: vardt every 20 steps
         self.outdir = outdir
         self.rank, self.nranks = rank, nranks
         self.barrier = barrier or (lambda: None)
-        kw = params_from_namelists(self.nl, rank, nranks, device)
+        kw = params_from_namelists(self.nl, rank, nranks, device, tree)
         self.kw = kw
         g = lambda grp, key, d: _get(self.nl, grp, key, d)  # noqa: E731
         self.tmax = float(g("genr", "tmax", 1.0))
@@ -98,13 +117,15 @@ class Driver:
             raise NotImplementedError("built-in initial data: ifield = 3 only (others: restart from an outNNN.dat)")
         bx0, by0, bz0 = float(g("field", "Bx0", 0.0)), float(g("field", "By0", 0.0)), float(g("field", "Bz0", 0.0))
         press0 = float(g("field", "press0", 1.0))
-        if ipert == 7:
+        if ipert == 7 and not self.two_d:
             n = int(g("pert", "nmodex", 8))
             return synthetic.turbulence_slab(self.nx, self.ny, self.nz, kw["Lx"], kw["Ly"], kw["Lz"], z_offset=self.zo,
                                              z_size=self.zn, bx0=bx0, by0=by0, bz0=bz0, press0=press0,
                                              db0=float(g("pert", "db0", 0.1)), dv0=float(g("pert", "dv0", 0.0)),
                                              drho0=float(g("pert", "drho0", 0.0)), kmax=n)
         prim = synthetic.uniform_background(self.nx, self.ny, self.zn, bx0, by0, bz0, press0)
+        if ipert == 7 and self.two_d:
+            raise NotImplementedError("built-in turbulence (ipert = 7) is the 3D mode table; use a restart file in 2D")
         if ipert == 1:
             ang = kw["corotating_angle"] if kw["if_corotating"] else 0.0
             synthetic.add_alfven_wave(prim, self.nx, kw["Lx"], db0=float(g("pert", "db0", 0.1)),
@@ -215,7 +236,8 @@ class Driver:
             if self.time >= tlog:
                 self.write_log(dt)
                 tlog += dtlog
-            dt = s.vardt()                                    # :285
+            if self.istep % self.dstep_calcdt == 0:
+                dt = s.vardt()                                # :285 (2D trees: every dstep_calcdt steps)
         self.write_log(dt)
         return self.istep
 
@@ -225,6 +247,7 @@ def main(argv=None):
     ap.add_argument("--input", default="mhd.input")
     ap.add_argument("--outdir", default=".")
     ap.add_argument("--max-steps", type=int, default=None)
+    ap.add_argument("--tree", default="compressible", choices=TREES)
     args = ap.parse_args(argv)
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     barrier, connect = None, None
@@ -243,7 +266,7 @@ def main(argv=None):
             dist.all_gather(blobs, blob)
             g.import_peer_blobs(b"".join(bytes(b.cpu().numpy().tobytes()) for b in blobs))
             dist.barrier()
-    d = Driver(args.input, args.outdir, rank, world, local, barrier=barrier, connect=connect)
+    d = Driver(args.input, args.outdir, rank, world, local, barrier=barrier, connect=connect, tree=args.tree)
     n = d.run(args.max_steps)
     if rank == 0:
         print(f"{n} steps, time = {d.time:.6f}")

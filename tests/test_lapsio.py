@@ -175,3 +175,36 @@ def test_driver_loop_files_and_restart_on_the_emulator(emu, tmp_path):
     assert r.time > o.time and r.istep == 1
     assert os.path.exists(tmp_path / lapsio.out_name(n + 1))
     r.solver.close()
+
+
+@pytest.mark.parametrize("tree", ["incompressible", "compressible2d", "incompressible2d"])
+def test_driver_runs_the_other_source_trees_on_the_emulator(emu, tmp_path, tree):
+    """The same mhd.input syntax drives the other three source trees (--tree): Alfven-wave data (ipert = 1),
+    two steps, files in place, state equal to the oracle class of that tree."""
+    text = INPUT.replace("ipert = 7", "ipert = 1").replace("Bx0 = 1.", "Bx0 = 1.\n   wave_number_jet = 2")
+    (tmp_path / "mhd.input").write_text(text)
+    d = Driver(str(tmp_path / "mhd.input"), str(tmp_path), lib_path=emu, tree=tree)
+    prim0 = d.initial_primitive()
+    assert prim0.shape == (8, 1 if tree.endswith("2d") else 16, 16, 16)
+    assert d.run(max_steps=2, echo=False) == 2
+    kw = {k: v for k, v in d.kw.items() if k not in ("rank", "nranks", "device", "ndim", "incompressible")}
+    p = lo.Params(incompressible=tree.startswith("incompressible"), **kw)
+    o = pc.oracle_state(p)
+    o.set_primitive(prim0)
+    o.vardt()
+    for i in range(2):
+        o.evolve()
+        o.time += o.dt
+        o.evolve_radius(o.time)
+        if i == 0 and not tree.endswith("2d"):       # the 2D drivers call vardt every 20 steps only
+            o.vardt()
+    assert abs(d.time - o.time) < 1e-12
+    names = sorted(f for f in os.listdir(tmp_path) if f.startswith("out"))
+    data = lapsio.read_out_slab(str(tmp_path / names[-1]), 16, 16, 1 if tree.endswith("2d") else 16)
+    ref = o.uu.copy()
+    ref[1:4] = o.uu_prim[0:3]
+    if not tree.startswith("incompressible"):
+        ref[7] = o.uu_prim[3]
+    for v in range(8):
+        assert pc.rel_l2(data[v], ref[v]) < 1e-10 or np.abs(data[v] - ref[v]).max() < 1e-13, v
+    d.solver.close()
