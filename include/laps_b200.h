@@ -98,6 +98,12 @@ int laps_connect_local(laps_handle* handles, int32_t nranks);
  * uu_local = primitive rho,ux,uy,uz,bx,by,bz,p as background/perturbation_initialize or
  * read_restart leave them (mhdinit.f90:183-1036, restart.f90:17-63). */
 int laps_set_primitive(laps_handle h, const double* uu_local);
+/* The same from a mode table instead of a host array: field_v(x) = background[v] + sum_m Re(coef[v][m]
+ * exp(i k_m.x)) for v = rho, ux, uy, uz, bx, by, bz and p = background[7] — the function the reference's
+ * ipert = 6/7 hooks evaluate by summing cosines point by point (mhdinit.f90:487-829, O(modes x N^3)).  Here it is a
+ * sparse spectrum and one inverse transform on the device; nothing but the table crosses PCIe.
+ * k = int32 [nmodes][3] integer wave vectors with kx >= 0, coef = complex128 pairs [7][nmodes]. */
+int laps_set_primitive_modes(laps_handle h, int32_t nmodes, const int32_t* k, const double* coef, const double* background);
 /* evolve_radius(time) (mhd.f90:102,248; AEBmod.f90:56-73): radius, tau_exp, k_square. */
 int laps_set_time(laps_handle h, double time);
 /* vardt (mhd.f90:136,285,328-429): CFL limit, global min, 2 % hysteresis on *dt_inout, rkt_init. */

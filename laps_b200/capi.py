@@ -61,7 +61,7 @@ SYMBOLS = [
     "laps_sync", "laps_get_stream", "laps_max_divb", "laps_rms", "laps_invariants", "laps_get_state", "laps_get_spectral",
     "laps_fft_forward", "laps_fft_inverse", "laps_transpose_yz_indexmap",
     "laps_last_step_ms", "laps_set_profiling", "laps_get_profile", "laps_get_pruning",
-    "laps_max_divv", "laps_max_div_real", "laps_get_rho0", "laps_get_field_counts", "laps_get_output", "laps_get_pruning_counts",
+    "laps_max_divv", "laps_max_div_real", "laps_get_rho0", "laps_get_field_counts", "laps_get_output", "laps_get_pruning_counts", "laps_set_primitive_modes",
 ]
 
 
@@ -93,6 +93,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.laps_import_peer_blobs.argtypes = [H, C.c_void_p]
     lib.laps_connect_local.argtypes = [C.POINTER(H), C.c_int32]
     lib.laps_set_primitive.argtypes = [H, dp]
+    lib.laps_set_primitive_modes.argtypes = [H, C.c_int32, C.POINTER(C.c_int32), dp, dp]
     lib.laps_set_time.argtypes = [H, C.c_double]
     lib.laps_vardt.argtypes = [H, dp]
     lib.laps_rkt_init.argtypes = [H, C.c_double]

@@ -379,4 +379,12 @@ __global__ void __launch_bounds__(256) k_absmax(const double* f, size_t n, int n
   }
 }
 
+// Sparse fill of the spectral buffer for laps_set_primitive_modes: u[v][idx[e]] = val[v][e]
+__global__ void __launch_bounds__(256) k_scatter_modes(cplx* u, size_t fstride, const long long* idx, const cplx* val, int nent, int nfields) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nent * nfields) return;
+  const int v = t / nent, e = t % nent;
+  u[(size_t)v * fstride + (size_t)idx[e]] = val[(size_t)v * nent + e];
+}
+
 }  // namespace laps

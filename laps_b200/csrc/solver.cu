@@ -1151,10 +1151,17 @@ int laps_get_stream(laps_handle s, void** stream_out) {
   return 0;
 }
 
+static int finish_set_primitive(laps_handle s);
+
 int laps_set_primitive(laps_handle s, const double* uu_local) {
   if (!s || !uu_local) return 1;
   s->front_ready = false;
   LAPS_CK(s, cudaMemcpyAsync(s->uu, uu_local, 8 * s->npts * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  return finish_set_primitive(s);
+}
+
+// initial_calc_conserve_variable + transform_uu_real_to_fourier on the primitive fields already in s->uu
+static int finish_set_primitive(laps_handle s) {
   {
     LaunchScope ls(s, "prim_to_cons");
     LAPS_LAUNCH(k_prim_to_cons, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, s->uu, s->npts, s->p.adiabatic_index, s->incomp ? 1 : 0);
@@ -1167,6 +1174,74 @@ int laps_set_primitive(laps_handle s, const double* uu_local) {
   s->j_stale = true;
   LAPS_CK(s, cudaStreamSynchronize(s->stream));  // the caller may reuse uu_local
   return 0;
+}
+
+// Initial data given as a mode table instead of a host array: the reference's ipert = 6/7
+// hooks sum cosines point by point, O(modes x N^3) (mhdinit.f90:487-829); the same field is a sparse spectrum
+// and one inverse transform.  field_v(x) = background[v] + sum_m Re( coef[v][m] exp(i k_m . x) ), v = rho, u, B;
+// p = background[7].  k = integer wave vectors (ikx >= 0), coef = complex128 pairs [7][nmodes].
+int laps_set_primitive_modes(laps_handle s, int32_t nmodes, const int32_t* k, const double* coef, const double* background) {
+  if (!s || nmodes < 0 || (nmodes > 0 && (!k || !coef)) || !background) return 1;
+  s->front_ready = false;
+  const int NYr = s->two_d ? s->nz : s->ny;       // the driver's ny
+  std::vector<long long> idx;
+  std::vector<cplx> val;                            // [8][nent]
+  std::vector<std::vector<cplx>> rows(8);
+  auto push = [&](long long i, const cplx* c8) {
+    for (size_t e = 0; e < idx.size(); ++e)
+      if (idx[e] == i) { for (int v = 0; v < 8; ++v) rows[v][e] = cadd(rows[v][e], c8[v]); return; }
+    idx.push_back(i);
+    for (int v = 0; v < 8; ++v) rows[v].push_back(c8[v]);
+  };
+  if (s->yo == 0) {  // the k = 0 mode carries the uniform background (ifield = 3)
+    cplx c8[8];
+    for (int v = 0; v < 8; ++v) c8[v] = mk(background[v], 0.0);
+    push(0, c8);
+  }
+  for (int m = 0; m < nmodes; ++m) {
+    const int ikx = k[3 * m], iky = k[3 * m + 1], ikz = k[3 * m + 2];
+    if (ikx < 0 || ikx > s->nx / 2 || std::abs(iky) >= NYr / 2 || (!s->two_d && std::abs(ikz) >= s->nz / 2) || (s->two_d && ikz != 0)) {
+      s->err = "laps_set_primitive_modes: mode " + std::to_string(m) + " is outside the grid's half spectrum"; return 1;
+    }
+    const int kyr = (iky + NYr) % NYr;
+    // internal axes: 3D (kx, ky, kz); 2D tree (kx, 0, ky) — the line axis carries the driver's ky
+    const int ky = s->two_d ? 0 : kyr, kz = s->two_d ? kyr : (ikz + s->nz) % s->nz;
+    if (ky < s->yo || ky >= s->yo + s->nyl) continue;          // another rank owns this row
+    const double w = ikx > 0 ? 0.5 : 1.0;                      // the c2r x pass doubles kx > 0 and keeps Re of kx = 0
+    cplx c8[8];
+    for (int v = 0; v < 7; ++v) c8[v] = mk(w * coef[2 * ((size_t)v * nmodes + m)], w * coef[2 * ((size_t)v * nmodes + m) + 1]);
+    c8[7] = mk(0.0, 0.0);
+    push(((long long)ikx * s->nyl + (ky - s->yo)) * s->nz + kz, c8);
+  }
+  const int nent = (int)idx.size();
+  for (int v = 0; v < 8; ++v) val.insert(val.end(), rows[v].begin(), rows[v].end());
+  LAPS_CK(s, cudaMemsetAsync(s->uB, 0, 8 * s->csz * sizeof(cplx), s->stream));
+  long long* d_idx = nullptr; cplx* d_val = nullptr;
+  if (nent > 0) {
+    LAPS_CK(s, cudaMalloc((void**)&d_idx, nent * sizeof(long long)));
+    LAPS_CK(s, cudaMalloc((void**)&d_val, (size_t)8 * nent * sizeof(cplx)));
+    LAPS_CK(s, cudaMemcpyAsync(d_idx, idx.data(), nent * sizeof(long long), cudaMemcpyHostToDevice, s->stream));
+    LAPS_CK(s, cudaMemcpyAsync(d_val, val.data(), (size_t)8 * nent * sizeof(cplx), cudaMemcpyHostToDevice, s->stream));
+    LaunchScope ls(s, "scatter_modes");
+    LAPS_LAUNCH(k_scatter_modes, dim3((unsigned)((8 * nent + 255) / 256)), dim3(256), 0, s->stream, s->uB, s->csz,
+                (const long long*)d_idx, (const cplx*)d_val, nent, 8);
+    LAPS_TRY(check_launch(s, "k_scatter_modes"));
+  }
+  {  // inverse transform of the 8 sparse spectra straight into uu (as primitives)
+    ZParams z; fill_zparams(s, z);
+    z.u_in = s->uB;
+    for (int v = 0; v < 8; ++v) {
+      ZTask t; std::memset(&t, 0, sizeof(t));
+      t.kind = kZInverseOnly; t.v = v; t.gout = v; t.fa = t.fb = t.fx = t.fc = -1;
+      z.task[v] = t;
+    }
+    LAPS_TRY(spec_z(s, z, 8, "inv_z"));
+    LAPS_TRY(host_barrier(s));
+    LAPS_TRY(inverse_yx(s, 0, 8, false));
+  }
+  LAPS_CK(s, cudaStreamSynchronize(s->stream));
+  cudaFree(d_idx); cudaFree(d_val);
+  return finish_set_primitive(s);
 }
 
 int laps_set_time(laps_handle s, double time) {  // AEBmod.f90:56-73

@@ -176,12 +176,21 @@ class Driver:
     # ------------------------------------------------------------------ program mhd
     def run(self, max_steps=None, echo=True):
         s, kw = self.solver, self.kw
-        prim = self.initial_primitive()
-        if self.if_restart:
-            s.time = self.time
-            s.evolve_radius(self.time)                        # mhd.f90:101-103
-            self.radius = kw["radius0"] + self.Ur * self.time
-        s.set_primitive(prim)                                 # mhd.f90:121-122
+        g = lambda grp, key, d: _get(self.nl, grp, key, d)  # noqa: E731
+        if (not self.if_restart and not self.two_d and int(g("field", "ifield", 3)) == 3 and int(g("pert", "ipert", 0)) == 7):
+            # the mode table goes to the device as it is (laps_set_primitive_modes): no N^3 host array, no upload
+            bx0, by0, bz0 = float(g("field", "Bx0", 0.0)), float(g("field", "By0", 0.0)), float(g("field", "Bz0", 0.0))
+            n = int(g("pert", "nmodex", 8))
+            ks, coefs = synthetic.mode_table(kw["Lx"], kw["Ly"], kw["Lz"], bx0, by0, bz0, n, n, n, (101, 116, 132),
+                                             float(g("pert", "db0", 0.1)), float(g("pert", "dv0", 0.0)), float(g("pert", "drho0", 0.0)))
+            s.set_primitive_modes(ks, coefs, [1.0, 0.0, 0.0, 0.0, bx0, by0, bz0, float(g("field", "press0", 1.0))])
+        else:
+            prim = self.initial_primitive()
+            if self.if_restart:
+                s.time = self.time
+                s.evolve_radius(self.time)                    # mhd.f90:101-103
+                self.radius = kw["radius0"] + self.Ur * self.time
+            s.set_primitive(prim)                             # mhd.f90:121-122
         s.dt = 0.0
         dt = s.vardt()                                        # mhd.f90:135-136
         if self.rank == 0:

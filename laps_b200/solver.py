@@ -78,6 +78,17 @@ class Solver:
         assert a.shape == (8,) + self.real_shape, (a.shape, self.real_shape)
         self._ck(self._lib.laps_set_primitive(self._h, capi._dptr(a)))
 
+    def set_primitive_modes(self, ks, coefs, background):
+        """laps_set_primitive_modes: ``ks`` int [nmodes, 3] (kx >= 0), ``coefs`` complex [7, nmodes]
+        (``synthetic.mode_table``), ``background`` = 8 uniform values (rho, u, B, p)."""
+        k = np.ascontiguousarray(ks, dtype=np.int32).reshape(-1, 3)
+        c = np.ascontiguousarray(coefs, dtype=np.complex128)
+        assert c.shape == (7, k.shape[0])
+        b = np.ascontiguousarray(background, dtype=np.float64)
+        assert b.shape == (8,)
+        self._ck(self._lib.laps_set_primitive_modes(self._h, k.shape[0], k.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                    c.ctypes.data_as(C.POINTER(C.c_double)), capi._dptr(b)))
+
     def evolve_radius(self, time: float):
         """AEBmod.f90:56-73."""
         self._ck(self._lib.laps_set_time(self._h, float(time)))

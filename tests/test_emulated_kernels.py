@@ -11,7 +11,7 @@ import pytest
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
 import build_emu  # noqa: E402
 import parity_common as pc  # noqa: E402
-from laps_b200 import synthetic  # noqa: E402
+from laps_b200 import Solver, synthetic  # noqa: E402
 from oracle import laps_oracle as lo  # noqa: E402
 
 
@@ -131,6 +131,34 @@ def test_mask_pruning_is_bit_exact(emu):
     assert counts[0] == (17 * 32, 17 * 32 * 32) and counts[1] == (189, 2699) and counts[2] == (231, 2699)
     pc.check_pruning_is_exact((32, 32), 2, lib_path=emu, hall=True, aeb=True, dealias=3)
     pc.check_pruning_is_exact((32, 16, 32), 2, lib_path=emu, incompressible=True, hall=True, aeb=True, dealias=1)
+
+
+def test_set_primitive_modes_equals_the_uploaded_field(emu):
+    """laps_set_primitive_modes (sparse spectrum + inverse transform on the device) against laps_set_primitive of
+    the host-built field, 3D and the 2D tree; the oracle's point-by-point cosine sum pins both."""
+    ks, coefs = synthetic.mode_table(24.0, 20.0, 12.0, 1.0, 0.3, 0.0, 3, 3, 3, (101, 116, 132), 0.1, 0.1, 0.01)
+    back = [1.0, 0.0, 0.0, 0.0, 1.0, 0.3, 0.0, 1.0]
+    p = lo.Params(nx=32, ny=16, nz=16, Lx=24.0, Ly=20.0, Lz=12.0)
+    ref = lo.ic_turbulence(p, lo.ic_uniform_background(p, bx0=1.0, by0=0.3, press0=1.0), 1.0, 0.3, 0.0, nmodex=3, nmodey=3, nmodez=3)
+    kw = dict(nx=32, ny=16, nz=16, Lx=24.0, Ly=20.0, Lz=12.0, dealias_option=1)
+    with Solver(emu, **kw) as a, Solver(emu, **kw) as b:
+        a.set_primitive(ref)
+        b.set_primitive_modes(ks, coefs, back)
+        assert np.abs(a.get_state()[0] - b.get_state()[0]).max() < 1e-13
+        assert np.abs(a.uu_fourier() - b.uu_fourier()).max() < 1e-14
+    # 2D tree: the modes with kz = 0
+    sel = ks[:, 2] == 0
+    with Solver(emu, nx=32, ny=16, nz=1, Lx=24.0, Ly=20.0, Lz=1.0, ndim=2, dealias_option=1) as c:
+        c.set_primitive_modes(ks[sel], coefs[:, sel], back)
+        uu, prim = c.get_state()
+        x = np.arange(32) * (24.0 / 32)
+        y = np.arange(16) * (20.0 / 16)
+        Y, X = np.meshgrid(y, x, indexing="ij")
+        bx = 1.0 + sum((coefs[4, m] * np.exp(1j * 2 * np.pi * (ks[m, 0] * X / 24.0 + ks[m, 1] * Y / 20.0))).real for m in np.nonzero(sel)[0])
+        assert np.abs(uu[4, 0] - bx).max() < 1e-13
+    with Solver(emu, **kw) as d:
+        with pytest.raises(Exception, match="outside the grid"):
+            d.set_primitive_modes(np.array([[17, 0, 0]]), np.zeros((7, 1), dtype=complex), back)
 
 
 def test_synthetic_slab_matches_the_mode_sum():

@@ -166,6 +166,21 @@ def test_incompressible_tree_256_properties():
         assert abs(uu[7].mean()) < 1e-14                      # the pressure carries no k=0 mode (mhdrhs.f90:505-508)
 
 
+def test_set_primitive_modes_128():
+    """Initial data from a mode table (laps_set_primitive_modes) against the uploaded host field at 128^3."""
+    n = 128
+    ks, coefs = synthetic.mode_table(24.0, 24.0, 24.0, 1.0, 0.0, 0.0, 8, 8, 8, (101, 116, 132), 0.1, 0.1, 0.01)
+    prim = synthetic.turbulence_slab(n, n, n, 24.0, 24.0, 24.0, kmax=8)
+    kw = dict(nx=n, ny=n, nz=n, Lx=24.0, Ly=24.0, Lz=24.0, dealias_option=1, if_hall=1, ion_inertial_length=0.2)
+    with Solver(**kw) as a, Solver(**kw) as b:
+        a.set_primitive(prim)
+        b.set_primitive_modes(ks, coefs, [1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 1.0])
+        assert np.abs(a.get_state()[0] - b.get_state()[0]).max() < 1e-13
+        a.vardt(); b.vardt()
+        a.step(); b.step()
+        assert pc.rel_l2(b.get_state()[0], a.get_state()[0]) < 1e-12 and abs(a.dt - b.dt) < 1e-13 * a.dt
+
+
 def test_dealias_mask_bit_exact():
     p, prim = pc.make_case(32, 64, 32, hall=False, aeb=False, dealias=1)
     o, g = pc.run_both(p, prim, 1)
