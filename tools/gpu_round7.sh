@@ -10,7 +10,7 @@ echo "pytest rc=$?" >> $OUT/pytest_multirank.log
 for n in 2 $N; do
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 10 --warmup 3 > $OUT/bench_${n}gpu.json 2> $OUT/bench_${n}gpu.err
 done
-timeout 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > $OUT/bench_1gpu.json 2> $OUT/bench_1gpu.err
+
 ls -la $OUT
 tail -5 $OUT/pytest_multirank.log
 python - <<PY
