@@ -576,6 +576,10 @@ int refresh_current(S* s) {
   if (!s->p.if_hall || !s->j_stale) return 0;
   // the state may still hold masked columns here (first stage after laps_set_primitive): no pruning then
   const bool prune = !s->spectrum_full;
+  // The tasks below store into the peers' V1 buffers: every peer must have finished the inverse y pass of the
+  // previous stage (which reads V1) first.  Between two steps driven as evolve; vardt the allreduce of vardt
+  // orders this; laps_step's speculative front half and back-to-back laps_evolve calls have no such call in between.
+  LAPS_TRY(host_barrier(s));
   LAPS_TRY(launch_current_tasks(s, s->uA, prune));
   LAPS_TRY(host_barrier(s));
   LAPS_TRY(inverse_yx(s, 8, 3, prune));
