@@ -608,6 +608,9 @@ int stage_incomp(S* s, int irk) {
   const bool prune = !s->spectrum_full;
   if (s->retransform) LAPS_TRY(spectrum_from_real(s, prune));            // mhd.f90:325
   {  // calc_current_density_real + calc_gradient_velocity_real (mhdrhs.f90:244-391): 12 inverse transforms
+    // (their stores go into the peers' V1 buffers, which the peers read in the inverse y pass that ended the
+    // previous stage: wait for every rank to be past it)
+    LAPS_TRY(host_barrier(s));
     ZParams z; fill_zparams(s, z, prune);
     z.u_in = s->uA;
     for (int j = 0; j < 3; ++j) {
@@ -1239,6 +1242,7 @@ int laps_set_primitive_modes(laps_handle s, int32_t nmodes, const int32_t* k, co
       t.kind = kZInverseOnly; t.v = v; t.gout = v; t.fa = t.fb = t.fx = t.fc = -1;
       z.task[v] = t;
     }
+    LAPS_TRY(host_barrier(s));   // the peers may still be reading their V1 (inverse y pass of the last stage)
     LAPS_TRY(spec_z(s, z, 8, "inv_z"));
     LAPS_TRY(host_barrier(s));
     LAPS_TRY(inverse_yx(s, 0, 8, false));
@@ -1440,6 +1444,7 @@ int laps_max_div_real(laps_handle s, double out[2]) {
     t.kind = kZDiv; t.v = j == 0 ? 4 : 1; t.cx = j == 0 ? 1.0 : (s->incomp ? s->rho0 : 1.0); t.gout = j; t.fa = t.fb = t.fx = t.fc = -1;
     z.task[j] = t;
   }
+  LAPS_TRY(host_barrier(s));   // the peers may still be reading their V1 (inverse y pass of the last stage)
   LAPS_TRY(spec_z(s, z, 2, "div_inv_z"));
   LAPS_TRY(host_barrier(s));
   const size_t vs = (size_t)s->nxh * s->ny * s->nzl;
@@ -1592,6 +1597,7 @@ int laps_fft_inverse(laps_handle s, const double* spec_in, int32_t nfields, doub
     t.kind = kZInverseOnly; t.v = v; t.gout = v; t.fa = t.fb = t.fx = t.fc = -1;
     z.task[v] = t;
   }
+  LAPS_TRY(host_barrier(s));   // the peers may still be reading their V1 (inverse y pass of the last stage)
   LAPS_TRY(spec_z(s, z, nfields, "inv_z"));
   LAPS_CK(s, cudaMemsetAsync(s->uB, 0, 8 * s->csz * sizeof(cplx), s->stream));   // u_B must keep its masked columns zero
   LAPS_TRY(host_barrier(s));
