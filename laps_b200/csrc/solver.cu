@@ -1447,13 +1447,11 @@ int laps_max_div_real(laps_handle s, double out[2]) {
   LAPS_TRY(host_barrier(s));   // the peers may still be reading their V1 (inverse y pass of the last stage)
   LAPS_TRY(spec_z(s, z, 2, "div_inv_z"));
   LAPS_TRY(host_barrier(s));
-  const size_t vs = (size_t)s->nxh * s->ny * s->nzl;
   // the two real fields land in the flux work area (free between stages)
   RealDst d; std::memset(&d, 0, sizeof(d));
   d.ptr[0] = buf_F(s) + (size_t)(s->nf - 2) * s->npts; d.ptr[1] = buf_F(s) + (size_t)(s->nf - 1) * s->npts;
   if (!s->two_d) LAPS_TRY(inv_y(s, buf_V1(s), buf_V2(s), 2, prune));
   LAPS_TRY(inv_x(s, s->two_d ? buf_V1(s) : buf_V2(s), d, 2, prune));
-  (void)vs;
   {
     LaunchScope ls(s, "absmax");
     LAPS_LAUNCH(k_absmax, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, (const double*)d.ptr[0], s->npts, 2, s->d_partial);
@@ -1601,11 +1599,8 @@ int laps_fft_inverse(laps_handle s, const double* spec_in, int32_t nfields, doub
   LAPS_TRY(spec_z(s, z, nfields, "inv_z"));
   LAPS_CK(s, cudaMemsetAsync(s->uB, 0, 8 * s->csz * sizeof(cplx), s->stream));   // u_B must keep its masked columns zero
   LAPS_TRY(host_barrier(s));
-  const size_t vs = (size_t)s->nxh * s->ny * s->nzl;
-  (void)vs;
   if (!s->two_d) LAPS_TRY(inv_y(s, buf_V1(s), buf_V2(s), nfields, false));
-  // real output goes to the flux scratch area?  bufX holds V2; use the prim scratch / J-free area:
-  // write into a temporary device buffer
+  // bufX holds V2 (the x pass's input) and uu must stay untouched: the real fields go to a temporary buffer
   double* tmp = nullptr;
   LAPS_CK(s, cudaMalloc((void**)&tmp, (size_t)nfields * s->npts * sizeof(double)));
   RealDst d; std::memset(&d, 0, sizeof(d));

@@ -63,3 +63,9 @@ def test_three_ranks_remainder_on_last_rank(emu):
 def test_two_ranks_incompressible_tree(emu):
     # src_incompressible: pressure projection, 12 inverse + 6 forward transforms per stage through the same exchange
     run_ranks(2, dict(lib=emu, shape=(16, 16, 16), incompressible=True, case=dict(hall=True, aeb=True, dealias=1), steps=1))
+
+
+def test_eight_ranks_two_of_them_without_surviving_columns(emu):
+    # ny = 32 over 8 ranks with the 1/3 mask (|ky| <= 10 survives): ranks 3 and 4 own rows 12..19 only, i.e. no
+    # column the z pass has to visit — the situation of the 512^3 benchmark on 8 GPUs
+    run_ranks(8, dict(lib=emu, shape=(16, 32, 16), case=dict(hall=True, aeb=True, dealias=1), steps=2))
