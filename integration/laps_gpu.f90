@@ -1,0 +1,104 @@
+! laps_gpu.f90 -- ISO_C_BINDING interface of the laps_b200 C ABI (include/laps_b200.h, ABI version 3).
+! Drop this file into src_compressible/ (or any of the other three source trees) and patch mhd.f90 as
+! INTEGRATION.md section 2 describes.  Not compiled in this repository's image (no Fortran compiler);
+! the same ABI with the same array layouts is exercised through laps_b200/capi.py.
+module laps_gpu
+  use iso_c_binding
+  implicit none
+  integer(c_int), parameter :: LAPS_ABI_VERSION = 3, LAPS_PEER_BLOB_BYTES = 256
+
+  type, bind(C) :: laps_params          ! field order = include/laps_b200.h
+    integer(c_int32_t) :: abi_version
+    integer(c_int32_t) :: nx, ny, nz
+    real(c_double)     :: Lx, Ly, Lz
+    real(c_double)     :: adiabatic_index
+    integer(c_int32_t) :: if_resis, if_resis_exp
+    real(c_double)     :: resistivity
+    integer(c_int32_t) :: if_visc, if_visc_exp
+    real(c_double)     :: viscosity
+    integer(c_int32_t) :: if_conserve_background
+    real(c_double)     :: cfl
+    integer(c_int32_t) :: dealias_option
+    real(c_double)     :: afx, afy, afz
+    integer(c_int32_t) :: if_AEB, if_corotating
+    real(c_double)     :: radius0, Ur0, corotating_angle
+    integer(c_int32_t) :: if_hall
+    real(c_double)     :: ion_inertial_length
+    integer(c_int32_t) :: rank, nranks
+    integer(c_int32_t) :: device
+    integer(c_int32_t) :: ndim                  ! 3 (or 0): 3D trees; 2: src_compressible/2D (nz = 1)
+    integer(c_int32_t) :: if_z_radial           ! 2D/mhd.f90:44
+    integer(c_int32_t) :: if_limit_dt_increase  ! 2D/mhd.f90:23
+    integer(c_int32_t) :: incompressible        ! 1: src_incompressible (uu(8) = pressure)
+    real(c_double)     :: rho0                  ! src_incompressible/mhdinit.f90:15
+  end type
+
+  type, bind(C) :: laps_extents
+    integer(c_int32_t) :: nx, ny, nz, nxh, z_offset, z_size, y_offset, y_size
+  end type
+
+  type(c_ptr) :: gpu = c_null_ptr        ! the handle
+
+  interface
+    integer(c_int) function laps_create(p, h) bind(C, name='laps_create')
+      import; type(laps_params), intent(in) :: p; type(c_ptr), intent(out) :: h
+    end function
+    integer(c_int) function laps_destroy(h) bind(C, name='laps_destroy')
+      import; type(c_ptr), value :: h
+    end function
+    type(c_ptr) function laps_last_error(h) bind(C, name='laps_last_error')
+      import; type(c_ptr), value :: h
+    end function
+    integer(c_int) function laps_get_extents(h, e) bind(C, name='laps_get_extents')
+      import; type(c_ptr), value :: h; type(laps_extents), intent(out) :: e
+    end function
+    integer(c_int) function laps_export_peer_blob(h, blob) bind(C, name='laps_export_peer_blob')
+      import; type(c_ptr), value :: h; character(kind=c_char) :: blob(*)
+    end function
+    integer(c_int) function laps_import_peer_blobs(h, blobs) bind(C, name='laps_import_peer_blobs')
+      import; type(c_ptr), value :: h; character(kind=c_char) :: blobs(*)
+    end function
+    integer(c_int) function laps_set_primitive(h, uu) bind(C, name='laps_set_primitive')
+      import; type(c_ptr), value :: h; real(c_double), intent(in) :: uu(*)
+    end function
+    integer(c_int) function laps_set_time(h, t) bind(C, name='laps_set_time')
+      import; type(c_ptr), value :: h; real(c_double), value :: t
+    end function
+    integer(c_int) function laps_vardt(h, dt) bind(C, name='laps_vardt')
+      import; type(c_ptr), value :: h; real(c_double), intent(inout) :: dt
+    end function
+    integer(c_int) function laps_evolve(h) bind(C, name='laps_evolve')
+      import; type(c_ptr), value :: h
+    end function
+    integer(c_int) function laps_max_divb(h, v) bind(C, name='laps_max_divb')
+      import; type(c_ptr), value :: h; real(c_double), intent(out) :: v
+    end function
+    integer(c_int) function laps_rms(h, out19) bind(C, name='laps_rms')
+      import; type(c_ptr), value :: h; real(c_double), intent(out) :: out19(19)
+    end function
+    integer(c_int) function laps_get_state(h, uu, uu_prim) bind(C, name='laps_get_state')
+      import; type(c_ptr), value :: h; real(c_double) :: uu(*), uu_prim(*)
+    end function
+    integer(c_int) function laps_get_output(h, out8, primitive) bind(C, name='laps_get_output')
+      import; type(c_ptr), value :: h; real(c_double) :: out8(*); integer(c_int32_t), value :: primitive
+    end function
+    integer(c_int) function laps_step(h, time, dt) bind(C, name='laps_step')
+      import; type(c_ptr), value :: h; real(c_double), intent(inout) :: time, dt
+    end function
+    integer(c_int) function laps_set_primitive_modes(h, nmodes, k, coef, background) bind(C, name='laps_set_primitive_modes')
+      import; type(c_ptr), value :: h; integer(c_int32_t), value :: nmodes
+      integer(c_int32_t), intent(in) :: k(3,*); complex(c_double_complex), intent(in) :: coef(nmodes,7)
+      real(c_double), intent(in) :: background(8)
+    end function
+    ! incompressible driver only (src_incompressible/mhd.f90:157-161,620-732)
+    integer(c_int) function laps_max_divv(h, v) bind(C, name='laps_max_divv')
+      import; type(c_ptr), value :: h; real(c_double), intent(out) :: v
+    end function
+    integer(c_int) function laps_max_div_real(h, out2) bind(C, name='laps_max_div_real')
+      import; type(c_ptr), value :: h; real(c_double), intent(out) :: out2(2)
+    end function
+    integer(c_int) function laps_get_rho0(h, rho0) bind(C, name='laps_get_rho0')
+      import; type(c_ptr), value :: h; real(c_double), intent(out) :: rho0
+    end function
+  end interface
+end module laps_gpu
