@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define LAPS_ABI_VERSION 3
+#define LAPS_ABI_VERSION 4
 #define LAPS_MAX_RANKS 8
 
 typedef struct laps_solver* laps_handle;
@@ -66,6 +66,10 @@ typedef struct laps_extents {
   int32_t nx, ny, nz, nxh;       /* nxh = nx/2+1 */
   int32_t z_offset, z_size;      /* real space: z in Zj(rank)   (zj_offset/zj_size) */
   int32_t y_offset, y_size;      /* Fourier space: ky in Yj(rank) (yj_offset/yj_size) */
+  int32_t y_stride;              /* this rank's Fourier rows are ky = y_offset + j * y_stride, j < y_size.  1: the reference's
+                                  * contiguous slabs (default).  nranks: rows dealt round-robin (LAPS_TUNE_CYCLIC=1, experimental:
+                                  * the rows the dealiasing mask keeps are then spread evenly over the ranks; real space, every
+                                  * result and every driver-facing array are unaffected) */
 } laps_extents;
 
 /* parallel_start + fftw_initialize + grid_initialize + arrays_initialize + AEB_initialize +

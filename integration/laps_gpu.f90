@@ -1,11 +1,11 @@
-! laps_gpu.f90 -- ISO_C_BINDING interface of the laps_b200 C ABI (include/laps_b200.h, ABI version 3).
+! laps_gpu.f90 -- ISO_C_BINDING interface of the laps_b200 C ABI (include/laps_b200.h, ABI version 4).
 ! Drop this file into src_compressible/ (or any of the other three source trees) and patch mhd.f90 as
 ! INTEGRATION.md section 2 describes.  Not compiled in this repository's image (no Fortran compiler);
 ! the same ABI with the same array layouts is exercised through laps_b200/capi.py.
 module laps_gpu
   use iso_c_binding
   implicit none
-  integer(c_int), parameter :: LAPS_ABI_VERSION = 3, LAPS_PEER_BLOB_BYTES = 256
+  integer(c_int), parameter :: LAPS_ABI_VERSION = 4, LAPS_PEER_BLOB_BYTES = 256
 
   type, bind(C) :: laps_params          ! field order = include/laps_b200.h
     integer(c_int32_t) :: abi_version
@@ -34,7 +34,7 @@ module laps_gpu
   end type
 
   type, bind(C) :: laps_extents
-    integer(c_int32_t) :: nx, ny, nz, nxh, z_offset, z_size, y_offset, y_size
+    integer(c_int32_t) :: nx, ny, nz, nxh, z_offset, z_size, y_offset, y_size, y_stride
   end type
 
   type(c_ptr) :: gpu = c_null_ptr        ! the handle

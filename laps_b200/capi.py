@@ -14,7 +14,7 @@ from typing import Optional
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_RANKS = 8
 PEER_BLOB_BYTES = 256
 
@@ -50,7 +50,7 @@ class LapsParams(C.Structure):
 class LapsExtents(C.Structure):
     _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32), ("nxh", C.c_int32),
                 ("z_offset", C.c_int32), ("z_size", C.c_int32),
-                ("y_offset", C.c_int32), ("y_size", C.c_int32)]
+                ("y_offset", C.c_int32), ("y_size", C.c_int32), ("y_stride", C.c_int32)]
 
 
 # every symbol include/laps_b200.h declares (tests check that the library exports all of them)

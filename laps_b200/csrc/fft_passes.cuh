@@ -27,7 +27,15 @@ struct PeerTable {
   int len[kMaxPeers];   // number owned
   int nparts;
   int quot;             // n / nparts (owner = min(i / quot, nparts-1))
-  LAPS_HD int owner(int i) const { int p = i / quot; return p < nparts - 1 ? p : nparts - 1; }
+  // cyclic = 0: contiguous slabs, the reference's decompose_1d (parallel.f90:326-349).  cyclic = 1 (ky axis only,
+  // LAPS_TUNE_CYCLIC): index i lives on rank i % nparts at local position i / nparts, which spreads the rows the
+  // dealiasing mask keeps (low |ky|) evenly over the ranks.
+  int cyclic;
+  LAPS_HD int owner(int i) const {
+    if (cyclic) return i % nparts;
+    int p = i / quot; return p < nparts - 1 ? p : nparts - 1;
+  }
+  LAPS_HD int local(int i, int p) const { return cyclic ? i / nparts : i - off[p]; }
 };
 
 // Shared-memory tile of TL lines.  A quarter warp (8 lanes of a 128-bit access) covers
@@ -139,7 +147,7 @@ k_fwd_y(const cplx* __restrict__ W1, PeerTable W2, int nzl, int nz, int zoff,
       const int ky = F::kout(u, e);
       if (ky > kymax && ky < N - kymax) continue;   // rows the dealiasing mask removes entirely
       const int p = W2.owner(ky);
-      cplx* dst = W2.base[p] + (((size_t)f * nxh + kx) * W2.len[p] + (ky - W2.off[p])) * nz + zoff + z0 + l;
+      cplx* dst = W2.base[p] + (((size_t)f * nxh + kx) * W2.len[p] + W2.local(ky, p)) * nz + zoff + z0 + l;
       *dst = cscale(r[e], scale);
     }
   }

@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) k_moments2(const double* uu, size_t n, do
 
 // mhd.f90:541-568: max | kx Bx^ + ky By^ + kz Bz^ | over the local modes; u = [8][ncol][nz]
 struct DivbParams {
-  const cplx* u; size_t fstride; int ncol, nz, nyl, yoff;
+  const cplx* u; size_t fstride; int ncol, nz, nyl, yoff, ystride;   // ky = yoff + kyl * ystride
   const double* kxr; const double* kyr; const double* kze;
   double radius0, radius, cosa, sina; int corot_k;
   int mode2d, z_radial;   // 2D tree: the line axis carries ky, kz = 0 (2D/mhd.f90:527-550)
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256) k_divb(const DivbParams P) {
   const size_t total = (size_t)P.ncol * P.nz;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int col = (int)(i / P.nz), kz = (int)(i % P.nz);
-    const int kx = col / P.nyl, ky = P.yoff + col % P.nyl;
+    const int kx = col / P.nyl, ky = P.yoff + (col % P.nyl) * P.ystride;
     const double kxr = P.kxr[kx], kyr = P.kyr[ky];
     double kxe = kxr, kye = __ddiv_rn(__dmul_rn(kyr, P.radius0), P.radius);
     if (P.corot_k) {

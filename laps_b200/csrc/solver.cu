@@ -78,6 +78,8 @@ struct laps_solver {
   int nx, ny, nz, nxh, P, rank;
   int zoffs[LAPS_MAX_RANKS], zlens[LAPS_MAX_RANKS], yoffs[LAPS_MAX_RANKS], ylens[LAPS_MAX_RANKS];
   int nzl, nyl, zo, yo;
+  int ystride = 1;       // global ky of local Fourier row kyl: yo + kyl * ystride (1: reference slabs; P: cyclic rows)
+  bool cyclic = false;   // LAPS_TUNE_CYCLIC=1: ky rows dealt round-robin to the ranks (balances the dealiased z pass)
   size_t npts;   // nx*ny*nzl      (real points per field)
   size_t ncol;   // nxh*nyl        (spectral columns)
   size_t csz;    // ncol*nz        (spectral elements per field)
@@ -474,7 +476,7 @@ void fill_zparams(S* s, ZParams& z, bool prune = false) {
     z.kzprune = s->kzprune ? 1 : 0;
   } else { z.nkyl = s->nyl; z.nA = s->nyl; z.a0 = 0; z.b0 = 0; z.ncolc = (int)s->ncol; }
   const laps_params& p = s->p;
-  z.nxh = s->nxh; z.ny = s->ny; z.nyl = s->nyl; z.yoff = s->yo; z.nz = s->nz; z.ncol = (int)s->ncol;
+  z.nxh = s->nxh; z.ny = s->ny; z.nyl = s->nyl; z.yoff = s->yo; z.ystride = s->ystride; z.nz = s->nz; z.ncol = (int)s->ncol;
   z.W2 = buf_W2(s); z.fstride = s->csz;
   z.u_in = s->uA; z.u_out = s->uB; z.fnl_rk = s->rk;
   z.V1 = s->tabV1; z.tw = s->tw_z;
@@ -901,6 +903,11 @@ int laps_create(const laps_params* params, laps_handle* out) {
   s->nx = p.nx; s->ny = p.ny; s->nz = p.nz; s->nxh = p.nx / 2 + 1; s->P = p.nranks; s->rank = p.rank;
   decompose_1d(s->nz, s->P, s->zoffs, s->zlens);   // zj_offset/zj_size (parallel.f90:102)
   decompose_1d(s->ny, s->P, s->yoffs, s->ylens);   // yj_offset/yj_size (parallel.f90:101)
+  if (const char* e = std::getenv("LAPS_TUNE_CYCLIC")) s->cyclic = std::atoi(e) != 0 && s->P > 1 && !two_d;
+  if (s->cyclic) {   // row ky belongs to rank ky % P; rank q holds rows q, q + P, q + 2P, ...
+    for (int q = 0; q < s->P; ++q) { s->yoffs[q] = q; s->ylens[q] = (s->ny - q + s->P - 1) / s->P; }
+    s->ystride = s->P;
+  }
   s->nzl = s->zlens[s->rank]; s->zo = s->zoffs[s->rank];
   s->nyl = s->ylens[s->rank]; s->yo = s->yoffs[s->rank];
   s->npts = (size_t)s->nx * s->ny * s->nzl;
@@ -1017,13 +1024,14 @@ int laps_create(const laps_params* params, laps_handle* out) {
       }
     }
     // this rank's surviving ky rows: run A = owned rows with ky <= kymax, run B = owned rows with ky >= ny - kymax
-    const int y0 = s->yo, y1 = s->yo + s->nyl;
-    const int aEnd = std::min(y1, s->kymax + 1);
-    s->pr_a0 = 0; s->pr_nA = std::max(0, aEnd - y0);
-    const int bBeg = std::max(std::max(y0, s->ny - s->kymax), y0 + s->pr_nA);
-    s->pr_b0 = bBeg - y0;
-    const int nB = std::max(0, y1 - bBeg);
-    s->pr_nkyl = s->pr_nA + nB;
+    // (local rows are in increasing ky for slabs and for cyclic ownership alike)
+    auto ky_of = [&](int kyl) { return s->yo + kyl * s->ystride; };
+    int nA = 0;
+    while (nA < s->nyl && ky_of(nA) <= s->kymax) ++nA;
+    int b0 = nA;
+    while (b0 < s->nyl && ky_of(b0) < s->ny - s->kymax) ++b0;
+    s->pr_a0 = 0; s->pr_nA = nA; s->pr_b0 = b0;
+    s->pr_nkyl = nA + (s->nyl - b0);
     if (s->kymax >= s->ny / 2) { s->pr_nkyl = s->nyl; s->pr_nA = s->nyl; s->pr_a0 = 0; s->pr_b0 = 0; }
     s->pr_ncol = s->nkx * s->pr_nkyl;
     const double* daz = day + s->ny;
@@ -1043,7 +1051,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
         kym[kx] = km;
         for (int r = 0; r < s->pr_nkyl; ++r) {
           const int kyl = r < s->pr_nA ? s->pr_a0 + r : s->pr_b0 + r - s->pr_nA;
-          const int ky = s->yo + kyl;
+          const int ky = ky_of(kyl);
           if (!(dax[kx] + day[ky] >= s->da_thresh)) cmap.push_back(kx * s->nyl + kyl);
         }
       }
@@ -1059,7 +1067,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
       long long m = 0;
       for (int kx = 0; kx < s->nxh; ++kx)
         for (int kyl = 0; kyl < s->nyl; ++kyl) {
-          const double dxy = (p.dealias_option == 1 || p.dealias_option == 3) ? dax[kx] + day[s->yo + kyl] : 0.0;
+          const double dxy = (p.dealias_option == 1 || p.dealias_option == 3) ? dax[kx] + day[ky_of(kyl)] : 0.0;
           for (int kz = 0; kz < s->nz; ++kz) {
             bool dead = false;
             if (masked && p.dealias_option == 1) dead = dxy + daz[kz] >= s->da_thresh;
@@ -1102,6 +1110,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
   s->tabW2.quot = s->ny / s->P; s->tabV1.quot = s->nz / s->P;
   for (int q = 0; q < s->P; ++q) {
     s->tabW2.off[q] = s->yoffs[q]; s->tabW2.len[q] = s->ylens[q];
+    s->tabW2.cyclic = s->cyclic ? 1 : 0;
     s->tabV1.off[q] = s->zoffs[q]; s->tabV1.len[q] = s->zlens[q];
   }
   s->tabW2.base[s->rank] = buf_W2(s);
@@ -1139,9 +1148,9 @@ int laps_destroy(laps_handle s) {
 int laps_get_extents(laps_handle s, laps_extents* e) {
   if (!s || !e) return 1;
   e->nx = s->nx; e->ny = s->ny; e->nz = s->nz; e->nxh = s->nxh;
-  e->z_offset = s->zo; e->z_size = s->nzl; e->y_offset = s->yo; e->y_size = s->nyl;
+  e->z_offset = s->zo; e->z_size = s->nzl; e->y_offset = s->yo; e->y_size = s->nyl; e->y_stride = s->ystride;
   if (s->two_d) {  // the driver's view: uu(1:nx, 1:ny, 1, 1:8); spectral block (kx, all ky)
-    e->ny = s->nz; e->nz = 1; e->z_offset = 0; e->z_size = 1; e->y_offset = 0; e->y_size = s->nz;
+    e->ny = s->nz; e->nz = 1; e->z_offset = 0; e->z_size = 1; e->y_offset = 0; e->y_size = s->nz; e->y_stride = 1;
   }
   return 0;
 }
@@ -1213,12 +1222,12 @@ int laps_set_primitive_modes(laps_handle s, int32_t nmodes, const int32_t* k, co
     const int kyr = (iky + NYr) % NYr;
     // internal axes: 3D (kx, ky, kz); 2D tree (kx, 0, ky) — the line axis carries the driver's ky
     const int ky = s->two_d ? 0 : kyr, kz = s->two_d ? kyr : (ikz + s->nz) % s->nz;
-    if (ky < s->yo || ky >= s->yo + s->nyl) continue;          // another rank owns this row
+    if (s->tabW2.owner(ky) != s->rank) continue;                // another rank owns this row
     const double w = ikx > 0 ? 0.5 : 1.0;                      // the c2r x pass doubles kx > 0 and keeps Re of kx = 0
     cplx c8[8];
     for (int v = 0; v < 7; ++v) c8[v] = mk(w * coef[2 * ((size_t)v * nmodes + m)], w * coef[2 * ((size_t)v * nmodes + m) + 1]);
     c8[7] = mk(0.0, 0.0);
-    push(((long long)ikx * s->nyl + (ky - s->yo)) * s->nz + kz, c8);
+    push(((long long)ikx * s->nyl + s->tabW2.local(ky, s->rank)) * s->nz + kz, c8);
   }
   const int nent = (int)idx.size();
   for (int v = 0; v < 8; ++v) val.insert(val.end(), rows[v].begin(), rows[v].end());
@@ -1400,7 +1409,7 @@ int laps_get_profile(laps_handle s, char* names, float* ms, int32_t cap, int32_t
 static int max_div_fourier(laps_handle s, int v0, double* out) {
   DivbParams d;
   d.v0 = v0;
-  d.u = s->uA; d.fstride = s->csz; d.ncol = (int)s->ncol; d.nz = s->nz; d.nyl = s->nyl; d.yoff = s->yo;
+  d.u = s->uA; d.fstride = s->csz; d.ncol = (int)s->ncol; d.nz = s->nz; d.nyl = s->nyl; d.yoff = s->yo; d.ystride = s->ystride;
   d.kxr = s->kxr; d.kyr = s->kyr; d.kze = s->kze;
   d.radius0 = s->p.radius0; d.radius = s->radius; d.cosa = s->cosa; d.sina = s->sina;
   d.corot_k = (s->p.if_AEB && s->p.if_corotating) ? 1 : 0;
@@ -1624,7 +1633,7 @@ int laps_transpose_yz_indexmap(laps_handle s, int64_t* out) {
       const int pq = s->tabW2.owner(ky);
       for (int zl = 0; zl < s->nzl; ++zl, ++i) {
         out[2 * i] = pq;
-        out[2 * i + 1] = ((int64_t)kx * s->tabW2.len[pq] + (ky - s->tabW2.off[pq])) * s->nz + s->zo + zl;
+        out[2 * i + 1] = ((int64_t)kx * s->tabW2.len[pq] + s->tabW2.local(ky, pq)) * s->nz + s->zo + zl;
       }
     }
   return 0;

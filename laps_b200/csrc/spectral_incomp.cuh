@@ -45,7 +45,7 @@ k_incomp_z(const ZParams P) {
   const bool live = colm >= 0;
   const int col = live ? colm : 0;
   const int kx = col / P.nyl;
-  const int ky = P.yoff + col % P.nyl;
+  const int ky = P.yoff + (col % P.nyl) * P.ystride;
   const size_t coff = (size_t)col * N;
   cplx* W = sm + l * T::COLSTRIDE;   // padded work line of the transforms
   cplx* S0 = W + T::PITCH;           // thread-private slots e*NT + u (forward OUTPUT order)

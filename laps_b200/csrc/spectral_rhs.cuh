@@ -92,7 +92,7 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
     const bool live = colm >= 0;
     const int col = live ? colm : 0;
     const int kx = col / P.nyl;
-    const int ky = P.yoff + col % P.nyl;
+    const int ky = P.yoff + (col % P.nyl) * P.ystride;
     const size_t coff = (size_t)col * N;
     const size_t voff = (size_t)K.v * P.fstride + coff;
     const bool hasC = K.fc >= 0;
@@ -114,7 +114,7 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
           // (state lines: not the 128-byte groups that lie entirely inside the masked kz interval)
           bool want = true;
           if (P.kzprune) {
-            const int kxn = coln / P.nyl, kyn = P.yoff + coln % P.nyl;
+            const int kxn = coln / P.nyl, kyn = P.yoff + (coln % P.nyl) * P.ystride;
             const double dn = __dadd_rn(__ldg(P.dax + kxn), __ldg(P.day + kyn));
             const int k0 = u * (N / G::NT);
             want = !(z_mode_dead(P, dn, k0) && z_mode_dead(P, dn, k0 + N / G::NT - 1));

@@ -40,7 +40,7 @@ struct ZTask {
 };
 
 struct ZParams {
-  int nxh, ny, nyl, yoff, nz, ncol;
+  int nxh, ny, nyl, yoff, ystride, nz, ncol;   // global ky of local row kyl: yoff + kyl * ystride (slabs: stride 1)
   const cplx* W2;        // [f][col][z]
   size_t fstride;        // ncol * nz
   const cplx* u_in;      // [v][col][kz]
@@ -164,7 +164,7 @@ k_spec_z(const ZParams P) {
   const bool live = colm >= 0;
   const int col = live ? colm : 0;
   const int kx = col / P.nyl;
-  const int ky = P.yoff + col % P.nyl;
+  const int ky = P.yoff + (col % P.nyl) * P.ystride;
   cplx* lineG = sm + l * T::COLSTRIDE;
   cplx* stash = lineG + T::PITCH;          // thread-private slots e*NT + u
   const size_t coff = (size_t)col * N;

@@ -31,6 +31,8 @@ class Solver:
         self.ext = ext
         self.nx, self.ny, self.nz, self.nxh = ext.nx, ext.ny, ext.nz, ext.nxh
         self.nzl, self.nyl = ext.z_size, ext.y_size
+        # global ky of this rank's Fourier rows (contiguous slab by default, see laps_extents.y_stride)
+        self.ky_rows = ext.y_offset + np.arange(ext.y_size) * max(1, ext.y_stride)
         self.time = 0.0
         self.dt = 0.0
 

@@ -48,12 +48,17 @@ def main():
     g = Solver(lib, rank=rank, nranks=world, device=rank if backend == "nccl" else 0, **pc.solver_kwargs(p))
     connect(g, world, device)
     zo, zn, yo, yn = g.ext.z_offset, g.ext.z_size, g.ext.y_offset, g.ext.y_size
+    rows = g.ky_rows                      # this rank's Fourier rows (a contiguous slab unless LAPS_TUNE_CYCLIC=1)
+    cyclic = g.ext.y_stride > 1
 
     # decomposition tables: decompose_1d gives n/P each, the remainder to the last rank (parallel.f90:326-349)
     q = nz // world
     assert zo == rank * q and zn == (q if rank < world - 1 else nz - (world - 1) * q)
     q = ny // world
-    assert yo == rank * q and yn == (q if rank < world - 1 else ny - (world - 1) * q)
+    if cyclic:
+        assert np.array_equal(rows, np.arange(rank, ny, world))
+    else:
+        assert yo == rank * q and yn == (q if rank < world - 1 else ny - (world - 1) * q)
 
     # transpose_yz index map against SURVEY 9.9: element (gx, gy, gz) of w_yxz goes to the owner of gy,
     # local offset gx + nxh*((gy - yj_off) + yj_size*gz) in the reference; this library keeps z fastest:
@@ -62,16 +67,21 @@ def main():
     offs, sizes = lo.decompose_1d(ny, world)
     owner = np.minimum(np.arange(ny) // (ny // world), world - 1)
     kx, ky, zl = np.meshgrid(np.arange(g.nxh), np.arange(ny), np.arange(zn), indexing="ij")
-    assert np.array_equal(m[..., 0], owner[ky])
-    assert np.array_equal(m[..., 1], (kx * np.asarray(sizes)[owner[ky]] + (ky - np.asarray(offs)[owner[ky]])) * nz + zo + zl)
+    if cyclic:   # the experimental round-robin ownership: ky -> rank ky % P, local row ky // P
+        cnt = np.array([len(range(r, ny, world)) for r in range(world)])
+        assert np.array_equal(m[..., 0], ky % world)
+        assert np.array_equal(m[..., 1], (kx * cnt[ky % world] + ky // world) * nz + zo + zl)
+    else:
+        assert np.array_equal(m[..., 0], owner[ky])
+        assert np.array_equal(m[..., 1], (kx * np.asarray(sizes)[owner[ky]] + (ky - np.asarray(offs)[owner[ky]])) * nz + zo + zl)
 
     # FFT of a position-encoding field (the idea of ipert=999, mhdinit.f90:1021-1030)
     rng = np.random.default_rng(7)
     a = rng.standard_normal((2, nz, ny, nx))
     w = g.fft_forward(a[:, zo:zo + zn])
     ref = lo.fft_forward(a)
-    assert pc.rel_l2(w, ref[:, :, yo:yo + yn, :]) < 1e-13
-    b = g.fft_inverse(np.ascontiguousarray(ref[:, :, yo:yo + yn, :]))
+    assert pc.rel_l2(w, ref[:, :, rows, :]) < 1e-13
+    b = g.fft_inverse(np.ascontiguousarray(ref[:, :, rows, :]))
     assert pc.rel_l2(b, a[:, zo:zo + zn]) < 1e-13
 
     # the RK step, driven like mhd.f90: vardt; nsteps x (evolve; evolve_radius; vardt)
@@ -90,7 +100,7 @@ def main():
         assert pc.rel_l2(uu[v], o.uu[v, zo:zo + zn]) < tol, (v, pc.rel_l2(uu[v], o.uu[v, zo:zo + zn]))
     uf = g.uu_fourier()
     for v in range(8):
-        assert pc.rel_l2(uf[v], o.uu_fourier[v][:, yo:yo + yn, :]) < tol * max(1.0, np.linalg.norm(o.uu_fourier[v]) / max(np.linalg.norm(o.uu_fourier[v][:, yo:yo + yn, :]), 1e-300))
+        assert pc.rel_l2(uf[v], o.uu_fourier[v][:, rows, :]) < tol * max(1.0, np.linalg.norm(o.uu_fourier[v]) / max(np.linalg.norm(o.uu_fourier[v][:, rows, :]), 1e-300))
     assert abs(g.dt - o.dt) <= 1e-12 * o.dt
     # diagnostics are global (allreduce) and identical on every rank
     ave, rms, ru2 = g.calc_rms()

@@ -29,7 +29,7 @@ def run_ranks(world, cfg, timeout=600):
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
-                   MASTER_PORT=str(port), OMP_NUM_THREADS="1", LAPS_ORACLE_WORKERS="2")
+                   MASTER_PORT=str(port), OMP_NUM_THREADS="1", LAPS_ORACLE_WORKERS="2", **cfg.get("env", {}))
         procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "mp_worker.py"), json.dumps(cfg)],
                                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = []
@@ -69,3 +69,15 @@ def test_eight_ranks_two_of_them_without_surviving_columns(emu):
     # ny = 32 over 8 ranks with the 1/3 mask (|ky| <= 10 survives): ranks 3 and 4 own rows 12..19 only, i.e. no
     # column the z pass has to visit — the situation of the 512^3 benchmark on 8 GPUs
     run_ranks(8, dict(lib=emu, shape=(16, 32, 16), case=dict(hall=True, aeb=True, dealias=1), steps=2))
+
+
+@pytest.mark.parametrize("world,shape", [(2, (16, 16, 16)), (3, (16, 16, 16)), (8, (16, 32, 16))])
+def test_cyclic_ky_ownership(emu, world, shape):
+    """LAPS_TUNE_CYCLIC=1 (experimental): Fourier rows dealt round-robin to the ranks.  Same results as the slab
+    ownership — the oracle parity, the distributed FFT and the allreduces of mp_worker hold unchanged."""
+    run_ranks(world, dict(lib=emu, shape=shape, case=dict(hall=True, aeb=True, dealias=1), steps=2, env=dict(LAPS_TUNE_CYCLIC="1")))
+
+
+def test_cyclic_ky_ownership_incompressible(emu):
+    run_ranks(2, dict(lib=emu, shape=(16, 16, 16), incompressible=True, case=dict(hall=True, aeb=True, dealias=2), steps=1,
+                      env=dict(LAPS_TUNE_CYCLIC="1")))
