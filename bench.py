@@ -314,6 +314,16 @@ def run_gpu(args):
     top = max(prof.items(), key=lambda kv: kv[1][0]) if prof else None
     roofline = None
     shares = {}
+    # DRAM bytes per launch measured by ncu --set full for this exact configuration (committed capture), or None
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01i_traffic.json")) as f:
+            tj = json.load(f)
+        c = tj["config"]
+        if (c["n"], c["n_gpus"], c["if_hall"], c["if_AEB"], c["dealias_option"]) == (n, world, kw["if_hall"], kw["if_AEB"], kw["dealias_option"]):
+            traffic, traffic_src = {k: v["dram_bytes_per_launch"] for k, v in tj["kernels"].items()}, tj["source"]
+    except Exception:
+        pass
     if top:
         tot = sum(v[0] for v in prof.values())
         shares = {k: round(v[0] / tot, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
@@ -322,7 +332,8 @@ def run_gpu(args):
         avg_ms = tms / cnt
         ach = b / (avg_ms * 1e-3) / 1e9 if b else None
         roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                    "frac": (ach / peak) if ach else None, "traffic": (traffic or {}).get(name), "traffic_source": traffic_src if (traffic or {}).get(name) else None,
+                    "peak_source": peak_src,
                     "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": b,
                     "per_kernel_GBps": {k: (kb(k) or 0) / (v[0] / v[1] * 1e-3) / 1e9 for k, v in prof.items() if kb(k)},
                     "pruning": {"nkx": nkx, "nxh": g.nxh, "kymax": kymax, "ny": n, "nky_local": nkyl, "live_column_fraction": fcol, "live_mode_fraction": fmode,
