@@ -399,3 +399,80 @@ def test_incompressible_2d_state_equals_a_z_uniform_3d_state():
         s_.evolve()
     assert all(np.array_equal(a.uu[v][0], b.uu[v][2]) for v in range(8))
     assert a.rho0 == b.rho0
+
+
+# --------------------------------------------------------------------------------------
+# Hall term: circularly polarised parallel waves are exact solutions of Hall-MHD
+# --------------------------------------------------------------------------------------
+def _hall_wave_error(cls, omega_sign, dt, T=0.3, di=0.5, kint=2, b0=0.05, incompressible=False):
+    """B = B0 x^ + b(x,t), b_y + i b_z = b0 exp(i(kx - wt)), u_perp = -(B0 k / (rho w)) b_perp, |b| uniform.
+    With E = -u x B + (di/rho) J x B (mhdrhs.f90:82-84,108-121) and dB/dt = -curl E this is an exact nonlinear
+    solution when  w^2 + (di B0 k^2 / rho) w - (B0 k)^2 / rho = 0  (whistler and ion-cyclotron branches)."""
+    L = 2 * lo.PI
+    p = lo.Params(nx=32, ny=8, nz=8, Lx=L, Ly=L, Lz=L, dealias_option=1, if_hall=True, ion_inertial_length=di,
+                  incompressible=incompressible)
+    B0, rho, k = 1.0, 1.0, float(kint)
+    sig = di * B0 * k * k / rho
+    w = 0.5 * (-sig + omega_sign * math.sqrt(sig * sig + 4 * k * k * B0 * B0 / rho))
+    x = lo.Grid(p).xgrid[None, None, :]
+    prim = lo.ic_uniform_background(p, bx0=B0, press0=1.0)
+    amp = -(B0 * k / (rho * w))
+    prim[5] += b0 * np.cos(k * x)
+    prim[6] += b0 * np.sin(k * x)
+    prim[2] += amp * b0 * np.cos(k * x)
+    prim[3] += amp * b0 * np.sin(k * x)
+    s = cls(p)
+    s.set_primitive(prim)
+    s.dt = dt
+    s.rkt_init(dt)
+    for _ in range(int(round(T / dt))):
+        s.evolve()
+        s.time += dt
+        s.evolve_radius(s.time)
+        s.rkt_init(dt)
+    xs = lo.Grid(p).xgrid
+    err = max(np.abs(s.uu[5][0, 0, :] - b0 * np.cos(k * xs - w * s.time)).max(),
+              np.abs(s.uu[6][0, 0, :] - b0 * np.sin(k * xs - w * s.time)).max())
+    return err / b0, w, s
+
+
+@pytest.mark.parametrize("cls,inc", [(lo.State, False), (lo.StateIncompressible, True)])
+@pytest.mark.parametrize("omega_sign", [+1, -1])
+def test_hall_wave_dispersion_both_branches(cls, inc, omega_sign):
+    """Pins the Hall electric field, J = curl B and the curl in the induction equation quantitatively: the wave must
+    travel at the Hall-MHD phase speed of its branch (not the Alfven speed) with the RK3 error only."""
+    e1, w, _ = _hall_wave_error(cls, omega_sign, 0.01, incompressible=inc)
+    e2, _, s = _hall_wave_error(cls, omega_sign, 0.005, incompressible=inc)
+    assert abs(abs(w) - 2.0) > 0.5                     # far from the Alfven frequency k v_A = 2: the Hall term matters
+    assert e1 < 2e-5 and e2 < 3e-6 and 6.0 < e1 / e2 < 10.0, (e1, e2)
+    assert np.abs(s.uu[0] - 1.0).max() < 1e-12        # |B| uniform: no compression
+    assert s.calc_max_divB() < 1e-14
+
+
+@pytest.mark.parametrize("explicit", [False, True])
+def test_resistive_decay_of_a_force_free_field_is_exact(explicit):
+    """b = b0 (0, cos kx, sin kx) with u = 0, B0 = 0: |b| uniform, J x B = 0, nothing moves, and the field only
+    diffuses.  Implicit treatment (rktmod.f90:54-60): each stage divides by 1 + ts_i dt k^2 eta; explicit
+    (mhdrhs.f90:262-275): the RK3 stability polynomial of z = -eta k^2 dt."""
+    L, k, eta, dt = 2 * lo.PI, 3.0, 0.05, 0.02
+    p = lo.Params(nx=32, ny=8, nz=8, Lx=L, Ly=L, Lz=L, dealias_option=1, if_resis=True, resistivity=eta, if_resis_exp=explicit)
+    x = lo.Grid(p).xgrid[None, None, :]
+    prim = lo.ic_uniform_background(p, press0=1.0)
+    prim[5] += 0.1 * np.cos(k * x)
+    prim[6] += 0.1 * np.sin(k * x)
+    s = lo.State(p)
+    s.set_primitive(prim)
+    b0 = s.uu_fourier[5, 0, 0, 3]
+    s.dt = dt
+    s.rkt_init(dt)
+    nsteps = 5
+    for _ in range(nsteps):
+        s.evolve()
+        s.rkt_init(dt)
+    z = -eta * k * k * dt
+    if explicit:
+        factor = (1 + z + z * z / 2 + z ** 3 / 6) ** nsteps
+    else:
+        factor = np.prod([1.0 / (1.0 - ts * z) for ts in (8.0 / 15.0, 2.0 / 15.0, 1.0 / 3.0)]) ** nsteps
+    assert abs(s.uu_fourier[5, 0, 0, 3] / b0 - factor) < 1e-13
+    assert np.abs(s.uu[1:4]).max() < 1e-15 and np.abs(s.uu[0] - 1.0).max() < 1e-14
