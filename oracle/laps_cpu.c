@@ -1,0 +1,449 @@
+/* CPU restatement (C + OpenMP) of the LAPS 3D compressible Hall-MHD + expanding-box RK step.
+ *
+ * TEST / BASELINE INFRASTRUCTURE ONLY: nothing in the product package links or loads this file.  It is the
+ * "port" that bench.py times as the CPU baseline (cpu_baseline, --impl reference) because the reference's own
+ * Fortran + MPI + FFTW build cannot be produced in this image.  PARITY UNPINNED in the same sense as
+ * oracle/laps_oracle.py (no reference run, no golden vectors); tests/test_cpu_port.py checks it against that
+ * NumPy oracle, which carries the analytic pins.
+ *
+ * It keeps the reference's STRUCTURE (file:line relative to /root/reference/src_compressible/): module-level
+ * arrays (mhdinit.f90:141-178), one field at a time through line-at-a-time 1-D transforms with strided
+ * gather/scatter (fftw.f90:42-103,136-222; mhdrhs.f90:128-172), separate pointwise sweeps for calc_flux
+ * (mhdrhs.f90:21-124), calc_rhs (:174-279), rkt (rktmod.f90:34-62), dealias (dealiasing.f90:70-112),
+ * update_uu_prim_from_uu (mhdrhs.f90:282-294), vardt (mhd.f90:328-429).  OpenMP threads stand in for the MPI
+ * ranks (the transposes of parallel.f90 are then plain strided access).  FFTW is replaced by a radix-2
+ * transform written here (power-of-two sizes only).
+ *
+ * Arrays are C order a[v][iz][iy][ix] = Fortran a(ix,iy,iz,v); spectra [v][kz][ky][kx], kx = 0..nx/2.
+ */
+#include <complex.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef double complex cplx;
+
+typedef struct {
+  int nx, ny, nz;
+  double Lx, Ly, Lz, gamma;
+  int if_resis, if_resis_exp; double eta;
+  int if_visc, if_visc_exp; double nu;
+  int if_conserve_background; double cfl;
+  int dealias_option; double afx, afy, afz;
+  int if_AEB, if_corotating; double radius0, Ur0, corotating_angle;
+  int if_hall; double di;
+} cpu_params;
+
+typedef struct {
+  cpu_params p;
+  int nxh; size_t nr, nc;                 /* points per real field, modes per spectral field */
+  double *uu, *prim, *flux, *J;           /* [8], [4], [19], [3] real fields */
+  cplx *uf, *ff, *fnl, *fnl_rk, *jf;      /* [8], [19], [8], [8], [3] spectra */
+  double *wnx, *wny, *wnz, *ksq;          /* wave numbers, k_square[kz][ky][kx] */
+  double *filtx, *filty, *filtz;
+  cplx *twx, *twy, *twz;                  /* exp(-2 pi i m / n) */
+  double Ur, radius, tau, cosa, sina, time, dt;
+  double cc1[3], dd1[3], tstep[3];
+} cpu_state;
+
+static const double kPi = 3.141592653589793;   /* mhdinit.f90:7 */
+
+/* ------------------------------------------------------------------ 1-D transforms (stand-in for FFTW) */
+static void fft_inplace(cplx* a, int n, const cplx* tw, int dir) {   /* dir = -1 forward, +1 backward, unnormalised */
+  for (int i = 1, j = 0; i < n; ++i) {             /* bit reversal */
+    int bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) { cplx t = a[i]; a[i] = a[j]; a[j] = t; }
+  }
+  for (int len = 2; len <= n; len <<= 1) {
+    const int half = len >> 1, step = n / len;
+    for (int i = 0; i < n; i += len)
+      for (int k = 0; k < half; ++k) {
+        cplx w = tw[k * step];
+        if (dir > 0) w = conj(w);
+        const cplx u = a[i + k], v = a[i + k + half] * w;
+        a[i + k] = u + v;
+        a[i + k + half] = u - v;
+      }
+  }
+}
+
+static cplx* twiddles(int n) {
+  cplx* t = (cplx*)malloc(sizeof(cplx) * n);
+  for (int m = 0; m < n; ++m) t[m] = cexp(-2.0 * kPi * I * m / n);
+  return t;
+}
+
+/* fftw.f90:42-71 + 136-180: r2c along x (/nx), c2c along y (/ny), c2c along z (/nz); one field */
+static void forward3d(const cpu_state* s, const double* a, cplx* w) {
+  const int nx = s->p.nx, ny = s->p.ny, nz = s->p.nz, nxh = s->nxh;
+#pragma omp parallel
+  {
+    cplx* line = (cplx*)malloc(sizeof(cplx) * (size_t)(nx > ny ? (nx > nz ? nx : nz) : (ny > nz ? ny : nz)));
+#pragma omp for collapse(2) schedule(static)
+    for (int iz = 0; iz < nz; ++iz)
+      for (int iy = 0; iy < ny; ++iy) {
+        const double* src = a + ((size_t)iz * ny + iy) * nx;
+        for (int i = 0; i < nx; ++i) line[i] = src[i];
+        fft_inplace(line, nx, s->twx, -1);
+        cplx* dst = w + ((size_t)iz * ny + iy) * nxh;
+        for (int k = 0; k < nxh; ++k) dst[k] = line[k] / nx;
+      }
+#pragma omp for collapse(2) schedule(static)
+    for (int iz = 0; iz < nz; ++iz)
+      for (int kx = 0; kx < nxh; ++kx) {
+        cplx* base = w + (size_t)iz * ny * nxh + kx;
+        for (int i = 0; i < ny; ++i) line[i] = base[(size_t)i * nxh];
+        fft_inplace(line, ny, s->twy, -1);
+        for (int i = 0; i < ny; ++i) base[(size_t)i * nxh] = line[i] / ny;
+      }
+#pragma omp for collapse(2) schedule(static)
+    for (int iy = 0; iy < ny; ++iy)
+      for (int kx = 0; kx < nxh; ++kx) {
+        cplx* base = w + (size_t)iy * nxh + kx;
+        for (int i = 0; i < nz; ++i) line[i] = base[(size_t)i * ny * nxh];
+        fft_inplace(line, nz, s->twz, -1);
+        for (int i = 0; i < nz; ++i) base[(size_t)i * ny * nxh] = line[i] / nz;
+      }
+    free(line);
+  }
+}
+
+/* fftw.f90:73-103 + 182-222: unnormalised backward c2c along z, then y, then c2r along x (w is overwritten) */
+static void inverse3d(const cpu_state* s, cplx* w, double* a) {
+  const int nx = s->p.nx, ny = s->p.ny, nz = s->p.nz, nxh = s->nxh;
+#pragma omp parallel
+  {
+    cplx* line = (cplx*)malloc(sizeof(cplx) * (size_t)(nx > ny ? (nx > nz ? nx : nz) : (ny > nz ? ny : nz)));
+#pragma omp for collapse(2) schedule(static)
+    for (int iy = 0; iy < ny; ++iy)
+      for (int kx = 0; kx < nxh; ++kx) {
+        cplx* base = w + (size_t)iy * nxh + kx;
+        for (int i = 0; i < nz; ++i) line[i] = base[(size_t)i * ny * nxh];
+        fft_inplace(line, nz, s->twz, +1);
+        for (int i = 0; i < nz; ++i) base[(size_t)i * ny * nxh] = line[i];
+      }
+#pragma omp for collapse(2) schedule(static)
+    for (int iz = 0; iz < nz; ++iz)
+      for (int kx = 0; kx < nxh; ++kx) {
+        cplx* base = w + (size_t)iz * ny * nxh + kx;
+        for (int i = 0; i < ny; ++i) line[i] = base[(size_t)i * nxh];
+        fft_inplace(line, ny, s->twy, +1);
+        for (int i = 0; i < ny; ++i) base[(size_t)i * nxh] = line[i];
+      }
+#pragma omp for collapse(2) schedule(static)
+    for (int iz = 0; iz < nz; ++iz)
+      for (int iy = 0; iy < ny; ++iy) {
+        const cplx* src = w + ((size_t)iz * ny + iy) * nxh;
+        /* c2r: Hermitian extension; like FFTW the imaginary parts of the DC and Nyquist bins are ignored */
+        line[0] = creal(src[0]);
+        for (int k = 1; k < nx / 2; ++k) { line[k] = src[k]; line[nx - k] = conj(src[k]); }
+        line[nx / 2] = creal(src[nx / 2]);
+        fft_inplace(line, nx, s->twx, +1);
+        double* dst = a + ((size_t)iz * ny + iy) * nx;
+        for (int i = 0; i < nx; ++i) dst[i] = creal(line[i]);
+      }
+    free(line);
+  }
+}
+
+/* ------------------------------------------------------------------ set-up */
+static double* wave_numbers(int n, double L) {   /* mhdinit.f90:79-110 (Nyquist kept positive) */
+  double* k = (double*)malloc(sizeof(double) * n);
+  for (int i = 1; i <= n; ++i) k[i - 1] = (i <= n / 2 + 1) ? 2 * kPi * (i - 1) / L : 2 * kPi * (i - 1 - n) / L;
+  return k;
+}
+
+static double filter_1d(double k, double L, int n, double af) {   /* dealiasing.f90:36-43 */
+  const double aj = (5.0 + 6.0 * af) / 8.0, bj = (1.0 + 2.0 * af) / 2.0, cj = -(1.0 - 2 * af) / 8.0, w = k * L / n;
+  return (aj + bj * cos(w) + cj * cos(2 * w)) / (1 + 2 * af * cos(w));
+}
+
+static void update_ksquare(cpu_state* s, int initial) {   /* mhdinit.f90:114-122, AEBmod.f90:87-124 */
+  const int ny = s->p.ny, nz = s->p.nz, nxh = s->nxh;
+  const double r0 = s->p.radius0, r = s->radius, c = s->cosa, sn = s->sina;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int iz = 0; iz < nz; ++iz)
+    for (int iy = 0; iy < ny; ++iy)
+      for (int ix = 0; ix < nxh; ++ix) {
+        const double kx = s->wnx[ix], ky = s->wny[iy], kz = s->wnz[iz];
+        double v;
+        if (initial) v = kx * kx + ky * ky + kz * kz;
+        else if (s->p.if_corotating)
+          v = kx * kx * (c * c + (sn * r0 / r) * (sn * r0 / r)) + ky * ky * (sn * sn + (c * r0 / r) * (c * r0 / r)) +
+              kx * ky * 2 * c * sn * (1 - (r0 / r) * (r0 / r)) + (kz * r0 / r) * (kz * r0 / r);
+        else v = kx * kx + (ky * r0 / r) * (ky * r0 / r) + (kz * r0 / r) * (kz * r0 / r);
+        s->ksq[((size_t)iz * ny + iy) * nxh + ix] = v;
+      }
+}
+
+void* cpu_create(const cpu_params* p) {
+  cpu_state* s = (cpu_state*)calloc(1, sizeof(cpu_state));
+  s->p = *p;
+  s->nxh = p->nx / 2 + 1;
+  s->nr = (size_t)p->nx * p->ny * p->nz;
+  s->nc = (size_t)s->nxh * p->ny * p->nz;
+  s->uu = (double*)calloc(8 * s->nr, sizeof(double));
+  s->prim = (double*)calloc(4 * s->nr, sizeof(double));
+  s->flux = (double*)calloc(19 * s->nr, sizeof(double));
+  s->J = (double*)calloc(3 * s->nr, sizeof(double));
+  s->uf = (cplx*)calloc(8 * s->nc, sizeof(cplx));
+  s->ff = (cplx*)calloc(19 * s->nc, sizeof(cplx));
+  s->fnl = (cplx*)calloc(8 * s->nc, sizeof(cplx));
+  s->fnl_rk = (cplx*)calloc(8 * s->nc, sizeof(cplx));
+  s->jf = (cplx*)calloc(3 * s->nc, sizeof(cplx));
+  s->ksq = (double*)calloc(s->nc, sizeof(double));
+  if (!s->uu || !s->prim || !s->flux || !s->J || !s->uf || !s->ff || !s->fnl || !s->fnl_rk || !s->jf || !s->ksq) return NULL;
+  s->wnx = wave_numbers(p->nx, p->Lx); s->wny = wave_numbers(p->ny, p->Ly); s->wnz = wave_numbers(p->nz, p->Lz);
+  s->twx = twiddles(p->nx); s->twy = twiddles(p->ny); s->twz = twiddles(p->nz);
+  s->filtx = (double*)malloc(sizeof(double) * s->nxh); s->filty = (double*)malloc(sizeof(double) * p->ny); s->filtz = (double*)malloc(sizeof(double) * p->nz);
+  for (int i = 0; i < s->nxh; ++i) s->filtx[i] = filter_1d(s->wnx[i], p->Lx, p->nx, p->afx);
+  for (int i = 0; i < p->ny; ++i) s->filty[i] = filter_1d(s->wny[i], p->Ly, p->ny, p->afy);
+  for (int i = 0; i < p->nz; ++i) s->filtz[i] = filter_1d(s->wnz[i], p->Lz, p->nz, p->afz);
+  s->Ur = p->if_AEB ? p->Ur0 : 0.0;           /* mhd.f90:88-90 */
+  s->radius = p->radius0;
+  s->tau = s->radius / s->Ur;
+  const double ang = p->if_corotating ? p->corotating_angle : 0.0;
+  s->cosa = cos(ang); s->sina = sin(ang);
+  update_ksquare(s, 1);
+  return s;
+}
+
+void cpu_destroy(void* h) {
+  cpu_state* s = (cpu_state*)h;
+  if (!s) return;
+  free(s->uu); free(s->prim); free(s->flux); free(s->J); free(s->uf); free(s->ff); free(s->fnl); free(s->fnl_rk); free(s->jf);
+  free(s->ksq); free(s->wnx); free(s->wny); free(s->wnz); free(s->twx); free(s->twy); free(s->twz);
+  free(s->filtx); free(s->filty); free(s->filtz); free(s);
+}
+
+int cpu_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+/* ------------------------------------------------------------------ pointwise pieces */
+static void update_prim(cpu_state* s) {   /* mhdrhs.f90:282-294 */
+  const size_t n = s->nr; const double gm1 = s->p.gamma - 1.0;
+  double* u = s->uu; double* q = s->prim;
+#pragma omp parallel for schedule(static)
+  for (size_t i = 0; i < n; ++i) {
+    q[i] = u[n + i] / u[i]; q[n + i] = u[2 * n + i] / u[i]; q[2 * n + i] = u[3 * n + i] / u[i];
+    q[3 * n + i] = (u[7 * n + i] - 0.5 * (u[n + i] * q[i] + u[2 * n + i] * q[n + i] + u[3 * n + i] * q[2 * n + i] +
+                                         u[4 * n + i] * u[4 * n + i] + u[5 * n + i] * u[5 * n + i] + u[6 * n + i] * u[6 * n + i])) * gm1;
+  }
+}
+
+/* derivative vectors (imaginary parts), mhdrhs.f90:191-204 */
+static inline void kvec(const cpu_state* s, int ix, int iy, int iz, double* kx, double* ky, double* kz) {
+  const double r0 = s->p.radius0, r = s->radius;
+  *kz = s->wnz[iz] * r0 / r;
+  *ky = s->wny[iy] * r0 / r;
+  *kx = s->wnx[ix];
+  if (s->p.if_AEB && s->p.if_corotating) {
+    *kx = s->wnx[ix] * s->cosa + s->wny[iy] * s->sina;
+    *ky = (-s->wnx[ix] * s->sina + s->wny[iy] * s->cosa) * r0 / r;
+  }
+}
+
+static void calc_current(cpu_state* s) {   /* mhdrhs.f90:296-362 */
+  const int ny = s->p.ny, nz = s->p.nz, nxh = s->nxh; const size_t nc = s->nc;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int iz = 0; iz < nz; ++iz)
+    for (int iy = 0; iy < ny; ++iy)
+      for (int ix = 0; ix < nxh; ++ix) {
+        double kx, ky, kz; kvec(s, ix, iy, iz, &kx, &ky, &kz);
+        const size_t m = ((size_t)iz * ny + iy) * nxh + ix;
+        const cplx bx = s->uf[4 * nc + m], by = s->uf[5 * nc + m], bz = s->uf[6 * nc + m];
+        s->jf[m] = I * ky * bz - I * kz * by;
+        s->jf[nc + m] = I * kz * bx - I * kx * bz;
+        s->jf[2 * nc + m] = I * kx * by - I * ky * bx;
+      }
+  for (int v = 0; v < 3; ++v) inverse3d(s, s->jf + v * nc, s->J + v * s->nr);
+}
+
+static void calc_flux(cpu_state* s) {   /* mhdrhs.f90:21-124 */
+  const size_t n = s->nr; const cpu_params* p = &s->p;
+  if (p->if_hall) calc_current(s);
+  const double* u = s->uu; const double* q = s->prim; double* f = s->flux;
+  const double gam = p->gamma, tau = s->tau;
+#pragma omp parallel for schedule(static)
+  for (size_t i = 0; i < n; ++i) {
+    const double rho = u[i], mx = u[n + i], my = u[2 * n + i], mz = u[3 * n + i];
+    const double Bx = u[4 * n + i], By = u[5 * n + i], Bz = u[6 * n + i], en = u[7 * n + i];
+    const double ux = q[i], uy = q[n + i], uz = q[2 * n + i], P = q[3 * n + i];
+    const double ptot = P + 0.5 * (Bx * Bx + By * By + Bz * Bz);
+    const double udotb = ux * Bx + uy * By + uz * Bz;
+    f[i] = mx; f[n + i] = my; f[2 * n + i] = mz;
+    f[3 * n + i] = mx * ux - Bx * Bx + ptot; f[4 * n + i] = my * ux - By * Bx; f[5 * n + i] = mz * ux - Bz * Bx;
+    f[6 * n + i] = mx * uy - Bx * By; f[7 * n + i] = my * uy - By * By + ptot; f[8 * n + i] = mz * uy - Bz * By;
+    f[9 * n + i] = mx * uz - Bx * Bz; f[10 * n + i] = my * uz - By * Bz; f[11 * n + i] = mz * uz - Bz * Bz + ptot;
+    double Ex = uz * By - uy * Bz, Ey = ux * Bz - uz * Bx, Ez = uy * Bx - ux * By;
+    if (p->if_hall) {
+      const double Jx = s->J[i], Jy = s->J[n + i], Jz = s->J[2 * n + i], dr = p->di / rho;
+      Ex = Ex + dr * (Jy * Bz - Jz * By); Ey = Ey + dr * (Jz * Bx - Jx * Bz); Ez = Ez + dr * (Jx * By - Jy * Bx);
+    }
+    f[12 * n + i] = Ex; f[13 * n + i] = Ey; f[14 * n + i] = Ez;
+    f[15 * n + i] = (en + ptot) * ux - udotb * Bx; f[16 * n + i] = (en + ptot) * uy - udotb * By; f[17 * n + i] = (en + ptot) * uz - udotb * Bz;
+    if (p->if_AEB)
+      f[18 * n + i] = -2 * gam / (gam - 1) * P / tau - (2.0 * Bx * Bx + By * By + Bz * Bz) / tau - (mx * ux + 2 * my * uy + 2 * mz * uz) / tau;
+  }
+}
+
+static void calc_rhs(cpu_state* s) {   /* mhdrhs.f90:174-279 */
+  const int ny = s->p.ny, nz = s->p.nz, nxh = s->nxh; const size_t nc = s->nc; const cpu_params* p = &s->p;
+  static const double aebc[7] = {2.0, 2.0, 3.0, 3.0, 2.0, 1.0, 1.0};
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int iz = 0; iz < nz; ++iz)
+    for (int iy = 0; iy < ny; ++iy)
+      for (int ix = 0; ix < nxh; ++ix) {
+        double kxr, kyr, kzr; kvec(s, ix, iy, iz, &kxr, &kyr, &kzr);
+        const cplx kx = I * kxr, ky = I * kyr, kz = I * kzr;
+        const size_t m = ((size_t)iz * ny + iy) * nxh + ix;
+        const cplx* ff = s->ff + m; cplx* fnl = s->fnl + m; const cplx* uf = s->uf + m;
+#define FF(j) ff[(size_t)(j) * nc]
+        fnl[0] = -(kx * FF(0) + ky * FF(1) + kz * FF(2));
+        fnl[nc] = -(kx * FF(3) + ky * FF(4) + kz * FF(5));
+        fnl[2 * nc] = -(kx * FF(6) + ky * FF(7) + kz * FF(8));
+        fnl[3 * nc] = -(kx * FF(9) + ky * FF(10) + kz * FF(11));
+        fnl[4 * nc] = kz * FF(13) - ky * FF(14);
+        fnl[5 * nc] = kx * FF(14) - kz * FF(12);
+        fnl[6 * nc] = ky * FF(12) - kx * FF(13);
+        fnl[7 * nc] = -(kx * FF(15) + ky * FF(16) + kz * FF(17));
+        if (p->if_AEB) {
+          for (int v = 0; v < 7; ++v) fnl[(size_t)v * nc] -= aebc[v] * uf[(size_t)v * nc] / s->tau;
+          fnl[7 * nc] += FF(18);
+        }
+#undef FF
+        const double k2 = s->ksq[m];
+        if (p->if_visc && p->if_visc_exp) for (int v = 1; v <= 3; ++v) fnl[(size_t)v * nc] -= p->nu * uf[(size_t)v * nc] * k2;
+        if (p->if_resis && p->if_resis_exp && !(p->if_conserve_background && ix == 0 && iz == 0))
+          for (int v = 4; v <= 6; ++v) fnl[(size_t)v * nc] -= p->eta * uf[(size_t)v * nc] * k2;
+      }
+}
+
+static void rkt_and_dealias(cpu_state* s, int irk) {   /* rktmod.f90:34-62, dealiasing.f90:70-112 */
+  const int ny = s->p.ny, nz = s->p.nz, nxh = s->nxh; const size_t nc = s->nc; const cpu_params* p = &s->p;
+  const double cc = s->cc1[irk], dd = s->dd1[irk], ts = s->tstep[irk];
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int iz = 0; iz < nz; ++iz)
+    for (int iy = 0; iy < ny; ++iy)
+      for (int ix = 0; ix < nxh; ++ix) {
+        const size_t m = ((size_t)iz * ny + iy) * nxh + ix;
+        const double k2 = s->ksq[m];
+        int masked = 0;
+        if (p->dealias_option == 1) {
+          const double tx = s->wnx[ix] * p->Lx / (2 * kPi * p->nx), ty = s->wny[iy] * p->Ly / (2 * kPi * p->ny), tz = s->wnz[iz] * p->Lz / (2 * kPi * p->nz);
+          masked = sqrt(tx * tx + ty * ty + tz * tz) > (1.0 / 3.0);
+        }
+        for (int v = 0; v < 8; ++v) {
+          const size_t j = (size_t)v * nc + m;
+          cplx un = cc * s->fnl[j] + dd * s->fnl_rk[j] + s->uf[j];
+          s->fnl_rk[j] = s->fnl[j];
+          if (v >= 1 && v <= 3 && p->if_visc && !p->if_visc_exp) un = un / (ts * k2 * p->nu + 1.0);
+          if (v >= 4 && v <= 6 && p->if_resis && !p->if_resis_exp) un = un / (ts * k2 * p->eta + 1.0);
+          if (masked) un = 0.0;
+          if (p->dealias_option == 2) un = un * s->filtx[ix] * s->filty[iy] * s->filtz[iz];
+          s->uf[j] = un;
+        }
+      }
+}
+
+/* ------------------------------------------------------------------ driver-level calls */
+void cpu_set_primitive(void* h, const double* prim8) {   /* mhdinit.f90:1038-1056 + fftw.f90:42-71 */
+  cpu_state* s = (cpu_state*)h; const size_t n = s->nr; const double gam = s->p.gamma;
+  memcpy(s->uu, prim8, 8 * n * sizeof(double));
+  double* u = s->uu; double* q = s->prim;
+#pragma omp parallel for schedule(static)
+  for (size_t i = 0; i < n; ++i) {
+    q[i] = u[n + i]; q[n + i] = u[2 * n + i]; q[2 * n + i] = u[3 * n + i]; q[3 * n + i] = u[7 * n + i];
+    u[n + i] = u[i] * q[i]; u[2 * n + i] = u[i] * q[n + i]; u[3 * n + i] = u[i] * q[2 * n + i];
+    u[7 * n + i] = q[3 * n + i] / (gam - 1) + 0.5 * (u[i] * (q[i] * q[i] + q[n + i] * q[n + i] + q[2 * n + i] * q[2 * n + i]) +
+                                                     u[4 * n + i] * u[4 * n + i] + u[5 * n + i] * u[5 * n + i] + u[6 * n + i] * u[6 * n + i]);
+  }
+  for (int v = 0; v < 8; ++v) forward3d(s, s->uu + v * n, s->uf + v * s->nc);
+  s->time = 0.0; s->dt = 0.0;
+}
+
+static void rkt_init(cpu_state* s, double dt) {   /* rktmod.f90:15-32 */
+  memset(s->fnl_rk, 0, 8 * s->nc * sizeof(cplx));
+  s->cc1[0] = 8.0 / 15.0 * dt; s->cc1[1] = 5.0 / 12.0 * dt; s->cc1[2] = 0.75 * dt;
+  s->dd1[0] = 0.0; s->dd1[1] = -17.0 / 60.0 * dt; s->dd1[2] = -5.0 / 12.0 * dt;
+  s->tstep[0] = 8.0 / 15.0 * dt; s->tstep[1] = 2.0 / 15.0 * dt; s->tstep[2] = 1.0 / 3.0 * dt;
+}
+
+double cpu_vardt(void* h) {   /* mhd.f90:328-429 */
+  cpu_state* s = (cpu_state*)h; const size_t n = s->nr; const cpu_params* p = &s->p;
+  const double dx = p->Lx / p->nx, dy = p->Ly / p->ny, dz = p->Lz / p->nz, s2 = sqrt(2.0), rr = s->radius / p->radius0;
+  const double dmin = fmin(fmin(dx, dy), dz);
+  const double* u = s->uu; const double* q = s->prim;
+  double dtmin = INFINITY;
+#pragma omp parallel for schedule(static) reduction(min : dtmin)
+  for (size_t i = 0; i < n; ++i) {
+    const double rho = u[i], cs2 = p->gamma * q[3 * n + i] / rho, sr = sqrt(rho);
+    const double ca[3] = {u[4 * n + i] / sr, u[5 * n + i] / sr, u[6 * n + i] / sr};
+    const double cms2 = cs2 + (ca[0] * ca[0] + ca[1] * ca[1] + ca[2] * ca[2]);
+    double chall = 0.0;
+    if (p->if_hall) chall = p->di / rho * fmax(fmax(u[4 * n + i], u[5 * n + i]), u[6 * n + i]) / dmin;   /* signed max, mhd.f90:396-398 */
+    double cm[3];
+    for (int d = 0; d < 3; ++d) {
+      const double cns = sqrt(fmax(cms2 * cms2 - 4 * cs2 * ca[d] * ca[d], 0.0));
+      const double cf = sqrt(cms2 + cns) / s2, csl = sqrt(fmax(cms2 - cns, 0.0)) / s2, v = q[(size_t)d * n + i];
+      double c = fabs(v + cf);
+      c = fmax(c, fabs(v + csl)); c = fmax(c, fabs(v + ca[d])); c = fmax(c, fabs(v - cf));
+      c = fmax(c, fabs(v - csl)); c = fmax(c, fabs(v - ca[d])); c = fmax(c, fabs(v));
+      if (p->if_hall) c = fmax(c, chall);
+      cm[d] = c;
+    }
+    const double t = fmin(fmin(dx / cm[0], dy / cm[1] * rr), dz / cm[2] * rr);
+    dtmin = fmin(dtmin, t);
+  }
+  dtmin = dtmin * p->cfl;
+  if (s->dt < 0.98 * dtmin || s->dt > 1.02 * dtmin) s->dt = dtmin;
+  rkt_init(s, s->dt);
+  return s->dt;
+}
+
+static void evolve_radius(cpu_state* s, double t) {   /* AEBmod.f90:56-73 */
+  s->radius = s->p.radius0 + s->Ur * t;
+  s->tau = s->radius / s->Ur;
+  update_ksquare(s, 0);
+}
+
+void cpu_evolve(void* h) {   /* mhd.f90:298-326 */
+  cpu_state* s = (cpu_state*)h; const int nf = s->p.if_AEB ? 19 : 18;
+  for (int irk = 0; irk < 3; ++irk) {
+    calc_flux(s);
+    for (int j = 0; j < nf; ++j) forward3d(s, s->flux + (size_t)j * s->nr, s->ff + (size_t)j * s->nc);   /* mhdrhs.f90:128-172 */
+    calc_rhs(s);
+    rkt_and_dealias(s, irk);
+    for (int v = 0; v < 8; ++v) {   /* fftw.f90:73-103 (the transform overwrites its input: work on a copy, fnl is free now) */
+      memcpy(s->fnl + (size_t)v * s->nc, s->uf + (size_t)v * s->nc, s->nc * sizeof(cplx));
+      inverse3d(s, s->fnl + (size_t)v * s->nc, s->uu + (size_t)v * s->nr);
+    }
+    update_prim(s);
+  }
+}
+
+double cpu_step(void* h) {   /* mhd.f90:244-248,285 */
+  cpu_state* s = (cpu_state*)h;
+  cpu_evolve(s);
+  s->time = s->time + s->dt;
+  evolve_radius(s, s->time);
+  return cpu_vardt(s);
+}
+
+void cpu_get_state(void* h, double* uu8, double* prim4, double* time, double* dt) {
+  cpu_state* s = (cpu_state*)h;
+  if (uu8) memcpy(uu8, s->uu, 8 * s->nr * sizeof(double));
+  if (prim4) memcpy(prim4, s->prim, 4 * s->nr * sizeof(double));
+  if (time) *time = s->time;
+  if (dt) *dt = s->dt;
+}
