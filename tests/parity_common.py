@@ -214,3 +214,38 @@ def check_pruning_is_exact(shape, nsteps, lib_path=None, incompressible=False, *
         assert out[0][2] == o[2] and out[0][3] == o[3]
     assert out[1][4][1] < out[0][4][1]          # the default does skip modes
     return [o[4] for o in out]
+
+
+def check_hall_wave_known_answer(lib_path=None, incompressible=False, nsteps=(30, 60)):
+    """Analytic known answer straight on the library (no oracle): a circularly polarised wave along B0 is an exact
+    solution of Hall-MHD with  w^2 + (di B0 k^2 / rho) w - (B0 k)^2 / rho = 0.  Fixed time step (laps_rkt_init),
+    two resolutions in time: the error must be the RK3 one (ratio ~ 8) and small."""
+    import math
+    L, di, kint, b0, B0, rho, T = 2 * np.pi, 0.5, 2, 0.05, 1.0, 1.0, 0.3
+    k = float(kint)
+    sig = di * B0 * k * k / rho
+    w = 0.5 * (-sig + math.sqrt(sig * sig + 4 * k * k * B0 * B0 / rho))
+    nx = 32
+    x = (np.arange(nx) * (L / nx))[None, None, :]
+    prim = np.zeros((8, 16, 16, nx))
+    prim[0], prim[4], prim[7] = rho, B0, 1.0
+    prim[5] += b0 * np.cos(k * x)
+    prim[6] += b0 * np.sin(k * x)
+    prim[2] += -(B0 * k / (rho * w)) * b0 * np.cos(k * x)
+    prim[3] += -(B0 * k / (rho * w)) * b0 * np.sin(k * x)
+    errs = []
+    for n in nsteps:
+        extra = dict(incompressible=1, rho0=1.0) if incompressible else {}
+        with Solver(lib_path, nx=nx, ny=16, nz=16, Lx=L, Ly=L, Lz=L, dealias_option=1, if_hall=1, ion_inertial_length=di, **extra) as g:
+            g.set_primitive(prim)
+            dt = T / n
+            for _ in range(n):
+                g.rkt_init(dt)
+                g.evolve()
+            uu, _ = g.get_state()
+            xs = x[0, 0]
+            errs.append(max(np.abs(uu[5][3, 5, :] - b0 * np.cos(k * xs - w * T)).max(),
+                            np.abs(uu[6][3, 5, :] - b0 * np.sin(k * xs - w * T)).max()) / b0)
+            assert np.abs(uu[0] - rho).max() < 1e-12 and g.calc_max_divB() < 1e-13
+    assert errs[0] < 2e-5 and errs[1] < 3e-6 and 6.0 < errs[0] / errs[1] < 10.0, errs
+    return errs

@@ -161,6 +161,11 @@ def test_set_primitive_modes_equals_the_uploaded_field(emu):
             d.set_primitive_modes(np.array([[17, 0, 0]]), np.zeros((7, 1), dtype=complex), back)
 
 
+@pytest.mark.parametrize("inc", [False, True])
+def test_hall_wave_known_answer_on_the_kernels(emu, inc):
+    pc.check_hall_wave_known_answer(emu, incompressible=inc, nsteps=(15, 30))
+
+
 def test_synthetic_slab_matches_the_mode_sum():
     p = lo.Params(nx=16, ny=32, nz=24, Lx=24.0, Ly=20.0, Lz=12.0)
     prim = lo.ic_uniform_background(p, bx0=1.0, by0=0.3, press0=1.0)

@@ -181,6 +181,13 @@ def test_set_primitive_modes_128():
         assert pc.rel_l2(b.get_state()[0], a.get_state()[0]) < 1e-12 and abs(a.dt - b.dt) < 1e-13 * a.dt
 
 
+@pytest.mark.parametrize("inc", [False, True])
+def test_hall_wave_known_answer(inc):
+    """Independent of the oracle: the CUDA path against the exact Hall-MHD wave solution (third-order convergence
+    to the whistler branch of the dispersion relation), compressible and incompressible trees."""
+    pc.check_hall_wave_known_answer(incompressible=inc)
+
+
 def test_dealias_mask_bit_exact():
     p, prim = pc.make_case(32, 64, 32, hall=False, aeb=False, dealias=1)
     o, g = pc.run_both(p, prim, 1)
