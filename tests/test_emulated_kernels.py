@@ -166,6 +166,16 @@ def test_hall_wave_known_answer_on_the_kernels(emu, inc):
     pc.check_hall_wave_known_answer(emu, incompressible=inc, nsteps=(15, 30))
 
 
+@pytest.mark.parametrize("shape", [(16, 16, 1024), (1024, 16, 16)])
+def test_long_lines_through_every_pass(emu, shape):
+    """1024-point lines (four radix stages, the line length of BASELINE config 5) through the RHS z pass and the
+    x passes, not only through the unit transforms."""
+    p, prim = pc.make_case(*shape, hall=True, aeb=True, dealias=1)
+    o, g = pc.run_both(p, prim, 1, lib_path=emu)
+    pc.check_state(o, g, 1e-11)
+    g.close()
+
+
 def test_synthetic_slab_matches_the_mode_sum():
     p = lo.Params(nx=16, ny=32, nz=24, Lx=24.0, Ly=20.0, Lz=12.0)
     prim = lo.ic_uniform_background(p, bx0=1.0, by0=0.3, press0=1.0)
