@@ -367,7 +367,8 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(n), "decomposition": f"slab over {world} GPU(s), z in real space / ky in Fourier space",
+        "config": {"workload": workload_name(n), "decomposition": f"slab over {world} GPU(s), z in real space / ky in Fourier space"
+                                    + (f" (ky rows dealt round-robin, y_stride {g.ext.y_stride})" if g.ext.y_stride > 1 else " (decompose_1d slabs)"),
                    "l2": "inputs larger than L2 (every pass streams >= 8 GB per GPU at 512^3/8 and above); no flush",
                    "ic": "ifield=3 uniform B0=(1,0,0) + ipert=7-style random-phase modes |k|<=8, k^-3/2"},
         "clocks": clocks,

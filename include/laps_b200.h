@@ -67,9 +67,10 @@ typedef struct laps_extents {
   int32_t z_offset, z_size;      /* real space: z in Zj(rank)   (zj_offset/zj_size) */
   int32_t y_offset, y_size;      /* Fourier space: ky in Yj(rank) (yj_offset/yj_size) */
   int32_t y_stride;              /* this rank's Fourier rows are ky = y_offset + j * y_stride, j < y_size.  1: the reference's
-                                  * contiguous slabs (default).  nranks: rows dealt round-robin (LAPS_TUNE_CYCLIC=1, experimental:
+                                  * contiguous slabs (1-3 ranks, 2D, unmasked dealiasing, or LAPS_TUNE_CYCLIC=0).  nranks: rows
+                                  * dealt round-robin (default from 4 ranks on with dealias options 1/3, or LAPS_TUNE_CYCLIC=1):
                                   * the rows the dealiasing mask keeps are then spread evenly over the ranks; real space, every
-                                  * result and every driver-facing array are unaffected) */
+                                  * result and every driver-facing array are unaffected */
 } laps_extents;
 
 /* parallel_start + fftw_initialize + grid_initialize + arrays_initialize + AEB_initialize +

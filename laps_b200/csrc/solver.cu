@@ -79,7 +79,7 @@ struct laps_solver {
   int zoffs[LAPS_MAX_RANKS], zlens[LAPS_MAX_RANKS], yoffs[LAPS_MAX_RANKS], ylens[LAPS_MAX_RANKS];
   int nzl, nyl, zo, yo;
   int ystride = 1;       // global ky of local Fourier row kyl: yo + kyl * ystride (1: reference slabs; P: cyclic rows)
-  bool cyclic = false;   // LAPS_TUNE_CYCLIC=1: ky rows dealt round-robin to the ranks (balances the dealiased z pass)
+  bool cyclic = false;   // ky rows dealt round-robin to the ranks (balances the dealiased z pass; default from 4 ranks on)
   size_t npts;   // nx*ny*nzl      (real points per field)
   size_t ncol;   // nxh*nyl        (spectral columns)
   size_t csz;    // ncol*nz        (spectral elements per field)
@@ -903,7 +903,15 @@ int laps_create(const laps_params* params, laps_handle* out) {
   s->nx = p.nx; s->ny = p.ny; s->nz = p.nz; s->nxh = p.nx / 2 + 1; s->P = p.nranks; s->rank = p.rank;
   decompose_1d(s->nz, s->P, s->zoffs, s->zlens);   // zj_offset/zj_size (parallel.f90:102)
   decompose_1d(s->ny, s->P, s->yoffs, s->ylens);   // yj_offset/yj_size (parallel.f90:101)
-  if (const char* e = std::getenv("LAPS_TUNE_CYCLIC")) s->cyclic = std::atoi(e) != 0 && s->P > 1 && !two_d;
+  {  // Fourier-row ownership.  Default: the reference's contiguous ky slabs up to 3 ranks; from 4 ranks on, when a
+     // dealiasing mask (options 1, 3) removes the middle of the ky axis and those rows are skipped, the rows are dealt
+     // round-robin so that every rank owns the same share of the surviving ones (with slabs the ranks in the middle of
+     // the spectrum idle: at 8 ranks two of them own no surviving row).  LAPS_TUNE_CYCLIC=0/1 forces either.
+    int prune = 1;
+    if (const char* e = std::getenv("LAPS_TUNE_PRUNE")) prune = std::atoi(e);
+    s->cyclic = s->P >= 4 && !two_d && prune != 0 && (p.dealias_option == 1 || p.dealias_option == 3);
+    if (const char* e = std::getenv("LAPS_TUNE_CYCLIC")) s->cyclic = std::atoi(e) != 0 && s->P > 1 && !two_d;
+  }
   if (s->cyclic) {   // row ky belongs to rank ky % P; rank q holds rows q, q + P, q + 2P, ...
     for (int q = 0; q < s->P; ++q) { s->yoffs[q] = q; s->ylens[q] = (s->ny - q + s->P - 1) / s->P; }
     s->ystride = s->P;

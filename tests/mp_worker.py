@@ -50,6 +50,8 @@ def main():
     zo, zn, yo, yn = g.ext.z_offset, g.ext.z_size, g.ext.y_offset, g.ext.y_size
     rows = g.ky_rows                      # this rank's Fourier rows (a contiguous slab unless LAPS_TUNE_CYCLIC=1)
     cyclic = g.ext.y_stride > 1
+    if "expect_stride" in cfg:
+        assert g.ext.y_stride == cfg["expect_stride"], (g.ext.y_stride, cfg["expect_stride"])
 
     # decomposition tables: decompose_1d gives n/P each, the remainder to the last rank (parallel.f90:326-349)
     q = nz // world

@@ -20,6 +20,15 @@ def test_multi_gpu_one_step_parity(world):
     run_ranks(world, dict(backend="nccl", shape=(64, 64, 64), case=dict(hall=True, aeb=True, dealias=1), steps=2))
 
 
+@pytest.mark.parametrize("world", [4, 8])
+def test_multi_gpu_reference_slabs(world):
+    """The reference's contiguous ky slabs at 4 and 8 GPUs (the default there deals the rows round-robin)."""
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    run_ranks(world, dict(backend="nccl", shape=(64, 64, 64), case=dict(hall=True, aeb=True, dealias=1), steps=2,
+                          env=dict(LAPS_TUNE_CYCLIC="0")))
+
+
 def test_three_gpus_remainder_on_last_rank():
     if _ngpu() < 3:
         pytest.skip("needs 3 GPUs")

@@ -68,12 +68,24 @@ def test_two_ranks_incompressible_tree(emu):
 def test_eight_ranks_two_of_them_without_surviving_columns(emu):
     # ny = 32 over 8 ranks with the 1/3 mask (|ky| <= 10 survives): ranks 3 and 4 own rows 12..19 only, i.e. no
     # column the z pass has to visit — the situation of the 512^3 benchmark on 8 GPUs
-    run_ranks(8, dict(lib=emu, shape=(16, 32, 16), case=dict(hall=True, aeb=True, dealias=1), steps=2))
+    # (LAPS_TUNE_CYCLIC=0 pins the reference's contiguous slabs; from 4 ranks on the default deals the rows round-robin)
+    run_ranks(8, dict(lib=emu, shape=(16, 32, 16), case=dict(hall=True, aeb=True, dealias=1), steps=2, env=dict(LAPS_TUNE_CYCLIC="0")))
+
+
+def test_four_ranks_default_ownership_is_cyclic(emu):
+    # no switch set: with a masked dealiasing option and >= 4 ranks the library deals the ky rows round-robin
+    # (mp_worker checks ky_rows == rank, rank + P, ... and the matching transpose index map when y_stride > 1)
+    run_ranks(4, dict(lib=emu, shape=(16, 16, 16), case=dict(hall=True, aeb=True, dealias=1), steps=1, expect_stride=4))
+
+
+def test_four_ranks_filter_dealiasing_keeps_reference_slabs(emu):
+    # dealias option 2 prunes nothing, so the reference's decompose_1d slabs stay (y_stride = 1)
+    run_ranks(4, dict(lib=emu, shape=(16, 16, 16), case=dict(hall=True, aeb=True, dealias=2), steps=1, expect_stride=1))
 
 
 @pytest.mark.parametrize("world,shape", [(2, (16, 16, 16)), (3, (16, 16, 16)), (8, (16, 32, 16))])
 def test_cyclic_ky_ownership(emu, world, shape):
-    """LAPS_TUNE_CYCLIC=1 (experimental): Fourier rows dealt round-robin to the ranks.  Same results as the slab
+    """LAPS_TUNE_CYCLIC=1: Fourier rows dealt round-robin to the ranks (the default from 4 ranks on).  Same results as the slab
     ownership — the oracle parity, the distributed FFT and the allreduces of mp_worker hold unchanged."""
     run_ranks(world, dict(lib=emu, shape=shape, case=dict(hall=True, aeb=True, dealias=1), steps=2, env=dict(LAPS_TUNE_CYCLIC="1")))
 
