@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define LAPS_ABI_VERSION 4
+#define LAPS_ABI_VERSION 5
 #define LAPS_MAX_RANKS 8
 
 typedef struct laps_solver* laps_handle;
@@ -48,7 +48,7 @@ typedef struct laps_params {
   /* 2D tree (src_compressible/2D/): ndim = 2 with nz = 1 runs the (nx, ny) algorithm of 2D/mhdrhs.f90,
    * 2D/mhd.f90:296-406 (vardt), 2D/dealiasing.f90 (dealias_option 3 = square truncation) on one GPU;
    * ndim = 0 or 3 is the 3D tree.  if_z_radial: 2D/mhd.f90:44 (&AEB); if_limit_dt_increase:
-   * 2D/mhd.f90:23,396-404 (&numerical).  Not supported in 2D: if_corotating, if_external_force. */
+   * 2D/mhd.f90:23,396-404 (&numerical).  Not supported in 2D: if_corotating. */
   int32_t ndim;
   int32_t if_z_radial;
   int32_t if_limit_dt_increase;
@@ -59,6 +59,8 @@ typedef struct laps_params {
    * rho0: the namelist background density (mhdinit.f90:15) that calc_gradient_velocity_real divides by. */
   int32_t incompressible;
   double rho0;
+  /* 2D compressible tree only (2D/mhd.f90:43, &pert): a driver-supplied forcing of B_z, see laps_set_external_force. */
+  int32_t if_external_force;
 } laps_params;
 
 /* Local extents as decompose_1d (parallel.f90:326-349) assigns them in slab mode. */
@@ -134,6 +136,15 @@ int laps_max_divv(laps_handle h, double* out);
  * (src_incompressible/mhdrhs.f90:532-648, mhd.f90:672-732), the pair the incompressible driver prints at
  * dtrms cadence: out[0] = max |div B|, out[1] = max |div (rho u)| / rho0, both in REAL space. */
 int laps_max_div_real(laps_handle h, double out[2]);
+/* checkNan (src_compressible/2D/mhd.f90:242-245,563-591; src_incompressible/2D/mhd.f90:745-773; any tree here):
+ * *is_nan = 1 if any uu(ix,iy,iz,1:8) on any rank is a NaN (MPI_Allreduce MAX), else 0.  The driver keeps the
+ * dstep_checknan cadence and the stop. */
+int laps_check_nan(laps_handle h, int32_t* is_nan);
+/* 2D compressible tree with if_external_force: the field external_force(1:nx, 1:ny, 1, 1) of the user routine
+ * calc_external_force_real (2D/mhdrhs.f90:480-531), which stays in the driver.  Every stage transforms it with the
+ * fluxes (2D/mhdrhs.f90:216-251) and adds it to fnl(7) (:370-372) until the next call replaces it; it depends on
+ * `time` only, so once per step (before laps_evolve / laps_step) is enough.  Zero until the first call.  Blocking. */
+int laps_set_external_force(laps_handle h, const double* force_local);
 /* Current rho0 (update_rho_p compounds it after every evolve in the expanding box, AEBmod.f90:123-134). */
 int laps_get_rho0(laps_handle h, double* rho0);
 /* calc_rms (mhdrms.f90:53-126): out = uu_ave(8), uu_rms(8), rho_u2(3); the driver keeps the

@@ -1,11 +1,11 @@
-! laps_gpu.f90 -- ISO_C_BINDING interface of the laps_b200 C ABI (include/laps_b200.h, ABI version 4).
+! laps_gpu.f90 -- ISO_C_BINDING interface of the laps_b200 C ABI (include/laps_b200.h, ABI version 5).
 ! Drop this file into src_compressible/ (or any of the other three source trees) and patch mhd.f90 as
 ! INTEGRATION.md section 2 describes.  Not compiled in this repository's image (no Fortran compiler);
 ! the same ABI with the same array layouts is exercised through laps_b200/capi.py.
 module laps_gpu
   use iso_c_binding
   implicit none
-  integer(c_int), parameter :: LAPS_ABI_VERSION = 4, LAPS_PEER_BLOB_BYTES = 256
+  integer(c_int), parameter :: LAPS_ABI_VERSION = 5, LAPS_PEER_BLOB_BYTES = 256
 
   type, bind(C) :: laps_params          ! field order = include/laps_b200.h
     integer(c_int32_t) :: abi_version
@@ -31,6 +31,7 @@ module laps_gpu
     integer(c_int32_t) :: if_limit_dt_increase  ! 2D/mhd.f90:23
     integer(c_int32_t) :: incompressible        ! 1: src_incompressible (uu(8) = pressure)
     real(c_double)     :: rho0                  ! src_incompressible/mhdinit.f90:15
+    integer(c_int32_t) :: if_external_force     ! 2D/mhd.f90:43 (&pert), 2D compressible tree only
   end type
 
   type, bind(C) :: laps_extents
@@ -99,6 +100,12 @@ module laps_gpu
     end function
     integer(c_int) function laps_get_rho0(h, rho0) bind(C, name='laps_get_rho0')
       import; type(c_ptr), value :: h; real(c_double), intent(out) :: rho0
+    end function
+    integer(c_int) function laps_check_nan(h, is_nan) bind(C, name='laps_check_nan')
+      import; type(c_ptr), value :: h; integer(c_int32_t), intent(out) :: is_nan
+    end function
+    integer(c_int) function laps_set_external_force(h, force_local) bind(C, name='laps_set_external_force')
+      import; type(c_ptr), value :: h; real(c_double), intent(in) :: force_local(*)
     end function
   end interface
 end module laps_gpu

@@ -14,7 +14,7 @@ from typing import Optional
 
 import numpy as np
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_RANKS = 8
 PEER_BLOB_BYTES = 256
 
@@ -44,6 +44,7 @@ class LapsParams(C.Structure):
         ("device", C.c_int32),
         ("ndim", C.c_int32), ("if_z_radial", C.c_int32), ("if_limit_dt_increase", C.c_int32),
         ("incompressible", C.c_int32), ("rho0", C.c_double),
+        ("if_external_force", C.c_int32),
     ]
 
 
@@ -62,6 +63,7 @@ SYMBOLS = [
     "laps_fft_forward", "laps_fft_inverse", "laps_transpose_yz_indexmap",
     "laps_last_step_ms", "laps_set_profiling", "laps_get_profile", "laps_get_pruning",
     "laps_max_divv", "laps_max_div_real", "laps_get_rho0", "laps_get_field_counts", "laps_get_output", "laps_get_pruning_counts", "laps_set_primitive_modes",
+    "laps_check_nan", "laps_set_external_force",
 ]
 
 
@@ -105,6 +107,8 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.laps_max_divv.argtypes = [H, dp]
     lib.laps_max_div_real.argtypes = [H, dp]
     lib.laps_get_rho0.argtypes = [H, dp]
+    lib.laps_check_nan.argtypes = [H, C.POINTER(C.c_int32)]
+    lib.laps_set_external_force.argtypes = [H, dp]
     lib.laps_rms.argtypes = [H, dp]
     lib.laps_invariants.argtypes = [H, dp]
     lib.laps_get_state.argtypes = [H, dp, dp]

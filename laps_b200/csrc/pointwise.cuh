@@ -379,6 +379,18 @@ __global__ void __launch_bounds__(256) k_absmax(const double* f, size_t n, int n
   }
 }
 
+// checkNan (2D/mhd.f90:563-591): 1.0 where any of the n values is a NaN; partial layout [gridDim.x]
+__global__ void __launch_bounds__(256) k_nan_flag(const double* f, size_t n, double* partial) {
+  __shared__ double scratch[32];
+  double bad = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double v = f[i];
+    if (v != v) bad = 1.0;
+  }
+  const double r = block_reduce(bad, OpMax(), scratch);
+  if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+
 // Sparse fill of the spectral buffer for laps_set_primitive_modes: u[v][idx[e]] = val[v][e]
 __global__ void __launch_bounds__(256) k_scatter_modes(cplx* u, size_t fstride, const long long* idx, const cplx* val, int nent, int nfields) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;

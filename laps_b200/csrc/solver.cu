@@ -89,6 +89,8 @@ struct laps_solver {
   double* uu = nullptr;   // [8][npts] conserved
   double* J = nullptr;    // [3][npts]
   double* prim = nullptr; // [4][npts] scratch for get_state
+  double* ext = nullptr;  // [npts] external_force(:,:,1,1) of the 2D compressible tree (2D/mhdinit.f90:146-148)
+  int ext_slot = -1;      // its forward-field slot (transformed with the fluxes, 2D/mhdrhs.f90:216-251)
   void* bufX = nullptr;   // F (real fluxes) | V2
   void* bufY = nullptr;   // W1 | V1 (peer-written)
   void* bufZ = nullptr;   // W2 (peer-written)
@@ -738,6 +740,8 @@ int stage_front(S* s, bool with_cfl) {
     LAPS_TRY(check_launch(s, "k_flux"));
   }
   if (with_cfl) LAPS_TRY(reduce_launch(s, 3, 2, 0.0));   // the maxima travel to the host while the passes below run
+  if (s->ext_slot >= 0)   // calc_external_force_real (2D/mhdrhs.f90:129-131): the driver's field, transformed with the fluxes
+    LAPS_CK(s, cudaMemcpyAsync(buf_F(s) + (size_t)s->ext_slot * s->npts, s->ext, s->npts * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
   // transform_flux_real_to_fourier (mhdrhs.f90:128-172)
   LAPS_TRY(forward_xy(s, buf_F(s), s->npts, s->nf, true));
   }
@@ -746,7 +750,8 @@ int stage_front(S* s, bool with_cfl) {
 
 // The CFL sweep can ride on calc_flux only on the plain path (one k_flux launch over the whole slab).
 bool can_speculate(const S* s) {
-  return s->tune_spec && !s->incomp && !use_fused_flux(s) && !(s->tune_zchunk > 0 && !s->two_d);
+  // (the external force is user data of the step's own time: the driver sets it between two steps)
+  return s->tune_spec && !s->incomp && s->ext_slot < 0 && !use_fused_flux(s) && !(s->tune_zchunk > 0 && !s->two_d);
 }
 
 int stage(S* s, int irk) {
@@ -785,6 +790,7 @@ int stage(S* s, int irk) {
       z.task[5] = rhs_task(5, 5, L[14], 1.0, -1, 0.0, -1, 0.0, +1.0, -1, 0.0);
       z.task[6] = rhs_task(6, 6, L[13], -1.0, -1, 0.0, -1, 0.0, +1.0, L[12], +1.0);
       z.task[7] = rhs_task(7, 7, L[15], 1.0, -1, 0.0, X, -1.0, -1.0, L[16], -1.0);
+      if (s->ext_slot >= 0) { z.task[6].fx = s->ext_slot; z.task[6].cx = 1.0; }   // fnl(7) += external_force_fourier(1), 2D/mhdrhs.f90:370-372
       if (p.if_AEB && p.if_z_radial) {   // 2D/mhdrhs.f90:324-343
         static const double c2[8] = {2.0, 3.0, 3.0, 2.0, 1.0, 1.0, 2.0, 0.0};
         for (int v = 0; v < 8; ++v) z.task[v].aeb_c = c2[v];
@@ -878,6 +884,9 @@ int laps_create(const laps_params* params, laps_handle* out) {
     if (p.dealias_option < 0 || p.dealias_option > 2) { g_create_error = "dealias_option must be 0, 1 or 2"; return 1; }
     p.if_z_radial = 0; p.if_limit_dt_increase = 0;
   }
+  if (u.if_external_force && (!two_d || u.incompressible)) {
+    g_create_error = "if_external_force exists only in the 2D compressible tree (src_compressible/2D/mhd.f90:43)"; return 1;
+  }
   if (u.incompressible) {
     if (two_d && u.if_z_radial) { g_create_error = "if_z_radial does not exist in src_incompressible/2D"; return 1; }
     if (!(u.rho0 > 0.0)) { g_create_error = "incompressible: rho0 must be positive (mhdinit.f90:15)"; return 1; }
@@ -936,6 +945,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
       const int twin = j == 6 ? 4 : (j == 9 ? 5 : (j == 10 ? 8 : -1));   // (row, dir) -> (dir, row)
       if (on && s->sym_tensor && twin >= 0 && s->slot[twin] >= 0) { s->slot[j] = s->slot[twin]; s->fslot[j] = -1; --n; }
     }
+    if (two_d && !u.incompressible && u.if_external_force) s->ext_slot = n++;   // external_force_fourier(:,:,:,1)
     s->nf = n;
   }
   s->ni = 8 + (p.if_hall ? 3 : 0);
@@ -984,6 +994,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
   alloc((void**)&s->uu, 8 * s->npts * sizeof(double));
   if (p.if_hall || s->incomp) alloc((void**)&s->J, 3 * s->npts * sizeof(double));
   if (s->incomp) alloc((void**)&s->G, 9 * s->npts * sizeof(double));
+  if (s->ext_slot >= 0) alloc((void**)&s->ext, s->npts * sizeof(double));
   alloc(&s->bufX, s->bytesX); alloc(&s->bufY, s->bytesY); alloc(&s->bufZ, s->bytesZ);
   alloc((void**)&s->uA, 8 * s->csz * sizeof(cplx));
   alloc((void**)&s->uB, 8 * s->csz * sizeof(cplx));
@@ -996,6 +1007,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
   if (!ok) return fail("device allocation failed (state + work buffers need about " +
                        std::to_string((s->bytesX + s->bytesY + s->bytesZ + 24 * s->csz * 16 + 11 * s->npts * 8) >> 20) + " MiB)");
   if (cudaMallocHost((void**)&s->h_scal, 64 * sizeof(double)) != cudaSuccess) return fail("cudaMallocHost failed");
+  if (s->ext && cudaMemsetAsync(s->ext, 0, s->npts * sizeof(double), s->stream) != cudaSuccess) return fail("cudaMemsetAsync failed");
   {
     double* t = s->d_tab;
     s->kxr = t; s->kyr = s->kxr + s->nxh; s->kze = s->kyr + s->ny;
@@ -1140,7 +1152,7 @@ int laps_destroy(laps_handle s) {
     for (int j = 0; j < 3; ++j)
       if (s->ipc_opened[q][j]) cudaIpcCloseMemHandle(s->ipc_opened[q][j]);
   cudaFree(s->xblk);
-  cudaFree(s->uu); cudaFree(s->J); cudaFree(s->G); cudaFree(s->prim); cudaFree(s->bufX); cudaFree(s->bufY); cudaFree(s->bufZ);
+  cudaFree(s->uu); cudaFree(s->J); cudaFree(s->G); cudaFree(s->prim); cudaFree(s->ext); cudaFree(s->bufX); cudaFree(s->bufY); cudaFree(s->bufZ);
   cudaFree(s->uA); cudaFree(s->uB); cudaFree(s->rk); cudaFree(s->tw_x); cudaFree(s->tw_y); cudaFree(s->tw_z);
   cudaFree(s->d_tab); cudaFree(s->d_partial); cudaFree(s->d_scal); cudaFree(s->d_kymax_x); cudaFree(s->d_colmap);
   if (s->h_scal) cudaFreeHost(s->h_scal);
@@ -1476,6 +1488,31 @@ int laps_max_div_real(laps_handle s, double out[2]) {
   }
   LAPS_TRY(reduce_final(s, 2, 2, 0.0));
   out[0] = s->h_scal[0]; out[1] = s->h_scal[1];
+  return 0;
+}
+
+// external_force(ix,iy,1,1) of the 2D compressible tree: the user routine calc_external_force_real
+// (2D/mhdrhs.f90:480-531) stays in the driver, which hands its field over whenever it changes (it depends on
+// `time` only, i.e. once per step); every stage transforms it with the fluxes and adds it to fnl(7).
+int laps_set_external_force(laps_handle s, const double* force_local) {
+  if (!s || !force_local) return 1;
+  if (s->ext_slot < 0) { s->err = "laps_set_external_force: the handle was created without if_external_force"; return 1; }
+  LAPS_CK(s, cudaMemcpyAsync(s->ext, force_local, s->npts * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+  LAPS_CK(s, cudaStreamSynchronize(s->stream));   // the caller may reuse force_local
+  return 0;
+}
+
+// checkNan (2D/mhd.f90:563-591, src_incompressible/2D/mhd.f90:745-773): is any uu(ix,iy,iz,1:nvar) a NaN, on any rank.
+int laps_check_nan(laps_handle s, int32_t* is_nan) {
+  if (!s || !is_nan) return 1;
+  LAPS_TRY(require_state(s));
+  {
+    LaunchScope ls(s, "check_nan");
+    LAPS_LAUNCH(k_nan_flag, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, (const double*)s->uu, 8 * s->npts, s->d_partial);
+    LAPS_TRY(check_launch(s, "k_nan_flag"));
+  }
+  LAPS_TRY(reduce_final(s, 1, 2, 0.0));   // MPI_MAX over the ranks
+  *is_nan = s->h_scal[0] != 0.0 ? 1 : 0;
   return 0;
 }
 

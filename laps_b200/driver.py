@@ -47,7 +47,8 @@ def params_from_namelists(nl, rank=0, nranks=1, device=0, tree="compressible"):
     if tree.endswith("2d"):
         extra.update(ndim=2, if_limit_dt_increase=bool(g("numerical", "if_limit_dt_increase", False)))
         if tree == "compressible2d":
-            extra.update(if_z_radial=bool(g("aeb", "if_z_radial", False)))
+            extra.update(if_z_radial=bool(g("aeb", "if_z_radial", False)),
+                         if_external_force=bool(g("pert", "if_external_force", False)))   # 2D/mhd.f90:43
     if tree.startswith("incompressible"):
         extra.update(incompressible=1, rho0=1.0)
     if int(g("prl", "ndim_parallel", 1)) != 1 and nranks > 1:
@@ -76,6 +77,8 @@ class Driver:
         self.tree = tree
         self.two_d = tree.endswith("2d")
         self.dstep_calcdt = 20 if self.two_d else 1          # 2D/mhd.f90:22,237-240: vardt every 20 steps
+        self.dstep_checknan = 200 if self.two_d else 0       # 2D/mhd.f90:25,242-252: checkNan every 200 steps
+        self.stopped_on_nan = False
         self.outdir = outdir
         self.rank, self.nranks = rank, nranks
         self.barrier = barrier or (lambda: None)
@@ -103,6 +106,20 @@ class Driver:
 
     def path(self, name):
         return os.path.join(self.outdir, name)
+
+    def external_force(self):
+        """The user routine calc_external_force_real as the reference ships it (2D/mhdrhs.f90:480-531): a Gaussian
+        forcing of B_z centred at x = Lx/2 whose y centre moves at speed 0.3, with its two periodic images."""
+        Lx, Ly = self.kw["Lx"], self.kw["Ly"]
+        x = np.arange(self.nx) * (Lx / self.nx)
+        y = np.arange(self.ny) * (Ly / self.ny)
+        dBdt, xc, w = 0.2, 0.5 * Lx, 0.05 * Ly
+        yc = math.fmod(0.2 * Ly + 0.3 * self.time, Ly)
+        fx = np.exp(-((x - xc) / w) ** 2)[None, :]
+        f = dBdt * fx * np.exp(-((y[:, None] - yc) / w) ** 2)
+        f = f + dBdt * fx * np.exp(-((y[:, None] - (yc + Ly)) / w) ** 2)
+        f = f + dBdt * fx * np.exp(-((y[:, None] - (yc - Ly)) / w) ** 2)
+        return f[None]
 
     # ------------------------------------------------------------------ initial data
     def initial_primitive(self):
@@ -230,6 +247,8 @@ class Driver:
                 self.output_aeb()
                 break
             s.time = self.time
+            if kw.get("if_external_force"):                   # calc_external_force_real, called from calc_flux with the
+                s.set_external_force(self.external_force())   # step's `time` (2D/mhdrhs.f90:129-131,480-531)
             s.evolve()                                        # mhd.f90:245
             self.time = self.time + dt
             self.istep += 1
@@ -247,6 +266,11 @@ class Driver:
                 tlog += dtlog
             if self.istep % self.dstep_calcdt == 0:
                 dt = s.vardt()                                # :285 (2D trees: every dstep_calcdt steps)
+            if self.dstep_checknan and self.istep % self.dstep_checknan == 0 and s.checkNan():   # 2D/mhd.f90:242-252
+                if echo and self.rank == 0:
+                    print(" NaN encountered!!! Exit the program at t = %10.4f" % self.time)
+                self.stopped_on_nan = True
+                break
         self.write_log(dt)
         return self.istep
 

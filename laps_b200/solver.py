@@ -153,6 +153,19 @@ class Solver:
         self._ck(self._lib.laps_max_div_real(self._h, capi._dptr(out)))
         return float(out[0]), float(out[1])
 
+    def checkNan(self) -> bool:
+        """2D/mhd.f90:563-591 (checkNan): is any uu value a NaN on any rank."""
+        out = C.c_int32()
+        self._ck(self._lib.laps_check_nan(self._h, C.byref(out)))
+        return bool(out.value)
+
+    def set_external_force(self, force: np.ndarray):
+        """The field of calc_external_force_real (2D/mhdrhs.f90:480-531), shape (1, ny, nx) like one variable of uu;
+        it is transformed and added to fnl(7) in every stage until it is replaced."""
+        f = np.ascontiguousarray(force, dtype=np.float64)
+        assert f.size == int(np.prod(self.real_shape)), (f.shape, self.real_shape)
+        self._ck(self._lib.laps_set_external_force(self._h, capi._dptr(f)))
+
     @property
     def rho0(self) -> float:
         """Background density of the incompressible tree after update_rho_p (AEBmod.f90:123-134)."""

@@ -67,6 +67,7 @@ class Params:
     # 2D tree only (src_compressible/2D/mhd.f90:23,35,44; 2D/mhdinit.f90:23)
     if_z_radial: bool = False
     if_limit_dt_increase: bool = False
+    if_external_force: bool = False              # 2D/mhdinit.f90:24 (&pert, 2D/mhd.f90:43)
     # incompressible tree only (src_incompressible/mhdinit.f90:15): which State class applies, and rho0
     incompressible: bool = False
     rho0: float = 1.0
@@ -477,7 +478,7 @@ class State2D(State):
     """Restatement of the 2D compressible tree; citations are relative to src_compressible/2D/.
     Arrays keep the 3D shapes with nz = 1 ([v, 0, iy, ix]), exactly like the Fortran arrays
     uu(ix,iy,1,v); the z transform of length 1 is the identity (2D/fftw.f90 has only x and y passes).
-    Not restated: the user-supplied external force (2D/mhdrhs.f90:480-531, if_external_force)."""
+    The user routine calc_external_force_real is restated as shipped (the moving Gaussian forcing of B_z)."""
 
     def __init__(self, p: Params):
         assert p.nz == 1, "the 2D tree has nz = 1"
@@ -527,6 +528,40 @@ class State2D(State):
                       - (Bx ** 2 + By ** 2 + 2.0 * Bz ** 2) / tau
                       - (2 * uu[1] * pr[0] + 2 * uu[2] * pr[1] + uu[3] * pr[2]) / tau)
         return flux, expand
+
+    def calc_external_force_real(self):
+        """2D/mhdrhs.f90:480-531 as shipped: dBz/dt forcing, Gaussian in x around Lx/2, Gaussian in y around a
+        centre that moves at 0.3 along y (with its two periodic images); `time` is the module variable, i.e. the
+        time at the start of the step for all three stages (it advances after evolve, 2D/mhd.f90:232)."""
+        p, g = self.p, self.g
+        dBdt = 0.2
+        xc = 0.5 * p.Lx
+        x_width = 0.05 * p.Ly
+        yc = math.fmod(0.2 * p.Ly + 0.3 * self.time, p.Ly)
+        y_width = 0.05 * p.Ly
+        func_x = np.exp(-((g.xgrid - xc) / x_width) ** 2)[None, None, :]
+        y = g.ygrid[None, :, None]
+        f = dBdt * func_x * np.exp(-((y - yc) / y_width) ** 2)
+        f = f + dBdt * func_x * np.exp(-((y - (yc + p.Ly)) / y_width) ** 2)
+        f = f + dBdt * func_x * np.exp(-((y - (yc - p.Ly)) / y_width) ** 2)
+        return f
+
+    def stage(self, irk):
+        """2D/mhd.f90 evolve: as the 3D loop body; calc_flux ends with calc_external_force_real (2D/mhdrhs.f90:129-131),
+        transform_flux_real_to_fourier transforms it (:216-251) and calc_rhs adds it to fnl(7) (:370-372)."""
+        if not self.p.if_external_force:
+            return super().stage(irk)
+        flux, expand = self.calc_flux()
+        self.external_force = self.calc_external_force_real()
+        ff = fft_forward(flux)
+        ef = fft_forward(expand) if expand is not None else None
+        xf = fft_forward(self.external_force)
+        self.calc_rhs(ff, ef)
+        self.fnl[6] = self.fnl[6] + xf
+        self.rkt(irk)
+        self.dealias()
+        self.uu = fft_inverse(self.uu_fourier, self.p.nx)
+        self.update_uu_prim_from_uu()
 
     def calc_rhs(self, flux_fourier, expand_fourier):
         """2D/mhdrhs.f90:255-392."""

@@ -45,6 +45,14 @@ def test_one_step_2d_tree(emu, kw):
     g.close()
 
 
+def test_external_force_2d_tree(emu):
+    pc.check_external_force((32, 16), lib_path=emu)
+
+
+def test_check_nan(emu):
+    pc.check_nan_detection(lib_path=emu)
+
+
 @pytest.mark.parametrize("kw", [dict(hall=True, aeb=True, dealias=1), dict(hall=True, aeb=True, corot=True, dealias=2),
                                 dict(hall=False, aeb=False, dealias=0, explicit=True, conserve_bg=True)])
 def test_one_step_incompressible_tree(emu, kw):

@@ -208,3 +208,28 @@ def test_driver_runs_the_other_source_trees_on_the_emulator(emu, tmp_path, tree)
     for v in range(8):
         assert pc.rel_l2(data[v], ref[v]) < 1e-10 or np.abs(data[v] - ref[v]).max() < 1e-13, v
     d.solver.close()
+
+
+def test_driver_external_force_and_checknan_on_the_emulator(emu, tmp_path):
+    """&pert if_external_force = T in the 2D compressible tree: the stand-in driver evaluates the shipped user routine
+    (2D/mhdrhs.f90:480-531) once per step and hands the field to the library; same state as the oracle.  checkNan
+    (2D/mhd.f90:242-252) runs at its cadence and does not stop a healthy run."""
+    text = INPUT.replace("ipert = 7", "ipert = 1\n   if_external_force = T").replace("Bx0 = 1.", "Bx0 = 1.\n   wave_number_jet = 2")
+    (tmp_path / "mhd.input").write_text(text)
+    d = Driver(str(tmp_path / "mhd.input"), str(tmp_path), lib_path=emu, tree="compressible2d")
+    assert d.kw["if_external_force"] is True
+    d.dstep_checknan = 2
+    prim0 = d.initial_primitive()
+    assert d.run(max_steps=3, echo=False) == 3 and not d.stopped_on_nan
+    kw = {k: v for k, v in d.kw.items() if k not in ("rank", "nranks", "device", "ndim", "incompressible")}
+    o = lo.State2D(lo.Params(**kw))
+    o.set_primitive(prim0)
+    o.vardt()
+    for _ in range(3):
+        o.step(calc_dt=False)
+    assert abs(d.time - o.time) < 1e-12
+    uu, _ = d.solver.get_state()
+    for v in range(8):
+        assert pc.rel_l2(uu[v], o.uu[v]) < 1e-11 or np.abs(uu[v] - o.uu[v]).max() < 1e-13, v
+    assert np.abs(o.uu[6]).max() > 1e-3          # the forcing has built up a B_z
+    d.solver.close()
