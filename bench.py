@@ -349,6 +349,32 @@ def run_gpu(args):
                                 "what": "columns removed by the dealiasing mask are skipped exactly (bit-identical state)"},
                     "time_share": shares}
 
+    # ---------------- NVLink: the slab transposes are the remote stores of the y pass and the z pass ----------------
+    nvlink = None
+    if world > 1:
+        t = torch.tensor([float(live_cols)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        total_cols = float(t.item())
+        per_kernel = {}
+        import re as _re
+        for k, (tms, cnt) in prof.items():
+            m = _re.fullmatch(r"fwd_y(\d+)", k)
+            if m:      # every surviving (kx, ky) column of this rank's z slab goes to the owner of ky (transpose_yz)
+                remote = int(m.group(1)) * 16.0 * g.nzl * (total_cols - live_cols)
+            elif k == "spec_z":       # the inverse-z lines of this rank's columns go to the owners of z (transpose_zy)
+                remote = rows * 16.0 * live_cols * (n - g.nzl)
+            elif k == "curl_b_inv_z":
+                remote = (3 + (1 if mass else 0)) * 16.0 * live_cols * (n - g.nzl)
+            else:
+                continue
+            per_kernel[k] = {"remote_bytes_per_launch": remote, "avg_launch_ms": tms / cnt,
+                             "egress_GBps": remote / (tms / cnt * 1e-3) / 1e9}
+        sent = sum(v["remote_bytes_per_launch"] * prof[k][1] for k, v in per_kernel.items()) / args.steps
+        nvlink = {"what": "bytes this rank stores into its peers' buffers over NVLink inside the y pass (transpose_yz) and the "
+                          "z passes (transpose_zy), per launch, over the launch's own duration (the kernel also does its HBM work in that time)",
+                  "peak": 900.0, "unit": "GB/s per direction (nominal NVLink 5)", "per_kernel": per_kernel,
+                  "egress_bytes_per_step": sent, "egress_GBps_over_the_step": sent / (ms_step * 1e-3) / 1e9}
+
     barrier()          # no rank may free its exchange buffers while a peer can still store into them
     g.close()
     if rank != 0:
@@ -375,6 +401,7 @@ def run_gpu(args):
         "e2e": {"value": float(n) ** 3 / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms, "what": "laps_set_primitive(host) + K x laps_step + laps_get_output(host), per step"},
         "gpu_launches": launches,
+        "nvlink": nvlink,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "state_finite": finite,
