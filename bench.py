@@ -141,6 +141,31 @@ def kernel_bytes(name, R, C, nf, ni, hall, fx=1.0, fcol=1.0, fmode=1.0, mass=Fal
     return table.get(name)
 
 
+def nvlink_model(prof, live_cols, total_cols, rows, mass, n, nzl, steps, ms_step):
+    """Bytes one rank stores into its peers' buffers (the reference's transpose_yz / transpose_zy, parallel.f90:273-324,
+    fused into the passes) per launch of each exchanging kernel, over that launch's mean duration.  prof: name ->
+    [total ms, launches]; live_cols / total_cols: surviving (kx, ky) columns owned by this rank / by all ranks."""
+    import re
+    per_kernel = {}
+    for k, (tms, cnt) in prof.items():
+        m = re.fullmatch(r"fwd_y(\d+)", k)
+        if m:      # every surviving (kx, ky) column of this rank's z slab goes to the owner of ky (transpose_yz)
+            remote = int(m.group(1)) * 16.0 * nzl * (total_cols - live_cols)
+        elif k == "spec_z":       # the inverse-z lines of this rank's columns go to the owners of z (transpose_zy)
+            remote = rows * 16.0 * live_cols * (n - nzl)
+        elif k == "curl_b_inv_z":  # J (3 lines) + the continuity row when it is taken from the state
+            remote = (3 + (1 if mass else 0)) * 16.0 * live_cols * (n - nzl)
+        else:
+            continue
+        per_kernel[k] = {"remote_bytes_per_launch": remote, "avg_launch_ms": tms / cnt,
+                         "egress_GBps": remote / (tms / cnt * 1e-3) / 1e9}
+    sent = sum(v["remote_bytes_per_launch"] * prof[k][1] for k, v in per_kernel.items()) / steps
+    return {"what": "bytes this rank stores into its peers' buffers over NVLink inside the y pass (transpose_yz) and the z passes "
+                    "(transpose_zy), per launch, over the launch's own duration (the kernel does its HBM work in the same time)",
+            "peak": 900.0, "unit": "GB/s per direction (nominal NVLink 5)", "per_kernel": per_kernel,
+            "egress_bytes_per_step": sent, "egress_GBps_over_the_step": sent / (ms_step * 1e-3) / 1e9}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -354,26 +379,7 @@ def run_gpu(args):
     if world > 1:
         t = torch.tensor([float(live_cols)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        total_cols = float(t.item())
-        per_kernel = {}
-        import re as _re
-        for k, (tms, cnt) in prof.items():
-            m = _re.fullmatch(r"fwd_y(\d+)", k)
-            if m:      # every surviving (kx, ky) column of this rank's z slab goes to the owner of ky (transpose_yz)
-                remote = int(m.group(1)) * 16.0 * g.nzl * (total_cols - live_cols)
-            elif k == "spec_z":       # the inverse-z lines of this rank's columns go to the owners of z (transpose_zy)
-                remote = rows * 16.0 * live_cols * (n - g.nzl)
-            elif k == "curl_b_inv_z":
-                remote = (3 + (1 if mass else 0)) * 16.0 * live_cols * (n - g.nzl)
-            else:
-                continue
-            per_kernel[k] = {"remote_bytes_per_launch": remote, "avg_launch_ms": tms / cnt,
-                             "egress_GBps": remote / (tms / cnt * 1e-3) / 1e9}
-        sent = sum(v["remote_bytes_per_launch"] * prof[k][1] for k, v in per_kernel.items()) / args.steps
-        nvlink = {"what": "bytes this rank stores into its peers' buffers over NVLink inside the y pass (transpose_yz) and the "
-                          "z passes (transpose_zy), per launch, over the launch's own duration (the kernel also does its HBM work in that time)",
-                  "peak": 900.0, "unit": "GB/s per direction (nominal NVLink 5)", "per_kernel": per_kernel,
-                  "egress_bytes_per_step": sent, "egress_GBps_over_the_step": sent / (ms_step * 1e-3) / 1e9}
+        nvlink = nvlink_model(prof, live_cols, float(t.item()), rows, mass, n, g.nzl, args.steps, ms_step)
 
     barrier()          # no rank may free its exchange buffers while a peer can still store into them
     g.close()

@@ -1,0 +1,52 @@
+"""The byte models bench.py reports: algorithmic HBM bytes per launch and the NVLink egress of
+the fused transposes.  Pure host arithmetic — importing bench.py needs neither a GPU nor the CUDA library."""
+import importlib.util
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _bench():
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_stage_bytes_add_up_to_the_survey_figure():
+    """with nothing pruned and the reference's 19 + 11 fields the passes of one stage move
+    B_stage = 2 ni R + (4 nf + 4 ni + 40) C."""
+    b = _bench()
+    R, C, nf, ni = 3.0, 5.0, 19, 11
+    kb = lambda k: b.kernel_bytes(k, R, C, nf, ni, True)  # noqa: E731
+    total = (kb("flux") + kb(f"fwd_x{nf}") + kb(f"fwd_y{nf}") + kb("spec_z") + kb("curl_b_inv_z")
+             + kb(f"inv_y{ni}") + kb(f"inv_x{ni}"))
+    # against that fused model: the separate calc_flux sweep writes the nf fluxes and the x pass reads them back
+    # (+2 nf R); the RK history is not read in stage 1 and not written in stage 3 (-16/3 C on the stage average); the
+    # inverse z transform starts from registers (-8 C); the current re-reads B^ (+3 C)
+    fused = 2 * ni * R + (4 * nf + 4 * ni + 40) * C
+    extra = 2 * nf * R + (-16.0 / 3 - 8 + 3) * C
+    assert abs(total - (fused + extra)) < 1e-9 * total, (total, fused + extra)
+
+
+def test_pruned_pass_bytes_scale_with_the_surviving_fractions():
+    b = _bench()
+    full = b.kernel_bytes("fwd_y13", 1.0, 1.0, 13, 11, True)
+    half = b.kernel_bytes("fwd_y13", 1.0, 1.0, 13, 11, True, fx=0.5, fcol=0.25)
+    assert full == 26.0 and half == 13 * 0.5 + 13 * 0.25
+    assert b.kernel_bytes("no_such_kernel", 1.0, 1.0, 13, 11, True) is None
+
+
+def test_nvlink_model_counts_the_remote_share():
+    b = _bench()
+    prof = {"fwd_y13": [20.0, 10], "spec_z": [30.0, 30], "curl_b_inv_z": [6.0, 30], "flux": [9.0, 30]}
+    n, nzl, mine, total = 512, 128, 1000, 4000.0
+    out = b.nvlink_model(prof, mine, total, rows=7, mass=True, n=n, nzl=nzl, steps=10, ms_step=25.0)
+    k = out["per_kernel"]
+    assert set(k) == {"fwd_y13", "spec_z", "curl_b_inv_z"}
+    assert k["fwd_y13"]["remote_bytes_per_launch"] == 13 * 16 * nzl * 3000
+    assert k["spec_z"]["remote_bytes_per_launch"] == 7 * 16 * mine * (n - nzl)
+    assert k["curl_b_inv_z"]["remote_bytes_per_launch"] == 4 * 16 * mine * (n - nzl)
+    assert abs(k["fwd_y13"]["egress_GBps"] - 13 * 16 * nzl * 3000 / 2e-3 / 1e9) < 1e-9
+    per_step = (13 * 16 * nzl * 3000 * 10 + 11 * 16 * mine * (n - nzl) * 30) / 10
+    assert out["egress_bytes_per_step"] == per_step
