@@ -1253,6 +1253,7 @@ int laps_set_primitive_modes(laps_handle s, int32_t nmodes, const int32_t* k, co
   for (int v = 0; v < 8; ++v) val.insert(val.end(), rows[v].begin(), rows[v].end());
   LAPS_CK(s, cudaMemsetAsync(s->uB, 0, 8 * s->csz * sizeof(cplx), s->stream));
   long long* d_idx = nullptr; cplx* d_val = nullptr;
+  struct Release { long long*& a; cplx*& b; ~Release() { cudaFree(a); cudaFree(b); } } release{d_idx, d_val};   // also on the error returns
   if (nent > 0) {
     LAPS_CK(s, cudaMalloc((void**)&d_idx, nent * sizeof(long long)));
     LAPS_CK(s, cudaMalloc((void**)&d_val, (size_t)8 * nent * sizeof(cplx)));
@@ -1277,7 +1278,6 @@ int laps_set_primitive_modes(laps_handle s, int32_t nmodes, const int32_t* k, co
     LAPS_TRY(inverse_yx(s, 0, 8, false));
   }
   LAPS_CK(s, cudaStreamSynchronize(s->stream));
-  cudaFree(d_idx); cudaFree(d_val);
   return finish_set_primitive(s);
 }
 
