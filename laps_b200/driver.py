@@ -214,8 +214,12 @@ class Driver:
             x = np.arange(self.nx) * (kw["Lx"] / self.nx)
             y = np.arange(self.ny) * (kw["Ly"] / self.ny)
             z = np.arange(self.nz) * (kw["Lz"] / self.nz)
-            lapsio.write_grid(self.path("grid.dat"), x, y, z)                                  # mhd.f90:139
-            lapsio.write_parallel_info(self.path("parallel_info.dat"), self.nranks, 1, self.nranks)   # :140
+            if self.two_d:                                    # 2D/mhdoutput.f90:45-63: nx, ny / npe, nvar only
+                lapsio.write_grid(self.path("grid.dat"), x, y)
+                lapsio.write_parallel_info(self.path("parallel_info.dat"), self.nranks)
+            else:
+                lapsio.write_grid(self.path("grid.dat"), x, y, z)                                  # mhd.f90:139
+                lapsio.write_parallel_info(self.path("parallel_info.dat"), self.nranks, 1, self.nranks)   # :140
             if not self.if_restart:
                 open(self.path("rms.dat"), "w").close()       # rms_initialize / AEB_initialize create or append
                 open(self.path("EBM_info.dat"), "w").close()

@@ -119,18 +119,20 @@ def _record(payload: bytes) -> bytes:
 # ----------------------------------------------------------------------------------------------
 # writers
 # ----------------------------------------------------------------------------------------------
-def write_grid(path: str, xgrid, ygrid, zgrid):
-    """mhdoutput.f90:51-60."""
-    nx, ny, nz = len(xgrid), len(ygrid), len(zgrid)
+def write_grid(path: str, xgrid, ygrid, zgrid=None):
+    """mhdoutput.f90:51-60; with ``zgrid=None`` the file of the 2D trees (2D/mhdoutput.f90:45-54): nx, ny and the
+    two grids only."""
+    grids = [g for g in (xgrid, ygrid, zgrid) if g is not None]
     with open(path, "wb") as f:
-        f.write(_record(np.array([nx, ny, nz], dtype="<f4").tobytes()))
-        f.write(_record(np.concatenate([np.asarray(g, dtype="<f4") for g in (xgrid, ygrid, zgrid)]).tobytes()))
+        f.write(_record(np.array([len(g) for g in grids], dtype="<f4").tobytes()))
+        f.write(_record(np.concatenate([np.asarray(g, dtype="<f4") for g in grids]).tobytes()))
 
 
-def write_parallel_info(path: str, npe: int, iproc: int, jproc: int, nvar: int = 8):
-    """mhdoutput.f90:62-69."""
+def write_parallel_info(path: str, npe: int, iproc: int | None = None, jproc: int | None = None, nvar: int = 8):
+    """mhdoutput.f90:62-69; with ``iproc=None`` the file of the 2D trees (2D/mhdoutput.f90:56-63): npe, nvar."""
+    vals = [npe, nvar] if iproc is None else [npe, iproc, jproc, nvar]
     with open(path, "wb") as f:
-        f.write(_record(np.array([npe, iproc, jproc, nvar], dtype="<f4").tobytes()))
+        f.write(_record(np.array(vals, dtype="<f4").tobytes()))
 
 
 OUT_DISPLACEMENT = 12   # mhdoutput.f90:10
@@ -190,16 +192,20 @@ def read_out_slab(path: str, nx: int, ny: int, nz: int, z_offset: int = 0, z_siz
 
 
 def read_grid(path: str):
+    """-> (xgrid, ygrid, zgrid), or (xgrid, ygrid) for a file of the 2D trees (the first record says which)."""
     with open(path, "rb") as f:
         raw = f.read()
     n0 = struct.unpack_from("<i", raw, 0)[0]
-    nx, ny, nz = (int(v) for v in np.frombuffer(raw, dtype="<f4", count=3, offset=4))
+    dims = [int(v) for v in np.frombuffer(raw, dtype="<f4", count=n0 // 4, offset=4)]
     off = 4 + n0 + 4 + 4
-    g = np.frombuffer(raw, dtype="<f4", count=nx + ny + nz, offset=off).astype(np.float64)
-    return g[:nx], g[nx:nx + ny], g[nx + ny:]
+    g = np.frombuffer(raw, dtype="<f4", count=sum(dims), offset=off).astype(np.float64)
+    edges = np.cumsum([0] + dims)
+    return tuple(g[a:b] for a, b in zip(edges[:-1], edges[1:]))
 
 
 def read_parallel_info(path: str):
+    """-> (npe, iproc, jproc, nvar), or (npe, nvar) for a file of the 2D trees."""
     with open(path, "rb") as f:
         raw = f.read()
-    return tuple(int(v) for v in np.frombuffer(raw, dtype="<f4", count=4, offset=4))
+    n0 = struct.unpack_from("<i", raw, 0)[0]
+    return tuple(int(v) for v in np.frombuffer(raw, dtype="<f4", count=n0 // 4, offset=4))

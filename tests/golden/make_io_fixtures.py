@@ -21,14 +21,33 @@ sys.path.insert(0, ROOT)
 from laps_b200 import lapsio  # noqa: E402
 
 REF = "/root/reference/data_process/3D_Python/read_output.py"
+REF_2D = "/root/reference/data_process/2D_Python/read_output.py"
 
 
-def reference_reader_functions():
-    tree = ast.parse(open(REF).read())
+def reference_reader_functions(path=REF):
+    tree = ast.parse(open(path).read())
     funcs = [n for n in tree.body if isinstance(n, ast.FunctionDef)]
     ns = {"np": np, "struct": struct}
-    exec(compile(ast.Module(body=funcs, type_ignores=[]), REF, "exec"), ns)
+    exec(compile(ast.Module(body=funcs, type_ignores=[]), path, "exec"), ns)
     return ns
+
+
+def write_all_2d(outdir, nx=6, ny=4, nranks=1):
+    """The files of the 2D trees (2D/mhdoutput.f90:45-63: grid.dat holds nx, ny and two grids, parallel_info.dat
+    npe and nvar; outNNN.dat is the 3D layout with nz = 1)."""
+    os.makedirs(outdir, exist_ok=True)
+    grids = [np.arange(n) * (l / n) for n, l in zip((nx, ny), (24.0, 12.0))]
+    lapsio.write_grid(os.path.join(outdir, "grid.dat"), *grids)
+    lapsio.write_parallel_info(os.path.join(outdir, "parallel_info.dat"), nranks)
+    a = sample_fields(nx, ny, 1)
+    path = os.path.join(outdir, lapsio.out_name(7))
+    lapsio.write_out_header(path, 0.375)
+    with open(path, "r+b") as f:
+        f.truncate(lapsio.OUT_DISPLACEMENT + 8 * a.size)
+    lapsio.write_out_slab(path, a, 1, 0)
+    with open(os.path.join(outdir, "EBM_info.dat"), "w") as f:
+        f.write(lapsio.ebm_line(0.0, 30.0, 1.167) + "\n")      # a single line: the reader's reshape branch
+    return a, grids
 
 
 def sample_fields(nx, ny, nz, nvar=8):
@@ -90,6 +109,23 @@ def main():
     np.savez(os.path.join(base, "expected.npz"), npe=npe, iproc=iproc, jproc=jproc, nvar=nvar, xgrid=xg, ygrid=yg, zgrid=zg,
              t=t, uu=uu, loc=loc, slice_xy=sl, t_ebm=t_ebm, radius=radius, ur=ur, rms=rms)
     print("fixtures written to", base)
+    # ---- the 2D trees, read back by data_process/2D_Python/read_output.py
+    base2 = os.path.join(HERE, "io2d")
+    a2, grids2 = write_all_2d(os.path.join(base2, "output"))
+    ns = reference_reader_functions(REF_2D)
+    os.chdir(base2)
+    try:
+        npe, nvar = ns["read_parallel_info"]()
+        xg, yg = ns["read_grid"]()
+        t, uu = ns["read_uu"]("./output/out007.dat", len(xg), len(yg), nvar)
+        t_ebm, radius, ur = ns["read_EBM"]()
+    finally:
+        os.chdir(cwd)
+    assert (npe, nvar) == (1, 8) and t == np.float32(0.375)
+    assert np.array_equal(uu, a2[:, 0].transpose(2, 1, 0))       # the 2D reader returns uu[ix,iy,ivar]
+    assert np.allclose(xg, grids2[0], rtol=1e-7) and np.allclose(yg, grids2[1], rtol=1e-7)
+    np.savez(os.path.join(base2, "expected.npz"), npe=npe, nvar=nvar, xgrid=xg, ygrid=yg, t=t, uu=uu, t_ebm=t_ebm, radius=radius, ur=ur)
+    print("fixtures written to", base2)
 
 
 if __name__ == "__main__":

@@ -48,6 +48,25 @@ def test_readers_agree_with_what_the_reference_reader_returned():
     assert np.array_equal(rms, e["rms"])
 
 
+def test_2d_tree_files_against_the_reference_2d_reader(tmp_path):
+    """2D/mhdoutput.f90:45-63: grid.dat = (nx, ny) + two grids, parallel_info.dat = (npe, nvar).  The golden files
+    were read back by data_process/2D_Python/read_output.py when they were generated."""
+    gold = os.path.join(HERE, "golden", "io2d")
+    fx.write_all_2d(str(tmp_path))
+    for name in ("grid.dat", "parallel_info.dat", "out007.dat", "EBM_info.dat"):
+        with open(os.path.join(gold, "output", name), "rb") as a, open(tmp_path / name, "rb") as b:
+            assert a.read() == b.read(), name
+    e = np.load(os.path.join(gold, "expected.npz"))
+    out = os.path.join(gold, "output")
+    assert lapsio.read_parallel_info(os.path.join(out, "parallel_info.dat")) == (int(e["npe"]), int(e["nvar"]))
+    xg, yg = lapsio.read_grid(os.path.join(out, "grid.dat"))
+    assert np.array_equal(xg, e["xgrid"]) and np.array_equal(yg, e["ygrid"])
+    f = os.path.join(out, "out007.dat")
+    assert lapsio.read_out_header(f) == float(e["t"])
+    full = lapsio.read_out_slab(f, len(xg), len(yg), 1)
+    assert np.array_equal(full[:, 0].transpose(2, 1, 0), e["uu"])        # the 2D reader's layout uu[ix,iy,ivar]
+
+
 def test_fortran_edit_descriptors():
     assert lapsio.fmt_1pe16_8(1.0) == "  1.00000000E+00"
     assert lapsio.fmt_1pe16_8(-3.75e5) == " -3.75000000E+05"
@@ -199,6 +218,12 @@ def test_driver_runs_the_other_source_trees_on_the_emulator(emu, tmp_path, tree)
         if i == 0 and not tree.endswith("2d"):       # the 2D drivers call vardt every 20 steps only
             o.vardt()
     assert abs(d.time - o.time) < 1e-12
+    if tree.endswith("2d"):      # 2D/mhdoutput.f90:45-63
+        assert len(lapsio.read_grid(str(tmp_path / "grid.dat"))) == 2
+        assert lapsio.read_parallel_info(str(tmp_path / "parallel_info.dat")) == (1, 8)
+    else:
+        assert len(lapsio.read_grid(str(tmp_path / "grid.dat"))) == 3
+        assert lapsio.read_parallel_info(str(tmp_path / "parallel_info.dat")) == (1, 1, 1, 8)
     names = sorted(f for f in os.listdir(tmp_path) if f.startswith("out"))
     data = lapsio.read_out_slab(str(tmp_path / names[-1]), 16, 16, 1 if tree.endswith("2d") else 16)
     ref = o.uu.copy()
