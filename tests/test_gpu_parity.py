@@ -92,15 +92,6 @@ def test_2d_tree_parity(name, kw):
     g.close()
 
 
-def test_2d_tree_external_force():
-    """if_external_force (2D/mhdrhs.f90:480-531) at 256 x 128, three steps, against the oracle."""
-    pc.check_external_force((256, 128))
-
-
-def test_check_nan():
-    pc.check_nan_detection()
-
-
 def test_2d_tree_2048_properties():
     """BASELINE config 2 at full size (2048^2, Hall, no expansion): k=0 mode conserved bit-exactly,
     div B conserved to round-off, forward transform of the real state reproduces the spectrum."""
@@ -264,3 +255,12 @@ def test_full_size_properties_512():
         spec = g.fft_forward(uu1[:2])
         ref = g.uu_fourier()[:2]
         assert pc.rel_l2(spec, ref) < 1e-13
+
+
+def test_2d_tree_external_force():
+    """if_external_force (2D/mhdrhs.f90:480-531) at 256 x 128, three steps, against the oracle."""
+    pc.check_external_force((256, 128))
+
+
+def test_check_nan():
+    pc.check_nan_detection()

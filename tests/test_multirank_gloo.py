@@ -93,3 +93,10 @@ def test_cyclic_ky_ownership(emu, world, shape):
 def test_cyclic_ky_ownership_incompressible(emu):
     run_ranks(2, dict(lib=emu, shape=(16, 16, 16), incompressible=True, case=dict(hall=True, aeb=True, dealias=2), steps=1,
                       env=dict(LAPS_TUNE_CYCLIC="1")))
+
+
+def test_four_ranks_incompressible_default_ownership(emu):
+    # the incompressible tree at 4 ranks with the spherical mask: round-robin rows by default (12 inverse + 6 forward
+    # transforms per stage and the projection kernel over the strided rows)
+    run_ranks(4, dict(lib=emu, shape=(16, 16, 16), incompressible=True, case=dict(hall=True, aeb=True, dealias=1), steps=1,
+                      expect_stride=4))
