@@ -1,4 +1,5 @@
-// In-shared-memory FP64 complex FFT building blocks for one "line" of N = 2^L points (16 <= N <= 4096).
+// In-shared-memory FP64 complex FFT building blocks for one "line" of N = 2^L points (8 <= N <= 4096; N = 8 is a
+// single register-resident radix-8 stage: one thread per line, no exchange).
 //
 // Replaces the per-line FFTW executions of the reference (fftw.f90:61,97,159,176,198,215 and
 // mhdrhs.f90:146,162,357): N/8 threads cooperate on a line, every thread holds 8 points in
@@ -19,7 +20,7 @@ constexpr int ilog2c(int n) { return n <= 1 ? 0 : 1 + ilog2c(n >> 1); }
 
 template <int N>
 struct Geom {
-  static_assert(N >= 16 && N <= 4096 && (N & (N - 1)) == 0, "line length must be a power of two in [16,4096]");
+  static_assert(N >= 8 && N <= 4096 && (N & (N - 1)) == 0, "line length must be a power of two in [8,4096]");
   static constexpr int LOG2 = ilog2c(N);
   static constexpr int NSTAGE = (LOG2 + 2) / 3;
   static constexpr int RLAST = 1 << (LOG2 - 3 * (NSTAGE - 1));
@@ -145,6 +146,7 @@ struct Fft {
   // Stage 0.  r[e] = x[u + e*N/8] on entry.  Leaves the twiddled outputs in the smem line.
   LAPS_D static void first_w(cplx (&r)[8], int u, cplx* __restrict__ line, cplx w) {
     bfly8<DIR>(r);
+    if constexpr (G::NSTAGE == 1) return;   // N = 8: r[e] = X[e] already, nothing goes through the line
     twiddle8(r, w);
     LAPS_UNROLL
     for (int e = 0; e < 8; ++e) line[G::pad(u + e * G::w(0))] = r[e];
@@ -175,7 +177,7 @@ struct Fft {
   // Base position (8 consecutive slots base..base+7) read by thread u in the last stage.
   LAPS_D static int last_base(int u) {
     constexpr int s = G::NSTAGE - 1;
-    if (G::RLAST == 8) {
+    if constexpr (G::RLAST == 8) {
       int base = 0;
       LAPS_UNROLL
       for (int t = 0; t < s; ++t) base += ((u >> (3 * t)) & 7) * G::w(t);
@@ -192,14 +194,17 @@ struct Fft {
 
   // Output index k held in register slot e of thread u after the last stage.
   LAPS_D static int kout(int u, int e) {
-    if (G::RLAST == 8) return u + e * (N / 8);
-    constexpr int s = G::NSTAGE - 1;
-    constexpr int R = G::RLAST;
-    constexpr int vsm1 = G::v(s - 1);
-    const int qlo = u & (vsm1 - 1);
-    const int h = u / vsm1;
-    const int i = e / R, ee = e % R;
-    return qlo + ((8 / R) * h + i) * vsm1 + ee * (N / R);
+    if constexpr (G::RLAST == 8) {
+      return u + e * (N / 8);
+    } else {
+      constexpr int s = G::NSTAGE - 1;
+      constexpr int R = G::RLAST;
+      constexpr int vsm1 = G::v(s - 1);
+      const int qlo = u & (vsm1 - 1);
+      const int h = u / vsm1;
+      const int i = e / R, ee = e % R;
+      return qlo + ((8 / R) * h + i) * vsm1 + ee * (N / R);
+    }
   }
 
   // Last stage: reads the line, leaves X[kout(u,e)] in r[e].
@@ -220,6 +225,7 @@ struct Fft {
   // All stages after `first` up to and including `last`; every thread of the CTA must call it
   // (it contains the block barriers).  `line` is this thread's line.
   LAPS_D static void finish(cplx (&r)[8], int u, cplx* __restrict__ line, const cplx* __restrict__ tw) {
+    if constexpr (G::NSTAGE == 1) return;
     __syncthreads();
     if constexpr (G::NSTAGE >= 3) { middle<1>(u, line, tw); __syncthreads(); }
     if constexpr (G::NSTAGE >= 4) { middle<2>(u, line, tw); __syncthreads(); }
@@ -229,12 +235,14 @@ struct Fft {
   // which every line is transformed by whole warps of its own, so that lines need not wait for each other.
   template <int NBAR>
   LAPS_D static void finish_g(cplx (&r)[8], int u, cplx* __restrict__ line, const cplx* __restrict__ tw, int bar) {
+    if constexpr (G::NSTAGE == 1) return;
     group_barrier<G::NT, NBAR>(bar);
     if constexpr (G::NSTAGE >= 3) { middle<1>(u, line, tw); group_barrier<G::NT, NBAR>(bar); }
     if constexpr (G::NSTAGE >= 4) { middle<2>(u, line, tw); group_barrier<G::NT, NBAR>(bar); }
     last(r, u, line);
   }
   LAPS_D static void finish_w(cplx (&r)[8], int u, cplx* __restrict__ line, cplx w1, cplx w2) {
+    if constexpr (G::NSTAGE == 1) return;
     __syncthreads();
     if constexpr (G::NSTAGE >= 3) { middle_w<1>(u, line, w1); __syncthreads(); }
     if constexpr (G::NSTAGE >= 4) { middle_w<2>(u, line, w2); __syncthreads(); }

@@ -293,12 +293,10 @@ cudaError_t prepare_kernel(K kernel, size_t smem, int ctas) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
 }
 // planes < 0: the whole slab; otherwise `in` holds the `planes` z planes starting at plane zl0 of the slab
-template <int N>
-int do_fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1, bool prune, int zl0, int planes, bool scoped) {
+template <int N, int TL>
+int do_fwd_x_tl(S* s, const double* in, size_t fstride, int nfields, cplx* W1, bool prune, int zl0, int planes, bool scoped) {
   char name[32]; std::snprintf(name, sizeof(name), "fwd_x%d", nfields);
-  constexpr int TL = tlx(N);
   typedef Tile<N, TL> T;
-  if (s->xy % (2 * TL) != 0) { s->err = "ny must be a multiple of " + std::to_string(2 * TL); return 1; }
   LAPS_CK(s, prepare_kernel(k_fwd_x<N, TL>, T::SMEM, T::MINB));
   const int np = planes < 0 ? s->xz : planes;
   dim3 grid((unsigned)(np * (s->xy / (2 * TL))), (unsigned)nfields);
@@ -312,6 +310,17 @@ int do_fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1, bool
                 1.0 / N, prune ? s->nkx : s->nxh, zl0);
   }
   return check_launch(s, "k_fwd_x");
+}
+// A CTA of the x passes takes 2 TL real lines of one plane; planes with fewer lines than the default tile (a 2D grid
+// with ny = 8) use the half-height tile.
+template <int N>
+int do_fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1, bool prune, int zl0, int planes, bool scoped) {
+  constexpr int TL = tlx(N);
+  if (s->xy % (2 * TL) == 0) return do_fwd_x_tl<N, TL>(s, in, fstride, nfields, W1, prune, zl0, planes, scoped);
+  if constexpr (TL == 8) {
+    if (s->xy % 8 == 0) return do_fwd_x_tl<N, 4>(s, in, fstride, nfields, W1, prune, zl0, planes, scoped);
+  }
+  s->err = "ny must be a multiple of " + std::to_string(TL == 8 ? 8 : 2 * TL); return 1;
 }
 
 constexpr int kFuseGroups = 10;   // thread groups (fluxes in flight) per CTA of k_flux_fwd_x: 19 fluxes in two rounds
@@ -358,10 +367,9 @@ int do_inv_y(S* s, const cplx* V1, cplx* V2, int nfields, bool prune) {
   return check_launch(s, "k_inv_y");
 }
 
-template <int N>
-int do_inv_x(S* s, const cplx* V2, const RealDst& dst, int nfields, bool prune) {
+template <int N, int TL>
+int do_inv_x_tl(S* s, const cplx* V2, const RealDst& dst, int nfields, bool prune) {
   char name[32]; std::snprintf(name, sizeof(name), "inv_x%d", nfields);
-  constexpr int TL = tlx(N);
   typedef Tile<N, TL> T;
   LAPS_CK(s, prepare_kernel(k_inv_x<N, TL>, T::SMEM, T::MINB));
   LaunchScope ls(s, name);
@@ -369,6 +377,15 @@ int do_inv_x(S* s, const cplx* V2, const RealDst& dst, int nfields, bool prune) 
   LAPS_LAUNCH((k_inv_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, V2, dst, s->xz, s->xy, s->tw_x,
               prune ? s->nkx : s->nxh);
   return check_launch(s, "k_inv_x");
+}
+template <int N>
+int do_inv_x(S* s, const cplx* V2, const RealDst& dst, int nfields, bool prune) {
+  constexpr int TL = tlx(N);
+  if (s->xy % (2 * TL) == 0) return do_inv_x_tl<N, TL>(s, V2, dst, nfields, prune);
+  if constexpr (TL == 8) {
+    if (s->xy % 8 == 0) return do_inv_x_tl<N, 4>(s, V2, dst, nfields, prune);
+  }
+  s->err = "ny must be a multiple of " + std::to_string(TL == 8 ? 8 : 2 * TL); return 1;
 }
 
 template <int N, int CG>
@@ -438,6 +455,22 @@ int do_incomp_z(S* s, const ZParams& zp) {
     default: s->err = "unsupported line length"; return 1;          \
   }
 
+// The line axis of the fused spectral pass (nz; ny in the 2D trees) may also be 8 points long — one register-resident
+// radix-8 stage, one thread per line (the 2D input the reference ships is 256 x 8, src_compressible/2D/mhd.input:12-13).
+#define LAPS_DISPATCH_Z(n, fn, ...)                                 \
+  switch (n) {                                                      \
+    case 8: return fn<8>(__VA_ARGS__);                              \
+    case 16: return fn<16>(__VA_ARGS__);                            \
+    case 32: return fn<32>(__VA_ARGS__);                            \
+    case 64: return fn<64>(__VA_ARGS__);                            \
+    case 128: return fn<128>(__VA_ARGS__);                          \
+    case 256: return fn<256>(__VA_ARGS__);                          \
+    case 512: return fn<512>(__VA_ARGS__);                          \
+    case 1024: return fn<1024>(__VA_ARGS__);                        \
+    case 2048: return fn<2048>(__VA_ARGS__);                        \
+    default: s->err = "unsupported line length"; return 1;          \
+  }
+
 int fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1, bool prune, int zl0 = 0, int planes = -1, bool scoped = true) {
   LAPS_DISPATCH(s->nx, do_fwd_x, s, in, fstride, nfields, W1, prune, zl0, planes, scoped)
 }
@@ -459,9 +492,9 @@ int forward_xy(S* s, const double* in, size_t fstride, int nfields, bool prune) 
   return fwd_y(s, (const cplx*)s->bufY, nfields, prune);
 }
 int inv_x(S* s, const cplx* V2, const RealDst& dst, int nfields, bool prune) { LAPS_DISPATCH(s->nx, do_inv_x, s, V2, dst, nfields, prune) }
-int spec_z(S* s, const ZParams& zp, int ntasks, const char* name) { LAPS_DISPATCH(s->nz, do_spec_z, s, zp, ntasks, name) }
-int rhs_z(S* s, const ZParams& zp, int ntasks) { LAPS_DISPATCH(s->nz, do_rhs_z, s, zp, ntasks) }
-int incomp_z(S* s, const ZParams& zp) { LAPS_DISPATCH(s->nz, do_incomp_z, s, zp) }
+int spec_z(S* s, const ZParams& zp, int ntasks, const char* name) { LAPS_DISPATCH_Z(s->nz, do_spec_z, s, zp, ntasks, name) }
+int rhs_z(S* s, const ZParams& zp, int ntasks) { LAPS_DISPATCH_Z(s->nz, do_rhs_z, s, zp, ntasks) }
+int incomp_z(S* s, const ZParams& zp) { LAPS_DISPATCH_Z(s->nz, do_incomp_z, s, zp) }
 
 // buffers (see the memory plan in DESIGN.md)
 double* buf_F(S* s) { return (double*)s->bufX; }
@@ -874,12 +907,12 @@ int laps_create(const laps_params* params, laps_handle* out) {
     if (u.nz != 1) { g_create_error = "ndim = 2 needs nz = 1"; return 1; }
     if (u.nranks != 1) { g_create_error = "the 2D tree runs on one GPU (nranks = 1)"; return 1; }
     if (u.if_AEB && u.if_corotating) { g_create_error = "if_corotating is not supported in the 2D tree"; return 1; }
-    if (!size_supported(u.nx) || !size_supported(u.ny)) { g_create_error = "nx, ny must be powers of two in [16, 2048]"; return 1; }
+    if (!size_supported(u.nx) || !(size_supported(u.ny) || u.ny == 8)) { g_create_error = "nx must be a power of two in [16, 2048], ny in [8, 2048]"; return 1; }
     p.ny = 1; p.nz = u.ny; p.Ly = 1.0; p.Lz = u.Ly; p.afz = u.afy; p.if_corotating = 0;
     if (u.dealias_option < 0 || u.dealias_option > 3) { g_create_error = "dealias_option must be 0..3 in the 2D tree"; return 1; }
   } else {
-    if (!size_supported(p.nx) || !size_supported(p.ny) || !size_supported(p.nz)) {
-      g_create_error = "nx, ny, nz must be powers of two in [16, 2048]"; return 1;
+    if (!size_supported(p.nx) || !size_supported(p.ny) || !(size_supported(p.nz) || p.nz == 8)) {
+      g_create_error = "nx, ny must be powers of two in [16, 2048], nz in [8, 2048]"; return 1;
     }
     if (p.dealias_option < 0 || p.dealias_option > 2) { g_create_error = "dealias_option must be 0, 1 or 2"; return 1; }
     p.if_z_radial = 0; p.if_limit_dt_increase = 0;

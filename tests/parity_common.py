@@ -254,6 +254,30 @@ def check_external_force(shape=(64, 32), lib_path=None, nsteps=3, tol=1e-11):
         Solver(lib_path, nx=16, ny=16, nz=16, if_external_force=1)
 
 
+def check_eight_point_lines(lib_path=None):
+    """The line axis of the fused spectral pass may be 8 points long (one register-resident radix-8 stage): the 2D
+    input the reference ships is 256 x 8 (src_compressible/2D/mhd.input:12-13), which also needs the half-height
+    x-pass tile.  All four trees, two steps, against the oracle."""
+    cases = [(make_case_2d, (256, 8), dict(hall=True, aeb=True, dealias=1)),
+             (make_case_2d, (64, 8), dict(hall=True, aeb=True, z_radial=True, dealias=3)),
+             (make_case_2d, (32, 8), dict(hall=False, aeb=False, dealias=2, explicit=True, conserve_bg=True, limit_dt=True)),
+             (make_case_incompressible_2d, (32, 8), dict(hall=True, aeb=True, dealias=1)),
+             (make_case, (16, 16, 8), dict(hall=True, aeb=True, dealias=1, nmode=1)),
+             (make_case_incompressible, (16, 16, 8), dict(hall=True, aeb=True, dealias=2, nmode=1))]
+    for make, shape, kw in cases:
+        p, prim = make(*shape, **kw)
+        o, g = run_both(p, prim, 2, lib_path=lib_path)
+        check_state(o, g, 1e-11)
+        check_diagnostics(o, g, 1e-9)
+        g.close()
+    import pytest
+    from laps_b200 import capi
+    with pytest.raises(capi.LapsError):      # only the line axis of the spectral pass: nx = 8 and a 3D ny = 8 are refused
+        Solver(lib_path, nx=8, ny=16, nz=16)
+    with pytest.raises(capi.LapsError):
+        Solver(lib_path, nx=16, ny=8, nz=16)
+
+
 def check_nan_detection(lib_path=None):
     """checkNan (2D/mhd.f90:563-591): clean state -> 0; one NaN anywhere in uu -> 1."""
     p, prim = make_case_2d(32, 16, hall=False, aeb=False, dealias=2)

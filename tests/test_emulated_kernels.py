@@ -49,6 +49,10 @@ def test_external_force_2d_tree(emu):
     pc.check_external_force((32, 16), lib_path=emu)
 
 
+def test_eight_point_lines(emu):
+    pc.check_eight_point_lines(lib_path=emu)
+
+
 def test_check_nan(emu):
     pc.check_nan_detection(lib_path=emu)
 

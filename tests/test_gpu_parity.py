@@ -264,3 +264,7 @@ def test_2d_tree_external_force():
 
 def test_check_nan():
     pc.check_nan_detection()
+
+
+def test_eight_point_lines():
+    pc.check_eight_point_lines()

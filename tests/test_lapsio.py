@@ -258,3 +258,26 @@ def test_driver_external_force_and_checknan_on_the_emulator(emu, tmp_path):
         assert pc.rel_l2(uu[v], o.uu[v]) < 1e-11 or np.abs(uu[v] - o.uu[v]).max() < 1e-13, v
     assert np.abs(o.uu[6]).max() > 1e-3          # the forcing has built up a B_z
     d.solver.close()
+
+
+def test_driver_runs_the_shipped_2d_input_grid(emu, tmp_path):
+    """&grid of the input the reference ships for the 2D compressible tree: nx = 256, ny = 8
+    (src_compressible/2D/mhd.input:12-13) — an 8-point line axis and the half-height x-pass tile."""
+    text = (INPUT.replace("ipert = 7", "ipert = 1").replace("Bx0 = 1.", "Bx0 = 1.\n   wave_number_jet = 2")
+            .replace("nx = 16", "nx = 256").replace("ny = 16", "ny = 8"))
+    assert "nx = 256" in text and "ny = 8" in text
+    (tmp_path / "mhd.input").write_text(text)
+    d = Driver(str(tmp_path / "mhd.input"), str(tmp_path), lib_path=emu, tree="compressible2d")
+    prim0 = d.initial_primitive()
+    assert prim0.shape == (8, 1, 8, 256)
+    assert d.run(max_steps=2, echo=False) == 2
+    kw = {k: v for k, v in d.kw.items() if k not in ("rank", "nranks", "device", "ndim", "incompressible")}
+    o = lo.State2D(lo.Params(**kw))
+    o.set_primitive(prim0)
+    o.vardt()
+    for _ in range(2):
+        o.step(calc_dt=False)
+    uu, _ = d.solver.get_state()
+    for v in range(8):
+        assert pc.rel_l2(uu[v], o.uu[v]) < 1e-11 or np.abs(uu[v] - o.uu[v]).max() < 1e-13, v
+    d.solver.close()
