@@ -51,8 +51,9 @@ def params_from_namelists(nl, rank=0, nranks=1, device=0, tree="compressible"):
                          if_external_force=bool(g("pert", "if_external_force", False)))   # 2D/mhd.f90:43
     if tree.startswith("incompressible"):
         extra.update(incompressible=1, rho0=1.0)
-    if int(g("prl", "ndim_parallel", 1)) != 1 and nranks > 1:
-        raise ValueError("only the slab decomposition (ndim_parallel = 1) is supported on more than one rank")
+    # &prl ndim_parallel (parallel.f90:56-70): the shipped 3D inputs ask for pencils (ndim_parallel = 2).  The library
+    # decomposes in slabs whatever the namelist says — results and outNNN.dat files do not depend on the decomposition,
+    # and parallel_info.dat records what was used (npe, iproc = 1, jproc = npe).
     return dict(
         nx=int(g("grid", "nx", 128)), ny=int(g("grid", "ny", 128)), nz=1 if tree.endswith("2d") else int(g("grid", "nz", 64)),
         Lx=float(g("grid", "Lx", 1.0)), Ly=float(g("grid", "Ly", 1.0)), Lz=float(g("grid", "Lz", 1.0)),

@@ -281,3 +281,25 @@ def test_driver_runs_the_shipped_2d_input_grid(emu, tmp_path):
     for v in range(8):
         assert pc.rel_l2(uu[v], o.uu[v]) < 1e-11 or np.abs(uu[v] - o.uu[v]).max() < 1e-13, v
     d.solver.close()
+
+
+@pytest.mark.parametrize("path,tree", [("src_compressible/mhd.input", "compressible"), ("src_compressible/2D/mhd.input", "compressible2d"),
+                                       ("src_incompressible/mhd.input", "incompressible"), ("src_incompressible/2D/mhd.input", "incompressible2d")])
+def test_the_four_shipped_inputs_are_accepted(emu, path, tree):
+    """The mhd.input files the reference ships (read where they lie; skipped where /root/reference does not exist):
+    the parser takes their syntax (one has a stray '/' line), and laps_create accepts their physics switches — on the
+    shipped grid where the emulator can hold it (256 x 8), else on a 16-point grid."""
+    full = os.path.join("/root/reference", path)
+    if not os.path.exists(full):
+        pytest.skip("/root/reference absent")
+    nl = lapsio.read_namelists(full)
+    kw = params_from_namelists(nl, 0, 1, 0, tree)
+    shipped = {"compressible": (512, 512, 512), "compressible2d": (256, 8, 1), "incompressible": (512, 512, 512),
+               "incompressible2d": (256, 1024, 1)}[tree]
+    assert (kw["nx"], kw["ny"], kw["nz"]) == shipped
+    assert kw["dealias_option"] == 1
+    if tree != "compressible2d":
+        kw.update(nx=16, ny=16, nz=1 if tree.endswith("2d") else 16)
+    from laps_b200 import Solver
+    with Solver(emu, **kw) as g:
+        assert (g.nx, g.ny) == (kw["nx"], kw["ny"])
