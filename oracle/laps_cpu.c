@@ -11,8 +11,9 @@
  * gather/scatter (fftw.f90:42-103,136-222; mhdrhs.f90:128-172), separate pointwise sweeps for calc_flux
  * (mhdrhs.f90:21-124), calc_rhs (:174-279), rkt (rktmod.f90:34-62), dealias (dealiasing.f90:70-112),
  * update_uu_prim_from_uu (mhdrhs.f90:282-294), vardt (mhd.f90:328-429).  OpenMP threads stand in for the MPI
- * ranks (the transposes of parallel.f90 are then plain strided access).  FFTW is replaced by a radix-2
- * transform written here (power-of-two sizes only).
+ * ranks (the transposes of parallel.f90 are then plain strided access).  FFTW is replaced by transforms written
+ * here (power-of-two sizes only): radix-2 passes taken two at a time, real lines through a half-length complex
+ * transform as FFTW's r2c/c2r plans do.
  *
  * Arrays are C order a[v][iz][iy][ix] = Fortran a(ix,iy,iz,v); spectra [v][kz][ky][kx], kx = 0..nx/2.
  */
@@ -52,24 +53,65 @@ typedef struct {
 static const double kPi = 3.141592653589793;   /* mhdinit.f90:7 */
 
 /* ------------------------------------------------------------------ 1-D transforms (stand-in for FFTW) */
-static void fft_inplace(cplx* a, int n, const cplx* tw, int dir) {   /* dir = -1 forward, +1 backward, unnormalised */
-  for (int i = 1, j = 0; i < n; ++i) {             /* bit reversal */
-    int bit = n >> 1;
+/* In-place complex transform of m points, m a power of two: bit reversal, then the radix-2 passes taken two at a
+ * time (one radix-4 style sweep over the line per pair).  tw = exp(-2 pi i q / ntab), q < ntab, ntab a multiple of m.
+ * dir = -1 forward, +1 backward, unnormalised. */
+static void fft_inplace(cplx* a, int m, const cplx* tw, int ntab, int dir) {
+  for (int i = 1, j = 0; i < m; ++i) {             /* bit reversal */
+    int bit = m >> 1;
     for (; j & bit; bit >>= 1) j ^= bit;
     j ^= bit;
     if (i < j) { cplx t = a[i]; a[i] = a[j]; a[j] = t; }
   }
-  for (int len = 2; len <= n; len <<= 1) {
-    const int half = len >> 1, step = n / len;
-    for (int i = 0; i < n; i += len)
-      for (int k = 0; k < half; ++k) {
-        cplx w = tw[k * step];
-        if (dir > 0) w = conj(w);
-        const cplx u = a[i + k], v = a[i + k + half] * w;
-        a[i + k] = u + v;
-        a[i + k + half] = u - v;
+  int h = 1, lg = 0;
+  while ((1 << lg) < m) ++lg;
+  if (lg & 1) {                                    /* odd number of passes: the first one (twiddle 1) on its own */
+    for (int i = 0; i < m; i += 2) { const cplx u = a[i], v = a[i + 1]; a[i] = u + v; a[i + 1] = u - v; }
+    h = 2;
+  }
+  const cplx rot = dir < 0 ? -I : I;               /* exp(dir * i pi / 2) */
+  for (; h < m; h <<= 2) {                         /* passes of half-length h and 2h together */
+    const int s1 = ntab / (2 * h), s2 = ntab / (4 * h);
+    for (int i = 0; i < m; i += 4 * h)
+      for (int k = 0; k < h; ++k) {
+        cplx w1 = tw[k * s1], w2 = tw[k * s2];
+        if (dir > 0) { w1 = conj(w1); w2 = conj(w2); }
+        const cplx w3 = w2 * rot;
+        cplx* q = a + i + k;
+        const cplx t1 = q[h] * w1, t3 = q[3 * h] * w1;
+        const cplx a0 = q[0] + t1, a1 = q[0] - t1, a2 = q[2 * h] + t3, a3 = q[2 * h] - t3;
+        const cplx u2 = a2 * w2, u3 = a3 * w3;
+        q[0] = a0 + u2; q[2 * h] = a0 - u2; q[h] = a1 + u3; q[3 * h] = a1 - u3;
       }
   }
+}
+
+/* r2c of n real points through one complex transform of n/2 points (what FFTW's r2c plans do as well):
+ * out[k], k = 0..n/2, unnormalised.  work: n/2 complex. */
+static void rfft_line(const double* x, int n, const cplx* tw, cplx* work, cplx* out) {
+  const int m = n / 2;
+  for (int j = 0; j < m; ++j) work[j] = x[2 * j] + I * x[2 * j + 1];
+  fft_inplace(work, m, tw, n, -1);
+  out[0] = creal(work[0]) + cimag(work[0]);
+  out[m] = creal(work[0]) - cimag(work[0]);
+  for (int k = 1; k < m; ++k) {
+    const cplx zk = work[k], zc = conj(work[m - k]);
+    out[k] = 0.5 * ((zk + zc) - I * tw[k] * (zk - zc));
+  }
+}
+
+/* c2r (unnormalised backward) of the half spectrum in[0..n/2] to n real points; like FFTW the imaginary parts of
+ * the DC and Nyquist bins are ignored.  work: n/2 complex. */
+static void irfft_line(const cplx* in, int n, const cplx* tw, cplx* work, double* x) {
+  const int m = n / 2;
+  const double x0 = creal(in[0]), xm = creal(in[m]);
+  work[0] = (x0 + xm) + I * (x0 - xm);
+  for (int k = 1; k < m; ++k) {
+    const cplx xk = in[k], xc = conj(in[m - k]);
+    work[k] = (xk + xc) + I * conj(tw[k]) * (xk - xc);
+  }
+  fft_inplace(work, m, tw, n, +1);
+  for (int j = 0; j < m; ++j) { x[2 * j] = creal(work[j]); x[2 * j + 1] = cimag(work[j]); }
 }
 
 static cplx* twiddles(int n) {
@@ -78,27 +120,31 @@ static cplx* twiddles(int n) {
   return t;
 }
 
+static int maxdim(const cpu_state* s) {
+  const int nx = s->p.nx, ny = s->p.ny, nz = s->p.nz;
+  return nx > ny ? (nx > nz ? nx : nz) : (ny > nz ? ny : nz);
+}
+
 /* fftw.f90:42-71 + 136-180: r2c along x (/nx), c2c along y (/ny), c2c along z (/nz); one field */
 static void forward3d(const cpu_state* s, const double* a, cplx* w) {
   const int nx = s->p.nx, ny = s->p.ny, nz = s->p.nz, nxh = s->nxh;
 #pragma omp parallel
   {
-    cplx* line = (cplx*)malloc(sizeof(cplx) * (size_t)(nx > ny ? (nx > nz ? nx : nz) : (ny > nz ? ny : nz)));
+    cplx* line = (cplx*)malloc(sizeof(cplx) * (size_t)(maxdim(s) + nxh));
+    cplx* half = line + maxdim(s);
 #pragma omp for collapse(2) schedule(static)
     for (int iz = 0; iz < nz; ++iz)
       for (int iy = 0; iy < ny; ++iy) {
-        const double* src = a + ((size_t)iz * ny + iy) * nx;
-        for (int i = 0; i < nx; ++i) line[i] = src[i];
-        fft_inplace(line, nx, s->twx, -1);
+        rfft_line(a + ((size_t)iz * ny + iy) * nx, nx, s->twx, line, half);
         cplx* dst = w + ((size_t)iz * ny + iy) * nxh;
-        for (int k = 0; k < nxh; ++k) dst[k] = line[k] / nx;
+        for (int k = 0; k < nxh; ++k) dst[k] = half[k] / nx;
       }
 #pragma omp for collapse(2) schedule(static)
     for (int iz = 0; iz < nz; ++iz)
       for (int kx = 0; kx < nxh; ++kx) {
         cplx* base = w + (size_t)iz * ny * nxh + kx;
         for (int i = 0; i < ny; ++i) line[i] = base[(size_t)i * nxh];
-        fft_inplace(line, ny, s->twy, -1);
+        fft_inplace(line, ny, s->twy, ny, -1);
         for (int i = 0; i < ny; ++i) base[(size_t)i * nxh] = line[i] / ny;
       }
 #pragma omp for collapse(2) schedule(static)
@@ -106,7 +152,7 @@ static void forward3d(const cpu_state* s, const double* a, cplx* w) {
       for (int kx = 0; kx < nxh; ++kx) {
         cplx* base = w + (size_t)iy * nxh + kx;
         for (int i = 0; i < nz; ++i) line[i] = base[(size_t)i * ny * nxh];
-        fft_inplace(line, nz, s->twz, -1);
+        fft_inplace(line, nz, s->twz, nz, -1);
         for (int i = 0; i < nz; ++i) base[(size_t)i * ny * nxh] = line[i] / nz;
       }
     free(line);
@@ -118,13 +164,13 @@ static void inverse3d(const cpu_state* s, cplx* w, double* a) {
   const int nx = s->p.nx, ny = s->p.ny, nz = s->p.nz, nxh = s->nxh;
 #pragma omp parallel
   {
-    cplx* line = (cplx*)malloc(sizeof(cplx) * (size_t)(nx > ny ? (nx > nz ? nx : nz) : (ny > nz ? ny : nz)));
+    cplx* line = (cplx*)malloc(sizeof(cplx) * (size_t)maxdim(s));
 #pragma omp for collapse(2) schedule(static)
     for (int iy = 0; iy < ny; ++iy)
       for (int kx = 0; kx < nxh; ++kx) {
         cplx* base = w + (size_t)iy * nxh + kx;
         for (int i = 0; i < nz; ++i) line[i] = base[(size_t)i * ny * nxh];
-        fft_inplace(line, nz, s->twz, +1);
+        fft_inplace(line, nz, s->twz, nz, +1);
         for (int i = 0; i < nz; ++i) base[(size_t)i * ny * nxh] = line[i];
       }
 #pragma omp for collapse(2) schedule(static)
@@ -132,21 +178,13 @@ static void inverse3d(const cpu_state* s, cplx* w, double* a) {
       for (int kx = 0; kx < nxh; ++kx) {
         cplx* base = w + (size_t)iz * ny * nxh + kx;
         for (int i = 0; i < ny; ++i) line[i] = base[(size_t)i * nxh];
-        fft_inplace(line, ny, s->twy, +1);
+        fft_inplace(line, ny, s->twy, ny, +1);
         for (int i = 0; i < ny; ++i) base[(size_t)i * nxh] = line[i];
       }
 #pragma omp for collapse(2) schedule(static)
     for (int iz = 0; iz < nz; ++iz)
-      for (int iy = 0; iy < ny; ++iy) {
-        const cplx* src = w + ((size_t)iz * ny + iy) * nxh;
-        /* c2r: Hermitian extension; like FFTW the imaginary parts of the DC and Nyquist bins are ignored */
-        line[0] = creal(src[0]);
-        for (int k = 1; k < nx / 2; ++k) { line[k] = src[k]; line[nx - k] = conj(src[k]); }
-        line[nx / 2] = creal(src[nx / 2]);
-        fft_inplace(line, nx, s->twx, +1);
-        double* dst = a + ((size_t)iz * ny + iy) * nx;
-        for (int i = 0; i < nx; ++i) dst[i] = creal(line[i]);
-      }
+      for (int iy = 0; iy < ny; ++iy)
+        irfft_line(w + ((size_t)iz * ny + iy) * nxh, nx, s->twx, line, a + ((size_t)iz * ny + iy) * nx);
     free(line);
   }
 }
