@@ -112,6 +112,7 @@ def main():
     inv = g.invariants()
     oinv = o.invariants()
     assert abs(inv[0] - oinv[0]) <= 1e-9 * abs(oinv[0])
+    assert g.checkNan() is False          # checkNan's MPI_Allreduce(MAX) over the ranks (2D/mhd.f90:563-591)
     extra = []
     if p.incompressible:   # the divergence diagnostics of the incompressible driver (mhd.f90:620-732)
         dv, odv = g.calc_max_divV(), o.calc_max_divV()
