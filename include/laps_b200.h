@@ -174,6 +174,10 @@ int laps_fft_inverse(laps_handle h, const double* spec_in, int32_t nfields, doub
  * destination rank and the destination linear offset in that rank's [kx][ky_local][z] block.
  * out = int64 pairs (rank, offset), nxh*ny*z_size of them. */
 int laps_transpose_yz_indexmap(laps_handle h, int64_t* out);
+/* The inverse direction, transpose_zy (parallel.f90:300-324), as the z pass realises it: for every element of this
+ * rank's spectral block (order: kx, ky_local, z with z fastest) the rank that owns z and the linear offset in that
+ * rank's [kx][ky][z_local] block.  out = int64 pairs (rank, offset), nxh*y_size*nz of them. */
+int laps_transpose_zy_indexmap(laps_handle h, int64_t* out);
 
 /* Work the passes skip exactly.  With dealias_option 1 (or 3 in 2D) every mode with kx >= *nkx, or with
  * *kymax < ky < ny - *kymax, is zeroed by the mask at the end of every stage (dealiasing.f90:87-99), so

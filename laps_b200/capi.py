@@ -60,7 +60,7 @@ SYMBOLS = [
     "laps_export_peer_blob", "laps_import_peer_blobs", "laps_connect_local",
     "laps_set_primitive", "laps_set_time", "laps_vardt", "laps_rkt_init", "laps_evolve", "laps_step",
     "laps_sync", "laps_get_stream", "laps_max_divb", "laps_rms", "laps_invariants", "laps_get_state", "laps_get_spectral",
-    "laps_fft_forward", "laps_fft_inverse", "laps_transpose_yz_indexmap",
+    "laps_fft_forward", "laps_fft_inverse", "laps_transpose_yz_indexmap", "laps_transpose_zy_indexmap",
     "laps_last_step_ms", "laps_set_profiling", "laps_get_profile", "laps_get_pruning",
     "laps_max_divv", "laps_max_div_real", "laps_get_rho0", "laps_get_field_counts", "laps_get_output", "laps_get_pruning_counts", "laps_set_primitive_modes",
     "laps_check_nan", "laps_set_external_force",
@@ -117,6 +117,7 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.laps_fft_forward.argtypes = [H, dp, C.c_int32, dp]
     lib.laps_fft_inverse.argtypes = [H, dp, C.c_int32, dp]
     lib.laps_transpose_yz_indexmap.argtypes = [H, C.POINTER(C.c_int64)]
+    lib.laps_transpose_zy_indexmap.argtypes = [H, C.POINTER(C.c_int64)]
     lib.laps_last_step_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     lib.laps_get_pruning.argtypes = [H, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.laps_get_field_counts.argtypes = [H, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]

@@ -1730,6 +1730,22 @@ static_assert(sizeof(PeerBlob) <= LAPS_PEER_BLOB_BYTES, "peer blob too large");
 constexpr uint32_t kBlobMagic = 0x4c415053u;  // "LAPS"
 }  // namespace
 
+int laps_transpose_zy_indexmap(laps_handle s, int64_t* out) {
+  if (!s || !out) return 1;
+  // destination of element (kx, ky_local, z) of this rank's inverse-z output, exactly as the z pass stores it
+  size_t i = 0;
+  for (int kx = 0; kx < s->nxh; ++kx)
+    for (int kyl = 0; kyl < s->nyl; ++kyl) {
+      const int ky = s->yo + kyl * s->ystride;
+      for (int z = 0; z < s->nz; ++z, ++i) {
+        const int pq = s->tabV1.owner(z);
+        out[2 * i] = pq;
+        out[2 * i + 1] = ((int64_t)kx * s->ny + ky) * s->tabV1.len[pq] + (z - s->tabV1.off[pq]);
+      }
+    }
+  return 0;
+}
+
 int laps_export_peer_blob(laps_handle s, void* blob) {
   if (!s || !blob) return 1;
   PeerBlob b; std::memset(&b, 0, sizeof(b));

@@ -228,6 +228,11 @@ class Solver:
         self._ck(self._lib.laps_transpose_yz_indexmap(self._h, out.ctypes.data_as(C.POINTER(C.c_int64))))
         return out
 
+    def transpose_zy_indexmap(self) -> np.ndarray:
+        out = np.empty((self.nxh * self.nyl * self.nz, 2), dtype=np.int64)
+        self._ck(self._lib.laps_transpose_zy_indexmap(self._h, out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return out
+
     # ------------------------------------------------------------------ measurement helpers
     def last_step_ms(self):
         ms = C.c_float()

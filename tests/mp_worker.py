@@ -77,6 +77,16 @@ def main():
         assert np.array_equal(m[..., 0], owner[ky])
         assert np.array_equal(m[..., 1], (kx * np.asarray(sizes)[owner[ky]] + (ky - np.asarray(offs)[owner[ky]])) * nz + zo + zl)
 
+    # transpose_zy (parallel.f90:300-324), the inverse direction: element (gx, gy, gz) of w_zxy goes to the owner of gz,
+    # local offset gx + nxh*(gy + ny*(gz - zj_off)) in the reference's w_yxz; this library keeps z fastest:
+    # (gx*ny + gy)*zj_size + (gz - zj_off).
+    m2 = g.transpose_zy_indexmap().reshape(g.nxh, yn, nz, 2)
+    zoffs, zsizes = lo.decompose_1d(nz, world)
+    zowner = np.minimum(np.arange(nz) // (nz // world), world - 1)
+    kx2, kyl2, z2 = np.meshgrid(np.arange(g.nxh), np.arange(yn), np.arange(nz), indexing="ij")
+    assert np.array_equal(m2[..., 0], zowner[z2])
+    assert np.array_equal(m2[..., 1], (kx2 * ny + rows[kyl2]) * np.asarray(zsizes)[zowner[z2]] + (z2 - np.asarray(zoffs)[zowner[z2]]))
+
     # FFT of a position-encoding field (the idea of ipert=999, mhdinit.f90:1021-1030)
     rng = np.random.default_rng(7)
     a = rng.standard_normal((2, nz, ny, nx))

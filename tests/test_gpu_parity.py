@@ -226,6 +226,10 @@ def test_transpose_yz_indexmap_matches_reference_tables():
         kx, ky, z = np.meshgrid(np.arange(g.nxh), np.arange(g.ny), np.arange(g.nzl), indexing="ij")
         assert np.all(m[..., 0] == 0)
         assert np.array_equal(m[..., 1], (kx * g.ny + ky) * g.nz + z)
+        m2 = g.transpose_zy_indexmap().reshape(g.nxh, g.nyl, g.nz, 2)      # the inverse direction (parallel.f90:300-324)
+        kx, ky, z = np.meshgrid(np.arange(g.nxh), np.arange(g.nyl), np.arange(g.nz), indexing="ij")
+        assert np.all(m2[..., 0] == 0)
+        assert np.array_equal(m2[..., 1], (kx * g.ny + ky) * g.nz + z)
 
 
 def test_full_size_properties_512():
