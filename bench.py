@@ -158,7 +158,7 @@ def nvlink_model(prof, live_cols, total_cols, rows, mass, n, nzl, steps, ms_step
         else:
             continue
         per_kernel[k] = {"remote_bytes_per_launch": remote, "avg_launch_ms": tms / cnt,
-                         "egress_GBps": remote / (tms / cnt * 1e-3) / 1e9}
+                         "egress_GBps": remote / (max(tms / cnt, 1e-9) * 1e-3) / 1e9}
     sent = sum(v["remote_bytes_per_launch"] * prof[k][1] for k, v in per_kernel.items()) / steps
     return {"what": "bytes this rank stores into its peers' buffers over NVLink inside the y pass (transpose_yz) and the z passes "
                     "(transpose_zy), per launch, over the launch's own duration (the kernel does its HBM work in the same time)",
@@ -359,17 +359,17 @@ def run_gpu(args):
     except Exception:
         pass
     if top:
-        tot = sum(v[0] for v in prof.values())
+        tot = sum(v[0] for v in prof.values()) or 1e-12
         shares = {k: round(v[0] / tot, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
         name, (tms, cnt) = top
         b = kb(name)
-        avg_ms = tms / cnt
+        avg_ms = max(tms / cnt, 1e-9)
         ach = b / (avg_ms * 1e-3) / 1e9 if b else None
         roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": (ach / peak) if ach else None, "traffic": (traffic or {}).get(name), "traffic_source": traffic_src if (traffic or {}).get(name) else None,
                     "peak_source": peak_src,
                     "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": b,
-                    "per_kernel_GBps": {k: (kb(k) or 0) / (v[0] / v[1] * 1e-3) / 1e9 for k, v in prof.items() if kb(k)},
+                    "per_kernel_GBps": {k: (kb(k) or 0) / (max(v[0] / v[1], 1e-9) * 1e-3) / 1e9 for k, v in prof.items() if kb(k)},
                     "pruning": {"nkx": nkx, "nxh": g.nxh, "kymax": kymax, "ny": n, "nky_local": nkyl, "live_column_fraction": fcol, "live_mode_fraction": fmode,
                                 "what": "columns removed by the dealiasing mask are skipped exactly (bit-identical state)"},
                     "time_share": shares}

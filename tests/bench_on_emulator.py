@@ -1,0 +1,46 @@
+"""Test helper (not a product path): runs bench.py's single-rank measurement code on the CPU kernel emulator by
+stubbing the handful of torch.cuda calls it makes, so that the assembly of the JSON line (metric, roofline, e2e,
+clocks, cpu_baseline, decomposition, ...) is exercised in the GPU-less build container.  The numbers are
+meaningless; tests/test_bench_model.py only checks structure.  Usage: python bench_on_emulator.py <emulator .so> <n>"""
+import importlib.util
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+class _Event:
+    def __init__(self, enable_timing=True):
+        self.t = None
+
+    def record(self, stream=None):
+        self.t = time.perf_counter()
+
+    def elapsed_time(self, other):
+        return (other.t - self.t) * 1e3
+
+
+def main():
+    emu, n = sys.argv[1], int(sys.argv[2])
+    from laps_b200 import capi
+    capi.DEFAULT_LIB = emu
+    _load = capi.load
+    capi.load = lambda path=None: _load(path or emu)
+    torch.cuda.set_device = lambda d: None
+    torch.cuda.synchronize = lambda *a, **k: None
+    torch.cuda.ExternalStream = lambda ptr, device=None: None
+    torch.cuda.Event = _Event
+    torch.Tensor.pin_memory = lambda self: self
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    sys.argv = ["bench.py", "--n", str(n), "--steps", "2", "--warmup", "3", "--cpu-n", "16"]
+    return bench.main()
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -50,3 +50,30 @@ def test_nvlink_model_counts_the_remote_share():
     assert abs(k["fwd_y13"]["egress_GBps"] - 13 * 16 * nzl * 3000 / 2e-3 / 1e9) < 1e-9
     per_step = (13 * 16 * nzl * 3000 * 10 + 11 * 16 * mine * (n - nzl) * 30) / 10
     assert out["egress_bytes_per_step"] == per_step
+
+
+def test_bench_line_is_assembled_on_the_emulator():
+    """bench.py's single-rank measurement code, run on the CPU kernel emulator with the few torch.cuda calls stubbed
+    (tests/bench_on_emulator.py): every key of the driver's contract is present and well-formed.  The numbers are
+    meaningless here; this guards the code that the driver runs once per round on a real B200."""
+    import json
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+    emu = build_emu.build()
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "bench_on_emulator.py"), emu, "16"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "nvlink"):
+        assert k in d, k
+    assert d["metric"] == "grid_point_steps_per_s" and d["dtype"] == "f64" and d["n_gpus"] == 1 and d["steps"] == 2
+    assert d["value"] > 0 and d["gpu_launches"] > 0 and d["vs_baseline"] is None and d["nvlink"] is None
+    assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    assert d["e2e"]["h2d_bytes_per_step"] == 8 * 16 ** 3 * 8 / 2
+    assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic", "kernel"}
+    assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] == "port"
+    assert "workload" in d["config"] and "decompose_1d slabs" in d["config"]["decomposition"]
+    assert d["state_finite"] is True
