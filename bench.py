@@ -345,7 +345,8 @@ def run_gpu(args):
     mass = rows < 8
     kb = lambda k: kernel_bytes(k, R, C, nf, ni, hall, fx, fcol, fmode, mass)  # noqa: E731
     peak, peak_src = peaks()
-    top = max(prof.items(), key=lambda kv: kv[1][0]) if prof else None
+    # the dominant kernel among those that move data (the one-CTA flag kernels have no byte model)
+    top = max((kv for kv in prof.items() if kb(kv[0])), key=lambda kv: kv[1][0], default=None)
     roofline = None
     shares = {}
     # DRAM bytes per launch measured by ncu --set full for this exact configuration (committed capture), or None

@@ -35,10 +35,17 @@ def main():
     torch.cuda.ExternalStream = lambda ptr, device=None: None
     torch.cuda.Event = _Event
     torch.Tensor.pin_memory = lambda self: self
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:      # multi-rank: gloo in place of NCCL, host tensors in place of device ones
+        import torch.distributed as dist
+        _init = dist.init_process_group
+        dist.init_process_group = lambda backend=None, **kw: _init("gloo")
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        _tensor = torch.tensor
+        torch.tensor = lambda *a, **k: _tensor(*a, **{kk: v for kk, v in k.items() if kk != "device"})
     spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
-    sys.argv = ["bench.py", "--n", str(n), "--steps", "2", "--warmup", "3", "--cpu-n", "16"]
+    sys.argv = ["bench.py", "--n", str(n), "--steps", "2", "--warmup", "3", "--cpu-n", "16", "--gpus", os.environ.get("WORLD_SIZE", "1")]
     return bench.main()
 
 

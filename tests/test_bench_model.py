@@ -77,3 +77,35 @@ def test_bench_line_is_assembled_on_the_emulator():
     assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] == "port"
     assert "workload" in d["config"] and "decompose_1d slabs" in d["config"]["decomposition"]
     assert d["state_finite"] is True
+
+
+def test_bench_line_multi_rank_on_the_emulator():
+    """The same with 4 ranks wired through gloo (the helper swaps NCCL for gloo and device tensors for host ones):
+    blob exchange, max over ranks, the round-robin default ownership in config.decomposition, the NVLink section."""
+    import json
+    import socket
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+    emu = build_emu.build()
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    world = 4
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "bench_on_emulator.py"), emu, "16"],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=600) for p in procs]
+    for r, (p, (so, se)) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {r}:\n{se[-3000:]}"
+    assert all(not so.strip() for so, _ in outs[1:]), "only rank 0 prints"
+    d = json.loads(outs[0][0].strip().splitlines()[-1])
+    assert d["n_gpus"] == world and d["scaling"] == "strong" and d["cpu_baseline"] is None
+    assert "y_stride 4" in d["config"]["decomposition"]
+    nv = d["nvlink"]
+    assert set(nv["per_kernel"]) == {"fwd_y13", "spec_z", "curl_b_inv_z"} and nv["egress_bytes_per_step"] > 0
+    assert d["roofline"]["kernel"] != "xchg_barrier" and d["roofline"]["algorithmic_bytes_per_launch"] > 0
