@@ -100,3 +100,14 @@ def test_four_ranks_incompressible_default_ownership(emu):
     # transforms per stage and the projection kernel over the strided rows)
     run_ranks(4, dict(lib=emu, shape=(16, 16, 16), incompressible=True, case=dict(hall=True, aeb=True, dealias=1), steps=1,
                       expect_stride=4))
+
+
+def test_eight_ranks_default_path_whole_z_tiles(emu):
+    # the 8-GPU benchmark situation in small: 64^3 over 8 ranks (8 planes and 8 round-robin rows per rank, i.e. whole
+    # 8-line z tiles in the y passes), Hall + expanding box + spherical mask, two steps through laps_step
+    run_ranks(8, dict(lib=emu, shape=(64, 64, 64), case=dict(hall=True, aeb=True, dealias=1), steps=2, expect_stride=8), timeout=1200)
+
+
+def test_five_ranks_uneven_round_robin_rows(emu):
+    # 64 rows over 5 ranks: 13, 13, 13, 13, 12 round-robin rows; z planes 12, 12, 12, 12, 16 (decompose_1d remainder)
+    run_ranks(5, dict(lib=emu, shape=(32, 64, 32), case=dict(hall=True, aeb=True, dealias=1), steps=2, expect_stride=5), timeout=1200)
