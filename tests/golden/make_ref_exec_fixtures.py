@@ -1,0 +1,177 @@
+#!/usr/bin/env python
+"""Generates tests/golden/ref_exec/*.npz: golden vectors produced by EXECUTING THE REFERENCE'S OWN FORTRAN SOURCE
+(src_compressible/{mhdinit,dealiasing,AEBmod,rktmod,mhdrhs,fftw,parallel,mhd,mhdrms}.f90, read where it lies under
+/root/reference) through the statement-by-statement translator of oracle/fortran_exec.py, on one rank.
+
+Run from the reference's text: grid_initialize, dealias_initialize, AEB_calc / evolve_radius / update_ksquare,
+initial_calc_conserve_variable, transform_uu_real_to_fourier, vardt (+ rkt_init), evolve = 3 x { calc_flux
+(+ calc_current_density_real), transform_flux_real_to_fourier, calc_rhs, rkt, dealias, transform_uu_fourier_to_real,
+update_uu_prim_from_uu }, from_xyz_to_zxy / from_zxy_to_xyz and the single-rank branches of transpose_xy/yx/yz/zy,
+calc_max_divB, calc_rms.  Supplied from outside: the three FFTW executions (numpy.fft on one line — the DFT FFTW
+computes, unnormalised, c2r ignoring the imaginary parts of the DC and Nyquist bins) and mpi_allreduce on one rank.
+
+Run in the build container (needs /root/reference):  python tests/golden/make_ref_exec_fixtures.py
+tests/test_reference_source_pins.py then checks the oracle (CPU) and the library (emulator / GPU) against the stored
+vectors without the reference."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import fortran_exec as fx  # noqa: E402
+
+REF = "/root/reference/src_compressible"
+
+CASES = {
+    # name: (grid, namelist-level switches)
+    "hall_aeb_mask": dict(nx=32, ny=16, nz=8, if_hall=True, if_aeb=True, if_corotating=False, dealias_option=1,
+                          if_resis=True, if_resis_exp=False, if_visc=True, if_visc_exp=False, if_conserve_background=False),
+    "corot_filter_explicit": dict(nx=16, ny=32, nz=8, if_hall=True, if_aeb=True, if_corotating=True, dealias_option=2,
+                                  if_resis=True, if_resis_exp=True, if_visc=True, if_visc_exp=True, if_conserve_background=True),
+}
+
+
+def build_namespace(c):
+    nx, ny, nz = c["nx"], c["ny"], c["nz"]
+    nxh = nx // 2 + 1
+    ns = fx.base_namespace()
+    F = fx.FArray
+
+    def real(*shape):      # C-ordered storage [.., z, y, x] seen by Fortran as (x, y, z, ..)
+        return np.zeros(shape[::-1])
+
+    def cplx(*shape):
+        return np.zeros(shape[::-1], dtype=np.complex128)
+
+    st = dict(uu=real(nx, ny, nz, 8), uu_prim=real(nx, ny, nz, 4), flux=real(nx, ny, nz, 18), expand_term=real(nx, ny, nz, 1),
+              current_density=real(nx, ny, nz, 3), uu_fourier=cplx(nxh, ny, nz, 8), flux_fourier=cplx(nxh, ny, nz, 18),
+              fnl=cplx(nxh, ny, nz, 8), fnl_rk=cplx(nxh, ny, nz, 8), current_density_fourier=cplx(nxh, ny, nz, 3),
+              expand_term_fourier=cplx(nxh, ny, nz, 1), k_square=real(nxh, ny, nz), w_xyz=cplx(nxh, ny, nz),
+              w_yxz=cplx(nxh, ny, nz), w_zxy=cplx(nxh, ny, nz), xgrid=real(nx), ygrid=real(ny), zgrid=real(nz),
+              wave_number_x=real(nx), wave_number_y=real(ny), wave_number_z=real(nz), fx_aux=real(nx), fx_aux_ft=cplx(nxh),
+              fy_aux=cplx(ny), fy_aux_ft=cplx(ny), fz_aux=cplx(nz), fz_aux_ft=cplx(nz), filtx=real(nxh), filty=real(ny),
+              filtz=real(nz), cc1=real(3), dd1=real(3), time_step=real(3), uu_ave=real(8), uu_square_ave=real(8),
+              uu_ave_sum=real(8), uu_square_ave_sum=real(8), uu_rms=real(8), b0_ave=real(8), rho_u2=real(3), rho_u2_sum=real(3))
+    for k, v in st.items():
+        ns[k] = F(v.T)
+    ns["_storage"] = st
+    one = lambda v: F(np.array([v]))  # noqa: E731
+    # parallel_start on one rank (parallel.f90:100-143): offsets 0, sizes = the whole axis
+    ns.update(xi_offset=one(0), xi_size=one(nxh), yi_offset=one(0), yi_size=one(ny), yj_offset=one(0), yj_size=one(ny),
+              zj_offset=one(0), zj_size=one(nz), dims=F(np.array([1, 1])), myid_i=0, myid_j=0, ipe=0, npe=1, ierr=0)
+    # namelist values (mhd.input of SURVEY 8(d)) and module defaults (mhdinit.f90:5-54, dealiasing.f90:9-10, AEBmod.f90:10-12)
+    ns.update(nx=nx, ny=ny, nz=nz, nvar=8, pi=3.141592653589793, lx=24.0, ly=12.0, lz=6.0, dx=0.0, dy=0.0, dz=0.0,
+              adiabatic_index=1.666667, resistivity=1e-3 if c["if_resis_exp"] else 1e-4, viscosity=1e-3 if c["if_visc_exp"] else 1e-4,
+              ion_inertial_length=0.2, cfl=0.5, afx=0.495, afy=0.495, afz=0.495, dealias_circle_radius=1. / 3.,
+              radius0=30.0, radius=30.0, ur0=1.167, ur=0.0, tau_exp=0.0, corotating_angle=0.3 if c["if_corotating"] else 0.0,
+              cos_cor_ang=1.0, sin_cor_ang=0.0, time=0.0, dt=0.0, max_divb=0.0, size_grid=nx * ny * nz,
+              mpi_realtype=None, mpi_sum=None, mpi_min=None, mpi_max=None, mpi_comm_world=None)
+    for k in ("if_hall", "if_aeb", "if_corotating", "dealias_option", "if_resis", "if_resis_exp", "if_visc", "if_visc_exp",
+              "if_conserve_background"):
+        ns[k] = c[k]
+    ns.update(plan_fft_x="r2c", plan_ifft_x="c2r", plan_fft_y=-1, plan_ifft_y=+1, plan_fft_z=-1, plan_ifft_z=+1)
+
+    # ---- the only pieces not taken from the reference's text: FFTW's 1-D executions (fftw.f90:27-33 plans)
+    def fftw_execute_dft_r2c(plan, a, out):
+        out.a[...] = np.fft.rfft(a.a)
+
+    def fftw_execute_dft_c2r(plan, a, out):
+        h = a.a.copy()
+        h[0] = h[0].real
+        h[-1] = h[-1].real                       # FFTW's c2r ignores the imaginary parts of the DC and Nyquist bins
+        out.a[...] = np.fft.irfft(h, n=out.a.size) * out.a.size
+
+    def fftw_execute_dft(plan, a, out):
+        out.a[...] = np.fft.fft(a.a) if plan < 0 else np.fft.ifft(a.a) * a.a.size
+
+    ns.update(fftw_execute_dft_r2c=fftw_execute_dft_r2c, fftw_execute_dft_c2r=fftw_execute_dft_c2r, fftw_execute_dft=fftw_execute_dft)
+    return ns
+
+
+def load_reference(ns):
+    src = {}
+    src.update(fx.load(ns, f"{REF}/parallel.f90", ["transpose_xy", "transpose_yx", "transpose_yz", "transpose_zy"]))
+    src.update(fx.load(ns, f"{REF}/mhdinit.f90", ["grid_initialize", "initial_calc_conserve_variable"]))
+    src.update(fx.load(ns, f"{REF}/dealiasing.f90", ["dealias_initialize", "dealias"]))
+    src.update(fx.load(ns, f"{REF}/AEBmod.f90", ["aeb_calc", "update_ksquare", "evolve_radius"]))
+    src.update(fx.load(ns, f"{REF}/rktmod.f90", ["rkt_init", "rkt"]))
+    src.update(fx.load(ns, f"{REF}/fftw.f90", ["from_xyz_to_zxy", "from_zxy_to_xyz", "transform_uu_real_to_fourier",
+                                               "transform_uu_fourier_to_real"]))
+    src.update(fx.load(ns, f"{REF}/mhdrhs.f90", ["calc_current_density_real", "calc_flux", "transform_flux_real_to_fourier",
+                                                 "calc_rhs", "update_uu_prim_from_uu"]))
+    src.update(fx.load(ns, f"{REF}/mhd.f90", ["evolve", "vardt", "calc_max_divb"]))
+    src.update(fx.load(ns, f"{REF}/mhdrms.f90", ["calc_rms"]))
+    return src
+
+
+def initial_primitive(c, seed=5):
+    """Smooth O(1) primitive fields (rho, u, B, p) with content in every direction, [8, nz, ny, nx]."""
+    import parity_common as pc
+    from oracle import laps_oracle as lo
+    p = lo.Params(nx=c["nx"], ny=c["ny"], nz=c["nz"], Lx=24.0, Ly=12.0, Lz=6.0)
+    prim = lo.ic_uniform_background(p, bx0=1.0, press0=1.0)
+    return lo.ic_turbulence(p, prim, 1.0, 0.0, 0.0, db0=0.1, dv0=0.1, drho0=0.01, nmodex=2, nmodey=2, nmodez=1,
+                            seeds=(seed, seed + 15, seed + 31))
+
+
+def run_case(name, c, nsteps=2):
+    ns = build_namespace(c)
+    load_reference(ns)
+    st = ns["_storage"]
+    out = {}
+    prim = initial_primitive(c)
+    out["prim0"] = prim.copy()
+    # program mhd, mhd.f90:58-136 on one rank
+    ns["grid_initialize"]()
+    ns["dealias_initialize"]()
+    if ns["if_aeb"]:                                   # AEB_initialize (AEBmod.f90:16-30) and mhd.f90:88-90
+        ns["aeb_calc"](ns["radius"])
+        ang = ns["corotating_angle"] if ns["if_corotating"] else 0.0
+        ns["cos_cor_ang"], ns["sin_cor_ang"] = float(np.cos(ang)), float(np.sin(ang))
+    else:
+        ns["ur0"] = 0.0
+    st["uu"][...] = prim
+    ns["initial_calc_conserve_variable"]()             # mhd.f90:121
+    ns["transform_uu_real_to_fourier"]()               # :122
+    out["k_square0"] = st["k_square"].copy()
+    out["wave_numbers"] = np.concatenate([st["wave_number_x"], st["wave_number_y"], st["wave_number_z"]])
+    out["uu_fourier0"] = st["uu_fourier"].copy()
+    ns["vardt"]()                                      # :136
+    out["dt0"] = ns["dt"]
+    dts, times, radii = [], [], []
+    for istep in range(nsteps):
+        if istep == 0:                                 # the pieces of the first stage, from the same text
+            keep = {k: v.copy() for k, v in st.items()}
+            ns["calc_flux"]()
+            out["flux_stage1"] = st["flux"].copy()
+            out["expand_stage1"] = st["expand_term"].copy()
+            out["current_density_stage1"] = st["current_density"].copy()
+            ns["transform_flux_real_to_fourier"]()
+            ns["calc_rhs"]()
+            out["fnl_stage1"] = st["fnl"].copy()
+            for k, v in keep.items():
+                st[k][...] = v
+        ns["evolve"]()                                 # mhd.f90:245
+        ns["time"] = ns["time"] + ns["dt"]             # :246
+        ns["evolve_radius"](ns["time"])                # :248
+        ns["vardt"]()                                  # :285
+        dts.append(ns["dt"]); times.append(ns["time"]); radii.append(ns["radius"])
+    out.update(uu=st["uu"].copy(), uu_prim=st["uu_prim"].copy(), uu_fourier=st["uu_fourier"].copy(), k_square=st["k_square"].copy(),
+               dt=np.array(dts), time=np.array(times), radius=np.array(radii))
+    ns["calc_max_divb"]()
+    ns["calc_rms"]()
+    out.update(max_divb=ns["max_divb"], uu_ave=st["uu_ave"].copy(), uu_rms=st["uu_rms"].copy(), rho_u2=st["rho_u2"].copy())
+    out["switches"] = np.array([c[k] for k in sorted(c)], dtype=np.float64)
+    out["switch_names"] = np.array(sorted(c))
+    os.makedirs(os.path.join(HERE, "ref_exec"), exist_ok=True)
+    np.savez_compressed(os.path.join(HERE, "ref_exec", name + ".npz"), **out)
+    print(name, "dt", dts, "max_divB", ns["max_divb"])
+
+
+if __name__ == "__main__":
+    for name, c in CASES.items():
+        run_case(name, c)

@@ -272,3 +272,11 @@ def test_check_nan():
 
 def test_eight_point_lines():
     pc.check_eight_point_lines()
+
+
+@pytest.mark.parametrize("name", ["hall_aeb_mask", "corot_filter_explicit"])
+def test_library_agrees_with_the_executed_reference_source(name):
+    """Golden vectors made by executing the reference's own Fortran source (tests/golden/make_ref_exec_fixtures.py):
+    two steps of the Principal loop, fields within 1e-11 relative L2."""
+    import test_reference_source_pins as rp
+    rp.check_library(name)

@@ -1,0 +1,111 @@
+"""Golden vectors produced by executing the reference's own Fortran source text (tests/golden/make_ref_exec_fixtures.py
+through oracle/fortran_exec.py: every subroutine of the hot path from src_compressible/*.f90, only FFTW's 1-D
+executions and one-rank mpi_allreduce supplied from outside) pin
+  * the oracle restatement (oracle/laps_oracle.py), stage pieces and whole steps, here on the CPU;
+  * the library on the kernel emulator here, and on the GPU in tests/test_gpu_parity.py."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "emu"))
+import parity_common as pc  # noqa: E402
+from oracle import laps_oracle as lo  # noqa: E402
+
+GOLD = os.path.join(HERE, "golden", "ref_exec")
+CASES = ["hall_aeb_mask", "corot_filter_explicit"]
+
+
+def load_case(name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    sw = {str(k): float(v) for k, v in zip(g["switch_names"], g["switches"])}
+    exp = bool(sw["if_resis_exp"])
+    p = lo.Params(nx=int(sw["nx"]), ny=int(sw["ny"]), nz=int(sw["nz"]), Lx=24.0, Ly=12.0, Lz=6.0, adiabatic_index=1.666667,
+                  if_resis=bool(sw["if_resis"]), if_resis_exp=exp, resistivity=1e-3 if exp else 1e-4,
+                  if_visc=bool(sw["if_visc"]), if_visc_exp=bool(sw["if_visc_exp"]), viscosity=1e-3 if sw["if_visc_exp"] else 1e-4,
+                  if_conserve_background=bool(sw["if_conserve_background"]), cfl=0.5, dealias_option=int(sw["dealias_option"]),
+                  if_AEB=bool(sw["if_aeb"]), radius0=30.0, Ur0=1.167, if_corotating=bool(sw["if_corotating"]),
+                  corotating_angle=0.3 if sw["if_corotating"] else 0.0, if_hall=bool(sw["if_hall"]), ion_inertial_length=0.2)
+    return g, p
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_agrees_with_the_executed_reference_source(name):
+    g, p = load_case(name)
+    o = lo.State(p)
+    # grid_initialize (mhdinit.f90:58-124): wave numbers with the Nyquist kept positive, k_square
+    assert np.array_equal(g["wave_numbers"], np.concatenate([o.g.wnx, o.g.wny, o.g.wnz]))
+    assert np.allclose(g["k_square0"], np.broadcast_to(o.k_square, g["k_square0"].shape), rtol=1e-15, atol=0)
+    # initial_calc_conserve_variable + transform_uu_real_to_fourier (mhd.f90:121-122)
+    o.set_primitive(g["prim0"])
+    assert pc.rel_l2(o.uu_fourier, g["uu_fourier0"]) < 1e-14
+    # vardt (mhd.f90:328-429)
+    o.vardt()
+    assert abs(o.dt - float(g["dt0"])) <= 1e-14 * o.dt
+    # the pieces of the first stage: calc_current_density_real, calc_flux, transforms, calc_rhs
+    flux, expand = o.calc_flux()
+    assert pc.rel_l2(flux, g["flux_stage1"]) < 1e-14
+    assert pc.rel_l2(o.current_density, g["current_density_stage1"]) < 1e-13
+    assert pc.rel_l2(expand, g["expand_stage1"][0]) < 1e-14
+    fnl = o.calc_rhs(lo.fft_forward(flux), lo.fft_forward(expand))
+    for v in range(8):
+        assert pc.rel_l2(fnl[v], g["fnl_stage1"][v]) < 1e-13, v
+    # two whole steps of the Principal loop (mhd.f90:244-248,285)
+    for i in range(len(g["dt"])):
+        o.step()
+        assert abs(o.dt - g["dt"][i]) <= 1e-13 * o.dt and abs(o.time - g["time"][i]) <= 1e-14 * o.time
+        assert abs(o.radius - g["radius"][i]) <= 1e-15 * o.radius
+    for v in range(8):
+        assert pc.rel_l2(o.uu[v], g["uu"][v]) < 1e-13, (v, pc.rel_l2(o.uu[v], g["uu"][v]))
+        assert pc.rel_l2(o.uu_fourier[v], g["uu_fourier"][v]) < 1e-13, v
+    for v in range(4):
+        assert pc.rel_l2(o.uu_prim[v], g["uu_prim"][v]) < 1e-12, v
+    assert np.allclose(np.broadcast_to(o.k_square, g["k_square"].shape), g["k_square"], rtol=1e-14, atol=0)   # update_ksquare
+    # diagnostics: calc_max_divB (mhd.f90:522-570), calc_rms (mhdrms.f90:53-126)
+    assert abs(o.calc_max_divB() - float(g["max_divb"])) <= 1e-9 * float(g["max_divb"])
+    ave, rms, ru2 = o.calc_rms()
+    assert np.allclose(ave, g["uu_ave"], rtol=1e-13, atol=1e-16)
+    # <u^2> - <u>^2 cancels five digits for B_x (mean 0.88, variance 1e-5): the sequential Fortran sum and NumPy's
+    # pairwise sum differ at 1e-13 before the subtraction
+    assert np.allclose(rms, g["uu_rms"], rtol=1e-7, atol=1e-17)
+    assert np.allclose(ru2, g["rho_u2"], rtol=1e-12, atol=1e-20)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import build_emu
+    return build_emu.build()
+
+
+def check_library(name, lib_path=None, tol=1e-11):
+    """The library, driven like mhd.f90, against the vectors of the executed reference source (north-star tolerances:
+    fields 1e-11 relative L2, diagnostics 1e-9)."""
+    from laps_b200 import Solver
+    g, p = load_case(name)
+    with Solver(lib_path, **pc.solver_kwargs(p)) as s:
+        s.set_primitive(g["prim0"])
+        assert pc.rel_l2(s.uu_fourier(), g["uu_fourier0"]) < 1e-13
+        s.vardt()
+        assert abs(s.dt - float(g["dt0"])) <= 1e-13 * s.dt
+        for i in range(len(g["dt"])):
+            s.step()
+            assert abs(s.dt - g["dt"][i]) <= 1e-12 * s.dt and abs(s.time - g["time"][i]) <= 1e-12 * s.time
+        uu, prim = s.get_state()
+        uf = s.uu_fourier()
+        for v in range(8):
+            assert pc.rel_l2(uu[v], g["uu"][v]) < tol, (v, pc.rel_l2(uu[v], g["uu"][v]))
+            assert pc.rel_l2(uf[v], g["uu_fourier"][v]) < tol, v
+        for v in range(4):
+            assert pc.rel_l2(prim[v], g["uu_prim"][v]) < 10 * tol, v
+        assert abs(s.calc_max_divB() - float(g["max_divb"])) <= 1e-7 * float(g["max_divb"])
+        ave, rms, ru2 = s.calc_rms()
+        assert np.allclose(ave, g["uu_ave"], rtol=1e-9, atol=1e-12)
+        assert np.allclose(rms, g["uu_rms"], rtol=1e-7, atol=1e-15)      # cancellation, see above
+        assert np.allclose(ru2, g["rho_u2"], rtol=1e-9, atol=1e-18)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_library_on_the_emulator_agrees_with_the_executed_reference_source(emu, name):
+    check_library(name, lib_path=emu)
