@@ -24,18 +24,26 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle import fortran_exec as fx  # noqa: E402
 
-REF = "/root/reference/src_compressible"
+REFROOT = "/root/reference"
+REF = REFROOT + "/src_compressible"
 
 CASES = {
-    # name: (grid, namelist-level switches)
+    # name: grid, namelist-level switches (3D compressible tree unless `tree` says otherwise)
     "hall_aeb_mask": dict(nx=32, ny=16, nz=8, if_hall=True, if_aeb=True, if_corotating=False, dealias_option=1,
                           if_resis=True, if_resis_exp=False, if_visc=True, if_visc_exp=False, if_conserve_background=False),
     "corot_filter_explicit": dict(nx=16, ny=32, nz=8, if_hall=True, if_aeb=True, if_corotating=True, dealias_option=2,
                                   if_resis=True, if_resis_exp=True, if_visc=True, if_visc_exp=True, if_conserve_background=True),
 }
+# src_incompressible: pressure projection, J and grad u, update_rho_p
+CASES_INCOMPRESSIBLE = {
+    "incomp_hall_aeb_mask": dict(nx=16, ny=32, nz=8, if_hall=True, if_aeb=True, if_corotating=False, dealias_option=1,
+                                 if_resis=True, if_resis_exp=False, if_visc=True, if_visc_exp=False, if_conserve_background=False),
+    "incomp_corot_filter_explicit": dict(nx=32, ny=16, nz=8, if_hall=True, if_aeb=True, if_corotating=True, dealias_option=2,
+                                         if_resis=True, if_resis_exp=True, if_visc=True, if_visc_exp=True, if_conserve_background=True),
+}
 
 
-def build_namespace(c):
+def build_namespace(c, incompressible=False):
     nx, ny, nz = c["nx"], c["ny"], c["nz"]
     nxh = nx // 2 + 1
     ns = fx.base_namespace()
@@ -56,6 +64,11 @@ def build_namespace(c):
               fy_aux=cplx(ny), fy_aux_ft=cplx(ny), fz_aux=cplx(nz), fz_aux_ft=cplx(nz), filtx=real(nxh), filty=real(ny),
               filtz=real(nz), cc1=real(3), dd1=real(3), time_step=real(3), uu_ave=real(8), uu_square_ave=real(8),
               uu_ave_sum=real(8), uu_square_ave_sum=real(8), uu_rms=real(8), b0_ave=real(8), rho_u2=real(3), rho_u2_sum=real(3))
+    if incompressible:     # src_incompressible/mhdinit.f90:5-6,126-190: nvarPrim = nflux = nfluxPressure = 3
+        st.update(uu_prim=real(nx, ny, nz, 3), flux=real(nx, ny, nz, 3), flux_pressure=real(nx, ny, nz, 3),
+                  grad_velocity=real(nx, ny, nz, 9), divb_arr=real(nx, ny, nz, 1), divv_arr=real(nx, ny, nz, 1),
+                  flux_fourier=cplx(nxh, ny, nz, 3), flux_pressure_fourier=cplx(nxh, ny, nz, 3),
+                  grad_velocity_fourier=cplx(nxh, ny, nz, 9), divb_arr_fourier=cplx(nxh, ny, nz, 1), divv_arr_fourier=cplx(nxh, ny, nz, 1))
     for k, v in st.items():
         ns[k] = F(v.T)
     ns["_storage"] = st
@@ -70,6 +83,8 @@ def build_namespace(c):
               radius0=30.0, radius=30.0, ur0=1.167, ur=0.0, tau_exp=0.0, corotating_angle=0.3 if c["if_corotating"] else 0.0,
               cos_cor_ang=1.0, sin_cor_ang=0.0, time=0.0, dt=0.0, max_divb=0.0, size_grid=nx * ny * nz,
               mpi_realtype=None, mpi_sum=None, mpi_min=None, mpi_max=None, mpi_comm_world=None)
+    if incompressible:
+        ns.update(nvarprim=3, nflux=3, nfluxpressure=3, rho0=1.0, p0=1.0, t0=1.0, max_divv=0.0)
     for k in ("if_hall", "if_aeb", "if_corotating", "dealias_option", "if_resis", "if_resis_exp", "if_visc", "if_visc_exp",
               "if_conserve_background"):
         ns[k] = c[k]
@@ -106,6 +121,89 @@ def load_reference(ns):
     src.update(fx.load(ns, f"{REF}/mhd.f90", ["evolve", "vardt", "calc_max_divb"]))
     src.update(fx.load(ns, f"{REF}/mhdrms.f90", ["calc_rms"]))
     return src
+
+
+def load_reference_incompressible(ns):
+    R = REFROOT + "/src_incompressible"
+    src = {}
+    src.update(fx.load(ns, f"{R}/parallel.f90", ["transpose_xy", "transpose_yx", "transpose_yz", "transpose_zy"]))
+    src.update(fx.load(ns, f"{R}/mhdinit.f90", ["grid_initialize", "initial_calc_conserve_variable"]))
+    src.update(fx.load(ns, f"{R}/dealiasing.f90", ["dealias_initialize", "dealias"]))
+    src.update(fx.load(ns, f"{R}/AEBmod.f90", ["aeb_calc", "update_ksquare", "evolve_radius", "update_rho_p"]))
+    src.update(fx.load(ns, f"{R}/rktmod.f90", ["rkt_init", "rkt"]))
+    src.update(fx.load(ns, f"{R}/fftw.f90", ["from_xyz_to_zxy", "from_zxy_to_xyz", "transform_uu_real_to_fourier",
+                                             "transform_uu_fourier_to_real"]))
+    src.update(fx.load(ns, f"{R}/mhdrhs.f90", ["calc_current_density_real", "calc_gradient_velocity_real", "calc_flux_for_pressure",
+                                               "transform_flux_for_pressure_real_to_fourier", "calc_pressure_fourier", "calc_flux",
+                                               "transform_flux_real_to_fourier", "calc_rhs", "update_uu_prim_from_uu",
+                                               "calc_divb_real", "calc_divv_real"]))
+    src.update(fx.load(ns, f"{R}/mhd.f90", ["evolve", "vardt", "calc_max_divb", "calc_max_divv", "calc_max_divb_real", "calc_max_divv_real"]))
+    return src
+
+
+def run_case_incompressible(name, c, nsteps=2):
+    """src_incompressible/mhd.f90:58-136,260-305 on one rank."""
+    ns = build_namespace(c, incompressible=True)
+    load_reference_incompressible(ns)
+    st = ns["_storage"]
+    out = {}
+    prim = initial_primitive(c, seed=9)
+    out["prim0"] = prim.copy()
+    ns["grid_initialize"]()
+    ns["dealias_initialize"]()
+    if ns["if_aeb"]:
+        ns["aeb_calc"](ns["radius"])
+        ang = ns["corotating_angle"] if ns["if_corotating"] else 0.0
+        ns["cos_cor_ang"], ns["sin_cor_ang"] = float(np.cos(ang)), float(np.sin(ang))
+    else:
+        ns["ur0"] = 0.0
+    st["uu"][...] = prim
+    ns["initial_calc_conserve_variable"]()
+    ns["transform_uu_real_to_fourier"]()
+    out["uu_fourier0"] = st["uu_fourier"].copy()
+    ns["vardt"]()
+    out["dt0"] = ns["dt"]
+    dts, times, radii, rho0s = [], [], [], []
+    for istep in range(nsteps):
+        if istep == 0:                                 # the pieces of the first stage, from the same text
+            keep = {k: v.copy() for k, v in st.items()}
+            ns["transform_uu_real_to_fourier"]()
+            ns["calc_current_density_real"]()
+            ns["calc_gradient_velocity_real"]()
+            out["current_density_stage1"] = st["current_density"].copy()
+            out["grad_velocity_stage1"] = st["grad_velocity"].copy()
+            ns["calc_flux_for_pressure"]()
+            out["flux_pressure_stage1"] = st["flux_pressure"].copy()
+            ns["transform_flux_for_pressure_real_to_fourier"]()
+            ns["calc_pressure_fourier"]()
+            out["pressure_fourier_stage1"] = st["uu_fourier"][7].copy()
+            ns["calc_flux"]()
+            out["flux_stage1"] = st["flux"].copy()
+            ns["transform_flux_real_to_fourier"]()
+            ns["calc_rhs"]()
+            out["fnl_stage1"] = st["fnl"].copy()
+            for k, v in keep.items():
+                st[k][...] = v
+        ns["evolve"]()
+        ns["time"] = ns["time"] + ns["dt"]
+        ns["evolve_radius"](ns["time"])
+        ns["vardt"]()
+        dts.append(ns["dt"]); times.append(ns["time"]); radii.append(ns["radius"]); rho0s.append(ns["rho0"])
+    out.update(uu=st["uu"].copy(), uu_prim=st["uu_prim"].copy(), uu_fourier=st["uu_fourier"].copy(),
+               dt=np.array(dts), time=np.array(times), radius=np.array(radii), rho0=np.array(rho0s), p0=ns["p0"])
+    ns["calc_max_divv"]()
+    ns["calc_max_divb"]()
+    out.update(max_divv=ns["max_divv"], max_divb=ns["max_divb"])
+    ns["calc_divb_real"](); ns["calc_max_divb_real"]()
+    out["max_divb_real"] = ns["max_divb"]
+    ns["calc_divv_real"](); ns["calc_max_divv_real"]()
+    out["max_divv_real"] = ns["max_divv"]
+    # calc_rms is not run in this tree: src_incompressible/mhdrms.f90:74,84 read uu_prim(ix,iy,iz,4) while nvarPrim = 3
+    # (mhdinit.f90:5) — out of bounds, undefined in the reference itself (the translator's bounds check stops there)
+    out["switches"] = np.array([c[k] for k in sorted(c)], dtype=np.float64)
+    out["switch_names"] = np.array(sorted(c))
+    np.savez_compressed(os.path.join(HERE, "ref_exec", name + ".npz"), **out)
+    print(name, "dt", dts, "max_divV", out["max_divv"], "rho0", rho0s)
 
 
 def initial_primitive(c, seed=5):
@@ -175,3 +273,5 @@ def run_case(name, c, nsteps=2):
 if __name__ == "__main__":
     for name, c in CASES.items():
         run_case(name, c)
+    for name, c in CASES_INCOMPRESSIBLE.items():
+        run_case_incompressible(name, c)

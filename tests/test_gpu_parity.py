@@ -280,3 +280,9 @@ def test_library_agrees_with_the_executed_reference_source(name):
     two steps of the Principal loop, fields within 1e-11 relative L2."""
     import test_reference_source_pins as rp
     rp.check_library(name)
+
+
+@pytest.mark.parametrize("name", ["incomp_hall_aeb_mask", "incomp_corot_filter_explicit"])
+def test_incompressible_library_agrees_with_the_executed_reference_source(name):
+    import test_reference_source_pins as rp
+    rp.check_library_incompressible(name)

@@ -16,6 +16,7 @@ from oracle import laps_oracle as lo  # noqa: E402
 
 GOLD = os.path.join(HERE, "golden", "ref_exec")
 CASES = ["hall_aeb_mask", "corot_filter_explicit"]
+CASES_INCOMPRESSIBLE = ["incomp_hall_aeb_mask", "incomp_corot_filter_explicit"]
 
 
 def load_case(name):
@@ -28,6 +29,9 @@ def load_case(name):
                   if_conserve_background=bool(sw["if_conserve_background"]), cfl=0.5, dealias_option=int(sw["dealias_option"]),
                   if_AEB=bool(sw["if_aeb"]), radius0=30.0, Ur0=1.167, if_corotating=bool(sw["if_corotating"]),
                   corotating_angle=0.3 if sw["if_corotating"] else 0.0, if_hall=bool(sw["if_hall"]), ion_inertial_length=0.2)
+    if name.startswith("incomp"):
+        p.incompressible = True
+        p.rho0 = 1.0
     return g, p
 
 
@@ -73,6 +77,73 @@ def test_oracle_agrees_with_the_executed_reference_source(name):
     assert np.allclose(ru2, g["rho_u2"], rtol=1e-12, atol=1e-20)
 
 
+@pytest.mark.parametrize("name", CASES_INCOMPRESSIBLE)
+def test_incompressible_oracle_agrees_with_the_executed_reference_source(name):
+    """src_incompressible: J and grad u, the flux for the pressure, the pressure projection, E, calc_rhs, then two whole
+    steps incl. update_rho_p (rho0 compounds with the radius of the evolve just done)."""
+    g, p = load_case(name)
+    o = lo.StateIncompressible(p)
+    o.set_primitive(g["prim0"])
+    assert pc.rel_l2(o.uu_fourier, g["uu_fourier0"]) < 1e-14
+    o.vardt()
+    assert abs(o.dt - float(g["dt0"])) <= 1e-14 * o.dt
+    # first stage, piece by piece (src_incompressible/mhd.f90:323-350)
+    o.uu_fourier = lo.fft_forward(o.uu)
+    o.calc_current_density_real()
+    o.calc_gradient_velocity_real()
+    assert pc.rel_l2(o.current_density, g["current_density_stage1"]) < 1e-13
+    assert pc.rel_l2(o.grad_velocity, g["grad_velocity_stage1"]) < 1e-13
+    fp = o.calc_flux_for_pressure()
+    assert pc.rel_l2(fp, g["flux_pressure_stage1"]) < 1e-13
+    fpf = lo.fft_forward(fp)
+    o.calc_pressure_fourier(fpf)
+    assert pc.rel_l2(o.uu_fourier[7], g["pressure_fourier_stage1"]) < 1e-12
+    flux = o.calc_flux()
+    assert pc.rel_l2(flux, g["flux_stage1"]) < 1e-13
+    fnl = o.calc_rhs(lo.fft_forward(flux), fpf)
+    for v in range(8):
+        ref = g["fnl_stage1"][v]
+        assert pc.rel_l2(fnl[v], ref) < 1e-12 or np.abs(fnl[v] - ref).max() < 1e-15, v
+    # whole steps
+    o = lo.StateIncompressible(p)
+    o.set_primitive(g["prim0"])
+    o.vardt()
+    for i in range(len(g["dt"])):
+        o.step()
+        assert abs(o.dt - g["dt"][i]) <= 1e-13 * o.dt and abs(o.time - g["time"][i]) <= 1e-14 * o.time
+        assert abs(o.rho0 - g["rho0"][i]) <= 1e-15
+    for v in range(8):
+        assert pc.rel_l2(o.uu[v], g["uu"][v]) < 1e-12, (v, pc.rel_l2(o.uu[v], g["uu"][v]))
+        assert pc.rel_l2(o.uu_fourier[v], g["uu_fourier"][v]) < 1e-12, v
+    for v in range(3):
+        assert pc.rel_l2(o.uu_prim[v], g["uu_prim"][v]) < 1e-12, v
+    assert abs(o.calc_max_divV() - float(g["max_divv"])) <= 1e-9 * float(g["max_divv"])
+    db, dv = o.calc_max_div_real()
+    assert abs(dv - float(g["max_divv_real"])) <= 1e-9 * float(g["max_divv_real"])
+    assert abs(db - float(g["max_divb_real"])) <= 1e-7 * max(float(g["max_divb_real"]), 1e-9)
+
+
+def check_library_incompressible(name, lib_path=None, tol=1e-11):
+    from laps_b200 import Solver
+    g, p = load_case(name)
+    with Solver(lib_path, **pc.solver_kwargs(p)) as s:
+        s.set_primitive(g["prim0"])
+        s.vardt()
+        assert abs(s.dt - float(g["dt0"])) <= 1e-13 * s.dt
+        for i in range(len(g["dt"])):
+            s.step()
+            assert abs(s.dt - g["dt"][i]) <= 1e-12 * s.dt
+            assert abs(s.rho0 - g["rho0"][i]) <= 1e-15
+        uu, prim = s.get_state()
+        uf = s.uu_fourier()
+        for v in range(8):
+            assert pc.rel_l2(uu[v], g["uu"][v]) < tol, (v, pc.rel_l2(uu[v], g["uu"][v]))
+            assert pc.rel_l2(uf[v], g["uu_fourier"][v]) < tol, v
+        assert abs(s.calc_max_divV() - float(g["max_divv"])) <= 1e-7 * float(g["max_divv"])
+        db, dv = s.calc_max_div_real()
+        assert abs(dv - float(g["max_divv_real"])) <= 1e-7 * float(g["max_divv_real"])
+
+
 @pytest.fixture(scope="module")
 def emu():
     import build_emu
@@ -109,3 +180,8 @@ def check_library(name, lib_path=None, tol=1e-11):
 @pytest.mark.parametrize("name", CASES)
 def test_library_on_the_emulator_agrees_with_the_executed_reference_source(emu, name):
     check_library(name, lib_path=emu)
+
+
+@pytest.mark.parametrize("name", CASES_INCOMPRESSIBLE)
+def test_incompressible_library_on_the_emulator_agrees_with_the_executed_reference_source(emu, name):
+    check_library_incompressible(name, lib_path=emu)
