@@ -206,6 +206,96 @@ def run_case_incompressible(name, c, nsteps=2):
     print(name, "dt", dts, "max_divV", out["max_divv"], "rho0", rho0s)
 
 
+# src_compressible/2D: kz = 0, two passes, if_z_radial, square truncation (dealias option 3), if_limit_dt_increase,
+# the user-defined external force
+CASES_2D = {
+    "c2d_hall_aeb_mask": dict(nx=32, ny=16, nz=1, if_hall=True, if_aeb=True, if_corotating=False, dealias_option=1, if_resis=True,
+                              if_resis_exp=False, if_visc=True, if_visc_exp=False, if_conserve_background=False,
+                              if_z_radial=False, if_limit_dt_increase=False, if_external_force=False),
+    "c2d_zradial_square_explicit": dict(nx=16, ny=32, nz=1, if_hall=True, if_aeb=True, if_corotating=False, dealias_option=3,
+                                        if_resis=True, if_resis_exp=True, if_visc=True, if_visc_exp=True, if_conserve_background=True,
+                                        if_z_radial=True, if_limit_dt_increase=True, if_external_force=False),
+    "c2d_external_force_filter": dict(nx=32, ny=32, nz=1, if_hall=True, if_aeb=True, if_corotating=False, dealias_option=2,
+                                      if_resis=True, if_resis_exp=False, if_visc=True, if_visc_exp=False, if_conserve_background=False,
+                                      if_z_radial=False, if_limit_dt_increase=False, if_external_force=True),
+}
+
+
+def initial_primitive_2d(c, seed=3):
+    import parity_common as pc
+    _, prim = pc.make_case_2d(c["nx"], c["ny"], seed=seed)
+    return prim
+
+
+def run_case_2d(name, c, nsteps=3):
+    """src_compressible/2D/mhd.f90 on one rank; vardt is called after every step here (the driver's dstep_calcdt
+    cadence is host logic, not part of the path)."""
+    R = REFROOT + "/src_compressible/2D"
+    nx, ny = c["nx"], c["ny"]
+    nxh = nx // 2 + 1
+    ns = build_namespace(c)
+    st = ns["_storage"]
+    F = fx.FArray
+    extra = dict(w_xy=np.zeros((1, ny, nxh), dtype=np.complex128), w_yx=np.zeros((1, ny, nxh), dtype=np.complex128),
+                 external_force=np.zeros((1, 1, ny, nx)), external_force_fourier=np.zeros((1, 1, ny, nxh), dtype=np.complex128))
+    for k, v in extra.items():
+        st[k] = v
+        ns[k] = F(v.T)
+    ns.update(if_z_radial=c["if_z_radial"], if_limit_dt_increase=c["if_limit_dt_increase"], if_external_force=c["if_external_force"],
+              nextern=1, isnanall=0, iproc=1)
+    fx.load(ns, f"{R}/parallel.f90", ["transpose_xy", "transpose_yx"])
+    fx.load(ns, f"{R}/mhdinit.f90", ["grid_initialize", "initial_calc_conserve_variable"])
+    fx.load(ns, f"{R}/dealiasing.f90", ["dealias_initialize", "dealias"])
+    fx.load(ns, f"{R}/AEBmod.f90", ["aeb_calc", "update_ksquare", "evolve_radius"])
+    fx.load(ns, f"{R}/rktmod.f90", ["rkt_init", "rkt"])
+    fx.load(ns, f"{R}/fftw.f90", ["transform_uu_real_to_fourier", "transform_uu_fourier_to_real"])
+    fx.load(ns, f"{R}/mhdrhs.f90", ["calc_external_force_real", "calc_current_density_real", "calc_flux", "transform_flux_real_to_fourier",
+                                    "calc_rhs", "update_uu_prim_from_uu"])
+    fx.load(ns, f"{R}/mhd.f90", ["evolve", "vardt", "calc_max_divb", "checknan"])
+    fx.load(ns, f"{R}/mhdrms.f90", ["calc_rms"])
+    out = {}
+    prim = initial_primitive_2d(c)
+    out["prim0"] = prim.copy()
+    ns["grid_initialize"]()
+    ns["dealias_initialize"]()
+    ns["aeb_calc"](ns["radius"])
+    st["uu"][...] = prim
+    ns["initial_calc_conserve_variable"]()
+    ns["transform_uu_real_to_fourier"]()
+    out["uu_fourier0"] = st["uu_fourier"].copy()
+    ns["vardt"]()
+    out["dt0"] = ns["dt"]
+    dts, times, forces = [], [], []
+    for istep in range(nsteps):
+        if istep == 0:
+            keep = {k: v.copy() for k, v in st.items()}
+            ns["calc_flux"]()
+            out["flux_stage1"] = st["flux"].copy()
+            out["expand_stage1"] = st["expand_term"].copy()
+            ns["transform_flux_real_to_fourier"]()
+            ns["calc_rhs"]()
+            out["fnl_stage1"] = st["fnl"].copy()
+            for k, v in keep.items():
+                st[k][...] = v
+        ns["evolve"]()
+        forces.append(st["external_force"][0].copy())     # calc_external_force_real ran inside calc_flux with this step's time
+        ns["time"] = ns["time"] + ns["dt"]
+        ns["evolve_radius"](ns["time"])
+        ns["vardt"]()
+        dts.append(ns["dt"]); times.append(ns["time"])
+    out.update(uu=st["uu"].copy(), uu_prim=st["uu_prim"].copy(), uu_fourier=st["uu_fourier"].copy(), k_square=st["k_square"].copy(),
+               dt=np.array(dts), time=np.array(times), external_force=np.array(forces))
+    ns["calc_max_divb"]()
+    ns["calc_rms"]()
+    ns["checknan"]()
+    out.update(max_divb=ns["max_divb"], uu_ave=st["uu_ave"].copy(), uu_rms=st["uu_rms"].copy(), rho_u2=st["rho_u2"].copy(),
+               isnanall=ns["isnanall"])
+    out["switches"] = np.array([c[k] for k in sorted(c)], dtype=np.float64)
+    out["switch_names"] = np.array(sorted(c))
+    np.savez_compressed(os.path.join(HERE, "ref_exec", name + ".npz"), **out)
+    print(name, "dt", dts, "max_divB", ns["max_divb"], "isNanAll", ns["isnanall"])
+
+
 def initial_primitive(c, seed=5):
     """Smooth O(1) primitive fields (rho, u, B, p) with content in every direction, [8, nz, ny, nx]."""
     import parity_common as pc
@@ -275,3 +365,5 @@ if __name__ == "__main__":
         run_case(name, c)
     for name, c in CASES_INCOMPRESSIBLE.items():
         run_case_incompressible(name, c)
+    for name, c in CASES_2D.items():
+        run_case_2d(name, c)

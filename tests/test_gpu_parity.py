@@ -286,3 +286,9 @@ def test_library_agrees_with_the_executed_reference_source(name):
 def test_incompressible_library_agrees_with_the_executed_reference_source(name):
     import test_reference_source_pins as rp
     rp.check_library_incompressible(name)
+
+
+@pytest.mark.parametrize("name", ["c2d_hall_aeb_mask", "c2d_zradial_square_explicit", "c2d_external_force_filter"])
+def test_2d_library_agrees_with_the_executed_reference_source(name):
+    import test_reference_source_pins as rp
+    rp.check_library_2d(name)

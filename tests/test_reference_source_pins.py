@@ -17,6 +17,7 @@ from oracle import laps_oracle as lo  # noqa: E402
 GOLD = os.path.join(HERE, "golden", "ref_exec")
 CASES = ["hall_aeb_mask", "corot_filter_explicit"]
 CASES_INCOMPRESSIBLE = ["incomp_hall_aeb_mask", "incomp_corot_filter_explicit"]
+CASES_2D = ["c2d_hall_aeb_mask", "c2d_zradial_square_explicit", "c2d_external_force_filter"]
 
 
 def load_case(name):
@@ -32,6 +33,11 @@ def load_case(name):
     if name.startswith("incomp"):
         p.incompressible = True
         p.rho0 = 1.0
+    if p.nz == 1:          # the 2D trees (2D/mhd.f90:23,43,44)
+        p.Lz = 1.0
+        p.if_z_radial = bool(sw["if_z_radial"])
+        p.if_limit_dt_increase = bool(sw["if_limit_dt_increase"])
+        p.if_external_force = bool(sw["if_external_force"])
     return g, p
 
 
@@ -144,6 +150,62 @@ def check_library_incompressible(name, lib_path=None, tol=1e-11):
         assert abs(dv - float(g["max_divv_real"])) <= 1e-7 * float(g["max_divv_real"])
 
 
+@pytest.mark.parametrize("name", CASES_2D)
+def test_2d_oracle_agrees_with_the_executed_reference_source(name):
+    """src_compressible/2D: kz = 0, if_z_radial, square truncation, if_limit_dt_increase, the external force."""
+    g, p = load_case(name)
+    o = lo.State2D(p)
+    o.set_primitive(g["prim0"])
+    assert pc.rel_l2(o.uu_fourier, g["uu_fourier0"]) < 1e-14
+    o.vardt()
+    assert abs(o.dt - float(g["dt0"])) <= 1e-14 * o.dt
+    flux, expand = o.calc_flux()
+    # the 2D tree leaves flux(:,:,:,3:...) of the z direction formed as well: compare what both hold
+    assert pc.rel_l2(flux, g["flux_stage1"]) < 1e-14
+    assert pc.rel_l2(expand, g["expand_stage1"][0]) < 1e-14
+    fnl = o.calc_rhs(lo.fft_forward(flux), lo.fft_forward(expand))
+    if p.if_external_force:
+        fnl[6] = fnl[6] + lo.fft_forward(o.calc_external_force_real())
+    for v in range(8):
+        assert pc.rel_l2(fnl[v], g["fnl_stage1"][v]) < 1e-13, v
+    for i in range(len(g["dt"])):
+        if p.if_external_force:     # calc_external_force_real (2D/mhdrhs.f90:480-531) at this step's time
+            assert np.abs(o.calc_external_force_real() - g["external_force"][i]).max() < 1e-15
+        o.step()
+        assert abs(o.dt - g["dt"][i]) <= 1e-13 * o.dt and abs(o.time - g["time"][i]) <= 1e-14 * o.time
+    for v in range(8):
+        assert pc.rel_l2(o.uu[v], g["uu"][v]) < 1e-13, (v, pc.rel_l2(o.uu[v], g["uu"][v]))
+        assert pc.rel_l2(o.uu_fourier[v], g["uu_fourier"][v]) < 1e-13, v
+    assert np.allclose(np.broadcast_to(o.k_square, g["k_square"].shape), g["k_square"], rtol=1e-14, atol=0)
+    assert abs(o.calc_max_divB() - float(g["max_divb"])) <= 1e-9 * float(g["max_divb"])
+    ave, rms, ru2 = o.calc_rms()
+    assert np.allclose(ave, g["uu_ave"], rtol=1e-13, atol=1e-16)
+    assert np.allclose(rms, g["uu_rms"], rtol=1e-7, atol=1e-17)
+    assert np.allclose(ru2, g["rho_u2"], rtol=1e-12, atol=1e-20)
+    assert int(g["isnanall"]) == 0
+
+
+def check_library_2d(name, lib_path=None, tol=1e-11):
+    from laps_b200 import Solver
+    g, p = load_case(name)
+    with Solver(lib_path, **pc.solver_kwargs(p)) as s:
+        s.set_primitive(g["prim0"])
+        s.vardt()
+        assert abs(s.dt - float(g["dt0"])) <= 1e-13 * s.dt
+        for i in range(len(g["dt"])):
+            if p.if_external_force:     # the field the reference's user routine produced for this step
+                s.set_external_force(g["external_force"][i])
+            s.step()
+            assert abs(s.dt - g["dt"][i]) <= 1e-12 * s.dt
+        uu, prim = s.get_state()
+        uf = s.uu_fourier()
+        for v in range(8):
+            assert pc.rel_l2(uu[v], g["uu"][v]) < tol, (v, pc.rel_l2(uu[v], g["uu"][v]))
+            assert pc.rel_l2(uf[v], g["uu_fourier"][v]) < tol, v
+        assert abs(s.calc_max_divB() - float(g["max_divb"])) <= 1e-7 * float(g["max_divb"])
+        assert s.checkNan() is bool(int(g["isnanall"]))
+
+
 @pytest.fixture(scope="module")
 def emu():
     import build_emu
@@ -185,3 +247,8 @@ def test_library_on_the_emulator_agrees_with_the_executed_reference_source(emu, 
 @pytest.mark.parametrize("name", CASES_INCOMPRESSIBLE)
 def test_incompressible_library_on_the_emulator_agrees_with_the_executed_reference_source(emu, name):
     check_library_incompressible(name, lib_path=emu)
+
+
+@pytest.mark.parametrize("name", CASES_2D)
+def test_2d_library_on_the_emulator_agrees_with_the_executed_reference_source(emu, name):
+    check_library_2d(name, lib_path=emu)
