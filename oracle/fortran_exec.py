@@ -190,7 +190,7 @@ class Translator:
         s = s.strip()
         s = re.sub(r"(\d+\.?\d*|\.\d+)d([+-]?\d+)", r"\1e\2", s)              # 1.0d0 -> 1.0e0
         for f, p in ((".and.", " and "), (".or.", " or "), (".not.", " not "), (".true.", " True "), (".false.", " False "),
-                     (".eq.", "=="), (".ne.", "!="), (".gt.", ">"), (".ge.", ">="), (".lt.", "<"), (".le.", "<="), ("/=", "!=")):
+                     (".eqv.", "=="), (".neqv.", "!="), (".eq.", "=="), (".ne.", "!="), (".gt.", ">"), (".ge.", ">="), (".lt.", "<"), (".le.", "<="), ("/=", "!=")):
             s = s.replace(f, p)
         out, i = "", 0
         while i < len(s):

@@ -141,7 +141,7 @@ def load_reference_incompressible(ns):
     return src
 
 
-def run_case_incompressible(name, c, nsteps=2):
+def run_case_incompressible(name, c, nsteps=2, pieces=True):
     """src_incompressible/mhd.f90:58-136,260-305 on one rank."""
     ns = build_namespace(c, incompressible=True)
     load_reference_incompressible(ns)
@@ -165,7 +165,7 @@ def run_case_incompressible(name, c, nsteps=2):
     out["dt0"] = ns["dt"]
     dts, times, radii, rho0s = [], [], [], []
     for istep in range(nsteps):
-        if istep == 0:                                 # the pieces of the first stage, from the same text
+        if istep == 0 and pieces:                      # the pieces of the first stage, from the same text
             keep = {k: v.copy() for k, v in st.items()}
             ns["transform_uu_real_to_fourier"]()
             ns["calc_current_density_real"]()
@@ -227,7 +227,7 @@ def initial_primitive_2d(c, seed=3):
     return prim
 
 
-def run_case_2d(name, c, nsteps=3):
+def run_case_2d(name, c, nsteps=3, pieces=True):
     """src_compressible/2D/mhd.f90 on one rank; vardt is called after every step here (the driver's dstep_calcdt
     cadence is host logic, not part of the path)."""
     R = REFROOT + "/src_compressible/2D"
@@ -267,7 +267,7 @@ def run_case_2d(name, c, nsteps=3):
     out["dt0"] = ns["dt"]
     dts, times, forces = [], [], []
     for istep in range(nsteps):
-        if istep == 0:
+        if istep == 0 and pieces:
             keep = {k: v.copy() for k, v in st.items()}
             ns["calc_flux"]()
             out["flux_stage1"] = st["flux"].copy()
@@ -296,6 +296,75 @@ def run_case_2d(name, c, nsteps=3):
     print(name, "dt", dts, "max_divB", ns["max_divb"], "isNanAll", ns["isnanall"])
 
 
+# src_incompressible/2D
+CASES_INCOMPRESSIBLE_2D = {
+    "i2d_hall_aeb_mask": dict(nx=32, ny=16, nz=1, if_hall=True, if_aeb=True, if_corotating=False, dealias_option=1, if_resis=True,
+                              if_resis_exp=False, if_visc=True, if_visc_exp=False, if_conserve_background=False,
+                              if_z_radial=False, if_limit_dt_increase=False, if_external_force=False),
+    "i2d_square_explicit_limit": dict(nx=16, ny=32, nz=1, if_hall=True, if_aeb=True, if_corotating=False, dealias_option=3,
+                                      if_resis=True, if_resis_exp=True, if_visc=True, if_visc_exp=True, if_conserve_background=True,
+                                      if_z_radial=False, if_limit_dt_increase=True, if_external_force=False),
+}
+
+
+def run_case_incompressible_2d(name, c, nsteps=3):
+    """src_incompressible/2D/mhd.f90 on one rank (vardt after every step, as in run_case_2d)."""
+    R = REFROOT + "/src_incompressible/2D"
+    nx, ny = c["nx"], c["ny"]
+    nxh = nx // 2 + 1
+    ns = build_namespace(c, incompressible=True)
+    st = ns["_storage"]
+    F = fx.FArray
+    extra = dict(w_xy=np.zeros((1, ny, nxh), dtype=np.complex128), w_yx=np.zeros((1, ny, nxh), dtype=np.complex128))
+    for k, v in extra.items():
+        st[k] = v
+        ns[k] = F(v.T)
+    ns.update(if_limit_dt_increase=c["if_limit_dt_increase"], isnanall=0, iproc=1, press0=1.0)   # &field press0 (2D/AEBmod.f90:122)
+    fx.load(ns, f"{R}/parallel.f90", ["transpose_xy", "transpose_yx"])
+    fx.load(ns, f"{R}/mhdinit.f90", ["grid_initialize", "initial_calc_conserve_variable"])
+    fx.load(ns, f"{R}/dealiasing.f90", ["dealias_initialize", "dealias"])
+    fx.load(ns, f"{R}/AEBmod.f90", ["aeb_calc", "update_ksquare", "evolve_radius", "update_rho_p"])
+    fx.load(ns, f"{R}/rktmod.f90", ["rkt_init", "rkt"])
+    fx.load(ns, f"{R}/fftw.f90", ["transform_uu_real_to_fourier", "transform_uu_fourier_to_real"])
+    fx.load(ns, f"{R}/mhdrhs.f90", ["calc_current_density_real", "calc_gradient_velocity_real", "calc_flux_for_pressure",
+                                    "transform_flux_for_pressure_real_to_fourier", "calc_pressure_fourier", "calc_flux",
+                                    "transform_flux_real_to_fourier", "calc_rhs", "update_uu_prim_from_uu", "calc_divb_real", "calc_divv_real"])
+    fx.load(ns, f"{R}/mhd.f90", ["evolve", "vardt", "calc_max_divb", "calc_max_divv", "calc_max_divb_real", "calc_max_divv_real", "checknan"])
+    out = {}
+    prim = initial_primitive_2d(c, seed=11)
+    out["prim0"] = prim.copy()
+    ns["grid_initialize"]()
+    ns["dealias_initialize"]()
+    ns["aeb_calc"](ns["radius"])
+    st["uu"][...] = prim
+    ns["initial_calc_conserve_variable"]()
+    ns["transform_uu_real_to_fourier"]()
+    out["uu_fourier0"] = st["uu_fourier"].copy()
+    ns["vardt"]()
+    out["dt0"] = ns["dt"]
+    dts, times, rho0s = [], [], []
+    for istep in range(nsteps):
+        ns["evolve"]()
+        ns["time"] = ns["time"] + ns["dt"]
+        ns["evolve_radius"](ns["time"])
+        ns["vardt"]()
+        dts.append(ns["dt"]); times.append(ns["time"]); rho0s.append(ns["rho0"])
+    out.update(uu=st["uu"].copy(), uu_prim=st["uu_prim"].copy(), uu_fourier=st["uu_fourier"].copy(),
+               dt=np.array(dts), time=np.array(times), rho0=np.array(rho0s))
+    ns["calc_max_divv"]()
+    out["max_divv"] = ns["max_divv"]
+    ns["calc_divb_real"](); ns["calc_max_divb_real"]()
+    out["max_divb_real"] = ns["max_divb"]
+    ns["calc_divv_real"](); ns["calc_max_divv_real"]()
+    out["max_divv_real"] = ns["max_divv"]
+    ns["checknan"]()
+    out["isnanall"] = ns["isnanall"]
+    out["switches"] = np.array([c[k] for k in sorted(c)], dtype=np.float64)
+    out["switch_names"] = np.array(sorted(c))
+    np.savez_compressed(os.path.join(HERE, "ref_exec", name + ".npz"), **out)
+    print(name, "dt", dts, "max_divV", out["max_divv"], "rho0", rho0s)
+
+
 def initial_primitive(c, seed=5):
     """Smooth O(1) primitive fields (rho, u, B, p) with content in every direction, [8, nz, ny, nx]."""
     import parity_common as pc
@@ -306,7 +375,7 @@ def initial_primitive(c, seed=5):
                             seeds=(seed, seed + 15, seed + 31))
 
 
-def run_case(name, c, nsteps=2):
+def run_case(name, c, nsteps=2, pieces=True):
     ns = build_namespace(c)
     load_reference(ns)
     st = ns["_storage"]
@@ -332,7 +401,7 @@ def run_case(name, c, nsteps=2):
     out["dt0"] = ns["dt"]
     dts, times, radii = [], [], []
     for istep in range(nsteps):
-        if istep == 0:                                 # the pieces of the first stage, from the same text
+        if istep == 0 and pieces:                      # the pieces of the first stage, from the same text
             keep = {k: v.copy() for k, v in st.items()}
             ns["calc_flux"]()
             out["flux_stage1"] = st["flux"].copy()
@@ -361,9 +430,11 @@ def run_case(name, c, nsteps=2):
 
 
 if __name__ == "__main__":
-    for name, c in CASES.items():
-        run_case(name, c)
-    for name, c in CASES_INCOMPRESSIBLE.items():
-        run_case_incompressible(name, c)
-    for name, c in CASES_2D.items():
-        run_case_2d(name, c)
+    for i, (name, c) in enumerate(CASES.items()):
+        run_case(name, c, pieces=(i == 0))
+    for i, (name, c) in enumerate(CASES_INCOMPRESSIBLE.items()):
+        run_case_incompressible(name, c, pieces=(i == 0))
+    for i, (name, c) in enumerate(CASES_2D.items()):
+        run_case_2d(name, c, pieces=(i != 1))          # the external-force case keeps its pieces (fnl(7) += force)
+    for name, c in CASES_INCOMPRESSIBLE_2D.items():
+        run_case_incompressible_2d(name, c)

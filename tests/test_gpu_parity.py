@@ -292,3 +292,9 @@ def test_incompressible_library_agrees_with_the_executed_reference_source(name):
 def test_2d_library_agrees_with_the_executed_reference_source(name):
     import test_reference_source_pins as rp
     rp.check_library_2d(name)
+
+
+@pytest.mark.parametrize("name", ["i2d_hall_aeb_mask", "i2d_square_explicit_limit"])
+def test_incompressible_2d_library_agrees_with_the_executed_reference_source(name):
+    import test_reference_source_pins as rp
+    rp.check_library_incompressible_2d(name)

@@ -17,6 +17,7 @@ from oracle import laps_oracle as lo  # noqa: E402
 GOLD = os.path.join(HERE, "golden", "ref_exec")
 CASES = ["hall_aeb_mask", "corot_filter_explicit"]
 CASES_INCOMPRESSIBLE = ["incomp_hall_aeb_mask", "incomp_corot_filter_explicit"]
+CASES_INCOMPRESSIBLE_2D = ["i2d_hall_aeb_mask", "i2d_square_explicit_limit"]
 CASES_2D = ["c2d_hall_aeb_mask", "c2d_zradial_square_explicit", "c2d_external_force_filter"]
 
 
@@ -30,7 +31,7 @@ def load_case(name):
                   if_conserve_background=bool(sw["if_conserve_background"]), cfl=0.5, dealias_option=int(sw["dealias_option"]),
                   if_AEB=bool(sw["if_aeb"]), radius0=30.0, Ur0=1.167, if_corotating=bool(sw["if_corotating"]),
                   corotating_angle=0.3 if sw["if_corotating"] else 0.0, if_hall=bool(sw["if_hall"]), ion_inertial_length=0.2)
-    if name.startswith("incomp"):
+    if name.startswith("incomp") or name.startswith("i2d"):
         p.incompressible = True
         p.rho0 = 1.0
     if p.nz == 1:          # the 2D trees (2D/mhd.f90:23,43,44)
@@ -54,14 +55,15 @@ def test_oracle_agrees_with_the_executed_reference_source(name):
     # vardt (mhd.f90:328-429)
     o.vardt()
     assert abs(o.dt - float(g["dt0"])) <= 1e-14 * o.dt
-    # the pieces of the first stage: calc_current_density_real, calc_flux, transforms, calc_rhs
-    flux, expand = o.calc_flux()
-    assert pc.rel_l2(flux, g["flux_stage1"]) < 1e-14
-    assert pc.rel_l2(o.current_density, g["current_density_stage1"]) < 1e-13
-    assert pc.rel_l2(expand, g["expand_stage1"][0]) < 1e-14
-    fnl = o.calc_rhs(lo.fft_forward(flux), lo.fft_forward(expand))
-    for v in range(8):
-        assert pc.rel_l2(fnl[v], g["fnl_stage1"][v]) < 1e-13, v
+    # the pieces of the first stage: calc_current_density_real, calc_flux, transforms, calc_rhs (first case only)
+    if "flux_stage1" in g.files:
+        flux, expand = o.calc_flux()
+        assert pc.rel_l2(flux, g["flux_stage1"]) < 1e-14
+        assert pc.rel_l2(o.current_density, g["current_density_stage1"]) < 1e-13
+        assert pc.rel_l2(expand, g["expand_stage1"][0]) < 1e-14
+        fnl = o.calc_rhs(lo.fft_forward(flux), lo.fft_forward(expand))
+        for v in range(8):
+            assert pc.rel_l2(fnl[v], g["fnl_stage1"][v]) < 1e-13, v
     # two whole steps of the Principal loop (mhd.f90:244-248,285)
     for i in range(len(g["dt"])):
         o.step()
@@ -93,23 +95,24 @@ def test_incompressible_oracle_agrees_with_the_executed_reference_source(name):
     assert pc.rel_l2(o.uu_fourier, g["uu_fourier0"]) < 1e-14
     o.vardt()
     assert abs(o.dt - float(g["dt0"])) <= 1e-14 * o.dt
-    # first stage, piece by piece (src_incompressible/mhd.f90:323-350)
-    o.uu_fourier = lo.fft_forward(o.uu)
-    o.calc_current_density_real()
-    o.calc_gradient_velocity_real()
-    assert pc.rel_l2(o.current_density, g["current_density_stage1"]) < 1e-13
-    assert pc.rel_l2(o.grad_velocity, g["grad_velocity_stage1"]) < 1e-13
-    fp = o.calc_flux_for_pressure()
-    assert pc.rel_l2(fp, g["flux_pressure_stage1"]) < 1e-13
-    fpf = lo.fft_forward(fp)
-    o.calc_pressure_fourier(fpf)
-    assert pc.rel_l2(o.uu_fourier[7], g["pressure_fourier_stage1"]) < 1e-12
-    flux = o.calc_flux()
-    assert pc.rel_l2(flux, g["flux_stage1"]) < 1e-13
-    fnl = o.calc_rhs(lo.fft_forward(flux), fpf)
-    for v in range(8):
-        ref = g["fnl_stage1"][v]
-        assert pc.rel_l2(fnl[v], ref) < 1e-12 or np.abs(fnl[v] - ref).max() < 1e-15, v
+    if "fnl_stage1" in g.files:
+        # first stage, piece by piece (src_incompressible/mhd.f90:323-350)
+        o.uu_fourier = lo.fft_forward(o.uu)
+        o.calc_current_density_real()
+        o.calc_gradient_velocity_real()
+        assert pc.rel_l2(o.current_density, g["current_density_stage1"]) < 1e-13
+        assert pc.rel_l2(o.grad_velocity, g["grad_velocity_stage1"]) < 1e-13
+        fp = o.calc_flux_for_pressure()
+        assert pc.rel_l2(fp, g["flux_pressure_stage1"]) < 1e-13
+        fpf = lo.fft_forward(fp)
+        o.calc_pressure_fourier(fpf)
+        assert pc.rel_l2(o.uu_fourier[7], g["pressure_fourier_stage1"]) < 1e-12
+        flux = o.calc_flux()
+        assert pc.rel_l2(flux, g["flux_stage1"]) < 1e-13
+        fnl = o.calc_rhs(lo.fft_forward(flux), fpf)
+        for v in range(8):
+            ref = g["fnl_stage1"][v]
+            assert pc.rel_l2(fnl[v], ref) < 1e-12 or np.abs(fnl[v] - ref).max() < 1e-15, v
     # whole steps
     o = lo.StateIncompressible(p)
     o.set_primitive(g["prim0"])
@@ -159,15 +162,16 @@ def test_2d_oracle_agrees_with_the_executed_reference_source(name):
     assert pc.rel_l2(o.uu_fourier, g["uu_fourier0"]) < 1e-14
     o.vardt()
     assert abs(o.dt - float(g["dt0"])) <= 1e-14 * o.dt
-    flux, expand = o.calc_flux()
-    # the 2D tree leaves flux(:,:,:,3:...) of the z direction formed as well: compare what both hold
-    assert pc.rel_l2(flux, g["flux_stage1"]) < 1e-14
-    assert pc.rel_l2(expand, g["expand_stage1"][0]) < 1e-14
-    fnl = o.calc_rhs(lo.fft_forward(flux), lo.fft_forward(expand))
-    if p.if_external_force:
-        fnl[6] = fnl[6] + lo.fft_forward(o.calc_external_force_real())
-    for v in range(8):
-        assert pc.rel_l2(fnl[v], g["fnl_stage1"][v]) < 1e-13, v
+    if "flux_stage1" in g.files:
+        flux, expand = o.calc_flux()
+        # the 2D tree leaves flux(:,:,:,3:...) of the z direction formed as well: compare what both hold
+        assert pc.rel_l2(flux, g["flux_stage1"]) < 1e-14
+        assert pc.rel_l2(expand, g["expand_stage1"][0]) < 1e-14
+        fnl = o.calc_rhs(lo.fft_forward(flux), lo.fft_forward(expand))
+        if p.if_external_force:
+            fnl[6] = fnl[6] + lo.fft_forward(o.calc_external_force_real())
+        for v in range(8):
+            assert pc.rel_l2(fnl[v], g["fnl_stage1"][v]) < 1e-13, v
     for i in range(len(g["dt"])):
         if p.if_external_force:     # calc_external_force_real (2D/mhdrhs.f90:480-531) at this step's time
             assert np.abs(o.calc_external_force_real() - g["external_force"][i]).max() < 1e-15
@@ -203,6 +207,47 @@ def check_library_2d(name, lib_path=None, tol=1e-11):
             assert pc.rel_l2(uu[v], g["uu"][v]) < tol, (v, pc.rel_l2(uu[v], g["uu"][v]))
             assert pc.rel_l2(uf[v], g["uu_fourier"][v]) < tol, v
         assert abs(s.calc_max_divB() - float(g["max_divb"])) <= 1e-7 * float(g["max_divb"])
+        assert s.checkNan() is bool(int(g["isnanall"]))
+
+
+@pytest.mark.parametrize("name", CASES_INCOMPRESSIBLE_2D)
+def test_incompressible_2d_oracle_agrees_with_the_executed_reference_source(name):
+    g, p = load_case(name)
+    o = lo.StateIncompressible2D(p)
+    o.set_primitive(g["prim0"])
+    assert pc.rel_l2(o.uu_fourier, g["uu_fourier0"]) < 1e-14
+    o.vardt()
+    assert abs(o.dt - float(g["dt0"])) <= 1e-14 * o.dt
+    for i in range(len(g["dt"])):
+        o.step()
+        assert abs(o.dt - g["dt"][i]) <= 1e-13 * o.dt and abs(o.time - g["time"][i]) <= 1e-14 * o.time
+        assert abs(o.rho0 - g["rho0"][i]) <= 1e-15
+    for v in range(8):
+        ref = g["uu"][v]
+        assert pc.rel_l2(o.uu[v], ref) < 1e-12 or np.abs(o.uu[v] - ref).max() < 1e-14, (v, pc.rel_l2(o.uu[v], ref))
+        assert pc.rel_l2(o.uu_fourier[v], g["uu_fourier"][v]) < 1e-12 or np.abs(o.uu_fourier[v] - g["uu_fourier"][v]).max() < 1e-15, v
+    assert abs(o.calc_max_divV() - float(g["max_divv"])) <= 1e-9 * float(g["max_divv"])
+    db, dv = o.calc_max_div_real()
+    assert abs(dv - float(g["max_divv_real"])) <= 1e-9 * float(g["max_divv_real"])
+    assert abs(db - float(g["max_divb_real"])) <= 1e-7 * max(float(g["max_divb_real"]), 1e-9)
+
+
+def check_library_incompressible_2d(name, lib_path=None, tol=1e-11):
+    from laps_b200 import Solver
+    g, p = load_case(name)
+    with Solver(lib_path, **pc.solver_kwargs(p)) as s:
+        s.set_primitive(g["prim0"])
+        s.vardt()
+        assert abs(s.dt - float(g["dt0"])) <= 1e-13 * s.dt
+        for i in range(len(g["dt"])):
+            s.step()
+            assert abs(s.dt - g["dt"][i]) <= 1e-12 * s.dt
+            assert abs(s.rho0 - g["rho0"][i]) <= 1e-15
+        uu, prim = s.get_state()
+        for v in range(8):
+            ref = g["uu"][v]
+            assert pc.rel_l2(uu[v], ref) < tol or np.abs(uu[v] - ref).max() < 1e-13, (v, pc.rel_l2(uu[v], ref))
+        assert abs(s.calc_max_divV() - float(g["max_divv"])) <= 1e-7 * float(g["max_divv"])
         assert s.checkNan() is bool(int(g["isnanall"]))
 
 
@@ -252,3 +297,8 @@ def test_incompressible_library_on_the_emulator_agrees_with_the_executed_referen
 @pytest.mark.parametrize("name", CASES_2D)
 def test_2d_library_on_the_emulator_agrees_with_the_executed_reference_source(emu, name):
     check_library_2d(name, lib_path=emu)
+
+
+@pytest.mark.parametrize("name", CASES_INCOMPRESSIBLE_2D)
+def test_incompressible_2d_library_on_the_emulator_agrees_with_the_executed_reference_source(emu, name):
+    check_library_incompressible_2d(name, lib_path=emu)
