@@ -2,9 +2,9 @@
  *
  * TEST / BASELINE INFRASTRUCTURE ONLY: nothing in the product package links or loads this file.  It is the
  * "port" that bench.py times as the CPU baseline (cpu_baseline, --impl reference) because the reference's own
- * Fortran + MPI + FFTW build cannot be produced in this image.  PARITY UNPINNED in the same sense as
- * oracle/laps_oracle.py (no reference run, no golden vectors); tests/test_cpu_port.py checks it against that
- * NumPy oracle, which carries the analytic pins.
+ * Fortran + MPI + FFTW build cannot be produced in this image.  tests/test_cpu_port.py checks it against the
+ * NumPy oracle (oracle/laps_oracle.py), which is pinned by golden vectors of the reference's own source executed
+ * through oracle/fortran_exec.py and by analytic known answers.
  *
  * It keeps the reference's STRUCTURE (file:line relative to /root/reference/src_compressible/): module-level
  * arrays (mhdinit.f90:141-178), one field at a time through line-at-a-time 1-D transforms with strided

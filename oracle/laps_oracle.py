@@ -6,13 +6,19 @@ module; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-base
 This is a NumPy/SciPy FP64 restatement of the reference algorithm, function by function.
 All citations are ``file:line`` relative to ``/root/reference/src_compressible/``.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures, and it cannot be
-compiled in this image (no Fortran compiler, MPI or FFTW).  The FFT arithmetic lives in FFTW 3
-(third-party, un-vendored, version unpinned: makefile:7,13 mention 3.3.4/3.3.8); it is restated
-here with ``scipy.fft`` (pocketfft), which implements the same DFT definition.  The oracle is
-pinned instead by analytic known answers (tests/test_oracle_analytic.py): Alfven-wave
-translation with third-order convergence, the exact RK3-polynomial decay of the k=0 mode in the
-expanding box, bit-exact conservation of the k=0 mode, div B at round-off.
+PARITY: the reference ships no tests, golden vectors or fixtures, and it cannot be compiled in this image (no
+Fortran compiler, MPI or FFTW).  What pins this restatement is the reference's own source EXECUTED here:
+oracle/fortran_exec.py translates the hot-path subroutines of all four source trees statement by statement
+(src_*/{mhdinit,dealiasing,AEBmod,rktmod,mhdrhs,fftw,parallel,mhd,mhdrms}.f90, read where they lie) and
+tests/golden/make_ref_exec_fixtures.py runs program mhd's sequence on one rank — grid/dealias/AEB initialisation,
+vardt, evolve with every loop around the FFTW calls and the single-rank branches of the transposes, diagnostics —
+storing golden vectors under tests/golden/ref_exec/ (tests/test_reference_source_pins.py: this oracle agrees to
+1e-12..1e-14).  Substituted, and therefore NOT pinned that way: FFTW's 1-D executions (third-party, un-vendored,
+version unpinned: makefile:7,13 mention 3.3.4/3.3.8; numpy.fft computes the same DFT definition, here restated with
+``scipy.fft``), MPI (one rank: the sendrecv loops have zero trips), and compiler-specific evaluation order.  In
+addition analytic known answers (tests/test_oracle_analytic.py): Alfven-wave translation with third-order
+convergence, the exact RK3-polynomial decay of the k=0 mode in the expanding box, bit-exact conservation of the k=0
+mode, div B at round-off, Hall-MHD dispersion relation.
 
 Array conventions: every array is NumPy C-order with the *last* axis = x, i.e. ``a[v, iz, iy, ix]``
 has exactly the memory layout of the Fortran ``a(ix, iy, iz, v)`` (x fastest).  Spectral arrays
