@@ -23,6 +23,48 @@ import re
 import numpy as np
 
 
+def _is_int(v):
+    return isinstance(v, (int, np.integer)) and not isinstance(v, (bool, np.bool_))
+
+
+class FInt(int):
+    """A Fortran INTEGER: closed under + - * and, unlike Python's int, under `/` (integer division truncating toward
+    zero, e.g. `normal_size = ngrid / nproc` in decompose_1d, parallel.f90:335).  Mixed with a real it behaves as a real."""
+
+    def _wrap(fn):
+        def op(self, o):
+            return FInt(fn(int(self), int(o))) if _is_int(o) else fn(int(self), o)
+        return op
+
+    def _rwrap(fn):
+        def op(self, o):
+            return FInt(fn(int(o), int(self))) if _is_int(o) else fn(o, int(self))
+        return op
+
+    def _tdiv(a, b):
+        if _is_int(a) and _is_int(b):
+            q = abs(a) // abs(b)
+            return q if (a >= 0) == (b >= 0) else -q
+        return a / b
+
+    __add__ = _wrap(lambda a, b: a + b)
+    __radd__ = _rwrap(lambda a, b: a + b)
+    __sub__ = _wrap(lambda a, b: a - b)
+    __rsub__ = _rwrap(lambda a, b: a - b)
+    __mul__ = _wrap(lambda a, b: a * b)
+    __rmul__ = _rwrap(lambda a, b: a * b)
+    __truediv__ = _wrap(_tdiv)
+    __rtruediv__ = _rwrap(_tdiv)
+    __pow__ = _wrap(lambda a, b: a ** b)
+    __mod__ = _wrap(lambda a, b: a % b)
+
+    def __neg__(self):
+        return FInt(-int(self))
+
+    def __pos__(self):
+        return self
+
+
 class FArray:
     """A NumPy array indexed the Fortran way: lower bound 1, inclusive upper bounds, first index fastest.
     ``a`` is stored with axes in Fortran order (axis 0 = first Fortran index); wrap a C-ordered [v, z, y, x] array
@@ -49,7 +91,8 @@ class FArray:
         return tuple(out)
 
     def __getitem__(self, key):
-        return self.a[self._key(key)]
+        v = self.a[self._key(key)]
+        return FInt(v) if isinstance(v, np.integer) else v
 
     def __setitem__(self, key, value):
         self.a[self._key(key)] = value.a if isinstance(value, FArray) else value
@@ -92,8 +135,14 @@ def _mod(a, p):
 INTRINSICS = {
     "cmplx": "_cmplx", "real": "_real", "sqrt": "_np.sqrt", "abs": "abs", "max": "max", "min": "min", "conjg": "_np.conj",
     "aimag": "_np.imag", "exp": "_np.exp", "cos": "_np.cos", "sin": "_np.sin", "tanh": "_np.tanh", "mod": "_mod",
-    "modulo": "_modulo", "floor": "_floor", "int": "int", "size": "_size", "dble": "float", "isnan": "_np.isnan",
+    "modulo": "_modulo", "floor": "_floor", "int": "_int", "size": "_size", "dble": "float", "isnan": "_np.isnan",
+    "kind": "_kind",
 }
+
+# Library calls whose results come back through scalar (or array-element) arguments: argument positions that are
+# outputs.  `call f(a, b, out, ierr)` becomes `out = f(a, b)` (several outputs: a tuple).
+OUT_ARGS = {"mpi_comm_rank": (1,), "mpi_comm_size": (1,), "mpi_cart_create": (5,), "mpi_cart_rank": (2,),
+            "mpi_comm_split": (3,), "mpi_type_create_subarray": (6,)}
 
 _DECL = re.compile(r"^(integer|real|complex|logical|character|type\s*\(|double\s+precision|use\b|implicit\b|include\b|save\b|external\b)", re.I)
 _SKIP = re.compile(r"^(write|print|open|close|inquire|read|allocate|deallocate|format|return\b|contains\b)", re.I)
@@ -187,11 +236,17 @@ class Translator:
         self.arrays = set(a.lower() for a in arrays)
 
     def expr(self, s: str) -> str:
+        """A whole Fortran expression (operators and literals are rewritten once, then names are resolved recursively)."""
         s = s.strip()
         s = re.sub(r"(\d+\.?\d*|\.\d+)d([+-]?\d+)", r"\1e\2", s)              # 1.0d0 -> 1.0e0
+        s = re.sub(r"(?<![\w.])(?<![eE][+-])(\d+)(?![\w.])", r"FInt(\1)", s)       # integer literals are Fortran INTEGERs
+        s = re.sub(r"\*\*\s*FInt\((\d+)\)", r"**\1", s)                           # ... except exponents (x**2 stays x*x in NumPy)
         for f, p in ((".and.", " and "), (".or.", " or "), (".not.", " not "), (".true.", " True "), (".false.", " False "),
                      (".eqv.", "=="), (".neqv.", "!="), (".eq.", "=="), (".ne.", "!="), (".gt.", ">"), (".ge.", ">="), (".lt.", "<"), (".le.", "<="), ("/=", "!=")):
             s = s.replace(f, p)
+        return self._names(s)
+
+    def _names(self, s: str) -> str:
         out, i = "", 0
         while i < len(s):
             m = _IDENT.match(s, i)
@@ -219,8 +274,8 @@ class Translator:
     def _arg(self, a: str) -> str:
         parts = _split_top(a, ":")
         if len(parts) == 1:
-            return self.expr(a)
-        return ":".join(self.expr(p) if p.strip() else "" for p in parts)
+            return self._names(a.strip())
+        return ":".join(self._names(p.strip()) if p.strip() else "" for p in parts)
 
     def subroutine(self, name: str, args, body, py_name=None) -> str:
         """Python source of one subroutine.  Names that are assigned but neither declared in the subroutine nor dummy
@@ -229,6 +284,14 @@ class Translator:
         local_arrays = set()
         lines, indent = [], 1
         assigned = set()
+        saved_arrays = set(self.arrays)
+        for st in body:          # dummy arguments declared with a shape are arrays inside this subroutine
+            if _DECL.match(st) and "::" in st:
+                attrs, names = st.split("::", 1)
+                for item in _split_top(names):
+                    nm = _IDENT.match(item.strip()).group(0)
+                    if nm in args and ("dimension" in attrs or "(" in item):
+                        self.arrays.add(nm)
 
         def emit(t):
             lines.append("    " * indent + t)
@@ -294,6 +357,7 @@ class Translator:
                 emit("pass")
                 continue
             self._simple(st, emit, assigned)
+        self.arrays = saved_arrays
         glob = sorted(n for n in assigned if n not in local)
         head = [f"def {py_name or name}({', '.join(args)}):"]
         if glob:
@@ -313,6 +377,17 @@ class Translator:
             else:
                 assigned.add(b)
                 emit(f"{b} = {a}")
+        elif st.startswith("call ") and _IDENT.match(st[5:].strip()).group(0) in OUT_ARGS:
+            rest = st[5:].strip()
+            nm = _IDENT.match(rest).group(0)
+            k = rest.index("(")
+            args = [a.strip() for a in _split_top(rest[k + 1:_match_paren(rest, k)])]
+            outs = [args[i] for i in OUT_ARGS[nm]]
+            ins = [self.expr(a) for i, a in enumerate(args[:-1]) if i not in OUT_ARGS[nm]]      # the last argument is ierr
+            for o in outs:
+                if "(" not in o:
+                    assigned.add(o)
+            emit(f"{', '.join(self.expr(o) for o in outs)} = {nm}({', '.join(ins)})")
         elif st.startswith("call "):
             rest = st[5:].strip()
             emit(self.expr(rest) if "(" in rest else f"{rest}()")
@@ -340,12 +415,13 @@ class Translator:
 
 
 def _frange(a, b, step=1):
-    return range(int(a), int(b) + (1 if step > 0 else -1), int(step))
+    return (FInt(i) for i in range(int(a), int(b) + (1 if step > 0 else -1), int(step)))
 
 
 def base_namespace():
     return {"_np": np, "_cmplx": _cmplx, "_real": _real, "_size": _size, "_mod": _mod, "_frange": _frange,
-            "_modulo": lambda a, p: a % p, "_floor": lambda x: int(np.floor(x))}
+            "_modulo": lambda a, p: a % p, "_floor": lambda x: FInt(np.floor(x)), "_kind": lambda x: 8, "_int": lambda x: FInt(x),
+            "FInt": FInt}
 
 
 def load(namespace: dict, path: str, names, arrays=None):

@@ -72,6 +72,7 @@ def build_namespace(c, incompressible=False):
     for k, v in st.items():
         ns[k] = F(v.T)
     ns["_storage"] = st
+    ns["_wrap_ints"] = lambda: ns.update({k: fx.FInt(v) for k, v in ns.items() if type(v) is int})   # Fortran INTEGER semantics
     one = lambda v: F(np.array([v]))  # noqa: E731
     # parallel_start on one rank (parallel.f90:100-143): offsets 0, sizes = the whole axis
     ns.update(xi_offset=one(0), xi_size=one(nxh), yi_offset=one(0), yi_size=one(ny), yj_offset=one(0), yj_size=one(ny),
@@ -104,6 +105,7 @@ def build_namespace(c, incompressible=False):
         out.a[...] = np.fft.fft(a.a) if plan < 0 else np.fft.ifft(a.a) * a.a.size
 
     ns.update(fftw_execute_dft_r2c=fftw_execute_dft_r2c, fftw_execute_dft_c2r=fftw_execute_dft_c2r, fftw_execute_dft=fftw_execute_dft)
+    ns["_wrap_ints"]()
     return ns
 
 
@@ -365,6 +367,68 @@ def run_case_incompressible_2d(name, c, nsteps=3):
     print(name, "dt", dts, "max_divV", out["max_divv"], "rho0", rho0s)
 
 
+def run_parallel_start(nx, ny, nz, npe):
+    """parallel_start + decompose_1d (parallel.f90:28-212,326-349) executed for every rank of a slab run
+    (ndim_parallel = 1) on a fake MPI world: the decomposition tables and the MPI subarray types that define
+    transpose_yz / transpose_zy.  Returns per rank: yj/zj offsets and sizes, and (full, sub, starts) of the send / receive
+    types towards every peer."""
+    ranks = []
+    for ipe in range(npe):
+        ns = fx.base_namespace()
+        F = fx.FArray
+        ints = lambda n: F(np.zeros(n, dtype=np.int64))  # noqa: E731
+        objs = lambda n: F(np.empty(n, dtype=object))    # noqa: E731
+        ns.update(dims=ints(2), periods=F(np.zeros(2, dtype=bool)), icoords=ints(2), reorder=True, ierr=0, ipe=0, npe=0, iproc=0, jproc=0,
+                  myid_i=0, myid_j=0, ipe_cart=0, comm_cart=None, comm1d_i=None, comm1d_j=None,
+                  xi_offset=ints(1), xi_size=ints(1), yi_offset=ints(1), yi_size=ints(1), yj_offset=ints(npe), yj_size=ints(npe),
+                  zj_offset=ints(npe), zj_size=ints(npe), subarr_type_xy_send=objs(1), subarr_type_xy_recv=objs(1),
+                  subarr_type_yz_send=objs(npe), subarr_type_yz_recv=objs(npe),
+                  mpi_comm_world="world", mpi_real=4, mpi_complex=4, mpi_double_precision=8, mpi_double_complex=8, mpi_realtype=0,
+                  mpi_complextype=0, mpi_order_fortran="F")
+
+        def comm_rank(comm, me=ipe):
+            if comm == "world":
+                return fx.FInt(me)
+            kind, color, key, members = comm
+            return fx.FInt(sorted(members[color]).index(key))
+
+        def comm_split(comm, color, key, me=ipe):
+            # the members of every colour group, by key: in the 1 x npe grid of ndim_parallel = 1 the coordinates of rank r are (0, r)
+            coords = [(0, r) for r in range(npe)]
+            if int(color) == coords[me][1] and int(key) == coords[me][0]:      # split by j (comm1d_i): colour = my j
+                members = {c[1]: [cc[0] for cc in coords if cc[1] == c[1]] for c in coords}
+            else:                                                              # split by i (comm1d_j): colour = my i
+                members = {c[0]: [cc[1] for cc in coords if cc[0] == c[0]] for c in coords}
+            return ("sub", int(color), int(key), members)
+
+        def cart_get(comm, nd, dims, periods, icoords, ierr, me=ipe):
+            icoords.a[:] = (me // int(dims.a[1]), me % int(dims.a[1]))
+
+        ns.update(mpi_init=lambda ierr: None, mpi_comm_rank=comm_rank, mpi_comm_size=lambda comm: fx.FInt(npe),
+                  mpi_cart_create=lambda comm, nd, dims, periods, reorder: "cart", mpi_cart_get=cart_get,
+                  mpi_cart_rank=lambda comm, icoords, me=ipe: fx.FInt(me), mpi_comm_split=comm_split,
+                  mpi_type_create_subarray=lambda nd, full, sub, starts, order, typ: tuple([int(v) for v in x] for x in (full, sub, starts)),
+                  mpi_type_commit=lambda t, ierr: None)
+        fx.load(ns, f"{REF}/parallel.f90", ["decompose_1d", "parallel_start"])
+        ns["parallel_start"](fx.FInt(nx), fx.FInt(ny), fx.FInt(nz), fx.FInt(8), fx.FInt(1))
+        assert (int(ns["myid_i"]), int(ns["myid_j"]), int(ns["iproc"]), int(ns["jproc"])) == (0, ipe, 1, npe)
+        ranks.append(dict(yj_offset=ns["yj_offset"].a.copy(), yj_size=ns["yj_size"].a.copy(), zj_offset=ns["zj_offset"].a.copy(),
+                          zj_size=ns["zj_size"].a.copy(), xi_size=int(ns["xi_size"].a[0]),
+                          yz_send=np.array([ns["subarr_type_yz_send"].a[q] for q in range(npe)], dtype=np.int64),
+                          yz_recv=np.array([ns["subarr_type_yz_recv"].a[q] for q in range(npe)], dtype=np.int64)))
+    return ranks
+
+
+def make_parallel_fixtures():
+    out = {}
+    for nx, ny, nz, npe in [(16, 16, 16, 2), (16, 16, 16, 3), (16, 32, 16, 8), (32, 64, 32, 5), (16, 16, 16, 4)]:
+        for r, d in enumerate(run_parallel_start(nx, ny, nz, npe)):
+            for k, v in d.items():
+                out[f"{nx}x{ny}x{nz}_p{npe}_r{r}_{k}"] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, "ref_exec", "parallel_start.npz"), **out)
+    print("parallel_start:", len(out), "arrays")
+
+
 def initial_primitive(c, seed=5):
     """Smooth O(1) primitive fields (rho, u, B, p) with content in every direction, [8, nz, ny, nx]."""
     import parity_common as pc
@@ -430,6 +494,8 @@ def run_case(name, c, nsteps=2, pieces=True):
 
 
 if __name__ == "__main__":
+    os.makedirs(os.path.join(HERE, "ref_exec"), exist_ok=True)
+    make_parallel_fixtures()
     for i, (name, c) in enumerate(CASES.items()):
         run_case(name, c, pieces=(i == 0))
     for i, (name, c) in enumerate(CASES_INCOMPRESSIBLE.items()):

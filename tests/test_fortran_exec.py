@@ -66,3 +66,38 @@ def test_translator_semantics(tmp_path):
 def test_statement_splitting():
     st = fx.statements("  x = 1 ! c\n  y = 'a!b' ; z = 2 &\n    & + 3\n")
     assert [' '.join(s.split()) for s in st] == ["x = 1", "y = 'a!b'", "z = 2 + 3"]
+
+
+SRC2 = """
+subroutine dec(ngrid, nproc, i_offset, i_size)
+    integer,intent(in) :: ngrid, nproc
+    integer,intent(out),allocatable,dimension(:) :: i_offset, i_size
+    integer :: normal_size, p
+    allocate(i_offset(nproc), i_size(nproc))
+    normal_size = ngrid / nproc          ! INTEGER division
+    half = 7/2 + (-7)/2 + nx/2+1          ! literals and a module integer
+    i_offset(1) = 0
+    do p = 1, nproc
+        i_size(p) = normal_size
+        if (p > 1) i_offset(p) = i_offset(p-1) + i_size(p-1)
+    enddo
+    call mpi_comm_rank(mpi_comm_world, me, ierr)
+    call mpi_type_create_subarray(3, [nx/2+1, 2, 3], [1, 1, 1], [0, 0, 0], 0, 0, types(2), ierr)
+end subroutine
+"""
+
+
+def test_integer_semantics_and_output_arguments(tmp_path):
+    f = tmp_path / "d.f90"
+    f.write_text(SRC2)
+    ns = fx.base_namespace()
+    off, siz = fx.FArray(np.zeros(3, dtype=np.int64)), fx.FArray(np.zeros(3, dtype=np.int64))
+    types = fx.FArray(np.empty(2, dtype=object))
+    ns.update(nx=fx.FInt(16), half=None, me=None, ierr=0, mpi_comm_world="w", types=types,
+              mpi_comm_rank=lambda comm: 5, mpi_type_create_subarray=lambda nd, full, sub, st, o, t: (list(full), list(sub), list(st)))
+    fx.load(ns, str(f), ["dec"])
+    ns["dec"](fx.FInt(16), fx.FInt(3), off, siz)
+    assert list(siz.a) == [5, 5, 5] and list(off.a) == [0, 5, 10]          # 16 / 3 = 5, not 5.33
+    assert ns["half"] == 3 + (-3) + 9 and isinstance(ns["half"], int)       # truncation toward zero; 16/2+1 = 9
+    assert ns["me"] == 5
+    assert types.a[1] == ([9, 2, 3], [1, 1, 1], [0, 0, 0]) and types.a[0] is None

@@ -275,6 +275,9 @@ def check_library(name, lib_path=None, tol=1e-11):
         for v in range(8):
             assert pc.rel_l2(uu[v], g["uu"][v]) < tol, (v, pc.rel_l2(uu[v], g["uu"][v]))
             assert pc.rel_l2(uf[v], g["uu_fourier"][v]) < tol, v
+        if p.dealias_option == 1:      # the truncation mask of dealias (dealiasing.f90:87-99), bit for bit: the same modes are zero
+            assert np.array_equal(uf == 0, g["uu_fourier"] == 0)
+            assert (g["uu_fourier"][0] == 0).mean() > 0.5
         for v in range(4):
             assert pc.rel_l2(prim[v], g["uu_prim"][v]) < 10 * tol, v
         assert abs(s.calc_max_divB() - float(g["max_divb"])) <= 1e-7 * float(g["max_divb"])
@@ -302,3 +305,64 @@ def test_2d_library_on_the_emulator_agrees_with_the_executed_reference_source(em
 @pytest.mark.parametrize("name", CASES_INCOMPRESSIBLE_2D)
 def test_incompressible_2d_library_on_the_emulator_agrees_with_the_executed_reference_source(emu, name):
     check_library_incompressible_2d(name, lib_path=emu)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# transpose index maps against the MPI subarray types of the executed parallel_start (parallel.f90:28-212)
+# ------------------------------------------------------------------------------------------------------------------
+def _par(shape, npe):
+    g = np.load(os.path.join(GOLD, "parallel_start.npz"))
+    nx, ny, nz = shape
+    pre = f"{nx}x{ny}x{nz}_p{npe}_r"
+    return [{k: g[f"{pre}{r}_{k}"] for k in ("yj_offset", "yj_size", "zj_offset", "zj_size", "xi_size", "yz_send", "yz_recv")}
+            for r in range(npe)]
+
+
+@pytest.mark.parametrize("shape,npe", [((16, 16, 16), 2), ((16, 16, 16), 3), ((16, 16, 16), 4), ((16, 32, 16), 8), ((32, 64, 32), 5)])
+def test_transpose_index_maps_match_the_executed_parallel_start(emu, shape, npe):
+    """transpose_yz sends, for every peer q, the MPI subarray yz_send(q) of w_yxz into the subarray yz_recv(me) of q's
+    w_zxy, element by element in Fortran order (parallel.f90:185-210,273-297); transpose_zy is the reverse pairing
+    (:300-324).  The types come from the reference's parallel_start executed for every rank
+    (tests/golden/make_ref_exec_fixtures.py); the library (reference slabs: LAPS_TUNE_CYCLIC=0) must send every element to
+    the same rank and the same local coordinates.  decompose_1d's tables (remainder on the last rank) are checked on the way."""
+    from laps_b200 import Solver
+    nx, ny, nz = shape
+    ranks = _par(shape, npe)
+    saved = os.environ.get("LAPS_TUNE_CYCLIC")
+    os.environ["LAPS_TUNE_CYCLIC"] = "0"
+    try:
+        for me, d in enumerate(ranks):
+            with Solver(emu, nx=nx, ny=ny, nz=nz, Lx=1.0, Ly=1.0, Lz=1.0, dealias_option=1, rank=me, nranks=npe) as s:
+                X = int(d["xi_size"])
+                assert (s.ext.z_offset, s.ext.z_size, s.ext.y_offset, s.ext.y_size) == (
+                    d["zj_offset"][me], d["zj_size"][me], d["yj_offset"][me], d["yj_size"][me]) and X == s.nxh
+                myz = s.transpose_yz_indexmap().reshape(s.nxh, ny, s.nzl, 2)
+                mzy = s.transpose_zy_indexmap().reshape(s.nxh, s.nyl, nz, 2)
+                for q, dq in enumerate(ranks):
+                    # ---- transpose_yz: me -> q
+                    full, sub, st = d["yz_send"][q]
+                    rfull, rsub, rst = dq["yz_recv"][me]
+                    assert list(sub) == list(rsub) and list(full) == [X, ny, d["zj_size"][me]] and list(rfull) == [X, dq["yj_size"][q], nz]
+                    i, j, l = np.meshgrid(np.arange(sub[0]), np.arange(sub[1]), np.arange(sub[2]), indexing="ij")
+                    ours = myz[st[0] + i, st[1] + j, st[2] + l]                 # source element, local coordinates in w_yxz
+                    assert np.all(ours[..., 0] == q)
+                    off, Yq = ours[..., 1], int(dq["yj_size"][q])
+                    assert np.array_equal(off % nz, rst[2] + l)                 # destination z in q's w_zxy
+                    assert np.array_equal((off // nz) % Yq, rst[1] + j)         # destination local y
+                    assert np.array_equal(off // (nz * Yq), rst[0] + i)         # destination x
+                    # ---- transpose_zy: me -> q sends subarray yz_recv(q) of w_zxy into subarray yz_send(me) of q's w_yxz
+                    full, sub, st = d["yz_recv"][q]
+                    rfull, rsub, rst = dq["yz_send"][me]
+                    assert list(sub) == list(rsub)
+                    i, j, l = np.meshgrid(np.arange(sub[0]), np.arange(sub[1]), np.arange(sub[2]), indexing="ij")
+                    ours = mzy[st[0] + i, st[1] + j, st[2] + l]
+                    assert np.all(ours[..., 0] == q)
+                    off, Zq = ours[..., 1], int(dq["zj_size"][q])
+                    assert np.array_equal(off % Zq, rst[2] + l)
+                    assert np.array_equal((off // Zq) % ny, rst[1] + j)
+                    assert np.array_equal(off // (Zq * ny), rst[0] + i)
+    finally:
+        if saved is None:
+            os.environ.pop("LAPS_TUNE_CYCLIC", None)
+        else:
+            os.environ["LAPS_TUNE_CYCLIC"] = saved
