@@ -367,6 +367,42 @@ def run_case_incompressible_2d(name, c, nsteps=3):
     print(name, "dt", dts, "max_divV", out["max_divv"], "rho0", rho0s)
 
 
+def run_case_100_steps(name="hall_aeb_mask_100steps", every=10, nsteps=100):
+    """The north star's second acceptance test on the executed reference source: 100 steps of the Principal loop (16 x 16 x 8, Hall +
+    expanding box + spherical mask); mean energy density, mean cross helicity, max div B and the rms.dat row every 10 steps."""
+    c = dict(CASES["hall_aeb_mask"], nx=16, ny=16, nz=8)
+    ns = build_namespace(c)
+    load_reference(ns)
+    st = ns["_storage"]
+    prim = initial_primitive(c, seed=21)
+    out = {"prim0": prim.copy()}
+    ns["grid_initialize"]()
+    ns["dealias_initialize"]()
+    ns["aeb_calc"](ns["radius"])
+    st["uu"][...] = prim
+    ns["initial_calc_conserve_variable"]()
+    ns["transform_uu_real_to_fourier"]()
+    ns["vardt"]()
+    rows = []
+    n = float(c["nx"] * c["ny"] * c["nz"])
+    for istep in range(1, nsteps + 1):
+        ns["evolve"]()
+        ns["time"] = ns["time"] + ns["dt"]
+        ns["evolve_radius"](ns["time"])
+        ns["vardt"]()
+        if istep % every == 0:
+            ns["calc_max_divb"]()
+            ns["calc_rms"]()
+            uu, pr = st["uu"], st["uu_prim"]
+            energy = uu[7].sum() / n                                           # mean total energy density uu(8)
+            helicity = (pr[0] * uu[4] + pr[1] * uu[5] + pr[2] * uu[6]).sum() / n   # mean u.B
+            rows.append(np.concatenate([[istep, ns["time"], ns["dt"], energy, helicity, ns["max_divb"]], st["uu_ave"], st["uu_rms"], st["rho_u2"]]))
+    out.update(rows=np.array(rows), uu=st["uu"].copy(), switches=np.array([c[k] for k in sorted(c)], dtype=np.float64),
+               switch_names=np.array(sorted(c)))
+    np.savez_compressed(os.path.join(HERE, "ref_exec", name + ".npz"), **out)
+    print(name, "time", ns["time"], "energy", rows[-1][3], "max_divB", rows[-1][5])
+
+
 def run_parallel_start(nx, ny, nz, npe):
     """parallel_start + decompose_1d (parallel.f90:28-212,326-349) executed for every rank of a slab run
     (ndim_parallel = 1) on a fake MPI world: the decomposition tables and the MPI subarray types that define
@@ -496,6 +532,7 @@ def run_case(name, c, nsteps=2, pieces=True):
 if __name__ == "__main__":
     os.makedirs(os.path.join(HERE, "ref_exec"), exist_ok=True)
     make_parallel_fixtures()
+    run_case_100_steps()
     for i, (name, c) in enumerate(CASES.items()):
         run_case(name, c, pieces=(i == 0))
     for i, (name, c) in enumerate(CASES_INCOMPRESSIBLE.items()):

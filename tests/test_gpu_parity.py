@@ -298,3 +298,10 @@ def test_2d_library_agrees_with_the_executed_reference_source(name):
 def test_incompressible_2d_library_agrees_with_the_executed_reference_source(name):
     import test_reference_source_pins as rp
     rp.check_library_incompressible_2d(name)
+
+
+def test_100_steps_against_the_executed_reference_source():
+    """North star: energy, cross helicity and div B within 1e-9 relative after 100 steps — here against golden vectors of
+    the reference's own source executed for 100 steps (tests/golden/ref_exec/hall_aeb_mask_100steps.npz)."""
+    import test_reference_source_pins as rp
+    rp.check_library_100_steps()

@@ -366,3 +366,63 @@ def test_transpose_index_maps_match_the_executed_parallel_start(emu, shape, npe)
             os.environ.pop("LAPS_TUNE_CYCLIC", None)
         else:
             os.environ["LAPS_TUNE_CYCLIC"] = saved
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# 100 steps (north star: energy, cross helicity and div B within 1e-9 relative after 100 steps)
+# ------------------------------------------------------------------------------------------------------------------
+def check_100_steps(make_state, tol=1e-9):
+    """make_state(p, prim) -> object with vardt(), step(), dt, time, invariants(), calc_rms(); rows of the fixture every 10 steps:
+    istep, time, dt, mean energy density, mean u.B, max |k.B^|, uu_ave(8), uu_rms(8), rho_u2(3)."""
+    g, p = load_case("hall_aeb_mask_100steps")
+    s = make_state(p, g["prim0"])
+    s.vardt()
+    rows = {int(r[0]): r for r in g["rows"]}
+    for istep in range(1, 101):
+        s.step()
+        if istep in rows:
+            r = rows[istep]
+            assert abs(s.time - r[1]) <= 1e-11 * r[1] and abs(s.dt - r[2]) <= 1e-10 * r[2], (istep, s.time, r[1], s.dt, r[2])
+            inv = s.invariants()
+            assert abs(inv[0] - r[3]) <= tol * abs(r[3]), (istep, inv[0], r[3])
+            assert abs(inv[1] - r[4]) <= tol * max(abs(r[4]), 1e-6), (istep, inv[1], r[4])
+            assert abs(inv[2] - r[5]) <= 1e-6 * r[5], (istep, inv[2], r[5])      # a maximum of round-off-sized differences
+            ave, rms, ru2 = s.calc_rms()
+            assert np.allclose(ave, r[6:14], rtol=tol, atol=1e-13), istep
+            assert np.allclose(rms, r[14:22], rtol=1e-6, atol=1e-15), istep      # <u^2> - <u>^2 cancels digits
+            assert np.allclose(ru2, r[22:25], rtol=1e-8, atol=1e-16), istep
+    return s
+
+
+def test_oracle_100_steps_against_the_executed_reference_source():
+    def make(p, prim):
+        o = lo.State(p)
+        o.set_primitive(prim)
+        return o
+    o = check_100_steps(make)
+    g, _ = load_case("hall_aeb_mask_100steps")
+    for v in range(8):
+        assert pc.rel_l2(o.uu[v], g["uu"][v]) < 1e-10, v
+
+
+def check_library_100_steps(lib_path=None):
+    from laps_b200 import Solver
+    holder = {}
+
+    def make(p, prim):
+        s = Solver(lib_path, **pc.solver_kwargs(p))
+        s.set_primitive(prim)
+        holder["s"] = s
+        return s
+    try:
+        s = check_100_steps(make)
+        g, _ = load_case("hall_aeb_mask_100steps")
+        uu, _ = s.get_state()
+        for v in range(8):
+            assert pc.rel_l2(uu[v], g["uu"][v]) < 1e-9, (v, pc.rel_l2(uu[v], g["uu"][v]))
+    finally:
+        holder["s"].close()
+
+
+def test_library_100_steps_on_the_emulator_against_the_executed_reference_source(emu):
+    check_library_100_steps(emu)
