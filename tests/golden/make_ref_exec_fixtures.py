@@ -220,6 +220,10 @@ CASES_2D = {
     "c2d_external_force_filter": dict(nx=32, ny=32, nz=1, if_hall=True, if_aeb=True, if_corotating=False, dealias_option=2,
                                       if_resis=True, if_resis_exp=False, if_visc=True, if_visc_exp=False, if_conserve_background=False,
                                       if_z_radial=False, if_limit_dt_increase=False, if_external_force=True),
+    # if_corotating in 2D: the oracle restates it, the library refuses it
+    "c2d_corotating_oracle_only": dict(nx=16, ny=16, nz=1, if_hall=True, if_aeb=True, if_corotating=True, dealias_option=1,
+                                       if_resis=True, if_resis_exp=True, if_visc=True, if_visc_exp=False, if_conserve_background=False,
+                                       if_z_radial=False, if_limit_dt_increase=False, if_external_force=False),
 }
 
 
@@ -261,6 +265,8 @@ def run_case_2d(name, c, nsteps=3, pieces=True):
     ns["grid_initialize"]()
     ns["dealias_initialize"]()
     ns["aeb_calc"](ns["radius"])
+    ang = ns["corotating_angle"] if ns["if_corotating"] else 0.0       # AEB_initialize (2D/AEBmod.f90:24-29)
+    ns["cos_cor_ang"], ns["sin_cor_ang"] = float(np.cos(ang)), float(np.sin(ang))
     st["uu"][...] = prim
     ns["initial_calc_conserve_variable"]()
     ns["transform_uu_real_to_fourier"]()
@@ -538,6 +544,6 @@ if __name__ == "__main__":
     for i, (name, c) in enumerate(CASES_INCOMPRESSIBLE.items()):
         run_case_incompressible(name, c, pieces=(i == 0))
     for i, (name, c) in enumerate(CASES_2D.items()):
-        run_case_2d(name, c, pieces=(i != 1))          # the external-force case keeps its pieces (fnl(7) += force)
+        run_case_2d(name, c, pieces=(i in (0, 2)))     # the external-force case keeps its pieces (fnl(7) += force)
     for name, c in CASES_INCOMPRESSIBLE_2D.items():
         run_case_incompressible_2d(name, c)

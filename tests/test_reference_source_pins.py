@@ -153,7 +153,7 @@ def check_library_incompressible(name, lib_path=None, tol=1e-11):
         assert abs(dv - float(g["max_divv_real"])) <= 1e-7 * float(g["max_divv_real"])
 
 
-@pytest.mark.parametrize("name", CASES_2D)
+@pytest.mark.parametrize("name", CASES_2D + ["c2d_corotating_oracle_only"])
 def test_2d_oracle_agrees_with_the_executed_reference_source(name):
     """src_compressible/2D: kz = 0, if_z_radial, square truncation, if_limit_dt_increase, the external force."""
     g, p = load_case(name)
@@ -426,3 +426,11 @@ def check_library_100_steps(lib_path=None):
 
 def test_library_100_steps_on_the_emulator_against_the_executed_reference_source(emu):
     check_library_100_steps(emu)
+
+
+def test_2d_corotation_is_refused_by_the_library(emu):
+    """The one option of the reference the library does not run; the oracle restates it and is pinned above."""
+    from laps_b200 import Solver, capi
+    g, p = load_case("c2d_corotating_oracle_only")
+    with pytest.raises(capi.LapsError, match="if_corotating"):
+        Solver(emu, **pc.solver_kwargs(p))
