@@ -97,6 +97,12 @@ class FArray:
     def __setitem__(self, key, value):
         self.a[self._key(key)] = value.a if isinstance(value, FArray) else value
 
+    def __iter__(self):
+        return iter(self.a)
+
+    def __len__(self):
+        return len(self.a)
+
     # whole-array arithmetic (e.g. `rho_u2 = rho_u2_sum / real(size_grid)`)
     def _v(self, o):
         return o.a if isinstance(o, FArray) else o
@@ -285,13 +291,16 @@ class Translator:
         lines, indent = [], 1
         assigned = set()
         saved_arrays = set(self.arrays)
-        for st in body:          # dummy arguments declared with a shape are arrays inside this subroutine
+        local_alloc = set()
+        for st in body:          # dummies and locals declared with a shape are arrays inside this subroutine
             if _DECL.match(st) and "::" in st:
                 attrs, names = st.split("::", 1)
                 for item in _split_top(names):
                     nm = _IDENT.match(item.strip()).group(0)
-                    if nm in args and ("dimension" in attrs or "(" in item):
+                    if "dimension" in attrs or ("(" in item.split("=")[0]):
                         self.arrays.add(nm)
+                        if nm not in args:
+                            local_alloc.add(nm)
 
         def emit(t):
             lines.append("    " * indent + t)
@@ -310,11 +319,30 @@ class Translator:
                             emit(f"{nm} = {self.expr(item.split('=', 1)[1])}")
                         elif "(" in item or "dimension" in attrs:
                             local_arrays.add(nm)
+                            # explicit shape: `real, dimension(3) :: d` / `integer :: a(3)`; deferred shape waits for allocate
+                            shape = item[item.index("(") + 1:_match_paren(item, item.index("("))] if "(" in item else None
+                            if shape is None:
+                                m2 = re.search(r"dimension\s*\(", attrs)
+                                if m2:
+                                    k2 = attrs.index("(", m2.start())
+                                    shape = attrs[k2 + 1:_match_paren(attrs, k2)]
+                            if shape is not None and ":" not in shape and nm not in args:
+                                dt = "complex" if attrs.strip().startswith("complex") else ("int" if attrs.strip().startswith("integer") else "float")
+                                emit(f"{nm} = _alloc(({self.expr(shape)},), '{dt}')")
                 else:                                              # old-style: `real dt` / `integer irk`
                     for item in _split_top(re.sub(r"^\w+(\s*\*\s*\d+)?\s+", "", st)):
                         m = _IDENT.match(item.strip())
                         if m:
                             local.add(m.group(0))
+                continue
+            if st.startswith("allocate"):                         # local allocatables only; module arrays are set up by the caller
+                k = st.index("(")
+                for item in _split_top(st[k + 1:_match_paren(st, k)]):
+                    item = item.strip()
+                    nm = _IDENT.match(item).group(0)
+                    if nm in local_alloc and "(" in item:
+                        shape = item[item.index("(") + 1:_match_paren(item, item.index("("))]
+                        emit(f"{nm} = _alloc(({self.expr(shape)},), 'float')")
                 continue
             if _SKIP.match(st):
                 if st.startswith("return"):
@@ -414,6 +442,34 @@ class Translator:
             raise ValueError("cannot translate statement: " + st)
 
 
+def _alloc(shape, kind):
+    dt = {"float": np.float64, "int": np.int64, "complex": np.complex128}[kind]
+    return FArray(np.zeros(tuple(int(n) for n in shape)[::-1], dtype=dt).T)
+
+
+def case_body(body, selector: str, value: str):
+    """The statements of `case(value)` of the (outermost) `select case(selector)` in a subroutine body."""
+    out, depth, active, inside = [], 0, False, False
+    for st in body:
+        m = re.match(r"^select\s*case\s*\((.*)\)$", st)
+        if m:
+            depth += 1
+            if depth == 1 and m.group(1).strip() == selector:
+                inside = True
+                continue
+        elif re.match(r"^end\s*select", st):
+            depth -= 1
+            if depth == 0 and inside:
+                return out
+        elif inside and depth == 1 and re.match(r"^case\b", st):
+            m = re.match(r"^case\s*\((.*)\)$", st)
+            active = bool(m) and value in [v.strip() for v in m.group(1).split(",")]
+            continue
+        if inside and active:
+            out.append(st)
+    raise KeyError(f"select case({selector}) / case({value}) not found")
+
+
 def _frange(a, b, step=1):
     return (FInt(i) for i in range(int(a), int(b) + (1 if step > 0 else -1), int(step)))
 
@@ -421,7 +477,7 @@ def _frange(a, b, step=1):
 def base_namespace():
     return {"_np": np, "_cmplx": _cmplx, "_real": _real, "_size": _size, "_mod": _mod, "_frange": _frange,
             "_modulo": lambda a, p: a % p, "_floor": lambda x: FInt(np.floor(x)), "_kind": lambda x: 8, "_int": lambda x: FInt(x),
-            "FInt": FInt}
+            "FInt": FInt, "_alloc": _alloc}
 
 
 def load(namespace: dict, path: str, names, arrays=None):

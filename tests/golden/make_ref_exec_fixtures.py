@@ -409,6 +409,49 @@ def run_case_100_steps(name="hall_aeb_mask_100steps", every=10, nsteps=100):
     print(name, "time", ns["time"], "energy", rows[-1][3], "max_divB", rows[-1][5])
 
 
+def run_initial_conditions(name="initial_conditions", nx=16, ny=8, nz=8):
+    """The initial-condition hooks the benchmark and the stand-in driver rely on, from the reference's text
+    (mhdinit.f90:183-260 background_fields_initialize case 3; :300-342 perturbation_initialize case 1; :695-823 case 7).
+    The reference seeds a compiler-specific generator (random_seed(PUT = ir + 100), :705-727); as everywhere in this
+    repository the three phase tables come from numpy.random.default_rng(ir + 100) instead — the hook below —
+    and everything else (mode table, isotropy cut, polarisation along k x B0, amplitudes) is the Fortran's."""
+    c = dict(CASES["hall_aeb_mask"], nx=nx, ny=ny, nz=nz)
+    out = {}
+    for ipert, extra in ((7, dict(nmodex=2, nmodey=2, nmodez=2, db0=0.1, dv0=0.1, drho0=0.01)),
+                         (1, dict(db0=0.1, wave_number_jet=2))):
+        ns = build_namespace(c)
+        st = ns["_storage"]
+        ns.update(rho0=1.0, t0=1.0, bx0=1.0, by0=0.25, bz0=-0.5, press0=1.0, ifield=3, ipert=ipert, nmode=0, correlation_vb=0.0,
+                  b0=1.0, a0=0.05, **extra)
+        seed = {}
+
+        def random_seed(put=None, size=None, seed=seed):
+            seed["s"] = int(put.a[0])
+
+        def random_number(a, seed=seed):
+            a.a[...] = np.random.default_rng(seed["s"]).random(a.a.size)
+
+        ns.update(random_seed=random_seed, random_number=random_number, exit=lambda code: (_ for _ in ()).throw(SystemExit(code)))
+        ns["_wrap_ints"]()
+        fx.load(ns, f"{REF}/mhdinit.f90", ["grid_initialize"])
+        ns["grid_initialize"]()
+        tr = fx.Translator({k for k, v in ns.items() if isinstance(v, fx.FArray)})
+        for sub, sel, val in (("background_fields_initialize", "ifield", "3"), ("perturbation_initialize", "ipert", str(ipert))):
+            args, body = fx.subroutine_statements(f"{REF}/mhdinit.f90", sub)
+            head = []
+            for stmt in body:                                   # declarations and the statements before the select
+                if stmt.startswith("select"):
+                    break
+                head.append(stmt)
+            code = tr.subroutine(sub, args, head + fx.case_body(body, sel, val))
+            exec(compile(code, f"<{sub}:case({val})>", "exec"), ns)
+            ns[sub]()
+        out[f"ipert{ipert}"] = st["uu"].copy()
+    out["params"] = np.array([nx, ny, nz, 24.0, 12.0, 6.0, 1.0, 0.25, -0.5])
+    np.savez_compressed(os.path.join(HERE, "ref_exec", name + ".npz"), **out)
+    print(name, "rms B perturbation (ipert 7):", float(np.std(out["ipert7"][4])))
+
+
 def run_parallel_start(nx, ny, nz, npe):
     """parallel_start + decompose_1d (parallel.f90:28-212,326-349) executed for every rank of a slab run
     (ndim_parallel = 1) on a fake MPI world: the decomposition tables and the MPI subarray types that define
@@ -538,6 +581,7 @@ def run_case(name, c, nsteps=2, pieces=True):
 if __name__ == "__main__":
     os.makedirs(os.path.join(HERE, "ref_exec"), exist_ok=True)
     make_parallel_fixtures()
+    run_initial_conditions()
     run_case_100_steps()
     for i, (name, c) in enumerate(CASES.items()):
         run_case(name, c, pieces=(i == 0))

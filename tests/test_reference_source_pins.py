@@ -434,3 +434,35 @@ def test_2d_corotation_is_refused_by_the_library(emu):
     g, p = load_case("c2d_corotating_oracle_only")
     with pytest.raises(capi.LapsError, match="if_corotating"):
         Solver(emu, **pc.solver_kwargs(p))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# initial-condition hooks (the benchmark's synthetic turbulence, the stand-in driver's Alfven wave)
+# ------------------------------------------------------------------------------------------------------------------
+def test_initial_conditions_against_the_executed_reference_source():
+    """background_fields_initialize case 3 + perturbation_initialize cases 7 and 1 (mhdinit.f90:183-260,300-342,695-823)
+    executed from the reference's text, the three phase tables supplied by numpy.random.default_rng(ir + 100) in place of
+    the compiler-specific generator.  The oracle's generators and the library-side ones (laps_b200.synthetic: bench.py's
+    workload, the stand-in driver, the mode table of laps_set_primitive_modes) produce the same fields."""
+    from laps_b200 import synthetic
+    g = np.load(os.path.join(GOLD, "initial_conditions.npz"))
+    nx, ny, nz, Lx, Ly, Lz, bx0, by0, bz0 = g["params"]
+    nx, ny, nz = int(nx), int(ny), int(nz)
+    p = lo.Params(nx=nx, ny=ny, nz=nz, Lx=Lx, Ly=Ly, Lz=Lz)
+    # ipert = 7
+    prim = lo.ic_uniform_background(p, bx0=bx0, by0=by0, bz0=bz0, press0=1.0)
+    prim = lo.ic_turbulence(p, prim, bx0, by0, bz0, db0=0.1, dv0=0.1, drho0=0.01, nmodex=2, nmodey=2, nmodez=2, seeds=(101, 116, 132))
+    for v in range(8):
+        assert np.abs(prim[v] - g["ipert7"][v]).max() < 1e-14, v
+    slab = synthetic.turbulence_slab(nx, ny, nz, Lx, Ly, Lz, bx0=bx0, by0=by0, bz0=bz0, db0=0.1, dv0=0.1, drho0=0.01, kmax=2)
+    for v in range(8):
+        assert np.abs(slab[v] - g["ipert7"][v]).max() < 1e-13, v
+    part = synthetic.turbulence_slab(nx, ny, nz, Lx, Ly, Lz, z_offset=3, z_size=4, bx0=bx0, by0=by0, bz0=bz0, kmax=2)
+    assert np.abs(part - g["ipert7"][:, 3:7]).max() < 1e-13                 # a rank's z slab
+    # ipert = 1
+    prim = lo.ic_uniform_background(p, bx0=bx0, by0=by0, bz0=bz0, press0=1.0)
+    prim = lo.ic_alfven_wave(p, prim, db0=0.1, wave_number_jet=2, cor_angle=0.0)
+    assert np.abs(prim - g["ipert1"]).max() < 1e-15
+    prim2 = lo.ic_uniform_background(p, bx0=bx0, by0=by0, bz0=bz0, press0=1.0)
+    synthetic.add_alfven_wave(prim2, nx, Lx, db0=0.1, wave_number_jet=2, cor_angle=0.0)
+    assert np.abs(prim2 - g["ipert1"]).max() < 1e-15
