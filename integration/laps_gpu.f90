@@ -107,5 +107,57 @@ module laps_gpu
     integer(c_int) function laps_set_external_force(h, force_local) bind(C, name='laps_set_external_force')
       import; type(c_ptr), value :: h; real(c_double), intent(in) :: force_local(*)
     end function
+    ! ---- optional: fixed time step, synchronisation, diagnostics beyond the reference's, unit-level parity, measurement
+    integer(c_int) function laps_rkt_init(h, dt) bind(C, name='laps_rkt_init')          ! rktmod.f90:15-32 with a given dt
+      import; type(c_ptr), value :: h; real(c_double), value :: dt
+    end function
+    integer(c_int) function laps_sync(h) bind(C, name='laps_sync')
+      import; type(c_ptr), value :: h
+    end function
+    integer(c_int) function laps_get_stream(h, stream) bind(C, name='laps_get_stream')
+      import; type(c_ptr), value :: h; type(c_ptr), intent(out) :: stream
+    end function
+    integer(c_int) function laps_connect_local(handles, nranks) bind(C, name='laps_connect_local')   ! one process driving several GPUs
+      import; type(c_ptr), intent(inout) :: handles(*); integer(c_int32_t), value :: nranks
+    end function
+    integer(c_int) function laps_invariants(h, out3) bind(C, name='laps_invariants')    ! mean energy, mean u.B, max |k.B^|
+      import; type(c_ptr), value :: h; real(c_double), intent(out) :: out3(3)
+    end function
+    integer(c_int) function laps_get_spectral(h, uu_fourier_local) bind(C, name='laps_get_spectral')
+      import; type(c_ptr), value :: h; complex(c_double_complex), intent(out) :: uu_fourier_local(*)
+    end function
+    integer(c_int) function laps_fft_forward(h, real_fields, nfields, spec_out) bind(C, name='laps_fft_forward')   ! fftw.f90:42-71
+      import; type(c_ptr), value :: h; real(c_double), intent(in) :: real_fields(*); integer(c_int32_t), value :: nfields
+      complex(c_double_complex), intent(out) :: spec_out(*)
+    end function
+    integer(c_int) function laps_fft_inverse(h, spec_in, nfields, real_out) bind(C, name='laps_fft_inverse')      ! fftw.f90:73-103
+      import; type(c_ptr), value :: h; complex(c_double_complex), intent(in) :: spec_in(*); integer(c_int32_t), value :: nfields
+      real(c_double), intent(out) :: real_out(*)
+    end function
+    integer(c_int) function laps_transpose_yz_indexmap(h, pairs) bind(C, name='laps_transpose_yz_indexmap')    ! parallel.f90:273-297
+      import; type(c_ptr), value :: h; integer(c_int64_t), intent(out) :: pairs(2,*)
+    end function
+    integer(c_int) function laps_transpose_zy_indexmap(h, pairs) bind(C, name='laps_transpose_zy_indexmap')    ! parallel.f90:300-324
+      import; type(c_ptr), value :: h; integer(c_int64_t), intent(out) :: pairs(2,*)
+    end function
+    integer(c_int) function laps_get_pruning(h, nkx, kymax, nky_local) bind(C, name='laps_get_pruning')
+      import; type(c_ptr), value :: h; integer(c_int32_t), intent(out) :: nkx, kymax, nky_local
+    end function
+    integer(c_int) function laps_get_pruning_counts(h, live_columns, live_modes) bind(C, name='laps_get_pruning_counts')
+      import; type(c_ptr), value :: h; integer(c_int64_t), intent(out) :: live_columns, live_modes
+    end function
+    integer(c_int) function laps_get_field_counts(h, nf, ni, spec_rows) bind(C, name='laps_get_field_counts')
+      import; type(c_ptr), value :: h; integer(c_int32_t), intent(out) :: nf, ni, spec_rows
+    end function
+    integer(c_int) function laps_last_step_ms(h, ms, launches) bind(C, name='laps_last_step_ms')
+      import; type(c_ptr), value :: h; real(c_float), intent(out) :: ms; integer(c_int32_t), intent(out) :: launches
+    end function
+    integer(c_int) function laps_set_profiling(h, on) bind(C, name='laps_set_profiling')
+      import; type(c_ptr), value :: h; integer(c_int32_t), value :: on
+    end function
+    integer(c_int) function laps_get_profile(h, names, ms, cap, count) bind(C, name='laps_get_profile')
+      import; type(c_ptr), value :: h; character(kind=c_char), intent(out) :: names(32,*); real(c_float), intent(out) :: ms(*)
+      integer(c_int32_t), value :: cap; integer(c_int32_t), intent(out) :: count
+    end function
   end interface
 end module laps_gpu

@@ -77,3 +77,13 @@ def test_package_has_no_reference_to_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_fortran_interface_module_binds_every_symbol_of_the_header():
+    """integration/laps_gpu.f90 (the ISO_C_BINDING module a LAPS driver would use) has a bind(C) interface for every
+    entry point include/laps_b200.h declares."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    f90 = open(os.path.join(root, "integration", "laps_gpu.f90")).read()
+    bound = set(re.findall(r"bind\(C,\s*name='(\w+)'\)", f90))
+    assert set(capi.SYMBOLS) <= bound, sorted(set(capi.SYMBOLS) - bound)
