@@ -33,6 +33,9 @@ CASES = {
                           if_resis=True, if_resis_exp=False, if_visc=True, if_visc_exp=False, if_conserve_background=False),
     "corot_filter_explicit": dict(nx=16, ny=32, nz=8, if_hall=True, if_aeb=True, if_corotating=True, dealias_option=2,
                                   if_resis=True, if_resis_exp=True, if_visc=True, if_visc_exp=True, if_conserve_background=True),
+    # plain MHD: no Hall term, no expanding box, no dealiasing (the library then does the reference's 19 transforms)
+    "plain_nodealias": dict(nx=16, ny=16, nz=16, if_hall=False, if_aeb=False, if_corotating=False, dealias_option=0,
+                            if_resis=True, if_resis_exp=False, if_visc=True, if_visc_exp=False, if_conserve_background=False),
 }
 # src_incompressible: pressure projection, J and grad u, update_rho_p
 CASES_INCOMPRESSIBLE = {
@@ -40,6 +43,9 @@ CASES_INCOMPRESSIBLE = {
                                  if_resis=True, if_resis_exp=False, if_visc=True, if_visc_exp=False, if_conserve_background=False),
     "incomp_corot_filter_explicit": dict(nx=32, ny=16, nz=8, if_hall=True, if_aeb=True, if_corotating=True, dealias_option=2,
                                          if_resis=True, if_resis_exp=True, if_visc=True, if_visc_exp=True, if_conserve_background=True),
+    # no dealiasing: the spectrum is re-derived from the real fields at the start of every stage (mhd.f90:325), which matters here
+    "incomp_plain_nodealias": dict(nx=16, ny=16, nz=16, if_hall=False, if_aeb=False, if_corotating=False, dealias_option=0,
+                                   if_resis=True, if_resis_exp=False, if_visc=True, if_visc_exp=False, if_conserve_background=False),
 }
 
 
@@ -158,7 +164,7 @@ def run_case_incompressible(name, c, nsteps=2, pieces=True):
         ang = ns["corotating_angle"] if ns["if_corotating"] else 0.0
         ns["cos_cor_ang"], ns["sin_cor_ang"] = float(np.cos(ang)), float(np.sin(ang))
     else:
-        ns["ur0"] = 0.0
+        ns["ur0"] = np.float64(0.0)                    # mhd.f90:88-90; tau_exp = r / Ur is then Inf as in IEEE Fortran, and unused
     st["uu"][...] = prim
     ns["initial_calc_conserve_variable"]()
     ns["transform_uu_real_to_fourier"]()
@@ -539,7 +545,7 @@ def run_case(name, c, nsteps=2, pieces=True):
         ang = ns["corotating_angle"] if ns["if_corotating"] else 0.0
         ns["cos_cor_ang"], ns["sin_cor_ang"] = float(np.cos(ang)), float(np.sin(ang))
     else:
-        ns["ur0"] = 0.0
+        ns["ur0"] = np.float64(0.0)                    # mhd.f90:88-90; tau_exp = r / Ur is then Inf as in IEEE Fortran, and unused
     st["uu"][...] = prim
     ns["initial_calc_conserve_variable"]()             # mhd.f90:121
     ns["transform_uu_real_to_fourier"]()               # :122

@@ -274,7 +274,7 @@ def test_eight_point_lines():
     pc.check_eight_point_lines()
 
 
-@pytest.mark.parametrize("name", ["hall_aeb_mask", "corot_filter_explicit"])
+@pytest.mark.parametrize("name", ["hall_aeb_mask", "corot_filter_explicit", "plain_nodealias"])
 def test_library_agrees_with_the_executed_reference_source(name):
     """Golden vectors made by executing the reference's own Fortran source (tests/golden/make_ref_exec_fixtures.py):
     two steps of the Principal loop, fields within 1e-11 relative L2."""
@@ -282,7 +282,7 @@ def test_library_agrees_with_the_executed_reference_source(name):
     rp.check_library(name)
 
 
-@pytest.mark.parametrize("name", ["incomp_hall_aeb_mask", "incomp_corot_filter_explicit"])
+@pytest.mark.parametrize("name", ["incomp_hall_aeb_mask", "incomp_corot_filter_explicit", "incomp_plain_nodealias"])
 def test_incompressible_library_agrees_with_the_executed_reference_source(name):
     import test_reference_source_pins as rp
     rp.check_library_incompressible(name)

@@ -15,8 +15,8 @@ import parity_common as pc  # noqa: E402
 from oracle import laps_oracle as lo  # noqa: E402
 
 GOLD = os.path.join(HERE, "golden", "ref_exec")
-CASES = ["hall_aeb_mask", "corot_filter_explicit"]
-CASES_INCOMPRESSIBLE = ["incomp_hall_aeb_mask", "incomp_corot_filter_explicit"]
+CASES = ["hall_aeb_mask", "corot_filter_explicit", "plain_nodealias"]
+CASES_INCOMPRESSIBLE = ["incomp_hall_aeb_mask", "incomp_corot_filter_explicit", "incomp_plain_nodealias"]
 CASES_INCOMPRESSIBLE_2D = ["i2d_hall_aeb_mask", "i2d_square_explicit_limit"]
 CASES_2D = ["c2d_hall_aeb_mask", "c2d_zradial_square_explicit", "c2d_external_force_filter"]
 
@@ -76,9 +76,9 @@ def test_oracle_agrees_with_the_executed_reference_source(name):
         assert pc.rel_l2(o.uu_prim[v], g["uu_prim"][v]) < 1e-12, v
     assert np.allclose(np.broadcast_to(o.k_square, g["k_square"].shape), g["k_square"], rtol=1e-14, atol=0)   # update_ksquare
     # diagnostics: calc_max_divB (mhd.f90:522-570), calc_rms (mhdrms.f90:53-126)
-    assert abs(o.calc_max_divB() - float(g["max_divb"])) <= 1e-9 * float(g["max_divb"])
+    assert abs(o.calc_max_divB() - float(g["max_divb"])) <= max(1e-9 * float(g["max_divb"]), 1e-14)
     ave, rms, ru2 = o.calc_rms()
-    assert np.allclose(ave, g["uu_ave"], rtol=1e-13, atol=1e-16)
+    assert np.allclose(ave, g["uu_ave"], rtol=1e-13, atol=1e-14)      # means that are zero up to summation round-off
     # <u^2> - <u>^2 cancels five digits for B_x (mean 0.88, variance 1e-5): the sequential Fortran sum and NumPy's
     # pairwise sum differ at 1e-13 before the subtraction
     assert np.allclose(rms, g["uu_rms"], rtol=1e-7, atol=1e-17)
@@ -181,9 +181,9 @@ def test_2d_oracle_agrees_with_the_executed_reference_source(name):
         assert pc.rel_l2(o.uu[v], g["uu"][v]) < 1e-13, (v, pc.rel_l2(o.uu[v], g["uu"][v]))
         assert pc.rel_l2(o.uu_fourier[v], g["uu_fourier"][v]) < 1e-13, v
     assert np.allclose(np.broadcast_to(o.k_square, g["k_square"].shape), g["k_square"], rtol=1e-14, atol=0)
-    assert abs(o.calc_max_divB() - float(g["max_divb"])) <= 1e-9 * float(g["max_divb"])
+    assert abs(o.calc_max_divB() - float(g["max_divb"])) <= max(1e-9 * float(g["max_divb"]), 1e-14)
     ave, rms, ru2 = o.calc_rms()
-    assert np.allclose(ave, g["uu_ave"], rtol=1e-13, atol=1e-16)
+    assert np.allclose(ave, g["uu_ave"], rtol=1e-13, atol=1e-14)      # means that are zero up to summation round-off
     assert np.allclose(rms, g["uu_rms"], rtol=1e-7, atol=1e-17)
     assert np.allclose(ru2, g["rho_u2"], rtol=1e-12, atol=1e-20)
     assert int(g["isnanall"]) == 0
@@ -280,7 +280,7 @@ def check_library(name, lib_path=None, tol=1e-11):
             assert (g["uu_fourier"][0] == 0).mean() > 0.5
         for v in range(4):
             assert pc.rel_l2(prim[v], g["uu_prim"][v]) < 10 * tol, v
-        assert abs(s.calc_max_divB() - float(g["max_divb"])) <= 1e-7 * float(g["max_divb"])
+        assert abs(s.calc_max_divB() - float(g["max_divb"])) <= max(1e-7 * float(g["max_divb"]), 1e-13)   # round-off sized without the box
         ave, rms, ru2 = s.calc_rms()
         assert np.allclose(ave, g["uu_ave"], rtol=1e-9, atol=1e-12)
         assert np.allclose(rms, g["uu_rms"], rtol=1e-7, atol=1e-15)      # cancellation, see above
