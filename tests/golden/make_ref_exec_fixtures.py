@@ -210,7 +210,7 @@ def run_case_incompressible(name, c, nsteps=2, pieces=True):
     # (mhdinit.f90:5) — out of bounds, undefined in the reference itself (the translator's bounds check stops there)
     out["switches"] = np.array([c[k] for k in sorted(c)], dtype=np.float64)
     out["switch_names"] = np.array(sorted(c))
-    np.savez_compressed(os.path.join(HERE, "ref_exec", name + ".npz"), **out)
+    save_case(name, out, pieces)
     print(name, "dt", dts, "max_divV", out["max_divv"], "rho0", rho0s)
 
 
@@ -306,7 +306,7 @@ def run_case_2d(name, c, nsteps=3, pieces=True):
                isnanall=ns["isnanall"])
     out["switches"] = np.array([c[k] for k in sorted(c)], dtype=np.float64)
     out["switch_names"] = np.array(sorted(c))
-    np.savez_compressed(os.path.join(HERE, "ref_exec", name + ".npz"), **out)
+    save_case(name, out, pieces)
     print(name, "dt", dts, "max_divB", ns["max_divb"], "isNanAll", ns["isnanall"])
 
 
@@ -321,7 +321,7 @@ CASES_INCOMPRESSIBLE_2D = {
 }
 
 
-def run_case_incompressible_2d(name, c, nsteps=3):
+def run_case_incompressible_2d(name, c, nsteps=3, pieces=False):
     """src_incompressible/2D/mhd.f90 on one rank (vardt after every step, as in run_case_2d)."""
     R = REFROOT + "/src_incompressible/2D"
     nx, ny = c["nx"], c["ny"]
@@ -375,7 +375,7 @@ def run_case_incompressible_2d(name, c, nsteps=3):
     out["isnanall"] = ns["isnanall"]
     out["switches"] = np.array([c[k] for k in sorted(c)], dtype=np.float64)
     out["switch_names"] = np.array(sorted(c))
-    np.savez_compressed(os.path.join(HERE, "ref_exec", name + ".npz"), **out)
+    save_case(name, out, pieces)
     print(name, "dt", dts, "max_divV", out["max_divv"], "rho0", rho0s)
 
 
@@ -520,6 +520,14 @@ def make_parallel_fixtures():
     print("parallel_start:", len(out), "arrays")
 
 
+def save_case(name, out, pieces):
+    """The initial spectrum and the k_square tables are oracle-only checks: kept with the stage pieces, dropped elsewhere."""
+    if not pieces:
+        for k in ("uu_fourier0", "k_square0", "k_square"):
+            out.pop(k, None)
+    np.savez_compressed(os.path.join(HERE, "ref_exec", name + ".npz"), **out)
+
+
 def initial_primitive(c, seed=5):
     """Smooth O(1) primitive fields (rho, u, B, p) with content in every direction, [8, nz, ny, nx]."""
     import parity_common as pc
@@ -580,7 +588,7 @@ def run_case(name, c, nsteps=2, pieces=True):
     out["switches"] = np.array([c[k] for k in sorted(c)], dtype=np.float64)
     out["switch_names"] = np.array(sorted(c))
     os.makedirs(os.path.join(HERE, "ref_exec"), exist_ok=True)
-    np.savez_compressed(os.path.join(HERE, "ref_exec", name + ".npz"), **out)
+    save_case(name, out, pieces)
     print(name, "dt", dts, "max_divB", ns["max_divb"])
 
 

@@ -48,10 +48,12 @@ def test_oracle_agrees_with_the_executed_reference_source(name):
     o = lo.State(p)
     # grid_initialize (mhdinit.f90:58-124): wave numbers with the Nyquist kept positive, k_square
     assert np.array_equal(g["wave_numbers"], np.concatenate([o.g.wnx, o.g.wny, o.g.wnz]))
-    assert np.allclose(g["k_square0"], np.broadcast_to(o.k_square, g["k_square0"].shape), rtol=1e-15, atol=0)
+    if "k_square0" in g.files:
+        assert np.allclose(g["k_square0"], np.broadcast_to(o.k_square, g["k_square0"].shape), rtol=1e-15, atol=0)
     # initial_calc_conserve_variable + transform_uu_real_to_fourier (mhd.f90:121-122)
     o.set_primitive(g["prim0"])
-    assert pc.rel_l2(o.uu_fourier, g["uu_fourier0"]) < 1e-14
+    if "uu_fourier0" in g.files:
+        assert pc.rel_l2(o.uu_fourier, g["uu_fourier0"]) < 1e-14
     # vardt (mhd.f90:328-429)
     o.vardt()
     assert abs(o.dt - float(g["dt0"])) <= 1e-14 * o.dt
@@ -74,7 +76,8 @@ def test_oracle_agrees_with_the_executed_reference_source(name):
         assert pc.rel_l2(o.uu_fourier[v], g["uu_fourier"][v]) < 1e-13, v
     for v in range(4):
         assert pc.rel_l2(o.uu_prim[v], g["uu_prim"][v]) < 1e-12, v
-    assert np.allclose(np.broadcast_to(o.k_square, g["k_square"].shape), g["k_square"], rtol=1e-14, atol=0)   # update_ksquare
+    if "k_square" in g.files:
+        assert np.allclose(np.broadcast_to(o.k_square, g["k_square"].shape), g["k_square"], rtol=1e-14, atol=0)   # update_ksquare
     # diagnostics: calc_max_divB (mhd.f90:522-570), calc_rms (mhdrms.f90:53-126)
     assert abs(o.calc_max_divB() - float(g["max_divb"])) <= max(1e-9 * float(g["max_divb"]), 1e-14)
     ave, rms, ru2 = o.calc_rms()
@@ -92,7 +95,8 @@ def test_incompressible_oracle_agrees_with_the_executed_reference_source(name):
     g, p = load_case(name)
     o = lo.StateIncompressible(p)
     o.set_primitive(g["prim0"])
-    assert pc.rel_l2(o.uu_fourier, g["uu_fourier0"]) < 1e-14
+    if "uu_fourier0" in g.files:
+        assert pc.rel_l2(o.uu_fourier, g["uu_fourier0"]) < 1e-14
     o.vardt()
     assert abs(o.dt - float(g["dt0"])) <= 1e-14 * o.dt
     if "fnl_stage1" in g.files:
@@ -159,7 +163,8 @@ def test_2d_oracle_agrees_with_the_executed_reference_source(name):
     g, p = load_case(name)
     o = lo.State2D(p)
     o.set_primitive(g["prim0"])
-    assert pc.rel_l2(o.uu_fourier, g["uu_fourier0"]) < 1e-14
+    if "uu_fourier0" in g.files:
+        assert pc.rel_l2(o.uu_fourier, g["uu_fourier0"]) < 1e-14
     o.vardt()
     assert abs(o.dt - float(g["dt0"])) <= 1e-14 * o.dt
     if "flux_stage1" in g.files:
@@ -180,7 +185,8 @@ def test_2d_oracle_agrees_with_the_executed_reference_source(name):
     for v in range(8):
         assert pc.rel_l2(o.uu[v], g["uu"][v]) < 1e-13, (v, pc.rel_l2(o.uu[v], g["uu"][v]))
         assert pc.rel_l2(o.uu_fourier[v], g["uu_fourier"][v]) < 1e-13, v
-    assert np.allclose(np.broadcast_to(o.k_square, g["k_square"].shape), g["k_square"], rtol=1e-14, atol=0)
+    if "k_square" in g.files:
+        assert np.allclose(np.broadcast_to(o.k_square, g["k_square"].shape), g["k_square"], rtol=1e-14, atol=0)
     assert abs(o.calc_max_divB() - float(g["max_divb"])) <= max(1e-9 * float(g["max_divb"]), 1e-14)
     ave, rms, ru2 = o.calc_rms()
     assert np.allclose(ave, g["uu_ave"], rtol=1e-13, atol=1e-14)      # means that are zero up to summation round-off
@@ -215,7 +221,8 @@ def test_incompressible_2d_oracle_agrees_with_the_executed_reference_source(name
     g, p = load_case(name)
     o = lo.StateIncompressible2D(p)
     o.set_primitive(g["prim0"])
-    assert pc.rel_l2(o.uu_fourier, g["uu_fourier0"]) < 1e-14
+    if "uu_fourier0" in g.files:
+        assert pc.rel_l2(o.uu_fourier, g["uu_fourier0"]) < 1e-14
     o.vardt()
     assert abs(o.dt - float(g["dt0"])) <= 1e-14 * o.dt
     for i in range(len(g["dt"])):
@@ -264,7 +271,8 @@ def check_library(name, lib_path=None, tol=1e-11):
     g, p = load_case(name)
     with Solver(lib_path, **pc.solver_kwargs(p)) as s:
         s.set_primitive(g["prim0"])
-        assert pc.rel_l2(s.uu_fourier(), g["uu_fourier0"]) < 1e-13
+        if "uu_fourier0" in g.files:
+            assert pc.rel_l2(s.uu_fourier(), g["uu_fourier0"]) < 1e-13
         s.vardt()
         assert abs(s.dt - float(g["dt0"])) <= 1e-13 * s.dt
         for i in range(len(g["dt"])):
