@@ -475,3 +475,43 @@ def test_initial_conditions_against_the_executed_reference_source():
     prim2 = lo.ic_uniform_background(p, bx0=bx0, by0=by0, bz0=bz0, press0=1.0)
     synthetic.add_alfven_wave(prim2, nx, Lx, db0=0.1, wave_number_jet=2, cor_angle=0.0)
     assert np.abs(prim2 - g["ipert1"]).max() < 1e-15
+
+
+def test_the_pins_are_live_a_changed_reference_source_changes_the_vectors(tmp_path):
+    """Sanity of the method (needs /root/reference, skipped elsewhere): the golden vectors come from the Fortran text itself
+    — re-running calc_rhs from a copy of mhdrhs.f90 in which one expanding-box coefficient is altered (3.0 -> 2.0 in the
+    rho u_y row, mhdrhs.f90:239) moves fnl(3) away from the stored vector, while the unaltered text reproduces it bit for bit."""
+    ref = "/root/reference/src_compressible/mhdrhs.f90"
+    if not os.path.exists(ref):
+        pytest.skip("/root/reference absent")
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_ref_exec_fixtures as m
+    from oracle import fortran_exec as fx
+    name = "corot_filter_explicit"
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    text = open(ref).read()
+    target = "fnl(ix,iy,iz,3) = fnl(ix,iy,iz,3) - 3.0 * uu_fourier(ix,iy,iz,3) / tau_exp"
+    assert text.count(target) == 1
+    (tmp_path / "mhdrhs.f90").write_text(text.replace(target, target.replace("3.0", "2.0")))
+    results = []
+    for path in (ref, str(tmp_path / "mhdrhs.f90")):
+        c = m.CASES[name]
+        ns = m.build_namespace(c)
+        m.load_reference(ns)
+        fx.load(ns, path, ["calc_rhs"])                      # calc_rhs from this text
+        st = ns["_storage"]
+        ns["grid_initialize"]()
+        ns["dealias_initialize"]()
+        ns["aeb_calc"](ns["radius"])
+        ns["cos_cor_ang"], ns["sin_cor_ang"] = float(np.cos(0.3)), float(np.sin(0.3))
+        st["uu"][...] = g["prim0"]
+        ns["initial_calc_conserve_variable"]()
+        ns["transform_uu_real_to_fourier"]()
+        ns["vardt"]()
+        ns["calc_flux"]()
+        ns["transform_flux_real_to_fourier"]()
+        ns["calc_rhs"]()
+        results.append(st["fnl"].copy())
+    assert np.array_equal(results[0], g["fnl_stage1"])                                   # the reference's text: the stored vector
+    assert pc.rel_l2(results[1][2], g["fnl_stage1"][2]) > 1e-3                            # the altered text: not
+    assert np.array_equal(results[1][[0, 1, 3, 4, 5, 6, 7]], g["fnl_stage1"][[0, 1, 3, 4, 5, 6, 7]])
