@@ -88,7 +88,6 @@ struct laps_solver {
 
   double* uu = nullptr;   // [8][npts] conserved
   double* J = nullptr;    // [3][npts]
-  double* prim = nullptr; // [4][npts] scratch for get_state
   double* ext = nullptr;  // [npts] external_force(:,:,1,1) of the 2D compressible tree (2D/mhdinit.f90:146-148)
   int ext_slot = -1;      // its forward-field slot (transformed with the fluxes, 2D/mhdrhs.f90:216-251)
   void* bufX = nullptr;   // F (real fluxes) | V2
@@ -118,8 +117,10 @@ struct laps_solver {
   // slab exchange (exchange.cuh): this rank's flag/mailbox block, the peers' mappings, the epoch
   XchgBlock* xblk = nullptr;
   XchgPeers xp;
-  unsigned long long epoch = 0;
+  unsigned long long epoch[kXchgChannels] = {0, 0, 0, 0};
   bool wired = false;
+  unsigned long long* h_abort = nullptr;   // pinned: the device writes the abort code here (exchange.cuh)
+  bool dead = false;                       // the slab exchange was aborted: every later call fails
   // Work skipped exactly (dealias option 1 / 3): every mode with kx >= nkx, or with kymax < ky < ny-kymax,
   // is zeroed by the mask at the end of each stage, so the passes of a stage neither compute nor
   // move those columns.  nkx = nxh and kymax = ny/2 mean "no pruning".
@@ -277,6 +278,45 @@ int check_launch(S* s, const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { s->err = std::string(what) + ": " + cudaGetErrorString(e); return 1; }
   return 0;
+}
+
+// Every entry point makes the handle's device current for the calling thread (a driver thread that owns several
+// handles, or a fresh thread, has another device current) and leaves it current, as cudaSetDevice itself would:
+// restoring "the previous device" would create a context on device 0 in every one-process-per-GPU rank that never
+// selected a device of its own.
+struct DeviceGuard {
+  bool ok = true;
+  explicit DeviceGuard(int device) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != device) ok = cudaSetDevice(device) == cudaSuccess;
+  }
+};
+#define LAPS_ENTER(S)                                                                           \
+  DeviceGuard guard_((S)->p.device);                                                            \
+  if (!guard_.ok) { (S)->err = "cudaSetDevice(" + std::to_string((S)->p.device) + ") failed"; return 1; } \
+  if ((S)->dead) { if ((S)->err.empty()) (S)->err = "the slab exchange of this handle was aborted"; return 1; }
+
+// The abort word of the slab exchange (exchange.cuh): checked after every host-side wait.
+int check_abort(S* s) {
+  if (!s->h_abort) return 0;
+  const unsigned long long code = *reinterpret_cast<volatile unsigned long long*>(s->h_abort);
+  if (code == 0) return 0;
+  const int who = (int)(code & 0xff) - 1;
+  const unsigned long long why = code >> 8;
+  s->dead = true;
+  s->err = std::string("slab exchange aborted: ") +
+           (why == kXchgTimeout ? "a wait for the peers' flags ran out of its budget (LAPS_XCHG_TIMEOUT_S) on rank " :
+            why == kXchgHostFailure ? "the host side failed between two collectives on rank " : "abort raised by rank ") +
+           std::to_string(who) + "; the state of every rank is undefined and the job must be torn down";
+  return 1;
+}
+// This rank cannot go on (an error between two collectives): release the peers, which would otherwise wait for it.
+void poison_peers(S* s) {
+  if (s->P > 1 && s->wired && !s->dead) {
+    LAPS_LAUNCH(k_xchg_abort, dim3(1), dim3(32), 0, s->stream, s->xp, kXchgHostFailure);
+    (void)cudaGetLastError();
+    s->dead = true;
+  }
 }
 
 // ---- pass launchers ---------------------------------------------------------------------------
@@ -502,6 +542,9 @@ cplx* buf_V2(S* s) { return (cplx*)s->bufX; }
 cplx* buf_W1(S* s) { return (cplx*)s->bufY; }
 cplx* buf_V1(S* s) { return (cplx*)s->bufY; }
 cplx* buf_W2(S* s) { return (cplx*)s->bufZ; }
+// uu_prim (4 real fields) for laps_get_state / laps_get_output: the flux work area is free between two API calls
+// (the real fluxes are dead once the forward x pass has run, which is stream-ordered before this use)
+double* prim_scratch(S* s) { return (double*)s->bufX; }
 
 void fill_zparams(S* s, ZParams& z, bool prune = false) {
   std::memset(&z, 0, sizeof(z));
@@ -577,9 +620,9 @@ int launch_current_tasks(S* s, const cplx* u, bool prune, bool want_j = true, in
 int host_barrier(S* s) {
   if (s->P > 1) {
     if (!s->wired) { s->err = "nranks > 1 but the ranks are not connected (laps_import_peer_blobs / laps_connect_local)"; return 1; }
-    ++s->epoch;
+    ++s->epoch[0];
     LaunchScope ls(s, "xchg_barrier");
-    LAPS_LAUNCH(k_xchg_barrier, dim3(1), dim3(32), 0, s->stream, s->xp, s->epoch);
+    LAPS_LAUNCH(k_xchg_barrier, dim3(1), dim3(32), 0, s->stream, s->xp, 0, s->epoch[0]);
     return check_launch(s, "k_xchg_barrier");
   }
   return 0;
@@ -863,8 +906,8 @@ int reduce_launch(S* s, int nrows, int op /*0 sum,1 min,2 max*/, double init) {
   LAPS_TRY(check_launch(s, "k_reduce_final"));
   if (s->P > 1) {  // mpi_allreduce (mhd.f90:419,567; mhdrms.f90:96,98,122), combined in rank order
     if (!s->wired) { s->err = "nranks > 1 but the ranks are not connected"; return 1; }
-    ++s->epoch;
-    LAPS_LAUNCH(k_xchg_allreduce, dim3(1), dim3(32), 0, s->stream, s->xp, s->epoch, s->d_scal, nrows, op);
+    ++s->epoch[0];
+    LAPS_LAUNCH(k_xchg_allreduce, dim3(1), dim3(32), 0, s->stream, s->xp, 0, s->epoch[0], s->d_scal, nrows, op);
     LAPS_TRY(check_launch(s, "k_xchg_allreduce"));
   }
   LAPS_CK(s, cudaMemcpyAsync(s->h_scal, s->d_scal, nrows * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
@@ -873,7 +916,7 @@ int reduce_launch(S* s, int nrows, int op /*0 sum,1 min,2 max*/, double init) {
 }
 int reduce_wait(S* s) {
   LAPS_CK(s, cudaEventSynchronize(s->ev_scal));
-  return 0;
+  return check_abort(s);
 }
 int reduce_final(S* s, int nrows, int op, double init) {
   LAPS_TRY(reduce_launch(s, nrows, op, init));
@@ -1040,6 +1083,8 @@ int laps_create(const laps_params* params, laps_handle* out) {
   if (!ok) return fail("device allocation failed (state + work buffers need about " +
                        std::to_string((s->bytesX + s->bytesY + s->bytesZ + 24 * s->csz * 16 + 11 * s->npts * 8) >> 20) + " MiB)");
   if (cudaMallocHost((void**)&s->h_scal, 64 * sizeof(double)) != cudaSuccess) return fail("cudaMallocHost failed");
+  if (cudaMallocHost((void**)&s->h_abort, 64) != cudaSuccess) return fail("cudaMallocHost failed");
+  std::memset(s->h_abort, 0, 64);
   if (s->ext && cudaMemsetAsync(s->ext, 0, s->npts * sizeof(double), s->stream) != cudaSuccess) return fail("cudaMemsetAsync failed");
   {
     double* t = s->d_tab;
@@ -1172,6 +1217,13 @@ int laps_create(const laps_params* params, laps_handle* out) {
   std::memset(s->ipc_opened, 0, sizeof(s->ipc_opened));
   s->xp.rank = s->rank; s->xp.nranks = s->P;
   s->xp.blk[s->rank] = s->xblk;
+  {  // budget of one inter-rank wait; a rank that exceeds it aborts the exchange on every rank (exchange.cuh)
+    double sec = 120.0;
+    if (const char* e = std::getenv("LAPS_XCHG_TIMEOUT_S")) sec = std::atof(e);
+    if (!(sec > 0.0)) sec = 120.0;
+    s->xp.timeout_ns = (unsigned long long)(sec * 1e9);
+    s->xp.host_abort = s->h_abort;
+  }
   if (cudaMemset(s->xblk, 0, sizeof(XchgBlock)) != cudaSuccess) return fail("cudaMemset failed");
   if (cudaStreamSynchronize(s->stream) != cudaSuccess) return fail("stream sync failed");
   *out = s;
@@ -1180,15 +1232,17 @@ int laps_create(const laps_params* params, laps_handle* out) {
 
 int laps_destroy(laps_handle s) {
   if (!s) return 0;
-  if (s->stream) cudaStreamSynchronize(s->stream);
+  DeviceGuard guard_(s->p.device);
+  if (s->stream) cudaStreamSynchronize(s->stream);   // bounded: the inter-rank waits time out (exchange.cuh)
   for (int q = 0; q < LAPS_MAX_RANKS; ++q)
     for (int j = 0; j < 3; ++j)
       if (s->ipc_opened[q][j]) cudaIpcCloseMemHandle(s->ipc_opened[q][j]);
   cudaFree(s->xblk);
-  cudaFree(s->uu); cudaFree(s->J); cudaFree(s->G); cudaFree(s->prim); cudaFree(s->ext); cudaFree(s->bufX); cudaFree(s->bufY); cudaFree(s->bufZ);
+  cudaFree(s->uu); cudaFree(s->J); cudaFree(s->G); cudaFree(s->ext); cudaFree(s->bufX); cudaFree(s->bufY); cudaFree(s->bufZ);
   cudaFree(s->uA); cudaFree(s->uB); cudaFree(s->rk); cudaFree(s->tw_x); cudaFree(s->tw_y); cudaFree(s->tw_z);
   cudaFree(s->d_tab); cudaFree(s->d_partial); cudaFree(s->d_scal); cudaFree(s->d_kymax_x); cudaFree(s->d_colmap);
   if (s->h_scal) cudaFreeHost(s->h_scal);
+  if (s->h_abort) cudaFreeHost(s->h_abort);
   for (auto& pe : s->prof) { cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1); }
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
@@ -1208,10 +1262,9 @@ int laps_get_extents(laps_handle s, laps_extents* e) {
   return 0;
 }
 
-int laps_sync(laps_handle s) {
-  if (!s) return 1;
+static int sync_body(laps_handle s) {
   LAPS_CK(s, cudaStreamSynchronize(s->stream));
-  return 0;
+  return check_abort(s);
 }
 
 int laps_get_stream(laps_handle s, void** stream_out) {
@@ -1222,7 +1275,7 @@ int laps_get_stream(laps_handle s, void** stream_out) {
 
 static int finish_set_primitive(laps_handle s);
 
-int laps_set_primitive(laps_handle s, const double* uu_local) {
+static int set_primitive_body(laps_handle s, const double* uu_local) {
   if (!s || !uu_local) return 1;
   s->front_ready = false;
   LAPS_CK(s, cudaMemcpyAsync(s->uu, uu_local, 8 * s->npts * sizeof(double), cudaMemcpyHostToDevice, s->stream));
@@ -1242,14 +1295,14 @@ static int finish_set_primitive(laps_handle s) {
   s->have_state = true;
   s->j_stale = true;
   LAPS_CK(s, cudaStreamSynchronize(s->stream));  // the caller may reuse uu_local
-  return 0;
+  return check_abort(s);
 }
 
 // Initial data given as a mode table instead of a host array: the reference's ipert = 6/7
 // hooks sum cosines point by point, O(modes x N^3) (mhdinit.f90:487-829); the same field is a sparse spectrum
 // and one inverse transform.  field_v(x) = background[v] + sum_m Re( coef[v][m] exp(i k_m . x) ), v = rho, u, B;
 // p = background[7].  k = integer wave vectors (ikx >= 0), coef = complex128 pairs [7][nmodes].
-int laps_set_primitive_modes(laps_handle s, int32_t nmodes, const int32_t* k, const double* coef, const double* background) {
+static int set_primitive_modes_body(laps_handle s, int32_t nmodes, const int32_t* k, const double* coef, const double* background) {
   if (!s || nmodes < 0 || (nmodes > 0 && (!k || !coef)) || !background) return 1;
   s->front_ready = false;
   const int NYr = s->two_d ? s->nz : s->ny;       // the driver's ny
@@ -1276,7 +1329,9 @@ int laps_set_primitive_modes(laps_handle s, int32_t nmodes, const int32_t* k, co
     // internal axes: 3D (kx, ky, kz); 2D tree (kx, 0, ky) — the line axis carries the driver's ky
     const int ky = s->two_d ? 0 : kyr, kz = s->two_d ? kyr : (ikz + s->nz) % s->nz;
     if (s->tabW2.owner(ky) != s->rank) continue;                // another rank owns this row
-    const double w = ikx > 0 ? 0.5 : 1.0;                      // the c2r x pass doubles kx > 0 and keeps Re of kx = 0
+    // the c2r x pass doubles 0 < kx < nx/2 and takes the real part of the kx = 0 and kx = nx/2 columns as they are:
+    // Re(c exp(i (ky y + kz z))) (-1)^ix is exactly the reference's cosine sampled at the Nyquist kx
+    const double w = (ikx > 0 && ikx < s->nx / 2) ? 0.5 : 1.0;
     cplx c8[8];
     for (int v = 0; v < 7; ++v) c8[v] = mk(w * coef[2 * ((size_t)v * nmodes + m)], w * coef[2 * ((size_t)v * nmodes + m) + 1]);
     c8[7] = mk(0.0, 0.0);
@@ -1286,10 +1341,12 @@ int laps_set_primitive_modes(laps_handle s, int32_t nmodes, const int32_t* k, co
   for (int v = 0; v < 8; ++v) val.insert(val.end(), rows[v].begin(), rows[v].end());
   LAPS_CK(s, cudaMemsetAsync(s->uB, 0, 8 * s->csz * sizeof(cplx), s->stream));
   long long* d_idx = nullptr; cplx* d_val = nullptr;
-  struct Release { long long*& a; cplx*& b; ~Release() { cudaFree(a); cudaFree(b); } } release{d_idx, d_val};   // also on the error returns
+  // stream-ordered temporaries (cudaFree would synchronise the whole device: ranks that share one device in a test
+  // would wait for each other's flag kernels); released also on the error returns
+  struct Release { long long*& a; cplx*& b; cudaStream_t st; ~Release() { if (a) cudaFreeAsync(a, st); if (b) cudaFreeAsync(b, st); } } release{d_idx, d_val, s->stream};
   if (nent > 0) {
-    LAPS_CK(s, cudaMalloc((void**)&d_idx, nent * sizeof(long long)));
-    LAPS_CK(s, cudaMalloc((void**)&d_val, (size_t)8 * nent * sizeof(cplx)));
+    LAPS_CK(s, cudaMallocAsync((void**)&d_idx, nent * sizeof(long long), s->stream));
+    LAPS_CK(s, cudaMallocAsync((void**)&d_val, (size_t)8 * nent * sizeof(cplx), s->stream));
     LAPS_CK(s, cudaMemcpyAsync(d_idx, idx.data(), nent * sizeof(long long), cudaMemcpyHostToDevice, s->stream));
     LAPS_CK(s, cudaMemcpyAsync(d_val, val.data(), (size_t)8 * nent * sizeof(cplx), cudaMemcpyHostToDevice, s->stream));
     LaunchScope ls(s, "scatter_modes");
@@ -1314,7 +1371,7 @@ int laps_set_primitive_modes(laps_handle s, int32_t nmodes, const int32_t* k, co
   return finish_set_primitive(s);
 }
 
-int laps_set_time(laps_handle s, double time) {  // AEBmod.f90:56-73
+static int set_time_body(laps_handle s, double time) {  // AEBmod.f90:56-73
   if (!s) return 1;
   s->front_ready = false;
   const double old = s->radius;
@@ -1364,7 +1421,7 @@ static int vardt_finish(laps_handle s, double* dt_inout) {
   return laps_rkt_init(s, dt);
 }
 
-int laps_vardt(laps_handle s, double* dt_inout) {  // mhd.f90:328-429
+static int vardt_body(laps_handle s, double* dt_inout) {  // mhd.f90:328-429
   if (!s || !dt_inout) return 1;
   LAPS_TRY(require_state(s));
   CflParams c;
@@ -1379,7 +1436,7 @@ int laps_vardt(laps_handle s, double* dt_inout) {  // mhd.f90:328-429
   return vardt_finish(s, dt_inout);
 }
 
-int laps_evolve(laps_handle s) {  // mhd.f90:298-326
+static int evolve_body(laps_handle s) {  // mhd.f90:298-326
   if (!s) return 1;
   LAPS_TRY(require_state(s));
   for (auto& pe : s->prof) { cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1); }
@@ -1396,7 +1453,7 @@ int laps_evolve(laps_handle s) {  // mhd.f90:298-326
   return 0;
 }
 
-int laps_step(laps_handle s, double* time_inout, double* dt_inout) {  // mhd.f90:245-248,285
+static int step_body(laps_handle s, double* time_inout, double* dt_inout) {  // mhd.f90:245-248,285
   if (!s || !time_inout || !dt_inout) return 1;
   LAPS_TRY(laps_evolve(s));
   *time_inout = *time_inout + s->dt;
@@ -1412,7 +1469,7 @@ int laps_step(laps_handle s, double* time_inout, double* dt_inout) {  // mhd.f90
   return vardt_finish(s, dt_inout);
 }
 
-int laps_last_step_ms(laps_handle s, float* ms, int32_t* launches) {
+static int last_step_ms_body(laps_handle s, float* ms, int32_t* launches) {
   if (!s) return 1;
   LAPS_CK(s, cudaEventSynchronize(s->ev1));
   if (ms) LAPS_CK(s, cudaEventElapsedTime(ms, s->ev0, s->ev1));
@@ -1445,7 +1502,7 @@ int laps_get_field_counts(laps_handle s, int32_t* nf, int32_t* ni, int32_t* spec
 
 int laps_set_profiling(laps_handle s, int32_t on) { if (!s) return 1; s->profiling = on != 0; return 0; }
 
-int laps_get_profile(laps_handle s, char* names, float* ms, int32_t cap, int32_t* count) {
+static int get_profile_body(laps_handle s, char* names, float* ms, int32_t cap, int32_t* count) {
   if (!s || !count) return 1;
   LAPS_CK(s, cudaStreamSynchronize(s->stream));
   int n = 0;
@@ -1478,13 +1535,13 @@ static int max_div_fourier(laps_handle s, int v0, double* out) {
   return 0;
 }
 
-int laps_max_divb(laps_handle s, double* out) {  // mhd.f90:522-570
+static int max_divb_body(laps_handle s, double* out) {  // mhd.f90:522-570
   if (!s || !out) return 1;
   LAPS_TRY(require_state(s));
   return max_div_fourier(s, 4, out);
 }
 
-int laps_max_divv(laps_handle s, double* out) {  // src_incompressible/mhd.f90:620-668: max |k . (rho u)^| / rho0
+static int max_divv_body(laps_handle s, double* out) {  // src_incompressible/mhd.f90:620-668: max |k . (rho u)^| / rho0
   if (!s || !out) return 1;
   LAPS_TRY(require_state(s));
   LAPS_TRY(max_div_fourier(s, 1, out));
@@ -1494,7 +1551,7 @@ int laps_max_divv(laps_handle s, double* out) {  // src_incompressible/mhd.f90:6
 
 // calc_divB_real + calc_max_divB_real, calc_divV_real + calc_max_divV_real
 // (src_incompressible/mhdrhs.f90:532-648, mhd.f90:672-732): maxima of |div B| and |div (rho u)/rho0| in REAL space.
-int laps_max_div_real(laps_handle s, double out[2]) {
+static int max_div_real_body(laps_handle s, double out[2]) {
   if (!s || !out) return 1;
   LAPS_TRY(require_state(s));
   s->front_ready = false;   // the work buffers are used as scratch
@@ -1527,7 +1584,7 @@ int laps_max_div_real(laps_handle s, double out[2]) {
 // external_force(ix,iy,1,1) of the 2D compressible tree: the user routine calc_external_force_real
 // (2D/mhdrhs.f90:480-531) stays in the driver, which hands its field over whenever it changes (it depends on
 // `time` only, i.e. once per step); every stage transforms it with the fluxes and adds it to fnl(7).
-int laps_set_external_force(laps_handle s, const double* force_local) {
+static int set_external_force_body(laps_handle s, const double* force_local) {
   if (!s || !force_local) return 1;
   if (s->ext_slot < 0) { s->err = "laps_set_external_force: the handle was created without if_external_force"; return 1; }
   LAPS_CK(s, cudaMemcpyAsync(s->ext, force_local, s->npts * sizeof(double), cudaMemcpyHostToDevice, s->stream));
@@ -1536,7 +1593,7 @@ int laps_set_external_force(laps_handle s, const double* force_local) {
 }
 
 // checkNan (2D/mhd.f90:563-591, src_incompressible/2D/mhd.f90:745-773): is any uu(ix,iy,iz,1:nvar) a NaN, on any rank.
-int laps_check_nan(laps_handle s, int32_t* is_nan) {
+static int check_nan_body(laps_handle s, int32_t* is_nan) {
   if (!s || !is_nan) return 1;
   LAPS_TRY(require_state(s));
   {
@@ -1566,7 +1623,7 @@ static int moments(laps_handle s, double sums[18]) {
   return 0;
 }
 
-int laps_rms(laps_handle s, double out[19]) {  // mhdrms.f90:53-126
+static int rms_body(laps_handle s, double out[19]) {  // mhdrms.f90:53-126
   if (!s || !out) return 1;
   LAPS_TRY(require_state(s));
   double sums[18];
@@ -1587,7 +1644,7 @@ int laps_rms(laps_handle s, double out[19]) {  // mhdrms.f90:53-126
   return 0;
 }
 
-int laps_invariants(laps_handle s, double out[3]) {
+static int invariants_body(laps_handle s, double out[3]) {
   if (!s || !out) return 1;
   LAPS_TRY(require_state(s));
   double sums[18];
@@ -1598,56 +1655,56 @@ int laps_invariants(laps_handle s, double out[3]) {
   return laps_max_divb(s, &out[2]);
 }
 
-int laps_get_state(laps_handle s, double* uu_local, double* uu_prim_local) {
+static int get_state_body(laps_handle s, double* uu_local, double* uu_prim_local) {
   if (!s) return 1;
   LAPS_TRY(require_state(s));
   if (uu_local) LAPS_CK(s, cudaMemcpyAsync(uu_local, s->uu, 8 * s->npts * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   if (uu_prim_local) {
-    if (!s->prim) LAPS_CK(s, cudaMalloc((void**)&s->prim, 4 * s->npts * sizeof(double)));
+    double* prim = prim_scratch(s);
     {
       LaunchScope ls(s, "cons_to_prim");
-      LAPS_LAUNCH(k_cons_to_prim, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, (const double*)s->uu, s->prim, s->npts, s->p.adiabatic_index, s->incomp ? 1 : 0);
+      LAPS_LAUNCH(k_cons_to_prim, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, (const double*)s->uu, prim, s->npts, s->p.adiabatic_index, s->incomp ? 1 : 0);
       LAPS_TRY(check_launch(s, "k_cons_to_prim"));
     }
-    LAPS_CK(s, cudaMemcpyAsync(uu_prim_local, s->prim, 4 * s->npts * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    LAPS_CK(s, cudaMemcpyAsync(uu_prim_local, prim, 4 * s->npts * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   }
   LAPS_CK(s, cudaStreamSynchronize(s->stream));
-  return 0;
+  return check_abort(s);
 }
 
 // The array output_uu writes (mhdoutput.f90:95-123): uu with rho u -> u and e -> p when output_primitive,
 // else the conserved uu.  One 8-field device->host copy instead of the 12 fields of laps_get_state.
-int laps_get_output(laps_handle s, double* out_local, int32_t primitive) {
+static int get_output_body(laps_handle s, double* out_local, int32_t primitive) {
   if (!s || !out_local) return 1;
   LAPS_TRY(require_state(s));
   const size_t fb = s->npts * sizeof(double);
   if (!primitive) {
     LAPS_CK(s, cudaMemcpyAsync(out_local, s->uu, 8 * fb, cudaMemcpyDeviceToHost, s->stream));
   } else {
-    if (!s->prim) LAPS_CK(s, cudaMalloc((void**)&s->prim, 4 * fb));
+    double* prim = prim_scratch(s);
     {
       LaunchScope ls(s, "cons_to_prim");
-      LAPS_LAUNCH(k_cons_to_prim, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, (const double*)s->uu, s->prim, s->npts, s->p.adiabatic_index, s->incomp ? 1 : 0);
+      LAPS_LAUNCH(k_cons_to_prim, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, (const double*)s->uu, prim, s->npts, s->p.adiabatic_index, s->incomp ? 1 : 0);
       LAPS_TRY(check_launch(s, "k_cons_to_prim"));
     }
     LAPS_CK(s, cudaMemcpyAsync(out_local, s->uu, fb, cudaMemcpyDeviceToHost, s->stream));                                 // rho
-    LAPS_CK(s, cudaMemcpyAsync(out_local + s->npts, s->prim, 3 * fb, cudaMemcpyDeviceToHost, s->stream));                  // u
+    LAPS_CK(s, cudaMemcpyAsync(out_local + s->npts, prim, 3 * fb, cudaMemcpyDeviceToHost, s->stream));                     // u
     LAPS_CK(s, cudaMemcpyAsync(out_local + 4 * s->npts, s->uu + 4 * s->npts, 3 * fb, cudaMemcpyDeviceToHost, s->stream)); // B
-    LAPS_CK(s, cudaMemcpyAsync(out_local + 7 * s->npts, s->prim + 3 * s->npts, fb, cudaMemcpyDeviceToHost, s->stream));   // p
+    LAPS_CK(s, cudaMemcpyAsync(out_local + 7 * s->npts, prim + 3 * s->npts, fb, cudaMemcpyDeviceToHost, s->stream));      // p
   }
   LAPS_CK(s, cudaStreamSynchronize(s->stream));
-  return 0;
+  return check_abort(s);
 }
 
-int laps_get_spectral(laps_handle s, double* out) {
+static int get_spectral_body(laps_handle s, double* out) {
   if (!s || !out) return 1;
   LAPS_TRY(require_state(s));
   LAPS_CK(s, cudaMemcpyAsync(out, s->uA, 8 * s->csz * sizeof(cplx), cudaMemcpyDeviceToHost, s->stream));
   LAPS_CK(s, cudaStreamSynchronize(s->stream));
-  return 0;
+  return check_abort(s);
 }
 
-int laps_fft_forward(laps_handle s, const double* real_fields, int32_t nfields, double* spec_out) {
+static int fft_forward_body(laps_handle s, const double* real_fields, int32_t nfields, double* spec_out) {
   if (!s || !real_fields || !spec_out) return 1;
   if (nfields < 1 || nfields > 8) { s->err = "laps_fft_forward: 1..8 fields per call"; return 1; }
   s->front_ready = false;   // the work buffers are used as scratch
@@ -1667,10 +1724,10 @@ int laps_fft_forward(laps_handle s, const double* real_fields, int32_t nfields, 
   LAPS_CK(s, cudaMemsetAsync(s->uB, 0, 8 * s->csz * sizeof(cplx), s->stream));   // u_B must keep its masked columns zero
   LAPS_CK(s, cudaStreamSynchronize(s->stream));
   LAPS_TRY(host_barrier(s));
-  return 0;
+  return check_abort(s);
 }
 
-int laps_fft_inverse(laps_handle s, const double* spec_in, int32_t nfields, double* real_out) {
+static int fft_inverse_body(laps_handle s, const double* spec_in, int32_t nfields, double* real_out) {
   if (!s || !spec_in || !real_out) return 1;
   if (nfields < 1 || nfields > 8) { s->err = "laps_fft_inverse: 1..8 fields per call"; return 1; }
   s->front_ready = false;   // the work buffers are used as scratch
@@ -1689,7 +1746,7 @@ int laps_fft_inverse(laps_handle s, const double* spec_in, int32_t nfields, doub
   if (!s->two_d) LAPS_TRY(inv_y(s, buf_V1(s), buf_V2(s), nfields, false));
   // bufX holds V2 (the x pass's input) and uu must stay untouched: the real fields go to a temporary buffer
   double* tmp = nullptr;
-  LAPS_CK(s, cudaMalloc((void**)&tmp, (size_t)nfields * s->npts * sizeof(double)));
+  LAPS_CK(s, cudaMallocAsync((void**)&tmp, (size_t)nfields * s->npts * sizeof(double), s->stream));
   RealDst d; std::memset(&d, 0, sizeof(d));
   for (int v = 0; v < nfields; ++v) d.ptr[v] = tmp + (size_t)v * s->npts;
   int rc = inv_x(s, s->two_d ? buf_V1(s) : buf_V2(s), d, nfields, false);
@@ -1698,8 +1755,8 @@ int laps_fft_inverse(laps_handle s, const double* spec_in, int32_t nfields, doub
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
     if (e != cudaSuccess) { s->err = std::string("laps_fft_inverse copy: ") + cudaGetErrorString(e); rc = 1; }
   }
-  cudaFree(tmp);
-  return rc;
+  cudaFreeAsync(tmp, s->stream);
+  return rc ? rc : check_abort(s);
 }
 
 int laps_transpose_yz_indexmap(laps_handle s, int64_t* out) {
@@ -1751,7 +1808,7 @@ int laps_export_peer_blob(laps_handle s, void* blob) {
   PeerBlob b; std::memset(&b, 0, sizeof(b));
   b.magic = kBlobMagic; b.rank = s->rank; b.nranks = s->P; b.device = s->p.device; b.pid = (int64_t)getpid();
   void* ptrs[3] = {s->bufY, s->bufZ, (void*)s->xblk};
-  LAPS_CK(s, cudaSetDevice(s->p.device));
+  LAPS_ENTER(s);
   for (int j = 0; j < 3; ++j) {
     b.ptr[j] = (uint64_t)(uintptr_t)ptrs[j];
     LAPS_CK(s, cudaIpcGetMemHandle(&b.ipc[j], ptrs[j]));
@@ -1763,7 +1820,7 @@ int laps_export_peer_blob(laps_handle s, void* blob) {
 
 int laps_import_peer_blobs(laps_handle s, const void* blobs) {
   if (!s || !blobs) return 1;
-  LAPS_CK(s, cudaSetDevice(s->p.device));
+  LAPS_ENTER(s);
   for (int q = 0; q < s->P; ++q) {
     if (q == s->rank) continue;
     PeerBlob b;
@@ -1806,6 +1863,160 @@ int laps_connect_local(laps_handle* handles, int32_t nranks) {
   }
   for (int q = 0; q < nranks; ++q) LAPS_TRY(laps_import_peer_blobs(handles[q], blobs.data()));
   return 0;
+}
+
+// ---- entry points whose bodies are above: device selection, dead-handle check, and (collectives) release of the
+// peers when this rank fails between two inter-rank waits
+int laps_set_primitive(laps_handle s, const double* uu_local) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  const int rc = set_primitive_body(s, uu_local);
+  if (rc) poison_peers(s);
+  return rc;
+}
+
+int laps_set_primitive_modes(laps_handle s, int32_t nmodes, const int32_t* k, const double* coef, const double* background) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  const int rc = set_primitive_modes_body(s, nmodes, k, coef, background);
+  if (rc) poison_peers(s);
+  return rc;
+}
+
+int laps_vardt(laps_handle s, double* dt_inout) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  const int rc = vardt_body(s, dt_inout);
+  if (rc) poison_peers(s);
+  return rc;
+}
+
+int laps_evolve(laps_handle s) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  const int rc = evolve_body(s);
+  if (rc) poison_peers(s);
+  return rc;
+}
+
+int laps_step(laps_handle s, double* time_inout, double* dt_inout) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  const int rc = step_body(s, time_inout, dt_inout);
+  if (rc) poison_peers(s);
+  return rc;
+}
+
+int laps_max_divb(laps_handle s, double* out) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  const int rc = max_divb_body(s, out);
+  if (rc) poison_peers(s);
+  return rc;
+}
+
+int laps_max_divv(laps_handle s, double* out) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  const int rc = max_divv_body(s, out);
+  if (rc) poison_peers(s);
+  return rc;
+}
+
+int laps_max_div_real(laps_handle s, double out[2]) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  const int rc = max_div_real_body(s, out);
+  if (rc) poison_peers(s);
+  return rc;
+}
+
+int laps_check_nan(laps_handle s, int32_t* is_nan) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  const int rc = check_nan_body(s, is_nan);
+  if (rc) poison_peers(s);
+  return rc;
+}
+
+int laps_rms(laps_handle s, double out[19]) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  const int rc = rms_body(s, out);
+  if (rc) poison_peers(s);
+  return rc;
+}
+
+int laps_invariants(laps_handle s, double out[3]) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  const int rc = invariants_body(s, out);
+  if (rc) poison_peers(s);
+  return rc;
+}
+
+int laps_fft_forward(laps_handle s, const double* real_fields, int32_t nfields, double* spec_out) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  const int rc = fft_forward_body(s, real_fields, nfields, spec_out);
+  if (rc) poison_peers(s);
+  return rc;
+}
+
+int laps_fft_inverse(laps_handle s, const double* spec_in, int32_t nfields, double* real_out) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  const int rc = fft_inverse_body(s, spec_in, nfields, real_out);
+  if (rc) poison_peers(s);
+  return rc;
+}
+
+int laps_sync(laps_handle s) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  return sync_body(s);
+}
+
+int laps_set_time(laps_handle s, double time) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  return set_time_body(s, time);
+}
+
+int laps_last_step_ms(laps_handle s, float* ms, int32_t* launches) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  return last_step_ms_body(s, ms, launches);
+}
+
+int laps_get_profile(laps_handle s, char* names, float* ms, int32_t cap, int32_t* count) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  return get_profile_body(s, names, ms, cap, count);
+}
+
+int laps_set_external_force(laps_handle s, const double* force_local) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  return set_external_force_body(s, force_local);
+}
+
+int laps_get_state(laps_handle s, double* uu_local, double* uu_prim_local) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  return get_state_body(s, uu_local, uu_prim_local);
+}
+
+int laps_get_output(laps_handle s, double* out_local, int32_t primitive) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  return get_output_body(s, out_local, primitive);
+}
+
+int laps_get_spectral(laps_handle s, double* out) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  return get_spectral_body(s, out);
 }
 
 }  // extern "C"

@@ -104,7 +104,10 @@ struct ZTile {
   // resident CTAs per SM to compile for: what shared memory allows, but never below 80 registers
   static constexpr int BY_SMEM = (int)((227 * 1024) / (SMEM + 1024));
   static constexpr int BY_REGS = 65536 / (NTHREADS * 80);
-  static constexpr int MINB = BY_SMEM < BY_REGS ? (BY_SMEM < 1 ? 1 : BY_SMEM) : (BY_REGS < 1 ? 1 : BY_REGS);
+  static constexpr int BY_THREADS = 2048 / NTHREADS;
+  static constexpr int M0 = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
+  static constexpr int M1 = M0 < BY_THREADS ? M0 : BY_THREADS;
+  static constexpr int MINB = M1 < 1 ? 1 : (M1 > 32 ? 32 : M1);
 };
 
 // memory column (kx * nyl + kyl) of compact column index cc; -1 past the end

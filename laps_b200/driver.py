@@ -73,16 +73,19 @@ def params_from_namelists(nl, rank=0, nranks=1, device=0, tree="compressible"):
 
 class Driver:
     def __init__(self, input_path="mhd.input", outdir=".", rank=0, nranks=1, device=0, lib_path=None, barrier=None,
-                 connect=None, tree="compressible"):
+                 connect=None, tree="compressible", bcast=None):
         self.nl = lapsio.read_namelists(input_path)
         self.tree = tree
         self.two_d = tree.endswith("2d")
         self.dstep_calcdt = 20 if self.two_d else 1          # 2D/mhd.f90:22,237-240: vardt every 20 steps
         self.dstep_checknan = 200 if self.two_d else 0       # 2D/mhd.f90:25,242-252: checkNan every 200 steps
+        self.dstep_checksave = 40                            # mhd.f90:20: look at the wall clock every 40 steps ...
+        self.delta_clocktime_output = 60.0 * 50.0            # mhd.f90:16: ... and dump out999.dat every 50 minutes of it
         self.stopped_on_nan = False
         self.outdir = outdir
         self.rank, self.nranks = rank, nranks
         self.barrier = barrier or (lambda: None)
+        self.bcast = bcast                                   # rank 0's integer to every rank (MPI_Bcast of mhd.f90:208)
         kw = params_from_namelists(self.nl, rank, nranks, device, tree)
         self.kw = kw
         g = lambda grp, key, d: _get(self.nl, grp, key, d)  # noqa: E731
@@ -221,9 +224,10 @@ class Driver:
             else:
                 lapsio.write_grid(self.path("grid.dat"), x, y, z)                                  # mhd.f90:139
                 lapsio.write_parallel_info(self.path("parallel_info.dat"), self.nranks, 1, self.nranks)   # :140
-            if not self.if_restart:
-                open(self.path("rms.dat"), "w").close()       # rms_initialize / AEB_initialize create or append
-                open(self.path("EBM_info.dat"), "w").close()
+            # rms_initialize / AEB_initialize (mhdrms.f90:29-36, AEBmod.f90:34-41): an existing file is opened for
+            # APPEND — a fresh run in a used directory adds to the old rows, as the reference does — else created
+            open(self.path("rms.dat"), "a").close()
+            open(self.path("EBM_info.dat"), "a").close()
         dtlog = min(self.dtout, self.dtrms) / 10.0            # mhd.f90:142-149
         iout = self.n_start
         tout, toutrms, tlog = self.time + self.dtout, self.time + self.dtrms, self.time + dtlog
@@ -234,6 +238,7 @@ class Driver:
             print("      OUTPUT RMS at time:  %10.4f, max(div B) = %10.2E, dt = %12.4E" % (self.time, max_divb, dt))
         self.output_rms()
         self.output_aeb()
+        clocktime_output = self.delta_clocktime_output        # mhd.f90:165-166
         while True:                                           # Principal, mhd.f90:169-287
             if self.time >= tout:
                 self.output_uu(iout)
@@ -246,6 +251,15 @@ class Driver:
                 self.output_rms()
                 self.output_aeb()
                 toutrms += self.dtrms
+            if self.istep > 0 and self.istep % self.dstep_checksave == 0:   # wall-clock backup dump, mhd.f90:194-214
+                save = (_time.perf_counter() - self.clock0) >= clocktime_output   # rank 0's clock decides (MPI_Bcast)
+                if self.bcast is not None:
+                    save = bool(self.bcast(int(save)))
+                if save:
+                    if echo and self.rank == 0:
+                        print("   OUTPUT for backup at real time (sec):%15.2f  , time =   %10.4f" % (_time.perf_counter() - self.clock0, self.time))
+                    self.output_uu(999)
+                    clocktime_output += self.delta_clocktime_output
             if dt < 1e-8:                                     # mhd.f90:205-228
                 self.output_uu(iout)
                 self.output_rms()
@@ -279,6 +293,12 @@ class Driver:
         self.write_log(dt)
         return self.istep
 
+    def close(self):
+        """parallel_end (mhd.f90:291-293): no rank may free its exchange buffers while a peer can still store into them."""
+        self.solver.sync()
+        self.barrier()
+        self.solver.close()
+
 
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
@@ -288,7 +308,7 @@ def main(argv=None):
     ap.add_argument("--tree", default="compressible", choices=TREES)
     args = ap.parse_args(argv)
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
-    barrier, connect = None, None
+    barrier, connect, bcast = None, None, None
     if world > 1:
         import torch
         import torch.distributed as dist
@@ -298,19 +318,22 @@ def main(argv=None):
         def barrier():
             dist.barrier()
 
+        def bcast(v):
+            t = torch.tensor([int(v)], device="cuda")
+            dist.broadcast(t, 0)
+            return int(t.item())
+
         def connect(g):
             blob = torch.from_numpy(np.frombuffer(g.export_peer_blob(), dtype=np.uint8).copy()).cuda()
             blobs = [torch.empty_like(blob) for _ in range(world)]
             dist.all_gather(blobs, blob)
             g.import_peer_blobs(b"".join(bytes(b.cpu().numpy().tobytes()) for b in blobs))
             dist.barrier()
-    d = Driver(args.input, args.outdir, rank, world, local, barrier=barrier, connect=connect, tree=args.tree)
+    d = Driver(args.input, args.outdir, rank, world, local, barrier=barrier, connect=connect, tree=args.tree, bcast=bcast)
     n = d.run(args.max_steps)
     if rank == 0:
         print(f"{n} steps, time = {d.time:.6f}")
-    if world > 1:
-        barrier()
-    d.solver.close()
+    d.close()
     return 0
 
 

@@ -73,6 +73,16 @@ class Solver:
         assert len(blobs) == capi.PEER_BLOB_BYTES * self.params.nranks
         self._ck(self._lib.laps_import_peer_blobs(self._h, C.create_string_buffer(blobs, len(blobs))))
 
+    @staticmethod
+    def connect_local(solvers):
+        """laps_connect_local: wire the handles of all ranks created in THIS process (ordered by rank) to each other.
+        Every handle must afterwards be driven by its own host thread (the collectives wait for each other)."""
+        arr = (C.c_void_p * len(solvers))(*[g._h for g in solvers])
+        rc = solvers[0]._lib.laps_connect_local(arr, len(solvers))
+        if rc:
+            msgs = [g._lib.laps_last_error(g._h).decode() for g in solvers]
+            raise capi.LapsError("laps_connect_local: " + "; ".join(m for m in msgs if m))
+
     # ------------------------------------------------------------------ driver-facing calls
     def set_primitive(self, prim: np.ndarray):
         """initial_calc_conserve_variable + transform_uu_real_to_fourier (mhd.f90:121-122)."""

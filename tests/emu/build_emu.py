@@ -9,8 +9,8 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 OUT = os.path.join(ROOT, "tests", "_build", "liblaps_emu.so")
 SRC = [os.path.join(ROOT, "laps_b200", "csrc", "solver.cu"), os.path.join(ROOT, "tests", "emu", "cuda_emu.cpp")]
-DEPS = SRC + [os.path.join(ROOT, "laps_b200", "csrc", f) for f in
-              ("compat.h", "exchange.cuh", "fft_core.cuh", "fft_passes.cuh", "spectral_z.cuh", "spectral_rhs.cuh", "spectral_incomp.cuh", "flux_fwd_x.cuh", "pointwise.cuh")] + [
+CSRC = os.path.join(ROOT, "laps_b200", "csrc")
+DEPS = SRC + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [
     os.path.join(ROOT, "tests", "emu", "cuda_emu.h"), os.path.join(ROOT, "include", "laps_b200.h")]
 
 

@@ -5,6 +5,7 @@
 #include <sched.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <map>
@@ -94,6 +95,11 @@ void* shm_import(const char name[64]) {
 void shm_unmap(void* p) { shm_free(p); }
 
 void spin_pause() { sched_yield(); }
+unsigned long long now_ns() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+}
 
 void yield_barrier() {
   int me = g_cur;

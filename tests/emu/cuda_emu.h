@@ -53,6 +53,7 @@ int shm_export(void* p, char name_out[64]);
 void* shm_import(const char name[64]);
 void shm_unmap(void* p);
 void spin_pause();
+unsigned long long now_ns();
 }  // namespace emu
 
 #define threadIdx (emu::g_threadIdx)
@@ -124,6 +125,8 @@ static inline cudaError_t cudaGetLastError() { return 0; }
 static inline cudaError_t cudaMalloc(void** p, size_t n) { *p = emu::shm_alloc(n ? n : 1); return *p ? 0 : 2; }
 template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
 static inline cudaError_t cudaFree(void* p) { emu::shm_free(p); return 0; }
+template <class T> static inline cudaError_t cudaMallocAsync(T** p, size_t n, cudaStream_t) { return cudaMalloc((void**)p, n); }
+static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { if (p) emu::shm_free(p); return 0; }
 static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { return emu::shm_export(p, h->reserved); }
 static inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { *p = emu::shm_import(h.reserved); return *p ? 0 : 2; }
 static inline cudaError_t cudaIpcCloseMemHandle(void* p) { emu::shm_unmap(p); return 0; }

@@ -1,0 +1,113 @@
+"""All ranks of a slab-decomposed run inside ONE process, one host thread per handle, wired with
+laps_connect_local (include/laps_b200.h) — the single-process multi-GPU mode of the boundary.  `devices` may name the
+same GPU for every rank: the peer stores then stay on one device, but the decomposition tables, the transpose index
+maps (contiguous ky slabs or round-robin rows), the device-side flag barriers and the allreduce are exactly those of
+an N-GPU run, so a box with a single GPU checks the multi-rank path against the single-grid oracle too.
+GPU only (the test-only kernel emulator is not thread-safe)."""
+import os
+import threading
+
+import numpy as np
+
+import parity_common as pc
+from laps_b200 import Solver
+
+
+class _Env:
+    def __init__(self, env):
+        self.env, self.saved = dict(env or {}), {}
+
+    def __enter__(self):
+        for k, v in self.env.items():
+            self.saved[k] = os.environ.get(k)
+            os.environ[k] = str(v)
+
+    def __exit__(self, *a):
+        for k, v in self.saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def make_solvers(world, p, devices=None, lib_path=None, env=None):
+    devices = list(devices) if devices is not None else [0] * world
+    base = {"LAPS_XCHG_TIMEOUT_S": os.environ.get("LAPS_XCHG_TIMEOUT_S", "30")}
+    base.update(env or {})
+    with _Env(base):
+        gs = [Solver(lib_path, rank=r, nranks=world, device=devices[r], **pc.solver_kwargs(p)) for r in range(world)]
+    Solver.connect_local(gs)
+    return gs
+
+
+def run_threads(gs, work):
+    """work(rank, solver) on one thread per handle; returns the list of results, re-raises the first failure."""
+    out, err = [None] * len(gs), [None] * len(gs)
+
+    def body(r):
+        try:
+            out[r] = work(r, gs[r])
+        except BaseException as e:  # noqa: BLE001 - reported below
+            err[r] = e
+
+    ts = [threading.Thread(target=body, args=(r,)) for r in range(len(gs))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for e in err:
+        if e is not None:
+            raise e
+    return out
+
+
+def run_local(world, shape, case, steps=2, devices=None, lib_path=None, env=None, incompressible=False, tol=1e-11,
+              expect_stride=None):
+    """`steps` Principal-loop steps on `world` ranks in this process against the single-grid oracle: fields and spectra
+    of every rank's slabs within `tol` (relative L2), dt and diagnostics identical on every rank."""
+    make = pc.make_case_incompressible if incompressible else pc.make_case
+    p, prim = make(*shape, **case)
+    o = pc.oracle_state(p)
+    o.set_primitive(prim)
+    o.vardt()
+    dt0 = o.dt
+    for _ in range(steps):
+        o.step()
+    gs = make_solvers(world, p, devices, lib_path, env)
+    if expect_stride is not None:
+        assert all(g.ext.y_stride == expect_stride for g in gs), [g.ext.y_stride for g in gs]
+
+    def work(r, g):
+        zo, zn = g.ext.z_offset, g.ext.z_size
+        g.set_primitive(prim[:, zo:zo + zn])
+        g.vardt()
+        d0 = g.dt
+        for _ in range(steps):
+            g.step()
+        uu, _ = g.get_state()
+        return dict(dt0=d0, dt=g.dt, uu=uu, uf=g.uu_fourier(), rms=np.concatenate(g.calc_rms()), inv=g.invariants(),
+                    nan=g.checkNan())
+
+    try:
+        res = run_threads(gs, work)
+        worst = 0.0
+        for r, (g, q) in enumerate(zip(gs, res)):
+            zo, zn, rows = g.ext.z_offset, g.ext.z_size, g.ky_rows
+            assert abs(q["dt0"] - dt0) <= 1e-13 * dt0 and abs(q["dt"] - o.dt) <= 1e-12 * o.dt, (q["dt0"], dt0, q["dt"], o.dt)
+            for v in range(8):
+                e = pc.rel_l2(q["uu"][v], o.uu[v, zo:zo + zn])
+                worst = max(worst, e)
+                assert e < tol, (r, v, e)
+                ref = o.uu_fourier[v][:, rows, :]
+                scale = max(1.0, np.linalg.norm(o.uu_fourier[v]) / max(np.linalg.norm(ref), 1e-300))
+                assert pc.rel_l2(q["uf"][v], ref) < tol * scale, (r, v)
+            assert not q["nan"]
+            assert np.array_equal(q["rms"], res[0]["rms"]) and np.array_equal(q["inv"], res[0]["inv"]) and q["dt"] == res[0]["dt"]
+        oave, orms, oru2 = o.calc_rms()
+        assert np.allclose(res[0]["rms"][:8], oave, rtol=1e-9, atol=1e-12)
+        assert np.allclose(res[0]["rms"][8:16], orms, rtol=1e-9, atol=1e-15)
+        assert abs(res[0]["inv"][0] - o.invariants()[0]) <= 1e-9 * abs(o.invariants()[0])
+        return worst
+    finally:
+        for g in gs:
+            g.close()

@@ -48,6 +48,23 @@ def main():
     g = Solver(lib, rank=rank, nranks=world, device=rank if backend == "nccl" else 0, **pc.solver_kwargs(p))
     connect(g, world, device)
     zo, zn, yo, yn = g.ext.z_offset, g.ext.z_size, g.ext.y_offset, g.ext.y_size
+    if cfg.get("absent_rank") is not None:
+        # A rank that never makes the matching collective call must not wedge its peers (exchange.cuh): the others give
+        # up after LAPS_XCHG_TIMEOUT_S with an error through laps_last_error, and their handles stay dead.
+        from laps_b200 import capi
+        if rank != cfg["absent_rank"]:
+            for _ in range(2):
+                try:
+                    g.set_primitive(prim[:, zo:zo + zn])
+                    raise SystemExit("the collective returned although a rank was absent")
+                except capi.LapsError as e:
+                    assert "slab exchange aborted" in str(e), str(e)
+        dist.barrier()
+        g.close()
+        dist.barrier()
+        dist.destroy_process_group()
+        print(f"rank {rank}/{world} ok")
+        return
     rows = g.ky_rows                      # this rank's Fourier rows (a contiguous slab unless LAPS_TUNE_CYCLIC=1)
     cyclic = g.ext.y_stride > 1
     if "expect_stride" in cfg:

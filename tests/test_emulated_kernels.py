@@ -171,6 +171,17 @@ def test_set_primitive_modes_equals_the_uploaded_field(emu):
     with Solver(emu, **kw) as d:
         with pytest.raises(Exception, match="outside the grid"):
             d.set_primitive_modes(np.array([[17, 0, 0]]), np.zeros((7, 1), dtype=complex), back)
+    # a mode on the Nyquist column kx = nx/2 (the stand-in driver's default nmodex = 8 on a 16-point grid): the
+    # reference's cosine sampled there, Re(c exp(i(ky y + kz z))) (-1)^ix, at FULL amplitude (the c2r pass does not
+    # double that column)
+    with Solver(emu, nx=16, ny=16, nz=16, Lx=1.0, Ly=1.0, Lz=1.0, dealias_option=0) as e:
+        c = np.zeros((7, 1), dtype=complex)
+        c[4, 0] = 0.2 * np.exp(0.7j)
+        e.set_primitive_modes(np.array([[8, 1, 0]]), c, [1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 1.0])
+        uu, _ = e.get_state()
+        j = np.arange(16)
+        want = 1.0 + (0.2 * np.exp(0.7j) * np.exp(2j * np.pi * j[:, None] / 16)).real * ((-1.0) ** j)[None, :]
+        assert np.abs(uu[4, 3] - want).max() < 1e-14
 
 
 @pytest.mark.parametrize("inc", [False, True])

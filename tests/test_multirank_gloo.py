@@ -111,3 +111,9 @@ def test_eight_ranks_default_path_whole_z_tiles(emu):
 def test_five_ranks_uneven_round_robin_rows(emu):
     # 64 rows over 5 ranks: 13, 13, 13, 13, 12 round-robin rows; z planes 12, 12, 12, 12, 16 (decompose_1d remainder)
     run_ranks(5, dict(lib=emu, shape=(32, 64, 32), case=dict(hall=True, aeb=True, dealias=1), steps=2, expect_stride=5), timeout=1200)
+
+
+def test_absent_rank_does_not_wedge_the_others(emu):
+    # rank 1 never calls the collective: ranks 0 and 2 must come back with an error inside the time budget
+    run_ranks(3, dict(lib=emu, shape=(16, 16, 16), case=dict(hall=True, aeb=True, dealias=1), absent_rank=1,
+                      env=dict(LAPS_XCHG_TIMEOUT_S="1.0")), timeout=120)
