@@ -2,28 +2,36 @@
 """Benchmark of the LAPS RK-step hot path (BASELINE.json: 512^3 compressible Hall-MHD + expanding
 box, grid-point-steps/s) on N B200s of one node, one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--n 512] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 1..5] [--n 512] [--impl reference]
 
 A "step" is one pass of the driver's Principal loop body (mhd.f90:245-248,285):
 evolve (3 RK stages) + evolve_radius + vardt, through the C ABI (include/laps_b200.h).
 
-value  : K steps with the state resident in HBM, CUDA events on the library's stream, max over ranks.
+parity : BEFORE anything is timed, every rank runs two steps of a 64^3 Hall-MHD + expanding-box case through the same
+         decomposition (N ranks, both Fourier-row ownership forms when N > 1) and compares its slabs with the CPU oracle
+         (relative L2 <= 1e-11); a failure ends the run with a non-zero exit code and no bench line.
+value  : K steps with the state resident in HBM, CUDA events on the library's stream, max over ranks; no per-launch
+         instrumentation inside this region.
 e2e    : a driver session through the same C ABI with HOST buffers inside the timed region:
          laps_set_primitive from pinned host memory (H2D + conversion + 8 forward FFTs), K steps
          (each reads dt back to the host), laps_get_output into pinned host memory (D2H of the 8-field
-         array output_uu writes) -- the traffic a LAPS driver generates between two outNNN.dat dumps.
-roofline: dominant kernel by device time (CUDA events around every launch, laps_set_profiling),
-         algorithmic bytes per launch as stated in DESIGN.md, against MEASURED_PEAKS.json.
+         array output_uu writes) -- the traffic a LAPS driver generates between two outNNN.dat dumps; the
+         h2d/d2h byte counts are those two copies spread over the K steps, not a per-step copy.
+roofline: a separate instrumented pass (CUDA events around every launch, laps_set_profiling) after the timed one:
+         dominant kernel by device time, algorithmic bytes per launch as the library states them
+         (laps_get_profile_bytes) against MEASURED_PEAKS.json; step_frac = the same for the
+         whole step (sum of algorithmic bytes / step time / peak).
 cpu_baseline / --impl reference: the CPU port (oracle/laps_cpu.c, a C + OpenMP restatement with the
          reference's structure, kind "port": the Fortran+MPI+FFTW reference cannot be built in this
-         image) on all host cores, on a 256^3 grid of the same physics (bounded sample), in
-         grid-point-steps/s.
+         image) on ALL host cores (whatever OMP_NUM_THREADS the launcher exported), on the workload's own grid when
+         the host has the memory for it (512^3 needs about 90 GB), else on a 256^3 sample, in grid-point-steps/s.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -37,6 +45,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "grid_point_steps_per_s"
 UNIT = "grid-point-steps/s"
+PARITY_TOL = 1e-11
 
 
 def workload_params(n):
@@ -50,6 +59,30 @@ def workload_params(n):
 
 def workload_name(n):
     return f"3D compressible Hall-MHD + expanding box {n}^3, FP64, RK3 step (src_compressible/mhd.input physics)"
+
+
+def config_spec(config, n_override=None):
+    """The five BASELINE.json configurations: (name, solver parameters, shape of one real field [nz, ny, nx], kwargs of
+    synthetic.turbulence_slab, number of grid points)."""
+    base = workload_params(64)
+    plain = dict(base, if_AEB=0, if_hall=0, ion_inertial_length=0.0, Ur0=0.0)
+    if config == 1:
+        n = n_override or 64
+        kw = dict(plain, nx=n, ny=n, nz=n)
+        return dict(name=f"config 1: 3D compressible MHD {n}^3 (src_compressible/mhd.input physics)", kw=kw, grid=(n, n, n), turb={})
+    if config == 2:
+        n = n_override or 2048
+        kw = dict(plain, nx=n, ny=n, nz=1, ndim=2, if_hall=1, ion_inertial_length=0.2)
+        return dict(name=f"config 2: 2D compressible Hall-MHD {n}^2 (src_compressible/2D)", kw=kw, grid=(n, n, 1), turb={})
+    if config == 3:
+        n = n_override or 256
+        kw = dict(plain, nx=n, ny=n, nz=n, incompressible=1, rho0=1.0)
+        return dict(name=f"config 3: 3D incompressible MHD {n}^3 decaying turbulence (src_incompressible)", kw=kw, grid=(n, n, n),
+                    turb=dict(drho0=0.0))
+    if config in (4, 5):
+        n = n_override or (512 if config == 4 else 1024)
+        return dict(name=workload_name(n), kw=workload_params(n), grid=(n, n, n), turb={})
+    raise SystemExit(f"unknown --config {config}")
 
 
 # ------------------------------------------------------------------------------------------
@@ -108,22 +141,25 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-# algorithmic bytes per launch of each kernel; R, C in bytes per field
+# algorithmic bytes per launch of each kernel; R, C in bytes per field.
+# The library reports the same figures per launch (laps_get_profile_bytes); this host-side model is what
+# tests/test_bench_model.py holds them to.
 # ------------------------------------------------------------------------------------------
-def kernel_bytes(name, R, C, nf, ni, hall, fx=1.0, fcol=1.0, fmode=1.0, mass=False):
+def kernel_bytes(name, R, C, nf, ni, hall, fx=1.0, fcol=1.0, fmode=1.0, mass=False, fcol_all=None):
     """Algorithmic HBM bytes of one launch.  Pass launches carry their field
     count in the name (fwd_x13, inv_y11, inv_y3 ...).  fx = fraction of the kx columns that survive
     the dealiasing mask, fcol = fraction of this rank's (kx, ky) columns, fmode = fraction of its
     (kx, ky, kz) modes (laps_get_pruning, laps_get_pruning_counts): the passes skip the rest exactly.
-    mass: the continuity row takes its fluxes from the state (laps_get_field_counts) and runs inside
-    the curl_b_inv_z launch instead of the spec_z one."""
-    import re
+    fcol_all = surviving fraction of the (kx, ky) columns of ALL ranks (what the y passes of this rank's z slab
+    visit; equal to fcol on one rank).  mass: the continuity row takes its fluxes from the state
+    (laps_get_field_counts) and runs inside the curl_b_inv_z launch instead of the spec_z one."""
     rows = 7 if mass else 8
+    fy = fcol if fcol_all is None else fcol_all
     m = re.fullmatch(r"(fwd_x|fwd_y|inv_y|inv_x)(\d+)", name)
     if m:
         k, n = m.group(1), int(m.group(2))
-        return {"fwd_x": n * R + n * C * fx, "fwd_y": n * C * fx + n * C * fcol,
-                "inv_y": n * C * fcol + n * C * fx, "inv_x": n * C * fx + n * R}[k]
+        return {"fwd_x": n * R + n * C * fx, "fwd_y": n * C * fx + n * C * fy,
+                "inv_y": n * C * fy + n * C * fx, "inv_x": n * C * fx + n * R}[k]
     flux = (8 + (3 if hall else 0)) * R + nf * R
     table = {
         "flux": flux,
@@ -145,9 +181,9 @@ def nvlink_model(prof, live_cols, total_cols, rows, mass, n, nzl, steps, ms_step
     """Bytes one rank stores into its peers' buffers (the reference's transpose_yz / transpose_zy, parallel.f90:273-324,
     fused into the passes) per launch of each exchanging kernel, over that launch's mean duration.  prof: name ->
     [total ms, launches]; live_cols / total_cols: surviving (kx, ky) columns owned by this rank / by all ranks."""
-    import re
     per_kernel = {}
-    for k, (tms, cnt) in prof.items():
+    for k, v in prof.items():
+        tms, cnt = v[0], v[1]
         m = re.fullmatch(r"fwd_y(\d+)", k)
         if m:      # every surviving (kx, ky) column of this rank's z slab goes to the owner of ky (transpose_yz)
             remote = int(m.group(1)) * 16.0 * nzl * (total_cols - live_cols)
@@ -175,27 +211,67 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def all_cores():
+    """Every CPU this process may run on after lifting the launcher's / the NUMA pinning's restrictions."""
+    n = os.cpu_count() or 1
+    try:
+        os.sched_setaffinity(0, range(n))
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    return n
+
+
+def pin_to_gpu_numa(index):
+    """Run this rank's host thread (and allocate its pinned buffers) on the CPUs next to its GPU: with 8 ranks the
+    H2D / D2H copies of the end-to-end session otherwise cross the socket interconnect for half of the GPUs."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return f"nvmlDeviceSetCpuAffinity(gpu {index}): {len(os.sched_getaffinity(0))} CPUs"
+    except Exception as e:
+        return f"not pinned ({type(e).__name__})"
+
+
 # ------------------------------------------------------------------------------------------
 # CPU oracle leg
 # ------------------------------------------------------------------------------------------
+def cpu_sample_size(n):
+    """The workload's own grid when the host has the memory for the port's arrays (34 real + 46 spectral fields +
+    k_square, the reference's own layout: 81.5 x 8 n^3 bytes), else 256^3."""
+    need = 81.5 * 8 * float(n) ** 3 * 1.25 + 8e9
+    try:
+        import psutil
+        if psutil.virtual_memory().available > need:
+            return n
+    except Exception:
+        pass
+    return min(n, 256)
+
+
 def cpu_oracle_run(n, steps, warmup):
     """The CPU port's Principal-loop step on an n^3 grid with the workload's physics; returns
     (grid-point-steps/s, seconds per step, threads, description).  The port is oracle/laps_cpu.c (C + OpenMP, all
-    host threads; the reference's structure: one field at a time, line-at-a-time transforms, separate pointwise
-    sweeps); if it cannot be built on this host, the NumPy/SciPy oracle."""
+    host threads; the reference's structure: one field at a time, 19 + 11 three-dimensional transforms per stage,
+    separate pointwise sweeps); if it cannot be built on this host, the NumPy/SciPy oracle."""
     from oracle import laps_oracle as lo
     from laps_b200 import synthetic
     kw = workload_params(n)
     p = lo.Params(**{k: (bool(v) if k.startswith("if_") else v) for k, v in kw.items()})
-    prim = synthetic.turbulence_slab(n, n, n, p.Lx, p.Ly, p.Lz, kmax=min(8, n // 2 - 1))
+    cores = all_cores()
+    prim = synthetic.turbulence_slab(n, n, n, p.Lx, p.Ly, p.Lz, kmax=min(8, n // 2 - 1), workers=cores)
     try:
         from oracle import cpu_port
         s = cpu_port.CpuPort(p)
-        what, cores = "oracle/laps_cpu.c (C + OpenMP restatement)", s.threads
+        s.set_threads(cores)       # torchrun exports OMP_NUM_THREADS=1: use every core regardless
+        what, cores = "oracle/laps_cpu.c (C + OpenMP restatement, batched SIMD transforms)", s.threads
     except Exception as e:  # no compiler on this host
         s = lo.State(p)
         what, cores = f"oracle/laps_oracle.py (NumPy/SciPy restatement; C port unavailable: {type(e).__name__})", lo._WORKERS
     s.set_primitive(prim)
+    del prim
     s.vardt()
     for _ in range(warmup):
         s.step()
@@ -203,6 +279,8 @@ def cpu_oracle_run(n, steps, warmup):
     for _ in range(steps):
         s.step()
     dt = (time.perf_counter() - t0) / max(steps, 1)
+    if hasattr(s, "close"):
+        s.close()
     return n ** 3 / dt, dt, cores, what
 
 
@@ -210,15 +288,18 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    n = args.cpu_n
-    steps = max(1, min(args.steps, 3))
+    spec = config_spec(args.config, args.n)
+    n = args.cpu_n or cpu_sample_size(spec["grid"][0])
+    steps = max(1, min(args.steps, 2 if n > 256 else 3))
     warm = 1
     v, sec, cores, what = cpu_oracle_run(n, steps, warm)
+    same = n == spec["grid"][0] and args.config in (4, 5)
     out = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.n), "sample": f"{n}^3 grid of the same physics"},
+        "config": {"workload": workload_name(spec["grid"][0]) if args.config in (4, 5) else spec["name"],
+                   "sample": ("the workload's own grid" if same else f"{n}^3 grid of the 3D compressible Hall + expanding-box physics")},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{what}, {n}^3 grid, {steps} RK steps after {warm} warm-up, {cores} threads"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -229,50 +310,146 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------
+# multi-rank plumbing shared by the parity gate and the timed run
+# ------------------------------------------------------------------------------------------
+class Ranks:
+    def __init__(self, args):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world > 1:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={self.world}")
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, x, op="max"):
+        if not self.dist:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op={"max": self.dist.ReduceOp.MAX, "sum": self.dist.ReduceOp.SUM, "min": self.dist.ReduceOp.MIN}[op])
+        return float(t.item())
+
+    def connect(self, g):
+        if not self.dist:
+            return
+        torch = self.torch
+        blob = torch.from_numpy(np.frombuffer(g.export_peer_blob(), dtype=np.uint8).copy()).cuda()
+        blobs = [torch.empty_like(blob) for _ in range(self.world)]
+        self.dist.all_gather(blobs, blob)
+        g.import_peer_blobs(b"".join(bytes(b.cpu().numpy().tobytes()) for b in blobs))
+
+    def close(self):
+        if self.dist:
+            self.dist.destroy_process_group()
+
+
+def parity_gate(R):
+    """Two Principal-loop steps of a 64^3 Hall-MHD + expanding-box case on this run's ranks against the CPU oracle
+    (oracle/laps_oracle.py State, the restatement pinned by the executed reference source): every rank's real-space and
+    Fourier-space slabs, relative L2 per field.  With N > 1 both Fourier-row ownership forms are run: the reference's
+    decompose_1d slabs and the round-robin rows (the default from 4 ranks on)."""
+    from laps_b200 import Solver
+    from oracle import laps_oracle as lo
+    n = 64
+    kw = workload_params(n)
+    p = lo.Params(**{k: (bool(v) if k.startswith("if_") else v) for k, v in kw.items()})
+    prim = lo.ic_uniform_background(p, bx0=1.0, press0=1.0)
+    prim = lo.ic_turbulence(p, prim, 1.0, 0.0, 0.0, db0=0.1, dv0=0.1, drho0=0.01, nmodex=2, nmodey=2, nmodez=2, seeds=(101, 116, 132))
+    o = lo.State(p)
+    o.set_primitive(prim)
+    o.vardt()
+    for _ in range(2):
+        o.step()
+    forms = [None] if R.world == 1 else ["0", "1"]
+    cases, ok = [], True
+    for form in forms:
+        saved = os.environ.get("LAPS_TUNE_CYCLIC")
+        if form is not None:
+            os.environ["LAPS_TUNE_CYCLIC"] = form
+        try:
+            g = Solver(rank=R.rank, nranks=R.world, device=R.local, **kw)
+        finally:
+            if form is not None:
+                if saved is None:
+                    os.environ.pop("LAPS_TUNE_CYCLIC", None)
+                else:
+                    os.environ["LAPS_TUNE_CYCLIC"] = saved
+        R.connect(g)
+        R.barrier()
+        zo, zn, rows = g.ext.z_offset, g.ext.z_size, g.ky_rows
+        g.set_primitive(prim[:, zo:zo + zn])
+        g.vardt()
+        for _ in range(2):
+            g.step()
+        uu, _ = g.get_state()
+        uf = g.uu_fourier()
+        worst = 0.0
+        for v in range(8):
+            a, b = uu[v], o.uu[v, zo:zo + zn]
+            worst = max(worst, float(np.linalg.norm(a - b) / np.linalg.norm(b)))
+            # this rank's Fourier rows against the norm of the whole field (a rank may own only near-empty rows)
+            a, b = uf[v], o.uu_fourier[v][:, rows, :]
+            worst = max(worst, float(np.linalg.norm(a - b) / np.linalg.norm(o.uu_fourier[v]) * np.sqrt(R.world)))
+        dt_err = abs(g.dt - o.dt) / o.dt
+        worst_all = R.reduce(worst, "max")
+        dt_all = R.reduce(dt_err, "max")
+        cases.append({"y_stride": int(g.ext.y_stride), "max_rel_l2": worst_all, "dt_rel": dt_all})
+        ok = ok and worst_all <= PARITY_TOL and dt_all <= 1e-12
+        R.barrier()
+        g.close()
+        R.barrier()
+    return {"ranks": R.world, "case": "64^3 Hall-MHD + expanding box, 2 steps, vs oracle/laps_oracle.py State", "tol": PARITY_TOL,
+            "fields": "uu(1:8) of every rank's z slab and uu_fourier(1:8) of its ky rows, relative L2", "cases": cases, "ok": bool(ok)}
+
+
+# ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
 def run_gpu(args):
-    import torch
-    import torch.distributed as dist
+    R = Ranks(args)
+    torch = R.torch
     from laps_b200 import Solver, synthetic
+    rank, world, local = R.rank, R.world, R.local
+    affinity = pin_to_gpu_numa(local)
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    parity = None
+    if not args.no_parity:
+        parity = parity_gate(R)
+        if not parity["ok"]:
+            if rank == 0:
+                sys.stderr.write("PARITY GATE FAILED: " + json.dumps(parity) + "\n")
+            R.close()
+            return 3
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    n = args.n
-    kw = workload_params(n)
+    spec = config_spec(args.config, args.n)
+    kw = spec["kw"]
+    gx, gy, gz = spec["grid"]
+    npoints = float(gx) * gy * gz
     g = Solver(rank=rank, nranks=world, device=local, **kw)
-    if world > 1:
-        blob = torch.from_numpy(np.frombuffer(g.export_peer_blob(), dtype=np.uint8).copy()).cuda()
-        blobs = [torch.empty_like(blob) for _ in range(world)]
-        dist.all_gather(blobs, blob)
-        g.import_peer_blobs(b"".join(bytes(b.cpu().numpy().tobytes()) for b in blobs))
+    R.connect(g)
     stream = torch.cuda.ExternalStream(g.cuda_stream(), device=torch.device("cuda", local))
+    footprint = R.reduce(float(g.footprint()), "max")
 
     # synthetic turbulence on this rank's z-slab, in pinned host memory (the driver's uu array)
     shape = (8,) + g.real_shape
     host_in = torch.empty(shape, dtype=torch.float64).pin_memory()
     prim = host_in.numpy()
-    synthetic.turbulence_slab(n, n, n, kw["Lx"], kw["Ly"], kw["Lz"], z_offset=g.ext.z_offset, z_size=g.ext.z_size,
-                              kmax=min(8, n // 2 - 1), out=prim)
+    if kw.get("ndim") == 2:     # the z = 0 plane of a 3D turbulence field
+        prim[...] = synthetic.turbulence_slab(gx, gy, 32, kw["Lx"], kw["Ly"], kw["Lz"], kmax=8, z_size=1, **spec["turb"])
+    else:
+        synthetic.turbulence_slab(gx, gy, gz, kw["Lx"], kw["Ly"], kw["Lz"], z_offset=g.ext.z_offset, z_size=g.ext.z_size,
+                                  kmax=min(8, gx // 2 - 1), out=prim, **spec["turb"])
     host_uu = torch.empty(shape, dtype=torch.float64).pin_memory()
 
     def ev():
@@ -280,41 +457,68 @@ def run_gpu(args):
 
     # ---------------- warm-up ----------------
     g.set_primitive(prim)
+    rho_mean0 = float(g.calc_rms()[0][0])     # the k = 0 mode of rho (collective; outside every timed region)
     g.vardt()
+    history = []                               # (time, dt) at the start of every step since set_primitive
     for _ in range(args.warmup):
+        history.append((g.time, g.dt))
         g.step()
     g.sync()
 
-    # ---------------- timed: resident state ----------------
+    # ---------------- timed: resident state, no instrumentation ----------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    g.set_profiling(True)
-    barrier()
+    R.barrier()
     e0, e1 = ev(), ev()
     tw0 = time.perf_counter()
     e0.record(stream)
     launches = 0
-    prof = {}
     for _ in range(args.steps):
+        history.append((g.time, g.dt))
         g.step()
-        _, nl = g.last_step_ms()
-        launches += nl
-        for name, ms in g.get_profile():
-            a = prof.setdefault(name, [0.0, 0])
-            a[0] += ms; a[1] += 1
+        launches += g.last_step_ms()[1]
     e1.record(stream)
-    barrier()
+    R.barrier()
     tw1 = time.perf_counter()
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    g.set_profiling(False)
+    ms_total = R.reduce(e0.elapsed_time(e1), "max")
     clocks = sampler.stop(tw0, tw1) if rank == 0 else None
     ms_step = ms_total / args.steps
-    value = float(n) ** 3 / (ms_step * 1e-3)
+    value = npoints / (ms_step * 1e-3)
+    # Size-independent property at the full grid size: the k = 0 mode of rho.  The continuity row has no flux at k = 0,
+    # so d<rho>/dt = -(2 / tau) <rho> with tau = R(t) / U_r frozen during a step (mhdrhs.f90:235-237): every RK3 step
+    # multiplies it by 1 + z + z^2/2 + z^3/6, z = -2 dt / tau (rktmod.f90:17-61 applied to a linear term) — and by
+    # exactly 1 without the expanding box.
+    rho_mean1 = float(g.calc_rms()[0][0])
+    expect = 1.0
+    if kw.get("if_AEB") and not kw.get("incompressible"):
+        for t, dt in history:
+            z = -2.0 * dt / ((kw["radius0"] + kw["Ur0"] * t) / kw["Ur0"])
+            expect *= 1.0 + z + z * z / 2.0 + z * z * z / 6.0
+    k0_mode = {"what": "mean rho (the k = 0 mode) after warm-up + K steps over its initial value, against the RK3 polynomial of the "
+                       "expanding-box term (exactly 1 without the box)", "measured": rho_mean1 / rho_mean0, "expected": expect,
+               "rel_err": abs(rho_mean1 / rho_mean0 / expect - 1.0), "ok": abs(rho_mean1 / rho_mean0 / expect - 1.0) < 1e-11}
+
+    # ---------------- instrumented pass: per-launch CUDA events (outside the timed region) ----------------
+    psteps = max(1, min(args.steps, 4))
+    g.set_profiling(True)
+    R.barrier()
+    p0, p1 = ev(), ev()
+    p0.record(stream)
+    prof = {}     # name -> [total ms, launches, total algorithmic bytes]
+    for _ in range(psteps):
+        g.step()
+        for name, ms, by in g.get_profile(with_bytes=True):
+            a = prof.setdefault(name, [0.0, 0, 0.0])
+            a[0] += ms; a[1] += 1; a[2] += by
+    p1.record(stream)
+    R.barrier()
+    ms_prof_step = R.reduce(p0.elapsed_time(p1), "max") / psteps
+    g.set_profiling(False)
 
     # ---------------- timed: end to end through the C ABI with host buffers ----------------
-    barrier()
+    R.barrier()
     f0, f1 = ev(), ev()
     f0.record(stream)
     g.time = 0.0
@@ -326,96 +530,101 @@ def run_gpu(args):
         g.step()                               # reads dt back every step
     g.get_output(True, out=host_uu.numpy())   # D2H of the array output_uu writes (rho, u, B, p) into pinned memory
     f1.record(stream)
-    barrier()
-    e2e_ms = max_over_ranks(f0.elapsed_time(f1)) / args.steps
+    R.barrier()
+    e2e_ms = R.reduce(f0.elapsed_time(f1), "max") / args.steps
     h2d = world * prim.nbytes / args.steps
     d2h = world * host_uu.numel() * 8 / args.steps + 8
     finite = bool(np.isfinite(host_uu.numpy()).all())
 
-    # ---------------- roofline of the dominant kernel ----------------
-    R = 8.0 * n * n * g.nzl
-    C = 16.0 * g.nxh * g.nyl * n
+    # ---------------- roofline ----------------
     nf, ni, rows = g.field_counts()
-    hall = bool(kw["if_hall"])
     nkx, kymax, nkyl = g.pruning()
     live_cols, live_modes = g.pruning_counts()
-    fx = nkx / g.nxh
-    fcol = live_cols / float(g.nxh * g.nyl)
-    fmode = live_modes / float(g.nxh * g.nyl * n)
+    nline = g.nz if kw.get("ndim") != 2 else g.ny
+    fcol = live_cols / float(g.nxh * max(g.nyl, 1)) if kw.get("ndim") != 2 else live_cols / float(g.nxh)
+    fmode = live_modes / float(g.nxh * max(g.nyl, 1) * nline) if kw.get("ndim") != 2 else live_modes / float(g.nxh * nline)
     mass = rows < 8
-    kb = lambda k: kernel_bytes(k, R, C, nf, ni, hall, fx, fcol, fmode, mass)  # noqa: E731
     peak, peak_src = peaks()
-    # the dominant kernel among those that move data (the one-CTA flag kernels have no byte model)
-    top = max((kv for kv in prof.items() if kb(kv[0])), key=lambda kv: kv[1][0], default=None)
+    timed = {k: v for k, v in prof.items() if v[2] > 0}
+    top = max(timed.items(), key=lambda kv: kv[1][0], default=None)
     roofline = None
-    shares = {}
     # DRAM bytes per launch measured by ncu --set full for this exact configuration (committed capture), or None
     traffic, traffic_src = None, None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01i_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
         c = tj["config"]
-        if (c["n"], c["n_gpus"], c["if_hall"], c["if_AEB"], c["dealias_option"]) == (n, world, kw["if_hall"], kw["if_AEB"], kw["dealias_option"]):
+        if (c["config"], c["n"], c["n_gpus"]) == (args.config, gx, world):
             traffic, traffic_src = {k: v["dram_bytes_per_launch"] for k, v in tj["kernels"].items()}, tj["source"]
     except Exception:
         pass
     if top:
         tot = sum(v[0] for v in prof.values()) or 1e-12
         shares = {k: round(v[0] / tot, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
-        name, (tms, cnt) = top
-        b = kb(name)
+        name, (tms, cnt, tby) = top
+        b = tby / cnt
         avg_ms = max(tms / cnt, 1e-9)
-        ach = b / (avg_ms * 1e-3) / 1e9 if b else None
+        ach = b / (avg_ms * 1e-3) / 1e9
+        step_bytes = sum(v[2] for v in prof.values()) / psteps
+        step_ach = step_bytes / (ms_step * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": (ach / peak) if ach else None, "traffic": (traffic or {}).get(name), "traffic_source": traffic_src if (traffic or {}).get(name) else None,
+                    "frac": ach / peak, "traffic": (traffic or {}).get(name), "traffic_source": traffic_src if (traffic or {}).get(name) else None,
                     "peak_source": peak_src,
                     "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": b,
-                    "per_kernel_GBps": {k: (kb(k) or 0) / (max(v[0] / v[1], 1e-9) * 1e-3) / 1e9 for k, v in prof.items() if kb(k)},
-                    "pruning": {"nkx": nkx, "nxh": g.nxh, "kymax": kymax, "ny": n, "nky_local": nkyl, "live_column_fraction": fcol, "live_mode_fraction": fmode,
+                    "step_frac": step_ach / peak, "step_achieved": step_ach, "step_algorithmic_bytes": step_bytes,
+                    "step_what": "sum of the algorithmic bytes of every launch of one step (laps_get_profile_bytes; exactly skipped "
+                                 "columns and modes left out) / ms_per_step of the un-instrumented timed region / peak",
+                    "per_kernel_GBps": {k: (v[2] / v[1]) / (max(v[0] / v[1], 1e-9) * 1e-3) / 1e9 for k, v in timed.items()},
+                    "per_kernel_frac": {k: round((v[2] / v[1]) / (max(v[0] / v[1], 1e-9) * 1e-3) / 1e9 / peak, 4) for k, v in timed.items()},
+                    "pruning": {"nkx": nkx, "nxh": g.nxh, "kymax": kymax, "ny": g.ny, "nky_local": nkyl, "live_column_fraction": fcol, "live_mode_fraction": fmode,
                                 "what": "columns removed by the dealiasing mask are skipped exactly (bit-identical state)"},
+                    "profiled_steps": psteps, "ms_per_step_instrumented": ms_prof_step,
                     "time_share": shares}
 
     # ---------------- NVLink: the slab transposes are the remote stores of the y pass and the z pass ----------------
     nvlink = None
-    if world > 1:
-        t = torch.tensor([float(live_cols)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        nvlink = nvlink_model(prof, live_cols, float(t.item()), rows, mass, n, g.nzl, args.steps, ms_step)
+    if world > 1 and not kw.get("incompressible"):
+        total_cols = R.reduce(float(live_cols), "sum")
+        nvlink = nvlink_model(prof, live_cols, total_cols, rows, mass, gz, g.nzl, psteps, ms_prof_step)
+        nvlink["egress_GBps_over_the_step"] = nvlink["egress_bytes_per_step"] / (ms_step * 1e-3) / 1e9   # un-instrumented step time
 
-    barrier()          # no rank may free its exchange buffers while a peer can still store into them
+    R.barrier()          # no rank may free its exchange buffers while a peer can still store into them
     g.close()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        R.close()
         return 0
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, sec, cores, what = cpu_oracle_run(args.cpu_n, 2, 1)
+        cn = args.cpu_n or cpu_sample_size(gx if args.config in (4, 5) else 256)
+        v, sec, cores, what = cpu_oracle_run(cn, 2, 1)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{what}, {args.cpu_n}^3 grid of the same physics, 2 RK steps after 1 warm-up, {cores} threads",
+               "sample": f"{what}, {cn}^3 grid of the 3D compressible Hall + expanding-box physics, 2 RK steps after 1 warm-up, {cores} threads",
                "ms_per_step": sec * 1e3}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(n), "decomposition": f"slab over {world} GPU(s), z in real space / ky in Fourier space"
+        "config": {"workload": spec["name"], "decomposition": f"slab over {world} GPU(s), z in real space / ky in Fourier space"
                                     + (f" (ky rows dealt round-robin, y_stride {g.ext.y_stride})" if g.ext.y_stride > 1 else " (decompose_1d slabs)"),
                    "l2": "inputs larger than L2 (every pass streams >= 8 GB per GPU at 512^3/8 and above); no flush",
-                   "ic": "ifield=3 uniform B0=(1,0,0) + ipert=7-style random-phase modes |k|<=8, k^-3/2"},
+                   "ic": "ifield=3 uniform B0=(1,0,0) + ipert=7-style random-phase modes |k|<=8, k^-3/2",
+                   "device_bytes_per_gpu": footprint, "host_affinity": affinity},
+        "parity": parity,
         "clocks": clocks,
-        "e2e": {"value": float(n) ** 3 / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms, "what": "laps_set_primitive(host) + K x laps_step + laps_get_output(host), per step"},
+        "e2e": {"value": npoints / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms, "what": "laps_set_primitive(host) + K x laps_step + laps_get_output(host), per step; the two "
+                                               "copies happen once per session (between two outNNN.dat dumps), their bytes are spread over the K steps"},
         "gpu_launches": launches,
         "nvlink": nvlink,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "state_finite": finite,
     }
+    out["k0_mode"] = k0_mode
     print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    R.close()
     return 0
 
 
@@ -425,9 +634,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=512, help="grid size (512 = BASELINE config 4)")
-    ap.add_argument("--cpu-n", type=int, default=256, help="grid of the bounded CPU-baseline sample")
+    ap.add_argument("--config", type=int, default=4, help="BASELINE.json configuration 1..5 (4 = the headline 512^3; 5 = 1024^3 over 8 GPUs)")
+    ap.add_argument("--n", type=int, default=None, help="override the configuration's grid size")
+    ap.add_argument("--cpu-n", type=int, default=None, help="grid of the CPU-baseline sample (default: the workload's own when the host has the memory, else 256)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the pre-timing parity gate (profiler runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

@@ -8,7 +8,8 @@
  *
  * Conventions: all functions return 0 on success, non-zero on failure (message via
  * laps_last_error); no exceptions cross the boundary; one host thread per handle; every device
- * allocation belongs to the library, every host buffer to the caller.  Host arrays use the
+ * allocation belongs to the library, every host buffer to the caller.  Every call makes the handle's
+ * CUDA device current for the calling thread and leaves it current (as cudaSetDevice would).  Host arrays use the
  * reference layout uu(ix,iy,iz,ivar): x fastest, then local y, local z, variable slowest.
  */
 #ifndef LAPS_B200_H
@@ -20,7 +21,7 @@
 extern "C" {
 #endif
 
-#define LAPS_ABI_VERSION 5
+#define LAPS_ABI_VERSION 6
 #define LAPS_MAX_RANKS 8
 
 typedef struct laps_solver* laps_handle;
@@ -94,12 +95,19 @@ int laps_get_extents(laps_handle h, laps_extents* out);
  * laps_invariants, laps_fft_forward and laps_fft_inverse are COLLECTIVE: every rank must call
  * them in the same order (exactly as every MPI rank of the reference does).  The driver must
  * synchronise the ranks (MPI_Barrier) before any of them calls laps_destroy.
+ * Failure model: a rank that returns an error from a collective, dies, or calls the collectives in a different
+ * order is FATAL FOR THE WHOLE JOB, as a failed MPI rank is for the reference.  The inter-rank waits are bounded
+ * (LAPS_XCHG_TIMEOUT_S, default 120 s per wait): a rank that runs out of budget, or that fails on the host side
+ * between two waits, raises an abort word on every rank; every rank's next host-side wait then returns an error
+ * ("slab exchange aborted", laps_last_error), and every later call on those handles fails until laps_destroy.
  * Not needed when nranks == 1. */
 #define LAPS_PEER_BLOB_BYTES 256
 int laps_export_peer_blob(laps_handle h, void* blob /* LAPS_PEER_BLOB_BYTES */);
 int laps_import_peer_blobs(laps_handle h, const void* blobs /* nranks * LAPS_PEER_BLOB_BYTES */);
 /* Single-process multi-GPU: wire the handles of all ranks created in this process to each other
- * (peer access instead of IPC).  Each handle must then be driven by its own host thread. */
+ * (peer access instead of IPC).  Each handle must then be driven by its own host thread (the collectives of the
+ * ranks wait for each other); the handles may also share a device (tests/test_gpu_multirank.py runs 2-8 ranks on
+ * one GPU this way). */
 int laps_connect_local(laps_handle* handles, int32_t nranks);
 
 /* initial_calc_conserve_variable + transform_uu_real_to_fourier (mhd.f90:121-122):
@@ -209,6 +217,15 @@ int laps_last_step_ms(laps_handle h, float* ms, int32_t* launches);
  * launches (laps_set_profiling(h,1) inserts events around every launch). */
 int laps_set_profiling(laps_handle h, int32_t on);
 int laps_get_profile(laps_handle h, char* names /* cap*32 */, float* ms, int32_t cap, int32_t* count);
+/* The ALGORITHMIC HBM bytes of the same launches, in the same order (what each pass has to read
+ * and write once, the exactly skipped columns and modes left out; 0 for the one-CTA flag kernels) — the numerators of
+ * the roofline figures bench.py prints. */
+int laps_get_profile_bytes(laps_handle h, double* bytes, int32_t cap, int32_t* count);
+/* Device memory this handle allocated (state, work and exchange buffers, tables). */
+int laps_get_footprint(laps_handle h, int64_t* device_bytes);
+/* Measurement helper: the LAPS_TUNE_* switches that select between equivalent kernels / launch shapes ("rhs", "rcg",
+ * "cgz", "z", "spec", ...), settable on a live handle so that one process can time the alternatives on one state. */
+int laps_set_tune(laps_handle h, const char* name, int32_t value);
 
 #ifdef __cplusplus
 }

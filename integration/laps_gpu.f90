@@ -5,7 +5,7 @@
 module laps_gpu
   use iso_c_binding
   implicit none
-  integer(c_int), parameter :: LAPS_ABI_VERSION = 5, LAPS_PEER_BLOB_BYTES = 256
+  integer(c_int), parameter :: LAPS_ABI_VERSION = 6, LAPS_PEER_BLOB_BYTES = 256
 
   type, bind(C) :: laps_params          ! field order = include/laps_b200.h
     integer(c_int32_t) :: abi_version
@@ -154,6 +154,16 @@ module laps_gpu
     end function
     integer(c_int) function laps_set_profiling(h, on) bind(C, name='laps_set_profiling')
       import; type(c_ptr), value :: h; integer(c_int32_t), value :: on
+    end function
+    integer(c_int) function laps_get_profile_bytes(h, bytes, cap, count) bind(C, name='laps_get_profile_bytes')
+      import; type(c_ptr), value :: h; real(c_double), intent(out) :: bytes(*); integer(c_int32_t), value :: cap
+      integer(c_int32_t), intent(out) :: count
+    end function
+    integer(c_int) function laps_get_footprint(h, device_bytes) bind(C, name='laps_get_footprint')
+      import; type(c_ptr), value :: h; integer(c_int64_t), intent(out) :: device_bytes
+    end function
+    integer(c_int) function laps_set_tune(h, name, value) bind(C, name='laps_set_tune')
+      import; type(c_ptr), value :: h; character(kind=c_char), intent(in) :: name(*); integer(c_int32_t), value :: value
     end function
     integer(c_int) function laps_get_profile(h, names, ms, cap, count) bind(C, name='laps_get_profile')
       import; type(c_ptr), value :: h; character(kind=c_char), intent(out) :: names(32,*); real(c_float), intent(out) :: ms(*)

@@ -14,7 +14,7 @@ from typing import Optional
 
 import numpy as np
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_RANKS = 8
 PEER_BLOB_BYTES = 256
 
@@ -63,7 +63,7 @@ SYMBOLS = [
     "laps_fft_forward", "laps_fft_inverse", "laps_transpose_yz_indexmap", "laps_transpose_zy_indexmap",
     "laps_last_step_ms", "laps_set_profiling", "laps_get_profile", "laps_get_pruning",
     "laps_max_divv", "laps_max_div_real", "laps_get_rho0", "laps_get_field_counts", "laps_get_output", "laps_get_pruning_counts", "laps_set_primitive_modes",
-    "laps_check_nan", "laps_set_external_force",
+    "laps_check_nan", "laps_set_external_force", "laps_get_profile_bytes", "laps_get_footprint", "laps_set_tune",
 ]
 
 
@@ -124,6 +124,9 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.laps_get_pruning_counts.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.laps_set_profiling.argtypes = [H, C.c_int32]
     lib.laps_get_profile.argtypes = [H, C.c_char_p, C.POINTER(C.c_float), C.c_int32, C.POINTER(C.c_int32)]
+    lib.laps_get_profile_bytes.argtypes = [H, dp, C.c_int32, C.POINTER(C.c_int32)]
+    lib.laps_get_footprint.argtypes = [H, C.POINTER(C.c_int64)]
+    lib.laps_set_tune.argtypes = [H, C.c_char_p, C.c_int32]
     for name in SYMBOLS:
         if name != "laps_last_error":
             getattr(lib, name).restype = C.c_int

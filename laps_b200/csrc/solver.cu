@@ -60,7 +60,7 @@ bool size_supported(int n) {
   }
 }
 
-struct ProfEntry { char name[32]; cudaEvent_t e0, e1; };
+struct ProfEntry { char name[32]; cudaEvent_t e0, e1; double bytes; };
 
 }  // namespace
 
@@ -130,6 +130,8 @@ struct laps_solver {
   int* d_kymax_x = nullptr;   // [nxh]
   int* d_colmap = nullptr;    // [pr_ncol]
   int pr_ncol = 0;            // this rank's surviving columns
+  long long pr_cols_all = 0;  // surviving (kx, ky) columns of ALL ranks (what the y passes of this rank's z slab visit)
+  size_t dev_bytes = 0;       // device memory allocated by this handle
   long long pr_modes = 0;     // this rank's surviving modes (kx, ky, kz), for the traffic model of bench.py
   bool kzprune = false;       // masked modes are neither loaded nor stored by the z pass (see ZParams::kzprune)
   bool spectrum_full = true;   // the state still holds masked columns (fresh from laps_set_primitive)
@@ -258,12 +260,15 @@ void aeb_calc(S* s) {  // AEBmod.f90:46-54
 }
 
 // ---- instrumentation ----------------------------------------------------------------------------
+// `bytes`: ALGORITHMIC HBM bytes of the launch (what the pass has to read and write once, with
+// the exactly skipped columns / modes left out) — the numerator of the roofline figures bench.py prints.
 struct LaunchScope {
   S* s; int idx = -1;
-  LaunchScope(S* s_, const char* name) : s(s_) {
+  LaunchScope(S* s_, const char* name, double bytes = 0.0) : s(s_) {
     ++s->launches;
     if (s->profiling) {
       ProfEntry pe;
+      pe.bytes = bytes;
       std::snprintf(pe.name, sizeof(pe.name), "%s", name);
       cudaEventCreate(&pe.e0); cudaEventCreate(&pe.e1);
       cudaEventRecord(pe.e0, s->stream);
@@ -278,6 +283,38 @@ int check_launch(S* s, const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { s->err = std::string(what) + ": " + cudaGetErrorString(e); return 1; }
   return 0;
+}
+
+// ---- algorithmic bytes of the passes (per launch) ---------------------------------------------
+// one real field of this rank's slab; the post-x-pass columns (kx < nkx survive) and the post-y-pass columns (the
+// (kx, ky) columns of ALL ranks that survive) of one field over this rank's z slab
+double bytes_real(const S* s) { return 8.0 * (double)s->npts; }
+double bytes_xcols(const S* s, bool prune) { return 16.0 * (prune ? s->nkx : s->nxh) * (double)s->nzl * s->ny; }
+double bytes_ycols(const S* s, bool prune) { return 16.0 * (prune ? (double)s->pr_cols_all : (double)s->nxh * s->ny) * s->nzl; }
+double bytes_z(const S* s, const ZParams& z, int ntasks) {
+  const double line = 16.0 * (double)z.ncolc * z.nz;                 // one z line of every visited column
+  const double modes = z.kzprune ? 16.0 * (double)s->pr_modes : line;   // state / RK-history entries actually touched
+  double b = 0.0;
+  // a flux spectrum that several rows of the launch combine (the off-diagonal momentum fluxes, the components of E)
+  // comes from HBM once: the CTAs of one column group run together and share it through L2
+  unsigned long long seen = 0;
+  auto in = [&](int f) { if (f >= 0 && !((seen >> f) & 1ull)) { seen |= 1ull << f; b += line; } };
+  for (int i = 0; i < ntasks; ++i) {
+    const ZTask& t = z.task[i];
+    const double out = t.gout >= 0 ? line : 0.0;
+    switch (t.kind) {
+      case kZRhs: in(t.fa); in(t.fb); in(t.fx); in(t.fc);
+                  b += out + modes * (1 + (z.read_rk ? 1 : 0) + 1 + (z.write_rk ? 1 : 0)); break;
+      case kZForwardOnly: in(t.fa); b += line; break;
+      case kZInverseOnly: b += line + out; break;
+      case kZCurrent: b += modes + out; break;            // each B component is read by two of the three tasks: once from HBM
+      case kZGrad: b += line / 3.0 + out; break;          // the three derivatives of one component share its line
+      case kZDiv: b += 3 * line + out; break;
+      case kZMass: b += modes * (4 + (z.read_rk ? 1 : 0) + 1 + (z.write_rk ? 1 : 0)) + out; break;
+      default: break;
+    }
+  }
+  return b;
 }
 
 // Every entry point makes the handle's device current for the calling thread (a driver thread that owns several
@@ -341,7 +378,7 @@ int do_fwd_x_tl(S* s, const double* in, size_t fstride, int nfields, cplx* W1, b
   const int np = planes < 0 ? s->xz : planes;
   dim3 grid((unsigned)(np * (s->xy / (2 * TL))), (unsigned)nfields);
   if (scoped) {
-    LaunchScope ls(s, name);
+    LaunchScope ls(s, name, nfields * ((double)np * s->xy * (8.0 * N + 16.0 * (prune ? s->nkx : s->nxh))));
     LAPS_LAUNCH((k_fwd_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, in, fstride, W1, s->xz, s->xy, s->tw_x,
                 1.0 / N, prune ? s->nkx : s->nxh, zl0);
   } else {
@@ -370,7 +407,7 @@ int do_flux_fwd_x(S* s, const FusedFluxParams& fp) {
     typedef FTile<N, kFuseGroups> T;
     constexpr int ctas = (227 * 1024) / (int)(T::SMEM + 1024) < 1 ? 1 : ((227 * 1024) / (int)(T::SMEM + 1024) > 2 ? 2 : (227 * 1024) / (int)(T::SMEM + 1024));
     LAPS_CK(s, prepare_kernel(k_flux_fwd_x<N, kFuseGroups>, T::SMEM, ctas));
-    LaunchScope ls(s, "flux_fwd_x");
+    LaunchScope ls(s, "flux_fwd_x", (8 + (s->p.if_hall ? 3 : 0)) * bytes_real(s) + s->nf * bytes_xcols(s, true));
     dim3 grid((unsigned)(s->nzl * (s->ny / 2)));
     LAPS_LAUNCH((k_flux_fwd_x<N, kFuseGroups>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, fp);
     return check_launch(s, "k_flux_fwd_x");
@@ -385,7 +422,7 @@ int do_fwd_y(S* s, const cplx* W1, int nfields, bool prune) {
   constexpr int TL = tly(N);
   typedef Tile<N, TL> T;
   LAPS_CK(s, prepare_kernel(k_fwd_y<N, TL>, T::SMEM, T::MINB));
-  LaunchScope ls(s, name);
+  LaunchScope ls(s, name, nfields * (bytes_xcols(s, prune) + bytes_ycols(s, prune)));
   const int ztiles = (s->nzl + TL - 1) / TL;
   dim3 grid((unsigned)(ztiles * (prune ? s->nkx : s->nxh)), (unsigned)nfields);
   LAPS_LAUNCH((k_fwd_y<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, W1, s->tabW2, s->nzl, s->nz, s->zo,
@@ -399,7 +436,7 @@ int do_inv_y(S* s, const cplx* V1, cplx* V2, int nfields, bool prune) {
   constexpr int TL = tly(N);
   typedef Tile<N, TL> T;
   LAPS_CK(s, prepare_kernel(k_inv_y<N, TL>, T::SMEM, T::MINB));
-  LaunchScope ls(s, name);
+  LaunchScope ls(s, name, nfields * (bytes_xcols(s, prune) + bytes_ycols(s, prune)));
   const int ztiles = (s->nzl + TL - 1) / TL;
   dim3 grid((unsigned)(ztiles * (prune ? s->nkx : s->nxh)), (unsigned)nfields);
   LAPS_LAUNCH((k_inv_y<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, V1, V2, s->nzl, s->tw_y, s->nxh,
@@ -412,7 +449,7 @@ int do_inv_x_tl(S* s, const cplx* V2, const RealDst& dst, int nfields, bool prun
   char name[32]; std::snprintf(name, sizeof(name), "inv_x%d", nfields);
   typedef Tile<N, TL> T;
   LAPS_CK(s, prepare_kernel(k_inv_x<N, TL>, T::SMEM, T::MINB));
-  LaunchScope ls(s, name);
+  LaunchScope ls(s, name, nfields * (bytes_real(s) + bytes_xcols(s, prune)));
   dim3 grid((unsigned)(s->xz * (s->xy / (2 * TL))), (unsigned)nfields);
   LAPS_LAUNCH((k_inv_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, V2, dst, s->xz, s->xy, s->tw_x,
               prune ? s->nkx : s->nxh);
@@ -432,7 +469,7 @@ template <int N, int CG>
 int do_spec_z_cg(S* s, const ZParams& zp, int ntasks, const char* name) {
   typedef ZTile<N, CG> T;
   LAPS_CK(s, prepare_kernel(k_spec_z<N, CG>, T::SMEM, T::MINB));
-  LaunchScope ls(s, name);
+  LaunchScope ls(s, name, bytes_z(s, zp, ntasks));
   if (zp.ncolc == 0) return 0;   // this rank owns no surviving column
   dim3 grid((unsigned)((zp.ncolc + CG - 1) / CG), (unsigned)ntasks);
   LAPS_LAUNCH((k_spec_z<N, CG>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, zp);
@@ -452,7 +489,7 @@ template <int N, int CG>
 int do_rhs_z_cg(S* s, const ZParams& zp, int ntasks) {
   typedef RTile<N, CG> T;
   LAPS_CK(s, prepare_kernel(k_rhs_z<N, CG>, T::SMEM, T::MINB));
-  LaunchScope ls(s, "spec_z");
+  LaunchScope ls(s, "spec_z", bytes_z(s, zp, ntasks));
   if (zp.ncolc == 0) return 0;   // this rank owns no surviving column
   const int ngroups = (zp.ncolc + CG - 1) / CG;
   const long long nitems = (long long)ngroups * ntasks;
@@ -475,7 +512,8 @@ int do_incomp_z(S* s, const ZParams& zp) {
   constexpr int CG = rcg(N);
   typedef ITile<N, CG> T;
   LAPS_CK(s, prepare_kernel(k_incomp_z<N, CG>, T::SMEM, T::MINB));
-  LaunchScope ls(s, "incomp_z");
+  const double iline = 16.0 * (double)zp.ncolc * zp.nz, imodes = zp.kzprune ? 16.0 * (double)s->pr_modes : iline;
+  LaunchScope ls(s, "incomp_z", (3 + 5) * iline + imodes * (5 + (zp.read_rk ? 5 : 0) + 5 + (zp.write_rk ? 5 : 0)));
   if (zp.ncolc == 0) return 0;
   dim3 grid((unsigned)((zp.ncolc + CG - 1) / CG));
   LAPS_LAUNCH((k_incomp_z<N, CG>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, zp);
@@ -712,7 +750,7 @@ int stage_incomp(S* s, int irk) {
     FluxIncParams f;
     f.uu = s->uu; f.J = s->J; f.G = s->G; f.F = buf_F(s); f.npts = s->npts;
     f.hall = p.if_hall; f.di = p.ion_inertial_length;
-    LaunchScope ls(s, "flux");
+    LaunchScope ls(s, "flux", (8 + 3 + 9 + 6) * bytes_real(s));
     LAPS_LAUNCH(k_flux_incomp, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, f);
     LAPS_TRY(check_launch(s, "k_flux_incomp"));
   }
@@ -787,7 +825,7 @@ int stage_front(S* s, bool with_cfl) {
     const size_t plane = (size_t)s->nx * s->ny;
     const int cz = std::min(s->tune_zchunk, s->nzl);
     f.fstride = (size_t)cz * plane;
-    LaunchScope ls(s, "flux+fwd_x");
+    LaunchScope ls(s, "flux+fwd_x", (8 + (p.if_hall ? 3 : 0) + 2 * s->nf) * bytes_real(s) + s->nf * bytes_xcols(s, true));
     for (int z0 = 0; z0 < s->nzl; z0 += cz) {
       const int nzc = std::min(cz, s->nzl - z0);
       f.in_off = (size_t)z0 * plane; f.count = (size_t)nzc * plane;
@@ -806,7 +844,9 @@ int stage_front(S* s, bool with_cfl) {
     f.hall = p.if_hall; f.aeb = p.if_AEB; f.gamma = p.adiabatic_index; f.di = p.ion_inertial_length; f.tau = s->tau;
     f.z_radial = s->two_d && p.if_z_radial;
     for (int j = 0; j < 19; ++j) f.slot[j] = s->fslot[j];
-    LaunchScope ls(s, with_cfl ? "flux+cfl" : "flux");
+    int stored = 0;
+    for (int j = 0; j < 19; ++j) stored += s->fslot[j] >= 0;
+    LaunchScope ls(s, with_cfl ? "flux+cfl" : "flux", (8 + (p.if_hall ? 3 : 0) + stored) * bytes_real(s));
     if (with_cfl) {
       fill_cfl_params(s, f.cfl);
       LAPS_LAUNCH(k_flux<true>, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, f);
@@ -1066,7 +1106,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
   s->bytesY = (size_t)nmax * s->w1sz * sizeof(cplx);
   s->bytesZ = (size_t)std::max(s->nf, 8) * s->csz * sizeof(cplx);   // the 8 state fields pass through W2 in laps_set_primitive
   bool ok = true;
-  auto alloc = [&](void** ptr, size_t bytes) { if (ok && cudaMalloc(ptr, bytes) != cudaSuccess) ok = false; };
+  auto alloc = [&](void** ptr, size_t bytes) { if (ok && cudaMalloc(ptr, bytes) != cudaSuccess) ok = false; else if (ok) s->dev_bytes += bytes; };
   alloc((void**)&s->uu, 8 * s->npts * sizeof(double));
   if (p.if_hall || s->incomp) alloc((void**)&s->J, 3 * s->npts * sizeof(double));
   if (s->incomp) alloc((void**)&s->G, 9 * s->npts * sizeof(double));
@@ -1160,6 +1200,16 @@ int laps_create(const laps_params* params, laps_handle* out) {
       if (cudaMemcpy(s->d_kymax_x, kym.data(), s->nxh * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
           (!cmap.empty() && cudaMemcpy(s->d_colmap, cmap.data(), cmap.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess))
         return fail("pruning table upload failed");
+    }
+    {  // surviving (kx, ky) columns of all ranks
+      long long n = 0;
+      for (int kx = 0; kx < s->nkx; ++kx)
+        for (int ky = 0; ky < s->ny; ++ky) {
+          if (ky > s->kymax && ky < s->ny - s->kymax) continue;
+          if (masked && p.dealias_option == 1 && tune_circle && dax[kx] + day[ky] >= s->da_thresh) continue;
+          ++n;
+        }
+      s->pr_cols_all = n;
     }
     {  // surviving modes of this rank (traffic model)
       long long m = 0;
@@ -1285,7 +1335,7 @@ static int set_primitive_body(laps_handle s, const double* uu_local) {
 // initial_calc_conserve_variable + transform_uu_real_to_fourier on the primitive fields already in s->uu
 static int finish_set_primitive(laps_handle s) {
   {
-    LaunchScope ls(s, "prim_to_cons");
+    LaunchScope ls(s, "prim_to_cons", (8 + 4) * bytes_real(s));
     LAPS_LAUNCH(k_prim_to_cons, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, s->uu, s->npts, s->p.adiabatic_index, s->incomp ? 1 : 0);
     LAPS_TRY(check_launch(s, "k_prim_to_cons"));
   }
@@ -1427,7 +1477,7 @@ static int vardt_body(laps_handle s, double* dt_inout) {  // mhd.f90:328-429
   CflParams c;
   fill_cfl_params(s, c);
   {
-    LaunchScope ls(s, "cfl");
+    LaunchScope ls(s, "cfl", 8 * bytes_real(s));
     if (s->incomp) LAPS_LAUNCH(k_cfl_incomp, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, c);   // src_incompressible/mhd.f90:369-476
     else LAPS_LAUNCH(k_cfl, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, c);
     LAPS_TRY(check_launch(s, "k_cfl"));
@@ -1516,6 +1566,37 @@ static int get_profile_body(laps_handle s, char* names, float* ms, int32_t cap, 
   return 0;
 }
 
+int laps_get_profile_bytes(laps_handle s, double* bytes, int32_t cap, int32_t* count) {
+  if (!s || !count) return 1;
+  int n = 0;
+  for (auto& pe : s->prof) {
+    if (n >= cap) break;
+    if (bytes) bytes[n] = pe.bytes;
+    ++n;
+  }
+  *count = n;
+  return 0;
+}
+
+int laps_get_footprint(laps_handle s, int64_t* device_bytes) {
+  if (!s || !device_bytes) return 1;
+  *device_bytes = (int64_t)s->dev_bytes;
+  return 0;
+}
+
+// Measurement helper: the LAPS_TUNE_* switches that only select between equivalent kernels / launch shapes, settable on a
+// live handle so that one process can time the alternatives on the same state.  Unknown names fail.
+int laps_set_tune(laps_handle s, const char* name, int32_t value) {
+  if (!s || !name) return 1;
+  const std::string n(name);
+  int* slot = n == "rhs" ? &s->tune_rhs : n == "rcg" ? &s->tune_rcg : n == "cgz" ? &s->tune_cgz : n == "z" ? &s->tune_z :
+              n == "spec" ? &s->tune_spec : nullptr;
+  if (!slot) { s->err = "laps_set_tune: unknown switch '" + n + "'"; return 1; }
+  *slot = value;
+  s->front_ready = false;
+  return 0;
+}
+
 static int max_div_fourier(laps_handle s, int v0, double* out) {
   DivbParams d;
   d.v0 = v0;
@@ -1526,7 +1607,7 @@ static int max_div_fourier(laps_handle s, int v0, double* out) {
   d.mode2d = s->two_d; d.z_radial = s->two_d && s->p.if_AEB && s->p.if_z_radial;
   d.partial = s->d_partial;
   {
-    LaunchScope ls(s, "divb");
+    LaunchScope ls(s, "divb", 3 * 16.0 * (double)s->csz);
     LAPS_LAUNCH(k_divb, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, d);
     LAPS_TRY(check_launch(s, "k_divb"));
   }
@@ -1572,7 +1653,7 @@ static int max_div_real_body(laps_handle s, double out[2]) {
   if (!s->two_d) LAPS_TRY(inv_y(s, buf_V1(s), buf_V2(s), 2, prune));
   LAPS_TRY(inv_x(s, s->two_d ? buf_V1(s) : buf_V2(s), d, 2, prune));
   {
-    LaunchScope ls(s, "absmax");
+    LaunchScope ls(s, "absmax", 2 * bytes_real(s));
     LAPS_LAUNCH(k_absmax, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, (const double*)d.ptr[0], s->npts, 2, s->d_partial);
     LAPS_TRY(check_launch(s, "k_absmax"));
   }
@@ -1597,7 +1678,7 @@ static int check_nan_body(laps_handle s, int32_t* is_nan) {
   if (!s || !is_nan) return 1;
   LAPS_TRY(require_state(s));
   {
-    LaunchScope ls(s, "check_nan");
+    LaunchScope ls(s, "check_nan", 8 * bytes_real(s));
     LAPS_LAUNCH(k_nan_flag, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, (const double*)s->uu, 8 * s->npts, s->d_partial);
     LAPS_TRY(check_launch(s, "k_nan_flag"));
   }
@@ -1614,7 +1695,7 @@ int laps_get_rho0(laps_handle s, double* rho0) {
 
 static int moments(laps_handle s, double sums[18]) {
   {
-    LaunchScope ls(s, "moments1");
+    LaunchScope ls(s, "moments1", 8 * bytes_real(s));
     LAPS_LAUNCH(k_moments1, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, s->uu, s->npts, s->p.adiabatic_index, s->d_partial, s->incomp ? 1 : 0);
     LAPS_TRY(check_launch(s, "k_moments1"));
   }
@@ -1635,7 +1716,7 @@ static int rms_body(laps_handle s, double out[19]) {  // mhdrms.f90:53-126
     out[8 + j] = sq - ave * ave;
   }
   {
-    LaunchScope ls(s, "moments2");
+    LaunchScope ls(s, "moments2", 4 * bytes_real(s));
     LAPS_LAUNCH(k_moments2, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, s->uu, s->npts, out[1], out[2], out[3], s->d_partial);
     LAPS_TRY(check_launch(s, "k_moments2"));
   }
@@ -1662,7 +1743,7 @@ static int get_state_body(laps_handle s, double* uu_local, double* uu_prim_local
   if (uu_prim_local) {
     double* prim = prim_scratch(s);
     {
-      LaunchScope ls(s, "cons_to_prim");
+      LaunchScope ls(s, "cons_to_prim", (8 + 4) * bytes_real(s));
       LAPS_LAUNCH(k_cons_to_prim, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, (const double*)s->uu, prim, s->npts, s->p.adiabatic_index, s->incomp ? 1 : 0);
       LAPS_TRY(check_launch(s, "k_cons_to_prim"));
     }
@@ -1683,7 +1764,7 @@ static int get_output_body(laps_handle s, double* out_local, int32_t primitive) 
   } else {
     double* prim = prim_scratch(s);
     {
-      LaunchScope ls(s, "cons_to_prim");
+      LaunchScope ls(s, "cons_to_prim", (8 + 4) * bytes_real(s));
       LAPS_LAUNCH(k_cons_to_prim, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, (const double*)s->uu, prim, s->npts, s->p.adiabatic_index, s->incomp ? 1 : 0);
       LAPS_TRY(check_launch(s, "k_cons_to_prim"));
     }

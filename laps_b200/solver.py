@@ -272,13 +272,28 @@ class Solver:
     def set_profiling(self, on: bool):
         self._ck(self._lib.laps_set_profiling(self._h, 1 if on else 0))
 
-    def get_profile(self, cap=512):
+    def get_profile(self, cap=512, with_bytes=False):
+        """(name, ms) of every launch of the last instrumented evolve/step; with_bytes: (name, ms, algorithmic bytes)."""
         names = C.create_string_buffer(cap * 32)
         ms = (C.c_float * cap)()
         cnt = C.c_int32()
         self._ck(self._lib.laps_get_profile(self._h, names, ms, cap, C.byref(cnt)))
+        by = (C.c_double * cap)()
+        if with_bytes:
+            c2 = C.c_int32()
+            self._ck(self._lib.laps_get_profile_bytes(self._h, by, cap, C.byref(c2)))
         out = []
         for i in range(cnt.value):
             nm = names.raw[i * 32:(i + 1) * 32].split(b"\0", 1)[0].decode()
-            out.append((nm, ms[i]))
+            out.append((nm, ms[i], by[i]) if with_bytes else (nm, ms[i]))
         return out
+
+    def footprint(self) -> int:
+        """Device bytes this handle allocated (laps_get_footprint)."""
+        out = C.c_int64()
+        self._ck(self._lib.laps_get_footprint(self._h, C.byref(out)))
+        return out.value
+
+    def set_tune(self, name: str, value: int):
+        """laps_set_tune: switch between equivalent kernels / launch shapes on a live handle (measurement helper)."""
+        self._ck(self._lib.laps_set_tune(self._h, name.encode(), int(value)))

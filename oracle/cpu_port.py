@@ -54,6 +54,8 @@ def _load():
         lib.cpu_step.restype = C.c_double
         lib.cpu_get_state.argtypes = [C.c_void_p, dp, dp, dp, dp]
         lib.cpu_threads.restype = C.c_int
+        lib.cpu_set_threads.argtypes = [C.c_int]
+        lib.cpu_set_fft.argtypes = [C.c_int]
         _lib = lib
     return _lib
 
@@ -78,6 +80,14 @@ class CpuPort:
     @property
     def threads(self) -> int:
         return int(self._lib.cpu_threads())
+
+    def set_threads(self, n: int):
+        """OpenMP threads for the calls that follow (overrides the launcher's OMP_NUM_THREADS)."""
+        self._lib.cpu_set_threads(int(n))
+
+    def set_fft(self, batched: bool):
+        """True (default): batched SIMD transforms; False: the per-line transforms (for comparison)."""
+        self._lib.cpu_set_fft(1 if batched else 0)
 
     def set_primitive(self, prim):
         a = np.ascontiguousarray(prim, dtype=np.float64)

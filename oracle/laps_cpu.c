@@ -12,8 +12,9 @@
  * (mhdrhs.f90:21-124), calc_rhs (:174-279), rkt (rktmod.f90:34-62), dealias (dealiasing.f90:70-112),
  * update_uu_prim_from_uu (mhdrhs.f90:282-294), vardt (mhd.f90:328-429).  OpenMP threads stand in for the MPI
  * ranks (the transposes of parallel.f90 are then plain strided access).  FFTW is replaced by transforms written
- * here (power-of-two sizes only): radix-2 passes taken two at a time, real lines through a half-length complex
- * transform as FFTW's r2c/c2r plans do.
+ * here (power-of-two sizes only): batched Stockham radix-4 transforms, LAPS_BL lines per SIMD batch, real lines
+ * through a half-length complex transform as FFTW's r2c/c2r plans do (the per-line radix-2/4 version this file
+ * started with stays selectable, cpu_set_fft(0), so that the gain can be stated).
  *
  * Arrays are C order a[v][iz][iy][ix] = Fortran a(ix,iy,iz,v); spectra [v][kz][ky][kx], kx = 0..nx/2.
  */
@@ -125,8 +126,214 @@ static int maxdim(const cpu_state* s) {
   return nx > ny ? (nx > nz ? nx : nz) : (ny > nz ? ny : nz);
 }
 
+/* ------------------------------------------------------------------ batched transforms
+ * The 3-D transforms below run LAPS_BL lines at a time through one Stockham autosort transform whose innermost,
+ * contiguous index is the line (split real / imaginary planes, so every butterfly is straight SIMD arithmetic over the
+ * batch: AVX-512 / AVX2 clones are picked at load time), and gather LAPS_BL neighbouring kx columns per cache line in
+ * the y and z passes instead of one strided element per line.  Same arithmetic as a per-line plan; this is what makes
+ * the CPU baseline a fair stand-in for an FFTW build (measured against the per-line version it replaces: see
+ * DESIGN.md, CPU baseline). */
+#define LAPS_BL 8
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define LAPS_CLONES __attribute__((target_clones("avx512f", "avx2", "default")))
+#else
+#define LAPS_CLONES
+#endif
+
+/* radix-4 Stockham passes (+ one radix-2 pass when log2 m is odd) over [point][LAPS_BL]; returns 0 if the result is
+ * in (xr, xi), 1 if it is in (yr, yi).  tw = exp(-2 pi i q / ntab), ntab a multiple of m. */
+LAPS_CLONES static int fft_batch(double* restrict xr, double* restrict xi, double* restrict yr, double* restrict yi,
+                                 int m, const cplx* tw, int ntab, int dir) {
+  int n = m, st = 1, flip = 0;
+  const double sg = dir < 0 ? 1.0 : -1.0;        /* forward: W = exp(-i..), j(b-d) enters with the signs below */
+  while (n >= 4) {
+    const int n1 = n / 4, step = ntab / n;
+    for (int p = 0; p < n1; ++p) {
+      cplx w1 = tw[p * step], w2 = tw[2 * p * step], w3 = tw[3 * p * step];
+      if (dir > 0) { w1 = conj(w1); w2 = conj(w2); w3 = conj(w3); }
+      const double w1r = creal(w1), w1i = cimag(w1), w2r = creal(w2), w2i = cimag(w2), w3r = creal(w3), w3i = cimag(w3);
+      for (int q = 0; q < st; ++q) {
+        const size_t ia = (size_t)(q + st * p) * LAPS_BL, ib = ia + (size_t)st * n1 * LAPS_BL;
+        const size_t ic = ib + (size_t)st * n1 * LAPS_BL, id = ic + (size_t)st * n1 * LAPS_BL;
+        const size_t o0 = (size_t)(q + st * 4 * p) * LAPS_BL, o1 = o0 + (size_t)st * LAPS_BL, o2 = o1 + (size_t)st * LAPS_BL, o3 = o2 + (size_t)st * LAPS_BL;
+#pragma omp simd
+        for (int b = 0; b < LAPS_BL; ++b) {
+          const double ar = xr[ia + b], ai = xi[ia + b], br = xr[ib + b], bi = xi[ib + b];
+          const double cr = xr[ic + b], ci = xi[ic + b], dr = xr[id + b], di = xi[id + b];
+          const double apcr = ar + cr, apci = ai + ci, amcr = ar - cr, amci = ai - ci;
+          const double bpdr = br + dr, bpdi = bi + di;
+          /* j (b - d): real part -(bi - di), imaginary part (br - dr); forward uses amc - j(b-d) for output 1 */
+          const double jr = -sg * (bi - di), ji = sg * (br - dr);
+          yr[o0 + b] = apcr + bpdr; yi[o0 + b] = apci + bpdi;
+          const double t1r = amcr - jr, t1i = amci - ji;
+          yr[o1 + b] = w1r * t1r - w1i * t1i; yi[o1 + b] = w1r * t1i + w1i * t1r;
+          const double t2r = apcr - bpdr, t2i = apci - bpdi;
+          yr[o2 + b] = w2r * t2r - w2i * t2i; yi[o2 + b] = w2r * t2i + w2i * t2r;
+          const double t3r = amcr + jr, t3i = amci + ji;
+          yr[o3 + b] = w3r * t3r - w3i * t3i; yi[o3 + b] = w3r * t3i + w3i * t3r;
+        }
+      }
+    }
+    { double* t = xr; xr = yr; yr = t; t = xi; xi = yi; yi = t; }
+    flip ^= 1; n = n1; st *= 4;
+  }
+  if (n == 2) {
+    for (int q = 0; q < st; ++q) {
+      const size_t ia = (size_t)q * LAPS_BL, ib = ia + (size_t)st * LAPS_BL;
+#pragma omp simd
+      for (int b = 0; b < LAPS_BL; ++b) {
+        const double ar = xr[ia + b], ai = xi[ia + b], br = xr[ib + b], bi = xi[ib + b];
+        yr[ia + b] = ar + br; yi[ia + b] = ai + bi; yr[ib + b] = ar - br; yi[ib + b] = ai - bi;
+      }
+    }
+    flip ^= 1;
+  }
+  return flip;
+}
+
+typedef struct { double *xr, *xi, *yr, *yi; } batch_buf;
+static batch_buf batch_alloc(int m) {
+  batch_buf b;
+  const size_t n = (size_t)m * LAPS_BL;
+  b.xr = (double*)aligned_alloc(64, 4 * n * sizeof(double));
+  b.xi = b.xr + n; b.yr = b.xi + n; b.yi = b.yr + n;
+  return b;
+}
+
+/* c2c along a strided axis for nb (<= LAPS_BL) neighbouring columns: base[i * stride + b], i < m; scaled by `scale` */
+LAPS_CLONES static void c2c_columns(cplx* base, size_t stride, int m, int nb, const cplx* tw, int dir, double scale, batch_buf B) {
+  for (int i = 0; i < m; ++i) {
+    const double* src = (const double*)(base + (size_t)i * stride);
+    for (int b = 0; b < nb; ++b) { B.xr[(size_t)i * LAPS_BL + b] = src[2 * b]; B.xi[(size_t)i * LAPS_BL + b] = src[2 * b + 1]; }
+    for (int b = nb; b < LAPS_BL; ++b) { B.xr[(size_t)i * LAPS_BL + b] = 0.0; B.xi[(size_t)i * LAPS_BL + b] = 0.0; }
+  }
+  const int f = fft_batch(B.xr, B.xi, B.yr, B.yi, m, tw, m, dir);
+  const double* rr = f ? B.yr : B.xr; const double* ri = f ? B.yi : B.xi;
+  for (int i = 0; i < m; ++i) {
+    double* dst = (double*)(base + (size_t)i * stride);
+    for (int b = 0; b < nb; ++b) { dst[2 * b] = rr[(size_t)i * LAPS_BL + b] * scale; dst[2 * b + 1] = ri[(size_t)i * LAPS_BL + b] * scale; }
+  }
+}
+
+/* r2c of nb (<= LAPS_BL) real lines a[b * lstride + j] through one batched complex transform of n/2 points;
+ * out[b * ostride + k] = X_b[k] * scale, k = 0..n/2 */
+LAPS_CLONES static void r2c_lines(const double* a, size_t lstride, int n, int nb, const cplx* tw, cplx* out, size_t ostride, double scale, batch_buf B) {
+  const int m = n / 2;
+  for (int b = 0; b < LAPS_BL; ++b) {
+    if (b < nb) { const double* x = a + (size_t)b * lstride; for (int j = 0; j < m; ++j) { B.xr[(size_t)j * LAPS_BL + b] = x[2 * j]; B.xi[(size_t)j * LAPS_BL + b] = x[2 * j + 1]; } }
+    else for (int j = 0; j < m; ++j) { B.xr[(size_t)j * LAPS_BL + b] = 0.0; B.xi[(size_t)j * LAPS_BL + b] = 0.0; }
+  }
+  const int f = fft_batch(B.xr, B.xi, B.yr, B.yi, m, tw, n, -1);
+  const double* zr = f ? B.yr : B.xr; const double* zi = f ? B.yi : B.xi;
+  for (int b = 0; b < nb; ++b) {
+    cplx* o = out + (size_t)b * ostride;
+    o[0] = (zr[b] + zi[b]) * scale;
+    o[m] = (zr[b] - zi[b]) * scale;
+  }
+  for (int k = 1; k < m; ++k) {
+    const double wr = creal(tw[k]), wi = cimag(tw[k]);
+    for (int b = 0; b < nb; ++b) {
+      const double ar = zr[(size_t)k * LAPS_BL + b], ai = zi[(size_t)k * LAPS_BL + b];
+      const double cr = zr[(size_t)(m - k) * LAPS_BL + b], ci = -zi[(size_t)(m - k) * LAPS_BL + b];   /* conj(Z[m-k]) */
+      const double sr = ar + cr, si = ai + ci, dr = ar - cr, di = ai - ci;
+      /* 0.5 * (s - i w d) */
+      const double tr = wr * dr - wi * di, ti = wr * di + wi * dr;     /* w d */
+      out[(size_t)b * ostride + k] = (0.5 * scale) * ((sr + ti) + I * (si - tr));
+    }
+  }
+}
+
+/* c2r (unnormalised backward) of nb half spectra in[b * istride + k] to real lines a[b * lstride + j]; the imaginary
+ * parts of the DC and Nyquist bins are ignored, as FFTW's c2r does */
+LAPS_CLONES static void c2r_lines(const cplx* in, size_t istride, int n, int nb, const cplx* tw, double* a, size_t lstride, batch_buf B) {
+  const int m = n / 2;
+  for (int b = 0; b < LAPS_BL; ++b) {
+    if (b >= nb) { for (int k = 0; k < m; ++k) { B.xr[(size_t)k * LAPS_BL + b] = 0.0; B.xi[(size_t)k * LAPS_BL + b] = 0.0; } continue; }
+    const cplx* x = in + (size_t)b * istride;
+    const double x0 = creal(x[0]), xm = creal(x[m]);
+    B.xr[b] = x0 + xm; B.xi[b] = x0 - xm;
+    for (int k = 1; k < m; ++k) {
+      const cplx xk = x[k], xc = conj(x[m - k]);
+      const cplx v = (xk + xc) + I * conj(tw[k]) * (xk - xc);
+      B.xr[(size_t)k * LAPS_BL + b] = creal(v); B.xi[(size_t)k * LAPS_BL + b] = cimag(v);
+    }
+  }
+  const int f = fft_batch(B.xr, B.xi, B.yr, B.yi, m, tw, n, +1);
+  const double* zr = f ? B.yr : B.xr; const double* zi = f ? B.yi : B.xi;
+  for (int b = 0; b < nb; ++b) {
+    double* x = a + (size_t)b * lstride;
+    for (int j = 0; j < m; ++j) { x[2 * j] = zr[(size_t)j * LAPS_BL + b]; x[2 * j + 1] = zi[(size_t)j * LAPS_BL + b]; }
+  }
+}
+
+static int g_per_line_fft = 0;   /* cpu_set_fft(0): the per-line transforms above (the version this file started with), for comparison */
+
 /* fftw.f90:42-71 + 136-180: r2c along x (/nx), c2c along y (/ny), c2c along z (/nz); one field */
+static void forward3d_per_line(const cpu_state* s, const double* a, cplx* w);
+static void inverse3d_per_line(const cpu_state* s, cplx* w, double* a);
+
 static void forward3d(const cpu_state* s, const double* a, cplx* w) {
+  if (g_per_line_fft) { forward3d_per_line(s, a, w); return; }
+  const int nx = s->p.nx, ny = s->p.ny, nz = s->p.nz, nxh = s->nxh;
+  const int nbx = (nxh + LAPS_BL - 1) / LAPS_BL, nby = (ny + LAPS_BL - 1) / LAPS_BL;
+#pragma omp parallel
+  {
+    batch_buf B = batch_alloc(maxdim(s));
+#pragma omp for collapse(2) schedule(static)
+    for (int iz = 0; iz < nz; ++iz)
+      for (int jb = 0; jb < nby; ++jb) {
+        const int iy = jb * LAPS_BL, nb = ny - iy < LAPS_BL ? ny - iy : LAPS_BL;
+        r2c_lines(a + ((size_t)iz * ny + iy) * nx, (size_t)nx, nx, nb, s->twx, w + ((size_t)iz * ny + iy) * nxh, (size_t)nxh, 1.0 / nx, B);
+      }
+#pragma omp for collapse(2) schedule(static)
+    for (int iz = 0; iz < nz; ++iz)
+      for (int kb = 0; kb < nbx; ++kb) {
+        const int kx = kb * LAPS_BL, nb = nxh - kx < LAPS_BL ? nxh - kx : LAPS_BL;
+        c2c_columns(w + (size_t)iz * ny * nxh + kx, (size_t)nxh, ny, nb, s->twy, -1, 1.0 / ny, B);
+      }
+#pragma omp for collapse(2) schedule(static)
+    for (int iy = 0; iy < ny; ++iy)
+      for (int kb = 0; kb < nbx; ++kb) {
+        const int kx = kb * LAPS_BL, nb = nxh - kx < LAPS_BL ? nxh - kx : LAPS_BL;
+        c2c_columns(w + (size_t)iy * nxh + kx, (size_t)ny * nxh, nz, nb, s->twz, -1, 1.0 / nz, B);
+      }
+    free(B.xr);
+  }
+}
+
+/* fftw.f90:73-103 + 182-222: unnormalised backward c2c along z, then y, then c2r along x (w is overwritten) */
+static void inverse3d(const cpu_state* s, cplx* w, double* a) {
+  if (g_per_line_fft) { inverse3d_per_line(s, w, a); return; }
+  const int nx = s->p.nx, ny = s->p.ny, nz = s->p.nz, nxh = s->nxh;
+  const int nbx = (nxh + LAPS_BL - 1) / LAPS_BL, nby = (ny + LAPS_BL - 1) / LAPS_BL;
+#pragma omp parallel
+  {
+    batch_buf B = batch_alloc(maxdim(s));
+#pragma omp for collapse(2) schedule(static)
+    for (int iy = 0; iy < ny; ++iy)
+      for (int kb = 0; kb < nbx; ++kb) {
+        const int kx = kb * LAPS_BL, nb = nxh - kx < LAPS_BL ? nxh - kx : LAPS_BL;
+        c2c_columns(w + (size_t)iy * nxh + kx, (size_t)ny * nxh, nz, nb, s->twz, +1, 1.0, B);
+      }
+#pragma omp for collapse(2) schedule(static)
+    for (int iz = 0; iz < nz; ++iz)
+      for (int kb = 0; kb < nbx; ++kb) {
+        const int kx = kb * LAPS_BL, nb = nxh - kx < LAPS_BL ? nxh - kx : LAPS_BL;
+        c2c_columns(w + (size_t)iz * ny * nxh + kx, (size_t)nxh, ny, nb, s->twy, +1, 1.0, B);
+      }
+#pragma omp for collapse(2) schedule(static)
+    for (int iz = 0; iz < nz; ++iz)
+      for (int jb = 0; jb < nby; ++jb) {
+        const int iy = jb * LAPS_BL, nb = ny - iy < LAPS_BL ? ny - iy : LAPS_BL;
+        c2r_lines(w + ((size_t)iz * ny + iy) * nxh, (size_t)nxh, nx, nb, s->twx, a + ((size_t)iz * ny + iy) * nx, (size_t)nx, B);
+      }
+    free(B.xr);
+  }
+}
+
+/* ---- the per-line version (cpu_set_fft(0)) ---- */
+/* fftw.f90:42-71 + 136-180: r2c along x (/nx), c2c along y (/ny), c2c along z (/nz); one field */
+static void forward3d_per_line(const cpu_state* s, const double* a, cplx* w) {
   const int nx = s->p.nx, ny = s->p.ny, nz = s->p.nz, nxh = s->nxh;
 #pragma omp parallel
   {
@@ -160,7 +367,7 @@ static void forward3d(const cpu_state* s, const double* a, cplx* w) {
 }
 
 /* fftw.f90:73-103 + 182-222: unnormalised backward c2c along z, then y, then c2r along x (w is overwritten) */
-static void inverse3d(const cpu_state* s, cplx* w, double* a) {
+static void inverse3d_per_line(const cpu_state* s, cplx* w, double* a) {
   const int nx = s->p.nx, ny = s->p.ny, nz = s->p.nz, nxh = s->nxh;
 #pragma omp parallel
   {
@@ -257,6 +464,18 @@ void cpu_destroy(void* h) {
   free(s->uu); free(s->prim); free(s->flux); free(s->J); free(s->uf); free(s->ff); free(s->fnl); free(s->fnl_rk); free(s->jf);
   free(s->ksq); free(s->wnx); free(s->wny); free(s->wnz); free(s->twx); free(s->twy); free(s->twz);
   free(s->filtx); free(s->filty); free(s->filtz); free(s);
+}
+
+/* 1: batched SIMD transforms (default), 0: the per-line transforms */
+void cpu_set_fft(int batched) { g_per_line_fft = !batched; }
+
+/* all host threads, whatever OMP_NUM_THREADS the launcher exported (torchrun sets it to 1) */
+void cpu_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
 }
 
 int cpu_threads(void) {
