@@ -158,7 +158,18 @@ struct laps_solver {
   int num_sms = 148;
   double da_thresh = 0;
   void* ipc_opened[LAPS_MAX_RANKS][3];   // mappings obtained with cudaIpcOpenMemHandle
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;    // main stream: every API call is ordered on it
+  // Second stream for the passes that store into the peers' buffers over NVLink (forward y pass, z passes) and the flag
+  // barriers that order them, so that they run beside the HBM-only passes of the other field chunk (stage_overlap).
+  // `cs` is the stream the pass launchers enqueue on (StreamScope), `cch` its flag channel (exchange.cuh).
+  cudaStream_t xstream = nullptr;
+  cudaStream_t cs = nullptr;
+  int cch = 0;
+  int cap_warps = 0;                 // > 0: the exchange-side launchers hold their grids to this many warps per SM (grid-stride loops)
+  cudaEvent_t ev_link[16] = {nullptr};
+  int ev_next = 0;
+  int tune_overlap = -1;             // LAPS_TUNE_OVERLAP: -1 = default (on from 2 ranks on), 0 = one stream, 1 = two streams
+  int ovl_y_warps = 16, ovl_z_warps = 8, ovl_chunks = 3;   // warps per SM given to the exchange-side passes; forward field chunks
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_scal = nullptr;
   int launches = 0;
   bool profiling = false;
@@ -271,12 +282,20 @@ struct LaunchScope {
       pe.bytes = bytes;
       std::snprintf(pe.name, sizeof(pe.name), "%s", name);
       cudaEventCreate(&pe.e0); cudaEventCreate(&pe.e1);
-      cudaEventRecord(pe.e0, s->stream);
+      cudaEventRecord(pe.e0, s->cs);
       s->prof.push_back(pe);
       idx = (int)s->prof.size() - 1;
     }
   }
-  ~LaunchScope() { if (idx >= 0) cudaEventRecord(s->prof[idx].e1, s->stream); }
+  ~LaunchScope() { if (idx >= 0) cudaEventRecord(s->prof[idx].e1, s->cs); }
+};
+
+// launches inside the scope go to `st` with flag channel `ch` and (cap > 0) at most `cap` warps per SM per exchange-side launch
+int capped_ctas(const S* s, int nthreads) { return std::max(1, s->num_sms * s->cap_warps / std::max(1, nthreads / 32)); }
+struct StreamScope {
+  S* s; cudaStream_t prev; int prev_ch, prev_cap;
+  StreamScope(S* s_, cudaStream_t st, int ch, int cap) : s(s_), prev(s_->cs), prev_ch(s_->cch), prev_cap(s_->cap_warps) { s->cs = st; s->cch = ch; s->cap_warps = cap; }
+  ~StreamScope() { s->cs = prev; s->cch = prev_ch; s->cap_warps = prev_cap; }
 };
 
 int check_launch(S* s, const char* what) {
@@ -379,11 +398,11 @@ int do_fwd_x_tl(S* s, const double* in, size_t fstride, int nfields, cplx* W1, b
   dim3 grid((unsigned)(np * (s->xy / (2 * TL))), (unsigned)nfields);
   if (scoped) {
     LaunchScope ls(s, name, nfields * ((double)np * s->xy * (8.0 * N + 16.0 * (prune ? s->nkx : s->nxh))));
-    LAPS_LAUNCH((k_fwd_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, in, fstride, W1, s->xz, s->xy, s->tw_x,
+    LAPS_LAUNCH((k_fwd_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->cs, in, fstride, W1, s->xz, s->xy, s->tw_x,
                 1.0 / N, prune ? s->nkx : s->nxh, zl0);
   } else {
     ++s->launches;
-    LAPS_LAUNCH((k_fwd_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, in, fstride, W1, s->xz, s->xy, s->tw_x,
+    LAPS_LAUNCH((k_fwd_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->cs, in, fstride, W1, s->xz, s->xy, s->tw_x,
                 1.0 / N, prune ? s->nkx : s->nxh, zl0);
   }
   return check_launch(s, "k_fwd_x");
@@ -409,24 +428,31 @@ int do_flux_fwd_x(S* s, const FusedFluxParams& fp) {
     LAPS_CK(s, prepare_kernel(k_flux_fwd_x<N, kFuseGroups>, T::SMEM, ctas));
     LaunchScope ls(s, "flux_fwd_x", (8 + (s->p.if_hall ? 3 : 0)) * bytes_real(s) + s->nf * bytes_xcols(s, true));
     dim3 grid((unsigned)(s->nzl * (s->ny / 2)));
-    LAPS_LAUNCH((k_flux_fwd_x<N, kFuseGroups>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, fp);
+    LAPS_LAUNCH((k_flux_fwd_x<N, kFuseGroups>), grid, dim3(T::NTHREADS), T::SMEM, s->cs, fp);
     return check_launch(s, "k_flux_fwd_x");
   } else {
     s->err = "k_flux_fwd_x: line too long for the shared-memory staging"; return 1;
   }
 }
 
+// f0: first field slot of the launch (W1 points at it; the peers' W2 bases are advanced to it here)
 template <int N>
-int do_fwd_y(S* s, const cplx* W1, int nfields, bool prune) {
+int do_fwd_y(S* s, const cplx* W1, int nfields, bool prune, int f0) {
+  PeerTable tabW2 = s->tabW2;
+  for (int q = 0; q < s->P; ++q)
+    if (tabW2.base[q]) tabW2.base[q] += (size_t)f0 * s->nxh * tabW2.len[q] * s->nz;
   char name[32]; std::snprintf(name, sizeof(name), "fwd_y%d", nfields);
   constexpr int TL = tly(N);
   typedef Tile<N, TL> T;
   LAPS_CK(s, prepare_kernel(k_fwd_y<N, TL>, T::SMEM, T::MINB));
   LaunchScope ls(s, name, nfields * (bytes_xcols(s, prune) + bytes_ycols(s, prune)));
   const int ztiles = (s->nzl + TL - 1) / TL;
-  dim3 grid((unsigned)(ztiles * (prune ? s->nkx : s->nxh)), (unsigned)nfields);
-  LAPS_LAUNCH((k_fwd_y<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, W1, s->tabW2, s->nzl, s->nz, s->zo,
-              s->tw_y, 1.0 / N, s->nxh, prune ? s->kymax : N, prune ? (const int*)s->d_kymax_x : (const int*)nullptr);
+  const int ntiles = ztiles * (prune ? s->nkx : s->nxh);
+  int gx = ntiles;
+  if (s->cap_warps > 0) gx = std::max(1, std::min(ntiles, capped_ctas(s, T::NTHREADS) / nfields));
+  dim3 grid((unsigned)gx, (unsigned)nfields);
+  LAPS_LAUNCH((k_fwd_y<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->cs, W1, tabW2, s->nzl, s->nz, s->zo,
+              s->tw_y, 1.0 / N, s->nxh, prune ? s->kymax : N, prune ? (const int*)s->d_kymax_x : (const int*)nullptr, ntiles);
   return check_launch(s, "k_fwd_y");
 }
 
@@ -439,7 +465,7 @@ int do_inv_y(S* s, const cplx* V1, cplx* V2, int nfields, bool prune) {
   LaunchScope ls(s, name, nfields * (bytes_xcols(s, prune) + bytes_ycols(s, prune)));
   const int ztiles = (s->nzl + TL - 1) / TL;
   dim3 grid((unsigned)(ztiles * (prune ? s->nkx : s->nxh)), (unsigned)nfields);
-  LAPS_LAUNCH((k_inv_y<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, V1, V2, s->nzl, s->tw_y, s->nxh,
+  LAPS_LAUNCH((k_inv_y<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->cs, V1, V2, s->nzl, s->tw_y, s->nxh,
               prune ? s->kymax : N, prune ? (const int*)s->d_kymax_x : (const int*)nullptr);
   return check_launch(s, "k_inv_y");
 }
@@ -451,7 +477,7 @@ int do_inv_x_tl(S* s, const cplx* V2, const RealDst& dst, int nfields, bool prun
   LAPS_CK(s, prepare_kernel(k_inv_x<N, TL>, T::SMEM, T::MINB));
   LaunchScope ls(s, name, nfields * (bytes_real(s) + bytes_xcols(s, prune)));
   dim3 grid((unsigned)(s->xz * (s->xy / (2 * TL))), (unsigned)nfields);
-  LAPS_LAUNCH((k_inv_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, V2, dst, s->xz, s->xy, s->tw_x,
+  LAPS_LAUNCH((k_inv_x<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->cs, V2, dst, s->xz, s->xy, s->tw_x,
               prune ? s->nkx : s->nxh);
   return check_launch(s, "k_inv_x");
 }
@@ -471,8 +497,11 @@ int do_spec_z_cg(S* s, const ZParams& zp, int ntasks, const char* name) {
   LAPS_CK(s, prepare_kernel(k_spec_z<N, CG>, T::SMEM, T::MINB));
   LaunchScope ls(s, name, bytes_z(s, zp, ntasks));
   if (zp.ncolc == 0) return 0;   // this rank owns no surviving column
-  dim3 grid((unsigned)((zp.ncolc + CG - 1) / CG), (unsigned)ntasks);
-  LAPS_LAUNCH((k_spec_z<N, CG>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, zp);
+  const int ngroups = (zp.ncolc + CG - 1) / CG;
+  int gx = ngroups;
+  if (s->cap_warps > 0) gx = std::max(1, std::min(ngroups, capped_ctas(s, T::NTHREADS) / ntasks));
+  dim3 grid((unsigned)gx, (unsigned)ntasks);
+  LAPS_LAUNCH((k_spec_z<N, CG>), grid, dim3(T::NTHREADS), T::SMEM, s->cs, zp, ngroups);
   return check_launch(s, "k_spec_z");
 }
 
@@ -493,9 +522,10 @@ int do_rhs_z_cg(S* s, const ZParams& zp, int ntasks) {
   if (zp.ncolc == 0) return 0;   // this rank owns no surviving column
   const int ngroups = (zp.ncolc + CG - 1) / CG;
   const long long nitems = (long long)ngroups * ntasks;
-  const long long wave = (long long)s->num_sms * T::MINB;
+  long long wave = (long long)s->num_sms * T::MINB;
+  if (s->cap_warps > 0) wave = std::min(wave, (long long)capped_ctas(s, T::NTHREADS));
   dim3 grid((unsigned)std::min(nitems, wave));
-  LAPS_LAUNCH((k_rhs_z<N, CG>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, zp, ntasks, ngroups);
+  LAPS_LAUNCH((k_rhs_z<N, CG>), grid, dim3(T::NTHREADS), T::SMEM, s->cs, zp, ntasks, ngroups);
   return check_launch(s, "k_rhs_z");
 }
 
@@ -516,7 +546,7 @@ int do_incomp_z(S* s, const ZParams& zp) {
   LaunchScope ls(s, "incomp_z", (3 + 5) * iline + imodes * (5 + (zp.read_rk ? 5 : 0) + 5 + (zp.write_rk ? 5 : 0)));
   if (zp.ncolc == 0) return 0;
   dim3 grid((unsigned)((zp.ncolc + CG - 1) / CG));
-  LAPS_LAUNCH((k_incomp_z<N, CG>), grid, dim3(T::NTHREADS), T::SMEM, s->stream, zp);
+  LAPS_LAUNCH((k_incomp_z<N, CG>), grid, dim3(T::NTHREADS), T::SMEM, s->cs, zp);
   return check_launch(s, "k_incomp_z");
 }
 
@@ -552,7 +582,7 @@ int do_incomp_z(S* s, const ZParams& zp) {
 int fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1, bool prune, int zl0 = 0, int planes = -1, bool scoped = true) {
   LAPS_DISPATCH(s->nx, do_fwd_x, s, in, fstride, nfields, W1, prune, zl0, planes, scoped)
 }
-int fwd_y(S* s, const cplx* W1, int nfields, bool prune) { LAPS_DISPATCH(s->ny, do_fwd_y, s, W1, nfields, prune) }
+int fwd_y(S* s, const cplx* W1, int nfields, bool prune, int f0 = 0) { LAPS_DISPATCH(s->ny, do_fwd_y, s, W1, nfields, prune, f0) }
 int flux_fwd_x(S* s, const FusedFluxParams& fp) { LAPS_DISPATCH(s->nx, do_flux_fwd_x, s, fp) }
 bool use_fused_flux(const S* s) {
   if (s->two_d || s->incomp || s->nx > 512 || (s->ny & 1)) return false;
@@ -658,9 +688,9 @@ int launch_current_tasks(S* s, const cplx* u, bool prune, bool want_j = true, in
 int host_barrier(S* s) {
   if (s->P > 1) {
     if (!s->wired) { s->err = "nranks > 1 but the ranks are not connected (laps_import_peer_blobs / laps_connect_local)"; return 1; }
-    ++s->epoch[0];
+    ++s->epoch[s->cch];
     LaunchScope ls(s, "xchg_barrier");
-    LAPS_LAUNCH(k_xchg_barrier, dim3(1), dim3(32), 0, s->stream, s->xp, 0, s->epoch[0]);
+    LAPS_LAUNCH(k_xchg_barrier, dim3(1), dim3(32), 0, s->cs, s->xp, s->cch, s->epoch[s->cch]);
     return check_launch(s, "k_xchg_barrier");
   }
   return 0;
@@ -798,6 +828,28 @@ void fill_cfl_params(S* s, CflParams& c) {
   c.hall = p.if_hall; c.partial = s->d_partial;
 }
 
+// `to` waits for everything enqueued on `from` so far (events from a small rotating pool: a wait captures the event's
+// state at the call, so re-recording an event later is harmless).
+int link_streams(S* s, cudaStream_t from, cudaStream_t to) {
+  cudaEvent_t e = s->ev_link[s->ev_next];
+  s->ev_next = (s->ev_next + 1) % 16;
+  LAPS_CK(s, cudaEventRecord(e, from));
+  LAPS_CK(s, cudaStreamWaitEvent(to, e, 0));
+  return 0;
+}
+
+// Two-stream schedule of a stage (3D compressible tree): the forward fields go through the x pass in chunks on the main
+// stream while the y pass of the previous chunk — whose stores leave over NVLink — runs on the exchange stream beside
+// it; after the last forward barrier the z passes (NVLink stores again) run on the exchange stream in row groups while
+// the inverse y and x passes of the previous group run on the main stream.  The reference's transposes block
+// (parallel.f90:273-324: mpi_sendrecv in a loop, nothing else runs); here the exchange hides behind the HBM-only passes.
+bool use_overlap(const S* s) {
+  if (s->two_d || s->incomp || s->ext_slot >= 0 || !s->xstream) return false;
+  if (use_fused_flux(s) || s->tune_zchunk > 0) return false;
+  if (s->tune_overlap >= 0) return s->tune_overlap != 0;
+  return s->P > 1;
+}
+
 // The part of a stage that does not depend on the time step: J refresh, calc_flux, forward x and y passes.
 // with_cfl: the CFL maxima of vardt (mhd.f90:352-416) are taken inside the calc_flux sweep (k_flux<true>) and
 // left in d_partial — used by laps_step, which runs this for the NEXT step before it knows the next dt.
@@ -859,7 +911,23 @@ int stage_front(S* s, bool with_cfl) {
   if (s->ext_slot >= 0)   // calc_external_force_real (2D/mhdrhs.f90:129-131): the driver's field, transformed with the fluxes
     LAPS_CK(s, cudaMemcpyAsync(buf_F(s) + (size_t)s->ext_slot * s->npts, s->ext, s->npts * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
   // transform_flux_real_to_fourier (mhdrhs.f90:128-172)
-  LAPS_TRY(forward_xy(s, buf_F(s), s->npts, s->nf, true));
+  if (!use_overlap(s)) {
+    LAPS_TRY(forward_xy(s, buf_F(s), s->npts, s->nf, true));
+  } else {
+    // x pass of chunk c on the main stream, y pass of chunk c (stores into the peers' W2) on the exchange stream
+    const int nc = std::max(1, std::min(s->ovl_chunks, s->nf));
+    for (int c = 0, f0 = 0; c < nc; ++c) {
+      const int n = s->nf / nc + (c < s->nf % nc ? 1 : 0);
+      LAPS_TRY(fwd_x(s, buf_F(s) + (size_t)f0 * s->npts, s->npts, n, buf_W1(s) + (size_t)f0 * s->w1sz, true));
+      LAPS_TRY(link_streams(s, s->stream, s->xstream));
+      {
+        StreamScope sc(s, s->xstream, 1, s->P > 1 ? s->ovl_y_warps : 0);
+        LAPS_TRY(fwd_y(s, buf_W1(s) + (size_t)f0 * s->w1sz, n, true, f0));
+      }
+      f0 += n;
+    }
+    LAPS_TRY(link_streams(s, s->xstream, s->stream));   // the main stream owns the buffers again (API calls are ordered on it)
+  }
   }
   return 0;
 }
@@ -870,12 +938,64 @@ bool can_speculate(const S* s) {
   return s->tune_spec && !s->incomp && s->ext_slot < 0 && !use_fused_flux(s) && !(s->tune_zchunk > 0 && !s->two_d);
 }
 
+// End of a stage: the buffer just read becomes the output buffer of the next stage.
+int stage_finish(S* s, bool want_j) {
+  if (s->spectrum_full) {
+    // First stage after laps_set_primitive: the buffer just read still holds the unmasked initial
+    // spectrum; it becomes the output buffer of the next stage, which writes surviving columns only.
+    if (s->nkx < s->nxh || s->kymax < s->ny / 2 || s->kzprune || s->d_colmap)
+      LAPS_CK(s, cudaMemsetAsync(s->uA, 0, 8 * s->csz * sizeof(cplx), s->stream));
+    s->spectrum_full = false;
+  }
+  std::swap(s->uA, s->uB);
+  s->j_stale = s->p.if_hall && !want_j;
+  return 0;
+}
+
+// Back half of a stage on two streams (see use_overlap).  `z` holds the `ntasks` RHS rows of the stage (v = 1..7, or
+// 0..7 when the continuity row is not taken from the state); rows [0, na) = density/momentum, the rest = B and energy.
+int stage_back_overlap(S* s, int irk, ZParams& z, int ntasks) {
+  const laps_params& p = s->p;
+  const bool want_j = p.if_hall && !(irk == 2 && s->Ur != 0.0);
+  const int cap = s->P > 1 ? s->ovl_z_warps : 0;
+  const int na = ntasks - 4;                      // rows up to momentum z
+  const int g0a = z.task[0].gout;                 // V1 slots of group A are g0a .. g0a + na - 1, of group B 4 .. 7
+  auto z_rows = [&](int first, int n) -> int {   // RHS rows [first, first + n) on the exchange stream, then the flag barrier
+    StreamScope sc(s, s->xstream, 1, cap);
+    ZParams zz = z;
+    for (int i = 0; i < n; ++i) zz.task[i] = z.task[first + i];
+    if (s->tune_rhs) LAPS_TRY(rhs_z(s, zz, n));
+    else LAPS_TRY(spec_z(s, zz, n, "spec_z"));
+    return host_barrier(s);
+  };
+  LAPS_TRY(link_streams(s, s->stream, s->xstream));
+  {  // every rank's forward y pass has landed in W2; every rank has finished reading V1 (previous stage's inverse y pass)
+    StreamScope sc(s, s->xstream, 1, cap);
+    LAPS_TRY(host_barrier(s));
+  }
+  LAPS_TRY(z_rows(0, na));
+  LAPS_TRY(link_streams(s, s->xstream, s->stream));
+  LAPS_TRY(z_rows(na, 4));                                   // beside ...
+  LAPS_TRY(inverse_yx(s, g0a, na, true));                    // ... the inverse y, x passes of group A (main stream)
+  LAPS_TRY(link_streams(s, s->xstream, s->stream));
+  {  // J for the next stage's calc_flux + the continuity row (reads the rows just updated: same stream, after them)
+    StreamScope sc(s, s->xstream, 1, cap);
+    LAPS_TRY(launch_current_tasks(s, s->uB, true, want_j, s->mass_from_state ? irk : -1));
+    if (want_j || s->mass_from_state) LAPS_TRY(host_barrier(s));
+  }
+  LAPS_TRY(inverse_yx(s, 4, 4, true));                       // group B beside the current / continuity tasks
+  LAPS_TRY(link_streams(s, s->xstream, s->stream));
+  if (s->mass_from_state) LAPS_TRY(inverse_yx(s, 0, 1, true));
+  if (want_j) LAPS_TRY(inverse_yx(s, 8, 3, true));
+  return stage_finish(s, want_j);
+}
+
 int stage(S* s, int irk) {
   const laps_params& p = s->p;
   if (s->incomp) return stage_incomp(s, irk);
   if (irk == 0 && s->front_ready) s->front_ready = false;   // laps_step has already run this stage's front half
   else LAPS_TRY(stage_front(s, false));
-  LAPS_TRY(host_barrier(s));
+  if (!use_overlap(s)) LAPS_TRY(host_barrier(s));
   {  // z-pass + calc_rhs + rkt + dealias + inverse z
     ZParams z; fill_zparams(s, z, true);
     z.cc = s->cc1[irk]; z.dd = s->dd1[irk]; z.dt_irk = s->tstep[irk];
@@ -914,6 +1034,7 @@ int stage(S* s, int irk) {
     }
     const int t0 = s->mass_from_state ? 1 : 0;   // the continuity row is a kZMass task of the launch below
     if (t0) for (int v = 1; v < 8; ++v) z.task[v - 1] = z.task[v];
+    if (use_overlap(s)) return stage_back_overlap(s, irk, z, 8 - t0);
     if (s->tune_rhs) LAPS_TRY(rhs_z(s, z, 8 - t0));
     else LAPS_TRY(spec_z(s, z, 8 - t0, "spec_z"));
   }
@@ -924,16 +1045,7 @@ int stage(S* s, int irk) {
   LAPS_TRY(launch_current_tasks(s, s->uB, true, want_j, s->mass_from_state ? irk : -1));
   LAPS_TRY(host_barrier(s));
   LAPS_TRY(inverse_yx(s, 0, want_j ? 11 : 8, true));
-  if (s->spectrum_full) {
-    // First stage after laps_set_primitive: the buffer just read still holds the unmasked initial
-    // spectrum; it becomes the output buffer of the next stage, which writes surviving columns only.
-    if (s->nkx < s->nxh || s->kymax < s->ny / 2 || s->kzprune || s->d_colmap)
-      LAPS_CK(s, cudaMemsetAsync(s->uA, 0, 8 * s->csz * sizeof(cplx), s->stream));
-    s->spectrum_full = false;
-  }
-  std::swap(s->uA, s->uB);
-  s->j_stale = p.if_hall && !want_j;
-  return 0;
+  return stage_finish(s, want_j);
 }
 
 // reduce_launch enqueues the final reduction (+ the inter-rank allreduce) and the copy of the scalars to the host,
@@ -1098,6 +1210,22 @@ int laps_create(const laps_params* params, laps_handle* out) {
   s->wnx = wave_numbers(s->nx, p.Lx); s->wny = wave_numbers(s->ny, p.Ly); s->wnz = wave_numbers(s->nz, p.Lz);
 
   if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
+  s->cs = s->stream;
+#ifndef LAPS_EMU_BUILD
+  {  // exchange stream: highest priority, so that its (grid-capped) passes get their share of every SM as CTAs retire
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&s->xstream, cudaStreamNonBlocking, hi) != cudaSuccess) return fail("cudaStreamCreateWithPriority failed");
+    for (int i = 0; i < 16; ++i)
+      if (cudaEventCreateWithFlags(&s->ev_link[i], cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate failed");
+  }
+#else
+  s->xstream = (cudaStream_t)1;   // the emulator runs launches synchronously: the two-stream schedule is exercised as a sequence
+#endif
+  if (const char* e = std::getenv("LAPS_TUNE_OVERLAP")) s->tune_overlap = std::atoi(e);
+  if (const char* e = std::getenv("LAPS_TUNE_OVL_Y")) s->ovl_y_warps = std::atoi(e);
+  if (const char* e = std::getenv("LAPS_TUNE_OVL_Z")) s->ovl_z_warps = std::atoi(e);
+  if (const char* e = std::getenv("LAPS_TUNE_OVL_CHUNKS")) s->ovl_chunks = std::atoi(e);
   cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1); cudaEventCreate(&s->ev_scal);
 
   const int nmax = s->nf > s->ni ? s->nf : s->ni;
@@ -1284,6 +1412,9 @@ int laps_destroy(laps_handle s) {
   if (!s) return 0;
   DeviceGuard guard_(s->p.device);
   if (s->stream) cudaStreamSynchronize(s->stream);   // bounded: the inter-rank waits time out (exchange.cuh)
+#ifndef LAPS_EMU_BUILD
+  if (s->xstream) cudaStreamSynchronize(s->xstream);
+#endif
   for (int q = 0; q < LAPS_MAX_RANKS; ++q)
     for (int j = 0; j < 3; ++j)
       if (s->ipc_opened[q][j]) cudaIpcCloseMemHandle(s->ipc_opened[q][j]);
@@ -1298,6 +1429,10 @@ int laps_destroy(laps_handle s) {
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->ev_scal) cudaEventDestroy(s->ev_scal);
   if (s->stream) cudaStreamDestroy(s->stream);
+#ifndef LAPS_EMU_BUILD
+  if (s->xstream) cudaStreamDestroy(s->xstream);
+  for (int i = 0; i < 16; ++i) if (s->ev_link[i]) cudaEventDestroy(s->ev_link[i]);
+#endif
   delete s;
   return 0;
 }
@@ -1590,7 +1725,8 @@ int laps_set_tune(laps_handle s, const char* name, int32_t value) {
   if (!s || !name) return 1;
   const std::string n(name);
   int* slot = n == "rhs" ? &s->tune_rhs : n == "rcg" ? &s->tune_rcg : n == "cgz" ? &s->tune_cgz : n == "z" ? &s->tune_z :
-              n == "spec" ? &s->tune_spec : nullptr;
+              n == "spec" ? &s->tune_spec : n == "overlap" ? &s->tune_overlap : n == "ovl_y" ? &s->ovl_y_warps :
+              n == "ovl_z" ? &s->ovl_z_warps : n == "ovl_chunks" ? &s->ovl_chunks : nullptr;
   if (!slot) { s->err = "laps_set_tune: unknown switch '" + n + "'"; return 1; }
   *slot = value;
   s->front_ready = false;

@@ -152,18 +152,16 @@ LAPS_D double ksq_xy_eval(const ZParams& P, double kxr, double kyr, int kx, int 
   return ksq_xy_of(P, kxr, kyr, __ldg(P.ksq_x + kx), __ldg(P.ksq_y + ky));
 }
 
+// one column group (CG columns) of one task row
 template <int N, int CG>
-__global__ void __launch_bounds__(ZTile<N, CG>::NTHREADS, ZTile<N, CG>::MINB)
-k_spec_z(const ZParams P) {
+LAPS_D void spec_z_group(const ZParams& P, const ZTask& K, const int group, cplx* sm) {
   typedef Geom<N> G;
   typedef Fft<N, -1> FF;
   typedef Fft<N, +1> FI;
   typedef ZTile<N, CG> T;
-  LAPS_DYN_SMEM(cplx, sm);
-  const ZTask& K = P.task[blockIdx.y];
   const int tid = threadIdx.x;
   const int l = tid / G::NT, u = tid % G::NT;
-  const int colm = z_column(P, blockIdx.x * CG + l);
+  const int colm = z_column(P, group * CG + l);
   const bool live = colm >= 0;
   const int col = live ? colm : 0;
   const int kx = col / P.nyl;
@@ -419,6 +417,18 @@ k_spec_z(const ZParams P) {
       cplx* dst = P.V1.base[p] + (((size_t)K.gout * P.nxh + kx) * P.ny + ky) * P.V1.len[p] + (z - P.V1.off[p]);
       *dst = r[e];
     }
+  }
+}
+
+// grid.x = column groups (or fewer: grid-stride loop, see k_fwd_y), grid.y = task rows
+template <int N, int CG>
+__global__ void __launch_bounds__(ZTile<N, CG>::NTHREADS, ZTile<N, CG>::MINB)
+k_spec_z(const ZParams P, const int ngroups) {
+  LAPS_DYN_SMEM(cplx, sm);
+  const ZTask& K = P.task[blockIdx.y];
+  for (int group = blockIdx.x; group < ngroups; group += gridDim.x) {
+    spec_z_group<N, CG>(P, K, group, sm);
+    if (group + (int)gridDim.x < ngroups) __syncthreads();   // the next group's first stage refills the lines
   }
 }
 

@@ -305,3 +305,18 @@ def test_100_steps_against_the_executed_reference_source():
     the reference's own source executed for 100 steps (tests/golden/ref_exec/hall_aeb_mask_100steps.npz)."""
     import test_reference_source_pins as rp
     rp.check_library_100_steps()
+
+
+def test_two_stream_schedule_single_gpu(monkeypatch):
+    """The two-stream stage schedule (default from 2 ranks on) forced on one GPU: same state as the oracle, and bit-identical
+    to the one-stream schedule (the same kernels on the same data; only the order of independent launches differs)."""
+    p, prim = pc.make_case(64, 64, 64, hall=True, aeb=True, dealias=1)
+    monkeypatch.setenv("LAPS_TUNE_OVERLAP", "1")
+    o, g = pc.run_both(p, prim, 2)
+    pc.check_state(o, g, 1e-11)
+    uu1, uf1 = g.get_state()[0], g.uu_fourier()
+    g.close()
+    monkeypatch.setenv("LAPS_TUNE_OVERLAP", "0")
+    o, g = pc.run_both(p, prim, 2)
+    assert np.array_equal(g.get_state()[0], uu1) and np.array_equal(g.uu_fourier(), uf1)
+    g.close()
