@@ -49,6 +49,7 @@ struct CflParams {
   double dmin;            // min(dx,dy,dz) (mhd.f90:398); min(dx,dy) in the 2D tree (2D/mhd.f90:369)
   double floor_x, floor_y; // resistivity/dx, resistivity/dy of the 2D tree's explicit-resistivity limit (2D/mhd.f90:361-364), else 0
   int hall;
+  int screen;       // 1: evaluate the FP64 signal speeds only where a cheap FP32 bound says they can raise a maximum (bit-identical)
   double* partial;  // [gridDim.x]
 };
 
@@ -81,6 +82,43 @@ LAPS_D void cfl_point(const CflParams& P, double rho, double Bx, double By, doub
   }
 }
 
+// A cheap FP32 upper bound of the three signal speeds of one point, so that the FP64 sqrt/div chain of cfl_point runs only
+// where it can raise a maximum.  With cf <= sqrt(cs^2 + ca^2) and |ca_d| <= |ca|:  c_d <= max(|u_d| + sqrt(cs^2 + ca^2),
+// floor_d, c_hall).  The bound is evaluated in FP32 from the conserved variables (one reciprocal, one square root) and
+// inflated by a slack that covers the FP32 rounding, including the cancellation in p = (gamma - 1)(e - ...): the error of
+// sqrt(cs^2 + ca^2) is below 5e-4 (|u| + sqrt(cs^2 + ca^2)), the slack is 4e-3 of that scale.  A point is skipped only
+// if its bound is below the running maxima `sb` (the CTA's, which hold exact values of other points), so the reduced
+// maxima are bit-identical to evaluating every point.  NaNs fail the comparison and take the exact path.
+LAPS_D bool cfl_may_raise(const CflParams& P, double rho, double mx, double my, double mz, double Bx, double By, double Bz,
+                          double en, const double (&sb)[3]) {
+  const float r = 1.0f / (float)rho;
+  const float ax = fabsf((float)mx) * r, ay = fabsf((float)my) * r, az = fabsf((float)mz) * r;
+  const float bx = (float)Bx, by = (float)By, bz = (float)Bz;
+  const float b2 = bx * bx + by * by + bz * bz;
+  const float m2r = ((float)mx * (float)mx + (float)my * (float)my + (float)mz * (float)mz) * r;
+  const float p = fmaxf(((float)en - 0.5f * (m2r + b2)) * (float)(P.gamma - 1.0), 0.0f);
+  const float c = sqrtf(((float)P.gamma * p + b2) * r);
+  const float slack = 4e-3f * (ax + ay + az + c);
+  float ch = 0.0f;
+  if (P.hall) ch = (float)P.di * r * fmaxf(fmaxf(fabsf(bx), fabsf(by)), fabsf(bz)) / (float)P.dmin * 1.001f;
+  const float ux_ = fmaxf(fmaxf(ax + c + slack, (float)P.floor_x * 1.001f), ch);
+  const float uy_ = fmaxf(fmaxf(ay + c + slack, (float)P.floor_y * 1.001f), ch);
+  const float uz_ = fmaxf(az + c + slack, ch);
+  return !((double)ux_ <= sb[0] && (double)uy_ <= sb[1] && (double)uz_ <= sb[2]);
+}
+
+// The CTA's running maxima (bit patterns of non-negative doubles order like the values): read by every thread before a
+// point, raised after an exact evaluation.  Stale reads only make the screen more conservative.
+LAPS_D void cfl_shared_read(const unsigned long long* s_best, double (&sb)[3]) {
+  LAPS_UNROLL
+  for (int d = 0; d < 3; ++d) sb[d] = __longlong_as_double((long long)*reinterpret_cast<const volatile unsigned long long*>(s_best + d));
+}
+LAPS_D void cfl_shared_raise(unsigned long long* s_best, const double (&best)[3], const double (&sb)[3]) {
+  LAPS_UNROLL
+  for (int d = 0; d < 3; ++d)
+    if (best[d] > sb[d]) atomicMax(s_best + d, (unsigned long long)__double_as_longlong(best[d]));
+}
+
 struct FluxParams {
   const double* uu;     // [8][npts]
   const double* J;      // [3][npts] (Hall) or null
@@ -101,12 +139,24 @@ __global__ void __launch_bounds__(256, CFL ? 2 : 3) k_flux(const FluxParams P) {
   const size_t n = P.npts;
   const double gm1 = P.gamma - 1.0;
   double best[3] = {0.0, 0.0, 0.0};
+  __shared__ unsigned long long s_best[3];
+  if (CFL) {
+    if (threadIdx.x < 3) s_best[threadIdx.x] = 0ull;
+    __syncthreads();
+  }
   for (size_t ii = blockIdx.x * (size_t)blockDim.x + threadIdx.x; ii < P.count; ii += (size_t)gridDim.x * blockDim.x) {
     const size_t i = P.in_off + ii;
     const double rho = P.uu[i], mx = P.uu[n + i], my = P.uu[2 * n + i], mz = P.uu[3 * n + i];
     const double Bx = P.uu[4 * n + i], By = P.uu[5 * n + i], Bz = P.uu[6 * n + i], en = P.uu[7 * n + i];
     const Prim q = prim_of(rho, mx, my, mz, Bx, By, Bz, en, gm1);
-    if (CFL) cfl_point(P.cfl, rho, Bx, By, Bz, q, best);
+    if (CFL) {   // the signal speeds of vardt, only where they can raise a maximum (cfl_may_raise)
+      double sb[3];
+      cfl_shared_read(s_best, sb);
+      if (!P.cfl.screen || cfl_may_raise(P.cfl, rho, mx, my, mz, Bx, By, Bz, en, sb)) {
+        cfl_point(P.cfl, rho, Bx, By, Bz, q, best);
+        cfl_shared_raise(s_best, best, sb);
+      }
+    }
     const double ux = q.ux, uy = q.uy, uz = q.uz, p = q.p;
     const double ptot = p + 0.5 * (Bx * Bx + By * By + Bz * Bz);
     const double udotb = ux * Bx + uy * By + uz * Bz;
@@ -192,13 +242,20 @@ __global__ void __launch_bounds__(256) k_cons_to_prim(const double* uu, double* 
 // division by sqrt(2) are monotonic), so they can never exceed max(|u + cf|, |u - cf|).
 __global__ void __launch_bounds__(256) k_cfl(const CflParams P) {
   __shared__ double scratch[32];
+  __shared__ unsigned long long s_best[3];
+  if (threadIdx.x < 3) s_best[threadIdx.x] = 0ull;
+  __syncthreads();
   const size_t n = P.npts;
   double best[3] = {0.0, 0.0, 0.0};
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const double rho = P.uu[i], mx = P.uu[n + i], my = P.uu[2 * n + i], mz = P.uu[3 * n + i];
     const double Bx = P.uu[4 * n + i], By = P.uu[5 * n + i], Bz = P.uu[6 * n + i], en = P.uu[7 * n + i];
+    double sb[3];
+    cfl_shared_read(s_best, sb);
+    if (P.screen && !cfl_may_raise(P, rho, mx, my, mz, Bx, By, Bz, en, sb)) continue;
     const Prim q = prim_of(rho, mx, my, mz, Bx, By, Bz, en, P.gamma - 1.0);
     cfl_point(P, rho, Bx, By, Bz, q, best);
+    cfl_shared_raise(s_best, best, sb);
   }
   LAPS_UNROLL
   for (int d = 0; d < 3; ++d) {

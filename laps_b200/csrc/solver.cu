@@ -168,6 +168,8 @@ struct laps_solver {
   int cap_warps = 0;                 // > 0: the exchange-side launchers hold their grids to this many warps per SM (grid-stride loops)
   cudaEvent_t ev_link[16] = {nullptr};
   int ev_next = 0;
+  int tune_tly = 0;                  // LAPS_TUNE_TLY=4: half-height tiles in the y passes
+  int tune_screen = 1;               // LAPS_TUNE_SCREEN=0: the signal speeds of vardt at every point (see cfl_may_raise)
   int tune_overlap = -1;             // LAPS_TUNE_OVERLAP: -1 = default (on from 2 ranks on), 0 = one stream, 1 = two streams
   int ovl_y_warps = 16, ovl_z_warps = 8, ovl_chunks = 3;   // warps per SM given to the exchange-side passes; forward field chunks
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_scal = nullptr;
@@ -436,13 +438,12 @@ int do_flux_fwd_x(S* s, const FusedFluxParams& fp) {
 }
 
 // f0: first field slot of the launch (W1 points at it; the peers' W2 bases are advanced to it here)
-template <int N>
-int do_fwd_y(S* s, const cplx* W1, int nfields, bool prune, int f0) {
+template <int N, int TL>
+int do_fwd_y_tl(S* s, const cplx* W1, int nfields, bool prune, int f0) {
   PeerTable tabW2 = s->tabW2;
   for (int q = 0; q < s->P; ++q)
     if (tabW2.base[q]) tabW2.base[q] += (size_t)f0 * s->nxh * tabW2.len[q] * s->nz;
   char name[32]; std::snprintf(name, sizeof(name), "fwd_y%d", nfields);
-  constexpr int TL = tly(N);
   typedef Tile<N, TL> T;
   LAPS_CK(s, prepare_kernel(k_fwd_y<N, TL>, T::SMEM, T::MINB));
   LaunchScope ls(s, name, nfields * (bytes_xcols(s, prune) + bytes_ycols(s, prune)));
@@ -457,9 +458,16 @@ int do_fwd_y(S* s, const cplx* W1, int nfields, bool prune, int f0) {
 }
 
 template <int N>
-int do_inv_y(S* s, const cplx* V1, cplx* V2, int nfields, bool prune) {
+int do_fwd_y(S* s, const cplx* W1, int nfields, bool prune, int f0) {
+  if constexpr (N >= 256 && N <= 1024 && tly(N) == 8) {   // tuning knob: half-height tiles (twice the CTAs per SM, 64-byte chunks)
+    if (s->tune_tly == 4) return do_fwd_y_tl<N, 4>(s, W1, nfields, prune, f0);
+  }
+  return do_fwd_y_tl<N, tly(N)>(s, W1, nfields, prune, f0);
+}
+
+template <int N, int TL>
+int do_inv_y_tl(S* s, const cplx* V1, cplx* V2, int nfields, bool prune) {
   char name[32]; std::snprintf(name, sizeof(name), "inv_y%d", nfields);
-  constexpr int TL = tly(N);
   typedef Tile<N, TL> T;
   LAPS_CK(s, prepare_kernel(k_inv_y<N, TL>, T::SMEM, T::MINB));
   LaunchScope ls(s, name, nfields * (bytes_xcols(s, prune) + bytes_ycols(s, prune)));
@@ -468,6 +476,14 @@ int do_inv_y(S* s, const cplx* V1, cplx* V2, int nfields, bool prune) {
   LAPS_LAUNCH((k_inv_y<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->cs, V1, V2, s->nzl, s->tw_y, s->nxh,
               prune ? s->kymax : N, prune ? (const int*)s->d_kymax_x : (const int*)nullptr);
   return check_launch(s, "k_inv_y");
+}
+
+template <int N>
+int do_inv_y(S* s, const cplx* V1, cplx* V2, int nfields, bool prune) {
+  if constexpr (N >= 256 && N <= 1024 && tly(N) == 8) {
+    if (s->tune_tly == 4) return do_inv_y_tl<N, 4>(s, V1, V2, nfields, prune);
+  }
+  return do_inv_y_tl<N, tly(N)>(s, V1, V2, nfields, prune);
 }
 
 template <int N, int TL>
@@ -514,10 +530,10 @@ int do_spec_z(S* s, const ZParams& zp, int ntasks, const char* name) {
   return do_spec_z_cg<N, cgz(N)>(s, zp, ntasks, name);
 }
 
-template <int N, int CG>
+template <int N, int CG, int NQ>
 int do_rhs_z_cg(S* s, const ZParams& zp, int ntasks) {
-  typedef RTile<N, CG> T;
-  LAPS_CK(s, prepare_kernel(k_rhs_z<N, CG>, T::SMEM, T::MINB));
+  typedef RTile<N, CG, NQ> T;
+  LAPS_CK(s, prepare_kernel(k_rhs_z<N, CG, NQ>, T::SMEM, T::MINB));
   LaunchScope ls(s, "spec_z", bytes_z(s, zp, ntasks));
   if (zp.ncolc == 0) return 0;   // this rank owns no surviving column
   const int ngroups = (zp.ncolc + CG - 1) / CG;
@@ -525,16 +541,17 @@ int do_rhs_z_cg(S* s, const ZParams& zp, int ntasks) {
   long long wave = (long long)s->num_sms * T::MINB;
   if (s->cap_warps > 0) wave = std::min(wave, (long long)capped_ctas(s, T::NTHREADS));
   dim3 grid((unsigned)std::min(nitems, wave));
-  LAPS_LAUNCH((k_rhs_z<N, CG>), grid, dim3(T::NTHREADS), T::SMEM, s->cs, zp, ntasks, ngroups);
+  LAPS_LAUNCH((k_rhs_z<N, CG, NQ>), grid, dim3(T::NTHREADS), T::SMEM, s->cs, zp, ntasks, ngroups);
   return check_launch(s, "k_rhs_z");
 }
 
 template <int N>
 int do_rhs_z(S* s, const ZParams& zp, int ntasks) {
   if constexpr (N == 512) {  // tuning knob for the benchmark grid (columns per CTA)
-    if (s->tune_rcg == 2) return do_rhs_z_cg<N, 2>(s, zp, ntasks);
+    if (s->tune_rcg == 2) return do_rhs_z_cg<N, 2, 2>(s, zp, ntasks);
   }
-  return do_rhs_z_cg<N, rcg(N)>(s, zp, ntasks);
+  if (s->tune_rhs == 2) return do_rhs_z_cg<N, rcg(N), 1>(s, zp, ntasks);   // one landing line, more resident columns
+  return do_rhs_z_cg<N, rcg(N), 2>(s, zp, ntasks);
 }
 
 template <int N>
@@ -825,7 +842,7 @@ void fill_cfl_params(S* s, CflParams& c) {
   const bool rfloor = s->two_d && p.if_resis && p.if_resis_exp;      // 2D/mhd.f90:361-364
   c.floor_x = rfloor ? p.resistivity / dx : 0.0;
   c.floor_y = rfloor ? p.resistivity / dy : 0.0;
-  c.hall = p.if_hall; c.partial = s->d_partial;
+  c.hall = p.if_hall; c.partial = s->d_partial; c.screen = s->tune_screen;
 }
 
 // `to` waits for everything enqueued on `from` so far (events from a small rotating pool: a wait captures the event's
@@ -1223,6 +1240,8 @@ int laps_create(const laps_params* params, laps_handle* out) {
   s->xstream = (cudaStream_t)1;   // the emulator runs launches synchronously: the two-stream schedule is exercised as a sequence
 #endif
   if (const char* e = std::getenv("LAPS_TUNE_OVERLAP")) s->tune_overlap = std::atoi(e);
+  if (const char* e = std::getenv("LAPS_TUNE_SCREEN")) s->tune_screen = std::atoi(e);
+  if (const char* e = std::getenv("LAPS_TUNE_TLY")) s->tune_tly = std::atoi(e);
   if (const char* e = std::getenv("LAPS_TUNE_OVL_Y")) s->ovl_y_warps = std::atoi(e);
   if (const char* e = std::getenv("LAPS_TUNE_OVL_Z")) s->ovl_z_warps = std::atoi(e);
   if (const char* e = std::getenv("LAPS_TUNE_OVL_CHUNKS")) s->ovl_chunks = std::atoi(e);
@@ -1726,7 +1745,7 @@ int laps_set_tune(laps_handle s, const char* name, int32_t value) {
   const std::string n(name);
   int* slot = n == "rhs" ? &s->tune_rhs : n == "rcg" ? &s->tune_rcg : n == "cgz" ? &s->tune_cgz : n == "z" ? &s->tune_z :
               n == "spec" ? &s->tune_spec : n == "overlap" ? &s->tune_overlap : n == "ovl_y" ? &s->ovl_y_warps :
-              n == "ovl_z" ? &s->ovl_z_warps : n == "ovl_chunks" ? &s->ovl_chunks : nullptr;
+              n == "ovl_z" ? &s->ovl_z_warps : n == "ovl_chunks" ? &s->ovl_chunks : n == "screen" ? &s->tune_screen : n == "tly" ? &s->tune_tly : nullptr;
   if (!slot) { s->err = "laps_set_tune: unknown switch '" + n + "'"; return 1; }
   *slot = value;
   s->front_ready = false;

@@ -24,35 +24,38 @@
 
 namespace laps {
 
-template <int N, int CG>
+// NQ = landing lines next to S: 2 (Q0, Q1: every input line is in flight one phase ahead) or 1 (Q0 only: the second
+// flux line of a combination, the expanding-box source and the RK history are fetched when they are needed — from L2, where
+// the look-ahead hints of the previous item have put them — in exchange for a third more resident columns per SM).
+template <int N, int CG, int NQ = 2>
 struct RTile {
   typedef Geom<N> G;
   static constexpr int PITCH = G::pitch(1);
   static constexpr int NTHREADS = CG * G::NT;
-  static constexpr int COLSTRIDE = PITCH + 3 * N;
+  static constexpr int COLSTRIDE = PITCH + (1 + NQ) * N;
   static constexpr size_t SMEM = (size_t)CG * COLSTRIDE * sizeof(cplx);
   static constexpr int BY_SMEM = (int)((227 * 1024) / (SMEM + 1024));
-  static constexpr int BY_REGS = 65536 / (NTHREADS * 80);
+  static constexpr int BY_REGS = 65536 / (NTHREADS * (NQ == 2 ? 80 : 112));
   static constexpr int BY_THREADS = 2048 / NTHREADS;
   static constexpr int M0 = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
   static constexpr int M1 = M0 < BY_THREADS ? M0 : BY_THREADS;
   static constexpr int MINB = M1 < 1 ? 1 : (M1 > 32 ? 32 : M1);
 };
 
-template <int N, int CG>
-__global__ void __launch_bounds__(RTile<N, CG>::NTHREADS, RTile<N, CG>::MINB)
+template <int N, int CG, int NQ = 2>
+__global__ void __launch_bounds__(RTile<N, CG, NQ>::NTHREADS, RTile<N, CG, NQ>::MINB)
 k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
   typedef Geom<N> G;
   typedef Fft<N, -1> FF;
   typedef Fft<N, +1> FI;
-  typedef RTile<N, CG> T;
+  typedef RTile<N, CG, NQ> T;
   LAPS_DYN_SMEM(cplx, sm);
   const int tid = threadIdx.x;
   const int l = tid / G::NT, u = tid % G::NT;
   cplx* W = sm + l * T::COLSTRIDE;      // padded work line
   cplx* S = W + T::PITCH;               // fc landing, then the (i kz) term
   cplx* Q0 = S + N;
-  cplx* Q1 = Q0 + N;
+  cplx* Q1 = NQ == 2 ? Q0 + N : Q0;   // NQ == 1: one landing line, used in turn
   // thread-constant base twiddles of every stage (forward; the inverse uses the conjugates)
   const cplx tw0 = FF::template tw_stage<0>(P.tw, u);
   const cplx tw1 = G::NSTAGE >= 3 ? FF::template tw_stage<1>(P.tw, u) : mk(1.0, 0.0);
@@ -98,7 +101,7 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
     const bool hasC = K.fc >= 0;
 
     land_in(Q0, P.W2 + (size_t)(K.fa >= 0 ? K.fa : 0) * P.fstride + coff, live && K.fa >= 0);
-    land_in(Q1, P.W2 + (size_t)(K.fb >= 0 ? K.fb : 0) * P.fstride + coff, live && K.fb >= 0);
+    if constexpr (NQ == 2) land_in(Q1, P.W2 + (size_t)(K.fb >= 0 ? K.fb : 0) * P.fstride + coff, live && K.fb >= 0);
     if (P.tune & 4) {
       // one item ahead: pull every line of the NEXT item into L2 (no registers, no shared memory),
       // so that its asynchronous copies run at L2 latency instead of DRAM latency
@@ -147,7 +150,8 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
 
     cplx r[8];
     // ---------------- forward z of the (i kz) term, result kept in S ----------------
-    cp_async_wait<2>();   // fc has landed (fa, fb may still be in flight)
+    if constexpr (NQ == 2) cp_async_wait<2>();   // fc has landed (fa, fb may still be in flight)
+    else cp_async_wait<1>();
     if (hasC) {
       LAPS_UNROLL
       for (int e = 0; e < 8; ++e) r[e] = live ? S[e * G::NT + u] : mk(0.0, 0.0);
@@ -159,27 +163,50 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
       __syncthreads();  // every last-stage read of the work line is done before it is refilled
     }
     // ---------------- G = (i kx ca) fa + (i ky cb) fb + cx fx ----------------
-    cp_async_wait<1>();   // fa
+    if constexpr (NQ == 2) cp_async_wait<1>();   // fa
+    else cp_async_wait<0>();
     {
       const double c = K.ca * kxe;
       const bool on = live && K.fa >= 0;
       LAPS_UNROLL
       for (int e = 0; e < 8; ++e) r[e] = on ? cmul_i(Q0[e * G::NT + u], c) : mk(0.0, 0.0);
     }
-    land_in(Q0, P.W2 + (size_t)(K.fx >= 0 ? K.fx : 0) * P.fstride + coff, live && K.fx >= 0);
-    cp_async_wait<1>();   // fb
-    if (live && K.fb >= 0) {
-      const double c = K.cb * kye;
-      LAPS_UNROLL
-      for (int e = 0; e < 8; ++e) r[e] = cadd(r[e], cmul_i(Q1[e * G::NT + u], c));
+    if constexpr (NQ == 2) {
+      land_in(Q0, P.W2 + (size_t)(K.fx >= 0 ? K.fx : 0) * P.fstride + coff, live && K.fx >= 0);
+      cp_async_wait<1>();   // fb
+      if (live && K.fb >= 0) {
+        const double c = K.cb * kye;
+        LAPS_UNROLL
+        for (int e = 0; e < 8; ++e) r[e] = cadd(r[e], cmul_i(Q1[e * G::NT + u], c));
+      }
+      land_out(Q1, P.u_in + voff, live, dead);
+      cp_async_wait<1>();   // fx
+      if (live && K.fx >= 0) {
+        LAPS_UNROLL
+        for (int e = 0; e < 8; ++e) r[e] = cadd(r[e], cscale(Q0[e * G::NT + u], K.cx));
+      }
+      land_out(Q0, P.fnl_rk + voff, live && P.read_rk, dead);
+    } else {
+      // one landing line: fb and fx come straight from L2 (hinted one item ahead) into registers, then u takes the line
+      if (live && K.fb >= 0) {
+        const cplx* sfb = P.W2 + (size_t)K.fb * P.fstride + coff;
+        const double c = K.cb * kye;
+        cplx t[8];
+        LAPS_UNROLL
+        for (int e = 0; e < 8; ++e) t[e] = sfb[u + e * G::NT];
+        LAPS_UNROLL
+        for (int e = 0; e < 8; ++e) r[e] = cadd(r[e], cmul_i(t[e], c));
+      }
+      if (live && K.fx >= 0) {
+        const cplx* sfx = P.W2 + (size_t)K.fx * P.fstride + coff;
+        cplx t[8];
+        LAPS_UNROLL
+        for (int e = 0; e < 8; ++e) t[e] = sfx[u + e * G::NT];
+        LAPS_UNROLL
+        for (int e = 0; e < 8; ++e) r[e] = cadd(r[e], cscale(t[e], K.cx));
+      }
+      land_out(Q0, P.u_in + voff, live, dead);
     }
-    land_out(Q1, P.u_in + voff, live, dead);
-    cp_async_wait<1>();   // fx
-    if (live && K.fx >= 0) {
-      LAPS_UNROLL
-      for (int e = 0; e < 8; ++e) r[e] = cadd(r[e], cscale(Q0[e * G::NT + u], K.cx));
-    }
-    land_out(Q0, P.fnl_rk + voff, live && P.read_rk, dead);
     FF::first_w(r, u, W, tw0);
     FF::finish_w(r, u, W, tw1, tw2);
 
@@ -200,6 +227,12 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
     const double ksq_xy = ksq_xy_of(P, kxr, kyr, ksqx, ksqy);
     const bool keep_bg = K.diff == 2 && P.conserve_bg && kx == 0;   // "ix==1 .and. iz==1" skip of mhdrhs.f90:262-270
     const double dfy = day;
+    cplx frd[NQ == 2 ? 1 : 8];   // NQ == 1: the RK history straight from L2 into registers
+    if constexpr (NQ == 1) {
+      LAPS_UNROLL
+      for (int e = 0; e < 8; ++e)
+        frd[e] = (P.read_rk && live && !((dead >> e) & 1u)) ? P.fnl_rk[voff + FF::kout(u, e)] : mk(0.0, 0.0);
+    }
     cp_async_wait<0>();   // u, rk
     LAPS_UNROLL
     for (int e = 0; e < 8; ++e) {
@@ -220,7 +253,9 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
       // rkt (rktmod.f90:40-42): u = cc*fnl + dd*fnl_rk + u ; fnl_rk = fnl
       cplx un;
       if (P.read_rk) {
-        const cplx fr = keep ? Q0[e * G::NT + u] : mk(0.0, 0.0);
+        cplx fr;
+        if constexpr (NQ == 2) fr = keep ? Q0[e * G::NT + u] : mk(0.0, 0.0);
+        else fr = frd[e];
         un = mk((P.cc * fnl.x + P.dd * fr.x) + uo.x, (P.cc * fnl.y + P.dd * fr.y) + uo.y);
       } else {
         un = mk(P.cc * fnl.x + uo.x, P.cc * fnl.y + uo.y);

@@ -338,3 +338,65 @@ def check_hall_wave_known_answer(lib_path=None, incompressible=False, nsteps=(30
             assert np.abs(uu[0] - rho).max() < 1e-12 and g.calc_max_divB() < 1e-13
     assert errs[0] < 2e-5 and errs[1] < 3e-6 and 6.0 < errs[0] / errs[1] < 10.0, errs
     return errs
+
+
+def check_cfl_screen_is_exact(lib_path=None, shape=(32, 32, 32), nsteps=3):
+    """vardt evaluates the FP64 signal speeds only where a cheap FP32 bound says they can raise a maximum
+    (pointwise.cuh: cfl_may_raise): dt must be BIT-IDENTICAL to evaluating every point (LAPS_TUNE_SCREEN=0), through
+    laps_vardt (k_cfl) and through laps_step (the sweep fused into calc_flux), also for a supersonic state in which the
+    transverse bounds are loose, and for a uniform state (every point attains the maximum)."""
+    import os
+    cases = []
+    p, prim = make_case(*shape, hall=True, aeb=True, dealias=1)
+    cases.append((p, prim))
+    fast = prim.copy()
+    fast[1] += 7.0                                   # Mach ~ 5 along x
+    fast[7] *= 0.05
+    cases.append((p, fast))
+    flat = np.zeros_like(prim)
+    flat[0], flat[4], flat[7] = 1.0, 1.0, 1.0
+    cases.append((p, flat))
+    for p, prim in cases:
+        dts = []
+        for screen in ("0", "1"):
+            saved = os.environ.get("LAPS_TUNE_SCREEN")
+            os.environ["LAPS_TUNE_SCREEN"] = screen
+            try:
+                g = Solver(lib_path, **solver_kwargs(p))
+            finally:
+                if saved is None:
+                    os.environ.pop("LAPS_TUNE_SCREEN", None)
+                else:
+                    os.environ["LAPS_TUNE_SCREEN"] = saved
+            g.set_primitive(prim)
+            d = [g.vardt()]
+            for _ in range(nsteps):
+                d.append(g.step())
+            d.append(g.vardt())
+            dts.append(d)
+            g.close()
+        assert dts[0] == dts[1], dts
+
+
+def check_rhs_kernel_variants(lib_path=None, shape=(32, 32, 32), nsteps=2, **case):
+    """The RK-stage z pass exists in three forms that do the same arithmetic in the same order: the persistent pipelined
+    kernel with two landing lines (LAPS_TUNE_RHS=1, default), with one landing line and more resident columns (=2), and
+    the plain k_spec_z rows (=0).  Each against the oracle; all three bit-identical to each other."""
+    import os
+    p, prim = make_case(*shape, **case)
+    states = []
+    for v in ("1", "2", "0"):
+        saved = os.environ.get("LAPS_TUNE_RHS")
+        os.environ["LAPS_TUNE_RHS"] = v
+        try:
+            o, g = run_both(p, prim, nsteps, lib_path=lib_path)
+        finally:
+            if saved is None:
+                os.environ.pop("LAPS_TUNE_RHS", None)
+            else:
+                os.environ["LAPS_TUNE_RHS"] = saved
+        check_state(o, g, 1e-11)
+        states.append((g.get_state()[0], g.uu_fourier()))
+        g.close()
+    for uu, uf in states[1:]:
+        assert np.array_equal(uu, states[0][0]) and np.array_equal(uf, states[0][1])

@@ -207,3 +207,12 @@ def test_synthetic_slab_matches_the_mode_sum():
     assert np.abs(a - prim).max() < 1e-13
     b = synthetic.turbulence_slab(16, 32, 24, 24.0, 20.0, 12.0, z_offset=5, z_size=7, bx0=1.0, by0=0.3, kmax=3)
     assert np.abs(b - prim[:, 5:12]).max() < 1e-13
+
+
+def test_cfl_screen_is_exact(emu):
+    pc.check_cfl_screen_is_exact(emu, shape=(16, 16, 16), nsteps=2)
+
+
+def test_rhs_kernel_variants(emu):
+    pc.check_rhs_kernel_variants(emu, shape=(16, 16, 32), nsteps=2, hall=True, aeb=True, dealias=1)
+    pc.check_rhs_kernel_variants(emu, shape=(16, 16, 16), nsteps=1, hall=True, aeb=True, corot=True, dealias=2, explicit=True)

@@ -320,3 +320,13 @@ def test_two_stream_schedule_single_gpu(monkeypatch):
     o, g = pc.run_both(p, prim, 2)
     assert np.array_equal(g.get_state()[0], uu1) and np.array_equal(g.uu_fourier(), uf1)
     g.close()
+
+
+def test_cfl_screen_is_exact():
+    pc.check_cfl_screen_is_exact(shape=(64, 64, 64), nsteps=3)
+
+
+def test_rhs_kernel_variants():
+    pc.check_rhs_kernel_variants(shape=(64, 64, 128), nsteps=2, hall=True, aeb=True, dealias=1)
+    pc.check_rhs_kernel_variants(shape=(32, 32, 64), nsteps=2, hall=True, aeb=True, corot=True, dealias=2, explicit=True)
+    pc.check_rhs_kernel_variants(shape=(64, 32, 32), nsteps=2, hall=False, aeb=False, dealias=0)

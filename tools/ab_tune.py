@@ -17,31 +17,33 @@ from laps_b200 import Solver, synthetic  # noqa: E402
 DEFAULT = [
     "default=",
     "rhs0=rhs:0",
-    "rhs0_cgz1=rhs:0,cgz:1",
-    "rhs0_cgz4=rhs:0,cgz:4",
-    "rcg2=rcg:2",
-    "z0=z:0", "z1=z:1", "z3=z:3", "z4=z:4", "z7=z:7",
+    "rhs2=rhs:2",
+    "noscreen=screen:0",
     "nospec=spec:0",
     "overlap=overlap:1",
-    "overlap_c2=overlap:1,ovl_chunks:2",
-    "overlap_c4=overlap:1,ovl_chunks:4",
 ]
-RESET = dict(rhs=1, cgz=0, rcg=0, z=3, spec=1, overlap=-1, ovl_chunks=3, ovl_y=16, ovl_z=8)
+RESET = dict(rhs=1, cgz=0, rcg=0, z=3, spec=1, overlap=-1, ovl_chunks=3, ovl_y=16, ovl_z=8, screen=1)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=512)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--rounds", type=int, default=3, help="passes over the whole variant list (the variants are interleaved: clocks drift under the power cap)")
     ap.add_argument("--variants", nargs="*", default=DEFAULT)
     ap.add_argument("--reset", default="", help="extra k:v defaults to restore between variants")
     args = ap.parse_args()
     import torch
     n = args.n
     kw = bench.workload_params(n)
-    g = Solver(**kw)
-    stream = torch.cuda.ExternalStream(g.cuda_stream())
-    prim = synthetic.turbulence_slab(n, n, n, kw["Lx"], kw["Ly"], kw["Lz"], kmax=min(8, n // 2 - 1))
+    args.gpus = int(os.environ.get("WORLD_SIZE", "1"))
+    R = bench.Ranks(args)                              # one process per GPU under torchrun, like bench.py
+    g = Solver(rank=R.rank, nranks=R.world, device=R.local, **kw)
+    R.connect(g)
+    R.barrier()
+    stream = torch.cuda.ExternalStream(g.cuda_stream(), device=torch.device("cuda", R.local))
+    prim = synthetic.turbulence_slab(n, n, n, kw["Lx"], kw["Ly"], kw["Lz"], z_offset=g.ext.z_offset, z_size=g.ext.z_size,
+                                     kmax=min(8, n // 2 - 1))
     g.set_primitive(prim)
     g.vardt()
     for _ in range(3):
@@ -50,37 +52,50 @@ def main():
     for kv in filter(None, args.reset.split(",")):
         k, v = kv.split(":")
         reset[k] = int(v)
-    for var in args.variants:
-        name, _, spec = var.partition("=")
-        for k, v in reset.items():
-            try:
-                g.set_tune(k, v)
-            except Exception:
-                pass
-        for kv in filter(None, spec.split(",")):
-            k, v = kv.split(":")
-            g.set_tune(k, int(v))
-        g.step()                                   # settle (the speculative front half of the previous variant is discarded)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(args.steps):
-            g.step()
-        e1.record(stream)
-        g.sync()
-        ms = e0.elapsed_time(e1) / args.steps
-        g.set_profiling(True)
-        g.step()
-        prof = {}
-        for nm, t, by in g.get_profile(with_bytes=True):
-            a = prof.setdefault(nm, [0.0, 0, 0.0])
-            a[0] += t; a[1] += 1; a[2] += by
-        g.set_profiling(False)
-        uu0 = g.calc_rms()[0]
-        print(json.dumps({"variant": name, "tune": spec, "ms_per_step": round(ms, 3),
+    results = {}
+    for rnd in range(args.rounds):
+        for var in args.variants:
+            name, _, spec = var.partition("=")
+            for k, v in reset.items():
+                try:
+                    g.set_tune(k, v)
+                except Exception:
+                    pass
+            for kv in filter(None, spec.split(",")):
+                k, v = kv.split(":")
+                g.set_tune(k, int(v))
+            g.step()                                   # settle (the speculative front half of the previous variant is discarded)
+            R.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(args.steps):
+                g.step()
+            e1.record(stream)
+            g.sync()
+            R.barrier()
+            r = results.setdefault(name, {"tune": spec, "ms": [], "prof": {}})
+            r["ms"].append(R.reduce(e0.elapsed_time(e1), "max") / args.steps)
+            if rnd == args.rounds - 1:
+                g.set_profiling(True)
+                g.step()
+                for nm, t, by in g.get_profile(with_bytes=True):
+                    a = r["prof"].setdefault(nm, [0.0, 0, 0.0])
+                    a[0] += t; a[1] += 1; a[2] += by
+                g.set_profiling(False)
+    finite = bool(np.isfinite(g.calc_rms()[0]).all())
+    R.barrier()
+    g.close()
+    if R.rank != 0:
+        R.close()
+        return
+    for name, r in results.items():
+        prof = r["prof"]
+        print(json.dumps({"variant": name, "tune": r["tune"], "ms_per_step_median": round(float(np.median(r["ms"])), 3),
+                          "ms_per_step_min": round(min(r["ms"]), 3), "ms_per_step_all": [round(x, 2) for x in r["ms"]],
                           "kernels_ms_per_launch": {k: round(v[0] / v[1], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])},
                           "kernels_GBps": {k: round(v[2] / v[1] / (v[0] / v[1] * 1e-3) / 1e9) for k, v in prof.items() if v[2] > 0},
-                          "finite": bool(np.isfinite(uu0).all())}), flush=True)
-    g.close()
+                          "finite": finite, "n_gpus": R.world}), flush=True)
+    R.close()
 
 
 if __name__ == "__main__":

@@ -10,7 +10,7 @@ trun() { n=$1; shift; timeout 900 python -m torch.distributed.run --nnodes=1 --n
 for stage in "$@"; do
   echo "== stage $stage ($(date +%T))"
   case $stage in
-    tests)        ( time timeout 1500 python -m pytest tests -m gpu -q --durations=10 -x ) > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log; tail -15 $OUT/pytest_gpu.log ;;
+    tests)        ( time timeout 1500 python -m pytest tests -m gpu -q --durations=10 --maxfail=8 ) > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log; tail -15 $OUT/pytest_gpu.log ;;
     tests_multi)  ( time timeout 1200 python -m pytest tests/test_gpu_multirank.py -m gpu -q --durations=10 ) > $OUT/pytest_multirank_${NG}gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_multirank_${NG}gpu.log; tail -8 $OUT/pytest_multirank_${NG}gpu.log ;;
     bench)        timeout 900 python bench.py --steps 10 --warmup 3 > $OUT/bench_512_1gpu.json 2> $OUT/bench_512_1gpu.err; tail -c 600 $OUT/bench_512_1gpu.err ;;
     bench_ref)    timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err; cat $OUT/bench_reference.json ;;
@@ -21,6 +21,10 @@ for stage in "$@"; do
                   ncu -i $OUT/stage_full.ncu-rep --page raw --csv > $OUT/stage_full_raw.csv 2>/dev/null ;;
     multi*)       n=${stage#multi}; trun $n bench.py --gpus $n --steps 10 --warmup 3 > $OUT/bench_512_${n}gpu.json 2> $OUT/bench_512_${n}gpu.err; tail -c 400 $OUT/bench_512_${n}gpu.err
                   LAPS_TUNE_OVERLAP=0 trun $n bench.py --gpus $n --steps 10 --warmup 3 --no-parity > $OUT/bench_512_${n}gpu_serial.json 2> $OUT/bench_512_${n}gpu_serial.err ;;
+    abmulti*)     n=${stage#abmulti}; trun $n tools/ab_tune.py --rounds 3 --steps 4 --variants serial=overlap:0 overlap=overlap:1 \
+                    ovl_y8=overlap:1,ovl_y:8 ovl_y32=overlap:1,ovl_y:32 ovl_y0=overlap:1,ovl_y:0 ovl_z4=overlap:1,ovl_z:4 ovl_z12=overlap:1,ovl_z:12 ovl_z0=overlap:1,ovl_z:0 \
+                    chunks2=overlap:1,ovl_chunks:2 chunks4=overlap:1,ovl_chunks:4 rhs2=overlap:1,rhs:2 > $OUT/ab_tune_${n}gpu.jsonl 2> $OUT/ab_tune_${n}gpu.err
+                  cut -c 1-200 $OUT/ab_tune_${n}gpu.jsonl; tail -3 $OUT/ab_tune_${n}gpu.err ;;
     cfg5)         trun $NG bench.py --gpus $NG --config 5 --steps 5 --warmup 3 > $OUT/bench_config5_${NG}gpu.json 2> $OUT/bench_config5_${NG}gpu.err; tail -c 400 $OUT/bench_config5_${NG}gpu.err ;;
     *)            echo "unknown stage $stage" ;;
   esac
