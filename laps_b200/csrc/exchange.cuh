@@ -91,6 +91,9 @@ LAPS_D void xchg_signal_and_wait(const XchgPeers& X, int ch, unsigned long long 
       emu::spin_pause();
 #endif
     }
+    // a peer that gave up earlier has still signalled its epochs (its kernels run on, on incomplete data): the wait
+    // above is then satisfied at once, so look at the abort word in any case
+    if (t == 0 && xchg_load_flag(ab) != 0) xchg_raise(X, kXchgPeerAbort);
   }
   __threadfence_system();
   __syncthreads();

@@ -28,6 +28,10 @@ struct Geom {
   LAPS_HD static constexpr int w(int s) { return s < NSTAGE - 1 ? (N >> (3 * (s + 1))) : 1; }
   LAPS_HD static constexpr int v(int s) { return 1 << (3 * s); }
   LAPS_HD static constexpr int pad(int i) { return i + (i >> 3) + (i >> 6) + (i >> 9); }
+  // pad(base + e * w) == pad(base) + pad(e * w) for e < 8 and w a power of two, whenever the three bits of `base` at the
+  // position of `e` are zero (every shift then splits without a carry): true for the stage-0 pattern (base = u < w) and
+  // for the middle stages (base = (u / w) * 8 w + u % w).  The second term is a compile-time constant in the unrolled
+  // loops below, so a padded address costs one addition instead of three shifts and three additions.
   // line pitch (in elements) congruent to `m` modulo 8: m=1 makes accesses that walk 8 lines at a
   // fixed position conflict free, m=2 serves 4 lines x 2 adjacent positions.
   LAPS_HD static constexpr int pitch(int m) {
@@ -148,8 +152,9 @@ struct Fft {
     bfly8<DIR>(r);
     if constexpr (G::NSTAGE == 1) return;   // N = 8: r[e] = X[e] already, nothing goes through the line
     twiddle8(r, w);
+    const int pu = G::pad(u);
     LAPS_UNROLL
-    for (int e = 0; e < 8; ++e) line[G::pad(u + e * G::w(0))] = r[e];
+    for (int e = 0; e < 8; ++e) line[pu + G::pad(e * G::w(0))] = r[e];
   }
   LAPS_D static void first(cplx (&r)[8], int u, cplx* __restrict__ line, const cplx* __restrict__ tw) {
     first_w(r, u, line, tw_stage<0>(tw, u));
@@ -160,14 +165,14 @@ struct Fft {
   LAPS_D static void middle_w(int u, cplx* __restrict__ line, cplx w) {
     constexpr int ws = G::w(S);
     const int jp = u & (ws - 1);
-    const int base = (u / ws) * (8 * ws) + jp;
+    const int pb = G::pad((u / ws) * (8 * ws) + jp);
     cplx r[8];
     LAPS_UNROLL
-    for (int e = 0; e < 8; ++e) r[e] = line[G::pad(base + e * ws)];
+    for (int e = 0; e < 8; ++e) r[e] = line[pb + G::pad(e * ws)];
     bfly8<DIR>(r);
     twiddle8(r, w);
     LAPS_UNROLL
-    for (int e = 0; e < 8; ++e) line[G::pad(base + e * ws)] = r[e];
+    for (int e = 0; e < 8; ++e) line[pb + G::pad(e * ws)] = r[e];
   }
   template <int S>
   LAPS_D static void middle(int u, cplx* __restrict__ line, const cplx* __restrict__ tw) {
@@ -192,6 +197,10 @@ struct Fft {
     }
   }
 
+  // padded position of element u + e * NT (the stage-0 input pattern; for RLAST == 8 also the output pattern kout):
+  // pad(u) + a constant, see Geom::pad
+  LAPS_D static int pad_in(int pu /* = G::pad(u) */, int e) { return pu + G::pad(e * G::NT); }
+
   // Output index k held in register slot e of thread u after the last stage.
   LAPS_D static int kout(int u, int e) {
     if constexpr (G::RLAST == 8) {
@@ -209,9 +218,9 @@ struct Fft {
 
   // Last stage: reads the line, leaves X[kout(u,e)] in r[e].
   LAPS_D static void last(cplx (&r)[8], int u, const cplx* __restrict__ line) {
-    const int base = last_base(u);
+    const int pb = G::pad(last_base(u));   // a multiple of 8: the eight slots are consecutive in the padded line too
     LAPS_UNROLL
-    for (int e = 0; e < 8; ++e) r[e] = line[G::pad(base + e)];
+    for (int e = 0; e < 8; ++e) r[e] = line[pb + e];
     if (G::RLAST == 8) {
       bfly8<DIR>(r);
     } else if (G::RLAST == 4) {

@@ -86,8 +86,14 @@ k_fwd_x(const double* __restrict__ in, size_t in_fstride, cplx* __restrict__ W1,
   F::first(r, u, line, tw);
   F::template finish_g<TL>(r, u, line, tw, 1 + l);   // a line's transform synchronises its own N/8 threads only
   group_barrier<G::NT, TL>(1 + l);          // everyone has consumed its last-stage slots
-  LAPS_UNROLL
-  for (int e = 0; e < 8; ++e) line[G::pad(F::kout(u, e))] = r[e];
+  if constexpr (G::RLAST == 8) {            // kout(u, e) = u + e * NT: one padded base + constants
+    const int pu = G::pad(u);
+    LAPS_UNROLL
+    for (int e = 0; e < 8; ++e) line[F::pad_in(pu, e)] = r[e];
+  } else {
+    LAPS_UNROLL
+    for (int e = 0; e < 8; ++e) line[G::pad(F::kout(u, e))] = r[e];
+  }
   __syncthreads();
   // split Z = A + iB into the two half spectra; TL line-pairs side by side give 2*TL*16-byte chunks,
   // each thread storing its (a, b) pair as one 256-bit access
@@ -252,8 +258,11 @@ k_inv_x(const cplx* __restrict__ V2, const LAPS_GRID_CONSTANT RealDst dst, int n
   const int l = tid / G::NT, u = tid % G::NT;
   cplx* line = sm + l * T::PITCH;
   cplx r[8];
-  LAPS_UNROLL
-  for (int e = 0; e < 8; ++e) r[e] = line[G::pad(u + e * G::NT)];
+  {
+    const int pu = G::pad(u);
+    LAPS_UNROLL
+    for (int e = 0; e < 8; ++e) r[e] = line[F::pad_in(pu, e)];
+  }
   F::first(r, u, line, tw);
   F::template finish_g<TL>(r, u, line, tw, 1 + l);   // a line's transform synchronises its own N/8 threads only
   double* oa = dst.ptr[g] + ((size_t)zl * ny + y0 + 2 * l) * N;

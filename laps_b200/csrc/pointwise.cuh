@@ -119,6 +119,20 @@ LAPS_D void cfl_shared_raise(unsigned long long* s_best, const double (&best)[3]
     if (best[d] > sb[d]) atomicMax(s_best + d, (unsigned long long)__double_as_longlong(best[d]));
 }
 
+// The exact evaluation as an out-of-line call: it runs for a small fraction of the points once the screen is active, and
+// keeping its live values (a dozen FP64 temporaries around the sqrt / div sequences) out of the calling loop leaves
+// calc_flux at three CTAs per SM.
+__device__ __noinline__ void cfl_point_call(double gamma, double di, double dmin, double floor_x, double floor_y, int hall,
+                                            double rho, double Bx, double By, double Bz, double ux, double uy, double uz, double p,
+                                            double& b0, double& b1, double& b2) {
+  CflParams P;
+  P.gamma = gamma; P.di = di; P.dmin = dmin; P.floor_x = floor_x; P.floor_y = floor_y; P.hall = hall;
+  Prim q; q.ux = ux; q.uy = uy; q.uz = uz; q.p = p;
+  double b[3] = {b0, b1, b2};
+  cfl_point(P, rho, Bx, By, Bz, q, b);
+  b0 = b[0]; b1 = b[1]; b2 = b[2];
+}
+
 struct FluxParams {
   const double* uu;     // [8][npts]
   const double* J;      // [3][npts] (Hall) or null
@@ -133,9 +147,10 @@ struct FluxParams {
   CflParams cfl;        // k_flux<true>: the CFL maxima of vardt are taken in the same sweep (same points, same primitives)
 };
 
-// 3 CTAs per SM (<= 85 registers): 11 loads + 19 stores per point want the occupancy (measured: 2 CTAs/SM cost 17 %)
+// 3 CTAs per SM (<= 85 registers): 11 loads + 19 stores per point want the occupancy (measured: 2 CTAs/SM cost 17 %);
+// the CFL variant reaches that through the out-of-line cfl_point_call
 template <bool CFL>
-__global__ void __launch_bounds__(256, CFL ? 2 : 3) k_flux(const FluxParams P) {
+__global__ void __launch_bounds__(256, 3) k_flux(const FluxParams P) {
   const size_t n = P.npts;
   const double gm1 = P.gamma - 1.0;
   double best[3] = {0.0, 0.0, 0.0};
@@ -153,7 +168,8 @@ __global__ void __launch_bounds__(256, CFL ? 2 : 3) k_flux(const FluxParams P) {
       double sb[3];
       cfl_shared_read(s_best, sb);
       if (!P.cfl.screen || cfl_may_raise(P.cfl, rho, mx, my, mz, Bx, By, Bz, en, sb)) {
-        cfl_point(P.cfl, rho, Bx, By, Bz, q, best);
+        cfl_point_call(P.cfl.gamma, P.cfl.di, P.cfl.dmin, P.cfl.floor_x, P.cfl.floor_y, P.cfl.hall, rho, Bx, By, Bz, q.ux, q.uy, q.uz, q.p,
+                       best[0], best[1], best[2]);
         cfl_shared_raise(s_best, best, sb);
       }
     }
@@ -327,6 +343,7 @@ struct DivbParams {
   const double* kxr; const double* kyr; const double* kze;
   double radius0, radius, cosa, sina; int corot_k;
   int mode2d, z_radial;   // 2D tree: the line axis carries ky, kz = 0 (2D/mhd.f90:527-550)
+  const double* kzr;      // 2D tree with if_corotating: raw line wave numbers (both components of k vary along the line)
   int v0;                 // first component of the vector: 4 = B (calc_max_divB), 1 = rho u (calc_max_divV, src_incompressible/mhd.f90:620-668)
   double* partial;
 };
@@ -346,7 +363,13 @@ __global__ void __launch_bounds__(256) k_divb(const DivbParams P) {
     if (P.z_radial) kxe = __ddiv_rn(__dmul_rn(kxr, P.radius0), P.radius);
     const double kzz = P.kze[kz];
     const cplx bx = P.u[(size_t)P.v0 * P.fstride + i], by = P.u[(size_t)(P.v0 + 1) * P.fstride + i], bz = P.u[(size_t)(P.v0 + 2) * P.fstride + i];
-    const cplx d = P.mode2d ? cadd(cadd(cmul_i(bx, kxe), cmul_i(by, kzz)), cmul_i(bz, 0.0))
+    double rx = kxe, ry = kzz;
+    if (P.mode2d && P.corot_k) {   // 2D/mhd.f90:539-545
+      const double kyl = P.kzr[kz];
+      rx = __dadd_rn(__dmul_rn(kxr, P.cosa), __dmul_rn(kyl, P.sina));
+      ry = __ddiv_rn(__dmul_rn(__dadd_rn(__dmul_rn(-kxr, P.sina), __dmul_rn(kyl, P.cosa)), P.radius0), P.radius);
+    }
+    const cplx d = P.mode2d ? cadd(cadd(cmul_i(bx, rx), cmul_i(by, ry)), cmul_i(bz, 0.0))
                             : cadd(cadd(cmul_i(bx, kxe), cmul_i(by, kye)), cmul_i(bz, kzz));
     best = fmax(best, sqrt(d.x * d.x + d.y * d.y));
   }

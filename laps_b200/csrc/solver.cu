@@ -97,7 +97,7 @@ struct laps_solver {
   cplx *uA = nullptr, *uB = nullptr, *rk = nullptr;   // u_fourier ping/pong, fnl_rk
   cplx *tw_x = nullptr, *tw_y = nullptr, *tw_z = nullptr;
   double *d_tab = nullptr;  // all 1-D tables in one allocation
-  double *kxr, *kyr, *kze, *ksq_x, *ksq_y, *ksq_z, *dax, *day, *daz;
+  double *kxr, *kyr, *kze, *ksq_x, *ksq_y, *ksq_z, *dax, *day, *daz, *kzr;
   std::vector<double> h_tab;
   std::vector<double> wnx, wny, wnz;
   double* d_partial = nullptr;
@@ -226,12 +226,14 @@ double filter_1d(double k, double L, int n, double af) {  // dealiasing.f90:36-4
 int upload_tables(S* s) {
   const laps_params& p = s->p;
   const int nxh = s->nxh, ny = s->ny, nz = s->nz;
-  s->h_tab.assign((size_t)3 * (nxh + ny + nz), 0.0);
+  s->h_tab.assign((size_t)3 * (nxh + ny + nz) + nz, 0.0);
   double* t = s->h_tab.data();
   double* kxr = t;            double* kyr = kxr + nxh;    double* kze = kyr + ny;
   double* ksq_x = kze + nz;   double* ksq_y = ksq_x + nxh; double* ksq_z = ksq_y + ny;
   double* dax = ksq_z + nz;   double* day = dax + nxh;     double* daz = day + ny;
+  double* kzr = daz + nz;     // raw line wave numbers (2D tree with if_corotating)
   const double r0 = p.radius0, r = s->radius;
+  for (int i = 0; i < nz; ++i) kzr[i] = s->wnz[i];
   for (int i = 0; i < nxh; ++i) kxr[i] = s->wnx[i];
   for (int i = 0; i < ny; ++i) kyr[i] = s->wny[i];
   for (int i = 0; i < nz; ++i) kze[i] = s->wnz[i] * r0 / r;          // mhdrhs.f90:192
@@ -241,6 +243,12 @@ int upload_tables(S* s) {
   if (s->ksq_initial) {                                               // mhdinit.f90:114-122
     for (int i = 0; i < ny; ++i) ksq_y[i] = s->wny[i] * s->wny[i];
     for (int i = 0; i < nz; ++i) ksq_z[i] = s->wnz[i] * s->wnz[i];
+  } else if (p.if_corotating && s->two_d) {                           // 2D/AEBmod.f90:101-106: the line axis carries ky
+    // k_square = kx^2 c1 + ky^2 c2 + kx ky 2 cos sin (1 - (R0/R)^2): the first term from ksq_x (times c1 on the device), the
+    // second from this table, the cross term per mode (corot2d_cross)
+    const double c2 = s->sina * s->sina + (s->cosa * r0 / r) * (s->cosa * r0 / r);
+    for (int i = 0; i < ny; ++i) ksq_y[i] = 0.0;
+    for (int i = 0; i < nz; ++i) ksq_z[i] = (s->wnz[i] * s->wnz[i]) * c2;
   } else if (p.if_corotating) {                                       // AEBmod.f90:103-110
     for (int i = 0; i < ny; ++i) ksq_y[i] = s->wny[i] * s->wny[i];
     for (int i = 0; i < nz; ++i) { const double a = s->wnz[i] * r0 / r; ksq_z[i] = a * a; }
@@ -652,6 +660,8 @@ void fill_zparams(S* s, ZParams& z, bool prune = false) {
   z.ksq_c2 = s->sina * s->sina + (s->cosa * p.radius0 / s->radius) * (s->cosa * p.radius0 / s->radius);
   z.ksq_c3 = 1 - q * q;
   z.corot_k = (p.if_AEB && p.if_corotating) ? 1 : 0;
+  z.corot2d = (s->two_d && z.corot_k) ? 1 : 0;
+  z.kzr = s->kzr; z.ksq_cross = z.ksq_c3;
   z.corot_ksq = (!s->ksq_initial && p.if_corotating) ? 1 : 0;
   z.aeb = p.if_AEB;
   z.visc_imp = p.if_visc && !p.if_visc_exp; z.visc_exp = p.if_visc && p.if_visc_exp;
@@ -666,8 +676,14 @@ void fill_zparams(S* s, ZParams& z, bool prune = false) {
   z.aeb_p = 2.0 * p.adiabatic_index;   // src_incompressible/mhdrhs.f90:202-203
 }
 
-ZTask rhs_task(int v, int gout, int fa, double ca, int fb, double cb, int fx, double cx, double sg, int fc, double sc) {
+ZTask blank_task() {
   ZTask t; std::memset(&t, 0, sizeof(t));
+  t.fa = t.fb = t.fx = t.fc = t.fc2 = -1; t.cf1 = 1.0; t.gout = -1;
+  return t;
+}
+
+ZTask rhs_task(int v, int gout, int fa, double ca, int fb, double cb, int fx, double cx, double sg, int fc, double sc) {
+  ZTask t = blank_task();
   t.kind = kZRhs; t.v = v; t.gout = gout;
   t.fa = fa; t.ca = ca; t.fb = fb; t.cb = cb; t.fx = fx; t.cx = cx; t.sg = sg; t.fc = fc; t.sc = sc;
   static const double aebc[8] = {2.0, 2.0, 3.0, 3.0, 2.0, 1.0, 1.0, 0.0};
@@ -684,7 +700,7 @@ int launch_current_tasks(S* s, const cplx* u, bool prune, bool want_j = true, in
   int n = 0;
   if (want_j)
     for (int j = 0; j < 3; ++j) {
-      ZTask t; std::memset(&t, 0, sizeof(t));
+      ZTask t = blank_task();
       t.kind = kZCurrent; t.jcomp = j; t.gout = 8 + j; t.fa = t.fb = t.fx = t.fc = -1;
       z.task[n++] = t;
     }
@@ -692,7 +708,7 @@ int launch_current_tasks(S* s, const cplx* u, bool prune, bool want_j = true, in
     z.u_old = s->uA; z.u_out = s->uB;
     z.cc = s->cc1[irk]; z.dd = s->dd1[irk]; z.dt_irk = s->tstep[irk];
     z.read_rk = (irk > 0); z.write_rk = (irk < 2);
-    ZTask t; std::memset(&t, 0, sizeof(t));
+    ZTask t = blank_task();
     t.kind = kZMass; t.v = 0; t.gout = 0; t.aeb_c = 2.0; t.fa = t.fb = t.fx = t.fc = -1;
     z.task[n++] = t;
   }
@@ -759,7 +775,7 @@ int spectrum_from_real(S* s, bool prune) {
   ZParams z; fill_zparams(s, z, prune);
   z.u_out = s->uA;
   for (int v = 0; v < 8; ++v) {
-    ZTask t; std::memset(&t, 0, sizeof(t));
+    ZTask t = blank_task();
     t.kind = kZForwardOnly; t.v = v; t.gout = -1; t.fa = v; t.fb = t.fx = t.fc = -1;
     z.task[v] = t;
   }
@@ -779,13 +795,13 @@ int stage_incomp(S* s, int irk) {
     ZParams z; fill_zparams(s, z, prune);
     z.u_in = s->uA;
     for (int j = 0; j < 3; ++j) {
-      ZTask t; std::memset(&t, 0, sizeof(t));
+      ZTask t = blank_task();
       t.kind = kZCurrent; t.jcomp = j; t.gout = j; t.fa = t.fb = t.fx = t.fc = -1;
       z.task[j] = t;
     }
     for (int b = 0; b < 3; ++b)
       for (int a = 0; a < 3; ++a) {
-        ZTask t; std::memset(&t, 0, sizeof(t));
+        ZTask t = blank_task();
         t.kind = kZGrad; t.v = 1 + b; t.jcomp = a; t.cx = s->rho0; t.gout = 3 + 3 * b + a; t.fa = t.fb = t.fx = t.fc = -1;
         z.task[3 + 3 * b + a] = t;
       }
@@ -1263,7 +1279,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
   alloc((void**)&s->uB, 8 * s->csz * sizeof(cplx));
   alloc((void**)&s->rk, 8 * s->csz * sizeof(cplx));
   alloc((void**)&s->tw_x, s->nx * sizeof(cplx)); alloc((void**)&s->tw_y, s->ny * sizeof(cplx)); alloc((void**)&s->tw_z, s->nz * sizeof(cplx));
-  alloc((void**)&s->d_tab, (size_t)3 * (s->nxh + s->ny + s->nz) * sizeof(double));
+  alloc((void**)&s->d_tab, ((size_t)3 * (s->nxh + s->ny + s->nz) + s->nz) * sizeof(double));
   alloc((void**)&s->d_partial, (size_t)32 * s->nblk * sizeof(double));
   alloc((void**)&s->d_scal, 64 * sizeof(double));
   alloc((void**)&s->xblk, sizeof(XchgBlock));
@@ -1278,6 +1294,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
     s->kxr = t; s->kyr = s->kxr + s->nxh; s->kze = s->kyr + s->ny;
     s->ksq_x = s->kze + s->nz; s->ksq_y = s->ksq_x + s->nxh; s->ksq_z = s->ksq_y + s->ny;
     s->dax = s->ksq_z + s->nz; s->day = s->dax + s->nxh; s->daz = s->day + s->ny;
+    s->kzr = s->daz + s->nz;
   }
   for (int a = 0; a < 3; ++a) {
     const int n = a == 0 ? s->nx : (a == 1 ? s->ny : s->nz);
@@ -1562,7 +1579,7 @@ static int set_primitive_modes_body(laps_handle s, int32_t nmodes, const int32_t
     ZParams z; fill_zparams(s, z);
     z.u_in = s->uB;
     for (int v = 0; v < 8; ++v) {
-      ZTask t; std::memset(&t, 0, sizeof(t));
+      ZTask t = blank_task();
       t.kind = kZInverseOnly; t.v = v; t.gout = v; t.fa = t.fb = t.fx = t.fc = -1;
       z.task[v] = t;
     }
@@ -1795,7 +1812,7 @@ static int max_div_real_body(laps_handle s, double out[2]) {
   ZParams z; fill_zparams(s, z, prune);
   z.u_in = s->uA;
   for (int j = 0; j < 2; ++j) {
-    ZTask t; std::memset(&t, 0, sizeof(t));
+    ZTask t = blank_task();
     t.kind = kZDiv; t.v = j == 0 ? 4 : 1; t.cx = j == 0 ? 1.0 : (s->incomp ? s->rho0 : 1.0); t.gout = j; t.fa = t.fb = t.fx = t.fc = -1;
     z.task[j] = t;
   }
@@ -1951,7 +1968,7 @@ static int fft_forward_body(laps_handle s, const double* real_fields, int32_t nf
   ZParams z; fill_zparams(s, z);
   z.u_out = s->uB;
   for (int v = 0; v < nfields; ++v) {
-    ZTask t; std::memset(&t, 0, sizeof(t));
+    ZTask t = blank_task();
     t.kind = kZForwardOnly; t.v = v; t.gout = -1; t.fa = v; t.fb = t.fx = t.fc = -1;
     z.task[v] = t;
   }
@@ -1971,7 +1988,7 @@ static int fft_inverse_body(laps_handle s, const double* spec_in, int32_t nfield
   ZParams z; fill_zparams(s, z);
   z.u_in = s->uB;
   for (int v = 0; v < nfields; ++v) {
-    ZTask t; std::memset(&t, 0, sizeof(t));
+    ZTask t = blank_task();
     t.kind = kZInverseOnly; t.v = v; t.gout = v; t.fa = t.fb = t.fx = t.fc = -1;
     z.task[v] = t;
   }

@@ -160,7 +160,7 @@ k_incomp_z(const ZParams P) {
       for (int e = 0; e < 8; ++e) W[G::pad(FF::kout(u, e))] = r[e];
       __syncthreads();
       LAPS_UNROLL
-      for (int e = 0; e < 8; ++e) r[e] = W[G::pad(u + e * G::NT)];
+      for (int e = 0; e < 8; ++e) r[e] = W[G::pad(u) + G::pad(e * G::NT)];
       __syncthreads();
     }
     FI::first(r, u, W, P.tw);

@@ -295,7 +295,7 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
       for (int e = 0; e < 8; ++e) W[G::pad(FF::kout(u, e))] = r[e];
       __syncthreads();
       LAPS_UNROLL
-      for (int e = 0; e < 8; ++e) r[e] = W[G::pad(u + e * G::NT)];
+      for (int e = 0; e < 8; ++e) r[e] = W[G::pad(u) + G::pad(e * G::NT)];
       __syncthreads();
     }
     // ---------------- inverse z, stored on the owner of each z (transpose_zy fused) ----------------

@@ -27,13 +27,18 @@ enum ZKind { kZRhs = 0, kZForwardOnly = 1, kZInverseOnly = 2, kZCurrent = 3,
 
 // One row of work (blockIdx.y).  For kZRhs:
 //   G = ca*(i kx)*W2[fa] + cb*(i ky)*W2[fb] + cx*W2[fx]      (missing terms have index < 0)
-//   fnl = sg*FFTz[G] + sc*(i kz)*FFTz[W2[fc]]
+//   fnl = sg*FFTz[G] + sc*(i kz)*FFTz[cf1*W2[fc] + cf2*W2[fc2]]
 struct ZTask {
   int kind;
   int v;       // state component updated (0..7) / read (kZInverseOnly)
   int gout;    // slot of the inverse-z output in V1, < 0: none
   int fa, fb, fx, fc;
   double ca, cb, cx, sg, sc;
+  // second field of the (i k_line) term: fnl = sg*FFTz[G] + sc*(i k_line)*FFTz[cf1*W2[fc] + cf2*W2[fc2]].  Used by the 2D tree
+  // with if_corotating, where both components of the rotated wave vector vary along the line (2D/mhdrhs.f90:282-288);
+  // everywhere else fc2 < 0 and cf1 = 1.
+  int fc2;
+  double cf1, cf2;
   double aeb_c;   // 2,2,3,3,2,1,1,0 (mhdrhs.f90:235-247)
   int diff;       // 0 none, 1 viscosity (v=1..3), 2 resistivity (v=4..6)
   int jcomp;      // kZCurrent: 0,1,2
@@ -83,6 +88,13 @@ struct ZParams {
   // non-zero per-axis flag (option 3).
   int kzprune;
   int mode2d;            // 2D tree: the line axis is the reference's y, d/dz = 0 (src_compressible/2D/mhdrhs.f90:272)
+  // 2D tree with if_corotating (2D/mhdrhs.f90:282-288, 2D/AEBmod.f90:101-106): kx_eff = kx cos + ky sin and
+  // ky_eff = (-kx sin + ky cos) R0/R both vary along the line (which carries ky).  The column constants kxe, kye below are
+  // then their kx parts (the 3D formulas with the column's ky = 0); the ky parts enter through ZTask::fc/fc2, and where a
+  // kernel needs the full vector per mode it uses kzr, the RAW line wave numbers.
+  int corot2d;
+  const double* kzr;
+  double ksq_cross;      // corot2d: 1 - (R0/R)^2 of the cross term of k_square (2D/AEBmod.f90:104-105)
   int z_radial;          // 2D/mhdrhs.f90:278-280: kx is stretched too
   int bg_all_kz;         // 2D/mhdrhs.f90:372-374: if_conserve_background skips every mode with ix == 1
   double da_thresh;      // dealias option 1: smallest s with sqrt(s) > 1./3. (dealiasing.f90:94)
@@ -152,6 +164,21 @@ LAPS_D double ksq_xy_eval(const ZParams& P, double kxr, double kyr, int kx, int 
   return ksq_xy_of(P, kxr, kyr, __ldg(P.ksq_x + kx), __ldg(P.ksq_y + ky));
 }
 
+// 2D tree with if_corotating: the rotated wave vector of mode (kx, ky = line index) in the reference's operation order
+// (2D/mhdrhs.f90:282-288)
+LAPS_D void corot2d_k(const ZParams& P, double kxr, double kyl, double& kx_eff, double& ky_eff) {
+  kx_eff = __dadd_rn(__dmul_rn(kxr, P.cosa), __dmul_rn(kyl, P.sina));
+  ky_eff = __ddiv_rn(__dmul_rn(__dadd_rn(__dmul_rn(-kxr, P.sina), __dmul_rn(kyl, P.cosa)), P.radius0), P.radius);
+}
+// ... and the cross term kx*ky*2*cos*sin*(1 - (R0/R)^2) of its k_square (2D/AEBmod.f90:104-105)
+LAPS_D double corot2d_cross(const ZParams& P, double kxr, double kyl) {
+  double t = __dmul_rn(kxr, kyl);
+  t = __dmul_rn(t, 2.0);
+  t = __dmul_rn(t, P.cosa);
+  t = __dmul_rn(t, P.sina);
+  return __dmul_rn(t, P.ksq_cross);
+}
+
 // one column group (CG columns) of one task row
 template <int N, int CG>
 LAPS_D void spec_z_group(const ZParams& P, const ZTask& K, const int group, cplx* sm) {
@@ -205,6 +232,14 @@ LAPS_D void spec_z_group(const ZParams& P, const ZTask& K, const int group, cplx
         const cplx* s = P.W2 + (size_t)K.fc * P.fstride + coff;
         LAPS_UNROLL
         for (int e = 0; e < 8; ++e) r[e] = s[u + e * G::NT];
+        if (K.fc2 >= 0) {   // 2D tree with if_corotating: two fields share the (i k_line) factor
+          const cplx* s2 = P.W2 + (size_t)K.fc2 * P.fstride + coff;
+          LAPS_UNROLL
+          for (int e = 0; e < 8; ++e) r[e] = cadd(cscale(r[e], K.cf1), cscale(s2[u + e * G::NT], K.cf2));
+        } else if (K.cf1 != 1.0) {
+          LAPS_UNROLL
+          for (int e = 0; e < 8; ++e) r[e] = cscale(r[e], K.cf1);
+        }
       }
       FF::first(r, u, lineG, P.tw);
       FF::finish(r, u, lineG, P.tw);
@@ -276,6 +311,7 @@ LAPS_D void spec_z_group(const ZParams& P, const ZTask& K, const int group, cplx
       double ksq = 0.0;
       if (need_ksq) {
         ksq = __dadd_rn(ksq_xy, __ldg(P.ksq_z + kz));
+        if (P.corot2d && P.corot_ksq) ksq = __dadd_rn(ksq, corot2d_cross(P, kxr, __ldg(P.kzr + kz)));
         const double cee = (keep_bg && (P.bg_all_kz || kz == 0)) ? 0.0 : ce;
         fnl.x -= (cee * uo.x) * ksq;
         fnl.y -= (cee * uo.y) * ksq;
@@ -314,7 +350,7 @@ LAPS_D void spec_z_group(const ZParams& P, const ZTask& K, const int group, cplx
       for (int e = 0; e < 8; ++e) lineG[G::pad(FF::kout(u, e))] = r[e];
       __syncthreads();
       LAPS_UNROLL
-      for (int e = 0; e < 8; ++e) r[e] = lineG[G::pad(u + e * G::NT)];
+      for (int e = 0; e < 8; ++e) r[e] = lineG[G::pad(u) + G::pad(e * G::NT)];
       __syncthreads();
     }
   } else if (K.kind == kZInverseOnly) {
@@ -333,12 +369,14 @@ LAPS_D void spec_z_group(const ZParams& P, const ZTask& K, const int group, cplx
     for (int e = 0; e < 8; ++e) {
       const int kz = u + e * G::NT;
       const double kzz = __ldg(P.kze + kz);
-      const double ry = P.mode2d ? kzz : kye, rz = P.mode2d ? 0.0 : kzz;
+      double rx = kxe, ry = P.mode2d ? kzz : kye;
+      const double rz = P.mode2d ? 0.0 : kzz;
+      if (P.corot2d) corot2d_k(P, kxr, __ldg(P.kzr + kz), rx, ry);
       const bool keep = live && !z_mode_dead(P, dxy, kz);   // masked modes: zero in memory, not touched
       const cplx m1 = keep ? M[kz] : mk(0.0, 0.0);
       const cplx m2 = keep ? M[P.fstride + kz] : mk(0.0, 0.0);
       const cplx m3 = keep ? M[2 * P.fstride + kz] : mk(0.0, 0.0);
-      const cplx sum = cadd(cadd(cmul_i(m1, kxe), cmul_i(m2, ry)), cmul_i(m3, rz));
+      const cplx sum = cadd(cadd(cmul_i(m1, rx), cmul_i(m2, ry)), cmul_i(m3, rz));
       cplx fnl = mk(-sum.x, -sum.y);
       const cplx uo = keep ? P.u_old[voff + kz] : mk(0.0, 0.0);
       fnl.x -= ca * uo.x;
@@ -396,9 +434,11 @@ LAPS_D void spec_z_group(const ZParams& P, const ZTask& K, const int group, cplx
       const double kzz = __ldg(P.kze + kz);
       // k_{j+1} B_{j+2} - k_{j+2} B_{j+1}   with (k0,k1,k2) = (kx,ky,kz) of the REFERENCE axes; in the
       // 2D tree the line axis carries the reference's ky and kz = 0 (2D/mhdrhs.f90:412-440)
-      const double ry = P.mode2d ? kzz : kye, rz = P.mode2d ? 0.0 : kzz;
-      const double k1 = (j == 0) ? ry : (j == 1 ? rz : kxe);
-      const double k2 = (j == 0) ? rz : (j == 1 ? kxe : ry);
+      double rx = kxe, ry = P.mode2d ? kzz : kye;
+      const double rz = P.mode2d ? 0.0 : kzz;
+      if (P.corot2d) corot2d_k(P, kxr, __ldg(P.kzr + kz), rx, ry);
+      const double k1 = (j == 0) ? ry : (j == 1 ? rz : rx);
+      const double k2 = (j == 0) ? rz : (j == 1 ? rx : ry);
       const bool keep = live && !z_mode_dead(P, dxy_col, kz);   // masked modes of the state are zero
       const cplx b1 = keep ? B1[kz] : mk(0.0, 0.0);
       const cplx b2 = keep ? B2[kz] : mk(0.0, 0.0);

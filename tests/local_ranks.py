@@ -3,7 +3,13 @@ laps_connect_local (include/laps_b200.h) — the single-process multi-GPU mode o
 same GPU for every rank: the peer stores then stay on one device, but the decomposition tables, the transpose index
 maps (contiguous ky slabs or round-robin rows), the device-side flag barriers and the allreduce are exactly those of
 an N-GPU run, so a box with a single GPU checks the multi-rank path against the single-grid oracle too.
-GPU only (the test-only kernel emulator is not thread-safe)."""
+GPU only (the test-only kernel emulator is not thread-safe).
+
+Ranks that SHARE a device need every stream of every handle in a hardware work queue of its own: with the default of 8
+queues (CUDA_DEVICE_MAX_CONNECTIONS) the 2 x N streams alias, and a flag kernel that spins in one stream then holds up the
+kernels of the rank it is waiting for — a deadlock that one-GPU-per-rank runs cannot have.  tests/test_gpu_multirank.py
+therefore runs this module in a child process with CUDA_DEVICE_MAX_CONNECTIONS=32 (it must be set before the CUDA
+context exists):   python tests/local_ranks.py '<json>'."""
 import os
 import threading
 
@@ -111,3 +117,51 @@ def run_local(world, shape, case, steps=2, devices=None, lib_path=None, env=None
     finally:
         for g in gs:
             g.close()
+
+
+def check_bounded_wait(devices):
+    """A rank that never makes the matching collective call must not wedge its peers (exchange.cuh): the waiting rank's
+    flag kernel gives up after LAPS_XCHG_TIMEOUT_S, the failure reaches the host through laps_last_error, and the abort
+    word it raises fails the other rank's next call as well."""
+    import time
+    from laps_b200 import capi
+    p, prim = pc.make_case(32, 32, 32, hall=True, aeb=True)
+    gs = make_solvers(2, p, devices, env=dict(LAPS_XCHG_TIMEOUT_S="1.0"))
+
+    def fails(fn, pattern):
+        try:
+            fn()
+        except capi.LapsError as e:
+            assert pattern in str(e), str(e)
+            return
+        raise AssertionError("did not raise a LapsError")
+
+    try:
+        t0 = time.perf_counter()
+        fails(lambda: gs[0].set_primitive(prim[:, :16]), "ran out of its budget")     # collective; rank 1 never calls it
+        assert time.perf_counter() - t0 < 20.0
+        fails(lambda: gs[0].vardt(), "abort")                                         # the handle stays dead
+
+        def other():                                                                  # and the peer learns about it at its next wait
+            gs[1].set_primitive(prim[:, 16:])
+            gs[1].sync()
+        fails(other, "abort")
+    finally:
+        for g in gs:
+            g.close()
+
+
+if __name__ == "__main__":
+    import json
+    import sys
+    cfg = json.loads(sys.argv[1])
+    import torch
+    ndev = torch.cuda.device_count()
+    if cfg.get("mode") == "bounded_wait":
+        check_bounded_wait([r % ndev for r in range(2)])
+    else:
+        world = cfg["world"]
+        worst = run_local(world, tuple(cfg["shape"]), cfg.get("case", {}), steps=cfg.get("steps", 2), devices=[r % ndev for r in range(world)],
+                          env=cfg.get("env"), incompressible=cfg.get("incompressible", False), expect_stride=cfg.get("expect_stride"))
+        print(f"max rel L2 {worst:.3e}")
+    print("local ranks ok")

@@ -44,54 +44,44 @@ def test_two_gpus_incompressible_tree():
 # ---------------------------------------------------------------------------------------------------------------
 # The same decomposition with every rank in ONE process (laps_connect_local, one host thread per handle).  The ranks
 # may share a device, so these run — and check the 4- and 8-rank ownership forms against the oracle — on a 1-GPU box.
+# Each case runs tests/local_ranks.py in a child process with CUDA_DEVICE_MAX_CONNECTIONS=32 (see there).
 # ---------------------------------------------------------------------------------------------------------------
-def _devices(world):
-    n = _ngpu()
-    return [r % n for r in range(world)]
+def _local(cfg, timeout=900):
+    import json
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", LAPS_ORACLE_WORKERS="4")
+    out = subprocess.run([sys.executable, os.path.join(here, "local_ranks.py"), json.dumps(cfg)], env=env, stdout=subprocess.PIPE,
+                         stderr=subprocess.STDOUT, text=True, timeout=timeout)
+    assert out.returncode == 0 and "local ranks ok" in out.stdout, out.stdout[-4000:]
 
 
 @pytest.mark.parametrize("world,stride", [(2, 1), (3, 1), (4, 4), (8, 8)])
 def test_connect_local_threads_parity(world, stride):
     """Default ownership: decompose_1d slabs up to 3 ranks, round-robin ky rows from 4 ranks on."""
-    from local_ranks import run_local
     shape = (64, 64, 64) if world != 3 else (32, 64, 32)
-    run_local(world, shape, dict(hall=True, aeb=True, dealias=1), steps=2, devices=_devices(world), expect_stride=stride)
+    _local(dict(world=world, shape=shape, case=dict(hall=True, aeb=True, dealias=1), steps=2, expect_stride=stride))
 
 
 @pytest.mark.parametrize("world", [4, 8])
 def test_connect_local_threads_reference_slabs(world):
-    from local_ranks import run_local
-    run_local(world, (64, 64, 64), dict(hall=True, aeb=True, dealias=1), steps=2, devices=_devices(world),
-              env=dict(LAPS_TUNE_CYCLIC="0"), expect_stride=1)
+    _local(dict(world=world, shape=(64, 64, 64), case=dict(hall=True, aeb=True, dealias=1), steps=2,
+                env=dict(LAPS_TUNE_CYCLIC="0"), expect_stride=1))
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_connect_local_threads_one_stream_schedule(world):
+    """LAPS_TUNE_OVERLAP=0: the one-stream schedule (the default schedule from 2 ranks on uses two streams)."""
+    _local(dict(world=world, shape=(64, 64, 64), case=dict(hall=True, aeb=True, dealias=1), steps=2, env=dict(LAPS_TUNE_OVERLAP="0")))
 
 
 def test_connect_local_threads_other_physics():
     """Corotation + filter dealiasing (no pruning) on 3 ranks with a remainder slab; incompressible tree on 2."""
-    from local_ranks import run_local
-    run_local(3, (32, 64, 32), dict(hall=True, aeb=True, corot=True, dealias=2), steps=1, devices=_devices(3))
-    run_local(2, (64, 64, 64), dict(hall=True, aeb=True, dealias=1), steps=2, devices=_devices(2), incompressible=True)
+    _local(dict(world=3, shape=(32, 64, 32), case=dict(hall=True, aeb=True, corot=True, dealias=2), steps=1))
+    _local(dict(world=2, shape=(64, 64, 64), case=dict(hall=True, aeb=True, dealias=1), steps=2, incompressible=True))
 
 
 def test_exchange_wait_is_bounded():
-    """A rank that never makes the matching collective call must not wedge its peers (exchange.cuh): the waiting rank's
-    flag kernel gives up after LAPS_XCHG_TIMEOUT_S, the failure reaches the host through laps_last_error, and the abort
-    word it raises fails the other rank's next call as well."""
-    import time
-    import parity_common as pc
-    from laps_b200 import capi
-    from local_ranks import make_solvers
-    p, prim = pc.make_case(32, 32, 32, hall=True, aeb=True)
-    gs = make_solvers(2, p, _devices(2), env=dict(LAPS_XCHG_TIMEOUT_S="1.0"))
-    try:
-        t0 = time.perf_counter()
-        with pytest.raises(capi.LapsError, match="ran out of its budget"):
-            gs[0].set_primitive(prim[:, :16])       # collective; rank 1 never calls it
-        assert time.perf_counter() - t0 < 20.0
-        with pytest.raises(capi.LapsError, match="abort"):
-            gs[0].vardt()                           # the handle stays dead
-        with pytest.raises(capi.LapsError, match="abort"):
-            gs[1].set_primitive(prim[:, 16:])       # and the peer learns about it at its next wait
-            gs[1].sync()
-    finally:
-        for g in gs:
-            g.close()
+    _local(dict(mode="bounded_wait"))
