@@ -26,16 +26,24 @@ struct PeerTable {
   int off[kMaxPeers];   // first global index owned by peer p
   int len[kMaxPeers];   // number owned
   int nparts;
-  int quot;             // n / nparts (owner = min(i / quot, nparts-1))
+  int quot;             // n / nparts (decompose_1d: every part has quot entries, the last one the remainder too)
   // cyclic = 0: contiguous slabs, the reference's decompose_1d (parallel.f90:326-349).  cyclic = 1 (ky axis only,
   // LAPS_TUNE_CYCLIC): index i lives on rank i % nparts at local position i / nparts, which spreads the rows the
   // dealiasing mask keeps (low |ky|) evenly over the ranks.
   int cyclic;
+  // (no integer divisions on the device: the passes call these once per stored element)
   LAPS_HD int owner(int i) const {
-    if (cyclic) return i % nparts;
-    int p = i / quot; return p < nparts - 1 ? p : nparts - 1;
+    if (nparts == 1) return 0;
+    if (cyclic) return (nparts & (nparts - 1)) == 0 ? (i & (nparts - 1)) : i % nparts;
+    int p = 0;
+    for (int q = 1; q < kMaxPeers; ++q) p += (q < nparts && i >= off[q]) ? 1 : 0;   // slabs are contiguous and ordered
+    return p;
   }
-  LAPS_HD int local(int i, int p) const { return cyclic ? i / nparts : i - off[p]; }
+  LAPS_HD int local(int i, int p) const {
+    if (!cyclic) return i - off[p];
+    return (nparts & (nparts - 1)) == 0 ? (i >> shift) : i / nparts;
+  }
+  int shift;            // log2(nparts) when nparts is a power of two (cyclic ownership)
 };
 
 // Shared-memory tile of TL lines.  A quarter warp (8 lanes of a 128-bit access) covers

@@ -129,6 +129,7 @@ struct laps_solver {
   // spherical mask (option 1): per-kx largest surviving |ky| and the list of this rank's surviving columns
   int* d_kymax_x = nullptr;   // [nxh]
   int* d_colmap = nullptr;    // [pr_ncol]
+  int* d_colkx = nullptr;     // [pr_ncol] kx of each entry of d_colmap
   int pr_ncol = 0;            // this rank's surviving columns
   long long pr_cols_all = 0;  // surviving (kx, ky) columns of ALL ranks (what the y passes of this rank's z slab visit)
   size_t dev_bytes = 0;       // device memory allocated by this handle
@@ -332,7 +333,7 @@ double bytes_z(const S* s, const ZParams& z, int ntasks) {
     const ZTask& t = z.task[i];
     const double out = t.gout >= 0 ? line : 0.0;
     switch (t.kind) {
-      case kZRhs: in(t.fa); in(t.fb); in(t.fx); in(t.fc);
+      case kZRhs: in(t.fa); in(t.fb); in(t.fx); in(t.fc); in(t.fc2);
                   b += out + modes * (1 + (z.read_rk ? 1 : 0) + 1 + (z.write_rk ? 1 : 0)); break;
       case kZForwardOnly: in(t.fa); b += line; break;
       case kZInverseOnly: b += line + out; break;
@@ -643,7 +644,7 @@ void fill_zparams(S* s, ZParams& z, bool prune = false) {
   std::memset(&z, 0, sizeof(z));
   if (prune) {
     z.nkyl = s->pr_nkyl; z.nA = s->pr_nA; z.a0 = s->pr_a0; z.b0 = s->pr_b0; z.ncolc = s->nkx * s->pr_nkyl;
-    if (s->d_colmap) { z.colmap = s->d_colmap; z.ncolc = s->pr_ncol; }
+    if (s->d_colmap) { z.colmap = s->d_colmap; z.colkx = s->d_colkx; z.ncolc = s->pr_ncol; }
     z.kzprune = s->kzprune ? 1 : 0;
   } else { z.nkyl = s->nyl; z.nA = s->nyl; z.a0 = 0; z.b0 = 0; z.ncolc = (int)s->ncol; }
   const laps_params& p = s->p;
@@ -1059,6 +1060,27 @@ int stage(S* s, int irk) {
       z.task[5] = rhs_task(5, 5, L[14], 1.0, -1, 0.0, -1, 0.0, +1.0, -1, 0.0);
       z.task[6] = rhs_task(6, 6, L[13], -1.0, -1, 0.0, -1, 0.0, +1.0, L[12], +1.0);
       z.task[7] = rhs_task(7, 7, L[15], 1.0, -1, 0.0, X, -1.0, -1.0, L[16], -1.0);
+      if (z.corot2d) {
+        // if_corotating (2D/mhdrhs.f90:282-288): kx_eff = kx cos + ky sin, ky_eff = (-kx sin + ky cos) R0/R.  The kx parts
+        // are the column constants the kernel applies to fa, fb before the line transform; the ky parts share the factor
+        // (i ky R0/R) the kernel applies after it:  ky sin F^a + ky cos (R0/R) F^b = (ky R0/R) [(sin R/R0) F^a + cos F^b].
+        const double cq = s->cosa, sq = s->sina * s->radius / p.radius0;
+        auto div_row = [&](int v, int fxa, int fya, int X_, double cxv) {   // -(kx_eff F^a + ky_eff F^b) (+ cx X^)
+          ZTask t = rhs_task(v, v, fxa, 1.0, fya, 1.0, X_, cxv, -1.0, fya, -1.0);
+          t.cf1 = cq; t.fc2 = fxa; t.cf2 = sq;
+          return t;
+        };
+        z.task[0] = div_row(0, L[0], L[1], -1, 0.0);
+        z.task[1] = div_row(1, L[3], L[4], -1, 0.0);
+        z.task[2] = div_row(2, L[6], L[7], -1, 0.0);
+        z.task[3] = div_row(3, L[9], L[10], -1, 0.0);
+        z.task[7] = div_row(7, L[15], L[16], X, -1.0);
+        // fnl5 = -ky_eff F15 ; fnl6 = kx_eff F15 ; fnl7 = ky_eff F13 - kx_eff F14
+        z.task[4] = rhs_task(4, 4, -1, 0.0, L[14], 1.0, -1, 0.0, -1.0, L[14], -1.0);  z.task[4].cf1 = cq;
+        z.task[5] = rhs_task(5, 5, L[14], 1.0, -1, 0.0, -1, 0.0, +1.0, L[14], +1.0);  z.task[5].cf1 = sq;
+        z.task[6] = rhs_task(6, 6, L[13], -1.0, L[12], 1.0, -1, 0.0, +1.0, L[12], +1.0);
+        z.task[6].cf1 = cq; z.task[6].fc2 = L[13]; z.task[6].cf2 = -sq;
+      }
       if (s->ext_slot >= 0) { z.task[6].fx = s->ext_slot; z.task[6].cx = 1.0; }   // fnl(7) += external_force_fourier(1), 2D/mhdrhs.f90:370-372
       if (p.if_AEB && p.if_z_radial) {   // 2D/mhdrhs.f90:324-343
         static const double c2[8] = {2.0, 3.0, 3.0, 2.0, 1.0, 1.0, 2.0, 0.0};
@@ -1068,7 +1090,8 @@ int stage(S* s, int irk) {
     const int t0 = s->mass_from_state ? 1 : 0;   // the continuity row is a kZMass task of the launch below
     if (t0) for (int v = 1; v < 8; ++v) z.task[v - 1] = z.task[v];
     if (use_overlap(s)) return stage_back_overlap(s, irk, z, 8 - t0);
-    if (s->tune_rhs) LAPS_TRY(rhs_z(s, z, 8 - t0));
+    // (the persistent kernel carries one field in its (i k_line) term: the 2D tree with if_corotating goes through k_spec_z)
+    if (s->tune_rhs && !z.corot2d) LAPS_TRY(rhs_z(s, z, 8 - t0));
     else LAPS_TRY(spec_z(s, z, 8 - t0, "spec_z"));
   }
   // J for the next stage's calc_flux.  After the last stage of a step in the expanding box the
@@ -1134,9 +1157,10 @@ int laps_create(const laps_params* params, laps_handle* out) {
     // ky tables become the internal z tables (Ly -> Lz, afy -> afz).
     if (u.nz != 1) { g_create_error = "ndim = 2 needs nz = 1"; return 1; }
     if (u.nranks != 1) { g_create_error = "the 2D tree runs on one GPU (nranks = 1)"; return 1; }
-    if (u.if_AEB && u.if_corotating) { g_create_error = "if_corotating is not supported in the 2D tree"; return 1; }
+    if (u.if_AEB && u.if_corotating && u.incompressible) { g_create_error = "if_corotating is not supported in the incompressible 2D tree"; return 1; }
+    if (u.if_AEB && u.if_corotating && u.if_z_radial) { g_create_error = "if_z_radial and if_corotating exclude each other (2D/mhd.f90:62-67)"; return 1; }
     if (!size_supported(u.nx) || !(size_supported(u.ny) || u.ny == 8)) { g_create_error = "nx must be a power of two in [16, 2048], ny in [8, 2048]"; return 1; }
-    p.ny = 1; p.nz = u.ny; p.Ly = 1.0; p.Lz = u.Ly; p.afz = u.afy; p.if_corotating = 0;
+    p.ny = 1; p.nz = u.ny; p.Ly = 1.0; p.Lz = u.Ly; p.afz = u.afy;
     if (u.dealias_option < 0 || u.dealias_option > 3) { g_create_error = "dealias_option must be 0..3 in the 2D tree"; return 1; }
   } else {
     if (!size_supported(p.nx) || !size_supported(p.ny) || !(size_supported(p.nz) || p.nz == 8)) {
@@ -1360,9 +1384,13 @@ int laps_create(const laps_params* params, laps_handle* out) {
       s->pr_ncol = (int)cmap.size();
       alloc((void**)&s->d_kymax_x, s->nxh * sizeof(int));
       alloc((void**)&s->d_colmap, std::max<size_t>(1, cmap.size()) * sizeof(int));
+      alloc((void**)&s->d_colkx, std::max<size_t>(1, cmap.size()) * sizeof(int));
       if (!ok) return fail("device allocation failed (pruning tables)");
+      std::vector<int> ckx(cmap.size());
+      for (size_t i = 0; i < cmap.size(); ++i) ckx[i] = cmap[i] / s->nyl;
       if (cudaMemcpy(s->d_kymax_x, kym.data(), s->nxh * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
-          (!cmap.empty() && cudaMemcpy(s->d_colmap, cmap.data(), cmap.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess))
+          (!cmap.empty() && (cudaMemcpy(s->d_colmap, cmap.data(), cmap.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+                             cudaMemcpy(s->d_colkx, ckx.data(), ckx.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)))
         return fail("pruning table upload failed");
     }
     {  // surviving (kx, ky) columns of all ranks
@@ -1419,6 +1447,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
   // single rank: the exchange tables point at this rank's own buffers
   std::memset(&s->tabW2, 0, sizeof(PeerTable)); std::memset(&s->tabV1, 0, sizeof(PeerTable));
   s->tabW2.nparts = s->tabV1.nparts = s->P;
+  { int sh = 0; while ((1 << sh) < s->P) ++sh; s->tabW2.shift = s->tabV1.shift = sh; }
   s->tabW2.quot = s->ny / s->P; s->tabV1.quot = s->nz / s->P;
   for (int q = 0; q < s->P; ++q) {
     s->tabW2.off[q] = s->yoffs[q]; s->tabW2.len[q] = s->ylens[q];
@@ -1457,7 +1486,7 @@ int laps_destroy(laps_handle s) {
   cudaFree(s->xblk);
   cudaFree(s->uu); cudaFree(s->J); cudaFree(s->G); cudaFree(s->ext); cudaFree(s->bufX); cudaFree(s->bufY); cudaFree(s->bufZ);
   cudaFree(s->uA); cudaFree(s->uB); cudaFree(s->rk); cudaFree(s->tw_x); cudaFree(s->tw_y); cudaFree(s->tw_z);
-  cudaFree(s->d_tab); cudaFree(s->d_partial); cudaFree(s->d_scal); cudaFree(s->d_kymax_x); cudaFree(s->d_colmap);
+  cudaFree(s->d_tab); cudaFree(s->d_partial); cudaFree(s->d_scal); cudaFree(s->d_kymax_x); cudaFree(s->d_colmap); cudaFree(s->d_colkx);
   if (s->h_scal) cudaFreeHost(s->h_scal);
   if (s->h_abort) cudaFreeHost(s->h_abort);
   for (auto& pe : s->prof) { cudaEventDestroy(pe.e0); cudaEventDestroy(pe.e1); }
@@ -1777,6 +1806,7 @@ static int max_div_fourier(laps_handle s, int v0, double* out) {
   d.radius0 = s->p.radius0; d.radius = s->radius; d.cosa = s->cosa; d.sina = s->sina;
   d.corot_k = (s->p.if_AEB && s->p.if_corotating) ? 1 : 0;
   d.mode2d = s->two_d; d.z_radial = s->two_d && s->p.if_AEB && s->p.if_z_radial;
+  d.kzr = s->kzr;
   d.partial = s->d_partial;
   {
     LaunchScope ls(s, "divb", 3 * 16.0 * (double)s->csz);

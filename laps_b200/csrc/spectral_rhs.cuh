@@ -60,7 +60,6 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
   const cplx tw0 = FF::template tw_stage<0>(P.tw, u);
   const cplx tw1 = G::NSTAGE >= 3 ? FF::template tw_stage<1>(P.tw, u) : mk(1.0, 0.0);
   const cplx tw2 = G::NSTAGE >= 4 ? FF::template tw_stage<2>(P.tw, u) : mk(1.0, 0.0);
-  const int nitems = ntasks * ngroups;  // task fastest: CTAs that share flux lines run together (L2)
 
   // slot e of this thread <- element idx(e) of a line (8 copies, one commit group; an absent line
   // still commits an (empty) group so that the group count is the same in every thread)
@@ -81,72 +80,39 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
     cp_async_commit();
   };
 
-  // compact column index -> memory column (see ZParams); -1 past the end
-  auto column_of = [&](int cc) -> int { return z_column(P, cc); };
-  int item = blockIdx.x;
-  if (item < nitems) {  // prologue: the first item's fc
-    const ZTask& K = P.task[item % ntasks];
-    const int col = column_of((item / ntasks) * CG + l);
-    land_in(S, P.W2 + (size_t)(K.fc >= 0 ? K.fc : 0) * P.fstride + (size_t)(col < 0 ? 0 : col) * N, K.fc >= 0 && col >= 0);
+  // Items = (column group, task), task fastest.  The walk over them carries (task, group) instead of dividing the item
+  // number, and the column of the NEXT item (memory column + kx: two table loads whose results are addresses) is fetched
+  // at the top of the current one, so that no item starts with a chain of dependent global loads.
+  const int st_t = (int)(gridDim.x % (unsigned)ntasks), st_g = (int)(gridDim.x / (unsigned)ntasks);
+  int task = (int)(blockIdx.x % (unsigned)ntasks), group = (int)(blockIdx.x / (unsigned)ntasks);
+  int colm = -1, kxc = 0;
+  if (group < ngroups) {  // prologue: the first item's column and its fc
+    colm = z_column_kx(P, group * CG + l, kxc);
+    const ZTask& K = P.task[task];
+    land_in(S, P.W2 + (size_t)(K.fc >= 0 ? K.fc : 0) * P.fstride + (size_t)(colm < 0 ? 0 : colm) * N, K.fc >= 0 && colm >= 0);
   }
-  for (; item < nitems; item += gridDim.x) {
-    const ZTask& K = P.task[item % ntasks];
-    const int colm = column_of((item / ntasks) * CG + l);
+  while (group < ngroups) {
+    const ZTask& K = P.task[task];
+    int ntask = task + st_t, ngroup = group + st_g;
+    if (ntask >= ntasks) { ntask -= ntasks; ++ngroup; }
+    const bool more = ngroup < ngroups;
+    int coln = -1, kxn = 0;
+    if (more) coln = z_column_kx(P, ngroup * CG + l, kxn);   // consumed after the first transform and at the end of the item
     const bool live = colm >= 0;
     const int col = live ? colm : 0;
-    const int kx = col / P.nyl;
-    const int ky = P.yoff + (col % P.nyl) * P.ystride;
+    const int kx = live ? kxc : 0;
+    const int ky = P.yoff + (col - kx * P.nyl) * P.ystride;
     const size_t coff = (size_t)col * N;
     const size_t voff = (size_t)K.v * P.fstride + coff;
     const bool hasC = K.fc >= 0;
 
     land_in(Q0, P.W2 + (size_t)(K.fa >= 0 ? K.fa : 0) * P.fstride + coff, live && K.fa >= 0);
     if constexpr (NQ == 2) land_in(Q1, P.W2 + (size_t)(K.fb >= 0 ? K.fb : 0) * P.fstride + coff, live && K.fb >= 0);
-    if (P.tune & 4) {
-      // one item ahead: pull every line of the NEXT item into L2 (no registers, no shared memory),
-      // so that its asynchronous copies run at L2 latency instead of DRAM latency
-      const int nxt = item + gridDim.x;
-      if (nxt < nitems) {
-        const ZTask& Kn = P.task[nxt % ntasks];
-        const int coln = column_of((nxt / ntasks) * CG + l);
-        if (coln >= 0) {
-          const size_t po = (size_t)coln * N + (size_t)u * (N / G::NT);
-          if (Kn.fa >= 0) prefetch_l2(P.W2 + (size_t)Kn.fa * P.fstride + po);
-          if (Kn.fb >= 0) prefetch_l2(P.W2 + (size_t)Kn.fb * P.fstride + po);
-          if (Kn.fx >= 0) prefetch_l2(P.W2 + (size_t)Kn.fx * P.fstride + po);
-          // (state lines: not the 128-byte groups that lie entirely inside the masked kz interval)
-          bool want = true;
-          if (P.kzprune) {
-            const int kxn = coln / P.nyl, kyn = P.yoff + (coln % P.nyl) * P.ystride;
-            const double dn = __dadd_rn(__ldg(P.dax + kxn), __ldg(P.day + kyn));
-            const int k0 = u * (N / G::NT);
-            want = !(z_mode_dead(P, dn, k0) && z_mode_dead(P, dn, k0 + N / G::NT - 1));
-          }
-          if (want) {
-            prefetch_l2(P.u_in + (size_t)Kn.v * P.fstride + po);
-            if (P.read_rk) prefetch_l2(P.fnl_rk + (size_t)Kn.v * P.fstride + po);
-          }
-        }
-      }
-    }
 
+    // per-column table entries: issued here, first used after the transform below
     const double kxr = __ldg(P.kxr + kx), kyr = __ldg(P.kyr + ky);
     const double ksqx = __ldg(P.ksq_x + kx), ksqy = __ldg(P.ksq_y + ky);
     const double dax = P.dealias_option ? __ldg(P.dax + kx) : 0.0, day = P.dealias_option ? __ldg(P.day + ky) : 0.0;
-    // derivative vectors (imaginary parts), mhdrhs.f90:191-204
-    double kxe = kxr, kye = __ddiv_rn(__dmul_rn(kyr, P.radius0), P.radius);
-    if (P.z_radial) kxe = __ddiv_rn(__dmul_rn(kxr, P.radius0), P.radius);
-    if (P.corot_k) {
-      kxe = __dadd_rn(__dmul_rn(kxr, P.cosa), __dmul_rn(kyr, P.sina));
-      kye = __ddiv_rn(__dmul_rn(__dadd_rn(__dmul_rn(-kxr, P.sina), __dmul_rn(kyr, P.cosa)), P.radius0), P.radius);
-    }
-
-    const double dxy = (P.dealias_option == 1 || P.dealias_option == 3) ? __dadd_rn(dax, day) : dax;
-    unsigned dead = 0;   // bit e: the mask removes mode kout(u, e) of this column
-    if (P.kzprune) {
-      LAPS_UNROLL
-      for (int e = 0; e < 8; ++e) dead |= z_mode_dead(P, dxy, FF::kout(u, e)) ? (1u << e) : 0u;
-    }
 
     cplx r[8];
     // ---------------- forward z of the (i kz) term, result kept in S ----------------
@@ -161,6 +127,40 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
       LAPS_UNROLL
       for (int e = 0; e < 8; ++e) S[e * G::NT + u] = cmul_i(r[e], cs * __ldg(P.kze + FF::kout(u, e)));
       __syncthreads();  // every last-stage read of the work line is done before it is refilled
+    }
+    // derivative vectors (imaginary parts), mhdrhs.f90:191-204
+    double kxe = kxr, kye = __ddiv_rn(__dmul_rn(kyr, P.radius0), P.radius);
+    if (P.z_radial) kxe = __ddiv_rn(__dmul_rn(kxr, P.radius0), P.radius);
+    if (P.corot_k) {
+      kxe = __dadd_rn(__dmul_rn(kxr, P.cosa), __dmul_rn(kyr, P.sina));
+      kye = __ddiv_rn(__dmul_rn(__dadd_rn(__dmul_rn(-kxr, P.sina), __dmul_rn(kyr, P.cosa)), P.radius0), P.radius);
+    }
+    const double dxy = (P.dealias_option == 1 || P.dealias_option == 3) ? __dadd_rn(dax, day) : dax;
+    unsigned dead = 0;   // bit e: the mask removes mode kout(u, e) of this column
+    if (P.kzprune) {
+      LAPS_UNROLL
+      for (int e = 0; e < 8; ++e) dead |= z_mode_dead(P, dxy, FF::kout(u, e)) ? (1u << e) : 0u;
+    }
+    if ((P.tune & 4) && more && coln >= 0) {
+      // one item ahead: pull every line of the NEXT item into L2 (no registers, no shared memory),
+      // so that its asynchronous copies run at L2 latency instead of DRAM latency
+      const ZTask& Kn = P.task[ntask];
+      const size_t po = (size_t)coln * N + (size_t)u * (N / G::NT);
+      if (Kn.fa >= 0) prefetch_l2(P.W2 + (size_t)Kn.fa * P.fstride + po);
+      if (Kn.fb >= 0) prefetch_l2(P.W2 + (size_t)Kn.fb * P.fstride + po);
+      if (Kn.fx >= 0) prefetch_l2(P.W2 + (size_t)Kn.fx * P.fstride + po);
+      // (state lines: not the 128-byte groups that lie entirely inside the masked kz interval)
+      bool want = true;
+      if (P.kzprune) {
+        const int kyn = P.yoff + (coln - kxn * P.nyl) * P.ystride;
+        const double dn = __dadd_rn(__ldg(P.dax + kxn), __ldg(P.day + kyn));
+        const int k0 = u * (N / G::NT);
+        want = !(z_mode_dead(P, dn, k0) && z_mode_dead(P, dn, k0 + N / G::NT - 1));
+      }
+      if (want) {
+        prefetch_l2(P.u_in + (size_t)Kn.v * P.fstride + po);
+        if (P.read_rk) prefetch_l2(P.fnl_rk + (size_t)Kn.v * P.fstride + po);
+      }
     }
     // ---------------- G = (i kx ca) fa + (i ky cb) fb + cx fx ----------------
     if constexpr (NQ == 2) cp_async_wait<1>();   // fa
@@ -279,10 +279,8 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
       r[e] = un;
     }
     {  // next item's fc -> S (this thread has finished with its S slots)
-      const int nxt = item + gridDim.x;
-      if (nxt < nitems) {
-        const ZTask& Kn = P.task[nxt % ntasks];
-        const int coln = column_of((nxt / ntasks) * CG + l);
+      if (more) {
+        const ZTask& Kn = P.task[ntask];
         land_in(S, P.W2 + (size_t)(Kn.fc >= 0 ? Kn.fc : 0) * P.fstride + (size_t)(coln < 0 ? 0 : coln) * N, Kn.fc >= 0 && coln >= 0);
       } else {
         cp_async_commit();
@@ -311,6 +309,7 @@ k_rhs_z(const ZParams P, const int ntasks, const int ngroups) {
       }
     }
     __syncthreads();  // W is refilled by the next item's first stage
+    task = ntask; group = ngroup; colm = coln; kxc = kxn;
   }
   cp_async_wait<0>();
 }

@@ -83,6 +83,7 @@ struct ZParams {
   // With the spherical mask (option 1) the surviving columns are those inside a circle in (kx, ky): colmap[c] is
   // then the memory column (kx * nyl + kyl) of compact index c and the formula above is not used.
   const int* colmap;
+  const int* colkx;      // kx of colmap[c] (saves the division by nyl where a kernel walks many columns)
   // kzprune: modes the mask removes are neither loaded nor stored (they are zero in the state arrays, and
   // whatever fnl_rk holds there is never used): mask(kz) = dax + day + daz[kz] >= da_thresh (option 1) or a
   // non-zero per-axis flag (option 3).
@@ -128,6 +129,16 @@ LAPS_D int z_column(const ZParams& P, int cc) {
   if (P.colmap) return __ldg(P.colmap + cc);
   const int kr = cc % P.nkyl;
   return (cc / P.nkyl) * P.nyl + (kr < P.nA ? P.a0 + kr : P.b0 + kr - P.nA);
+}
+
+// the same, also returning kx of the column (kyl = column - kx * nyl)
+LAPS_D int z_column_kx(const ZParams& P, int cc, int& kx) {
+  kx = 0;
+  if (cc >= P.ncolc) return -1;
+  if (P.colmap) { kx = __ldg(P.colkx + cc); return __ldg(P.colmap + cc); }
+  const int q = cc / P.nkyl, kr = cc - q * P.nkyl;
+  kx = q;
+  return q * P.nyl + (kr < P.nA ? P.a0 + kr : P.b0 + kr - P.nA);
 }
 
 // true where the dealiasing mask removes mode (kx, ky, kz): dxy = dax + day of the column (options 1, 3)

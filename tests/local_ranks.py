@@ -11,12 +11,18 @@ kernels of the rank it is waiting for — a deadlock that one-GPU-per-rank runs 
 therefore runs this module in a child process with CUDA_DEVICE_MAX_CONNECTIONS=32 (it must be set before the CUDA
 context exists):   python tests/local_ranks.py '<json>'."""
 import os
+import sys
 import threading
 
 import numpy as np
 
-import parity_common as pc
-from laps_b200 import Solver
+_HERE = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.dirname(_HERE), _HERE):      # run as a script by tests/test_gpu_multirank.py
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import parity_common as pc  # noqa: E402
+from laps_b200 import Solver  # noqa: E402
 
 
 class _Env:

@@ -31,13 +31,14 @@ def make_case(nx, ny, nz, hall=True, aeb=True, corot=False, dealias=1, visc=True
 
 
 def make_case_2d(nx, ny, hall=True, aeb=True, z_radial=False, dealias=1, visc=True, resis=True, explicit=False,
-                 conserve_bg=False, limit_dt=False, seed=3):
+                 conserve_bg=False, limit_dt=False, seed=3, corot=False):
     """2D tree (src_compressible/2D): oracle parameters + smooth random primitive data on (nx, ny, 1)."""
     p = lo.Params(nx=nx, ny=ny, nz=1, Lx=24.0, Ly=12.0, Lz=1.0, adiabatic_index=1.666667,
                   if_resis=resis, resistivity=1e-4 if not explicit else 1e-3, if_resis_exp=explicit,
                   if_visc=visc, viscosity=1e-4 if not explicit else 1e-3, if_visc_exp=explicit,
                   if_conserve_background=conserve_bg, cfl=0.5, dealias_option=dealias,
                   if_AEB=aeb, radius0=30.0, Ur0=1.167 if aeb else 0.0, if_z_radial=z_radial,
+                  if_corotating=corot, corotating_angle=0.4 if corot else 0.0,
                   if_hall=hall, ion_inertial_length=0.2 if hall else 0.0, if_limit_dt_increase=limit_dt)
     rng = np.random.default_rng(seed)
     x = 2 * np.pi * np.arange(nx) / nx

@@ -36,10 +36,14 @@ def test_one_step(emu, kw):
 
 
 @pytest.mark.parametrize("kw", [dict(hall=True, aeb=True, dealias=1), dict(hall=True, aeb=True, z_radial=True, dealias=3),
-                                dict(hall=False, aeb=False, dealias=2, explicit=True, conserve_bg=True, limit_dt=True)])
+                                dict(hall=False, aeb=False, dealias=2, explicit=True, conserve_bg=True, limit_dt=True),
+                                # if_corotating (2D/mhdrhs.f90:282-288): both components of the rotated wave vector vary along the line
+                                dict(hall=True, aeb=True, corot=True, dealias=1),
+                                dict(hall=True, aeb=True, corot=True, dealias=2, explicit=True, conserve_bg=True),
+                                dict(hall=False, aeb=True, corot=True, dealias=0)])
 def test_one_step_2d_tree(emu, kw):
     p, prim = pc.make_case_2d(32, 16, **kw)
-    o, g = pc.run_both(p, prim, 2, lib_path=emu)
+    o, g = pc.run_both(p, prim, 2, lib_path=emu, t0=2.0 if kw.get("corot") else 0.0)
     pc.check_state(o, g, 1e-11)
     pc.check_diagnostics(o, g, 1e-9)
     g.close()

@@ -82,11 +82,14 @@ def test_mask_pruning_is_bit_exact():
 
 @pytest.mark.parametrize("name,kw", [("hall_aeb", dict(hall=True, aeb=True, dealias=1)),
                                      ("z_radial_square", dict(hall=True, aeb=True, z_radial=True, dealias=3)),
-                                     ("filter_explicit", dict(hall=False, aeb=False, dealias=2, explicit=True, conserve_bg=True, limit_dt=True))])
+                                     ("filter_explicit", dict(hall=False, aeb=False, dealias=2, explicit=True, conserve_bg=True, limit_dt=True)),
+                                     ("corotating", dict(hall=True, aeb=True, corot=True, dealias=1)),
+                                     ("corotating_filter_explicit", dict(hall=True, aeb=True, corot=True, dealias=2, explicit=True, conserve_bg=True)),
+                                     ("corotating_nodealias", dict(hall=False, aeb=True, corot=True, dealias=0))])
 def test_2d_tree_parity(name, kw):
     """BASELINE config 2 family (src_compressible/2D) at 256 x 128, two steps."""
     p, prim = pc.make_case_2d(256, 128, **kw)
-    o, g = pc.run_both(p, prim, 2)
+    o, g = pc.run_both(p, prim, 2, t0=2.0 if kw.get("corot") else 0.0)   # (a late start: the rotated wave vectors differ from t = 0)
     pc.check_state(o, g, 1e-11)
     pc.check_diagnostics(o, g, 1e-9)
     g.close()
@@ -288,7 +291,7 @@ def test_incompressible_library_agrees_with_the_executed_reference_source(name):
     rp.check_library_incompressible(name)
 
 
-@pytest.mark.parametrize("name", ["c2d_hall_aeb_mask", "c2d_zradial_square_explicit", "c2d_external_force_filter"])
+@pytest.mark.parametrize("name", ["c2d_hall_aeb_mask", "c2d_zradial_square_explicit", "c2d_external_force_filter", "c2d_corotating_oracle_only"])
 def test_2d_library_agrees_with_the_executed_reference_source(name):
     import test_reference_source_pins as rp
     rp.check_library_2d(name)

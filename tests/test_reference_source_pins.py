@@ -212,7 +212,7 @@ def check_library_2d(name, lib_path=None, tol=1e-11):
         for v in range(8):
             assert pc.rel_l2(uu[v], g["uu"][v]) < tol, (v, pc.rel_l2(uu[v], g["uu"][v]))
             assert pc.rel_l2(uf[v], g["uu_fourier"][v]) < tol, v
-        assert abs(s.calc_max_divB() - float(g["max_divb"])) <= 1e-7 * float(g["max_divb"])
+        assert abs(s.calc_max_divB() - float(g["max_divb"])) <= 1e-9 * float(g["max_divb"]) + 1e-13
         assert s.checkNan() is bool(int(g["isnanall"]))
 
 
@@ -304,7 +304,7 @@ def test_incompressible_library_on_the_emulator_agrees_with_the_executed_referen
     check_library_incompressible(name, lib_path=emu)
 
 
-@pytest.mark.parametrize("name", CASES_2D)
+@pytest.mark.parametrize("name", CASES_2D + ["c2d_corotating_oracle_only"])
 def test_2d_library_on_the_emulator_agrees_with_the_executed_reference_source(emu, name):
     check_library_2d(name, lib_path=emu)
 
@@ -450,12 +450,17 @@ def test_library_40_steps_on_the_emulator_against_the_executed_reference_source(
     check_library_100_steps(emu, nsteps=40)
 
 
-def test_2d_corotation_is_refused_by_the_library(emu):
-    """The one option of the reference the library does not run; the oracle restates it and is pinned above."""
+def test_2d_corotation_where_the_reference_has_none(emu):
+    """if_corotating in the 2D tree runs (fixture c2d_corotating_oracle_only above; the name dates from the round in which only
+    the oracle had it); what stays refused: together with if_z_radial (the reference stops, 2D/mhd.f90:62-67) and in the
+    incompressible 2D tree."""
     from laps_b200 import Solver, capi
     g, p = load_case("c2d_corotating_oracle_only")
-    with pytest.raises(capi.LapsError, match="if_corotating"):
-        Solver(emu, **pc.solver_kwargs(p))
+    kw = pc.solver_kwargs(p)
+    with pytest.raises(capi.LapsError, match="exclude each other"):
+        Solver(emu, **dict(kw, if_z_radial=1))
+    with pytest.raises(capi.LapsError, match="incompressible 2D"):
+        Solver(emu, **dict(kw, incompressible=1, rho0=1.0))
 
 
 # ------------------------------------------------------------------------------------------------------------------
