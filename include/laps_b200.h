@@ -170,6 +170,14 @@ int laps_get_state(laps_handle h, double* uu_local, double* uu_prim_local);
 /* The 8-field array output_uu writes (mhdoutput.f90:95-123): primitive != 0 -> rho, u, B, p
  * (output_primitive = .true.), else the conserved uu.  Same layout as uu_local. */
 int laps_get_output(laps_handle h, double* out_local, int32_t primitive);
+/* The same without blocking the run: the output array is packed into a device snapshot, stream-ordered behind the steps
+ * enqueued so far, and copied to out_local on a copy stream while the steps that follow run (a dump then costs the run
+ * one pointwise sweep instead of a PCIe transfer: output_uu of the reference blocks every rank in MPI-IO,
+ * mhdoutput.f90:95-131).  out_local must stay valid — pinned, for the copy to overlap — until laps_output_wait returns;
+ * one request in flight per handle (a second one waits for the first on the device).  The snapshot buffer (8 real
+ * fields) is allocated at the first request. */
+int laps_get_output_async(laps_handle h, double* out_local, int32_t primitive);
+int laps_output_wait(laps_handle h);
 /* Spectral state uu_fourier as complex128 pairs in the library's internal layout
  * [ivar][kx][ky_local][kz] (kz fastest) — for parity tests. */
 int laps_get_spectral(laps_handle h, double* uu_fourier_local);

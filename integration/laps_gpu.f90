@@ -155,6 +155,12 @@ module laps_gpu
     integer(c_int) function laps_set_profiling(h, on) bind(C, name='laps_set_profiling')
       import; type(c_ptr), value :: h; integer(c_int32_t), value :: on
     end function
+    integer(c_int) function laps_get_output_async(h, out_local, primitive) bind(C, name='laps_get_output_async')
+      import; type(c_ptr), value :: h; real(c_double), intent(out) :: out_local(*); integer(c_int32_t), value :: primitive
+    end function
+    integer(c_int) function laps_output_wait(h) bind(C, name='laps_output_wait')
+      import; type(c_ptr), value :: h
+    end function
     integer(c_int) function laps_get_profile_bytes(h, bytes, cap, count) bind(C, name='laps_get_profile_bytes')
       import; type(c_ptr), value :: h; real(c_double), intent(out) :: bytes(*); integer(c_int32_t), value :: cap
       integer(c_int32_t), intent(out) :: count

@@ -64,6 +64,7 @@ SYMBOLS = [
     "laps_last_step_ms", "laps_set_profiling", "laps_get_profile", "laps_get_pruning",
     "laps_max_divv", "laps_max_div_real", "laps_get_rho0", "laps_get_field_counts", "laps_get_output", "laps_get_pruning_counts", "laps_set_primitive_modes",
     "laps_check_nan", "laps_set_external_force", "laps_get_profile_bytes", "laps_get_footprint", "laps_set_tune",
+    "laps_get_output_async", "laps_output_wait",
 ]
 
 
@@ -127,6 +128,8 @@ def load(path: Optional[str] = None) -> C.CDLL:
     lib.laps_get_profile_bytes.argtypes = [H, dp, C.c_int32, C.POINTER(C.c_int32)]
     lib.laps_get_footprint.argtypes = [H, C.POINTER(C.c_int64)]
     lib.laps_set_tune.argtypes = [H, C.c_char_p, C.c_int32]
+    lib.laps_get_output_async.argtypes = [H, dp, C.c_int32]
+    lib.laps_output_wait.argtypes = [H]
     for name in SYMBOLS:
         if name != "laps_last_error":
             getattr(lib, name).restype = C.c_int

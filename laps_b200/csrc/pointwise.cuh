@@ -250,6 +250,21 @@ __global__ void __launch_bounds__(256) k_cons_to_prim(const double* uu, double* 
   }
 }
 
+// The 8-field array output_uu writes (mhdoutput.f90:95-123) into a snapshot buffer: primitive != 0 -> rho, u, B, p, else uu
+__global__ void __launch_bounds__(256) k_output_pack(const double* uu, double* out, size_t n, double gamma, int incomp, int primitive) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double rho = uu[i], mx = uu[n + i], my = uu[2 * n + i], mz = uu[3 * n + i];
+    const double bx = uu[4 * n + i], by = uu[5 * n + i], bz = uu[6 * n + i], en = uu[7 * n + i];
+    out[i] = rho; out[4 * n + i] = bx; out[5 * n + i] = by; out[6 * n + i] = bz;
+    if (primitive) {
+      const Prim q = prim_of(rho, mx, my, mz, bx, by, bz, en, gamma - 1.0);
+      out[n + i] = q.ux; out[2 * n + i] = q.uy; out[3 * n + i] = q.uz; out[7 * n + i] = incomp ? en : q.p;
+    } else {
+      out[n + i] = mx; out[2 * n + i] = my; out[3 * n + i] = mz; out[7 * n + i] = en;
+    }
+  }
+}
+
 // mhd.f90:352-416.  partial[d][b] = max over the block's points of the signal speed along d.
 // The reference takes min over points of dx/cmax_x, dy/cmax_y*(R/R0), dz/cmax_z*(R/R0); a correctly
 // rounded division (and the product with R/R0) is monotonic, so min_i fl(dx/c_i) == fl(dx/max_i c_i)

@@ -167,6 +167,11 @@ struct laps_solver {
   cudaStream_t cs = nullptr;
   int cch = 0;
   int cap_warps = 0;                 // > 0: the exchange-side launchers hold their grids to this many warps per SM (grid-stride loops)
+  // asynchronous output (laps_get_output_async): device snapshot of the output array + a copy stream
+  cudaStream_t ostream = nullptr;
+  double* snap = nullptr;            // [8][npts], allocated at the first request
+  cudaEvent_t ev_snap = nullptr, ev_out = nullptr;
+  bool out_pending = false;
   cudaEvent_t ev_link[16] = {nullptr};
   int ev_next = 0;
   int tune_tly = 0;                  // LAPS_TUNE_TLY=4: half-height tiles in the y passes
@@ -1479,6 +1484,7 @@ int laps_destroy(laps_handle s) {
   if (s->stream) cudaStreamSynchronize(s->stream);   // bounded: the inter-rank waits time out (exchange.cuh)
 #ifndef LAPS_EMU_BUILD
   if (s->xstream) cudaStreamSynchronize(s->xstream);
+  if (s->ostream) cudaStreamSynchronize(s->ostream);
 #endif
   for (int q = 0; q < LAPS_MAX_RANKS; ++q)
     for (int j = 0; j < 3; ++j)
@@ -1493,8 +1499,12 @@ int laps_destroy(laps_handle s) {
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->ev_scal) cudaEventDestroy(s->ev_scal);
+  cudaFree(s->snap);
+  if (s->ev_snap) cudaEventDestroy(s->ev_snap);
+  if (s->ev_out) cudaEventDestroy(s->ev_out);
   if (s->stream) cudaStreamDestroy(s->stream);
 #ifndef LAPS_EMU_BUILD
+  if (s->ostream) cudaStreamDestroy(s->ostream);
   if (s->xstream) cudaStreamDestroy(s->xstream);
   for (int i = 0; i < 16; ++i) if (s->ev_link[i]) cudaEventDestroy(s->ev_link[i]);
 #endif
@@ -1979,6 +1989,43 @@ static int get_output_body(laps_handle s, double* out_local, int32_t primitive) 
   return check_abort(s);
 }
 
+// laps_get_output without the wait: the output array is packed into a device snapshot (stream-ordered behind the steps
+// enqueued so far, 2 x 8R of HBM traffic) and leaves over PCIe on a copy stream while later steps run on the main one.
+static int get_output_async_body(laps_handle s, double* out_local, int32_t primitive) {
+  if (!out_local) return 1;
+  LAPS_TRY(require_state(s));
+  const size_t bytes = 8 * s->npts * sizeof(double);
+  if (!s->snap) {
+    LAPS_CK(s, cudaMalloc((void**)&s->snap, bytes));
+    s->dev_bytes += bytes;
+#ifndef LAPS_EMU_BUILD
+    LAPS_CK(s, cudaStreamCreateWithFlags(&s->ostream, cudaStreamNonBlocking));
+#endif
+    LAPS_CK(s, cudaEventCreateWithFlags(&s->ev_snap, cudaEventDisableTiming));
+    LAPS_CK(s, cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming));
+  }
+  if (s->out_pending) LAPS_CK(s, cudaStreamWaitEvent(s->stream, s->ev_out, 0));   // the previous copy still reads the snapshot
+  {
+    LaunchScope ls(s, "output_pack", 16 * bytes_real(s));
+    LAPS_LAUNCH(k_output_pack, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, (const double*)s->uu, s->snap, s->npts,
+                s->p.adiabatic_index, s->incomp ? 1 : 0, primitive ? 1 : 0);
+    LAPS_TRY(check_launch(s, "k_output_pack"));
+  }
+  LAPS_CK(s, cudaEventRecord(s->ev_snap, s->stream));
+  LAPS_CK(s, cudaStreamWaitEvent(s->ostream, s->ev_snap, 0));
+  LAPS_CK(s, cudaMemcpyAsync(out_local, s->snap, bytes, cudaMemcpyDeviceToHost, s->ostream));
+  LAPS_CK(s, cudaEventRecord(s->ev_out, s->ostream));
+  s->out_pending = true;
+  return 0;
+}
+
+static int output_wait_body(laps_handle s) {
+  if (!s->out_pending) return 0;
+  LAPS_CK(s, cudaEventSynchronize(s->ev_out));
+  s->out_pending = false;
+  return check_abort(s);
+}
+
 static int get_spectral_body(laps_handle s, double* out) {
   if (!s || !out) return 1;
   LAPS_TRY(require_state(s));
@@ -2294,6 +2341,18 @@ int laps_get_output(laps_handle s, double* out_local, int32_t primitive) {
   if (!s) return 1;
   LAPS_ENTER(s);
   return get_output_body(s, out_local, primitive);
+}
+
+int laps_get_output_async(laps_handle s, double* out_local, int32_t primitive) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  return get_output_async_body(s, out_local, primitive);
+}
+
+int laps_output_wait(laps_handle s) {
+  if (!s) return 1;
+  LAPS_ENTER(s);
+  return output_wait_body(s);
 }
 
 int laps_get_spectral(laps_handle s, double* out) {

@@ -209,6 +209,16 @@ class Solver:
         self._ck(self._lib.laps_get_output(self._h, capi._dptr(a), 1 if primitive else 0))
         return a
 
+    def get_output_async(self, out: np.ndarray, primitive=True):
+        """laps_get_output_async: the dump leaves on a copy stream while the following steps run; ``out`` (pinned, to
+        overlap) must stay alive until ``output_wait`` returns."""
+        assert out.shape == (8,) + self.real_shape and out.dtype == np.float64 and out.flags.c_contiguous
+        self._ck(self._lib.laps_get_output_async(self._h, capi._dptr(out), 1 if primitive else 0))
+        return out
+
+    def output_wait(self):
+        self._ck(self._lib.laps_output_wait(self._h))
+
     def uu_fourier(self) -> np.ndarray:
         """Spectral state in the reference index order [v, kz, ky_local, kx]."""
         raw = np.empty((8, self.nxh, self.nyl, self.nz), dtype=np.complex128)

@@ -405,3 +405,25 @@ def check_rhs_kernel_variants(lib_path=None, shape=(32, 32, 32), nsteps=2, exact
             assert np.array_equal(uu, states[0][0]) and np.array_equal(uf, states[0][1])
         else:
             assert rel_l2(uu, states[0][0]) < 1e-13 and rel_l2(uf, states[0][1]) < 1e-13
+
+
+def check_async_output(lib_path=None, shape=(32, 32, 32)):
+    """laps_get_output_async / laps_output_wait: the dump is the state at the request, whatever runs afterwards; a second
+    request before the wait is served after the first (one snapshot buffer)."""
+    p, prim = make_case(*shape, hall=True, aeb=True, dealias=1)
+    with Solver(lib_path, **solver_kwargs(p)) as g:
+        g.set_primitive(prim)
+        g.vardt()
+        g.step()
+        want1 = g.get_output(True)
+        a = np.empty_like(want1)
+        g.get_output_async(a, True)
+        g.step()
+        g.step()
+        want2 = g.get_output(False)
+        b = np.empty_like(want2)
+        g.get_output_async(b, False)      # first request still pending on the host side
+        g.step()
+        g.output_wait()
+        assert np.array_equal(a, want1) and np.array_equal(b, want2)
+        g.output_wait()                   # nothing pending: returns at once

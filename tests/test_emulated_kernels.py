@@ -220,3 +220,7 @@ def test_cfl_screen_is_exact(emu):
 def test_rhs_kernel_variants(emu):
     pc.check_rhs_kernel_variants(emu, shape=(16, 16, 32), nsteps=2, exact=True, hall=True, aeb=True, dealias=1)
     pc.check_rhs_kernel_variants(emu, shape=(16, 16, 16), nsteps=1, exact=True, hall=True, aeb=True, corot=True, dealias=2, explicit=True)
+
+
+def test_async_output(emu):
+    pc.check_async_output(emu, shape=(16, 16, 16))

@@ -333,3 +333,7 @@ def test_rhs_kernel_variants():
     pc.check_rhs_kernel_variants(shape=(64, 64, 128), nsteps=2, hall=True, aeb=True, dealias=1)
     pc.check_rhs_kernel_variants(shape=(32, 32, 64), nsteps=2, hall=True, aeb=True, corot=True, dealias=2, explicit=True)
     pc.check_rhs_kernel_variants(shape=(64, 32, 32), nsteps=2, hall=False, aeb=False, dealias=0)
+
+
+def test_async_output():
+    pc.check_async_output(shape=(64, 64, 64))
