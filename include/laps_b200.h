@@ -108,7 +108,8 @@ int laps_import_peer_blobs(laps_handle h, const void* blobs /* nranks * LAPS_PEE
 /* Single-process multi-GPU: wire the handles of all ranks created in this process to each other
  * (peer access instead of IPC).  Each handle must then be driven by its own host thread (the collectives of the
  * ranks wait for each other); the handles may also share a device (tests/test_gpu_multirank.py runs 2-8 ranks on
- * one GPU this way). */
+ * one GPU this way — which needs CUDA_MODULE_LOADING=EAGER and one hardware queue per stream,
+ * CUDA_DEVICE_MAX_CONNECTIONS=32, see tests/local_ranks.py; with one GPU per handle neither matters). */
 int laps_connect_local(laps_handle* handles, int32_t nranks);
 
 /* initial_calc_conserve_variable + transform_uu_real_to_fourier (mhd.f90:121-122):

@@ -9,7 +9,8 @@ Ranks that SHARE a device need every stream of every handle in a hardware work q
 queues (CUDA_DEVICE_MAX_CONNECTIONS) the 2 x N streams alias, and a flag kernel that spins in one stream then holds up the
 kernels of the rank it is waiting for — a deadlock that one-GPU-per-rank runs cannot have.  tests/test_gpu_multirank.py
 therefore runs this module in a child process with CUDA_DEVICE_MAX_CONNECTIONS=32 (it must be set before the CUDA
-context exists):   python tests/local_ranks.py '<json>'."""
+context exists) and CUDA_MODULE_LOADING=EAGER (a lazily loaded kernel synchronises the device at its first launch — behind the
+flag kernel of the rank that waits for that very launch):   python tests/local_ranks.py '<json>'."""
 import os
 import sys
 import threading

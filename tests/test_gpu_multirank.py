@@ -52,7 +52,9 @@ def _local(cfg, timeout=900):
     import subprocess
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
-    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", LAPS_ORACLE_WORKERS="4")
+    # EAGER module loading: the first launch of a kernel otherwise loads it lazily, which synchronises the device — behind the
+    # flag kernel of the rank that is waiting for exactly this launch when the ranks share one GPU
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", CUDA_MODULE_LOADING="EAGER", LAPS_ORACLE_WORKERS="4")
     out = subprocess.run([sys.executable, os.path.join(here, "local_ranks.py"), json.dumps(cfg)], env=env, stdout=subprocess.PIPE,
                          stderr=subprocess.STDOUT, text=True, timeout=timeout)
     assert out.returncode == 0 and "local ranks ok" in out.stdout, out.stdout[-4000:]

@@ -11,6 +11,7 @@ for stage in "$@"; do
   echo "== stage $stage ($(date +%T))"
   case $stage in
     tests)        ( time timeout 1500 python -m pytest tests -m gpu -q --durations=10 --maxfail=8 ) > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log; tail -15 $OUT/pytest_gpu.log ;;
+    tests_new)    ( time timeout 900 python -m pytest tests/test_gpu_driver.py tests/test_gpu_parity.py -m gpu -q -k "driver or async or rhs_kernel or cfl_screen or two_stream or 2d_tree_parity or 2d_library" ) > $OUT/pytest_new.log 2>&1; tail -5 $OUT/pytest_new.log ;;
     tests_multi)  ( time timeout 1200 python -m pytest tests/test_gpu_multirank.py -m gpu -q --durations=10 ) > $OUT/pytest_multirank_${NG}gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_multirank_${NG}gpu.log; tail -8 $OUT/pytest_multirank_${NG}gpu.log ;;
     bench)        timeout 900 python bench.py --steps 10 --warmup 3 > $OUT/bench_512_1gpu.json 2> $OUT/bench_512_1gpu.err; tail -c 600 $OUT/bench_512_1gpu.err ;;
     bench_ref)    timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err; cat $OUT/bench_reference.json ;;
