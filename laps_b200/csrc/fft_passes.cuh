@@ -129,26 +129,29 @@ k_fwd_x(const double* __restrict__ in, size_t in_fstride, cplx* __restrict__ W1,
 template <int N, int TL>
 __global__ void __launch_bounds__(Tile<N, TL>::NTHREADS, Tile<N, TL>::MINB)
 k_fwd_y(const cplx* __restrict__ W1, PeerTable W2, int nzl, int nz, int zoff,
-        const cplx* __restrict__ tw, double scale, int nxh, int kymax_all, const int* __restrict__ kymax_x, int ntiles) {
+        const cplx* __restrict__ tw, double scale, int nxh, int kymax_all, const int* __restrict__ kymax_x, int ntiles,
+        int zbase, int zcount) {
   typedef Geom<N> G;
   typedef Fft<N, -1> F;
   typedef Tile<N, TL> T;
   LAPS_DYN_SMEM(cplx, sm);
   const int tid = threadIdx.x;
-  const int ztiles = (nzl + TL - 1) / TL;
+  // the launch covers the z planes [zbase, zbase + zcount) of the slab (the whole slab, or one z chunk of the two-stream schedule)
+  const int ztiles = (zcount + TL - 1) / TL;
+  const int zend = zbase + zcount;
   const int f = blockIdx.y;
   // one tile per CTA, or — when the launch is held to a few CTAs per SM so that an HBM-bound pass of another stream
   // can share the SMs while this one waits on NVLink — a grid-stride loop over the tiles
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int kx = tile / ztiles;
-    const int z0 = (tile % ztiles) * TL;
+    const int z0 = zbase + (tile % ztiles) * TL;
     // rows kymax < ky < N - kymax of this kx column are removed by the dealiasing mask for every kz (per-kx
     // table: the mask is a sphere, dealiasing.f90:91-94)
     const int kymax = kymax_x ? __ldg(kymax_x + kx) : kymax_all;
     {
       const int l = tid / G::NT, u = tid % G::NT;  // mapping A: coalesced along the line
       cplx r[8];
-      if (z0 + l < nzl) {
+      if (z0 + l < zend) {
         const cplx* src = W1 + (((size_t)f * nxh + kx) * nzl + z0 + l) * N;
         LAPS_UNROLL
         for (int e = 0; e < 8; ++e) r[e] = src[u + e * G::NT];
@@ -161,7 +164,7 @@ k_fwd_y(const cplx* __restrict__ W1, PeerTable W2, int nzl, int nz, int zoff,
     const int l = tid % TL, u = tid / TL;  // mapping B: TL lines side by side
     cplx r[8];
     F::finish(r, u, sm + l * T::PITCH, tw);
-    if (z0 + l < nzl) {
+    if (z0 + l < zend) {
       LAPS_UNROLL
       for (int e = 0; e < 8; ++e) {
         const int ky = F::kout(u, e);

@@ -50,7 +50,8 @@ struct CflParams {
   double floor_x, floor_y; // resistivity/dx, resistivity/dy of the 2D tree's explicit-resistivity limit (2D/mhd.f90:361-364), else 0
   int hall;
   int screen;       // 1: evaluate the FP64 signal speeds only where a cheap FP32 bound says they can raise a maximum (bit-identical)
-  double* partial;  // [gridDim.x]
+  double* partial;  // [3][row_stride]: CTA b of this launch writes entry boff + b of every row
+  int row_stride, boff;   // (the sweep may be split into several launches over z chunks: together they fill [0, row_stride))
 };
 
 // Signal speeds of one point along x, y, z, folded into best[] (mhd.f90:352-416; see k_cfl for why the
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(256, 3) k_flux(const FluxParams P) {
     LAPS_UNROLL
     for (int d = 0; d < 3; ++d) {
       const double r = block_reduce(best[d], OpMax(), scratch);
-      if (threadIdx.x == 0) P.cfl.partial[(size_t)d * gridDim.x + blockIdx.x] = r;
+      if (threadIdx.x == 0) P.cfl.partial[(size_t)d * P.cfl.row_stride + P.cfl.boff + blockIdx.x] = r;
     }
   }
 }
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(256) k_cfl(const CflParams P) {
   LAPS_UNROLL
   for (int d = 0; d < 3; ++d) {
     const double r = block_reduce(best[d], OpMax(), scratch);
-    if (threadIdx.x == 0) P.partial[(size_t)d * gridDim.x + blockIdx.x] = r;
+    if (threadIdx.x == 0) P.partial[(size_t)d * P.row_stride + P.boff + blockIdx.x] = r;
   }
 }
 
@@ -457,7 +458,7 @@ __global__ void __launch_bounds__(256) k_cfl_incomp(const CflParams P) {
   LAPS_UNROLL
   for (int d = 0; d < 3; ++d) {
     const double r = block_reduce(best[d], OpMax(), scratch);
-    if (threadIdx.x == 0) P.partial[(size_t)d * gridDim.x + blockIdx.x] = r;
+    if (threadIdx.x == 0) P.partial[(size_t)d * P.row_stride + P.boff + blockIdx.x] = r;
   }
 }
 

@@ -44,7 +44,7 @@ constexpr double kPi = 3.141592653589793;  // mhdinit.f90:7
 constexpr int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 constexpr int cap_threads(int t, int nt) { return t * nt > 1024 ? 1024 / nt : t; }
 constexpr int tlx(int N) { return cap_threads(clampi(256 / (N / 8), 4, 8), N / 8); }   // complex lines per x-pass CTA
-constexpr int tly(int N) { return cap_threads(clampi(512 / (N / 8), 4, 8), N / 8); }   // lines per y-pass CTA
+constexpr int tly(int N) { return cap_threads(clampi(1024 / (N / 8), 4, 8), N / 8); }  // lines per y-pass CTA (8 up to 1024-point lines: 128-byte chunks on the strided side)
 constexpr int rcg(int N) { return clampi(64 / (N / 8), 1, 32); }                       // columns per CTA of the pipelined RHS z pass
 constexpr int cgz(int N) { return clampi(128 / (N / 8), 1, 32); }                      // columns per z-pass CTA
 
@@ -177,7 +177,7 @@ struct laps_solver {
   int tune_tly = 0;                  // LAPS_TUNE_TLY=4: half-height tiles in the y passes
   int tune_screen = 1;               // LAPS_TUNE_SCREEN=0: the signal speeds of vardt at every point (see cfl_may_raise)
   int tune_overlap = -1;             // LAPS_TUNE_OVERLAP: -1 = default (on from 2 ranks on), 0 = one stream, 1 = two streams
-  int ovl_y_warps = 16, ovl_z_warps = 12, ovl_chunks = 3;   // warps per SM given to the exchange-side passes; forward field chunks
+  int ovl_y_warps = 16, ovl_z_warps = 12, ovl_chunks = 4;   // warps per SM given to the exchange-side passes; z chunks of the front half
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_scal = nullptr;
   int launches = 0;
   bool profiling = false;
@@ -453,30 +453,32 @@ int do_flux_fwd_x(S* s, const FusedFluxParams& fp) {
 
 // f0: first field slot of the launch (W1 points at it; the peers' W2 bases are advanced to it here)
 template <int N, int TL>
-int do_fwd_y_tl(S* s, const cplx* W1, int nfields, bool prune, int f0) {
+int do_fwd_y_tl(S* s, const cplx* W1, int nfields, bool prune, int f0, int zbase, int zcount) {
+  if (zcount < 0) { zbase = 0; zcount = s->nzl; }
   PeerTable tabW2 = s->tabW2;
   for (int q = 0; q < s->P; ++q)
     if (tabW2.base[q]) tabW2.base[q] += (size_t)f0 * s->nxh * tabW2.len[q] * s->nz;
   char name[32]; std::snprintf(name, sizeof(name), "fwd_y%d", nfields);
   typedef Tile<N, TL> T;
   LAPS_CK(s, prepare_kernel(k_fwd_y<N, TL>, T::SMEM, T::MINB));
-  LaunchScope ls(s, name, nfields * (bytes_xcols(s, prune) + bytes_ycols(s, prune)));
-  const int ztiles = (s->nzl + TL - 1) / TL;
+  LaunchScope ls(s, name, nfields * (bytes_xcols(s, prune) + bytes_ycols(s, prune)) * ((double)zcount / s->nzl));
+  const int ztiles = (zcount + TL - 1) / TL;
   const int ntiles = ztiles * (prune ? s->nkx : s->nxh);
   int gx = ntiles;
   if (s->cap_warps > 0) gx = std::max(1, std::min(ntiles, capped_ctas(s, T::NTHREADS) / nfields));
   dim3 grid((unsigned)gx, (unsigned)nfields);
   LAPS_LAUNCH((k_fwd_y<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->cs, W1, tabW2, s->nzl, s->nz, s->zo,
-              s->tw_y, 1.0 / N, s->nxh, prune ? s->kymax : N, prune ? (const int*)s->d_kymax_x : (const int*)nullptr, ntiles);
+              s->tw_y, 1.0 / N, s->nxh, prune ? s->kymax : N, prune ? (const int*)s->d_kymax_x : (const int*)nullptr, ntiles,
+              zbase, zcount);
   return check_launch(s, "k_fwd_y");
 }
 
 template <int N>
-int do_fwd_y(S* s, const cplx* W1, int nfields, bool prune, int f0) {
+int do_fwd_y(S* s, const cplx* W1, int nfields, bool prune, int f0, int zbase, int zcount) {
   if constexpr (N >= 256 && N <= 1024 && tly(N) == 8) {   // tuning knob: half-height tiles (twice the CTAs per SM, 64-byte chunks)
-    if (s->tune_tly == 4) return do_fwd_y_tl<N, 4>(s, W1, nfields, prune, f0);
+    if (s->tune_tly == 4) return do_fwd_y_tl<N, 4>(s, W1, nfields, prune, f0, zbase, zcount);
   }
-  return do_fwd_y_tl<N, tly(N)>(s, W1, nfields, prune, f0);
+  return do_fwd_y_tl<N, tly(N)>(s, W1, nfields, prune, f0, zbase, zcount);
 }
 
 template <int N, int TL>
@@ -613,7 +615,9 @@ int do_incomp_z(S* s, const ZParams& zp) {
 int fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1, bool prune, int zl0 = 0, int planes = -1, bool scoped = true) {
   LAPS_DISPATCH(s->nx, do_fwd_x, s, in, fstride, nfields, W1, prune, zl0, planes, scoped)
 }
-int fwd_y(S* s, const cplx* W1, int nfields, bool prune, int f0 = 0) { LAPS_DISPATCH(s->ny, do_fwd_y, s, W1, nfields, prune, f0) }
+int fwd_y(S* s, const cplx* W1, int nfields, bool prune, int f0 = 0, int zbase = 0, int zcount = -1) {
+  LAPS_DISPATCH(s->ny, do_fwd_y, s, W1, nfields, prune, f0, zbase, zcount)
+}
 int flux_fwd_x(S* s, const FusedFluxParams& fp) { LAPS_DISPATCH(s->nx, do_flux_fwd_x, s, fp) }
 bool use_fused_flux(const S* s) {
   if (s->two_d || s->incomp || s->nx > 512 || (s->ny & 1)) return false;
@@ -865,6 +869,7 @@ void fill_cfl_params(S* s, CflParams& c) {
   c.floor_x = rfloor ? p.resistivity / dx : 0.0;
   c.floor_y = rfloor ? p.resistivity / dy : 0.0;
   c.hall = p.if_hall; c.partial = s->d_partial; c.screen = s->tune_screen;
+  c.row_stride = s->nblk; c.boff = 0;
 }
 
 // `to` waits for everything enqueued on `from` so far (events from a small rotating pool: a wait captures the event's
@@ -928,6 +933,52 @@ int stage_front(S* s, bool with_cfl) {
     }
     LAPS_TRY(fwd_y(s, buf_W1(s), s->nf, true));
   } else {
+  if (use_overlap(s)) {
+    // Two-stream schedule of the front half over z chunks: calc_flux and the forward x pass of chunk c on the main stream,
+    // the forward y pass of chunk c — whose stores leave over NVLink — on the exchange stream beside the calc_flux and x
+    // pass of chunk c + 1.  (A y line needs every x line of its plane, nothing of other planes.)
+    FluxParams f;
+    f.uu = s->uu; f.J = s->J; f.npts = s->npts; f.fstride = s->npts;
+    f.hall = p.if_hall; f.aeb = p.if_AEB; f.gamma = p.adiabatic_index; f.di = p.ion_inertial_length; f.tau = s->tau;
+    f.z_radial = 0;
+    for (int j = 0; j < 19; ++j) f.slot[j] = s->fslot[j];
+    int stored = 0;
+    for (int j = 0; j < 19; ++j) stored += s->fslot[j] >= 0;
+    if (with_cfl) fill_cfl_params(s, f.cfl);
+    const size_t plane = (size_t)s->nx * s->ny;
+    constexpr int kZAlign = 8;   // the y pass takes 8 planes per tile
+    int nc = std::max(1, std::min(s->ovl_chunks, (s->nzl + kZAlign - 1) / kZAlign));
+    const int cz = ((s->nzl + nc - 1) / nc + kZAlign - 1) / kZAlign * kZAlign;
+    nc = (s->nzl + cz - 1) / cz;
+    int boff = 0;
+    for (int c = 0; c < nc; ++c) {
+      const int z0 = c * cz, nzc = std::min(cz, s->nzl - z0);
+      f.in_off = (size_t)z0 * plane; f.count = (size_t)nzc * plane;
+      f.F = buf_F(s) + f.in_off;      // full-slab flux layout: F[slot][point]
+      // this launch's share of the nblk CTAs (together the launches fill every entry of the CFL partial rows)
+      const int gb = c == nc - 1 ? s->nblk - boff : std::max(1, (int)((long long)s->nblk * nzc / s->nzl));
+      {
+        LaunchScope ls(s, with_cfl ? "flux+cfl" : "flux", (8 + (p.if_hall ? 3 : 0) + stored) * bytes_real(s) * ((double)nzc / s->nzl));
+        if (with_cfl) {
+          f.cfl.boff = boff;
+          LAPS_LAUNCH(k_flux<true>, dim3((unsigned)gb), dim3(256), 0, s->stream, f);
+        } else {
+          LAPS_LAUNCH(k_flux<false>, dim3((unsigned)gb), dim3(256), 0, s->stream, f);
+        }
+        LAPS_TRY(check_launch(s, "k_flux"));
+      }
+      boff += gb;
+      LAPS_TRY(fwd_x(s, buf_F(s) + f.in_off, s->npts, s->nf, buf_W1(s), true, z0, nzc));
+      LAPS_TRY(link_streams(s, s->stream, s->xstream));
+      {
+        StreamScope sc(s, s->xstream, 1, s->P > 1 ? s->ovl_y_warps : 0);
+        LAPS_TRY(fwd_y(s, buf_W1(s), s->nf, true, 0, z0, nzc));
+      }
+    }
+    if (with_cfl) LAPS_TRY(reduce_launch(s, 3, 2, 0.0));   // the maxima travel to the host while the last y pass runs
+    LAPS_TRY(link_streams(s, s->xstream, s->stream));      // the main stream owns the buffers again (API calls are ordered on it)
+    return 0;
+  }
   {  // calc_flux (mhdrhs.f90:21-124; 2D/mhdrhs.f90:23-128)
     FluxParams f;
     f.uu = s->uu; f.J = s->J; f.F = buf_F(s); f.npts = s->npts;
@@ -950,23 +1001,7 @@ int stage_front(S* s, bool with_cfl) {
   if (s->ext_slot >= 0)   // calc_external_force_real (2D/mhdrhs.f90:129-131): the driver's field, transformed with the fluxes
     LAPS_CK(s, cudaMemcpyAsync(buf_F(s) + (size_t)s->ext_slot * s->npts, s->ext, s->npts * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
   // transform_flux_real_to_fourier (mhdrhs.f90:128-172)
-  if (!use_overlap(s)) {
-    LAPS_TRY(forward_xy(s, buf_F(s), s->npts, s->nf, true));
-  } else {
-    // x pass of chunk c on the main stream, y pass of chunk c (stores into the peers' W2) on the exchange stream
-    const int nc = std::max(1, std::min(s->ovl_chunks, s->nf));
-    for (int c = 0, f0 = 0; c < nc; ++c) {
-      const int n = s->nf / nc + (c < s->nf % nc ? 1 : 0);
-      LAPS_TRY(fwd_x(s, buf_F(s) + (size_t)f0 * s->npts, s->npts, n, buf_W1(s) + (size_t)f0 * s->w1sz, true));
-      LAPS_TRY(link_streams(s, s->stream, s->xstream));
-      {
-        StreamScope sc(s, s->xstream, 1, s->P > 1 ? s->ovl_y_warps : 0);
-        LAPS_TRY(fwd_y(s, buf_W1(s) + (size_t)f0 * s->w1sz, n, true, f0));
-      }
-      f0 += n;
-    }
-    LAPS_TRY(link_streams(s, s->xstream, s->stream));   // the main stream owns the buffers again (API calls are ordered on it)
-  }
+  LAPS_TRY(forward_xy(s, buf_F(s), s->npts, s->nf, true));
   }
   return 0;
 }
