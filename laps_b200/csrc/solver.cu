@@ -478,6 +478,9 @@ int do_fwd_y(S* s, const cplx* W1, int nfields, bool prune, int f0, int zbase, i
   if constexpr (N >= 256 && N <= 1024 && tly(N) == 8) {   // tuning knob: half-height tiles (twice the CTAs per SM, 64-byte chunks)
     if (s->tune_tly == 4) return do_fwd_y_tl<N, 4>(s, W1, nfields, prune, f0, zbase, zcount);
   }
+  if constexpr (N >= 128 && N <= 512) {   // 16 planes per tile: 256-byte runs in the peers' buffers (fewer, larger NVLink writes)
+    if (s->tune_tly == 16 || (s->tune_tly == 0 && s->P > 1 && s->nzl % 16 == 0)) return do_fwd_y_tl<N, 16>(s, W1, nfields, prune, f0, zbase, zcount);
+  }
   return do_fwd_y_tl<N, tly(N)>(s, W1, nfields, prune, f0, zbase, zcount);
 }
 
@@ -946,7 +949,7 @@ int stage_front(S* s, bool with_cfl) {
     for (int j = 0; j < 19; ++j) stored += s->fslot[j] >= 0;
     if (with_cfl) fill_cfl_params(s, f.cfl);
     const size_t plane = (size_t)s->nx * s->ny;
-    constexpr int kZAlign = 8;   // the y pass takes 8 planes per tile
+    constexpr int kZAlign = 16;  // the y pass takes 8 or 16 planes per tile
     int nc = std::max(1, std::min(s->ovl_chunks, (s->nzl + kZAlign - 1) / kZAlign));
     const int cz = ((s->nzl + nc - 1) / nc + kZAlign - 1) / kZAlign * kZAlign;
     nc = (s->nzl + cz - 1) / cz;
