@@ -177,7 +177,7 @@ struct laps_solver {
   int tune_tly = 0;                  // LAPS_TUNE_TLY=4: half-height tiles in the y passes
   int tune_screen = 1;               // LAPS_TUNE_SCREEN=0: the signal speeds of vardt at every point (see cfl_may_raise)
   int tune_overlap = -1;             // LAPS_TUNE_OVERLAP: -1 = default (on from 2 ranks on), 0 = one stream, 1 = two streams
-  int ovl_y_warps = 16, ovl_z_warps = 12, ovl_chunks = 4;   // warps per SM given to the exchange-side passes; z chunks of the front half
+  int ovl_y_warps = 32, ovl_z_warps = 12, ovl_chunks = 4;   // warps per SM given to the exchange-side passes; z chunks of the front half
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_scal = nullptr;
   int launches = 0;
   bool profiling = false;
