@@ -179,6 +179,52 @@ k_fwd_y(const cplx* __restrict__ W1, PeerTable W2, int nzl, int nz, int zoff,
 }
 
 // ---------------------------------------------------------------------------------------------
+// transpose_yz as a separate, light kernel (two-stream schedule): the forward y pass has stored its lines into a LOCAL
+// staging buffer laid out like the owners' W2 blocks but with this rank's z slab only ([peer][f][kx][kyl_p][zl]); this
+// kernel moves every row (one (f, kx, kyl) of one peer: nzl contiguous values) to its place in the owner's W2
+// ([f][kx][kyl_p][z], at this rank's z offset).  It needs no shared memory and few registers, so it runs beside the
+// HBM-bound passes of the compute stream without taking their occupancy, and NVLink is busy while they compute — the
+// reference's transpose blocks every rank in mpi_sendrecv (parallel.f90:273-297).
+// One warp per (f, kx, row of the rectangle); every warp walks the peers in its own rotation, so that at any moment
+// the ranks write to different peers.  Rows outside the dealiasing circle of their kx hold nothing and are skipped.
+struct PushParams {
+  const cplx* src[kMaxPeers];
+  cplx* dst[kMaxPeers];
+  int len[kMaxPeers];        // rows (ky) owned by peer p
+  int yoff[kMaxPeers];       // global ky of its row kyl: yoff + kyl * ystride
+  int nA[kMaxPeers], b0[kMaxPeers];   // its rows inside the rectangle |ky| <= kymax: kyl < nA or kyl >= b0
+  int nparts, rank, ystride, ny, nxh, nkx, nzl, nz, zoff, f0, nfc, maxrows;
+  const int* kymax_x;        // per-kx circle (nullptr: the rectangle)
+  int kymax;
+};
+
+__global__ void __launch_bounds__(256) k_xchg_push(const PushParams P) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  const int nwarps = (int)((gridDim.x * (unsigned)blockDim.x) >> 5);
+  const int total = P.nfc * P.nkx * P.maxrows;
+  for (int item = warp; item < total; item += nwarps) {
+    const int rl = item % P.maxrows;
+    const int t = item / P.maxrows;
+    const int kx = t % P.nkx, f = P.f0 + t / P.nkx;
+    const int kym = P.kymax_x ? __ldg(P.kymax_x + kx) : P.kymax;
+    for (int q = 0; q < P.nparts; ++q) {
+      int p = P.rank + 1 + q + item;
+      p %= P.nparts;
+      const int nlive = P.nA[p] + (P.len[p] - P.b0[p]);
+      if (rl >= nlive) continue;
+      const int kyl = rl < P.nA[p] ? rl : P.b0[p] + rl - P.nA[p];
+      const int ky = P.yoff[p] + kyl * P.ystride;
+      if (ky > kym && ky < P.ny - kym) continue;
+      const size_t row = ((size_t)f * P.nxh + kx) * P.len[p] + kyl;
+      const cplx* s = P.src[p] + row * P.nzl;
+      cplx* d = P.dst[p] + row * P.nz + P.zoff;
+      for (int i = lane; i < P.nzl; i += 32) d[i] = s[i];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // inverse y: V1 [g][kx][ky][zl] (z fastest) -> contiguous y-lines V2 [g][kx][zl][y]
 // (fftw.f90:212-218, unnormalised).  grid.x = ceil(nzl/TL) * nxh, grid.y = fields
 template <int N, int TL>

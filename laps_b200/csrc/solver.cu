@@ -93,7 +93,13 @@ struct laps_solver {
   void* bufX = nullptr;   // F (real fluxes) | V2
   void* bufY = nullptr;   // W1 | V1 (peer-written)
   void* bufZ = nullptr;   // W2 (peer-written)
-  size_t bytesX = 0, bytesY = 0, bytesZ = 0;
+  void* bufT = nullptr;   // two-stream schedule: local staging of the forward y pass, [peer][f][kx][kyl_p][zl]
+  size_t bytesX = 0, bytesY = 0, bytesZ = 0, bytesT = 0;
+  PeerTable tabT;         // the staging blocks, addressed like tabW2
+  int peer_nA[LAPS_MAX_RANKS], peer_b0[LAPS_MAX_RANKS];   // every peer's rows inside the rectangle |ky| <= kymax
+  cudaEvent_t ev_push[4] = {nullptr};   // chunk c of the forward fields has arrived on every rank
+  cudaEvent_t ev_zrow[3] = {nullptr};   // the z-pass stores of row group g have arrived on every rank
+  bool x_inflight = false;              // the exchange stream still works on the buffers (front half enqueued)
   cplx *uA = nullptr, *uB = nullptr, *rk = nullptr;   // u_fourier ping/pong, fnl_rk
   cplx *tw_x = nullptr, *tw_y = nullptr, *tw_z = nullptr;
   double *d_tab = nullptr;  // all 1-D tables in one allocation
@@ -177,7 +183,7 @@ struct laps_solver {
   int tune_tly = 0;                  // LAPS_TUNE_TLY=4: half-height tiles in the y passes
   int tune_screen = 1;               // LAPS_TUNE_SCREEN=0: the signal speeds of vardt at every point (see cfl_may_raise)
   int tune_overlap = -1;             // LAPS_TUNE_OVERLAP: -1 = default (on from 2 ranks on), 0 = one stream, 1 = two streams
-  int ovl_y_warps = 32, ovl_z_warps = 12, ovl_chunks = 4;   // warps per SM given to the exchange-side passes; z chunks of the front half
+  int ovl_push_ctas = 2, ovl_chunks = 3;   // CTAs per SM of the transpose kernel; forward field chunks
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_scal = nullptr;
   int launches = 0;
   bool profiling = false;
@@ -452,12 +458,14 @@ int do_flux_fwd_x(S* s, const FusedFluxParams& fp) {
 }
 
 // f0: first field slot of the launch (W1 points at it; the peers' W2 bases are advanced to it here)
+// staged: the lines go to this rank's staging blocks (tabT, z = this slab only) instead of the owners' W2 (k_xchg_push moves them)
 template <int N, int TL>
-int do_fwd_y_tl(S* s, const cplx* W1, int nfields, bool prune, int f0, int zbase, int zcount) {
+int do_fwd_y_tl(S* s, const cplx* W1, int nfields, bool prune, int f0, int zbase, int zcount, bool staged) {
   if (zcount < 0) { zbase = 0; zcount = s->nzl; }
-  PeerTable tabW2 = s->tabW2;
+  PeerTable tabW2 = staged ? s->tabT : s->tabW2;
+  const int dnz = staged ? s->nzl : s->nz, dzo = staged ? 0 : s->zo;
   for (int q = 0; q < s->P; ++q)
-    if (tabW2.base[q]) tabW2.base[q] += (size_t)f0 * s->nxh * tabW2.len[q] * s->nz;
+    if (tabW2.base[q]) tabW2.base[q] += (size_t)f0 * s->nxh * tabW2.len[q] * dnz;
   char name[32]; std::snprintf(name, sizeof(name), "fwd_y%d", nfields);
   typedef Tile<N, TL> T;
   LAPS_CK(s, prepare_kernel(k_fwd_y<N, TL>, T::SMEM, T::MINB));
@@ -467,21 +475,21 @@ int do_fwd_y_tl(S* s, const cplx* W1, int nfields, bool prune, int f0, int zbase
   int gx = ntiles;
   if (s->cap_warps > 0) gx = std::max(1, std::min(ntiles, capped_ctas(s, T::NTHREADS) / nfields));
   dim3 grid((unsigned)gx, (unsigned)nfields);
-  LAPS_LAUNCH((k_fwd_y<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->cs, W1, tabW2, s->nzl, s->nz, s->zo,
+  LAPS_LAUNCH((k_fwd_y<N, TL>), grid, dim3(T::NTHREADS), T::SMEM, s->cs, W1, tabW2, s->nzl, dnz, dzo,
               s->tw_y, 1.0 / N, s->nxh, prune ? s->kymax : N, prune ? (const int*)s->d_kymax_x : (const int*)nullptr, ntiles,
               zbase, zcount);
   return check_launch(s, "k_fwd_y");
 }
 
 template <int N>
-int do_fwd_y(S* s, const cplx* W1, int nfields, bool prune, int f0, int zbase, int zcount) {
+int do_fwd_y(S* s, const cplx* W1, int nfields, bool prune, int f0, int zbase, int zcount, bool staged) {
   if constexpr (N >= 256 && N <= 1024 && tly(N) == 8) {   // tuning knob: half-height tiles (twice the CTAs per SM, 64-byte chunks)
-    if (s->tune_tly == 4) return do_fwd_y_tl<N, 4>(s, W1, nfields, prune, f0, zbase, zcount);
+    if (s->tune_tly == 4) return do_fwd_y_tl<N, 4>(s, W1, nfields, prune, f0, zbase, zcount, staged);
   }
-  if constexpr (N >= 128 && N <= 512) {   // 16 planes per tile: 256-byte runs in the peers' buffers (fewer, larger NVLink writes)
-    if (s->tune_tly == 16 || (s->tune_tly == 0 && s->P > 1 && s->nzl % 16 == 0)) return do_fwd_y_tl<N, 16>(s, W1, nfields, prune, f0, zbase, zcount);
+  if constexpr (N >= 128 && N <= 512) {   // tuning knob: 16 planes per tile, 256-byte runs (measured at 8 GPUs: no gain over 128-byte runs)
+    if (s->tune_tly == 16) return do_fwd_y_tl<N, 16>(s, W1, nfields, prune, f0, zbase, zcount, staged);
   }
-  return do_fwd_y_tl<N, tly(N)>(s, W1, nfields, prune, f0, zbase, zcount);
+  return do_fwd_y_tl<N, tly(N)>(s, W1, nfields, prune, f0, zbase, zcount, staged);
 }
 
 template <int N, int TL>
@@ -618,8 +626,28 @@ int do_incomp_z(S* s, const ZParams& zp) {
 int fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1, bool prune, int zl0 = 0, int planes = -1, bool scoped = true) {
   LAPS_DISPATCH(s->nx, do_fwd_x, s, in, fstride, nfields, W1, prune, zl0, planes, scoped)
 }
-int fwd_y(S* s, const cplx* W1, int nfields, bool prune, int f0 = 0, int zbase = 0, int zcount = -1) {
-  LAPS_DISPATCH(s->ny, do_fwd_y, s, W1, nfields, prune, f0, zbase, zcount)
+int fwd_y(S* s, const cplx* W1, int nfields, bool prune, int f0 = 0, int zbase = 0, int zcount = -1, bool staged = false) {
+  LAPS_DISPATCH(s->ny, do_fwd_y, s, W1, nfields, prune, f0, zbase, zcount, staged)
+}
+
+// transpose_yz of the forward fields [f0, f0 + nfc) from the staging blocks to the owners' W2 (k_xchg_push), on s->cs
+int push_y(S* s, int f0, int nfc) {
+  PushParams pp; std::memset(&pp, 0, sizeof(pp));
+  int maxrows = 0;
+  for (int q = 0; q < s->P; ++q) {
+    pp.src[q] = s->tabT.base[q]; pp.dst[q] = s->tabW2.base[q];
+    pp.len[q] = s->ylens[q]; pp.yoff[q] = s->yoffs[q]; pp.nA[q] = s->peer_nA[q]; pp.b0[q] = s->peer_b0[q];
+    maxrows = std::max(maxrows, pp.nA[q] + (pp.len[q] - pp.b0[q]));
+  }
+  pp.nparts = s->P; pp.rank = s->rank; pp.ystride = s->ystride; pp.ny = s->ny; pp.nxh = s->nxh; pp.nkx = s->nkx;
+  pp.nzl = s->nzl; pp.nz = s->nz; pp.zoff = s->zo; pp.f0 = f0; pp.nfc = nfc; pp.maxrows = maxrows;
+  pp.kymax_x = s->d_kymax_x; pp.kymax = s->kymax;
+  char name[32]; std::snprintf(name, sizeof(name), "push_y%d", nfc);
+  LaunchScope ls(s, name, nfc * bytes_ycols(s, true));
+  const long long warps = (long long)nfc * s->nkx * maxrows;
+  const int ctas = (int)std::max<long long>(1, std::min<long long>((warps + 7) / 8, (long long)s->num_sms * std::max(1, s->ovl_push_ctas)));
+  LAPS_LAUNCH(k_xchg_push, dim3((unsigned)ctas), dim3(256), 0, s->cs, pp);
+  return check_launch(s, "k_xchg_push");
 }
 int flux_fwd_x(S* s, const FusedFluxParams& fp) { LAPS_DISPATCH(s->nx, do_flux_fwd_x, s, fp) }
 bool use_fused_flux(const S* s) {
@@ -885,16 +913,46 @@ int link_streams(S* s, cudaStream_t from, cudaStream_t to) {
   return 0;
 }
 
-// Two-stream schedule of a stage (3D compressible tree): the forward fields go through the x pass in chunks on the main
-// stream while the y pass of the previous chunk — whose stores leave over NVLink — runs on the exchange stream beside
-// it; after the last forward barrier the z passes (NVLink stores again) run on the exchange stream in row groups while
-// the inverse y and x passes of the previous group run on the main stream.  The reference's transposes block
-// (parallel.f90:273-324: mpi_sendrecv in a loop, nothing else runs); here the exchange hides behind the HBM-only passes.
+// Two-stream schedule of a stage (3D compressible tree, several ranks).  Every pass runs on the main stream at the
+// speed it has on one GPU; what the reference's transpose_yz does (parallel.f90:273-297: every rank blocked in
+// mpi_sendrecv) is a light copy kernel on the exchange stream (k_xchg_push) that moves chunk c of the forward fields to
+// their owners while the x and y passes of chunk c + 1 — and the first z-pass rows, which need only the first chunk —
+// compute.  The flag barriers that order the exchange live on the exchange stream as well (their own channel), so the
+// main stream never waits inside one: it waits for the EVENT recorded behind it, usually long after it has fired.
+// The inverse direction (transpose_zy) stays fused into the z passes: their stores are 1 KB runs that NVLink takes at
+// more than 800 GB/s while the kernel is bound by its own arithmetic.
 bool use_overlap(const S* s) {
-  if (s->two_d || s->incomp || s->ext_slot >= 0 || !s->xstream) return false;
+  if (s->two_d || s->incomp || s->ext_slot >= 0 || !s->xstream || !s->bufT) return false;
   if (use_fused_flux(s) || s->tune_zchunk > 0) return false;
   if (s->tune_overlap >= 0) return s->tune_overlap != 0;
   return s->P > 1;
+}
+
+// Forward field chunks of the two-stream schedule: chunk 0 = the fluxes of the density / momentum rows (all the first
+// z-pass row group needs: a prefix of the slots, which follow the flux numbering), the rest in ovl_chunks - 1 parts.
+int forward_chunks(const S* s, int (&f0)[4], int (&n)[4]) {
+  int cA = 0;
+  for (int j = 0; j < 12; ++j) if (s->slot[j] >= 0) cA = std::max(cA, s->slot[j] + 1);
+  const int parts = std::max(1, std::min(3, s->ovl_chunks - 1));
+  int nc = 0;
+  if (cA > 0 && cA < s->nf) { f0[nc] = 0; n[nc] = cA; ++nc; } else cA = 0;
+  const int rem = s->nf - cA;
+  for (int i = 0, at = cA; i < parts && at < s->nf; ++i) {
+    const int m = rem / parts + (i < rem % parts ? 1 : 0);
+    if (m == 0) continue;
+    f0[nc] = at; n[nc] = m; ++nc; at += m;
+  }
+  return nc;
+}
+
+// The exchange stream is still moving forward fields (a front half enqueued by laps_step): make the main stream wait
+// for it before anything else touches the work buffers.
+int settle_exchange(S* s) {
+  if (s->x_inflight) {
+    for (int c = 0; c < 4; ++c) if (s->ev_push[c]) LAPS_CK(s, cudaStreamWaitEvent(s->stream, s->ev_push[c], 0));
+    s->x_inflight = false;
+  }
+  return 0;
 }
 
 // The part of a stage that does not depend on the time step: J refresh, calc_flux, forward x and y passes.
@@ -936,52 +994,6 @@ int stage_front(S* s, bool with_cfl) {
     }
     LAPS_TRY(fwd_y(s, buf_W1(s), s->nf, true));
   } else {
-  if (use_overlap(s)) {
-    // Two-stream schedule of the front half over z chunks: calc_flux and the forward x pass of chunk c on the main stream,
-    // the forward y pass of chunk c — whose stores leave over NVLink — on the exchange stream beside the calc_flux and x
-    // pass of chunk c + 1.  (A y line needs every x line of its plane, nothing of other planes.)
-    FluxParams f;
-    f.uu = s->uu; f.J = s->J; f.npts = s->npts; f.fstride = s->npts;
-    f.hall = p.if_hall; f.aeb = p.if_AEB; f.gamma = p.adiabatic_index; f.di = p.ion_inertial_length; f.tau = s->tau;
-    f.z_radial = 0;
-    for (int j = 0; j < 19; ++j) f.slot[j] = s->fslot[j];
-    int stored = 0;
-    for (int j = 0; j < 19; ++j) stored += s->fslot[j] >= 0;
-    if (with_cfl) fill_cfl_params(s, f.cfl);
-    const size_t plane = (size_t)s->nx * s->ny;
-    constexpr int kZAlign = 16;  // the y pass takes 8 or 16 planes per tile
-    int nc = std::max(1, std::min(s->ovl_chunks, (s->nzl + kZAlign - 1) / kZAlign));
-    const int cz = ((s->nzl + nc - 1) / nc + kZAlign - 1) / kZAlign * kZAlign;
-    nc = (s->nzl + cz - 1) / cz;
-    int boff = 0;
-    for (int c = 0; c < nc; ++c) {
-      const int z0 = c * cz, nzc = std::min(cz, s->nzl - z0);
-      f.in_off = (size_t)z0 * plane; f.count = (size_t)nzc * plane;
-      f.F = buf_F(s) + f.in_off;      // full-slab flux layout: F[slot][point]
-      // this launch's share of the nblk CTAs (together the launches fill every entry of the CFL partial rows)
-      const int gb = c == nc - 1 ? s->nblk - boff : std::max(1, (int)((long long)s->nblk * nzc / s->nzl));
-      {
-        LaunchScope ls(s, with_cfl ? "flux+cfl" : "flux", (8 + (p.if_hall ? 3 : 0) + stored) * bytes_real(s) * ((double)nzc / s->nzl));
-        if (with_cfl) {
-          f.cfl.boff = boff;
-          LAPS_LAUNCH(k_flux<true>, dim3((unsigned)gb), dim3(256), 0, s->stream, f);
-        } else {
-          LAPS_LAUNCH(k_flux<false>, dim3((unsigned)gb), dim3(256), 0, s->stream, f);
-        }
-        LAPS_TRY(check_launch(s, "k_flux"));
-      }
-      boff += gb;
-      LAPS_TRY(fwd_x(s, buf_F(s) + f.in_off, s->npts, s->nf, buf_W1(s), true, z0, nzc));
-      LAPS_TRY(link_streams(s, s->stream, s->xstream));
-      {
-        StreamScope sc(s, s->xstream, 1, s->P > 1 ? s->ovl_y_warps : 0);
-        LAPS_TRY(fwd_y(s, buf_W1(s), s->nf, true, 0, z0, nzc));
-      }
-    }
-    if (with_cfl) LAPS_TRY(reduce_launch(s, 3, 2, 0.0));   // the maxima travel to the host while the last y pass runs
-    LAPS_TRY(link_streams(s, s->xstream, s->stream));      // the main stream owns the buffers again (API calls are ordered on it)
-    return 0;
-  }
   {  // calc_flux (mhdrhs.f90:21-124; 2D/mhdrhs.f90:23-128)
     FluxParams f;
     f.uu = s->uu; f.J = s->J; f.F = buf_F(s); f.npts = s->npts;
@@ -1004,7 +1016,25 @@ int stage_front(S* s, bool with_cfl) {
   if (s->ext_slot >= 0)   // calc_external_force_real (2D/mhdrhs.f90:129-131): the driver's field, transformed with the fluxes
     LAPS_CK(s, cudaMemcpyAsync(buf_F(s) + (size_t)s->ext_slot * s->npts, s->ext, s->npts * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
   // transform_flux_real_to_fourier (mhdrhs.f90:128-172)
-  LAPS_TRY(forward_xy(s, buf_F(s), s->npts, s->nf, true));
+  if (!use_overlap(s)) {
+    LAPS_TRY(forward_xy(s, buf_F(s), s->npts, s->nf, true));
+  } else {
+    int f0[4], n[4];
+    const int nc = forward_chunks(s, f0, n);
+    for (int c = 0; c < nc; ++c) {
+      LAPS_TRY(fwd_x(s, buf_F(s) + (size_t)f0[c] * s->npts, s->npts, n[c], buf_W1(s) + (size_t)f0[c] * s->w1sz, true));
+      LAPS_TRY(fwd_y(s, buf_W1(s) + (size_t)f0[c] * s->w1sz, n[c], true, f0[c], 0, -1, true));   // into the staging blocks
+      LAPS_TRY(link_streams(s, s->stream, s->xstream));
+      {
+        StreamScope sc(s, s->xstream, 1, 0);
+        LAPS_TRY(push_y(s, f0[c], n[c]));       // transpose_yz of this chunk, beside the passes of the next one
+        LAPS_TRY(host_barrier(s));              // ... and it has arrived on every rank
+      }
+      LAPS_CK(s, cudaEventRecord(s->ev_push[c], s->xstream));
+    }
+    for (int c = nc; c < 4; ++c) LAPS_CK(s, cudaEventRecord(s->ev_push[c], s->xstream));
+    s->x_inflight = true;
+  }
   }
   return 0;
 }
@@ -1029,41 +1059,50 @@ int stage_finish(S* s, bool want_j) {
   return 0;
 }
 
-// Back half of a stage on two streams (see use_overlap).  `z` holds the `ntasks` RHS rows of the stage (v = 1..7, or
-// 0..7 when the continuity row is not taken from the state); rows [0, na) = density/momentum, the rest = B and energy.
+// Back half of a stage in the two-stream schedule (see use_overlap).  `z` holds the `ntasks` RHS rows of the stage
+// (v = 1..7, or 0..7 when the continuity row is not taken from the state); rows [0, na) = density / momentum, which need
+// the first forward chunk only, the rest = B and energy.
 int stage_back_overlap(S* s, int irk, ZParams& z, int ntasks) {
   const laps_params& p = s->p;
   const bool want_j = p.if_hall && !(irk == 2 && s->Ur != 0.0);
-  const int cap = s->P > 1 ? s->ovl_z_warps : 0;
   const int na = ntasks - 4;                      // rows up to momentum z
   const int g0a = z.task[0].gout;                 // V1 slots of group A are g0a .. g0a + na - 1, of group B 4 .. 7
-  auto z_rows = [&](int first, int n) -> int {   // RHS rows [first, first + n) on the exchange stream, then the flag barrier
-    StreamScope sc(s, s->xstream, 1, cap);
+  auto z_rows = [&](int first, int n) -> int {   // RHS rows [first, first + n): stores into the peers' V1 (transpose_zy fused)
     ZParams zz = z;
     for (int i = 0; i < n; ++i) zz.task[i] = z.task[first + i];
-    if (s->tune_rhs) LAPS_TRY(rhs_z(s, zz, n));
-    else LAPS_TRY(spec_z(s, zz, n, "spec_z"));
-    return host_barrier(s);
+    if (s->tune_rhs) return rhs_z(s, zz, n);
+    return spec_z(s, zz, n, "spec_z");
   };
-  LAPS_TRY(link_streams(s, s->stream, s->xstream));
-  {  // every rank's forward y pass has landed in W2; every rank has finished reading V1 (previous stage's inverse y pass)
-    StreamScope sc(s, s->xstream, 1, cap);
-    LAPS_TRY(host_barrier(s));
-  }
+  auto arrived = [&](int g) -> int {             // flag barrier behind the rows just enqueued, on the exchange stream
+    LAPS_TRY(link_streams(s, s->stream, s->xstream));
+    {
+      StreamScope sc(s, s->xstream, 1, 0);
+      LAPS_TRY(host_barrier(s));
+    }
+    LAPS_CK(s, cudaEventRecord(s->ev_zrow[g], s->xstream));
+    return 0;
+  };
+  LAPS_CK(s, cudaStreamWaitEvent(s->stream, s->ev_push[0], 0));    // chunk 0 is in W2 on every rank (and nobody reads V1 any more)
   LAPS_TRY(z_rows(0, na));
-  LAPS_TRY(link_streams(s, s->xstream, s->stream));
-  LAPS_TRY(z_rows(na, 4));                                   // beside ...
-  LAPS_TRY(inverse_yx(s, g0a, na, true));                    // ... the inverse y, x passes of group A (main stream)
-  LAPS_TRY(link_streams(s, s->xstream, s->stream));
-  {  // J for the next stage's calc_flux + the continuity row (reads the rows just updated: same stream, after them)
-    StreamScope sc(s, s->xstream, 1, cap);
+  LAPS_TRY(arrived(0));
+  for (int c = 1; c < 4; ++c) LAPS_CK(s, cudaStreamWaitEvent(s->stream, s->ev_push[c], 0));
+  s->x_inflight = false;
+  LAPS_TRY(z_rows(na, 4));
+  LAPS_TRY(arrived(1));
+  const bool group_c = want_j || s->mass_from_state;
+  if (group_c) {  // J for the next stage's calc_flux + the continuity row (reads the rows just updated)
     LAPS_TRY(launch_current_tasks(s, s->uB, true, want_j, s->mass_from_state ? irk : -1));
-    if (want_j || s->mass_from_state) LAPS_TRY(host_barrier(s));
+    LAPS_TRY(arrived(2));
   }
-  LAPS_TRY(inverse_yx(s, 4, 4, true));                       // group B beside the current / continuity tasks
-  LAPS_TRY(link_streams(s, s->xstream, s->stream));
-  if (s->mass_from_state) LAPS_TRY(inverse_yx(s, 0, 1, true));
-  if (want_j) LAPS_TRY(inverse_yx(s, 8, 3, true));
+  LAPS_CK(s, cudaStreamWaitEvent(s->stream, s->ev_zrow[0], 0));
+  LAPS_TRY(inverse_yx(s, g0a, na, true));
+  LAPS_CK(s, cudaStreamWaitEvent(s->stream, s->ev_zrow[1], 0));
+  LAPS_TRY(inverse_yx(s, 4, 4, true));
+  if (group_c) {
+    LAPS_CK(s, cudaStreamWaitEvent(s->stream, s->ev_zrow[2], 0));
+    if (s->mass_from_state) LAPS_TRY(inverse_yx(s, 0, 1, true));
+    if (want_j) LAPS_TRY(inverse_yx(s, 8, 3, true));
+  }
   return stage_finish(s, want_j);
 }
 
@@ -1318,6 +1357,10 @@ int laps_create(const laps_params* params, laps_handle* out) {
     if (cudaStreamCreateWithPriority(&s->xstream, cudaStreamNonBlocking, hi) != cudaSuccess) return fail("cudaStreamCreateWithPriority failed");
     for (int i = 0; i < 16; ++i)
       if (cudaEventCreateWithFlags(&s->ev_link[i], cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate failed");
+    for (int i = 0; i < 4; ++i)
+      if (cudaEventCreateWithFlags(&s->ev_push[i], cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate failed");
+    for (int i = 0; i < 3; ++i)
+      if (cudaEventCreateWithFlags(&s->ev_zrow[i], cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate failed");
   }
 #else
   s->xstream = (cudaStream_t)1;   // the emulator runs launches synchronously: the two-stream schedule is exercised as a sequence
@@ -1325,8 +1368,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
   if (const char* e = std::getenv("LAPS_TUNE_OVERLAP")) s->tune_overlap = std::atoi(e);
   if (const char* e = std::getenv("LAPS_TUNE_SCREEN")) s->tune_screen = std::atoi(e);
   if (const char* e = std::getenv("LAPS_TUNE_TLY")) s->tune_tly = std::atoi(e);
-  if (const char* e = std::getenv("LAPS_TUNE_OVL_Y")) s->ovl_y_warps = std::atoi(e);
-  if (const char* e = std::getenv("LAPS_TUNE_OVL_Z")) s->ovl_z_warps = std::atoi(e);
+  if (const char* e = std::getenv("LAPS_TUNE_OVL_PUSH")) s->ovl_push_ctas = std::atoi(e);
   if (const char* e = std::getenv("LAPS_TUNE_OVL_CHUNKS")) s->ovl_chunks = std::atoi(e);
   cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1); cudaEventCreate(&s->ev_scal);
 
@@ -1342,6 +1384,14 @@ int laps_create(const laps_params* params, laps_handle* out) {
   if (s->incomp) alloc((void**)&s->G, 9 * s->npts * sizeof(double));
   if (s->ext_slot >= 0) alloc((void**)&s->ext, s->npts * sizeof(double));
   alloc(&s->bufX, s->bytesX); alloc(&s->bufY, s->bytesY); alloc(&s->bufZ, s->bytesZ);
+  {  // staging blocks of the two-stream schedule (3D compressible tree on several ranks, or LAPS_TUNE_OVERLAP=1)
+    int want = s->P > 1 ? 1 : 0;
+    if (const char* e = std::getenv("LAPS_TUNE_OVERLAP")) want = std::atoi(e) != 0 ? 1 : want;
+    if (want && !two_d && !s->incomp) {
+      s->bytesT = (size_t)s->nf * s->w1sz * sizeof(cplx);
+      alloc(&s->bufT, s->bytesT);
+    }
+  }
   alloc((void**)&s->uA, 8 * s->csz * sizeof(cplx));
   alloc((void**)&s->uB, 8 * s->csz * sizeof(cplx));
   alloc((void**)&s->rk, 8 * s->csz * sizeof(cplx));
@@ -1499,6 +1549,21 @@ int laps_create(const laps_params* params, laps_handle* out) {
   }
   s->tabW2.base[s->rank] = buf_W2(s);
   s->tabV1.base[s->rank] = buf_V1(s);
+  s->tabT = s->tabW2;     // same ownership tables; the blocks lie one behind the other in this rank's staging buffer
+  {
+    size_t at = 0;
+    for (int q = 0; q < s->P; ++q) {
+      s->tabT.base[q] = s->bufT ? (cplx*)s->bufT + at : nullptr;
+      at += (size_t)s->nf * s->nxh * s->ylens[q] * s->nzl;
+      // rows of peer q inside the rectangle |ky| <= kymax (run A: ky <= kymax, run B: ky >= ny - kymax)
+      int nA = 0;
+      while (nA < s->ylens[q] && s->yoffs[q] + nA * s->ystride <= s->kymax) ++nA;
+      int b0 = nA;
+      while (b0 < s->ylens[q] && s->yoffs[q] + b0 * s->ystride < s->ny - s->kymax) ++b0;
+      if (s->kymax >= s->ny / 2) { nA = s->ylens[q]; b0 = s->ylens[q]; }
+      s->peer_nA[q] = nA; s->peer_b0[q] = b0;
+    }
+  }
   std::memset(&s->xp, 0, sizeof(s->xp));
   std::memset(s->ipc_opened, 0, sizeof(s->ipc_opened));
   s->xp.rank = s->rank; s->xp.nranks = s->P;
@@ -1528,7 +1593,7 @@ int laps_destroy(laps_handle s) {
     for (int j = 0; j < 3; ++j)
       if (s->ipc_opened[q][j]) cudaIpcCloseMemHandle(s->ipc_opened[q][j]);
   cudaFree(s->xblk);
-  cudaFree(s->uu); cudaFree(s->J); cudaFree(s->G); cudaFree(s->ext); cudaFree(s->bufX); cudaFree(s->bufY); cudaFree(s->bufZ);
+  cudaFree(s->uu); cudaFree(s->J); cudaFree(s->G); cudaFree(s->ext); cudaFree(s->bufX); cudaFree(s->bufY); cudaFree(s->bufZ); cudaFree(s->bufT);
   cudaFree(s->uA); cudaFree(s->uB); cudaFree(s->rk); cudaFree(s->tw_x); cudaFree(s->tw_y); cudaFree(s->tw_z);
   cudaFree(s->d_tab); cudaFree(s->d_partial); cudaFree(s->d_scal); cudaFree(s->d_kymax_x); cudaFree(s->d_colmap); cudaFree(s->d_colkx);
   if (s->h_scal) cudaFreeHost(s->h_scal);
@@ -1545,6 +1610,8 @@ int laps_destroy(laps_handle s) {
   if (s->ostream) cudaStreamDestroy(s->ostream);
   if (s->xstream) cudaStreamDestroy(s->xstream);
   for (int i = 0; i < 16; ++i) if (s->ev_link[i]) cudaEventDestroy(s->ev_link[i]);
+  for (int i = 0; i < 4; ++i) if (s->ev_push[i]) cudaEventDestroy(s->ev_push[i]);
+  for (int i = 0; i < 3; ++i) if (s->ev_zrow[i]) cudaEventDestroy(s->ev_zrow[i]);
 #endif
   delete s;
   return 0;
@@ -1576,6 +1643,7 @@ static int finish_set_primitive(laps_handle s);
 static int set_primitive_body(laps_handle s, const double* uu_local) {
   if (!s || !uu_local) return 1;
   s->front_ready = false;
+  LAPS_TRY(settle_exchange(s));
   LAPS_CK(s, cudaMemcpyAsync(s->uu, uu_local, 8 * s->npts * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   return finish_set_primitive(s);
 }
@@ -1603,6 +1671,7 @@ static int finish_set_primitive(laps_handle s) {
 static int set_primitive_modes_body(laps_handle s, int32_t nmodes, const int32_t* k, const double* coef, const double* background) {
   if (!s || nmodes < 0 || (nmodes > 0 && (!k || !coef)) || !background) return 1;
   s->front_ready = false;
+  LAPS_TRY(settle_exchange(s));
   const int NYr = s->two_d ? s->nz : s->ny;       // the driver's ny
   std::vector<long long> idx;
   std::vector<cplx> val;                            // [8][nent]
@@ -1672,6 +1741,7 @@ static int set_primitive_modes_body(laps_handle s, int32_t nmodes, const int32_t
 static int set_time_body(laps_handle s, double time) {  // AEBmod.f90:56-73
   if (!s) return 1;
   s->front_ready = false;
+  LAPS_TRY(settle_exchange(s));
   const double old = s->radius;
   s->radius = s->p.radius0 + s->Ur * time;
   aeb_calc(s);
@@ -1838,11 +1908,12 @@ int laps_set_tune(laps_handle s, const char* name, int32_t value) {
   if (!s || !name) return 1;
   const std::string n(name);
   int* slot = n == "rhs" ? &s->tune_rhs : n == "rcg" ? &s->tune_rcg : n == "cgz" ? &s->tune_cgz : n == "z" ? &s->tune_z :
-              n == "spec" ? &s->tune_spec : n == "overlap" ? &s->tune_overlap : n == "ovl_y" ? &s->ovl_y_warps :
-              n == "ovl_z" ? &s->ovl_z_warps : n == "ovl_chunks" ? &s->ovl_chunks : n == "screen" ? &s->tune_screen : n == "tly" ? &s->tune_tly : nullptr;
+              n == "spec" ? &s->tune_spec : n == "overlap" ? &s->tune_overlap : n == "ovl_push" ? &s->ovl_push_ctas :
+              n == "ovl_chunks" ? &s->ovl_chunks : n == "screen" ? &s->tune_screen : n == "tly" ? &s->tune_tly : nullptr;
   if (!slot) { s->err = "laps_set_tune: unknown switch '" + n + "'"; return 1; }
   *slot = value;
   s->front_ready = false;
+  LAPS_TRY(settle_exchange(s));
   return 0;
 }
 
@@ -1886,6 +1957,7 @@ static int max_div_real_body(laps_handle s, double out[2]) {
   if (!s || !out) return 1;
   LAPS_TRY(require_state(s));
   s->front_ready = false;   // the work buffers are used as scratch
+  LAPS_TRY(settle_exchange(s));
   const bool prune = !s->spectrum_full;
   ZParams z; fill_zparams(s, z, prune);
   z.u_in = s->uA;
@@ -2076,6 +2148,7 @@ static int fft_forward_body(laps_handle s, const double* real_fields, int32_t nf
   if (!s || !real_fields || !spec_out) return 1;
   if (nfields < 1 || nfields > 8) { s->err = "laps_fft_forward: 1..8 fields per call"; return 1; }
   s->front_ready = false;   // the work buffers are used as scratch
+  LAPS_TRY(settle_exchange(s));
   // uses the flux work buffers and u_B as scratch; the state (u_A, uu) is untouched
   LAPS_CK(s, cudaMemcpyAsync(buf_F(s), real_fields, (size_t)nfields * s->npts * sizeof(double), cudaMemcpyHostToDevice, s->stream));
   LAPS_TRY(forward_xy(s, buf_F(s), s->npts, nfields, false));
@@ -2099,6 +2172,7 @@ static int fft_inverse_body(laps_handle s, const double* spec_in, int32_t nfield
   if (!s || !spec_in || !real_out) return 1;
   if (nfields < 1 || nfields > 8) { s->err = "laps_fft_inverse: 1..8 fields per call"; return 1; }
   s->front_ready = false;   // the work buffers are used as scratch
+  LAPS_TRY(settle_exchange(s));
   LAPS_CK(s, cudaMemcpyAsync(s->uB, spec_in, (size_t)nfields * s->csz * sizeof(cplx), cudaMemcpyHostToDevice, s->stream));
   ZParams z; fill_zparams(s, z);
   z.u_in = s->uB;

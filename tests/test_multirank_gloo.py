@@ -121,12 +121,12 @@ def test_absent_rank_does_not_wedge_the_others(emu):
 
 @pytest.mark.parametrize("world", [1, 2, 4])
 def test_two_stream_schedule_in_sequence(emu, world):
-    """The two-stream stage schedule (forward fields in chunks, z-pass rows in groups, flag barriers on their own channel,
-    grid-capped exchange-side launches: the default from 2 ranks on) gives the same state as the oracle.  The emulator
-    runs launches synchronously, so this checks the index math, the chunk / group bookkeeping and the barrier pairing,
-    not the stream ordering (tests/test_gpu_multirank.py does that on hardware)."""
+    """The two-stream stage schedule (forward fields in chunks through local staging blocks, transpose_yz as a copy kernel
+    on the exchange stream, z-pass rows in groups, flag barriers on their own channel: the default from 2 ranks on) gives
+    the same state as the oracle.  The emulator runs launches synchronously, so this checks the index math, the chunk /
+    group bookkeeping and the barrier pairing, not the stream ordering (tests/test_gpu_multirank.py does that on hardware)."""
     run_ranks(world, dict(lib=emu, shape=(16, 16, 16), case=dict(hall=True, aeb=True, dealias=1), steps=2,
-                          env=dict(LAPS_TUNE_OVERLAP="1", LAPS_TUNE_OVL_Y="1", LAPS_TUNE_OVL_Z="1")))
+                          env=dict(LAPS_TUNE_OVERLAP="1")))
     if world == 2:   # no Hall term, no dealiasing mask (the continuity row is then an ordinary RHS row), 2 chunks
         run_ranks(world, dict(lib=emu, shape=(16, 16, 16), case=dict(hall=False, aeb=False, dealias=0), steps=2,
                               env=dict(LAPS_TUNE_OVERLAP="1", LAPS_TUNE_OVL_CHUNKS="2")))

@@ -25,9 +25,8 @@ for stage in "$@"; do
     multi*)       n=${stage#multi}; trun $n bench.py --gpus $n --steps 10 --warmup 3 > $OUT/bench_512_${n}gpu.json 2> $OUT/bench_512_${n}gpu.err; tail -c 400 $OUT/bench_512_${n}gpu.err
                   LAPS_TUNE_OVERLAP=0 trun $n bench.py --gpus $n --steps 10 --warmup 3 --no-parity > $OUT/bench_512_${n}gpu_serial.json 2> $OUT/bench_512_${n}gpu_serial.err ;;
     abmulti*)     n=${stage#abmulti}; trun $n tools/ab_tune.py --rounds 3 --steps 5 --variants serial=overlap:0 overlap=overlap:1 \
-                    serial_tly8=overlap:0,tly:8 overlap_tly8=overlap:1,tly:8 y16=overlap:1,ovl_y:16 y64=overlap:1,ovl_y:64 y0=overlap:1,ovl_y:0 \
-                    z8=overlap:1,ovl_z:8 z16=overlap:1,ovl_z:16 z0=overlap:1,ovl_z:0 c2=overlap:1,ovl_chunks:2 c8=overlap:1,ovl_chunks:8 \
-                    y0z0=overlap:1,ovl_y:0,ovl_z:0 > $OUT/ab_tune_${n}gpu.jsonl 2> $OUT/ab_tune_${n}gpu.err
+                    c2=overlap:1,ovl_chunks:2 c4=overlap:1,ovl_chunks:4 push1=overlap:1,ovl_push:1 push4=overlap:1,ovl_push:4 push8=overlap:1,ovl_push:8 \
+                    tly16=overlap:1,tly:16 rhs0=overlap:1,rhs:0 > $OUT/ab_tune_${n}gpu.jsonl 2> $OUT/ab_tune_${n}gpu.err
                   grep "^{" $OUT/ab_tune_${n}gpu.jsonl | cut -c 1-200; tail -3 $OUT/ab_tune_${n}gpu.err ;;
     tests_nccl)   ( time timeout 1200 python -m pytest tests/test_gpu_multirank.py -m gpu -q --durations=10 -k "not connect_local and not exchange_wait" ) > $OUT/pytest_multirank_nccl_${NG}gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_multirank_nccl_${NG}gpu.log; tail -8 $OUT/pytest_multirank_nccl_${NG}gpu.log ;;
     cfg5)         trun $NG bench.py --gpus $NG --config 5 --steps 5 --warmup 3 > $OUT/bench_config5_${NG}gpu.json 2> $OUT/bench_config5_${NG}gpu.err; tail -c 400 $OUT/bench_config5_${NG}gpu.err ;;
