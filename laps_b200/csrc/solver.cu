@@ -1873,6 +1873,9 @@ int laps_set_profiling(laps_handle s, int32_t on) { if (!s) return 1; s->profili
 static int get_profile_body(laps_handle s, char* names, float* ms, int32_t cap, int32_t* count) {
   if (!s || !count) return 1;
   LAPS_CK(s, cudaStreamSynchronize(s->stream));
+#ifndef LAPS_EMU_BUILD
+  if (s->xstream) LAPS_CK(s, cudaStreamSynchronize(s->xstream));   // the transpose kernels of a front half enqueued by laps_step
+#endif
   int n = 0;
   for (auto& pe : s->prof) {
     if (n >= cap) break;
