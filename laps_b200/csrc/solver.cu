@@ -39,6 +39,7 @@ std::string g_create_error;
 #define LAPS_TRY(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
 
 constexpr double kPi = 3.141592653589793;  // mhdinit.f90:7
+constexpr int kDefaultOverlap = 0;         // stage schedule on several ranks (use_overlap)
 
 // ---- per-size tile shapes --------------------------------------------------------------------
 constexpr int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -184,6 +185,7 @@ struct laps_solver {
   int tune_screen = 1;               // LAPS_TUNE_SCREEN=0: the signal speeds of vardt at every point (see cfl_may_raise)
   int tune_overlap = -1;             // LAPS_TUNE_OVERLAP: -1 = default (on from 2 ranks on), 0 = one stream, 1 = two streams
   int ovl_push_ctas = 2, ovl_chunks = 3;   // CTAs per SM of the transpose kernel; forward field chunks
+  int ovl_y_warps = 16, ovl_z_warps = 12;  // form 1: warps per SM given to the exchange-side y pass / z passes
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_scal = nullptr;
   int launches = 0;
   bool profiling = false;
@@ -921,11 +923,18 @@ int link_streams(S* s, cudaStream_t from, cudaStream_t to) {
 // main stream never waits inside one: it waits for the EVENT recorded behind it, usually long after it has fired.
 // The inverse direction (transpose_zy) stays fused into the z passes: their stores are 1 KB runs that NVLink takes at
 // more than 800 GB/s while the kernel is bound by its own arithmetic.
-bool use_overlap(const S* s) {
-  if (s->two_d || s->incomp || s->ext_slot >= 0 || !s->xstream || !s->bufT) return false;
-  if (use_fused_flux(s) || s->tune_zchunk > 0) return false;
-  if (s->tune_overlap >= 0) return s->tune_overlap != 0;
-  return s->P > 1;
+// Returns 0 (one stream), 1 (two streams, the y pass and the z passes store straight into the peers' buffers from the
+// exchange stream, with their grids held to a share of every SM, beside the x passes / inverse passes of the main
+// stream) or 2 (two streams, transpose_yz as the copy kernel described above).  Measured on 8 B200s at 512^3
+// (profiles/r02_multi_gpu.md): 10.7 ms per step on one stream, 10.4 with form 1, 11.4 with form 2 — NVLink carries
+// about 1 GB per stage per GPU at 550-660 GB/s, half of the stage's compute time, and whatever runs beside the transfers
+// loses about what the overlap wins (the passes share SMs, L2 and HBM with them).
+int use_overlap(const S* s) {
+  if (s->two_d || s->incomp || s->ext_slot >= 0 || !s->xstream) return 0;
+  if (use_fused_flux(s) || s->tune_zchunk > 0) return 0;
+  int mode = s->tune_overlap >= 0 ? s->tune_overlap : (s->P > 1 ? kDefaultOverlap : 0);
+  if (mode == 2 && !s->bufT) mode = 1;
+  return mode;
 }
 
 // Forward field chunks of the two-stream schedule: chunk 0 = the fluxes of the density / momentum rows (all the first
@@ -1018,6 +1027,20 @@ int stage_front(S* s, bool with_cfl) {
   // transform_flux_real_to_fourier (mhdrhs.f90:128-172)
   if (!use_overlap(s)) {
     LAPS_TRY(forward_xy(s, buf_F(s), s->npts, s->nf, true));
+  } else if (use_overlap(s) == 1) {
+    // x pass of chunk c on the main stream, y pass of chunk c (stores into the peers' W2) on the exchange stream
+    const int nc = std::max(1, std::min(s->ovl_chunks, s->nf));
+    for (int c = 0, f0 = 0; c < nc; ++c) {
+      const int n = s->nf / nc + (c < s->nf % nc ? 1 : 0);
+      LAPS_TRY(fwd_x(s, buf_F(s) + (size_t)f0 * s->npts, s->npts, n, buf_W1(s) + (size_t)f0 * s->w1sz, true));
+      LAPS_TRY(link_streams(s, s->stream, s->xstream));
+      {
+        StreamScope sc(s, s->xstream, 1, s->P > 1 ? s->ovl_y_warps : 0);
+        LAPS_TRY(fwd_y(s, buf_W1(s) + (size_t)f0 * s->w1sz, n, true, f0));
+      }
+      f0 += n;
+    }
+    LAPS_TRY(link_streams(s, s->xstream, s->stream));   // the main stream owns the buffers again (API calls are ordered on it)
   } else {
     int f0[4], n[4];
     const int nc = forward_chunks(s, f0, n);
@@ -1062,7 +1085,7 @@ int stage_finish(S* s, bool want_j) {
 // Back half of a stage in the two-stream schedule (see use_overlap).  `z` holds the `ntasks` RHS rows of the stage
 // (v = 1..7, or 0..7 when the continuity row is not taken from the state); rows [0, na) = density / momentum, which need
 // the first forward chunk only, the rest = B and energy.
-int stage_back_overlap(S* s, int irk, ZParams& z, int ntasks) {
+int stage_back_push(S* s, int irk, ZParams& z, int ntasks) {
   const laps_params& p = s->p;
   const bool want_j = p.if_hall && !(irk == 2 && s->Ur != 0.0);
   const int na = ntasks - 4;                      // rows up to momentum z
@@ -1103,6 +1126,44 @@ int stage_back_overlap(S* s, int irk, ZParams& z, int ntasks) {
     if (s->mass_from_state) LAPS_TRY(inverse_yx(s, 0, 1, true));
     if (want_j) LAPS_TRY(inverse_yx(s, 8, 3, true));
   }
+  return stage_finish(s, want_j);
+}
+
+// Back half of a stage, two-stream form 1 (see use_overlap): the z passes store into the peers' V1 from the exchange
+// stream, the inverse y and x passes of the previous row group run on the main stream beside them.
+int stage_back_direct(S* s, int irk, ZParams& z, int ntasks) {
+  const laps_params& p = s->p;
+  const bool want_j = p.if_hall && !(irk == 2 && s->Ur != 0.0);
+  const int cap = s->P > 1 ? s->ovl_z_warps : 0;
+  const int na = ntasks - 4;                      // rows up to momentum z
+  const int g0a = z.task[0].gout;                 // V1 slots of group A are g0a .. g0a + na - 1, of group B 4 .. 7
+  auto z_rows = [&](int first, int n) -> int {   // RHS rows [first, first + n) on the exchange stream, then the flag barrier
+    StreamScope sc(s, s->xstream, 1, cap);
+    ZParams zz = z;
+    for (int i = 0; i < n; ++i) zz.task[i] = z.task[first + i];
+    if (s->tune_rhs) LAPS_TRY(rhs_z(s, zz, n));
+    else LAPS_TRY(spec_z(s, zz, n, "spec_z"));
+    return host_barrier(s);
+  };
+  LAPS_TRY(link_streams(s, s->stream, s->xstream));
+  {  // every rank's forward y pass has landed in W2; every rank has finished reading V1 (previous stage's inverse y pass)
+    StreamScope sc(s, s->xstream, 1, cap);
+    LAPS_TRY(host_barrier(s));
+  }
+  LAPS_TRY(z_rows(0, na));
+  LAPS_TRY(link_streams(s, s->xstream, s->stream));
+  LAPS_TRY(z_rows(na, 4));                                   // beside ...
+  LAPS_TRY(inverse_yx(s, g0a, na, true));                    // ... the inverse y, x passes of group A (main stream)
+  LAPS_TRY(link_streams(s, s->xstream, s->stream));
+  {  // J for the next stage's calc_flux + the continuity row (reads the rows just updated: same stream, after them)
+    StreamScope sc(s, s->xstream, 1, cap);
+    LAPS_TRY(launch_current_tasks(s, s->uB, true, want_j, s->mass_from_state ? irk : -1));
+    if (want_j || s->mass_from_state) LAPS_TRY(host_barrier(s));
+  }
+  LAPS_TRY(inverse_yx(s, 4, 4, true));                       // group B beside the current / continuity tasks
+  LAPS_TRY(link_streams(s, s->xstream, s->stream));
+  if (s->mass_from_state) LAPS_TRY(inverse_yx(s, 0, 1, true));
+  if (want_j) LAPS_TRY(inverse_yx(s, 8, 3, true));
   return stage_finish(s, want_j);
 }
 
@@ -1171,7 +1232,8 @@ int stage(S* s, int irk) {
     }
     const int t0 = s->mass_from_state ? 1 : 0;   // the continuity row is a kZMass task of the launch below
     if (t0) for (int v = 1; v < 8; ++v) z.task[v - 1] = z.task[v];
-    if (use_overlap(s)) return stage_back_overlap(s, irk, z, 8 - t0);
+    if (use_overlap(s) == 1) return stage_back_direct(s, irk, z, 8 - t0);
+    if (use_overlap(s) == 2) return stage_back_push(s, irk, z, 8 - t0);
     // (the persistent kernel carries one field in its (i k_line) term: the 2D tree with if_corotating goes through k_spec_z)
     if (s->tune_rhs && !z.corot2d) LAPS_TRY(rhs_z(s, z, 8 - t0));
     else LAPS_TRY(spec_z(s, z, 8 - t0, "spec_z"));
@@ -1385,8 +1447,9 @@ int laps_create(const laps_params* params, laps_handle* out) {
   if (s->ext_slot >= 0) alloc((void**)&s->ext, s->npts * sizeof(double));
   alloc(&s->bufX, s->bytesX); alloc(&s->bufY, s->bytesY); alloc(&s->bufZ, s->bytesZ);
   {  // staging blocks of the two-stream schedule (3D compressible tree on several ranks, or LAPS_TUNE_OVERLAP=1)
-    int want = s->P > 1 ? 1 : 0;
-    if (const char* e = std::getenv("LAPS_TUNE_OVERLAP")) want = std::atoi(e) != 0 ? 1 : want;
+    int want = (s->P > 1 && kDefaultOverlap == 2) ? 1 : 0;
+    if (const char* e = std::getenv("LAPS_TUNE_OVERLAP")) want = std::atoi(e) == 2 ? 1 : want;
+    if (const char* e = std::getenv("LAPS_TUNE_STAGING")) want = std::atoi(e) != 0 ? 1 : want;   // (A/B on a live handle: laps_set_tune)
     if (want && !two_d && !s->incomp) {
       s->bytesT = (size_t)s->nf * s->w1sz * sizeof(cplx);
       alloc(&s->bufT, s->bytesT);
@@ -1911,7 +1974,7 @@ int laps_set_tune(laps_handle s, const char* name, int32_t value) {
   if (!s || !name) return 1;
   const std::string n(name);
   int* slot = n == "rhs" ? &s->tune_rhs : n == "rcg" ? &s->tune_rcg : n == "cgz" ? &s->tune_cgz : n == "z" ? &s->tune_z :
-              n == "spec" ? &s->tune_spec : n == "overlap" ? &s->tune_overlap : n == "ovl_push" ? &s->ovl_push_ctas :
+              n == "spec" ? &s->tune_spec : n == "overlap" ? &s->tune_overlap : n == "ovl_push" ? &s->ovl_push_ctas : n == "ovl_y" ? &s->ovl_y_warps : n == "ovl_z" ? &s->ovl_z_warps :
               n == "ovl_chunks" ? &s->ovl_chunks : n == "screen" ? &s->tune_screen : n == "tly" ? &s->tune_tly : nullptr;
   if (!slot) { s->err = "laps_set_tune: unknown switch '" + n + "'"; return 1; }
   *slot = value;

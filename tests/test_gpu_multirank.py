@@ -73,10 +73,11 @@ def test_connect_local_threads_reference_slabs(world):
                 env=dict(LAPS_TUNE_CYCLIC="0"), expect_stride=1))
 
 
-@pytest.mark.parametrize("world", [2, 8])
-def test_connect_local_threads_one_stream_schedule(world):
-    """LAPS_TUNE_OVERLAP=0: the one-stream schedule (the default schedule from 2 ranks on uses two streams)."""
-    _local(dict(world=world, shape=(64, 64, 64), case=dict(hall=True, aeb=True, dealias=1), steps=2, env=dict(LAPS_TUNE_OVERLAP="0")))
+@pytest.mark.parametrize("world,form", [(2, "1"), (8, "1"), (2, "2"), (3, "2"), (8, "2")])
+def test_connect_local_threads_two_stream_schedules(world, form):
+    """LAPS_TUNE_OVERLAP=1 / 2: the opt-in two-stream stage schedules (use_overlap in csrc/solver.cu) on real streams."""
+    shape = (64, 64, 64) if world != 3 else (32, 64, 32)
+    _local(dict(world=world, shape=shape, case=dict(hall=True, aeb=True, dealias=1), steps=2, env=dict(LAPS_TUNE_OVERLAP=form)))
 
 
 def test_connect_local_threads_other_physics():
@@ -87,3 +88,10 @@ def test_connect_local_threads_other_physics():
 
 def test_exchange_wait_is_bounded():
     _local(dict(mode="bounded_wait"))
+
+
+@pytest.mark.parametrize("form", ["1", "2"])
+def test_two_gpus_two_stream_schedules(form):
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    run_ranks(2, dict(backend="nccl", shape=(64, 64, 64), case=dict(hall=True, aeb=True, dealias=1), steps=2, env=dict(LAPS_TUNE_OVERLAP=form)))

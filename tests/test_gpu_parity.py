@@ -310,11 +310,12 @@ def test_100_steps_against_the_executed_reference_source():
     rp.check_library_100_steps()
 
 
-def test_two_stream_schedule_single_gpu(monkeypatch):
-    """The two-stream stage schedule (default from 2 ranks on) forced on one GPU: same state as the oracle, and bit-identical
+@pytest.mark.parametrize("form", ["1", "2"])
+def test_two_stream_schedule_single_gpu(monkeypatch, form):
+    """The opt-in two-stream stage schedules (LAPS_TUNE_OVERLAP) forced on one GPU: same state as the oracle, and bit-identical
     to the one-stream schedule (the same kernels on the same data; only the order of independent launches differs)."""
     p, prim = pc.make_case(64, 64, 64, hall=True, aeb=True, dealias=1)
-    monkeypatch.setenv("LAPS_TUNE_OVERLAP", "1")
+    monkeypatch.setenv("LAPS_TUNE_OVERLAP", form)
     o, g = pc.run_both(p, prim, 2)
     pc.check_state(o, g, 1e-11)
     uu1, uf1 = g.get_state()[0], g.uu_fourier()

@@ -119,14 +119,16 @@ def test_absent_rank_does_not_wedge_the_others(emu):
                       env=dict(LAPS_XCHG_TIMEOUT_S="1.0")), timeout=120)
 
 
-@pytest.mark.parametrize("world", [1, 2, 4])
-def test_two_stream_schedule_in_sequence(emu, world):
-    """The two-stream stage schedule (forward fields in chunks through local staging blocks, transpose_yz as a copy kernel
-    on the exchange stream, z-pass rows in groups, flag barriers on their own channel: the default from 2 ranks on) gives
-    the same state as the oracle.  The emulator runs launches synchronously, so this checks the index math, the chunk /
-    group bookkeeping and the barrier pairing, not the stream ordering (tests/test_gpu_multirank.py does that on hardware)."""
-    run_ranks(world, dict(lib=emu, shape=(16, 16, 16), case=dict(hall=True, aeb=True, dealias=1), steps=2,
-                          env=dict(LAPS_TUNE_OVERLAP="1")))
+@pytest.mark.parametrize("world,form", [(1, "1"), (2, "1"), (4, "1"), (1, "2"), (2, "2"), (3, "2"), (8, "2")])
+def test_two_stream_schedule_in_sequence(emu, world, form):
+    """The two-stream stage schedules (LAPS_TUNE_OVERLAP; opt-in, see use_overlap in csrc/solver.cu) give the same state as
+    the oracle.  Form 1: the y pass and the z passes store into the peers' buffers from the exchange stream, in field
+    chunks / row groups, with grid-capped launches.  Form 2: the y pass stores into local staging blocks and a copy
+    kernel on the exchange stream (k_xchg_push) does transpose_yz, chunk by chunk, with the flag barriers as events.
+    The emulator runs launches synchronously, so this checks the index math, the chunk / group bookkeeping and the
+    barrier pairing, not the stream ordering (tests/test_gpu_multirank.py does that on hardware)."""
+    shape = (16, 16, 16) if world != 3 else (16, 32, 16)
+    run_ranks(world, dict(lib=emu, shape=shape, case=dict(hall=True, aeb=True, dealias=1), steps=2, env=dict(LAPS_TUNE_OVERLAP=form)))
     if world == 2:   # no Hall term, no dealiasing mask (the continuity row is then an ordinary RHS row), 2 chunks
         run_ranks(world, dict(lib=emu, shape=(16, 16, 16), case=dict(hall=False, aeb=False, dealias=0), steps=2,
-                              env=dict(LAPS_TUNE_OVERLAP="1", LAPS_TUNE_OVL_CHUNKS="2")))
+                              env=dict(LAPS_TUNE_OVERLAP=form, LAPS_TUNE_OVL_CHUNKS="2")))

@@ -22,7 +22,7 @@ DEFAULT = [
     "nospec=spec:0",
     "overlap=overlap:1",
 ]
-RESET = dict(rhs=1, cgz=0, rcg=0, z=3, spec=1, overlap=-1, ovl_chunks=3, ovl_push=2, screen=1, tly=0)
+RESET = dict(rhs=1, cgz=0, rcg=0, z=3, spec=1, overlap=-1, ovl_chunks=3, ovl_push=2, ovl_y=16, ovl_z=12, screen=1, tly=0)
 
 
 def main():

@@ -23,10 +23,10 @@ for stage in "$@"; do
     ncu_z)        timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_rhs_z|k_inv_y" -s 8 -c 2 -o $OUT/zpass python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity > $OUT/ncu_z.log 2>&1
                   ncu -i $OUT/zpass.ncu-rep --page raw --csv > $OUT/zpass_raw.csv 2>/dev/null; ls -la $OUT/zpass.ncu-rep ;;
     multi*)       n=${stage#multi}; trun $n bench.py --gpus $n --steps 10 --warmup 3 > $OUT/bench_512_${n}gpu.json 2> $OUT/bench_512_${n}gpu.err; tail -c 400 $OUT/bench_512_${n}gpu.err
-                  LAPS_TUNE_OVERLAP=0 trun $n bench.py --gpus $n --steps 10 --warmup 3 --no-parity > $OUT/bench_512_${n}gpu_serial.json 2> $OUT/bench_512_${n}gpu_serial.err ;;
-    abmulti*)     n=${stage#abmulti}; trun $n tools/ab_tune.py --rounds 3 --steps 5 --variants serial=overlap:0 overlap=overlap:1 \
-                    c2=overlap:1,ovl_chunks:2 c4=overlap:1,ovl_chunks:4 push1=overlap:1,ovl_push:1 push4=overlap:1,ovl_push:4 push8=overlap:1,ovl_push:8 \
-                    tly16=overlap:1,tly:16 rhs0=overlap:1,rhs:0 > $OUT/ab_tune_${n}gpu.jsonl 2> $OUT/ab_tune_${n}gpu.err
+                  LAPS_TUNE_OVERLAP=${ALT_OVERLAP:-0} trun $n bench.py --gpus $n --steps 10 --warmup 3 --no-parity > $OUT/bench_512_${n}gpu_overlap${ALT_OVERLAP:-0}.json 2> $OUT/bench_512_${n}gpu_overlap${ALT_OVERLAP:-0}.err ;;
+    abmulti*)     n=${stage#abmulti}; LAPS_TUNE_STAGING=1 trun $n tools/ab_tune.py --rounds 3 --steps 5 --variants serial=overlap:0 form1=overlap:1 form2=overlap:2 \
+                    form1_c2=overlap:1,ovl_chunks:2 form1_c4=overlap:1,ovl_chunks:4 form1_y8=overlap:1,ovl_y:8 form1_y32=overlap:1,ovl_y:32 \
+                    form1_z16=overlap:1,ovl_z:16 form1_z0=overlap:1,ovl_z:0 form2_c4=overlap:2,ovl_chunks:4 > $OUT/ab_tune_${n}gpu.jsonl 2> $OUT/ab_tune_${n}gpu.err
                   grep "^{" $OUT/ab_tune_${n}gpu.jsonl | cut -c 1-200; tail -3 $OUT/ab_tune_${n}gpu.err ;;
     tests_nccl)   ( time timeout 1200 python -m pytest tests/test_gpu_multirank.py -m gpu -q --durations=10 -k "not connect_local and not exchange_wait" ) > $OUT/pytest_multirank_nccl_${NG}gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_multirank_nccl_${NG}gpu.log; tail -8 $OUT/pytest_multirank_nccl_${NG}gpu.log ;;
     cfg5)         trun $NG bench.py --gpus $NG --config 5 --steps 5 --warmup 3 > $OUT/bench_config5_${NG}gpu.json 2> $OUT/bench_config5_${NG}gpu.err; tail -c 400 $OUT/bench_config5_${NG}gpu.err ;;
