@@ -39,7 +39,7 @@ std::string g_create_error;
 #define LAPS_TRY(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
 
 constexpr double kPi = 3.141592653589793;  // mhdinit.f90:7
-constexpr int kDefaultOverlap = 0;         // stage schedule on several ranks (use_overlap)
+
 
 // ---- per-size tile shapes --------------------------------------------------------------------
 constexpr int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -926,13 +926,14 @@ int link_streams(S* s, cudaStream_t from, cudaStream_t to) {
 // Returns 0 (one stream), 1 (two streams, the y pass and the z passes store straight into the peers' buffers from the
 // exchange stream, with their grids held to a share of every SM, beside the x passes / inverse passes of the main
 // stream) or 2 (two streams, transpose_yz as the copy kernel described above).  Measured on 8 B200s at 512^3
-// (profiles/r02_multi_gpu.md): 10.7 ms per step on one stream, 10.4 with form 1, 11.4 with form 2 — NVLink carries
-// about 1 GB per stage per GPU at 550-660 GB/s, half of the stage's compute time, and whatever runs beside the transfers
-// loses about what the overlap wins (the passes share SMs, L2 and HBM with them).
+// (profiles/r02_multi_gpu.md): 10.7 ms per step on one stream, 10.4 with form 1, 11.4 with form 2; on 4: 19.5 / 18.9 /
+// 21.0; on 2 the forms are within 1 % of each other.  NVLink carries about 1 GB per stage per GPU at 550-660 GB/s —
+// half of the stage's compute time — and whatever runs beside the transfers loses most of what the overlap wins (the
+// passes share SMs, L2 and HBM with them).  Default: form 1 from 4 ranks on, one stream below.
 int use_overlap(const S* s) {
   if (s->two_d || s->incomp || s->ext_slot >= 0 || !s->xstream) return 0;
   if (use_fused_flux(s) || s->tune_zchunk > 0) return 0;
-  int mode = s->tune_overlap >= 0 ? s->tune_overlap : (s->P > 1 ? kDefaultOverlap : 0);
+  int mode = s->tune_overlap >= 0 ? s->tune_overlap : (s->P >= 4 ? 1 : 0);   // default: form 1 from 4 ranks on
   if (mode == 2 && !s->bufT) mode = 1;
   return mode;
 }
@@ -1447,7 +1448,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
   if (s->ext_slot >= 0) alloc((void**)&s->ext, s->npts * sizeof(double));
   alloc(&s->bufX, s->bytesX); alloc(&s->bufY, s->bytesY); alloc(&s->bufZ, s->bytesZ);
   {  // staging blocks of the two-stream schedule (3D compressible tree on several ranks, or LAPS_TUNE_OVERLAP=1)
-    int want = (s->P > 1 && kDefaultOverlap == 2) ? 1 : 0;
+    int want = 0;
     if (const char* e = std::getenv("LAPS_TUNE_OVERLAP")) want = std::atoi(e) == 2 ? 1 : want;
     if (const char* e = std::getenv("LAPS_TUNE_STAGING")) want = std::atoi(e) != 0 ? 1 : want;   // (A/B on a live handle: laps_set_tune)
     if (want && !two_d && !s->incomp) {
