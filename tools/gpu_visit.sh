@@ -19,7 +19,9 @@ for stage in "$@"; do
     configs)      for c in 1 2 3; do timeout 600 python bench.py --config $c --steps 10 --warmup 3 --no-cpu-baseline > $OUT/bench_config$c.json 2> $OUT/bench_config$c.err; done ;;
     launches)     timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_512_1gpu.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity > $OUT/launches_bench.log 2>&1 ;;
     ncu_stage)    timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"k_rhs_z|k_spec_z|k_fwd|k_inv|k_flux|k_cfl" -s 60 -c 12 -o $OUT/stage_full python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity > $OUT/ncu_full.log 2>&1
-                  ncu -i $OUT/stage_full.ncu-rep --page raw --csv > $OUT/stage_full_raw.csv 2>/dev/null ;;
+                  ncu -i $OUT/stage_full.ncu-rep --page raw --csv > $OUT/stage_full_raw.csv 2>/dev/null
+                  python tools/ncu_traffic.py $OUT/stage_full_raw.csv 4 512 1 "profiles/${TAG}_ncu_stage.md (ncu --set full, 512^3 Hall + expanding box, 1 B200; dram__bytes_read.sum + dram__bytes_write.sum per launch)" $OUT/traffic.json $OUT/ncu_stage_table.md > /dev/null
+                  rm -f $OUT/stage_full.ncu-rep; cat $OUT/ncu_stage_table.md ;;
     ncu_z)        timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_rhs_z|k_inv_y" -s 8 -c 2 -o $OUT/zpass python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity > $OUT/ncu_z.log 2>&1
                   ncu -i $OUT/zpass.ncu-rep --page raw --csv > $OUT/zpass_raw.csv 2>/dev/null; ls -la $OUT/zpass.ncu-rep ;;
     multi*)       n=${stage#multi}; trun $n bench.py --gpus $n --steps 10 --warmup 3 > $OUT/bench_512_${n}gpu.json 2> $OUT/bench_512_${n}gpu.err; tail -c 400 $OUT/bench_512_${n}gpu.err
