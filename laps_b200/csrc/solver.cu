@@ -856,7 +856,7 @@ int stage_incomp(S* s, int irk) {
     FluxIncParams f;
     f.uu = s->uu; f.J = s->J; f.G = s->G; f.F = buf_F(s); f.npts = s->npts;
     f.hall = p.if_hall; f.di = p.ion_inertial_length;
-    LaunchScope ls(s, "flux", (8 + 3 + 9 + 6) * bytes_real(s));
+    LaunchScope ls(s, "flux", (7 + 3 + 9 + 6) * bytes_real(s));   // reads rho, rho u, B (the pressure is not an input), J, grad u; writes Fp, E
     LAPS_LAUNCH(k_flux_incomp, dim3((unsigned)s->nblk), dim3(256), 0, s->stream, f);
     LAPS_TRY(check_launch(s, "k_flux_incomp"));
   }
