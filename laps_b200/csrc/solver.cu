@@ -510,7 +510,10 @@ int do_inv_y_tl(S* s, const cplx* V1, cplx* V2, int nfields, bool prune) {
 template <int N>
 int do_inv_y(S* s, const cplx* V1, cplx* V2, int nfields, bool prune) {
   if constexpr (N >= 256 && N <= 1024 && tly(N) == 8) {
-    if (s->tune_tly == 4) return do_inv_y_tl<N, 4>(s, V1, V2, nfields, prune);
+    // 1024-point lines: 8-line tiles are 1024-thread CTAs, one per SM.  The forward pass wants them (128-byte runs in the
+    // peers' buffers: 662 against 427 GB/s of NVLink egress at 1024^3 on 8 GPUs), the inverse pass, whose strided side is
+    // local, runs better with two 4-line CTAs per SM (0.63 against 0.50 of the HBM peak, profiles/r02_multi_gpu.md)
+    if (s->tune_tly == 4 || (N == 1024 && s->tune_tly == 0)) return do_inv_y_tl<N, 4>(s, V1, V2, nfields, prune);
   }
   return do_inv_y_tl<N, tly(N)>(s, V1, V2, nfields, prune);
 }
