@@ -60,30 +60,34 @@ def _local(cfg, timeout=900):
     assert out.returncode == 0 and "local ranks ok" in out.stdout, out.stdout[-4000:]
 
 
-@pytest.mark.parametrize("world,stride", [(2, 1), (3, 1), (4, 4), (8, 8)])
-def test_connect_local_threads_parity(world, stride):
-    """Default ownership: decompose_1d slabs up to 3 ranks, round-robin ky rows from 4 ranks on."""
-    shape = (64, 64, 64) if world != 3 else (32, 64, 32)
-    _local(dict(world=world, shape=shape, case=dict(hall=True, aeb=True, dealias=1), steps=2, expect_stride=stride))
+_HALL = dict(hall=True, aeb=True, dealias=1)
 
 
-@pytest.mark.parametrize("world", [4, 8])
-def test_connect_local_threads_reference_slabs(world):
-    _local(dict(world=world, shape=(64, 64, 64), case=dict(hall=True, aeb=True, dealias=1), steps=2,
-                env=dict(LAPS_TUNE_CYCLIC="0"), expect_stride=1))
+def test_connect_local_threads_parity():
+    """Default ownership and schedule: decompose_1d slabs up to 3 ranks, round-robin ky rows from 4 ranks on (2, 3, 4, 8 ranks);
+    the reference's slabs forced at 4 and 8 ranks."""
+    _local([dict(world=2, shape=(64, 64, 64), case=_HALL, steps=2, expect_stride=1),
+            dict(world=4, shape=(64, 64, 64), case=_HALL, steps=2, expect_stride=4),
+            dict(world=8, shape=(64, 64, 64), case=_HALL, steps=2, expect_stride=8),
+            dict(world=4, shape=(64, 64, 64), case=_HALL, steps=2, env=dict(LAPS_TUNE_CYCLIC="0"), expect_stride=1),
+            dict(world=8, shape=(64, 64, 64), case=_HALL, steps=2, env=dict(LAPS_TUNE_CYCLIC="0"), expect_stride=1),
+            dict(world=3, shape=(32, 64, 32), case=_HALL, steps=2, expect_stride=1)])
 
 
-@pytest.mark.parametrize("world,form", [(2, "1"), (8, "1"), (2, "2"), (3, "2"), (8, "2")])
-def test_connect_local_threads_two_stream_schedules(world, form):
-    """LAPS_TUNE_OVERLAP=1 / 2: the opt-in two-stream stage schedules (use_overlap in csrc/solver.cu) on real streams."""
-    shape = (64, 64, 64) if world != 3 else (32, 64, 32)
-    _local(dict(world=world, shape=shape, case=dict(hall=True, aeb=True, dealias=1), steps=2, env=dict(LAPS_TUNE_OVERLAP=form)))
+def test_connect_local_threads_stage_schedules():
+    """LAPS_TUNE_OVERLAP=0 / 1 / 2 on real streams: one stream (forced at 8 ranks, where form 1 is the default), form 1 (forced at
+    2 ranks, default at 8 above), form 2 at 2, 3 and 8 ranks (use_overlap in csrc/solver.cu)."""
+    _local([dict(world=8, shape=(64, 64, 64), case=_HALL, steps=2, env=dict(LAPS_TUNE_OVERLAP="0")),
+            dict(world=2, shape=(64, 64, 64), case=_HALL, steps=2, env=dict(LAPS_TUNE_OVERLAP="1")),
+            dict(world=2, shape=(64, 64, 64), case=_HALL, steps=2, env=dict(LAPS_TUNE_OVERLAP="2")),
+            dict(world=8, shape=(64, 64, 64), case=_HALL, steps=2, env=dict(LAPS_TUNE_OVERLAP="2")),
+            dict(world=3, shape=(32, 64, 32), case=_HALL, steps=2, env=dict(LAPS_TUNE_OVERLAP="2"))])
 
 
 def test_connect_local_threads_other_physics():
     """Corotation + filter dealiasing (no pruning) on 3 ranks with a remainder slab; incompressible tree on 2."""
-    _local(dict(world=3, shape=(32, 64, 32), case=dict(hall=True, aeb=True, corot=True, dealias=2), steps=1))
-    _local(dict(world=2, shape=(64, 64, 64), case=dict(hall=True, aeb=True, dealias=1), steps=2, incompressible=True))
+    _local([dict(world=3, shape=(32, 64, 32), case=dict(hall=True, aeb=True, corot=True, dealias=2), steps=1),
+            dict(world=2, shape=(64, 64, 64), case=_HALL, steps=2, incompressible=True)])
 
 
 def test_exchange_wait_is_bounded():
