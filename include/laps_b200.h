@@ -49,8 +49,8 @@ typedef struct laps_params {
   /* 2D tree (src_compressible/2D/): ndim = 2 with nz = 1 runs the (nx, ny) algorithm of 2D/mhdrhs.f90,
    * 2D/mhd.f90:296-406 (vardt), 2D/dealiasing.f90 (dealias_option 3 = square truncation) on one GPU;
    * ndim = 0 or 3 is the 3D tree.  if_z_radial: 2D/mhd.f90:44 (&AEB); if_limit_dt_increase:
-   * 2D/mhd.f90:23,396-404 (&numerical).  if_corotating (2D/mhdrhs.f90:282-288, 2D/AEBmod.f90:101-106) is supported in the
-   * compressible 2D tree (not together with if_z_radial, 2D/mhd.f90:62-67), not in the incompressible one. */
+   * 2D/mhd.f90:23,396-404 (&numerical).  if_corotating (2D/mhdrhs.f90:282-288, 2D/AEBmod.f90:101-106) is supported in both
+   * 2D trees (not together with if_z_radial, 2D/mhd.f90:62-67). */
   int32_t ndim;
   int32_t if_z_radial;
   int32_t if_limit_dt_increase;

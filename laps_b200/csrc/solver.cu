@@ -880,6 +880,13 @@ int stage_incomp(S* s, int irk) {
       z.task[0] = rhs_task(4, 4, -1, 0.0, -1, 0.0, -1, 0.0, -1.0, 5, -1.0);
       z.task[1] = rhs_task(5, 5, 5, 1.0, -1, 0.0, -1, 0.0, +1.0, -1, 0.0);
       z.task[2] = rhs_task(6, 6, 4, -1.0, -1, 0.0, -1, 0.0, +1.0, 3, +1.0);
+      if (z.corot2d) {   // if_corotating (src_incompressible/2D/mhdrhs.f90:196-201): see the compressible 2D rows in stage()
+        const double cq = s->cosa, sq = s->sina * s->radius / p.radius0;
+        z.task[0] = rhs_task(4, 4, -1, 0.0, 5, 1.0, -1, 0.0, -1.0, 5, -1.0);  z.task[0].cf1 = cq;
+        z.task[1] = rhs_task(5, 5, 5, 1.0, -1, 0.0, -1, 0.0, +1.0, 5, +1.0);  z.task[1].cf1 = sq;
+        z.task[2] = rhs_task(6, 6, 4, -1.0, 3, 1.0, -1, 0.0, +1.0, 3, +1.0);
+        z.task[2].cf1 = cq; z.task[2].fc2 = 4; z.task[2].cf2 = -sq;
+      }
     }
     LAPS_TRY(spec_z(s, z, 3, "spec_z"));
   }
@@ -1305,7 +1312,6 @@ int laps_create(const laps_params* params, laps_handle* out) {
     // ky tables become the internal z tables (Ly -> Lz, afy -> afz).
     if (u.nz != 1) { g_create_error = "ndim = 2 needs nz = 1"; return 1; }
     if (u.nranks != 1) { g_create_error = "the 2D tree runs on one GPU (nranks = 1)"; return 1; }
-    if (u.if_AEB && u.if_corotating && u.incompressible) { g_create_error = "if_corotating is not supported in the incompressible 2D tree"; return 1; }
     if (u.if_AEB && u.if_corotating && u.if_z_radial) { g_create_error = "if_z_radial and if_corotating exclude each other (2D/mhd.f90:62-67)"; return 1; }
     if (!size_supported(u.nx) || !(size_supported(u.ny) || u.ny == 8)) { g_create_error = "nx must be a power of two in [16, 2048], ny in [8, 2048]"; return 1; }
     p.ny = 1; p.nz = u.ny; p.Ly = 1.0; p.Lz = u.Ly; p.afz = u.afy;

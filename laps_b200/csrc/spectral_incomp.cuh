@@ -86,16 +86,22 @@ k_incomp_z(const ZParams P) {
     const int kz = FF::kout(u, e);
     // 2D tree (src_incompressible/2D/mhdrhs.f90:189): the line axis carries the reference's ky, kz = 0
     const double kl = __ldg(P.kze + kz);
-    const double kyy = P.mode2d ? kl : kye, kzz = P.mode2d ? 0.0 : kl;
-    const double k2 = __dadd_rn(ksq_xy, __ldg(P.ksq_z + kz));
+    double kxx = kxe, kyy = P.mode2d ? kl : kye;
+    const double kzz = P.mode2d ? 0.0 : kl;
+    double k2 = __dadd_rn(ksq_xy, __ldg(P.ksq_z + kz));
+    if (P.corot2d) {   // 2D tree with if_corotating (2D/mhdrhs.f90:196-201,593-598): both components vary along the line
+      const double kyl = __ldg(P.kzr + kz);
+      corot2d_k(P, kxr, kyl, kxx, kyy);
+      if (P.corot_ksq) k2 = __dadd_rn(k2, corot2d_cross(P, kxr, kyl));
+    }
     const cplx f1 = S0[e * G::NT + u], f2 = S1[e * G::NT + u], f3 = cscale(r[e], P.scale);
-    const cplx sum = cadd(cadd(cmul_i(f1, kxe), cmul_i(f2, kyy)), cmul_i(f3, kzz));
+    const cplx sum = cadd(cadd(cmul_i(f1, kxx), cmul_i(f2, kyy)), cmul_i(f3, kzz));
     if (k2 < 1e-10) {   // "background field, not important in Fourier space" (mhdrhs.f90:155-159,505-508)
       S0[e * G::NT + u] = mk(0.0, 0.0); S1[e * G::NT + u] = mk(0.0, 0.0); S2[e * G::NT + u] = mk(0.0, 0.0);
       r[e] = mk(0.0, 0.0);
     } else {
       const cplx kd = mk(__ddiv_rn(sum.x, k2), __ddiv_rn(sum.y, k2));
-      S0[e * G::NT + u] = cadd(f1, cmul_i(kd, kxe));
+      S0[e * G::NT + u] = cadd(f1, cmul_i(kd, kxx));
       S1[e * G::NT + u] = cadd(f2, cmul_i(kd, kyy));
       S2[e * G::NT + u] = cadd(f3, cmul_i(kd, kzz));
       r[e] = mk(-kd.x, -kd.y);   // p^
@@ -127,6 +133,7 @@ k_incomp_z(const ZParams P) {
       double ksq = 0.0;
       if (need_ksq) {
         ksq = __dadd_rn(ksq_xy, __ldg(P.ksq_z + kz));
+        if (P.corot2d && P.corot_ksq) ksq = __dadd_rn(ksq, corot2d_cross(P, kxr, __ldg(P.kzr + kz)));
         fnl.x -= (ce * uo.x) * ksq;
         fnl.y -= (ce * uo.y) * ksq;
       }

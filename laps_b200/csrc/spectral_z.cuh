@@ -418,7 +418,9 @@ LAPS_D void spec_z_group(const ZParams& P, const ZTask& K, const int group, cplx
       const int kz = u + e * G::NT;
       // 2D trees: the line axis carries the reference's ky and kz = 0 (src_incompressible/2D/mhdrhs.f90:396)
       const double kzz = __ldg(P.kze + kz);
-      const double ka = K.jcomp == 0 ? kxe : (K.jcomp == 1 ? (P.mode2d ? kzz : kye) : (P.mode2d ? 0.0 : kzz));
+      double rx = kxe, ry = P.mode2d ? kzz : kye;
+      if (P.corot2d) corot2d_k(P, kxr, __ldg(P.kzr + kz), rx, ry);
+      const double ka = K.jcomp == 0 ? rx : (K.jcomp == 1 ? ry : (P.mode2d ? 0.0 : kzz));
       const cplx t = cmul_i(live ? U[kz] : mk(0.0, 0.0), ka);
       r[e] = mk(__ddiv_rn(t.x, K.cx), __ddiv_rn(t.y, K.cx));
     }
@@ -431,7 +433,9 @@ LAPS_D void spec_z_group(const ZParams& P, const ZTask& K, const int group, cplx
       const cplx b = live ? U[P.fstride + kz] : mk(0.0, 0.0);
       const cplx c = live ? U[2 * P.fstride + kz] : mk(0.0, 0.0);
       const double kzz = __ldg(P.kze + kz);
-      const cplx t = cadd(cadd(cmul_i(a, kxe), cmul_i(b, P.mode2d ? kzz : kye)), cmul_i(c, P.mode2d ? 0.0 : kzz));
+      double rx = kxe, ry = P.mode2d ? kzz : kye;
+      if (P.corot2d) corot2d_k(P, kxr, __ldg(P.kzr + kz), rx, ry);
+      const cplx t = cadd(cadd(cmul_i(a, rx), cmul_i(b, ry)), cmul_i(c, P.mode2d ? 0.0 : kzz));
       r[e] = mk(__ddiv_rn(t.x, K.cx), __ddiv_rn(t.y, K.cx));
     }
   } else {  // kZCurrent: J^ = i k x B^ (mhdrhs.f90:329-336) from the updated state

@@ -318,6 +318,10 @@ CASES_INCOMPRESSIBLE_2D = {
     "i2d_square_explicit_limit": dict(nx=16, ny=32, nz=1, if_hall=True, if_aeb=True, if_corotating=False, dealias_option=3,
                                       if_resis=True, if_resis_exp=True, if_visc=True, if_visc_exp=True, if_conserve_background=True,
                                       if_z_radial=False, if_limit_dt_increase=True, if_external_force=False),
+    # if_corotating (src_incompressible/2D/mhdrhs.f90:196-201,318-323; 2D/mhd.f90:602-607,653-658; 2D/AEBmod.f90:101-106)
+    "i2d_corotating": dict(nx=16, ny=32, nz=1, if_hall=True, if_aeb=True, if_corotating=True, dealias_option=1, if_resis=True,
+                           if_resis_exp=True, if_visc=True, if_visc_exp=False, if_conserve_background=False,
+                           if_z_radial=False, if_limit_dt_increase=False, if_external_force=False),
 }
 
 
@@ -350,6 +354,8 @@ def run_case_incompressible_2d(name, c, nsteps=3, pieces=False):
     ns["grid_initialize"]()
     ns["dealias_initialize"]()
     ns["aeb_calc"](ns["radius"])
+    ang = ns["corotating_angle"] if ns["if_corotating"] else 0.0       # AEB_initialize (src_incompressible/2D/AEBmod.f90:24-29)
+    ns["cos_cor_ang"], ns["sin_cor_ang"] = float(np.cos(ang)), float(np.sin(ang))
     st["uu"][...] = prim
     ns["initial_calc_conserve_variable"]()
     ns["transform_uu_real_to_fourier"]()

@@ -134,11 +134,13 @@ def test_incompressible_tree_parity_64(name, kw):
 
 @pytest.mark.parametrize("name,kw", [("hall_aeb_square", dict(hall=True, aeb=True, dealias=3)),
                                      ("filter_explicit", dict(hall=False, aeb=False, dealias=2, explicit=True, conserve_bg=True, limit_dt=True)),
-                                     ("retransform", dict(hall=True, aeb=False, dealias=0))])
+                                     ("retransform", dict(hall=True, aeb=False, dealias=0)),
+                                     ("corotating", dict(hall=True, aeb=True, corot=True, dealias=1)),
+                                     ("corotating_filter_explicit", dict(hall=True, aeb=True, corot=True, dealias=2, explicit=True, conserve_bg=True))])
 def test_incompressible_2d_tree_parity(name, kw):
     """src_incompressible/2D at 256 x 128, two steps, against the oracle."""
     p, prim = pc.make_case_incompressible_2d(256, 128, **kw)
-    o, g = pc.run_both(p, prim, 2)
+    o, g = pc.run_both(p, prim, 2, t0=2.0 if kw.get("corot") else 0.0)
     pc.check_state(o, g, 1e-11)
     pc.check_diagnostics(o, g, 1e-9)
     db, dv = g.calc_max_div_real()
@@ -297,7 +299,7 @@ def test_2d_library_agrees_with_the_executed_reference_source(name):
     rp.check_library_2d(name)
 
 
-@pytest.mark.parametrize("name", ["i2d_hall_aeb_mask", "i2d_square_explicit_limit"])
+@pytest.mark.parametrize("name", ["i2d_hall_aeb_mask", "i2d_square_explicit_limit", "i2d_corotating"])
 def test_incompressible_2d_library_agrees_with_the_executed_reference_source(name):
     import test_reference_source_pins as rp
     rp.check_library_incompressible_2d(name)

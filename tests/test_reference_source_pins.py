@@ -17,7 +17,7 @@ from oracle import laps_oracle as lo  # noqa: E402
 GOLD = os.path.join(HERE, "golden", "ref_exec")
 CASES = ["hall_aeb_mask", "corot_filter_explicit", "plain_nodealias"]
 CASES_INCOMPRESSIBLE = ["incomp_hall_aeb_mask", "incomp_corot_filter_explicit", "incomp_plain_nodealias"]
-CASES_INCOMPRESSIBLE_2D = ["i2d_hall_aeb_mask", "i2d_square_explicit_limit"]
+CASES_INCOMPRESSIBLE_2D = ["i2d_hall_aeb_mask", "i2d_square_explicit_limit", "i2d_corotating"]
 CASES_2D = ["c2d_hall_aeb_mask", "c2d_zradial_square_explicit", "c2d_external_force_filter"]
 
 
@@ -451,16 +451,14 @@ def test_library_40_steps_on_the_emulator_against_the_executed_reference_source(
 
 
 def test_2d_corotation_where_the_reference_has_none(emu):
-    """if_corotating in the 2D tree runs (fixture c2d_corotating_oracle_only above; the name dates from the round in which only
-    the oracle had it); what stays refused: together with if_z_radial (the reference stops, 2D/mhd.f90:62-67) and in the
-    incompressible 2D tree."""
+    """if_corotating runs in both 2D trees (fixtures c2d_corotating_oracle_only — the name dates from the round in which only the
+    oracle had it — and i2d_corotating above); what stays refused is the combination with if_z_radial, at which the reference
+    stops too (2D/mhd.f90:62-67)."""
     from laps_b200 import Solver, capi
     g, p = load_case("c2d_corotating_oracle_only")
     kw = pc.solver_kwargs(p)
     with pytest.raises(capi.LapsError, match="exclude each other"):
         Solver(emu, **dict(kw, if_z_radial=1))
-    with pytest.raises(capi.LapsError, match="incompressible 2D"):
-        Solver(emu, **dict(kw, incompressible=1, rho0=1.0))
 
 
 # ------------------------------------------------------------------------------------------------------------------
