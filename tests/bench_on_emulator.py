@@ -35,6 +35,10 @@ def main():
     torch.cuda.ExternalStream = lambda ptr, device=None: None
     torch.cuda.Event = _Event
     torch.Tensor.pin_memory = lambda self: self
+    import contextlib
+    torch.cuda.stream = lambda s: contextlib.nullcontext()
+    _empty = torch.empty
+    torch.empty = lambda *a, **k: _empty(*a, **{kk: v for kk, v in k.items() if kk != 'device'})
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:      # multi-rank: gloo in place of NCCL, host tensors in place of device ones
         import torch.distributed as dist
         _init = dist.init_process_group
