@@ -241,6 +241,8 @@ def pin_to_gpu_numa(index):
 def cpu_sample_size(n):
     """The workload's own grid when the host has the memory for the port's arrays (34 real + 46 spectral fields +
     k_square, the reference's own layout: 81.5 x 8 n^3 bytes), else 256^3."""
+    if n & (n - 1):      # the port's 1-D transforms are radix-2/4 only: an odd-factor grid (--n 384) is sampled on the power of two below
+        n = 1 << (n.bit_length() - 1)
     need = 81.5 * 8 * float(n) ** 3 * 1.25 + 8e9
     try:
         import psutil

@@ -1,5 +1,7 @@
 // In-shared-memory FP64 complex FFT building blocks for one "line" of N = 2^L points (8 <= N <= 4096; N = 8 is a
-// single register-resident radix-8 stage: one thread per line, no exchange).
+// single register-resident radix-8 stage: one thread per line, no exchange), and of N = P * 2^L points with a small odd
+// factor P (3, 5, ...: the second Fft template at the end of the file), which runs P power-of-two transforms side by
+// side and joins them with one more exchange.
 //
 // Replaces the per-line FFTW executions of the reference (fftw.f90:61,97,159,176,198,215 and
 // mhdrhs.f90:146,162,357): N/8 threads cooperate on a line, every thread holds 8 points in
@@ -17,13 +19,19 @@
 namespace laps {
 
 constexpr int ilog2c(int n) { return n <= 1 ? 0 : 1 + ilog2c(n >> 1); }
+constexpr int odd_part(int n) { return (n & 1) ? n : odd_part(n >> 1); }
 
 template <int N>
 struct Geom {
-  static_assert(N >= 8 && N <= 4096 && (N & (N - 1)) == 0, "line length must be a power of two in [8,4096]");
-  static constexpr int LOG2 = ilog2c(N);
-  static constexpr int NSTAGE = (LOG2 + 2) / 3;
-  static constexpr int RLAST = 1 << (LOG2 - 3 * (NSTAGE - 1));
+  static constexpr int P = odd_part(N);   // 1: a power of two
+  static constexpr int M = N / P;         // the power-of-two part
+  static constexpr bool POW2 = P == 1;
+  static_assert(N >= 8 && N <= 4096 && (POW2 || (M >= 16 && P <= 15)), "line length must be 2^L in [8,4096] or P * 2^L with P odd <= 15, 2^L >= 16");
+  // stage structure of the power-of-two transform (the members up to v() are meaningless when P > 1: RLAST = 0 there,
+  // so that the shortcuts the kernels take for RLAST == 8 stay switched off)
+  static constexpr int LOG2 = ilog2c(M);
+  static constexpr int NSTAGE = POW2 ? (LOG2 + 2) / 3 : 0;
+  static constexpr int RLAST = POW2 ? 1 << (LOG2 - 3 * (NSTAGE - 1)) : 0;
   static constexpr int NT = N / 8;  // threads per line
   LAPS_HD static constexpr int w(int s) { return s < NSTAGE - 1 ? (N >> (3 * (s + 1))) : 1; }
   LAPS_HD static constexpr int v(int s) { return 1 << (3 * s); }
@@ -128,8 +136,11 @@ LAPS_D void group_barrier(int bar) {
 
 // ------------------------------------------------------------------ staged FFT of one line
 // `tw` points to the forward table tw[m] = exp(-2 pi i m / N), m < N (global memory, L1 resident).
+template <int N, int DIR, int P = Geom<N>::P>
+struct Fft;
+
 template <int N, int DIR>
-struct Fft {
+struct Fft<N, DIR, 1> {
   typedef Geom<N> G;
 
   LAPS_D static cplx twid(const cplx* __restrict__ tw, int m) {
@@ -200,6 +211,7 @@ struct Fft {
   // padded position of element u + e * NT (the stage-0 input pattern; for RLAST == 8 also the output pattern kout):
   // pad(u) + a constant, see Geom::pad
   LAPS_D static int pad_in(int pu /* = G::pad(u) */, int e) { return pu + G::pad(e * G::NT); }
+  LAPS_D static int in_pos(int /*u*/, int pu, int e) { return pad_in(pu, e); }
 
   // Output index k held in register slot e of thread u after the last stage.
   LAPS_D static int kout(int u, int e) {
@@ -256,6 +268,86 @@ struct Fft {
     if constexpr (G::NSTAGE >= 3) { middle_w<1>(u, line, w1); __syncthreads(); }
     if constexpr (G::NSTAGE >= 4) { middle_w<2>(u, line, w2); __syncthreads(); }
     last(r, u, line);
+  }
+};
+
+// ------------------------------------------------------------------ N = P * M, P odd (3, 5, ...), M = 2^L >= 16
+// FFTW plans any length (fftw.f90:27-33); this covers the lengths with one small odd factor.  Decimation in time over
+// the P residue classes of the input index:
+//   X[k + j M] = sum_q  w_P^(j q) * ( W_N^(q k) * Y_q[k] ),     Y_q = FFT_M( x[P n + q], n < M ),   k < M, j < P.
+// Thread u of the N/8 threads holds x[u + e N/8] = x[P (v + e M/8) + q] with q = u % P, v = u / P: exactly the stage-0
+// input pattern of lane v of the M-point transform of class q, so the P transforms run side by side on the same
+// registers, each in its own part of the line (class q at pad(q M) — pad(q M + i) = pad(q M) + pad(i) for i < M, so the
+// parts are disjoint and a part is addressed by the M-point transform's own padded offsets).  One more exchange joins
+// them: every thread parks its twiddled Y_q[k], then forms output block j = q at the k's it holds (P-term sums; each
+// radix-P butterfly is evaluated by P threads, one output each, which keeps eight values per thread throughout).
+// Same interface as the power-of-two transform (first / finish / finish_g / kout / in_pos) with RLAST = 0; the
+// stage-level entry points (first_w, middle_w, finish_w) of the pipelined z pass do not exist here.
+// `tw`: W_N table (N entries) followed by the W_M table (M entries), see twiddle_table() in solver.cu.
+template <int N, int DIR, int P>
+struct Fft {
+  typedef Geom<N> G;
+  static constexpr int M = G::M;
+  typedef Geom<M> GM;
+  typedef Fft<M, DIR, 1> FM;
+  static_assert(GM::NSTAGE >= 2, "the sub-transforms go through the line");
+
+  LAPS_D static cplx twid(const cplx* __restrict__ tw, int m) {
+    cplx w = __ldg(tw + m);
+    if (DIR > 0) w.y = -w.y;
+    return w;
+  }
+  template <int NBAR>
+  LAPS_D static void sync(int bar) {
+    if constexpr (NBAR == 0) { (void)bar; __syncthreads(); }
+    else group_barrier<G::NT, NBAR>(bar);
+  }
+
+  LAPS_D static void first(cplx (&r)[8], int u, cplx* __restrict__ line, const cplx* __restrict__ tw) {
+    FM::first(r, u / P, line + G::pad((u % P) * M), tw + N);
+  }
+
+  LAPS_D static int in_pos(int u, int /*pu*/, int e) { return G::pad(u + e * G::NT); }
+
+  LAPS_D static int kout(int u, int e) { return FM::kout(u / P, e) + (u % P) * M; }
+
+  template <int NBAR>
+  LAPS_D static void finish_b(cplx (&r)[8], int u, cplx* __restrict__ line, const cplx* __restrict__ tw, int bar) {
+    const int q = u % P, v = u / P;
+    cplx* sub = line + G::pad(q * M);
+    const cplx* twm = tw + N;
+    sync<NBAR>(bar);
+    if constexpr (GM::NSTAGE >= 3) { FM::template middle<1>(v, sub, twm); sync<NBAR>(bar); }
+    if constexpr (GM::NSTAGE >= 4) { FM::template middle<2>(v, sub, twm); sync<NBAR>(bar); }
+    FM::last(r, v, sub);
+    sync<NBAR>(bar);   // every last-stage slot has been read: the parts can be refilled
+    LAPS_UNROLL
+    for (int e = 0; e < 8; ++e) {
+      const int k = FM::kout(v, e);
+      sub[GM::pad(k)] = q == 0 ? r[e] : cmul(r[e], twid(tw, q * k));
+    }
+    cplx wj[P];        // w_P^(q t), t < P: this thread forms block j = q
+    LAPS_UNROLL
+    for (int t = 1; t < P; ++t) wj[t] = twid(tw, ((q * t) % P) * M);
+    sync<NBAR>(bar);
+    LAPS_UNROLL
+    for (int e = 0; e < 8; ++e) {
+      const int pk = GM::pad(FM::kout(v, e));
+      cplx acc = line[pk];
+      LAPS_UNROLL
+      for (int t = 1; t < P; ++t) {
+        const cplx y = line[G::pad(t * M) + pk];
+        acc = cadd(acc, cmul(y, wj[t]));
+      }
+      r[e] = acc;
+    }
+  }
+  LAPS_D static void finish(cplx (&r)[8], int u, cplx* __restrict__ line, const cplx* __restrict__ tw) {
+    finish_b<0>(r, u, line, tw, 0);
+  }
+  template <int NBAR>
+  LAPS_D static void finish_g(cplx (&r)[8], int u, cplx* __restrict__ line, const cplx* __restrict__ tw, int bar) {
+    finish_b<NBAR>(r, u, line, tw, bar);
   }
 };
 

@@ -57,8 +57,9 @@ struct Tile {
   static constexpr size_t SMEM = (size_t)TL * PITCH * sizeof(cplx);
   // resident CTAs per SM to compile for: what shared memory allows, but never below 64 registers
   static constexpr int BY_SMEM = (int)((227 * 1024) / (SMEM + 1024));
-  static constexpr int BY_REGS = 65536 / (NTHREADS * 64);
-  static constexpr int BY_THREADS = 2048 / NTHREADS;
+  static constexpr int WTHREADS = (NTHREADS + 31) / 32 * 32;   // registers and thread slots are handed out per warp
+  static constexpr int BY_REGS = 65536 / (WTHREADS * 64);
+  static constexpr int BY_THREADS = 2048 / WTHREADS;
   static constexpr int M0 = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
   static constexpr int M1 = M0 < BY_THREADS ? M0 : BY_THREADS;
   static constexpr int MINB = M1 < 1 ? 1 : (M1 > 32 ? 32 : M1);   // what an SM can hold: ptxas ignores bounds beyond it
@@ -114,7 +115,7 @@ k_fwd_x(const double* __restrict__ in, size_t in_fstride, cplx* __restrict__ W1,
     if (it < nkx * TL) {   // nkx <= N/2+1: columns beyond it are removed by the dealiasing mask anyway
       const int lp = it % TL, k = it / TL;
       const cplx zk = sm[lp * T::PITCH + G::pad(k)];
-      const cplx zn = sm[lp * T::PITCH + G::pad((N - k) & (N - 1))];
+      const cplx zn = sm[lp * T::PITCH + G::pad(G::POW2 ? ((N - k) & (N - 1)) : (k ? N - k : 0))];
       const cplx a = mk((zk.x + zn.x) * hs, (zk.y - zn.y) * hs);
       const cplx b = mk((zk.y + zn.y) * hs, (zn.x - zk.x) * hs);
       st256(W1 + (((size_t)f * nxh + k) * nzl + zl0 + zl) * ny + y0 + 2 * lp, a, b);
@@ -318,8 +319,10 @@ k_inv_x(const cplx* __restrict__ V2, const LAPS_GRID_CONSTANT RealDst dst, int n
   {
     const int pu = G::pad(u);
     LAPS_UNROLL
-    for (int e = 0; e < 8; ++e) r[e] = line[F::pad_in(pu, e)];
+    for (int e = 0; e < 8; ++e) r[e] = line[F::in_pos(u, pu, e)];
   }
+  // (a power-of-two first stage writes the slots it has read; the composite one writes elsewhere in the line)
+  if constexpr (!G::POW2) group_barrier<G::NT, TL>(1 + l);
   F::first(r, u, line, tw);
   F::template finish_g<TL>(r, u, line, tw, 1 + l);   // a line's transform synchronises its own N/8 threads only
   double* oa = dst.ptr[g] + ((size_t)zl * ny + y0 + 2 * l) * N;

@@ -43,13 +43,18 @@ constexpr double kPi = 3.141592653589793;  // mhdinit.f90:7
 
 // ---- per-size tile shapes --------------------------------------------------------------------
 constexpr int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
-constexpr int cap_threads(int t, int nt) { return t * nt > 1024 ? 1024 / nt : t; }
-constexpr int tlx(int N) { return cap_threads(clampi(256 / (N / 8), 4, 8), N / 8); }   // complex lines per x-pass CTA
-constexpr int tly(int N) { return cap_threads(clampi(1024 / (N / 8), 4, 8), N / 8); }  // lines per y-pass CTA (8 up to 1024-point lines: 128-byte chunks on the strided side)
-constexpr int rcg(int N) { return clampi(64 / (N / 8), 1, 32); }                       // columns per CTA of the pipelined RHS z pass
-constexpr int cgz(int N) { return clampi(128 / (N / 8), 1, 32); }                      // columns per z-pass CTA
+constexpr int p2floor(int v) { return v < 2 ? 1 : 2 * p2floor(v / 2); }   // tiles hold a power-of-two number of lines (line lengths with an odd factor)
+constexpr int cap_threads(int t, int nt) { return t * nt > 1024 ? p2floor(1024 / nt) : t; }
+constexpr int tlx(int N) { return cap_threads(clampi(p2floor(256 / (N / 8)), 4, 8), N / 8); }   // complex lines per x-pass CTA
+constexpr int tly(int N) { return cap_threads(clampi(p2floor(1024 / (N / 8)), 4, 8), N / 8); }  // lines per y-pass CTA (8 up to 1024-point lines: 128-byte chunks on the strided side)
+constexpr int rcg(int N) { return clampi(p2floor(64 / (N / 8)), 1, 32); }                       // columns per CTA of the pipelined RHS z pass
+constexpr int cgz(int N) { return clampi(p2floor(128 / (N / 8)), 1, 32); }                      // columns per z-pass CTA
 
-#define LAPS_FOR_SIZES(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048)
+// Line lengths with compiled transforms: powers of two, and 3 * 2^k, 5 * 2^k (FFTW plans any length, fftw.f90:27-33;
+// these are the ones a 2/3-rule grid is usually given).  The odd-factor lengths run the composite transform of
+// fft_core.cuh in every pass and the unpipelined z pass (k_spec_z).
+#define LAPS_FOR_SIZES(X) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) \
+  X(48) X(96) X(192) X(384) X(768) X(1536) X(80) X(160) X(320) X(640) X(1280)
 
 bool size_supported(int n) {
   switch (n) {
@@ -215,16 +220,25 @@ std::vector<double> wave_numbers(int n, double L) {  // mhdinit.f90:79-110
   return k;
 }
 
+int pow2_part(int n) { int m = 1; while (n % (2 * m) == 0) m *= 2; return m; }
+// entries of the twiddle table of an n-point line: W_n, and for n = P * 2^L with P odd > 1 also W_(2^L) behind it
+// (the sub-transforms of the composite Fft, fft_core.cuh)
+size_t twiddle_len(int n) { const int m = pow2_part(n); return m == n ? (size_t)n : (size_t)n + m; }
+
 std::vector<cplx> twiddle_table(int n) {
-  std::vector<cplx> t(n);
+  std::vector<cplx> t(twiddle_len(n));
   const long double two_pi = 6.283185307179586476925286766559005768L;
-  for (int m = 0; m < n; ++m) {
-    long double a = -two_pi * (long double)m / (long double)n;
-    t[m] = mk((double)cosl(a), (double)sinl(a));
+  for (size_t off = 0, len = n; off < t.size(); off += len, len = pow2_part(n)) {
+    const int nn = (int)len;
+    cplx* tt = t.data() + off;
+    for (int m = 0; m < nn; ++m) {
+      long double a = -two_pi * (long double)m / (long double)nn;
+      tt[m] = mk((double)cosl(a), (double)sinl(a));
+    }
+    // exact values on the axes
+    tt[0] = mk(1.0, 0.0);
+    if (nn % 4 == 0) { tt[nn / 4] = mk(0.0, -1.0); tt[nn / 2] = mk(-1.0, 0.0); tt[3 * nn / 4] = mk(0.0, 1.0); }
   }
-  // exact values on the axes
-  t[0] = mk(1.0, 0.0);
-  if (n % 4 == 0) { t[n / 4] = mk(0.0, -1.0); t[n / 2] = mk(-1.0, 0.0); t[3 * n / 4] = mk(0.0, 1.0); }
   return t;
 }
 
@@ -446,7 +460,7 @@ int do_fwd_x(S* s, const double* in, size_t fstride, int nfields, cplx* W1, bool
 constexpr int kFuseGroups = 10;   // thread groups (fluxes in flight) per CTA of k_flux_fwd_x: 19 fluxes in two rounds
 template <int N>
 int do_flux_fwd_x(S* s, const FusedFluxParams& fp) {
-  if constexpr (N <= 512) {
+  if constexpr (N <= 512 && Geom<N>::POW2) {
     typedef FTile<N, kFuseGroups> T;
     constexpr int ctas = (227 * 1024) / (int)(T::SMEM + 1024) < 1 ? 1 : ((227 * 1024) / (int)(T::SMEM + 1024) > 2 ? 2 : (227 * 1024) / (int)(T::SMEM + 1024));
     LAPS_CK(s, prepare_kernel(k_flux_fwd_x<N, kFuseGroups>, T::SMEM, ctas));
@@ -455,7 +469,7 @@ int do_flux_fwd_x(S* s, const FusedFluxParams& fp) {
     LAPS_LAUNCH((k_flux_fwd_x<N, kFuseGroups>), grid, dim3(T::NTHREADS), T::SMEM, s->cs, fp);
     return check_launch(s, "k_flux_fwd_x");
   } else {
-    s->err = "k_flux_fwd_x: line too long for the shared-memory staging"; return 1;
+    s->err = "k_flux_fwd_x: power-of-two lines of up to 512 points only"; return 1;
   }
 }
 
@@ -485,10 +499,10 @@ int do_fwd_y_tl(S* s, const cplx* W1, int nfields, bool prune, int f0, int zbase
 
 template <int N>
 int do_fwd_y(S* s, const cplx* W1, int nfields, bool prune, int f0, int zbase, int zcount, bool staged) {
-  if constexpr (N >= 256 && N <= 1024 && tly(N) == 8) {   // tuning knob: half-height tiles (twice the CTAs per SM, 64-byte chunks)
+  if constexpr (Geom<N>::POW2 && N >= 256 && N <= 1024 && tly(N) == 8) {   // tuning knob: half-height tiles (twice the CTAs per SM, 64-byte chunks)
     if (s->tune_tly == 4) return do_fwd_y_tl<N, 4>(s, W1, nfields, prune, f0, zbase, zcount, staged);
   }
-  if constexpr (N >= 128 && N <= 512) {   // tuning knob: 16 planes per tile, 256-byte runs (measured at 8 GPUs: no gain over 128-byte runs)
+  if constexpr (Geom<N>::POW2 && N >= 128 && N <= 512) {   // tuning knob: 16 planes per tile, 256-byte runs (measured at 8 GPUs: no gain over 128-byte runs)
     if (s->tune_tly == 16) return do_fwd_y_tl<N, 16>(s, W1, nfields, prune, f0, zbase, zcount, staged);
   }
   return do_fwd_y_tl<N, tly(N)>(s, W1, nfields, prune, f0, zbase, zcount, staged);
@@ -509,7 +523,7 @@ int do_inv_y_tl(S* s, const cplx* V1, cplx* V2, int nfields, bool prune) {
 
 template <int N>
 int do_inv_y(S* s, const cplx* V1, cplx* V2, int nfields, bool prune) {
-  if constexpr (N >= 256 && N <= 1024 && tly(N) == 8) {
+  if constexpr (Geom<N>::POW2 && N >= 256 && N <= 1024 && tly(N) == 8) {
     // 1024-point lines: 8-line tiles are 1024-thread CTAs, one per SM.  The forward pass wants them (128-byte runs in the
     // peers' buffers: 662 against 427 GB/s of NVLink egress at 1024^3 on 8 GPUs), the inverse pass, whose strided side is
     // local, runs better with two 4-line CTAs per SM (0.63 against 0.50 of the HBM peak, profiles/r02_multi_gpu.md)
@@ -579,11 +593,14 @@ int do_rhs_z_cg(S* s, const ZParams& zp, int ntasks) {
 
 template <int N>
 int do_rhs_z(S* s, const ZParams& zp, int ntasks) {
+  if constexpr (!Geom<N>::POW2) return do_spec_z<N>(s, zp, ntasks, "spec_z");   // the pipelined kernel drives the power-of-two stages itself
+  else {
   if constexpr (N == 512) {  // tuning knob for the benchmark grid (columns per CTA)
     if (s->tune_rcg == 2) return do_rhs_z_cg<N, 2, 2>(s, zp, ntasks);
   }
   if (s->tune_rhs == 2) return do_rhs_z_cg<N, rcg(N), 1>(s, zp, ntasks);   // one landing line, more resident columns
   return do_rhs_z_cg<N, rcg(N), 2>(s, zp, ntasks);
+  }
 }
 
 template <int N>
@@ -609,6 +626,17 @@ int do_incomp_z(S* s, const ZParams& zp) {
     case 512: return fn<512>(__VA_ARGS__);                          \
     case 1024: return fn<1024>(__VA_ARGS__);                        \
     case 2048: return fn<2048>(__VA_ARGS__);                        \
+    case 48: return fn<48>(__VA_ARGS__);                        \
+    case 96: return fn<96>(__VA_ARGS__);                        \
+    case 192: return fn<192>(__VA_ARGS__);                      \
+    case 384: return fn<384>(__VA_ARGS__);                      \
+    case 768: return fn<768>(__VA_ARGS__);                      \
+    case 1536: return fn<1536>(__VA_ARGS__);                    \
+    case 80: return fn<80>(__VA_ARGS__);                        \
+    case 160: return fn<160>(__VA_ARGS__);                      \
+    case 320: return fn<320>(__VA_ARGS__);                      \
+    case 640: return fn<640>(__VA_ARGS__);                      \
+    case 1280: return fn<1280>(__VA_ARGS__);                    \
     default: s->err = "unsupported line length"; return 1;          \
   }
 
@@ -625,6 +653,17 @@ int do_incomp_z(S* s, const ZParams& zp) {
     case 512: return fn<512>(__VA_ARGS__);                          \
     case 1024: return fn<1024>(__VA_ARGS__);                        \
     case 2048: return fn<2048>(__VA_ARGS__);                        \
+    case 48: return fn<48>(__VA_ARGS__);                        \
+    case 96: return fn<96>(__VA_ARGS__);                        \
+    case 192: return fn<192>(__VA_ARGS__);                      \
+    case 384: return fn<384>(__VA_ARGS__);                      \
+    case 768: return fn<768>(__VA_ARGS__);                      \
+    case 1536: return fn<1536>(__VA_ARGS__);                    \
+    case 80: return fn<80>(__VA_ARGS__);                        \
+    case 160: return fn<160>(__VA_ARGS__);                      \
+    case 320: return fn<320>(__VA_ARGS__);                      \
+    case 640: return fn<640>(__VA_ARGS__);                      \
+    case 1280: return fn<1280>(__VA_ARGS__);                    \
     default: s->err = "unsupported line length"; return 1;          \
   }
 
@@ -1313,12 +1352,12 @@ int laps_create(const laps_params* params, laps_handle* out) {
     if (u.nz != 1) { g_create_error = "ndim = 2 needs nz = 1"; return 1; }
     if (u.nranks != 1) { g_create_error = "the 2D tree runs on one GPU (nranks = 1)"; return 1; }
     if (u.if_AEB && u.if_corotating && u.if_z_radial) { g_create_error = "if_z_radial and if_corotating exclude each other (2D/mhd.f90:62-67)"; return 1; }
-    if (!size_supported(u.nx) || !(size_supported(u.ny) || u.ny == 8)) { g_create_error = "nx must be a power of two in [16, 2048], ny in [8, 2048]"; return 1; }
+    if (!size_supported(u.nx) || !(size_supported(u.ny) || u.ny == 8)) { g_create_error = "nx, ny must be 2^k, 3 * 2^k or 5 * 2^k in [16, 2048] (ny = 8 too)"; return 1; }
     p.ny = 1; p.nz = u.ny; p.Ly = 1.0; p.Lz = u.Ly; p.afz = u.afy;
     if (u.dealias_option < 0 || u.dealias_option > 3) { g_create_error = "dealias_option must be 0..3 in the 2D tree"; return 1; }
   } else {
     if (!size_supported(p.nx) || !size_supported(p.ny) || !(size_supported(p.nz) || p.nz == 8)) {
-      g_create_error = "nx, ny must be powers of two in [16, 2048], nz in [8, 2048]"; return 1;
+      g_create_error = "nx, ny, nz must be 2^k, 3 * 2^k or 5 * 2^k in [16, 2048] (nz = 8 too)"; return 1;
     }
     if (p.dealias_option < 0 || p.dealias_option > 2) { g_create_error = "dealias_option must be 0, 1 or 2"; return 1; }
     p.if_z_radial = 0; p.if_limit_dt_increase = 0;
@@ -1468,7 +1507,8 @@ int laps_create(const laps_params* params, laps_handle* out) {
   alloc((void**)&s->uA, 8 * s->csz * sizeof(cplx));
   alloc((void**)&s->uB, 8 * s->csz * sizeof(cplx));
   alloc((void**)&s->rk, 8 * s->csz * sizeof(cplx));
-  alloc((void**)&s->tw_x, s->nx * sizeof(cplx)); alloc((void**)&s->tw_y, s->ny * sizeof(cplx)); alloc((void**)&s->tw_z, s->nz * sizeof(cplx));
+  alloc((void**)&s->tw_x, twiddle_len(s->nx) * sizeof(cplx)); alloc((void**)&s->tw_y, twiddle_len(s->ny) * sizeof(cplx));
+  alloc((void**)&s->tw_z, twiddle_len(s->nz) * sizeof(cplx));
   alloc((void**)&s->d_tab, ((size_t)3 * (s->nxh + s->ny + s->nz) + s->nz) * sizeof(double));
   alloc((void**)&s->d_partial, (size_t)32 * s->nblk * sizeof(double));
   alloc((void**)&s->d_scal, 64 * sizeof(double));
@@ -1490,7 +1530,7 @@ int laps_create(const laps_params* params, laps_handle* out) {
     const int n = a == 0 ? s->nx : (a == 1 ? s->ny : s->nz);
     cplx* d = a == 0 ? s->tw_x : (a == 1 ? s->tw_y : s->tw_z);
     std::vector<cplx> t = twiddle_table(n);
-    if (cudaMemcpy(d, t.data(), n * sizeof(cplx), cudaMemcpyHostToDevice) != cudaSuccess) return fail("twiddle upload failed");
+    if (cudaMemcpy(d, t.data(), t.size() * sizeof(cplx), cudaMemcpyHostToDevice) != cudaSuccess) return fail("twiddle upload failed");
   }
   if (upload_tables(s)) return fail(s->err);
   {  // columns the dealiasing mask removes entirely (see laps_solver::nkx)

@@ -24,8 +24,9 @@ struct ITile {
   static constexpr int COLSTRIDE = PITCH + 3 * N;
   static constexpr size_t SMEM = (size_t)CG * COLSTRIDE * sizeof(cplx);
   static constexpr int BY_SMEM = (int)((227 * 1024) / (SMEM + 1024));
-  static constexpr int BY_REGS = 65536 / (NTHREADS * 96);
-  static constexpr int BY_THREADS = 2048 / NTHREADS;
+  static constexpr int WTHREADS = (NTHREADS + 31) / 32 * 32;   // registers and thread slots are handed out per warp
+  static constexpr int BY_REGS = 65536 / (WTHREADS * 96);
+  static constexpr int BY_THREADS = 2048 / WTHREADS;
   static constexpr int M0 = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
   static constexpr int M1 = M0 < BY_THREADS ? M0 : BY_THREADS;
   static constexpr int MINB = M1 < 1 ? 1 : (M1 > 32 ? 32 : M1);
@@ -167,7 +168,7 @@ k_incomp_z(const ZParams P) {
       for (int e = 0; e < 8; ++e) W[G::pad(FF::kout(u, e))] = r[e];
       __syncthreads();
       LAPS_UNROLL
-      for (int e = 0; e < 8; ++e) r[e] = W[G::pad(u) + G::pad(e * G::NT)];
+      for (int e = 0; e < 8; ++e) r[e] = W[FI::in_pos(u, G::pad(u), e)];
       __syncthreads();
     }
     FI::first(r, u, W, P.tw);

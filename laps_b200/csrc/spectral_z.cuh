@@ -116,8 +116,9 @@ struct ZTile {
   static constexpr size_t SMEM = (size_t)CG * COLSTRIDE * sizeof(cplx);
   // resident CTAs per SM to compile for: what shared memory allows, but never below 80 registers
   static constexpr int BY_SMEM = (int)((227 * 1024) / (SMEM + 1024));
-  static constexpr int BY_REGS = 65536 / (NTHREADS * 80);
-  static constexpr int BY_THREADS = 2048 / NTHREADS;
+  static constexpr int WTHREADS = (NTHREADS + 31) / 32 * 32;   // registers and thread slots are handed out per warp
+  static constexpr int BY_REGS = 65536 / (WTHREADS * 80);
+  static constexpr int BY_THREADS = 2048 / WTHREADS;
   static constexpr int M0 = BY_SMEM < BY_REGS ? BY_SMEM : BY_REGS;
   static constexpr int M1 = M0 < BY_THREADS ? M0 : BY_THREADS;
   static constexpr int MINB = M1 < 1 ? 1 : (M1 > 32 ? 32 : M1);
@@ -361,7 +362,7 @@ LAPS_D void spec_z_group(const ZParams& P, const ZTask& K, const int group, cplx
       for (int e = 0; e < 8; ++e) lineG[G::pad(FF::kout(u, e))] = r[e];
       __syncthreads();
       LAPS_UNROLL
-      for (int e = 0; e < 8; ++e) r[e] = lineG[G::pad(u) + G::pad(e * G::NT)];
+      for (int e = 0; e < 8; ++e) r[e] = lineG[FI::in_pos(u, G::pad(u), e)];
       __syncthreads();
     }
   } else if (K.kind == kZInverseOnly) {

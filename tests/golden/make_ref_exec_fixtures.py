@@ -36,6 +36,10 @@ CASES = {
     # plain MHD: no Hall term, no expanding box, no dealiasing (the library then does the reference's 19 transforms)
     "plain_nodealias": dict(nx=16, ny=16, nz=16, if_hall=False, if_aeb=False, if_corotating=False, dealias_option=0,
                             if_resis=True, if_resis_exp=False, if_visc=True, if_visc_exp=False, if_conserve_background=False),
+    # a line length with an odd factor (FFTW plans any length, fftw.f90:27-33): n/2+1 wave numbers, the 1/3 mask and the
+    # library's composite transforms (fft_core.cuh) on the x axis
+    "lines48_hall_aeb_corot_mask": dict(nx=48, ny=16, nz=16, if_hall=True, if_aeb=True, if_corotating=True, dealias_option=1,
+                                        if_resis=True, if_resis_exp=False, if_visc=True, if_visc_exp=False, if_conserve_background=False),
 }
 # src_incompressible: pressure projection, J and grad u, update_rho_p
 CASES_INCOMPRESSIBLE = {
@@ -46,6 +50,9 @@ CASES_INCOMPRESSIBLE = {
     # no dealiasing: the spectrum is re-derived from the real fields at the start of every stage (mhd.f90:325), which matters here
     "incomp_plain_nodealias": dict(nx=16, ny=16, nz=16, if_hall=False, if_aeb=False, if_corotating=False, dealias_option=0,
                                    if_resis=True, if_resis_exp=False, if_visc=True, if_visc_exp=False, if_conserve_background=False),
+    # 48-point lines on the y axis (3 * 16)
+    "incomp_lines48_hall_aeb_mask": dict(nx=16, ny=48, nz=16, if_hall=True, if_aeb=True, if_corotating=False, dealias_option=1,
+                                         if_resis=True, if_resis_exp=False, if_visc=True, if_visc_exp=False, if_conserve_background=False),
 }
 
 
@@ -230,6 +237,11 @@ CASES_2D = {
     "c2d_corotating_oracle_only": dict(nx=16, ny=16, nz=1, if_hall=True, if_aeb=True, if_corotating=True, dealias_option=1,
                                        if_resis=True, if_resis_exp=True, if_visc=True, if_visc_exp=False, if_conserve_background=False,
                                        if_z_radial=False, if_limit_dt_increase=False, if_external_force=False),
+    # 80-point x lines (5 * 16) and 48-point y lines (3 * 16)
+    "c2d_lines80x48_hall_aeb_filter": dict(nx=80, ny=48, nz=1, if_hall=True, if_aeb=True, if_corotating=False, dealias_option=2,
+                                           if_resis=True, if_resis_exp=False, if_visc=True, if_visc_exp=False,
+                                           if_conserve_background=False, if_z_radial=False, if_limit_dt_increase=False,
+                                           if_external_force=False),
 }
 
 
@@ -322,6 +334,11 @@ CASES_INCOMPRESSIBLE_2D = {
     "i2d_corotating": dict(nx=16, ny=32, nz=1, if_hall=True, if_aeb=True, if_corotating=True, dealias_option=1, if_resis=True,
                            if_resis_exp=True, if_visc=True, if_visc_exp=False, if_conserve_background=False,
                            if_z_radial=False, if_limit_dt_increase=False, if_external_force=False),
+    # 48-point x lines and 80-point y lines
+    "i2d_lines48x80_hall_aeb_mask": dict(nx=48, ny=80, nz=1, if_hall=True, if_aeb=True, if_corotating=False, dealias_option=1,
+                                         if_resis=True, if_resis_exp=False, if_visc=True, if_visc_exp=False,
+                                         if_conserve_background=False, if_z_radial=False, if_limit_dt_increase=False,
+                                         if_external_force=False),
 }
 
 
@@ -600,14 +617,20 @@ def run_case(name, c, nsteps=2, pieces=True):
 
 if __name__ == "__main__":
     os.makedirs(os.path.join(HERE, "ref_exec"), exist_ok=True)
-    make_parallel_fixtures()
-    run_initial_conditions()
-    run_case_100_steps()
+    only = set(sys.argv[1:])                                   # case names to (re)make; none: everything
+    if not only:
+        make_parallel_fixtures()
+        run_initial_conditions()
+        run_case_100_steps()
     for i, (name, c) in enumerate(CASES.items()):              # stage pieces on the smaller grid of each tree (oracle-only check)
-        run_case(name, c, pieces=(i == 1))
+        if not only or name in only:
+            run_case(name, c, pieces=(i == 1))
     for i, (name, c) in enumerate(CASES_INCOMPRESSIBLE.items()):
-        run_case_incompressible(name, c, pieces=(i == 1))
+        if not only or name in only:
+            run_case_incompressible(name, c, pieces=(i == 1))
     for i, (name, c) in enumerate(CASES_2D.items()):
-        run_case_2d(name, c, pieces=(i in (0, 2)))     # the external-force case keeps its pieces (fnl(7) += force)
+        if not only or name in only:
+            run_case_2d(name, c, pieces=(i in (0, 2)))     # the external-force case keeps its pieces (fnl(7) += force)
     for name, c in CASES_INCOMPRESSIBLE_2D.items():
-        run_case_incompressible_2d(name, c)
+        if not only or name in only:
+            run_case_incompressible_2d(name, c)

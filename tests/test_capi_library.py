@@ -61,9 +61,10 @@ def test_no_cpu_fallback_without_a_device(lib):
 
 def test_create_rejects_bad_arguments(lib):
     h = C.c_void_p()
-    p = capi.make_params(nx=48, ny=16, nz=16)
-    assert lib.laps_create(C.byref(p), C.byref(h)) != 0
-    assert b"powers of two" in lib.laps_last_error(None)
+    for n in (24, 36, 144, 100, 4096):     # below 48 with an odd factor, 9 * 2^k, 25 * 4, too long
+        p = capi.make_params(nx=n, ny=16, nz=16)
+        assert lib.laps_create(C.byref(p), C.byref(h)) != 0
+        assert b"3 * 2^k or 5 * 2^k" in lib.laps_last_error(None)
     p = capi.make_params(nx=16, ny=16, nz=16)
     p.abi_version = 99
     assert lib.laps_create(C.byref(p), C.byref(h)) != 0

@@ -206,6 +206,42 @@ def test_long_lines_through_every_pass(emu, shape):
     g.close()
 
 
+# Line lengths with an odd factor (3 * 2^k, 5 * 2^k; FFTW plans any length, fftw.f90:27-33): the composite transform of
+# fft_core.cuh (P power-of-two transforms side by side + one radix-P exchange) in every pass of every tree.
+@pytest.mark.parametrize("shape", [(48, 16, 16), (16, 80, 16), (16, 16, 96), (160, 48, 80)])
+def test_fft_odd_factor_lines(emu, shape):
+    pc.check_fft(*shape, lib_path=emu)
+
+
+@pytest.mark.parametrize("shape,kw", [((48, 16, 16), dict(hall=True, aeb=True, dealias=1)),
+                                      ((16, 48, 16), dict(hall=False, aeb=True, corot=True, dealias=2)),
+                                      ((16, 16, 80), dict(hall=True, aeb=False, explicit=True, conserve_bg=True))])
+def test_one_step_odd_factor_lines(emu, shape, kw):
+    p, prim = pc.make_case(*shape, **kw)
+    o, g = pc.run_both(p, prim, 1, lib_path=emu)
+    pc.check_state(o, g, 1e-11)
+    pc.check_diagnostics(o, g, 1e-9)
+    g.close()
+
+
+def test_odd_factor_lines_other_trees(emu):
+    for shape, kw in [((80, 48), dict(hall=True, aeb=True, corot=True, dealias=2, explicit=True, conserve_bg=True)),
+                      ((48, 80), dict(hall=True, aeb=True, z_radial=True, dealias=3))]:
+        p, prim = pc.make_case_2d(*shape, **kw)
+        o, g = pc.run_both(p, prim, 2, lib_path=emu, t0=2.0 if kw.get("corot") else 0.0)
+        pc.check_state(o, g, 1e-11)
+        pc.check_diagnostics(o, g, 1e-9)
+        g.close()
+    p, prim = pc.make_case_incompressible(16, 16, 48, hall=True, aeb=True, dealias=1)
+    o, g = pc.run_both(p, prim, 1, lib_path=emu)
+    pc.check_state(o, g, 1e-11)
+    g.close()
+    p, prim = pc.make_case_incompressible_2d(48, 80, hall=True, aeb=True, dealias=3)
+    o, g = pc.run_both(p, prim, 2, lib_path=emu)
+    pc.check_state(o, g, 1e-11)
+    g.close()
+
+
 def test_synthetic_slab_matches_the_mode_sum():
     p = lo.Params(nx=16, ny=32, nz=24, Lx=24.0, Ly=20.0, Lz=12.0)
     prim = lo.ic_uniform_background(p, bx0=1.0, by0=0.3, press0=1.0)

@@ -113,6 +113,15 @@ def test_five_ranks_uneven_round_robin_rows(emu):
     run_ranks(5, dict(lib=emu, shape=(32, 64, 32), case=dict(hall=True, aeb=True, dealias=1), steps=2, expect_stride=5), timeout=1200)
 
 
+@pytest.mark.parametrize("world,shape,env", [(4, (16, 48, 16), {}),                        # 48 round-robin ky rows, 12 per rank
+                                             (3, (16, 16, 48), dict(LAPS_TUNE_CYCLIC="0")),   # 48-point z lines stored across 3 slabs of 16 planes
+                                             (5, (16, 80, 48), {})])                          # 16 rows per rank; planes 9, 9, 9, 9, 12
+def test_odd_factor_lines_across_ranks(emu, world, shape, env):
+    """Line lengths with an odd factor (3 * 16, 5 * 16) on the exchanged axes: the composite transforms of fft_core.cuh store
+    through the same peer tables as the power-of-two ones."""
+    run_ranks(world, dict(lib=emu, shape=shape, case=dict(hall=True, aeb=True, dealias=1), steps=1, env=env), timeout=1200)
+
+
 def test_absent_rank_does_not_wedge_the_others(emu):
     # rank 1 never calls the collective: ranks 0 and 2 must come back with an error inside the time budget
     run_ranks(3, dict(lib=emu, shape=(16, 16, 16), case=dict(hall=True, aeb=True, dealias=1), absent_rank=1,

@@ -15,10 +15,11 @@ import parity_common as pc  # noqa: E402
 from oracle import laps_oracle as lo  # noqa: E402
 
 GOLD = os.path.join(HERE, "golden", "ref_exec")
-CASES = ["hall_aeb_mask", "corot_filter_explicit", "plain_nodealias"]
-CASES_INCOMPRESSIBLE = ["incomp_hall_aeb_mask", "incomp_corot_filter_explicit", "incomp_plain_nodealias"]
-CASES_INCOMPRESSIBLE_2D = ["i2d_hall_aeb_mask", "i2d_square_explicit_limit", "i2d_corotating"]
-CASES_2D = ["c2d_hall_aeb_mask", "c2d_zradial_square_explicit", "c2d_external_force_filter"]
+# the `lines48` / `lines80` cases have line lengths with an odd factor (3 * 16, 5 * 16): FFTW plans any length (fftw.f90:27-33)
+CASES = ["hall_aeb_mask", "corot_filter_explicit", "plain_nodealias", "lines48_hall_aeb_corot_mask"]
+CASES_INCOMPRESSIBLE = ["incomp_hall_aeb_mask", "incomp_corot_filter_explicit", "incomp_plain_nodealias", "incomp_lines48_hall_aeb_mask"]
+CASES_INCOMPRESSIBLE_2D = ["i2d_hall_aeb_mask", "i2d_square_explicit_limit", "i2d_corotating", "i2d_lines48x80_hall_aeb_mask"]
+CASES_2D = ["c2d_hall_aeb_mask", "c2d_zradial_square_explicit", "c2d_external_force_filter", "c2d_lines80x48_hall_aeb_filter"]
 
 
 def load_case(name):
