@@ -78,8 +78,9 @@ typedef struct laps_extents {
 } laps_extents;
 
 /* parallel_start + fftw_initialize + grid_initialize + arrays_initialize + AEB_initialize +
- * dealias_initialize (mhd.f90:58-99).  Grid sizes: powers of two in [16, 2048] per axis; nz (3D) / ny (2D trees)
- * may also be 8.  Anything else fails here with a message (the reference's FFTW plans take any length). */
+ * dealias_initialize (mhd.f90:58-99).  Grid sizes per axis: 2^k in [16, 2048], 3 * 2^k in [48, 1536], 5 * 2^k in
+ * [80, 1280]; nz (3D) / ny (2D trees) may also be 8.  Anything else fails here with a message (the reference's FFTW
+ * plans, fftw.f90:27-33, take any length). */
 int laps_create(const laps_params* params, laps_handle* out);
 /* parallel_end + fftw_finalize (mhd.f90:291-293). */
 int laps_destroy(laps_handle h);
