@@ -279,8 +279,9 @@ struct Fft<N, DIR, 1> {
 // input pattern of lane v of the M-point transform of class q, so the P transforms run side by side on the same
 // registers, each in its own part of the line (class q at pad(q M) — pad(q M + i) = pad(q M) + pad(i) for i < M, so the
 // parts are disjoint and a part is addressed by the M-point transform's own padded offsets).  One more exchange joins
-// them: every thread parks its twiddled Y_q[k], then forms output block j = q at the k's it holds (P-term sums; each
-// radix-P butterfly is evaluated by P threads, one output each, which keeps eight values per thread throughout).
+// them: every thread parks its twiddled Y_q[k], then forms output block j = q at the k's it holds (P-term sums, the
+// thread's own term from its register; each radix-P butterfly is evaluated by P threads, one output each, which keeps
+// eight values per thread throughout).
 // Same interface as the power-of-two transform (first / finish / finish_g / kout / in_pos) with RLAST = 0; the
 // stage-level entry points (first_w, middle_w, finish_w) of the pipelined z pass do not exist here.
 // `tw`: W_N table (N entries) followed by the W_M table (M entries), see twiddle_table() in solver.cu.
@@ -324,19 +325,22 @@ struct Fft {
     LAPS_UNROLL
     for (int e = 0; e < 8; ++e) {
       const int k = FM::kout(v, e);
-      sub[GM::pad(k)] = q == 0 ? r[e] : cmul(r[e], twid(tw, q * k));
+      if (q != 0) r[e] = cmul(r[e], twid(tw, q * k));
+      sub[GM::pad(k)] = r[e];
     }
     cplx wj[P];        // w_P^(q t), t < P: this thread forms block j = q
     LAPS_UNROLL
     for (int t = 1; t < P; ++t) wj[t] = twid(tw, ((q * t) % P) * M);
     sync<NBAR>(bar);
     LAPS_UNROLL
-    for (int e = 0; e < 8; ++e) {
+    for (int e = 0; e < 8; ++e) {   // the term of this thread's own class stays in its register: P - 1 reads per output
       const int pk = GM::pad(FM::kout(v, e));
-      cplx acc = line[pk];
+      cplx acc = r[e];
+      if (q != 0) acc = line[pk];
       LAPS_UNROLL
       for (int t = 1; t < P; ++t) {
-        const cplx y = line[G::pad(t * M) + pk];
+        cplx y = r[e];
+        if (t != q) y = line[G::pad(t * M) + pk];
         acc = cadd(acc, cmul(y, wj[t]));
       }
       r[e] = acc;

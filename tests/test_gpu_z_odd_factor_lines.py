@@ -78,6 +78,17 @@ def test_mask_pruning_is_bit_exact():
     pc.check_pruning_is_exact((48, 96, 80), 2, hall=True, aeb=True, dealias=1)
 
 
+def test_odd_factor_lines_across_ranks_sharing_the_gpu():
+    """48- and 80-point lines on the exchanged axes with 4, 3 and 5 ranks as threads of one process (laps_connect_local; the ranks
+    share the device, tests/test_gpu_multirank.py): round-robin ky rows, the reference's slabs, remainder planes on the last rank."""
+    from test_gpu_multirank import _local
+    hall = dict(hall=True, aeb=True, dealias=1)
+    _local([dict(world=4, shape=(48, 48, 48), case=hall, steps=2, expect_stride=4),
+            dict(world=3, shape=(32, 48, 48), case=hall, steps=2, env=dict(LAPS_TUNE_CYCLIC="0"), expect_stride=1),
+            dict(world=5, shape=(32, 80, 48), case=hall, steps=1, expect_stride=5),
+            dict(world=2, shape=(48, 80, 32), case=hall, steps=1, incompressible=True)])
+
+
 def test_unsupported_lengths_are_refused_with_a_message():
     from laps_b200 import LapsError, Solver
     for n in (24, 144, 100):

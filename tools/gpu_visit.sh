@@ -13,8 +13,8 @@ for stage in "$@"; do
     tests)        ( time timeout 1500 python -m pytest tests -m gpu -q --durations=10 --maxfail=8 ) > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log; tail -15 $OUT/pytest_gpu.log ;;
     tests_new)    ( time timeout 900 python -m pytest tests/test_gpu_driver.py tests/test_gpu_parity.py -m gpu -q -k "driver or async or rhs_kernel or cfl_screen or two_stream or 2d_tree_parity or 2d_library" ) > $OUT/pytest_new.log 2>&1; tail -5 $OUT/pytest_new.log ;;
     tests_multi)  ( time timeout 1200 python -m pytest tests/test_gpu_multirank.py -m gpu -q --durations=10 ) > $OUT/pytest_multirank_${NG}gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_multirank_${NG}gpu.log; tail -8 $OUT/pytest_multirank_${NG}gpu.log ;;
-    odd)          ( time timeout 100 python -m pytest tests/test_gpu_z_odd_factor_lines.py -m gpu -q --durations=8 --maxfail=20 ) > $OUT/pytest_odd.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_odd.log; tail -12 $OUT/pytest_odd.log
-                  timeout 50 python bench.py --n 384 --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench_384_1gpu.json 2> $OUT/bench_384_1gpu.err; cut -c 1-400 $OUT/bench_384_1gpu.json; tail -c 300 $OUT/bench_384_1gpu.err ;;
+    odd)          ( time timeout ${ODD_T:-100} python -m pytest tests/test_gpu_z_odd_factor_lines.py -m gpu -q --durations=8 --maxfail=20 ) > $OUT/pytest_odd.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_odd.log; tail -12 $OUT/pytest_odd.log
+                  timeout ${ODD_B:-50} python bench.py --n 384 --steps 5 --warmup 3 --no-cpu-baseline > $OUT/bench_384_1gpu.json 2> $OUT/bench_384_1gpu.err; cut -c 1-400 $OUT/bench_384_1gpu.json; tail -c 300 $OUT/bench_384_1gpu.err ;;
     bench)        timeout 900 python bench.py --steps 10 --warmup 3 > $OUT/bench_512_1gpu.json 2> $OUT/bench_512_1gpu.err; tail -c 600 $OUT/bench_512_1gpu.err ;;
     bench_ref)    timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_reference.json 2> $OUT/bench_reference.err; cat $OUT/bench_reference.json ;;
     ab)           timeout 900 python tools/ab_tune.py > $OUT/ab_tune.jsonl 2> $OUT/ab_tune.err; cut -c 1-260 $OUT/ab_tune.jsonl; tail -3 $OUT/ab_tune.err ;;
