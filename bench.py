@@ -363,7 +363,7 @@ def parity_gate(R):
     decompose_1d slabs and the round-robin rows (the default from 4 ranks on)."""
     from laps_b200 import Solver
     from oracle import laps_oracle as lo
-    n = 64
+    n = int(os.environ.get("LAPS_BENCH_PARITY_N", "64"))   # tests/bench_on_emulator.py runs the gate at 16^3 (the kernel emulator is slow)
     kw = workload_params(n)
     p = lo.Params(**{k: (bool(v) if k.startswith("if_") else v) for k, v in kw.items()})
     prim = lo.ic_uniform_background(p, bx0=1.0, press0=1.0)
@@ -411,7 +411,7 @@ def parity_gate(R):
         R.barrier()
         g.close()
         R.barrier()
-    return {"ranks": R.world, "case": "64^3 Hall-MHD + expanding box, 2 steps, vs oracle/laps_oracle.py State", "tol": PARITY_TOL,
+    return {"ranks": R.world, "case": f"{n}^3 Hall-MHD + expanding box, 2 steps, vs oracle/laps_oracle.py State", "tol": PARITY_TOL,
             "fields": "uu(1:8) of every rank's z slab and uu_fourier(1:8) of its ky rows, relative L2", "cases": cases, "ok": bool(ok)}
 
 

@@ -26,6 +26,7 @@ class _Event:
 
 def main():
     emu, n = sys.argv[1], int(sys.argv[2])
+    os.environ.setdefault("LAPS_BENCH_PARITY_N", "16")   # the gate's logic, not its size, is what this helper exercises
     from laps_b200 import capi
     capi.DEFAULT_LIB = emu
     _load = capi.load
