@@ -135,6 +135,76 @@ def fft_model(x, sign=-1):
     return out
 
 
+# ---- line lengths with an odd factor: N = P * M, M a power of two (Fft<N, DIR, P> of fft_core.cuh) -----------------
+def odd_part(n):
+    while n % 2 == 0:
+        n //= 2
+    return n
+
+
+def fft_model_odd(x, sign=-1):
+    """The composite transform as the CUDA code does it: thread u of the N/8 threads is lane v = u // P of the M-point
+    transform of residue class q = u % P (its registers x[u + e N/8] ARE that lane's stage-0 inputs), the P transforms
+    run side by side, then one exchange: park W_N^(q k) Y_q[k] in part q of the line, form block j = q as P-term sums."""
+    N = len(x)
+    P = odd_part(N)
+    M = N // P
+    g, gm = None, Geom(M)
+    nt = N // 8
+    twN = np.exp(sign * 2j * np.pi * np.arange(N) / N)
+    # the registers of thread u on entry, and the claim that they are lane v's inputs of class q
+    for u in range(nt):
+        q, v = u % P, u // P
+        pos, _ = gm.stage_positions(0, v)
+        assert [u + e * nt for e in range(8)] == [P * p_ + q for p_ in pos]
+    Y = [fft_model(x[q::P], sign) for q in range(P)]           # the M-point transforms (model above)
+    part = lambda q: Geom.pad(q * M)                             # noqa: E731  part q of the padded line
+    for q in range(P):                                           # pad(q M + i) = pad(q M) + pad(i): the parts are disjoint
+        assert all(Geom.pad(q * M + i) == part(q) + Geom.pad(i) for i in range(M))
+    sm = np.zeros(Geom.pad(N - 1) + 1, dtype=complex)
+    for u in range(nt):
+        q, v = u % P, u // P
+        for k in gm.last_stage_outputs(v):
+            sm[part(q) + Geom.pad(k)] = Y[q][k] * twN[(q * k) % N]
+    out = np.zeros(N, dtype=complex)
+    for u in range(nt):
+        q, v = u % P, u // P
+        wj = [twN[((q * t) % P) * M] for t in range(P)]
+        for k in gm.last_stage_outputs(v):
+            out[k + q * M] = sum(wj[t] * sm[part(t) + Geom.pad(k)] for t in range(P))     # kout(u, e) = kout_M(v, e) + q M
+    return out
+
+
+def report_conflicts_odd(N, TL):
+    """Wavefronts per ideal wavefront of the two phases of the radix-P exchange (mapping A: a line's threads are consecutive)."""
+    P = odd_part(N)
+    M = N // P
+    gm = Geom(M)
+    nt = N // 8
+    LP = Geom.pad(N - 1) + 1
+    while LP % 8 != 1:
+        LP += 1
+    res = {}
+    for phase in ("park", "read"):
+        tot = cnt = 0
+        for w0 in range(0, TL * nt, 32):
+            for e in range(8):
+                for t in range(1 if phase == "park" else P):
+                    addrs = []
+                    for tid in range(w0, min(w0 + 32, TL * nt)):
+                        l, u = tid // nt, tid % nt
+                        q, v = u % P, u // P
+                        k = gm.last_stage_outputs(v)[e]
+                        if phase == "read" and t == q:
+                            continue                                # the thread's own term stays in its register
+                        addrs.append(l * LP + Geom.pad((q if phase == "park" else t) * M) + Geom.pad(k))
+                    if addrs:
+                        tot += conflicts_16B(addrs)
+                        cnt += (len(addrs) + 7) // 8
+        res[phase] = tot / cnt
+    return res
+
+
 # ---- bank conflict counting -------------------------------------------------------
 def conflicts_16B(addrs_elems):
     """addrs_elems: per-lane element addresses (16-byte elements) of one warp-wide LDS/STS.128.
@@ -193,3 +263,9 @@ if __name__ == "__main__":
     for N, TL in ((64, 32), (256, 8), (512, 4), (512, 8), (1024, 4), (2048, 2)):
         res = report_conflicts(N, TL)
         print(f"N={N} TL={TL}: " + "  ".join(f"s{s}{m}:{a:.2f}/{w:.1f}" for (s, m), (a, w) in sorted(res.items())))
+    for N in (48, 80, 96, 160, 192, 320, 384, 640, 768, 1280, 1536):
+        x = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+        for sign in (-1, 1):
+            ref = np.fft.fft(x) if sign < 0 else np.fft.ifft(x) * N
+            assert np.abs(fft_model_odd(x, sign) - ref).max() / np.abs(ref).max() < 1e-12, (N, sign)
+        print(f"N={N} = {odd_part(N)} x {N // odd_part(N)}: OK; exchange wavefronts / ideal (4 lines per CTA): {report_conflicts_odd(N, 4)}")
