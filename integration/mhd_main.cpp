@@ -1,6 +1,8 @@
 // Compiled stand-in for `program mhd` (src_compressible/mhd.f90:43-293) over the C ABI of include/laps_b200.h:
 // what the Fortran driver does around the hot path once its FFTW / MPI-transpose calls are replaced by the library
-// (INTEGRATION.md), written in C++ because this image has no Fortran compiler.  One rank, 3D compressible tree:
+// (INTEGRATION.md), written in C++ because this image has no Fortran compiler.  One rank; the four source trees share the
+// namelist syntax and are chosen with --tree compressible | compressible2d | incompressible | incompressible2d (the 2D trees:
+// nz = 1, vardt every 20 steps, checkNan every 200, two-grid grid.dat, 2D/mhd.f90:22-25,237-252, 2D/mhdoutput.f90:45-63):
 //   namelists (mhd.f90:30-53)  ->  laps_create            initial data (ifield = 3, ipert = 0 / 1; or a restart file)
 //   Principal loop (mhd.f90:169-287): output at dtout / dtrms cadence, evolve, time += dt, evolve_radius, vardt
 //   files in the reference's formats: grid.dat, parallel_info.dat (mhdoutput.f90:51-69), outNNN.dat (:72-131),
@@ -10,7 +12,7 @@
 // the same files.
 //
 //   g++ -std=c++17 -O2 -Iinclude integration/mhd_main.cpp -Llaps_b200/_lib -l:liblaps_b200.so -Wl,-rpath,$PWD/laps_b200/_lib -o mhd_main
-//   ./mhd_main --input mhd.input --outdir run1 [--max-steps N]
+//   ./mhd_main --input mhd.input --outdir run1 [--tree compressible2d] [--max-steps N]
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -151,17 +153,23 @@ struct Run {
 }  // namespace
 
 int main(int argc, char** argv) {
-  std::string input = "mhd.input", outdir = ".";
+  std::string input = "mhd.input", outdir = ".", tree = "compressible";
   long max_steps = -1;
   bool echo = true;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     if (a == "--input" && i + 1 < argc) input = argv[++i];
     else if (a == "--outdir" && i + 1 < argc) outdir = argv[++i];
+    else if (a == "--tree" && i + 1 < argc) tree = argv[++i];
     else if (a == "--max-steps" && i + 1 < argc) max_steps = std::atol(argv[++i]);
     else if (a == "--quiet") echo = false;
-    else { std::fprintf(stderr, "usage: mhd_main [--input mhd.input] [--outdir DIR] [--max-steps N] [--quiet]\n"); return 2; }
+    else { std::fprintf(stderr, "usage: mhd_main [--input mhd.input] [--outdir DIR] [--tree compressible|compressible2d|incompressible|incompressible2d] [--max-steps N] [--quiet]\n"); return 2; }
   }
+  if (tree != "compressible" && tree != "compressible2d" && tree != "incompressible" && tree != "incompressible2d") {
+    std::fprintf(stderr, "unknown --tree %s\n", tree.c_str()); return 2;
+  }
+  const bool two_d = tree.size() > 2 && tree.compare(tree.size() - 2, 2, "2d") == 0;
+  const bool incompressible = tree.compare(0, 6, "incomp") == 0;
   const Namelists nl = read_namelists(input);
   const Input in{nl};
   Run r;
@@ -184,6 +192,17 @@ int main(int argc, char** argv) {
   p.corotating_angle = in.real("AEB", "corotating_angle", 0.0);
   p.if_hall = in.logical("Hall", "if_Hall", false); p.ion_inertial_length = in.real("Hall", "ion_inertial_length", 0.0);
   p.rank = 0; p.nranks = 1; p.device = 0; p.ndim = 3; p.rho0 = 1.0;
+  if (two_d) {                                        // 2D/mhd.f90:23,43,44
+    p.ndim = 2; p.nz = 1;
+    p.if_limit_dt_increase = in.logical("numerical", "if_limit_dt_increase", false);
+    if (!incompressible) {
+      p.if_z_radial = in.logical("AEB", "if_z_radial", false);
+      p.if_external_force = in.logical("pert", "if_external_force", false);
+    }
+  }
+  if (incompressible) p.incompressible = 1;           // rho0 = 1 (src_incompressible/mhdinit.f90:15)
+  const long dstep_calcdt = two_d ? 20 : 1;           // 2D/mhd.f90:22,237-240
+  const long dstep_checknan = two_d ? 200 : 0;        // 2D/mhd.f90:25,242-252
   const double tmax = in.real("genr", "tmax", 1.0), dtout = in.real("genr", "dtout", 1.0), dtrms = in.real("genr", "dtrms", 1.0);
   r.output_primitive = in.logical("genr", "output_primitive", true);
   const bool if_restart = in.logical("genr", "if_restart", false);
@@ -241,18 +260,18 @@ int main(int argc, char** argv) {
 
   // ---- grid.dat, parallel_info.dat (mhdoutput.f90:51-69); rms.dat / EBM_info.dat are opened for append -----------------
   {
-    std::vector<float> g;
+    std::vector<float> g;                             // the 2D trees write nx, ny and two grids; npe, nvar (2D/mhdoutput.f90:45-63)
     const float dims[3] = {(float)p.nx, (float)p.ny, (float)p.nz};
     for (int i = 0; i < p.nx; ++i) g.push_back((float)(i * (p.Lx / p.nx)));
     for (int i = 0; i < p.ny; ++i) g.push_back((float)(i * (p.Ly / p.ny)));
-    for (int i = 0; i < p.nz; ++i) g.push_back((float)(i * (p.Lz / p.nz)));
+    if (!two_d) for (int i = 0; i < p.nz; ++i) g.push_back((float)(i * (p.Lz / p.nz)));
     std::FILE* f = std::fopen(r.path("grid.dat").c_str(), "wb");
     if (!f) { std::fprintf(stderr, "cannot write into %s\n", outdir.c_str()); return 2; }
-    put_record(f, dims, 12); put_record(f, g.data(), (int32_t)(4 * g.size()));
+    put_record(f, dims, two_d ? 8 : 12); put_record(f, g.data(), (int32_t)(4 * g.size()));
     std::fclose(f);
-    const float info[4] = {1.f, 1.f, 1.f, 8.f};       // npe, iproc, jproc, nvar
+    const float info3[4] = {1.f, 1.f, 1.f, 8.f}, info2[2] = {1.f, 8.f};   // npe, iproc, jproc, nvar / npe, nvar
     f = std::fopen(r.path("parallel_info.dat").c_str(), "wb");
-    put_record(f, info, 16);
+    if (two_d) put_record(f, info2, 8); else put_record(f, info3, 16);
     std::fclose(f);
     std::fclose(std::fopen(r.path("rms.dat").c_str(), "a"));
     std::fclose(std::fopen(r.path("EBM_info.dat").c_str(), "a"));
@@ -272,6 +291,7 @@ int main(int argc, char** argv) {
   r.output_uu(iout++);
   rms_block();
   double clocktime_output = delta_clocktime_output;
+  std::vector<double> force;
 
   // ---- Principal (mhd.f90:169-287) ---------------------------------------------------------------------------------------
   for (;;) {
@@ -283,6 +303,20 @@ int main(int argc, char** argv) {
       clocktime_output += delta_clocktime_output;
     }
     if (dt < 1e-8) { r.output_uu(iout); r.output_rms(); r.output_aeb(); break; }          // :205-228
+    if (p.if_external_force) {   // the user routine calc_external_force_real as shipped (2D/mhdrhs.f90:480-531): a Gaussian forcing of
+      // B_z centred at x = Lx/2 whose y centre moves at speed 0.3, with its two periodic images; called with the step's time
+      const double dBdt = 0.2, xc = 0.5 * p.Lx, w = 0.05 * p.Ly, yc = std::fmod(0.2 * p.Ly + 0.3 * r.time, p.Ly);
+      force.resize((size_t)p.nx * p.ny);
+      for (int iy = 0; iy < p.ny; ++iy)
+        for (int ix = 0; ix < p.nx; ++ix) {
+          const double x = ix * (p.Lx / p.nx), y = iy * (p.Ly / p.ny), fx = std::exp(-((x - xc) / w) * ((x - xc) / w));
+          double v = dBdt * fx * std::exp(-((y - yc) / w) * ((y - yc) / w));
+          v = v + dBdt * fx * std::exp(-((y - (yc + p.Ly)) / w) * ((y - (yc + p.Ly)) / w));
+          v = v + dBdt * fx * std::exp(-((y - (yc - p.Ly)) / w) * ((y - (yc - p.Ly)) / w));
+          force[(size_t)iy * p.nx + ix] = v;
+        }
+      r.ck(laps_set_external_force(r.h, force.data()), "laps_set_external_force");
+    }
     r.ck(laps_evolve(r.h), "laps_evolve");                                                // :245
     r.time = r.time + dt;                                                                 // :246
     ++r.istep;
@@ -296,7 +330,12 @@ int main(int argc, char** argv) {
       break;
     }
     if (r.time >= tlog) { r.write_log(dt); tlog += dtlog; }
-    r.ck(laps_vardt(r.h, &dt), "laps_vardt");                                             // :285
+    if (r.istep % dstep_calcdt == 0) r.ck(laps_vardt(r.h, &dt), "laps_vardt");            // :285 (2D trees: every 20 steps)
+    if (dstep_checknan && r.istep % dstep_checknan == 0) {                                // 2D/mhd.f90:242-252
+      int32_t is_nan = 0;
+      r.ck(laps_check_nan(r.h, &is_nan), "laps_check_nan");
+      if (is_nan) { if (echo) std::printf(" NaN encountered!!! Exit the program at t = %10.4f\n", r.time); break; }
+    }
   }
   r.write_log(dt);
   r.ck(laps_sync(r.h), "laps_sync");

@@ -28,24 +28,25 @@ def build_cpp_driver(lib, out):
     return out
 
 
-def compare_runs(exe, lib_for_python, tmp_path, text, steps):
+def compare_runs(exe, lib_for_python, tmp_path, text, steps, tree="compressible"):
     """Run both stand-ins on the same input in two directories and compare every file they leave."""
     a, b = tmp_path / "cpp", tmp_path / "py"
     for d in (a, b):
         d.mkdir()
         (d / "mhd.input").write_text(text)
-    out = subprocess.run([exe, "--input", str(a / "mhd.input"), "--outdir", str(a), "--max-steps", str(steps)],
+    out = subprocess.run([exe, "--input", str(a / "mhd.input"), "--outdir", str(a), "--max-steps", str(steps), "--tree", tree],
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:]
     assert "OUTPUT RMS at time:" in out.stdout
-    d = Driver(str(b / "mhd.input"), str(b), lib_path=lib_for_python)
+    d = Driver(str(b / "mhd.input"), str(b), lib_path=lib_for_python, tree=tree)
     assert d.run(max_steps=steps, echo=False) == steps
     d.close()
     names = sorted(os.listdir(b))
     assert sorted(os.listdir(a)) == names and "out000.dat" in names and "rms.dat" in names
     for n in ("grid.dat", "parallel_info.dat"):                       # byte for byte
         assert (a / n).read_bytes() == (b / n).read_bytes(), n
-    nx = ny = nz = 16
+    nx = ny = 16
+    nz = 1 if tree.endswith("2d") else 16
     for n in names:
         if n.startswith("out"):
             assert lapsio.read_out_header(str(a / n)) == lapsio.read_out_header(str(b / n))
@@ -80,6 +81,22 @@ def test_compiled_driver_writes_the_files_the_python_stand_in_writes(emu, tmp_pa
     assert out.returncode == 0, out.stdout[-3000:]
     assert os.path.exists(a / lapsio.out_name(n + 1))
     assert lapsio.read_out_header(str(a / lapsio.out_name(n + 1))) > lapsio.read_out_header(str(a / last))
+
+
+@pytest.mark.parametrize("tree", ["incompressible", "compressible2d", "incompressible2d"])
+def test_compiled_driver_runs_the_other_source_trees(emu, tmp_path, tree):
+    exe = build_cpp_driver(emu, os.path.join(HERE, "_build", "mhd_main_emu"))
+    compare_runs(exe, emu, tmp_path, ALFVEN, 2, tree=tree)
+
+
+def test_compiled_driver_external_force_of_the_2d_tree(emu, tmp_path):
+    """The user routine calc_external_force_real as shipped (2D/mhdrhs.f90:480-531), evaluated by the driver once per step."""
+    exe = build_cpp_driver(emu, os.path.join(HERE, "_build", "mhd_main_emu"))
+    text = ALFVEN.replace("ipert = 1", "ipert = 1\n   if_external_force = T")
+    a, _ = compare_runs(exe, emu, tmp_path, text, 2, tree="compressible2d")
+    x0 = lapsio.read_out_slab(str(a / "out000.dat"), 16, 16, 1)
+    x1 = lapsio.read_out_slab(str(a / sorted(f for f in os.listdir(a) if f.startswith("out"))[-1]), 16, 16, 1)
+    assert np.abs(x1[6] - x0[6]).max() > 1e-3          # B_z was driven
 
 
 def test_compiled_driver_reports_library_errors(emu, tmp_path):

@@ -11,8 +11,9 @@ import test_cpp_driver as cd
 pytestmark = pytest.mark.gpu
 
 
-def test_compiled_driver_on_the_gpu(tmp_path):
+@pytest.mark.parametrize("tree", ["compressible", "incompressible", "compressible2d", "incompressible2d"])
+def test_compiled_driver_on_the_gpu(tmp_path, tree):
     from laps_b200 import capi
     lib = capi.DEFAULT_LIB
     exe = cd.build_cpp_driver(lib, os.path.join(cd.HERE, "_build", "mhd_main"))
-    cd.compare_runs(exe, None, tmp_path, cd.ALFVEN, 3)
+    cd.compare_runs(exe, None, tmp_path, cd.ALFVEN, 3, tree=tree)
