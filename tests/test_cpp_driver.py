@@ -1,6 +1,6 @@
 """integration/mhd_main.cpp — the compiled stand-in for `program mhd` over the C ABI — against the Python stand-in
 (laps_b200/driver.py) on the same mhd.input: same files, same numbers.  Here the program is linked with the test-only kernel
-emulator; tests/test_gpu_z_cpp_driver.py links it with the real library on the GPU box."""
+emulator; tests/test_gpu_zz_cpp_driver.py links it with the real library on the GPU box."""
 import os
 import subprocess
 import sys
