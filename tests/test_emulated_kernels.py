@@ -242,6 +242,18 @@ def test_odd_factor_lines_other_trees(emu):
     g.close()
 
 
+def test_random_cases_fixed_seed(emu):
+    """Ten cases of tools/fuzz_parity.py (random tree, grid with power-of-two / odd-factor / 8-point lines, switches, 1 - 2
+    steps) with a fixed seed; the long sweeps are run by hand."""
+    import random
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import fuzz_parity as fz
+    rng = random.Random(2)
+    for _ in range(10):
+        case = fz.random_case(rng, max_points=32 * 32 * 32)
+        fz.run_case(case, emu)
+
+
 def test_synthetic_slab_matches_the_mode_sum():
     p = lo.Params(nx=16, ny=32, nz=24, Lx=24.0, Ly=20.0, Lz=12.0)
     prim = lo.ic_uniform_background(p, bx0=1.0, by0=0.3, press0=1.0)
