@@ -4,6 +4,7 @@ emulator (no GPU needed); with --gpu through the real library.  Development tool
 fixed-seed sweep of it.
 
     python tools/fuzz_parity.py --seed 7 --seconds 1500        # round 2: 471 cases, 0 failures
+    python tools/fuzz_parity.py --ranks --seed 3 --seconds 1200   # 2 - 8 ranks over gloo on the emulator: 108 cases, 0 failures
 """
 import argparse
 import os
@@ -53,11 +54,33 @@ def run_case(case, lib_path, tol=1e-11):
         g.close()
 
 
+def random_multirank_case(rng):
+    """World size 2 - 8, 3D trees, both ownership forms and the three stage schedules (tests/test_multirank_gloo.py runs the ranks)."""
+    while True:
+        world = rng.choice([2, 3, 4, 5, 8])
+        sizes = [16, 32, 48]
+        shape = (rng.choice(sizes), rng.choice([n for n in sizes + [80] if n >= world]), rng.choice([n for n in sizes if n >= world]))
+        if shape[0] * shape[1] * shape[2] <= 32 * 48 * 48:
+            break
+    case = dict(hall=rng.random() < 0.7, aeb=rng.random() < 0.7, dealias=rng.choice([0, 1, 2]))
+    if case["aeb"] and rng.random() < 0.4:
+        case["corot"] = True
+    env = {}
+    r = rng.random()
+    if r < 0.5:
+        env["LAPS_TUNE_CYCLIC"] = "0" if r < 0.25 else "1"
+    r = rng.random()
+    if r < 0.6:
+        env["LAPS_TUNE_OVERLAP"] = "1" if r < 0.3 else ("2" if r < 0.5 else "0")
+    return world, dict(shape=shape, case=case, steps=rng.choice([1, 2]), env=env, incompressible=rng.random() < 0.25)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--seconds", type=float, default=600.0)
     ap.add_argument("--gpu", action="store_true", help="the real library on cuda:0 instead of the kernel emulator")
+    ap.add_argument("--ranks", action="store_true", help="multi-rank cases (separate processes over gloo on the emulator)")
     a = ap.parse_args()
     lib = None
     if not a.gpu:
@@ -66,12 +89,18 @@ def main():
     rng = random.Random(a.seed)
     t0, n, bad = time.time(), 0, 0
     while time.time() - t0 < a.seconds:
-        case = random_case(rng)
         n += 1
         try:
-            run_case(case, lib)
+            if a.ranks:
+                import test_multirank_gloo as mg
+                world, cfg = random_multirank_case(rng)
+                case = (world, cfg)
+                mg.run_ranks(world, dict(cfg, lib=lib), timeout=900)
+            else:
+                case = random_case(rng)
+                run_case(case, lib)
             print(n, *case, "ok", flush=True)
-        except Exception as e:   # noqa: BLE001
+        except (Exception, AssertionError) as e:   # noqa: BLE001
             bad += 1
             print(n, *case, "FAIL", repr(e)[:300], flush=True)
             traceback.print_exc()
