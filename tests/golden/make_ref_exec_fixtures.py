@@ -535,7 +535,8 @@ def run_parallel_start(nx, ny, nz, npe):
 
 def make_parallel_fixtures():
     out = {}
-    for nx, ny, nz, npe in [(16, 16, 16, 2), (16, 16, 16, 3), (16, 32, 16, 8), (32, 64, 32, 5), (16, 16, 16, 4)]:
+    for nx, ny, nz, npe in [(16, 16, 16, 2), (16, 16, 16, 3), (16, 32, 16, 8), (32, 64, 32, 5), (16, 16, 16, 4),
+                            (16, 48, 80, 5), (48, 80, 48, 3)]:       # odd-factor lengths: 48 = 9+9+9+9+12, 80 = 16 x 5 / 26+26+28
         for r, d in enumerate(run_parallel_start(nx, ny, nz, npe)):
             for k, v in d.items():
                 out[f"{nx}x{ny}x{nz}_p{npe}_r{r}_{k}"] = np.asarray(v)

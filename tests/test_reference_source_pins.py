@@ -326,7 +326,8 @@ def _par(shape, npe):
             for r in range(npe)]
 
 
-@pytest.mark.parametrize("shape,npe", [((16, 16, 16), 2), ((16, 16, 16), 3), ((16, 16, 16), 4), ((16, 32, 16), 8), ((32, 64, 32), 5)])
+@pytest.mark.parametrize("shape,npe", [((16, 16, 16), 2), ((16, 16, 16), 3), ((16, 16, 16), 4), ((16, 32, 16), 8), ((32, 64, 32), 5),
+                                       ((16, 48, 80), 5), ((48, 80, 48), 3)])
 def test_transpose_index_maps_match_the_executed_parallel_start(emu, shape, npe):
     """transpose_yz sends, for every peer q, the MPI subarray yz_send(q) of w_yxz into the subarray yz_recv(me) of q's
     w_zxy, element by element in Fortran order (parallel.f90:185-210,273-297); transpose_zy is the reverse pairing
